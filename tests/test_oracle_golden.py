@@ -1,0 +1,135 @@
+"""
+Pin the oracle (oracle/oracle_np.py) against the golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  CPU only.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_golden, relerr, eof_tables, sl_tables, eof_geo_args, build_field, O
+
+TOL = 1e-12     # vectorisation changes FP64 summation order only
+
+EOF_CASES = ['eof_small_random_cmap1', 'eof_small_random_cmap0', 'eof_std_smooth']
+SL_CASES = ['sl_small_random_cmap1', 'sl_small_random_cmap0', 'sl_std_l4', 'sl_std_l6']
+FIELD_CASES = ['field_small', 'field_std']
+
+
+@pytest.mark.parametrize('name', EOF_CASES)
+def test_eof_accumulate(name):
+    d, meta = load_golden(name)
+    p, T, g = eof_tables(meta)
+    for k, v in meta['geo'].items():                 # geometry agrees with eof.set_table_params
+        assert abs(g[k] - v) <= 1e-15 * max(1.0, abs(v)), k
+    c, s = O.eof_accumulate(d['x'], d['y'], d['z'], d['m'], T['potC'], T['potS'], g['mmax'], g['norder'],
+                            *eof_geo_args(g), g['ascale'], g['hscale'], g['cmap'])
+    assert relerr(c, d['cos']) < TOL
+    assert relerr(s, d['sin']) < TOL
+    # the reference's own 3-process split differs from its 1-process run by summation order only
+    assert relerr(d['cos_multi3'], d['cos']) < TOL
+
+
+@pytest.mark.parametrize('name', EOF_CASES)
+def test_eof_force_particles(name):
+    d, meta = load_golden(name)
+    p, T, g = eof_tables(meta)
+    nf = meta['nforce']
+    args = (d['x'][:nf], d['y'][:nf], d['z'][:nf], d['cos'], d['sin'], T['potC'], T['rforceC'], T['zforceC'],
+            T['potS'], T['rforceS'], T['zforceS'], *eof_geo_args(g), g['mmax'], g['norder'],
+            g['ascale'], g['hscale'], g['cmap'])
+    full = O.eof_force_particles(*args)
+    win = O.eof_force_particles(*args, m1=1, m2=2)
+    for i in range(6):
+        assert relerr(full[i], d['full'][i]) < TOL, i
+        assert relerr(win[i], d['win12'][i]) < TOL, i
+
+
+@pytest.mark.parametrize('name', EOF_CASES)
+def test_eof_force_eval(name):
+    d, meta = load_golden(name)
+    p, T, g = eof_tables(meta)
+    variants = dict(full=(g['mmax'], g['norder'], False, False),
+                    trunc=(max(g['mmax'] - 1, 1), max(g['norder'] - 1, 1), False, False),
+                    noodd=(g['mmax'], g['norder'], True, False),
+                    perturb=(g['mmax'], g['norder'], False, True))
+    for vname, (M, N, no_odd, perturb) in variants.items():
+        out = O.eof_force_eval(d['pt_r'], d['pt_z'], d['pt_phi'], d['cos'], d['sin'], T['potC'], T['rforceC'],
+                               T['zforceC'], T['potS'], T['rforceS'], T['zforceS'], *eof_geo_args(g), M, N,
+                               g['ascale'], g['hscale'], g['cmap'], no_odd=no_odd, perturb=perturb)
+        ref = d['fe_' + vname]
+        for i in range(ref.shape[1]):
+            assert relerr(out[i], ref[:, i]) < TOL, (vname, i)
+
+
+@pytest.mark.parametrize('name', SL_CASES)
+def test_sl_tables_and_accumulate(name):
+    d, meta = load_golden(name)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    assert relerr(xi, d['xi']) < 1e-15
+    assert relerr(p0, d['p0']) < 1e-14
+    assert relerr(d0, d['d0']) < 1e-14
+    c = O.sl_accumulate(d['x'], d['y'], d['z'], d['m'], p['lmax'], p['nmax'], ev, ef, xi, p0, p['cmap'], p['scale'])
+    assert relerr(c, d['coef']) < TOL
+    c2 = O.sl_accumulate(d['x'], d['y'], d['z'], d['m'], p['lmax'], p['nmax'], ev, ef, xi, p0, p['cmap'], p['scale'],
+                         no_odd=True)
+    assert relerr(c2, d['coef_noodd']) < TOL
+
+
+@pytest.mark.parametrize('name', SL_CASES)
+def test_sl_eval_particles(name):
+    d, meta = load_golden(name)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    nf = meta['nforce']
+    a = (d['x'][1:nf + 1], d['y'][1:nf + 1], d['z'][1:nf + 1], d['coef'], p['lmax'], p['nmax'], ev, ef, xi, p0, d0,
+         p['cmap'], p['scale'])
+    for key, kw in (('allp', {}), ('allp_win12', dict(L1=1, L2=2)), ('allp_noodd', dict(NO_ODD=True))):
+        out = O.sl_all_eval_particles(*a, **kw)
+        ref = d[key]          # den0,den1,pot0,pot1,potr,pott,potp,rr
+        for i, j in enumerate((2, 3, 4, 5, 6, 7)):
+            assert relerr(out[i], ref[j]) < TOL, (key, j)
+
+
+@pytest.mark.parametrize('name', SL_CASES)
+def test_sl_force_eval(name):
+    d, meta = load_golden(name)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    L, N = p['lmax'], p['nmax']
+    a = (d['pt_r'], d['pt_costh'], d['pt_phi'], d['coef'], xi, p0, d0, p['cmap'], p['scale'])
+    for key, (l, n, no_odd) in dict(fe_full=(L, N, False), fe_trunc=(max(L - 1, 1), max(N - 2, 1), False),
+                                    fe_noodd=(L, N, True)).items():
+        out = O.sl_force_eval(*a, l, n, ev, ef, no_odd=no_odd)
+        for i in range(5):
+            assert relerr(out[i], d[key][:, i]) < TOL, (key, i)
+    out = O.sl_all_eval(*a, L, N, ev, ef)     # den0,den1,pot0,pot1,potr,pott,potp
+    for i, j in enumerate((2, 3, 4, 5, 6)):
+        assert relerr(out[i], d['ae_full'][:, j]) < TOL, j
+
+
+@pytest.mark.parametrize('name', FIELD_CASES)
+def test_fields_forces_cart(name):
+    d, meta = load_golden(name)
+    F = build_field(meta, d)
+    out = O.fields_forces_cart(F, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+    for i in range(8):
+        assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+    F.set_field_parameters(no_odd=True, halo_l=2, halo_n=3, disk_m=2, disk_n=3)
+    out = O.fields_forces_cart(F, d['px'], d['py'], d['pz'], rotpos=meta['rot_trunc'])
+    for i in range(8):
+        assert relerr(out[i], d['cart_trunc'][:, i]) < TOL, i
+
+
+@pytest.mark.parametrize('name', FIELD_CASES)
+def test_leapfrog(name):
+    d, meta = load_golden(name)
+    F = build_field(meta, d)
+    nint = meta['nint']
+    pos, vel, pot, traj = O.leapfrog(F, nint, meta['dt'], d['pos0'], d['vel0'], rotfreq=meta['rotfreq'],
+                                     keep_trajectory=True)
+    ref = d['orbits']        # (norb, 15, nint): X Y Z VX VY VZ P FX FY FZ TX TY VTX VTY T
+    for k in range(ref.shape[0]):
+        for j, key in enumerate(('X', 'Y', 'Z', 'VX', 'VY', 'VZ', 'P', 'FX', 'FY', 'FZ')):
+            assert relerr(traj[key][:, k], ref[k, j]) < 1e-9, (k, key)
+    F2 = build_field(meta, d)
+    pos, vel, pot, traj = O.leapfrog(F2, nint, meta['dt'], d['pos0'][:, :1], d['vel0'][:, :1], rotfreq=3.0,
+                                     no_odd=True, halo_l=2, halo_n=4, disk_m=4, disk_n=5, keep_trajectory=True)
+    for j, key in enumerate(('X', 'Y', 'Z', 'VX', 'VY', 'VZ', 'P')):
+        assert relerr(traj[key][:, 0], d['orbit_trunc'][j]) < 1e-9, key
