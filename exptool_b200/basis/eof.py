@@ -1,0 +1,376 @@
+"""
+eof.py -- drop-in for the hot-path entry points of exptool/basis/eof.py.
+
+Same names, argument order, return shapes and NumPy return types as the
+reference; the arithmetic runs in libbfe.so on the current CUDA device
+(exptool_b200.ops -> include/bfe.h).  Table readers and coefficient-file I/O
+are host-side NumPy, as in the reference.
+
+Not mirrored (outside the path): wake grids, phase /
+pattern-speed post-processing, variance (VAR) jackknife sums, plotting, density
+evaluation.
+"""
+import time
+from collections import OrderedDict
+
+import numpy as np
+
+from . import compatibility
+from ..io import particle
+from .. import ops
+
+r_to_xi = compatibility.r_to_xi
+z_to_y = compatibility.z_to_y
+
+
+# ---------------------------------------------------------------------------
+# cache-file readers (host) -- eof.py:98-313
+# ---------------------------------------------------------------------------
+def _read_header(f):
+    tmagic = np.fromfile(f, dtype='<i4', count=1)
+    hmagic = 0xc0a57a1
+    if tmagic.size and tmagic[0] == hmagic:
+        # new-style header (eof.py:126-157): magic, length, YAML block
+        import yaml
+        ssize = int(np.fromfile(f, dtype='<i4', count=1)[0])
+        data = yaml.safe_load(f.read(ssize).decode('utf-8').rstrip('\x00'))
+        cmap = data['cmap'] if 'cmap' in data else data['cmapr']
+        hdr = dict(mmax=int(data['mmax']), numx=int(data['numx']), numy=int(data['numy']), nmax=int(data['nmax']),
+                   norder=int(data['norder']), dens=int(data['dens']), cmap=int(cmap), rmin=float(data['rmin']),
+                   rmax=float(data['rmax']), ascale=float(data['ascl']), hscale=float(data['hscl']),
+                   cylmass=float(data['cmass']), time=float(data['time']))
+        offset = 8 + ssize
+    else:
+        # old-style header (eof.py:159-181): 7 x u4 + 6 x f8 = 76 bytes
+        f.seek(0, 0)
+        a = np.fromfile(f, dtype=np.uint32, count=7)
+        b = np.fromfile(f, dtype='<f8', count=6)
+        hdr = dict(mmax=int(a[0]), numx=int(a[1]), numy=int(a[2]), nmax=int(a[3]), norder=int(a[4]),
+                   dens=int(a[5]), cmap=int(a[6]), rmin=float(b[0]), rmax=float(b[1]), ascale=float(b[2]),
+                   hscale=float(b[3]), cylmass=float(b[4]), time=float(b[5]))
+        offset = 76
+    return hdr, offset
+
+
+def eof_params(file, verbose=0):
+    '''eof.eof_params (eof.py:98-200): rmin,rmax,numx,numy,mmax,norder,ascale,hscale,cmap,dens'''
+    with open(file, 'rb') as f:
+        h, _ = _read_header(f)
+    if verbose:
+        print('eof.eof_params: The parameters for this EOF file are:')
+        print('RMIN={0:5.4f},RMAX={1:5.4f}'.format(h['rmin'], h['rmax']))
+        print('MMAX={0:d}'.format(h['mmax']))
+        print('NORDER={0:d}'.format(h['norder']))
+        print('NMAX={0:d}'.format(h['nmax']))
+        print('NUMX,NUMY={0:d},{1:d}'.format(h['numx'], h['numy']))
+        print('DENS,CMAP={0:d},{1:d}'.format(h['dens'], h['cmap']))
+        print('ASCALE,HSCALE={0:5.4f},{1:5.4f}'.format(h['ascale'], h['hscale']))
+        print('CYLMASS={0:5.4f}'.format(h['cylmass']))
+        print('TNOW={0:5.4f}'.format(h['time']))
+    return h['rmin'], h['rmax'], h['numx'], h['numy'], h['mmax'], h['norder'], h['ascale'], h['hscale'], h['cmap'], h['dens']
+
+
+def parse_eof(file, verbose=0):
+    '''
+    eof.parse_eof (eof.py:224-313): potC,rforceC,zforceC,densC,potS,rforceS,zforceS,densS,
+    each (mmax+1, norder, numx+1, numy+1); sine arrays have a zero m=0 plane.
+    One bulk read per block instead of the reference's row-by-row np.fromfile loop.
+    '''
+    with open(file, 'rb') as f:
+        h, offset = _read_header(f)
+        f.seek(offset)
+        M, N, NX, NY = h['mmax'] + 1, h['norder'], h['numx'] + 1, h['numy'] + 1
+        nf = 4 if h['dens'] == 1 else 3
+        cosb = np.fromfile(f, dtype='<f8', count=M * N * nf * NX * NY).reshape(M, N, nf, NX, NY)
+        sinb = np.fromfile(f, dtype='<f8', count=(M - 1) * N * nf * NX * NY).reshape(M - 1, N, nf, NX, NY)
+    shape = (M, N, NX, NY)
+    out = []
+    for blk, first in ((cosb, 0), (sinb, 1)):
+        for k in range(4):
+            a = np.zeros(shape)
+            if k < nf:
+                a[first:] = blk[:, :, k]
+            out.append(a)
+    potC, rforcec, zforcec, densc, potS, rforces, zforces, denss = out
+    return potC, rforcec, zforcec, densc, potS, rforces, zforces, denss
+
+
+def read_eof_file(file):
+    """dictionary wrapper for parse_eof (eof.py:205-221)"""
+    keys = ('potC', 'rforceC', 'zforceC', 'densC', 'potS', 'rforceS', 'zforceS', 'densS')
+    return dict(zip(keys, parse_eof(file)))
+
+
+def set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=0):
+    '''eof.set_table_params (eof.py:316-347): XMIN,XMAX,dX,YMIN,YMAX,dY'''
+    M_SQRT1_2 = np.sqrt(0.5)
+    Rtable = M_SQRT1_2 * RMAX
+    XMIN = r_to_xi(RMIN * ASCALE, CMAP, ASCALE)
+    XMAX = r_to_xi(Rtable * ASCALE, CMAP, ASCALE)
+    dX = (XMAX - XMIN) / NUMX
+    YMIN = z_to_y(-Rtable * ASCALE, HSCALE)
+    YMAX = z_to_y(Rtable * ASCALE, HSCALE)
+    dY = (YMAX - YMIN) / NUMY
+    return XMIN, XMAX, dX, YMIN, YMAX, dY
+
+
+# ---------------------------------------------------------------------------
+# device table cache: the reference API passes the NumPy tables on every call
+# ---------------------------------------------------------------------------
+_TABLE_CACHE = OrderedDict()
+_TABLE_CACHE_MAX = 4
+
+
+def _fingerprint(a):
+    if a is None:
+        return None
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 509)
+    return (a.__array_interface__['data'][0], a.shape, a.dtype.str, float(flat[::step].sum()))
+
+
+def device_tables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP,
+                  rforceC=None, zforceC=None, rforceS=None, zforceS=None):
+    """ops.EOFTables for these host tables (uploaded once, then cached)."""
+    key = (tuple(_fingerprint(t) for t in (potC, potS, rforceC, zforceC, rforceS, zforceS)),
+           int(MMAX), int(NMAX), float(XMIN), float(dX), float(YMIN), float(dY), int(NUMX), int(NUMY),
+           float(ASCALE), float(HSCALE), int(CMAP), ops.torch.cuda.current_device() if ops.torch.cuda.is_available() else -1)
+    E = _TABLE_CACHE.get(key)
+    if E is None:
+        E = ops.EOFTables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP,
+                          rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
+        _TABLE_CACHE[key] = E
+        while len(_TABLE_CACHE) > _TABLE_CACHE_MAX:
+            _TABLE_CACHE.popitem(last=False)
+    else:
+        _TABLE_CACHE.move_to_end(key)
+    return E
+
+
+def clear_table_cache():
+    _TABLE_CACHE.clear()
+
+
+# ---------------------------------------------------------------------------
+# accumulation -- eof.py:492-640, 1415-1455, 1158-1260
+# ---------------------------------------------------------------------------
+def accumulate(ParticleInstance, potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP,
+               verbose=0, no_odd=False, VAR=0):
+    '''
+    eof.accumulate (eof.py:492-640) -> accum_cos, accum_sin, each (MMAX+1, NMAX) float64.
+    `no_odd` is accepted and, as in the reference (mask computed at 545-548 but never
+    applied), has no effect.  VAR (jackknife sub-sampling with unseeded np.random,
+    554-574) is outside the path.
+    '''
+    if VAR:
+        raise NotImplementedError('eof.accumulate: VAR sub-sampling is outside the B200 hot path')
+    x, y, z, m = particle.particle_arrays(ParticleInstance)
+    E = device_tables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP)
+    c, s = E.accumulate(x, y, z, m)
+    return c.cpu().numpy(), s.cpu().numpy()
+
+
+def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy,
+                            ascale, hscale, cmap, verbose=0, no_odd=False, VAR=False):
+    '''
+    eof.make_coefficients_multi (eof.py:1415-1455).  The reference splits the particles over
+    `nprocs` worker processes and sums the partial coefficients on the parent; here one GPU
+    takes the whole set, or -- when torch.distributed is initialised -- every rank takes its
+    block of the particles and the partial coefficients are summed with one NCCL allreduce
+    (exptool_b200.parallel).  `nprocs` is accepted for call compatibility.
+    '''
+    if VAR:
+        raise NotImplementedError('eof.make_coefficients_multi: VAR is outside the B200 hot path')
+    t1 = time.time()
+    from .. import parallel
+    x, y, z, m = particle.particle_arrays(ParticleInstance)
+    E = device_tables(potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap)
+    c, s = parallel.eof_accumulate_sharded(E, x, y, z, m)
+    if verbose:
+        dt = time.time() - t1
+        print('eof.make_coefficients_multi: Accumulation took {0:3.2f} seconds, or {1:4.2f} microseconds per orbit.'
+              .format(dt, 1.e6 * dt / max(len(x), 1)))
+    return c.cpu().numpy(), s.cpu().numpy()
+
+
+class EOF_Object(object):
+    '''eof.EOF_Object (eof.py:1627-1636)'''
+    time = None
+    dump = None
+    comp = None
+    nbodies = None
+    mmax = None
+    nmax = None
+    eof_file = None
+    cos = None
+    sin = None
+
+
+def compute_coefficients(PSPInput, eof_file, verbose=1, no_odd=False, nprocs_max=-1, VAR=False, nanblock=False):
+    '''
+    eof.compute_coefficients (eof.py:1158-1260) -> EOF_Object.
+    NaN positions are moved to the origin unless nanblock (the reference's intent at
+    1190-1204; its own `if nanvals > 0` raises on NumPy >= 2.2).
+    '''
+    x, y, z, m = particle.particle_arrays(PSPInput)
+    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64); z = np.asarray(z, dtype=np.float64)
+    nanvals = np.where(np.isnan(x) | np.isnan(y) | np.isnan(z))[0]
+    if nanvals.size > 0:
+        print('eof.compute_coefficients: NaN values found in output file {}.'.format(getattr(PSPInput, 'filename', None)))
+        if not nanblock:
+            x = x.copy(); y = y.copy(); z = z.copy()
+            x[nanvals] = 0.; y[nanvals] = 0.; z[nanvals] = 0.
+    EOF_Out = EOF_Object()
+    EOF_Out.time = getattr(PSPInput, 'time', None)
+    EOF_Out.filename = getattr(PSPInput, 'filename', None)
+    EOF_Out.comp = getattr(PSPInput, 'comp', None)
+    EOF_Out.nbodies = np.asarray(m).size
+    EOF_Out.eof_file = eof_file
+    potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS = parse_eof(eof_file)
+    rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, dens = eof_params(eof_file, verbose=(verbose > 1))
+    XMIN, XMAX, dX, YMIN, YMAX, dY = set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ascale, HSCALE=hscale,
+                                                      NUMX=numx, NUMY=numy, CMAP=cmap)
+    EOF_Out.mmax = mmax
+    EOF_Out.nmax = norder
+    a_cos, a_sin = make_coefficients_multi((x, y, z, m), 1, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy,
+                                           ascale, hscale, cmap, verbose=verbose, no_odd=no_odd, VAR=VAR)
+    EOF_Out.cos = a_cos
+    EOF_Out.sin = a_sin
+    return EOF_Out
+
+
+# ---------------------------------------------------------------------------
+# field evaluation -- eof.py:756-870, 989-1144, 1263-1317
+# ---------------------------------------------------------------------------
+def _scalar_or_array(vals, scalar):
+    if scalar:
+        return tuple(np.float64(v[0]) for v in vals)
+    return tuple(vals)
+
+
+def force_eval(r, z, phi, accum_cos, accum_sin, potC, rforceC, zforceC, potS, rforceS, zforceS,
+               rmin=0, dR=0, zmin=0, dZ=0, numx=0, numy=0, fac=1.0, MMAX=6, NMAX=18, ASCALE=0.0, HSCALE=0.0,
+               CMAP=0, no_odd=False, perturb=False):
+    '''
+    eof.force_eval (eof.py:756-870): (fr+fr0, fp, fz+fz0, p+p0, p0), or
+    (fr, fp, fz, p, p0, fr0, fz0) if perturb.  r, z, phi may be scalars (as the
+    reference is called) or equal-length arrays (batched extension).
+    '''
+    scalar = np.ndim(r) == 0
+    r1 = np.atleast_1d(np.asarray(r, dtype=np.float64))
+    z1 = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    p1 = np.atleast_1d(np.asarray(phi, dtype=np.float64))
+    E = device_tables(potC, potS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
+                      rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
+    if not perturb:
+        E.contract(accum_cos, accum_sin, m1=0, m2=MMAX, nuse=NMAX, no_odd=no_odd)
+        fr, fp, fz, p, p0 = E.force_eval_points(r1, z1, p1).cpu().numpy()
+        return _scalar_or_array((fr, fp, fz, p, p0), scalar)
+    E.contract(accum_cos, accum_sin, m1=1, m2=MMAX, nuse=NMAX, no_odd=no_odd)
+    fr, fp, fz, p, _ = E.force_eval_points(r1, z1, p1).cpu().numpy()
+    E.contract(accum_cos, accum_sin, m1=0, m2=0, nuse=NMAX, no_odd=False)
+    fr0, _, fz0, _, p0 = E.force_eval_points(r1, z1, p1).cpu().numpy()
+    return _scalar_or_array((fr, fp, fz, p, p0, fr0, fz0), scalar)
+
+
+def accumulated_eval_particles(Particles, accum_cos, accum_sin, potC=0, rforceC=0, zforceC=0, potS=0, rforceS=0,
+                               zforceS=0, rmin=0, dR=0, zmin=0, dZ=0, numx=0, numy=0, MMAX=6, NMAX=18, ASCALE=0.0,
+                               HSCALE=0.0, CMAP=0, m1=0, m2=1000, verbose=1, density=False, eof_file=''):
+    '''
+    eof.accumulated_eval_particles (eof.py:989-1144): p0, p, fr, fp, fz, R, one value per particle.
+    p excludes m=0; fr, fz include it; only m1 <= m <= m2 contribute.
+    '''
+    if eof_file != '':
+        potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS = parse_eof(eof_file)
+        rmin, rmax, numx, numy, MMAX, NMAX, ASCALE, HSCALE, CMAP, dens = eof_params(eof_file)
+        rmin, rmax, dR, zmin, zmax, dZ = set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ASCALE, HSCALE=HSCALE,
+                                                          NUMX=numx, NUMY=numy, CMAP=CMAP)
+    if density:
+        if verbose > 0:
+            print('eof.accumulated_eval_particles: cannot compute density (outside the B200 hot path). moving on without...')
+        density = False
+    x, y, z, _ = particle.particle_arrays(Particles)
+    E = device_tables(potC, potS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
+                      rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
+    E.contract(accum_cos, accum_sin, m1=m1, m2=m2)
+    p0, p, fr, fp, fz, R = E.force(x, y, z).cpu().numpy()
+    return p0, p, fr, fp, fz, R
+
+
+def compute_forces(PSPInput, EOF_Object, verbose=1, nprocs=-1, m1=0, m2=1000, density=False):
+    '''eof.compute_forces (eof.py:1263-1317): p0, p, fr, fp, fz, r'''
+    potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS = parse_eof(EOF_Object.eof_file)
+    rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, dens = eof_params(EOF_Object.eof_file)
+    XMIN, XMAX, dX, YMIN, YMAX, dY = set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ascale, HSCALE=hscale,
+                                                      NUMX=numx, NUMY=numy, CMAP=cmap)
+    return accumulated_eval_particles(PSPInput, EOF_Object.cos, EOF_Object.sin, potC, rforceC, zforceC, potS,
+                                      rforceS, zforceS, rmin=XMIN, dR=dX, zmin=YMIN, dZ=dY, numx=numx, numy=numy,
+                                      MMAX=mmax, NMAX=norder, ASCALE=ascale, HSCALE=hscale, CMAP=cmap, m1=m1, m2=m2,
+                                      verbose=verbose, density=density)
+
+
+# ---------------------------------------------------------------------------
+# coefficient dump files -- eof.py:1646-1760 (byte-compatible)
+# ---------------------------------------------------------------------------
+def eof_coefficients_to_file(f, EOF_Object):
+    '''eof.py:1646-1667: 224-byte header then cos, sin as f8'''
+    np.array([EOF_Object.time], dtype='f4').tofile(f)
+    np.array([EOF_Object.filename], dtype='S100').tofile(f)
+    np.array([EOF_Object.comp], dtype='S8').tofile(f)
+    np.array([EOF_Object.nbodies], dtype='i4').tofile(f)
+    np.array([EOF_Object.eof_file], dtype='S100').tofile(f)
+    np.array([EOF_Object.mmax, EOF_Object.nmax], dtype='i4').tofile(f)
+    np.array(EOF_Object.cos.reshape(-1, ), dtype='f8').tofile(f)
+    np.array(EOF_Object.sin.reshape(-1, ), dtype='f8').tofile(f)
+
+
+def save_eof_coefficients(outfile, EOF_Object, verbose=0):
+    '''eof.py:1671-1706: append one dump, bump the leading i4 counter'''
+    try:
+        f = open(outfile, 'rb+')
+        f.close()
+    except IOError:
+        f = open(outfile, 'wb')
+        np.array([0], dtype='i4').tofile(f)
+        f.close()
+    with open(outfile, 'rb+') as f:
+        ndumps = int(np.fromfile(f, dtype='i4', count=1)[0]) + 1
+        f.seek(0)
+        np.array([ndumps], dtype='i4').tofile(f)
+        if verbose:
+            print('eof.save_eof_coefficients: coefficient file currently has {0:d} dumps.'.format(ndumps))
+        f.seek(4 + (ndumps - 1) * (16 * (EOF_Object.mmax + 1) * (EOF_Object.nmax) + 224))
+        eof_coefficients_to_file(f, EOF_Object)
+
+
+def extract_eof_coefficients(f):
+    '''eof.py:1740-1760'''
+    EOF_Obj = EOF_Object()
+    [EOF_Obj.time] = np.fromfile(f, dtype='f4', count=1)
+    [EOF_Obj.filename] = np.fromfile(f, dtype='S100', count=1)
+    [EOF_Obj.comp] = np.fromfile(f, dtype='S8', count=1)
+    [EOF_Obj.nbodies] = np.fromfile(f, dtype='i4', count=1)
+    [EOF_Obj.eof_file] = np.fromfile(f, dtype='S100', count=1)
+    [EOF_Obj.mmax, EOF_Obj.nmax] = np.fromfile(f, dtype='i4', count=2)
+    cosine_flat = np.fromfile(f, dtype='f8', count=(EOF_Obj.mmax + 1) * EOF_Obj.nmax)
+    sine_flat = np.fromfile(f, dtype='f8', count=(EOF_Obj.mmax + 1) * EOF_Obj.nmax)
+    EOF_Obj.cos = cosine_flat.reshape([(EOF_Obj.mmax + 1), EOF_Obj.nmax])
+    EOF_Obj.sin = sine_flat.reshape([(EOF_Obj.mmax + 1), EOF_Obj.nmax])
+    return EOF_Obj
+
+
+def restore_eof_coefficients(infile):
+    '''eof.py:1709-1737: (last EOF_Object, OrderedDict time -> EOF_Object)'''
+    EOF_Dict = OrderedDict()
+    EOF_Out = None
+    with open(infile, 'rb') as f:
+        [ndumps] = np.fromfile(f, dtype='i4', count=1)
+        f.seek(4)
+        for step in range(0, ndumps):
+            try:
+                EOF_Out = extract_eof_coefficients(f)
+                EOF_Dict[EOF_Out.time] = EOF_Out
+            except Exception:
+                pass
+    return EOF_Out, EOF_Dict

@@ -1,0 +1,368 @@
+// bfe_device.cuh -- per-point device arithmetic shared by all kernels.
+//
+// Every function restates one piece of the reference (file:line cited); the
+// oracle (oracle/oracle_np.py) restates the same lines on the CPU.
+#pragma once
+#include "bfe_internal.h"
+
+#define BFE_FOURPI_NEG (-12.566370614359172953850573533118)
+#define BFE_TWOPI      (6.283185307179586476925286766559)
+
+// ---------------------------------------------------------------------------
+// coordinate maps -- exptool/basis/compatibility.py:16-99
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double bfe_r_to_xi(double r, int cmap, double scale) {
+    // compatibility.py:30-43 ; negatives map to 0
+    double out;
+    if (cmap == 1) {
+        double q = r / scale;
+        out = (q - 1.0) / (q + 1.0);
+    } else if (cmap == 2) {
+        out = log(r);
+    } else {
+        out = r;
+    }
+    return (r < 0.0) ? 0.0 : out;
+}
+
+__device__ __forceinline__ double bfe_d_xi_to_r(double xi, int cmap, double scale) {
+    // compatibility.py:73-80
+    if (cmap == 1) return 0.5 * (1.0 - xi) * (1.0 - xi) / scale;
+    if (cmap == 2) return exp(-xi);
+    return 1.0;
+}
+
+__device__ __forceinline__ double bfe_z_to_y(double z, double hscale) {
+    // compatibility.py:91 (epsilon 1e-8: the live Python value, not accumulate.c's 1e-10)
+    double az = fabs(z);
+    return (z / (az + 1.0e-8)) * asinh(fabs(z / hscale));
+}
+
+// ---------------------------------------------------------------------------
+// EOF bins + bilinear weights -- eof.py:394-422, 443-451
+// ---------------------------------------------------------------------------
+struct EofBin {
+    int node;              // ix*(numy+1)+iy ; the other corners are +1, +ny1, +ny1+1
+    double c00, c10, c01, c11;
+};
+
+__device__ __forceinline__ EofBin bfe_eof_bin(const EofGeom& g, double r, double z) {
+    double X = (bfe_r_to_xi(r, g.cmap, g.ascale) - g.xmin) / g.dx;
+    double Y = (bfe_z_to_y(z, g.hscale) - g.ymin) / g.dy;
+    int ix = (int)X;                       // truncation, eof.py:404 (NaN -> 0, +-inf saturate)
+    int iy = (int)Y;
+    if (ix < 0) ix = 0;                    // 410
+    if (X < 0.0) X = 0.0;                  // 412
+    if (ix >= g.numx) ix = g.numx - 1;     // 414 (X deliberately NOT clamped: 415 is a no-op)
+    if (iy < 0) iy = 0;
+    if (Y < 0.0) Y = 0.0;
+    if (iy >= g.numy) iy = g.numy - 1;
+    double delx0 = (double)ix + 1.0 - X;
+    double dely0 = (double)iy + 1.0 - Y;
+    double delx1 = X - (double)ix;
+    double dely1 = Y - (double)iy;
+    EofBin b;
+    b.node = ix * g.ny1 + iy;
+    b.c00 = delx0 * dely0;
+    b.c10 = delx1 * dely0;
+    b.c01 = delx0 * dely1;
+    b.c11 = delx1 * dely1;
+    return b;
+}
+
+// cos(phi), sin(phi) of phi = atan2(y, x) without the atan2 (eof.py:532, spheresl.py:613).
+__device__ __forceinline__ void bfe_cossin_phi(double x, double y, double& c, double& s) {
+    double h2 = x * x + y * y;
+    if (h2 > 0.0 && h2 < 1.0e300) {
+        double ih = rsqrt(h2);
+        // one Newton step: rsqrt() is not correctly rounded
+        ih = ih * (1.5 - 0.5 * h2 * ih * ih);
+        c = x * ih;
+        s = y * ih;
+    } else {
+        double phi = atan2(y, x);         // zeros / denormals / huge: defer to libm semantics
+        sincos(phi, &s, &c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// EOF field from contracted grids.  G[node][m][6] = (pc, ps, rc, rs, zc, zs) with
+// pc[m] = sum_n cos[m,n] potC[m,n,node] etc.  Restates eof.py:842-864 / 1092-1134 with
+// the sum over n done once per coefficient set (exact algebra; FP64 order differs).
+// ---------------------------------------------------------------------------
+struct EofField {
+    double p0;   // m = 0 potential
+    double p;    // sum over m >= 1
+    double fr;   // includes m = 0
+    double fp;
+    double fz;   // includes m = 0
+};
+
+template <int MCAP>
+__device__ __forceinline__ EofField bfe_eof_eval(const EofGeom& g, const double* __restrict__ G, int gstride,
+                                                 const EofBin& b, double c1, double s1) {
+    const double2* n00 = reinterpret_cast<const double2*>(G + (size_t)b.node * gstride);
+    const double2* n01 = reinterpret_cast<const double2*>(G + (size_t)(b.node + 1) * gstride);
+    const double2* n10 = reinterpret_cast<const double2*>(G + (size_t)(b.node + g.ny1) * gstride);
+    const double2* n11 = reinterpret_cast<const double2*>(G + (size_t)(b.node + g.ny1 + 1) * gstride);
+    EofField f;
+    f.p0 = 0.0; f.p = 0.0; f.fr = 0.0; f.fp = 0.0; f.fz = 0.0;
+    double cm = 1.0, sm = 0.0;
+#pragma unroll
+    for (int m = 0; m <= MCAP; ++m) {
+        if (m <= g.mmax) {
+            double2 a0 = __ldg(n00 + 3 * m), a1 = __ldg(n00 + 3 * m + 1), a2 = __ldg(n00 + 3 * m + 2);
+            double2 b0 = __ldg(n10 + 3 * m), b1 = __ldg(n10 + 3 * m + 1), b2 = __ldg(n10 + 3 * m + 2);
+            double2 c0 = __ldg(n01 + 3 * m), c1v = __ldg(n01 + 3 * m + 1), c2 = __ldg(n01 + 3 * m + 2);
+            double2 d0 = __ldg(n11 + 3 * m), d1 = __ldg(n11 + 3 * m + 1), d2 = __ldg(n11 + 3 * m + 2);
+            double vpc = a0.x * b.c00 + b0.x * b.c10 + c0.x * b.c01 + d0.x * b.c11;
+            double vps = a0.y * b.c00 + b0.y * b.c10 + c0.y * b.c01 + d0.y * b.c11;
+            double vrc = a1.x * b.c00 + b1.x * b.c10 + c1v.x * b.c01 + d1.x * b.c11;
+            double vrs = a1.y * b.c00 + b1.y * b.c10 + c1v.y * b.c01 + d1.y * b.c11;
+            double vzc = a2.x * b.c00 + b2.x * b.c10 + c2.x * b.c01 + d2.x * b.c11;
+            double vzs = a2.y * b.c00 + b2.y * b.c10 + c2.y * b.c01 + d2.y * b.c11;
+            if (m == 0) {
+                f.p0 = vpc;
+                f.fr = vrc;
+                f.fz = vzc;
+            } else {
+                f.p  += cm * vpc + sm * vps;
+                f.fr += cm * vrc + sm * vrs;
+                f.fz += cm * vzc + sm * vzs;
+                f.fp += (double)m * (sm * vpc - cm * vps);
+            }
+            // advance to (m+1) phi
+            double cn = cm * c1 - sm * s1;
+            double sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+    }
+    return f;
+}
+
+// ---------------------------------------------------------------------------
+// associated Legendre functions -- spheresl.py:664-700 (legendre_R), 706-770 (dlegendre_R)
+// ---------------------------------------------------------------------------
+template <int LCAP>
+struct LegTable {
+    double p[LCAP + 1][LCAP + 1];
+};
+
+// The recurrences are evaluated with explicitly rounded (non-fused) operations in the
+// reference's own operation order: dlegendre divides a cancelling difference by
+// (x^2 - 1), so near the poles a 1-ulp change in P is amplified by up to 1e8 in the
+// reference itself; matching NumPy's rounding step by step keeps parity there.
+#define BFE_MUL(a, b) __dmul_rn((a), (b))
+#define BFE_ADD(a, b) __dadd_rn((a), (b))
+#define BFE_SUB(a, b) __dadd_rn((a), -(b))
+#define BFE_DIV(a, b) __ddiv_rn((a), (b))
+
+template <int LCAP>
+__device__ __forceinline__ void bfe_legendre(int lmax, double x, LegTable<LCAP>& T) {
+    T.p[0][0] = 1.0;
+    double pll = 1.0;
+    double somx2 = sqrt(BFE_MUL(BFE_SUB(1.0, x), BFE_ADD(1.0, x)));       // spheresl.py:679
+    double fact = 1.0;
+#pragma unroll
+    for (int m = 1; m <= LCAP; ++m) {
+        if (m <= lmax) {
+            pll = BFE_MUL(pll, BFE_MUL(-fact, somx2));                    // 682
+            T.p[m][m] = pll;
+            fact += 2.0;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < LCAP; ++m) {
+        if (m < lmax) {
+            double pl2 = T.p[m][m];
+            double pl1 = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl2);         // 689
+            T.p[m + 1][m] = pl1;
+#pragma unroll
+            for (int l = m + 2; l <= LCAP; ++l) {
+                if (l <= lmax) {
+                    // (x*(2*l-1)*pl1-(l+m-1)*pl2)/(l-m)                   // 693
+                    double a = BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1);
+                    double b = BFE_MUL((double)(l + m - 1), pl2);
+                    double v = BFE_DIV(BFE_SUB(a, b), (double)(l - m));
+                    T.p[l][m] = v;
+                    pl2 = pl1;
+                    pl1 = v;
+                }
+            }
+        }
+    }
+}
+
+// derivative table, spheresl.py:751-768; p must already hold legendre(x)
+template <int LCAP>
+__device__ __forceinline__ void bfe_dlegendre(int lmax, double x, const LegTable<LCAP>& T, LegTable<LCAP>& D) {
+    const double MINEPS = 1.0e-8;
+    if (1.0 - fabs(x) < MINEPS) x = (x > 0.0) ? (1.0 - MINEPS) : -(1.0 - MINEPS);
+    double somx2 = BFE_DIV(1.0, BFE_SUB(BFE_MUL(x, x), 1.0));             // 757
+    D.p[0][0] = 0.0;
+#pragma unroll
+    for (int l = 1; l <= LCAP; ++l) {
+        if (l <= lmax) {
+#pragma unroll
+            for (int m = 0; m < l; ++m) {
+                // somx2*(x*l*p[l][m] - (l+m)*p[l-1][m])                   // 763
+                double a = BFE_MUL(BFE_MUL(x, (double)l), T.p[l][m]);
+                double b = BFE_MUL((double)(l + m), T.p[l - 1][m]);
+                D.p[l][m] = BFE_MUL(somx2, BFE_SUB(a, b));
+            }
+            D.p[l][l] = BFE_MUL(BFE_MUL(BFE_MUL(somx2, x), (double)l), T.p[l][l]);   // 765
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SL radial bin -- spheresl.py:123-142 / 309-328
+// ---------------------------------------------------------------------------
+struct SlBin {
+    int i;          // lower node of the interpolation interval, clamped to [0, numr-2]
+    double x1, x2;  // linear weights of nodes i, i+1
+    double fac;     // d_xi_to_r(xi)/dxi
+};
+
+__device__ __forceinline__ SlBin bfe_sl_bin(const SlGeom& g, const double* __restrict__ xi, double r) {
+    double x = bfe_r_to_xi(r, g.cmap, g.scale);
+    if (g.cmap == 1) {
+        if (x < -1.0) x = -1.0;
+        if (x >= 1.0) x = 1.0 - 1.0e-08;
+    }
+    double fi = floor((x - g.xi0) / g.dxi);
+    int i;
+    if (!(fi >= 0.0)) i = 0;
+    else if (fi > (double)(g.numr - 2)) i = g.numr - 2;
+    else i = (int)fi;
+    SlBin b;
+    b.i = i;
+    b.x1 = (__ldg(xi + i + 1) - x) / g.dxi;
+    b.x2 = (x - __ldg(xi + i)) / g.dxi;
+    b.fac = bfe_d_xi_to_r(x, g.cmap, g.scale) / g.dxi;
+    return b;
+}
+
+// ---------------------------------------------------------------------------
+// SL field from contracted rows.  A[i][k] = sum_n c[k,n] eftable[l(k),n,i]/sqrt(ev[l,n])
+// (node-major, row stride kpad).  Restates spheresl.py:1041-1086 / 1200-1228 / 1289-1339
+// with the sum over n done once per coefficient set.
+// ---------------------------------------------------------------------------
+struct SlField {
+    double pot0, pot1, potr, pott, potp;
+};
+
+template <int LCAP>
+__device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double* __restrict__ A, int kpad,
+                                               const double* __restrict__ p0tab, const double* __restrict__ fac,
+                                               const SlBin& b, double costh, double c1, double s1,
+                                               bool trig_index_l) {
+    LegTable<LCAP> P, D;
+    bfe_legendre<LCAP>(g.lmax, costh, P);
+    bfe_dlegendre<LCAP>(g.lmax, costh, P, D);
+
+    // nodes: potential uses (i, i+1); derivative stencil uses (j-1, j, j+1), j = max(i,1)
+    const int j = (b.i == 0) ? 1 : b.i;
+    const double* rowm = A + (size_t)(j - 1) * kpad;
+    const double* row0 = A + (size_t)j * kpad;
+    const double* rowp = A + (size_t)(j + 1) * kpad;
+    const double pm = __ldg(p0tab + j - 1), pc = __ldg(p0tab + j), pp = __ldg(p0tab + j + 1);
+    // weights so that pot = wA*A[j-1] + wB*A[j] + wC*A[j+1]
+    double P0, wA, wB, wC;
+    if (b.i == 0) { P0 = b.x1 * pm + b.x2 * pc; wA = b.x1; wB = b.x2; wC = 0.0; }
+    else          { P0 = b.x1 * pc + b.x2 * pp; wA = 0.0; wB = b.x1; wC = b.x2; }
+    const double dA = (b.x2 - 0.5) * pm, dB = -2.0 * b.x2 * pc, dC = (b.x2 + 0.5) * pp;
+
+    SlField f;
+    f.pot1 = 0.0; f.pott = 0.0; f.potp = 0.0;
+    {
+        double am = __ldg(rowm), a0 = __ldg(row0), ap = __ldg(rowp);
+        double sp = (wA * am + wB * a0 + wC * ap) * P0;
+        double sd = b.fac * (dA * am + dB * a0 + dC * ap);
+        double f00 = __ldg(fac);
+        f.pot0 = f00 * sp;
+        f.potr = f00 * sd;
+    }
+    // cos/sin(l phi) by recurrence for the force_eval quirk; cos/sin(m phi) otherwise
+    double cl = 1.0, sl = 0.0;
+#pragma unroll
+    for (int l = 1; l <= LCAP; ++l) {
+        if (l <= g.lmax) {
+            { double cn = cl * c1 - sl * s1; double sn = sl * c1 + cl * s1; cl = cn; sl = sn; }
+            const int k0 = l * l;
+            {   // m = 0
+                double am = __ldg(rowm + k0), a0 = __ldg(row0 + k0), ap = __ldg(rowp + k0);
+                double sp = (wA * am + wB * a0 + wC * ap) * P0;
+                double sd = b.fac * (dA * am + dB * a0 + dC * ap);
+                double fl = __ldg(fac + l * (g.lmax + 1));
+                f.pot1 += fl * P.p[l][0] * sp;
+                f.potr += fl * P.p[l][0] * sd;
+                f.pott += fl * D.p[l][0] * sp;
+            }
+            double cm = 1.0, sm = 0.0;
+#pragma unroll
+            for (int m = 1; m <= l; ++m) {
+                { double cn = cm * c1 - sm * s1; double sn = sm * c1 + cm * s1; cm = cn; sm = sn; }
+                const double ct = trig_index_l ? cl : cm;
+                const double st = trig_index_l ? sl : sm;
+                const int kc = k0 + 2 * m - 1;
+                double amc = __ldg(rowm + kc), a0c = __ldg(row0 + kc), apc = __ldg(rowp + kc);
+                double ams = __ldg(rowm + kc + 1), a0s = __ldg(row0 + kc + 1), aps = __ldg(rowp + kc + 1);
+                double spc = (wA * amc + wB * a0c + wC * apc) * P0;
+                double sps = (wA * ams + wB * a0s + wC * aps) * P0;
+                double sdc = b.fac * (dA * amc + dB * a0c + dC * apc);
+                double sds = b.fac * (dA * ams + dB * a0s + dC * aps);
+                double Ap = spc * ct + sps * st;
+                double Ad = sdc * ct + sds * st;
+                double Bp = -spc * st + sps * ct;
+                double fl = __ldg(fac + l * (g.lmax + 1) + m);
+                f.pot1 += fl * P.p[l][m] * Ap;
+                f.potr += fl * P.p[l][m] * Ad;
+                f.pott += fl * D.p[l][m] * Ap;
+                f.potp += fl * P.p[l][m] * (double)m * Bp;
+            }
+        }
+    }
+    return f;
+}
+
+// ---------------------------------------------------------------------------
+// Fields.return_forces_cart -- potential.py:455-497
+// ---------------------------------------------------------------------------
+struct CartForce {
+    double fxd, fxh, fyd, fyh, fzd, fzh, pd, ph;
+};
+
+template <int MCAP, int LCAP>
+__device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const double* __restrict__ G, int gstride,
+                                                    const SlGeom& gs, const double* __restrict__ A, int kpad,
+                                                    const double* __restrict__ xi, const double* __restrict__ p0tab,
+                                                    const double* __restrict__ fac,
+                                                    double x, double y, double z, double crot, double srot) {
+    double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + 1.e-15;       // 455
+    double r3 = sqrt(BFE_ADD(BFE_MUL(r2, r2), BFE_MUL(z, z))) + 1.e-15;     // 456
+    double costh = BFE_DIV(z, r3);                                          // 457
+    double c1, s1;
+    bfe_cossin_phi(x, y, c1, s1);                           // 458
+    // phi + rotpos
+    double cr = c1 * crot - s1 * srot;
+    double sr = s1 * crot + c1 * srot;
+    EofBin eb = bfe_eof_bin(ge, r2, z);
+    EofField d = bfe_eof_eval<MCAP>(ge, G, gstride, eb, cr, sr);
+    SlBin sb = bfe_sl_bin(gs, xi, r3);
+    SlField h = bfe_sl_eval<LCAP>(gs, A, kpad, p0tab, fac, sb, costh, cr, sr, true);
+    double diskfr = d.fr, diskfp = d.fp, diskfz = d.fz, diskp = d.p + d.p0;
+    double halofr = h.potr, haloft = h.pott, halofp = h.potp;
+    if (r3 < gs.xi0) { halofp = 0.0; diskfp = 0.0; }         // 483-485 (min(xi) = xi[0])
+    CartForce o;
+    double r2sq = r2 * r2, r3cu = r3 * r3 * r3;
+    o.fxd = diskfr * (x / r2) - diskfp * (y / r2sq);
+    o.fxh = -1.0 * (halofr * (x / r3) - haloft * (x * z / r3cu)) + halofp * (y / r2sq);
+    o.fyd = diskfr * (y / r2) + diskfp * (x / r2sq);
+    o.fyh = -1.0 * (halofr * (y / r3) - haloft * (y * z / r3cu)) - halofp * (x / r2sq);
+    o.fzd = diskfz;
+    o.fzh = -1.0 * (halofr * (z / r3) + haloft * (r2sq / r3cu));
+    o.pd = diskp;
+    o.ph = h.pot1 + h.pot0;
+    return o;
+}

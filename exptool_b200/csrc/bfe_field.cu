@@ -1,0 +1,153 @@
+// bfe_field.cu -- combined disc+halo force and leapfrog orbit integration.
+//
+//   field_cart_kernel : Fields.return_forces_cart (potential.py:445-497), thread per point
+//   leapfrog_kernel   : integrate.leapfrog_integrate (integrate.py:53-190), thread per orbit,
+//                       phase-space state in registers for the whole integration
+#include "bfe_device.cuh"
+#include <string.h>
+#include <cstdio>
+#include <atomic>
+
+template <int MCAP, int LCAP>
+__global__ void __launch_bounds__(128)
+field_cart_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
+                  SlGeom gs, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+                  const double* __restrict__ p0tab, const double* __restrict__ fac,
+                  int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                  const double* __restrict__ z, double crot, double srot, double* __restrict__ out8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        CartForce f = bfe_field_cart<MCAP, LCAP>(ge, G, gstride, gs, A, kpad, xi, p0tab, fac,
+                                                 __ldg(x + i), __ldg(y + i), __ldg(z + i), crot, srot);
+        out8[i] = f.fxd;
+        out8[n + i] = f.fxh;
+        out8[2 * n + i] = f.fyd;
+        out8[3 * n + i] = f.fyh;
+        out8[4 * n + i] = f.fzd;
+        out8[5 * n + i] = f.fzh;
+        out8[6 * n + i] = f.pd;
+        out8[7 * n + i] = f.ph;
+    }
+}
+
+template <int MCAP, int LCAP>
+__global__ void __launch_bounds__(128)
+leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
+                SlGeom gs, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+                const double* __restrict__ p0tab, const double* __restrict__ fac,
+                int64_t norbit, int64_t nint, double dt, double rotfreq,
+                double* __restrict__ state6, double* __restrict__ traj, int64_t traj_stride,
+                int apse, int ap_max, int* __restrict__ nsteps_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= norbit) return;
+    double px = state6[i], py = state6[norbit + i], pz = state6[2 * norbit + i];
+    double vx = state6[3 * norbit + i], vy = state6[4 * norbit + i], vz = state6[5 * norbit + i];
+    const double w = BFE_TWOPI * rotfreq;                    // barpos = 2 pi rotfreq (k dt), integrate.py:94-97
+    const double hdt2 = 0.5 * (dt * dt);
+
+    double srot, crot;
+    sincos(w * (0.0 * dt), &srot, &crot);
+    CartForce f = bfe_field_cart<MCAP, LCAP>(ge, G, gstride, gs, A, kpad, xi, p0tab, fac, px, py, pz, crot, srot);
+    double ax = f.fxd + f.fxh, ay = f.fyd + f.fyh, az = f.fzd + f.fzh, pot = f.pd + f.ph;   // 119-122
+    if (traj) {
+        double* t = traj + i;
+        t[0] = px; t[norbit] = py; t[2 * norbit] = pz; t[3 * norbit] = vx; t[4 * norbit] = vy; t[5 * norbit] = vz;
+        t[6 * norbit] = pot; t[7 * norbit] = ax; t[8 * norbit] = ay; t[9 * norbit] = az;
+    }
+    int n_aps = 0;
+    double rs0 = 0.0, rs1 = px * px + py * py;               // planar r^2 at steps k-2, k-1
+    int64_t step = 1;
+    while (n_aps < ap_max && step < nint) {                  // 126
+        px = px + (vx * dt) + (ax * hdt2);                   // 129-131
+        py = py + (vy * dt) + (ay * hdt2);
+        pz = pz + (vz * dt) + (az * hdt2);
+        sincos(w * ((double)step * dt), &srot, &crot);
+        f = bfe_field_cart<MCAP, LCAP>(ge, G, gstride, gs, A, kpad, xi, p0tab, fac, px, py, pz, crot, srot);
+        double bx = f.fxd + f.fxh, by = f.fyd + f.fyh, bz = f.fzd + f.fzh;                   // 134-138
+        pot = f.pd + f.ph;
+        vx = vx + (0.5 * (ax + bx) * dt);                    // 141-143
+        vy = vy + (0.5 * (ay + by) * dt);
+        vz = vz + (0.5 * (az + bz) * dt);
+        ax = bx; ay = by; az = bz;
+        double rs2 = px * px + py * py;
+        if (apse && step > 1 && rs1 > rs0 && rs1 > rs2) ++n_aps;                              // 146-153
+        rs0 = rs1; rs1 = rs2;
+        if (traj && (step % traj_stride) == 0) {
+            double* t = traj + (step / traj_stride) * 10 * norbit + i;
+            t[0] = px; t[norbit] = py; t[2 * norbit] = pz; t[3 * norbit] = vx; t[4 * norbit] = vy;
+            t[5 * norbit] = vz; t[6 * norbit] = pot; t[7 * norbit] = ax; t[8 * norbit] = ay; t[9 * norbit] = az;
+        }
+        ++step;
+    }
+    state6[i] = px; state6[norbit + i] = py; state6[2 * norbit + i] = pz;
+    state6[3 * norbit + i] = vx; state6[4 * norbit + i] = vy; state6[5 * norbit + i] = vz;
+    if (nsteps_out) nsteps_out[i] = (int)step;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+#define FIELD_DISPATCH(KERN, ...)                                                                         \
+    do {                                                                                                  \
+        if (he->g.mmax <= 6 && hs->g.lmax <= 4)      KERN<6, 4><<<grid, 128, 0, stream>>>(__VA_ARGS__);    \
+        else if (he->g.mmax <= 6 && hs->g.lmax <= 6) KERN<6, 6><<<grid, 128, 0, stream>>>(__VA_ARGS__);    \
+        else KERN<BFE_MAX_MMAX, BFE_MAX_LMAX><<<grid, 128, 0, stream>>>(__VA_ARGS__);                      \
+    } while (0)
+
+extern "C" int bfe_field_force_cart(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y,
+                                    const double* z, double rotpos, double* out8, void* stream_) {
+    if (!he || !hs || n < 0) return BFE_ERR_ARG;
+    if (!he->contracted || !hs->contracted) return BFE_ERR_STATE;
+    if (n == 0) return BFE_OK;
+    if (!x || !y || !z || !out8) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int64_t need = (n + 127) / 128, cap = (int64_t)he->num_sms * 16;
+    int grid = (int)(need < cap ? need : cap);
+    double crot = cos(rotpos), srot = sin(rotpos);
+    FIELD_DISPATCH(field_cart_kernel, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0,
+                   hs->fac, n, x, y, z, crot, srot, out8);
+    BFE_LAUNCH_CHECK("field_cart_kernel");
+    return BFE_OK;
+}
+
+extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, double rotfreq,
+                            double* state6, double* traj, int64_t traj_stride, int apse, int ap_max,
+                            int32_t* nsteps_out, void* stream_) {
+    if (!he || !hs || norbit < 0 || nint < 1) return BFE_ERR_ARG;
+    if (!he->contracted || !hs->contracted) return BFE_ERR_STATE;
+    if (norbit == 0) return BFE_OK;
+    if (!state6) return BFE_ERR_ARG;
+    if (traj && traj_stride < 1) return BFE_ERR_ARG;
+    if (ap_max < 1) ap_max = 1;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int grid = (int)((norbit + 127) / 128);
+    FIELD_DISPATCH(leapfrog_kernel, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0,
+                   hs->fac, norbit, nint, dt, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
+    BFE_LAUNCH_CHECK("leapfrog_kernel");
+    return BFE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// library-wide helpers
+// ---------------------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+static thread_local char g_cuda_err[256] = "";
+
+extern "C" void bfe_count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
+extern "C" uint64_t bfe_launch_count(void) { return g_launches.load(); }
+extern "C" int bfe_version(void) { return 100; }
+
+void bfe_set_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+}
+extern "C" const char* bfe_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" const char* bfe_error_string(int code) {
+    switch (code) {
+        case BFE_OK: return "ok";
+        case BFE_ERR_ARG: return "invalid argument";
+        case BFE_ERR_CUDA: return "CUDA error (see bfe_last_cuda_error)";
+        case BFE_ERR_UNSUPPORTED: return "basis size or mapping not supported by the compiled kernels";
+        case BFE_ERR_STATE: return "handle holds no coefficient contraction (call bfe_*_contract first)";
+        default: return "unknown error";
+    }
+}

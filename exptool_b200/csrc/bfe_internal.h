@@ -1,0 +1,81 @@
+// bfe_internal.h -- handle layouts and launch helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bfe.h"
+
+// Geometry passed by value to kernels (eof.set_table_params, eof.py:316-347).
+struct EofGeom {
+    int mmax, norder, numx, numy, cmap;
+    int nnode;          // (numx+1)*(numy+1)
+    int ny1;            // numy+1 : node = ix*ny1 + iy
+    double xmin, dx, ymin, dy, ascale, hscale;
+    double inv_dx, inv_dy_unused;
+};
+
+// halo_methods.init_table:178-220 geometry
+struct SlGeom {
+    int lmax, nmax, numr, cmap;
+    int nrow;           // (lmax+1)^2
+    int ln;             // (lmax+1)*nmax
+    double scale, xi0, dxi;
+};
+
+struct bfe_eof {
+    bfe_eof_params par;
+    EofGeom g;
+    int device;
+    int num_sms;
+    // accumulate table: node-major [nnode][nch_pad], channels = cos (m*norder+n) then sin ((m-1)*norder+n, m>=1)
+    int nch, nch_pad;
+    double* t_acc;
+    // reference-layout copies of the six force tables [6][m][n][node] (potC,rfC,zfC,potS,rfS,zfS)
+    double* t_force;
+    size_t tab_elems;    // (mmax+1)*norder*nnode
+    // contracted grids G[node][m][6] (pc,ps,rc,rs,zc,zs)
+    double* g_con;
+    int gstride;         // 6*(mmax+1)
+    int contracted;
+    // accumulate workspace
+    double* partial;     // [max_ctas][nch_pad]
+    unsigned int* counter;
+    int max_ctas;
+    // cell-sorted accumulate workspace (grown on demand)
+    int64_t sort_cap;
+    void* sort_ws;
+};
+
+struct bfe_sl {
+    bfe_sl_params par;
+    SlGeom g;
+    int device;
+    int num_sms;
+    double* e_node;      // node-major [numr][(lmax+1)*nmax], pre-divided by sqrt(ev)
+    double* xi;          // [numr]
+    double* p0;          // [numr]
+    double* d0;          // [numr]
+    double* fac;         // factorial_return [(lmax+1)*(lmax+1)]
+    double fac_host[(BFE_MAX_LMAX + 1) * (BFE_MAX_LMAX + 1)];
+    double* a_con;       // contracted rows, node-major [numr][kpad]
+    int kpad;
+    int contracted;
+    double* partial;     // [max_ctas][nrow*nmax]
+    unsigned int* counter;
+    int max_ctas;
+};
+
+extern "C" void bfe_count_launch(int n);
+void bfe_set_cuda_error(cudaError_t e, const char* where);
+
+#define BFE_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) { bfe_set_cuda_error(_e, #call); return BFE_ERR_CUDA; } \
+    } while (0)
+
+#define BFE_LAUNCH_CHECK(where)                                         \
+    do {                                                                \
+        cudaError_t _e = cudaGetLastError();                            \
+        if (_e != cudaSuccess) { bfe_set_cuda_error(_e, where); return BFE_ERR_CUDA; } \
+        bfe_count_launch(1);                                            \
+    } while (0)

@@ -1,0 +1,360 @@
+// bfe_sl.cu -- spherical Sturm-Liouville (halo basis) kernels.
+//
+//   sl_relayout_kernel   : eftable[l][n][i] -> node-major e_node[i][l][n] / sqrt(ev[l][n])
+//   sl_accumulate_kernel : spheresl.compute_coefficients_solitary (spheresl.py:567-656)
+//   sl_contract_kernel   : A[i][k] = sum_n expcoef[k,n] e_node[i][l(k)][n]
+//   sl_force_kernel      : spheresl.all_eval_particles (spheresl.py:1240-1362), potential part
+//   sl_points_kernel     : spheresl.force_eval / all_eval (spheresl.py:1107-1234 / 987-1102)
+#include "bfe_device.cuh"
+#include <math.h>
+
+__global__ void sl_relayout_kernel(SlGeom g, const double* __restrict__ ev, const double* __restrict__ ef,
+                                   double* __restrict__ e_node) {
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;          // c = l*nmax+n
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, i = i0 + threadIdx.x;
+        double v = 0.0;
+        if (c < g.ln && i < g.numr) v = ef[(size_t)c * g.numr + i] / sqrt(ev[c]);   // spheresl.py:332
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int i = i0 + r, c = c0 + threadIdx.x;
+        if (i < g.numr && c < g.ln) e_node[(size_t)i * g.ln + c] = tile[threadIdx.x][r];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// accumulate, direct formulation.
+//
+// Thread (l,n) owns the 2l+1 coefficient rows of its radial function in registers.
+// Phase A (thread per particle): r, cos(theta), P_l^m recurrence, cos/sin(m phi)
+// recurrence, radial bin; writes w_k = -4pi m f_lm P_lm {1|cos|sin} P0 for all
+// (lmax+1)^2 rows k and (i, x1, x2) to shared memory.  Phase B (thread per (l,n)):
+// e = x1 E[i][l][n] + x2 E[i+1][l][n] (coalesced over n within l), acc[k] += w_k e.
+// ---------------------------------------------------------------------------
+template <int LCAP, int TILE>
+__global__ void __launch_bounds__(256)
+sl_accumulate_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ xi,
+                     const double* __restrict__ p0tab, const double* __restrict__ fac,
+                     int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                     const double* __restrict__ z, const double* __restrict__ mass, int no_odd,
+                     double* __restrict__ partial, unsigned int* __restrict__ counter,
+                     double* __restrict__ expcoef) {
+    constexpr int NROW = (LCAP + 1) * (LCAP + 1);
+    extern __shared__ double s_dyn[];
+    double* s_w = s_dyn;                          // [nrow][TILE]
+    double* s_x1 = s_w + (size_t)g.nrow * TILE;   // [TILE]
+    double* s_x2 = s_x1 + TILE;                   // [TILE]
+    int* s_i = reinterpret_cast<int*>(s_x2 + TILE);
+    __shared__ bool s_last;
+    (void)NROW;
+
+    const int tid = threadIdx.x;
+    const int my_l = tid / g.nmax;                // thread -> (l, n)
+    const bool active = tid < g.ln && !(no_odd && (my_l & 1));
+    double acc[2 * LCAP + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * LCAP + 1; ++k) acc[k] = 0.0;
+
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tid < TILE) {
+            int64_t ip = tile * TILE + tid;
+            double px = 0.0, py = 0.0, pz = 0.0, pm = 0.0;
+            if (ip < n) { px = __ldg(x + ip); py = __ldg(y + ip); pz = __ldg(z + ip); pm = __ldg(mass + ip); }
+            double r2 = BFE_ADD(BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py)), BFE_MUL(pz, pz));   // spheresl.py:610
+            double r = fmax(sqrt(r2), 1.0e-10);                   // 611
+            double costh = BFE_DIV(pz, r);                        // 612
+            double c1, s1;
+            bfe_cossin_phi(px, py, c1, s1);                       // 613
+            LegTable<LCAP> P;
+            bfe_legendre<LCAP>(g.lmax, costh, P);                 // 618
+            SlBin b = bfe_sl_bin(g, xi, r);                       // 623 -> 309-328
+            double P0 = b.x1 * __ldg(p0tab + b.i) + b.x2 * __ldg(p0tab + b.i + 1);
+            double W = BFE_FOURPI_NEG * pm * P0;
+            s_i[tid] = b.i; s_x1[tid] = b.x1; s_x2[tid] = b.x2;
+            // cos/sin(m phi) for m = 0..lmax
+            double cm[LCAP + 1], sm[LCAP + 1];
+            cm[0] = 1.0; sm[0] = 0.0;
+#pragma unroll
+            for (int m = 1; m <= LCAP; ++m) {
+                cm[m] = cm[m - 1] * c1 - sm[m - 1] * s1;
+                sm[m] = sm[m - 1] * c1 + cm[m - 1] * s1;
+            }
+#pragma unroll
+            for (int l = 0; l <= LCAP; ++l) {
+                if (l <= g.lmax) {
+                    const int k0 = l * l;
+                    s_w[(size_t)k0 * TILE + tid] = W * __ldg(fac + l * (g.lmax + 1)) * P.p[l][0];
+#pragma unroll
+                    for (int m = 1; m <= l; ++m) {
+                        double fw = W * __ldg(fac + l * (g.lmax + 1) + m) * P.p[l][m];
+                        s_w[(size_t)(k0 + 2 * m - 1) * TILE + tid] = fw * cm[m];
+                        s_w[(size_t)(k0 + 2 * m) * TILE + tid] = fw * sm[m];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (active) {
+            const double* ecol = e_node + tid;       // tid == l*nmax + n
+            const double* wrow = s_w + (size_t)(my_l * my_l) * TILE;
+#pragma unroll 2
+            for (int p = 0; p < TILE; ++p) {
+                const double* e = ecol + (size_t)s_i[p] * g.ln;
+                double ev = s_x1[p] * __ldg(e) + s_x2[p] * __ldg(e + g.ln);
+#pragma unroll
+                for (int k = 0; k < 2 * LCAP + 1; ++k)
+                    if (k < 2 * my_l + 1) acc[k] = fma(wrow[(size_t)k * TILE + p], ev, acc[k]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // partial layout: [cta][k][n] with k over nrow rows
+    const int ncoef = g.nrow * g.nmax;
+    if (tid < g.ln) {
+        const int nn = tid - my_l * g.nmax;
+#pragma unroll
+        for (int k = 0; k < 2 * LCAP + 1; ++k)
+            if (k < 2 * my_l + 1)
+                partial[(size_t)blockIdx.x * ncoef + (size_t)(my_l * my_l + k) * g.nmax + nn] = acc[k];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int done = atomicAdd(counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int c = tid; c < ncoef; c += blockDim.x) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * ncoef + c);
+            expcoef[c] = s;
+        }
+        if (tid == 0) *counter = 0u;
+    }
+}
+
+// A[i][k] = sum_{n<nuse} c[k][n] * e_node[i][l(k)][n]; rows outside the l window are zero
+__global__ void sl_contract_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ expcoef,
+                                   int l1, int l2, int nuse, int no_odd, double* __restrict__ A, int kpad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (i >= g.numr) return;
+    int l = (int)sqrt((double)k);
+    while ((l + 1) * (l + 1) <= k) ++l;
+    while (l * l > k) --l;
+    double s = 0.0;
+    bool use = (l == 0) || ((l >= l1) && (l <= l2) && !(no_odd && (l & 1)));
+    if (k < g.nrow && use) {
+        const double* e = e_node + (size_t)i * g.ln + l * g.nmax;
+        const double* c = expcoef + (size_t)k * g.nmax;
+        const int nn = nuse < g.nmax ? nuse : g.nmax;
+        for (int q = 0; q < nn; ++q) s = fma(__ldg(c + q), __ldg(e + q), s);
+    }
+    A[(size_t)i * kpad + k] = s;
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+sl_force_kernel(SlGeom g, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+                const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
+                const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                double* __restrict__ pot0, double* __restrict__ pot1, double* __restrict__ potr,
+                double* __restrict__ pott, double* __restrict__ potp, double* __restrict__ rr) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        double rxy2 = BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py));
+        double r = sqrt(BFE_ADD(rxy2, BFE_MUL(pz, pz)));          // spheresl.py:1257 (no epsilon)
+        double rxy = sqrt(rxy2);                                  // 1259
+        double costh = BFE_DIV(pz, r);                            // 1265
+        double c1, s1;
+        bfe_cossin_phi(px, py, c1, s1);                           // 1261
+        SlBin b = bfe_sl_bin(g, xi, r);
+        SlField f = bfe_sl_eval<LCAP>(g, A, kpad, p0tab, fac, b, costh, c1, s1, false);
+        pot0[i] = f.pot0; pot1[i] = f.pot1; potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; rr[i] = rxy;
+    }
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+sl_points_kernel(SlGeom g, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+                 const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
+                 const double* __restrict__ r, const double* __restrict__ costh, const double* __restrict__ phi,
+                 int trig_index_l,
+                 double* __restrict__ potr, double* __restrict__ pott, double* __restrict__ potp,
+                 double* __restrict__ pot1, double* __restrict__ pot0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double c1, s1;
+        sincos(__ldg(phi + i), &s1, &c1);
+        SlBin b = bfe_sl_bin(g, xi, __ldg(r + i));
+        SlField f = bfe_sl_eval<LCAP>(g, A, kpad, p0tab, fac, b, __ldg(costh + i), c1, s1, trig_index_l != 0);
+        potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; pot1[i] = f.pot1; pot0[i] = f.pot0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int sl_grid_for(int64_t n, int block, int num_sms, int per_sm) {
+    int64_t need = (n + block - 1) / block;
+    int64_t cap = (int64_t)num_sms * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+template <int LCAP, int TILE>
+static int sl_acc_launch(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                         const double* mass, int no_odd, double* expcoef, cudaStream_t stream) {
+    int block = (h->g.ln + 31) / 32 * 32;
+    if (block < TILE) block = TILE;
+    if (block > 256) return BFE_ERR_UNSUPPORTED;
+    size_t smem = ((size_t)h->g.nrow * TILE + 2 * TILE) * sizeof(double) + TILE * sizeof(int);
+    auto kern = sl_accumulate_kernel<LCAP, TILE>;
+    BFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t ntiles = (n + TILE - 1) / TILE;
+    int grid = (int)(ntiles < h->max_ctas ? (ntiles < 1 ? 1 : ntiles) : h->max_ctas);
+    kern<<<grid, block, smem, stream>>>(h->g, h->e_node, h->xi, h->p0, h->fac, n, x, y, z, mass, no_odd,
+                                        h->partial, h->counter, expcoef);
+    BFE_LAUNCH_CHECK("sl_accumulate_kernel");
+    return BFE_OK;
+}
+
+extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, const double* eftable,
+                             const double* xi, const double* p0, const double* d0, void* stream_, bfe_sl** out) {
+    if (!p || !out || !evtable || !eftable || !xi || !p0) return BFE_ERR_ARG;
+    if (p->lmax < 0 || p->lmax > BFE_MAX_LMAX || p->nmax < 1 || p->numr < 3) return BFE_ERR_ARG;
+    if (p->cmap != 0 && p->cmap != 1) return BFE_ERR_UNSUPPORTED;   // cmap=2 is broken in the reference
+    cudaStream_t stream = (cudaStream_t)stream_;
+    bfe_sl* h = new bfe_sl();
+    h->par = *p;
+    SlGeom& g = h->g;
+    g.lmax = p->lmax; g.nmax = p->nmax; g.numr = p->numr; g.cmap = p->cmap; g.scale = p->scale;
+    g.nrow = (p->lmax + 1) * (p->lmax + 1);
+    g.ln = (p->lmax + 1) * p->nmax;
+    if (g.ln > 256) { delete h; return BFE_ERR_UNSUPPORTED; }
+    BFE_CUDA(cudaGetDevice(&h->device));
+    BFE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    double xi01[2];
+    BFE_CUDA(cudaMemcpyAsync(xi01, xi, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    BFE_CUDA(cudaStreamSynchronize(stream));
+    g.xi0 = xi01[0];                        // np.min(xi), spheresl.py:319
+    g.dxi = xi01[1] - xi01[0];              // xi[1]-xi[0], spheresl.py:317
+    h->kpad = (g.nrow + 1) / 2 * 2;
+    h->contracted = 0;
+    h->max_ctas = h->num_sms * 8;
+    size_t nr = (size_t)p->numr;
+    BFE_CUDA(cudaMalloc(&h->e_node, nr * g.ln * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->xi, nr * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->p0, nr * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->d0, nr * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->fac, sizeof(double) * (p->lmax + 1) * (p->lmax + 1)));
+    BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->counter, sizeof(unsigned int)));
+    BFE_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream));
+    BFE_CUDA(cudaMemsetAsync(h->a_con, 0, nr * h->kpad * sizeof(double), stream));
+    BFE_CUDA(cudaMemcpyAsync(h->xi, xi, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    BFE_CUDA(cudaMemcpyAsync(h->p0, p0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if (d0) BFE_CUDA(cudaMemcpyAsync(h->d0, d0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    // factorial_return, spheresl.py:823-863 (lgamma for scipy.special.gammaln)
+    for (int l = 0; l <= p->lmax; ++l)
+        for (int m = 0; m <= p->lmax; ++m) {
+            double v = 0.0;
+            if (m <= l) {
+                v = sqrt((0.5 * l + 0.25) / M_PI * exp(lgamma(1.0 + l - m) - lgamma(1.0 + l + m)));
+                if (m != 0) v *= sqrt(2.0);
+            }
+            h->fac_host[l * (p->lmax + 1) + m] = v;
+        }
+    BFE_CUDA(cudaMemcpyAsync(h->fac, h->fac_host, sizeof(double) * (p->lmax + 1) * (p->lmax + 1),
+                             cudaMemcpyHostToDevice, stream));
+    dim3 blk(32, 8), grd((p->numr + 31) / 32, (g.ln + 31) / 32);
+    sl_relayout_kernel<<<grd, blk, 0, stream>>>(g, evtable, eftable, h->e_node);
+    BFE_LAUNCH_CHECK("sl_relayout_kernel");
+    BFE_CUDA(cudaStreamSynchronize(stream));      // fac_host is pageable; keep create() self-contained
+    *out = h;
+    return BFE_OK;
+}
+
+extern "C" void bfe_sl_destroy(bfe_sl* h) {
+    if (!h) return;
+    cudaFree(h->e_node); cudaFree(h->xi); cudaFree(h->p0); cudaFree(h->d0); cudaFree(h->fac);
+    cudaFree(h->a_con); cudaFree(h->partial); cudaFree(h->counter);
+    delete h;
+}
+
+extern "C" int bfe_sl_accumulate(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                                 const double* mass, int no_odd, double* expcoef, void* stream_) {
+    if (!h || n < 0 || !expcoef) return BFE_ERR_ARG;
+    if (n > 0 && (!x || !y || !z || !mass)) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (h->g.lmax <= 4) return sl_acc_launch<4, 128>(h, n, x, y, z, mass, no_odd, expcoef, stream);
+    if (h->g.lmax <= 6) return sl_acc_launch<6, 128>(h, n, x, y, z, mass, no_odd, expcoef, stream);
+    return sl_acc_launch<BFE_MAX_LMAX, 32>(h, n, x, y, z, mass, no_odd, expcoef, stream);
+}
+
+extern "C" int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2, int nuse, int no_odd,
+                               void* stream_) {
+    if (!h || !expcoef) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nuse < 0) nuse = 0;
+    dim3 grd((h->g.numr + 127) / 128, h->kpad);
+    sl_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->e_node, expcoef, l1, l2, nuse, no_odd, h->a_con, h->kpad);
+    BFE_LAUNCH_CHECK("sl_contract_kernel");
+    h->contracted = 1;
+    return BFE_OK;
+}
+
+#define SL_DISPATCH(KERN, ...)                                                                   \
+    do {                                                                                         \
+        if (h->g.lmax <= 4)      KERN<4><<<grid, 128, 0, stream>>>(__VA_ARGS__);                  \
+        else if (h->g.lmax <= 6) KERN<6><<<grid, 128, 0, stream>>>(__VA_ARGS__);                  \
+        else                     KERN<BFE_MAX_LMAX><<<grid, 128, 0, stream>>>(__VA_ARGS__);       \
+    } while (0)
+
+extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                                       double* pot0, double* pot1, double* potr, double* pott, double* potp,
+                                       double* rr, void* stream_) {
+    if (!h || n < 0) return BFE_ERR_ARG;
+    if (!h->contracted) return BFE_ERR_STATE;
+    if (n == 0) return BFE_OK;
+    if (!x || !y || !z || !pot0 || !pot1 || !potr || !pott || !potp || !rr) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    SL_DISPATCH(sl_force_kernel, h->g, h->a_con, h->kpad, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott,
+                potp, rr);
+    BFE_LAUNCH_CHECK("sl_force_kernel");
+    return BFE_OK;
+}
+
+extern "C" int bfe_sl_force(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                            const double* expcoef, int l1, int l2, int no_odd,
+                            double* pot0, double* pot1, double* potr, double* pott, double* potp, double* rr,
+                            void* stream) {
+    if (!h) return BFE_ERR_ARG;
+    int rc = bfe_sl_contract(h, expcoef, l1, l2, h->g.nmax, no_odd, stream);
+    if (rc != BFE_OK) return rc;
+    return bfe_sl_force_contracted(h, n, x, y, z, pot0, pot1, potr, pott, potp, rr, stream);
+}
+
+extern "C" int bfe_sl_force_eval_points(bfe_sl* h, int64_t n, const double* r, const double* costh,
+                                        const double* phi, int trig_index_l,
+                                        double* potr, double* pott, double* potp, double* pot1, double* pot0,
+                                        void* stream_) {
+    if (!h || n < 0) return BFE_ERR_ARG;
+    if (!h->contracted) return BFE_ERR_STATE;
+    if (n == 0) return BFE_OK;
+    if (!r || !costh || !phi || !potr || !pott || !potp || !pot1 || !pot0) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    SL_DISPATCH(sl_points_kernel, h->g, h->a_con, h->kpad, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l,
+                potr, pott, potp, pot1, pot0);
+    BFE_LAUNCH_CHECK("sl_points_kernel");
+    return BFE_OK;
+}

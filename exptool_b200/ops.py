@@ -1,0 +1,244 @@
+"""
+ops.py -- device-tensor operators over the C ABI (include/bfe.h).
+
+PyTorch supplies device memory, the current CUDA stream and (in parallel.py)
+torch.distributed; all arithmetic is in libbfe.so.  Inputs are FP64 CUDA
+tensors (SoA particle arrays); NumPy arrays / CPU tensors are copied to the
+current device.  Nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('exptool_b200 needs a CUDA device (sm_100a); there is no CPU path')
+
+
+def dev(a, device=None):
+    """FP64 contiguous CUDA tensor from tensor / ndarray / scalar (no copy if already so)."""
+    _require_cuda()
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+    if t.dtype != torch.float64 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float64).contiguous()
+    return t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(_lib.load().bfe_launch_count())
+
+
+class EOFTables(object):
+    """
+    Device-resident EOF basis (eof.parse_eof tables + eof.set_table_params geometry).
+
+    tables: potC, rforceC, zforceC, potS, rforceS, zforceS, each
+    (mmax+1, norder, numx+1, numy+1) as in eof.py:224-313.  rforce*/zforce* may be
+    None if only accumulation is needed.
+    """
+
+    def __init__(self, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap,
+                 rforceC=None, zforceC=None, rforceS=None, zforceS=None, dens=0):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.mmax, self.norder, self.numx, self.numy = int(mmax), int(norder), int(numx), int(numy)
+        self.cmap = int(cmap)
+        shape = (self.mmax + 1, self.norder, self.numx + 1, self.numy + 1)
+        tabs = []
+        for t in (potC, rforceC, zforceC, potS, rforceS, zforceS):
+            if t is None:
+                tabs.append(None)
+                continue
+            if tuple(t.shape) != shape:
+                if t.shape[0] < shape[0] or t.shape[1] < shape[1] or tuple(t.shape[2:]) != shape[2:]:
+                    raise ValueError('EOF table shape %s does not match %s' % (tuple(t.shape), shape))
+                t = t[:shape[0], :shape[1]]            # MMAX/NMAX slicing as eof.force_eval, eof.py:784-793
+            tabs.append(dev(t))
+        self.params = _lib.EofParams(self.mmax, self.norder, self.numx, self.numy, self.cmap, int(dens),
+                                     float(XMIN), float(dX), float(YMIN), float(dY), float(ascale), float(hscale))
+        h = C.c_void_p()
+        _lib.check(self.lib.bfe_eof_create(C.byref(self.params), *[_ptr(t) for t in tabs], _stream(), C.byref(h)))
+        torch.cuda.current_stream().synchronize()   # staging tensors may now be freed
+        self.h = h
+        self.has_force = all(t is not None for t in tabs)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.bfe_eof_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def accumulate(self, x, y, z, m):
+        """eof.accumulate (eof.py:492-551) -> (cos, sin) device tensors (mmax+1, norder)."""
+        x, y, z, m = dev(x), dev(y), dev(z), dev(m)
+        n = x.numel()
+        if not (y.numel() == n and z.numel() == n and m.numel() == n):
+            raise ValueError('particle arrays differ in length')
+        out = torch.empty((2, self.mmax + 1, self.norder), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_eof_accumulate(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(m),
+                                               _ptr(out[0]), _ptr(out[1]), _stream()))
+        return out[0], out[1]
+
+    def contract(self, cosc, sinc, m1=0, m2=1000, nuse=None, no_odd=False):
+        cosc, sinc = self._coef(cosc), self._coef(sinc)
+        nuse = self.norder if nuse is None else int(nuse)
+        _lib.check(self.lib.bfe_eof_contract(self.h, _ptr(cosc), _ptr(sinc), int(m1), int(min(m2, self.mmax)),
+                                             nuse, int(bool(no_odd)), _stream()))
+
+    def _coef(self, c):
+        c = dev(c)
+        if tuple(c.shape) != (self.mmax + 1, self.norder):
+            if c.dim() != 2 or c.shape[0] < self.mmax + 1 or c.shape[1] < self.norder:
+                raise ValueError('coefficient shape %s, expected at least %s' %
+                                 (tuple(c.shape), (self.mmax + 1, self.norder)))
+            c = c[:self.mmax + 1, :self.norder].contiguous()
+        return c
+
+    def force(self, x, y, z):
+        """eof.accumulated_eval_particles outputs p0, p, fr, fp, fz, R (uses the held contraction)."""
+        x, y, z = dev(x), dev(y), dev(z)
+        n = x.numel()
+        out = torch.empty((6, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_eof_force_contracted(self.h, n, _ptr(x), _ptr(y), _ptr(z),
+                                                     *[_ptr(out[i]) for i in range(6)], _stream()))
+        return out
+
+    def force_eval_points(self, r, z, phi):
+        """eof.force_eval outputs fr, fp, fz, p (incl. m=0), p0 at cylindrical points."""
+        r, z, phi = dev(r), dev(z), dev(phi)
+        n = r.numel()
+        out = torch.empty((5, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_eof_force_eval_points(self.h, n, _ptr(r), _ptr(z), _ptr(phi),
+                                                      *[_ptr(out[i]) for i in range(5)], _stream()))
+        return out
+
+
+class SLTables(object):
+    """Device-resident SL basis (halo_methods.read_cached_table + init_table)."""
+
+    def __init__(self, lmax, nmax, numr, cmap, scale, evtable, eftable, xi, p0, d0=None):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.lmax, self.nmax, self.numr, self.cmap = int(lmax), int(nmax), int(numr), int(cmap)
+        self.scale = float(scale)
+        ev = np.asarray(evtable)[:self.lmax + 1, :self.nmax] if not isinstance(evtable, torch.Tensor) \
+            else evtable[:self.lmax + 1, :self.nmax]
+        ef = np.asarray(eftable)[:self.lmax + 1, :self.nmax] if not isinstance(eftable, torch.Tensor) \
+            else eftable[:self.lmax + 1, :self.nmax]
+        ev, ef, xi, p0 = dev(ev), dev(ef), dev(xi), dev(p0)
+        d0 = dev(d0) if d0 is not None else None
+        if tuple(ef.shape) != (self.lmax + 1, self.nmax, self.numr) or xi.numel() != self.numr or p0.numel() != self.numr:
+            raise ValueError('SL table shapes do not match (lmax, nmax, numr)')
+        self.params = _lib.SlParams(self.lmax, self.nmax, self.numr, self.cmap, self.scale)
+        h = C.c_void_p()
+        _lib.check(self.lib.bfe_sl_create(C.byref(self.params), _ptr(ev), _ptr(ef), _ptr(xi), _ptr(p0), _ptr(d0),
+                                          _stream(), C.byref(h)))
+        torch.cuda.current_stream().synchronize()
+        self.h = h
+        self.nrow = (self.lmax + 1) ** 2
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.bfe_sl_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def accumulate(self, x, y, z, m, no_odd=False):
+        """spheresl.compute_coefficients_solitary (spheresl.py:567-656) -> expcoef ((lmax+1)^2, nmax)."""
+        x, y, z, m = dev(x), dev(y), dev(z), dev(m)
+        n = x.numel()
+        if not (y.numel() == n and z.numel() == n and m.numel() == n):
+            raise ValueError('particle arrays differ in length')
+        out = torch.empty((self.nrow, self.nmax), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_sl_accumulate(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(m), int(bool(no_odd)),
+                                              _ptr(out), _stream()))
+        return out
+
+    def _coef(self, c):
+        c = dev(c)
+        if tuple(c.shape) != (self.nrow, self.nmax):
+            if c.dim() != 2 or c.shape[0] < self.nrow or c.shape[1] < self.nmax:
+                raise ValueError('expcoef shape %s, expected at least %s' % (tuple(c.shape), (self.nrow, self.nmax)))
+            c = c[:self.nrow, :self.nmax].contiguous()
+        return c
+
+    def contract(self, expcoef, l1=-1000, l2=1000, nuse=None, no_odd=False):
+        c = self._coef(expcoef)
+        nuse = self.nmax if nuse is None else int(nuse)
+        l1 = max(int(l1), 0)
+        l2 = min(int(l2), self.lmax)
+        _lib.check(self.lib.bfe_sl_contract(self.h, _ptr(c), l1, l2, nuse, int(bool(no_odd)), _stream()))
+
+    def force(self, x, y, z):
+        """spheresl.all_eval_particles outputs pot0, pot1, potr, pott, potp, rr."""
+        x, y, z = dev(x), dev(y), dev(z)
+        n = x.numel()
+        out = torch.empty((6, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_sl_force_contracted(self.h, n, _ptr(x), _ptr(y), _ptr(z),
+                                                    *[_ptr(out[i]) for i in range(6)], _stream()))
+        return out
+
+    def force_eval_points(self, r, costh, phi, trig_index_l=True):
+        """spheresl.force_eval (trig_index_l) / all_eval outputs potr, pott, potp, pot1, pot0."""
+        r, costh, phi = dev(r), dev(costh), dev(phi)
+        n = r.numel()
+        out = torch.empty((5, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_sl_force_eval_points(self.h, n, _ptr(r), _ptr(costh), _ptr(phi),
+                                                     int(bool(trig_index_l)), *[_ptr(out[i]) for i in range(5)],
+                                                     _stream()))
+        return out
+
+
+def field_force_cart(eof_tables, sl_tables, x, y, z, rotpos=0.0):
+    """Fields.return_forces_cart (potential.py:445-497) at n points -> (8, n) device tensor."""
+    x, y, z = dev(x), dev(y), dev(z)
+    n = x.numel()
+    out = torch.empty((8, n), dtype=torch.float64, device=x.device)
+    _lib.check(eof_tables.lib.bfe_field_force_cart(eof_tables.h, sl_tables.h, n, _ptr(x), _ptr(y), _ptr(z),
+                                                   float(rotpos), _ptr(out), _stream()))
+    return out
+
+
+def leapfrog(eof_tables, sl_tables, pos0, vel0, nint, dt, rotfreq=0.0, traj_stride=0, apse=False, ap_max=1000):
+    """
+    integrate.leapfrog_integrate (integrate.py:53-190) for a batch of orbits.
+    pos0, vel0: (3, norbit).  Returns (state6 (6, norbit) at the last step,
+    traj (nsave, 10, norbit) or None, nsteps (norbit,) int32).
+    """
+    pos0, vel0 = dev(pos0), dev(vel0)
+    pos0 = pos0.reshape(3, -1)
+    vel0 = vel0.reshape(3, -1)
+    norb = pos0.shape[1]
+    state = torch.cat([pos0, vel0], dim=0).contiguous()
+    traj = None
+    if traj_stride and traj_stride > 0:
+        nsave = (int(nint) - 1) // int(traj_stride) + 1
+        traj = torch.zeros((nsave, 10, norb), dtype=torch.float64, device=state.device)
+    nsteps = torch.empty((norb,), dtype=torch.int32, device=state.device)
+    _lib.check(eof_tables.lib.bfe_leapfrog(eof_tables.h, sl_tables.h, norb, int(nint), float(dt), float(rotfreq),
+                                           _ptr(state), _ptr(traj), int(traj_stride) if traj is not None else 1,
+                                           int(bool(apse)), int(ap_max), _ptr(nsteps), _stream()))
+    return state, traj, nsteps

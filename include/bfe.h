@@ -1,0 +1,169 @@
+/*
+ * bfe.h -- C ABI of libbfe.so: B200 (sm_100a) kernels for exptool's
+ * basis-function-expansion hot path.
+ *
+ * The reference (michael-petersen/exptool) is pure Python and has no FFI for this
+ * path; the only native code, exptool/basis/accumulate_c/
+ * accumulate.h:3-13, is a dormant CPython module of five scalar coordinate maps.
+ * This header therefore DEFINES the boundary a maintainer binds with ctypes
+ * (see INTEGRATION.md); each entry point names the reference function it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all arrays are FP64, particle data is SoA, contiguous;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *     synchronises the device unless stated;
+ *   - return value: 0 = ok, negative = error (bfe_error_string());
+ *   - the caller owns every buffer; a handle owns only its re-laid-out tables and
+ *     workspaces.  A handle must not be used from two streams at once.
+ */
+#ifndef BFE_H
+#define BFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFE_OK                 0
+#define BFE_ERR_ARG          (-1)
+#define BFE_ERR_CUDA         (-2)
+#define BFE_ERR_UNSUPPORTED  (-3)
+#define BFE_ERR_STATE        (-4)
+
+/* limits of the compiled kernels */
+#define BFE_MAX_MMAX   16
+#define BFE_MAX_LMAX   16
+
+typedef struct bfe_eof_params {
+    int32_t mmax, norder, numx, numy, cmap, dens;   /* eof.eof_params, eof.py:98-200           */
+    double  xmin, dx, ymin, dy;                     /* eof.set_table_params, eof.py:316-347     */
+    double  ascale, hscale;
+} bfe_eof_params;
+
+typedef struct bfe_sl_params {
+    int32_t lmax, nmax, numr, cmap;                 /* halo_methods.read_cached_table:128-140   */
+    double  scale;
+} bfe_sl_params;
+
+typedef struct bfe_eof bfe_eof;     /* EOF tables on the device                                */
+typedef struct bfe_sl  bfe_sl;      /* SL tables on the device                                 */
+
+const char* bfe_error_string(int code);
+const char* bfe_last_cuda_error(void);
+int  bfe_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t bfe_launch_count(void);
+
+/* ---------------------------------------------------------------- EOF (disc) ---------------- */
+
+/* Tables in the reference layout [m][n][ix][iy] (eof.parse_eof, eof.py:224-313), each
+ * (mmax+1)*norder*(numx+1)*(numy+1) doubles.  Copies / re-lays them out on the device. */
+int bfe_eof_create(const bfe_eof_params* p,
+                   const double* potC, const double* rforceC, const double* zforceC,
+                   const double* potS, const double* rforceS, const double* zforceS,
+                   void* stream, bfe_eof** out);
+void bfe_eof_destroy(bfe_eof* h);
+
+/* eof.accumulate (eof.py:492-551) for n particles:
+ *   cos_out[m*norder+n] = sum_p -4pi cos(m phi_p) m_p interp_p(potC[m,n]),  sin_out likewise.
+ * cos_out/sin_out: (mmax+1)*norder doubles each, overwritten. */
+int bfe_eof_accumulate(bfe_eof* h, int64_t n,
+                       const double* x, const double* y, const double* z, const double* mass,
+                       double* cos_out, double* sin_out, void* stream);
+
+/* Contract the tables with a coefficient set:  G_f[m,trig,node] = sum_{n<nuse} coef[m,n] T_f[m,n,node]
+ * for m1 <= m <= min(m2, muse), skipping odd m if no_odd.  Must precede the *_contracted calls,
+ * bfe_field_force_cart and bfe_leapfrog.  cosc/sinc: (mmax+1)*norder doubles. */
+int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* sinc,
+                     int m1, int m2, int nuse, int no_odd, void* stream);
+
+/* eof.accumulated_eval_particles (eof.py:989-1144): p0, p (m>=1 only), fr, fp, fz, R per particle,
+ * R = sqrt(x^2+y^2+1e-10).  Uses the contraction held by the handle. */
+int bfe_eof_force_contracted(bfe_eof* h, int64_t n,
+                             const double* x, const double* y, const double* z,
+                             double* p0, double* p, double* fr, double* fp, double* fz, double* R,
+                             void* stream);
+
+/* contract + evaluate in one call (the drop-in for eof.compute_forces, eof.py:1263-1317) */
+int bfe_eof_force(bfe_eof* h, int64_t n,
+                  const double* x, const double* y, const double* z,
+                  const double* cosc, const double* sinc, int m1, int m2, int nuse, int no_odd,
+                  double* p0, double* p, double* fr, double* fp, double* fz, double* R,
+                  void* stream);
+
+/* eof.force_eval (eof.py:756-870) at n cylindrical points (r, z, phi given directly):
+ * fr (incl. m=0), fp, fz (incl. m=0), p (incl. m=0), p0.  Uses the held contraction. */
+int bfe_eof_force_eval_points(bfe_eof* h, int64_t n,
+                              const double* r, const double* z, const double* phi,
+                              double* fr, double* fp, double* fz, double* p, double* p0,
+                              void* stream);
+
+/* ---------------------------------------------------------------- SL (halo) ----------------- */
+
+/* evtable (lmax+1)*nmax, eftable (lmax+1)*nmax*numr (halo_methods.read_cached_table:96-169);
+ * xi, p0, d0: numr each (halo_methods.init_table:178-220). */
+int bfe_sl_create(const bfe_sl_params* p, const double* evtable, const double* eftable,
+                  const double* xi, const double* p0, const double* d0,
+                  void* stream, bfe_sl** out);
+void bfe_sl_destroy(bfe_sl* h);
+
+/* spheresl.compute_coefficients_solitary (spheresl.py:567-656):
+ * expcoef[(lmax+1)^2 * nmax], rows l^2 (m=0), l^2+2m-1 (cos), l^2+2m (sin); overwritten. */
+int bfe_sl_accumulate(bfe_sl* h, int64_t n,
+                      const double* x, const double* y, const double* z, const double* mass,
+                      int no_odd, double* expcoef, void* stream);
+
+/* A[k,i] = sum_{n<nuse} expcoef[k,n] eftable[l(k),n,i]/sqrt(ev[l,n]) for l1 <= l <= min(l2,lmax)
+ * (l=0 always kept), skipping odd l if no_odd.  expcoef: (lmax+1)^2*nmax doubles. */
+int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2, int nuse,
+                    int no_odd, void* stream);
+
+/* spheresl.all_eval_particles (spheresl.py:1240-1362), potential outputs:
+ * pot0, pot1, potr, pott, potp, rr per particle; r = sqrt(x^2+y^2+z^2), trig = cos/sin(m phi). */
+int bfe_sl_force_contracted(bfe_sl* h, int64_t n,
+                            const double* x, const double* y, const double* z,
+                            double* pot0, double* pot1, double* potr, double* pott, double* potp,
+                            double* rr, void* stream);
+
+int bfe_sl_force(bfe_sl* h, int64_t n,
+                 const double* x, const double* y, const double* z,
+                 const double* expcoef, int l1, int l2, int no_odd,
+                 double* pot0, double* pot1, double* potr, double* pott, double* potp, double* rr,
+                 void* stream);
+
+/* spheresl.force_eval / all_eval (spheresl.py:1107-1234 / 987-1102) at n points (r, costh, phi):
+ * potr, pott, potp, pot1, pot0.  trig_index_l=1 reproduces force_eval's cos/sin(l phi)
+ * (spheresl.py:1173,1222-1225); 0 gives all_eval's cos/sin(m phi). */
+int bfe_sl_force_eval_points(bfe_sl* h, int64_t n,
+                             const double* r, const double* costh, const double* phi,
+                             int trig_index_l,
+                             double* potr, double* pott, double* potp, double* pot1, double* pot0,
+                             void* stream);
+
+/* ---------------------------------------------------------------- combined field ------------ */
+
+/* Fields.return_forces_cart (potential.py:445-497) at n points in a frame rotated by rotpos:
+ * out8 = 8 SoA rows of n: fxdisk, fxhalo, fydisk, fyhalo, fzdisk, fzhalo, diskp, halop+halop0.
+ * Both handles must hold a contraction (halofac already folded into expcoef). */
+int bfe_field_force_cart(bfe_eof* he, bfe_sl* hs, int64_t n,
+                         const double* x, const double* y, const double* z, double rotpos,
+                         double* out8, void* stream);
+
+/* integrate.leapfrog_integrate (integrate.py:53-190) for norbit independent orbits.
+ * state6: 6 SoA rows of norbit (x,y,z,vx,vy,vz): initial state in, state at the last step out.
+ * nint steps INCLUDING step 0 (the reference's arrays have nint entries).
+ * traj (optional, may be NULL): every traj_stride-th step k = 0, s, 2s, ... is written as
+ *   traj[(k/s) * 10 * norbit + q * norbit + orbit], q = x,y,z,vx,vy,vz,pot,fx,fy,fz.
+ * apse != 0: count planar apocentres and stop an orbit after ap_max (integrate.py:126,146-153);
+ * nsteps_out (optional, int32 per orbit) receives the number of steps taken. */
+int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, double rotfreq,
+                 double* state6, double* traj, int64_t traj_stride,
+                 int apse, int ap_max, int32_t* nsteps_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFE_H */

@@ -1,0 +1,249 @@
+"""
+GPU parity tests (run with -m gpu on the B200): the CUDA path, called through
+the C ABI (exptool_b200.ops -> libbfe.so), against (a) the golden vectors the
+unmodified reference produced and (b) the oracle on larger seeded inputs.
+
+Tolerances (BASELINE.json north_star): <= 1e-10 relative (max-norm) for FP64
+coefficients and forces; orbit states <= 1e-8.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_golden, relerr, eof_tables, sl_tables, eof_geo_args, build_field, O, S
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+ORBIT_TOL = 1e-8
+
+EOF_CASES = ['eof_small_random_cmap1', 'eof_small_random_cmap0', 'eof_std_smooth']
+SL_CASES = ['sl_small_random_cmap1', 'sl_small_random_cmap0', 'sl_std_l4', 'sl_std_l6']
+FIELD_CASES = ['field_small', 'field_std']
+
+
+@pytest.fixture(scope='module')
+def ops():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail('GPU tests selected but CUDA is not available')
+    from exptool_b200 import ops as _ops
+    return _ops
+
+
+def make_eof(ops, T, g):
+    return ops.EOFTables(T['potC'], T['potS'], g['mmax'], g['norder'], g['XMIN'], g['dX'], g['YMIN'], g['dY'],
+                         g['numx'], g['numy'], g['ascale'], g['hscale'], g['cmap'],
+                         rforceC=T['rforceC'], zforceC=T['zforceC'], rforceS=T['rforceS'], zforceS=T['zforceS'])
+
+
+def make_sl(ops, p, ev, ef, xi, p0, d0):
+    return ops.SLTables(p['lmax'], p['nmax'], p['numr'], p['cmap'], p['scale'], ev, ef, xi, p0, d0)
+
+
+@pytest.mark.parametrize('name', EOF_CASES)
+def test_eof_accumulate_golden(ops, name):
+    d, meta = load_golden(name)
+    p, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    c, s = E.accumulate(d['x'], d['y'], d['z'], d['m'])
+    assert relerr(c.cpu().numpy(), d['cos']) < TOL
+    assert relerr(s.cpu().numpy(), d['sin']) < TOL
+    # repeat: the handle's workspace/counter must be reusable and the result deterministic
+    c2, s2 = E.accumulate(d['x'], d['y'], d['z'], d['m'])
+    assert np.array_equal(c2.cpu().numpy(), c.cpu().numpy())
+
+
+@pytest.mark.parametrize('name', EOF_CASES)
+def test_eof_force_golden(ops, name):
+    d, meta = load_golden(name)
+    p, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    nf = meta['nforce']
+    E.contract(d['cos'], d['sin'])
+    out = E.force(d['x'][:nf], d['y'][:nf], d['z'][:nf]).cpu().numpy()
+    for i in range(6):
+        assert relerr(out[i], d['full'][i]) < TOL, i
+    E.contract(d['cos'], d['sin'], m1=1, m2=2)
+    out = E.force(d['x'][:nf], d['y'][:nf], d['z'][:nf]).cpu().numpy()
+    for i in range(6):
+        assert relerr(out[i], d['win12'][i]) < TOL, i
+    # eof.force_eval variants at cylindrical points
+    variants = dict(full=(g['mmax'], g['norder'], False), trunc=(max(g['mmax'] - 1, 1), max(g['norder'] - 1, 1), False),
+                    noodd=(g['mmax'], g['norder'], True))
+    for vname, (M, N, no_odd) in variants.items():
+        E.contract(d['cos'], d['sin'], m1=0, m2=M, nuse=N, no_odd=no_odd)
+        out = E.force_eval_points(d['pt_r'], d['pt_z'], d['pt_phi']).cpu().numpy()
+        ref = d['fe_' + vname]
+        for i in range(5):
+            assert relerr(out[i], ref[:, i]) < TOL, (vname, i)
+
+
+@pytest.mark.parametrize('name', SL_CASES)
+def test_sl_accumulate_golden(ops, name):
+    d, meta = load_golden(name)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    c = H.accumulate(d['x'], d['y'], d['z'], d['m']).cpu().numpy()
+    assert relerr(c, d['coef']) < TOL
+    c2 = H.accumulate(d['x'], d['y'], d['z'], d['m'], no_odd=True).cpu().numpy()
+    assert relerr(c2, d['coef_noodd']) < TOL
+
+
+@pytest.mark.parametrize('name', SL_CASES)
+def test_sl_force_golden(ops, name):
+    d, meta = load_golden(name)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    nf = meta['nforce']
+    xs, ys, zs = d['x'][1:nf + 1], d['y'][1:nf + 1], d['z'][1:nf + 1]
+    for key, kw in (('allp', {}), ('allp_win12', dict(l1=1, l2=2)), ('allp_noodd', dict(no_odd=True))):
+        H.contract(d['coef'], **kw)
+        out = H.force(xs, ys, zs).cpu().numpy()
+        ref = d[key]          # den0,den1,pot0,pot1,potr,pott,potp,rr
+        for i, j in enumerate((2, 3, 4, 5, 6, 7)):
+            assert relerr(out[i], ref[j]) < TOL, (key, j)
+    L, N = p['lmax'], p['nmax']
+    for key, (l, n, no_odd) in dict(fe_full=(L, N, False), fe_trunc=(max(L - 1, 1), max(N - 2, 1), False),
+                                    fe_noodd=(L, N, True)).items():
+        H.contract(d['coef'], l1=0, l2=l, nuse=n, no_odd=no_odd)
+        out = H.force_eval_points(d['pt_r'], d['pt_costh'], d['pt_phi'], trig_index_l=True).cpu().numpy()
+        for i in range(5):
+            assert relerr(out[i], d[key][:, i]) < TOL, (key, i)
+    H.contract(d['coef'])
+    out = H.force_eval_points(d['pt_r'], d['pt_costh'], d['pt_phi'], trig_index_l=False).cpu().numpy()
+    for i, j in enumerate((4, 5, 6, 3, 2)):     # ae_full: den0,den1,pot0,pot1,potr,pott,potp
+        assert relerr(out[i], d['ae_full'][:, j]) < TOL, j
+
+
+def _field_handles(ops, meta, d):
+    pe, T, g = eof_tables(meta)
+    ps, ev, ef, xi, p0, d0 = sl_tables(meta, seed_offset=1)
+    return make_eof(ops, T, g), make_sl(ops, ps, ev, ef, xi, p0, d0), g, ps
+
+
+@pytest.mark.parametrize('name', FIELD_CASES)
+def test_field_cart_golden(ops, name):
+    d, meta = load_golden(name)
+    E, H, g, ps = _field_handles(ops, meta, d)
+    E.contract(d['cos'], d['sin'])
+    H.contract(meta['halofac'] * d['coef'])
+    out = ops.field_force_cart(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full']).cpu().numpy()
+    for i in range(8):
+        assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+    E.contract(d['cos'], d['sin'], m1=0, m2=2, nuse=3, no_odd=True)
+    H.contract(meta['halofac'] * d['coef'], l1=0, l2=2, nuse=3, no_odd=True)
+    out = ops.field_force_cart(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_trunc']).cpu().numpy()
+    for i in range(8):
+        assert relerr(out[i], d['cart_trunc'][:, i]) < TOL, i
+
+
+@pytest.mark.parametrize('name', FIELD_CASES)
+def test_leapfrog_golden(ops, name):
+    d, meta = load_golden(name)
+    E, H, g, ps = _field_handles(ops, meta, d)
+    E.contract(d['cos'], d['sin'])
+    H.contract(meta['halofac'] * d['coef'])
+    nint = meta['nint']
+    state, traj, nsteps = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, meta['dt'], rotfreq=meta['rotfreq'],
+                                       traj_stride=1)
+    traj = traj.cpu().numpy()
+    ref = d['orbits']        # (norb, 15, nint): X Y Z VX VY VZ P FX FY FZ ...
+    assert (nsteps.cpu().numpy() == nint).all()
+    for k in range(ref.shape[0]):
+        for j in range(10):
+            assert relerr(traj[:, j, k], ref[k, j]) < ORBIT_TOL, (k, j)
+    # end state equals last trajectory sample
+    assert np.array_equal(state.cpu().numpy(), traj[-1, :6, :])
+    # truncated, no_odd, rotfreq > 0
+    E.contract(d['cos'], d['sin'], m1=0, m2=4, nuse=5, no_odd=True)
+    H.contract(meta['halofac'] * d['coef'], l1=0, l2=2, nuse=4, no_odd=True)
+    state, traj, nsteps = ops.leapfrog(E, H, d['pos0'][:, :1], d['vel0'][:, :1], nint, meta['dt'], rotfreq=3.0,
+                                       traj_stride=1)
+    traj = traj.cpu().numpy()
+    for j in range(7):
+        assert relerr(traj[:, j, 0], d['orbit_trunc'][j]) < ORBIT_TOL, j
+
+
+# ---------------------------------------------------------------------------
+# larger seeded inputs against the oracle (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------
+def test_eof_accumulate_force_oracle_50k(ops):
+    p, T = S.make_eof_tables({}, kind='smooth')
+    XMIN, XMAX, dX, YMIN, YMAX, dY = O.eof_set_table_params(RMAX=p['rmax'], RMIN=p['rmin'], ASCALE=p['ascale'],
+                                                            HSCALE=p['hscale'], NUMX=p['numx'], NUMY=p['numy'], CMAP=p['cmap'])
+    g = dict(XMIN=XMIN, dX=dX, YMIN=YMIN, dY=dY, numx=p['numx'], numy=p['numy'], mmax=p['mmax'], norder=p['norder'],
+             ascale=p['ascale'], hscale=p['hscale'], cmap=p['cmap'])
+    E = make_eof(ops, T, g)
+    x, y, z, m = S.exponential_disc(50001, 2002)
+    c, s = E.accumulate(x, y, z, m)
+    co, so = O.eof_accumulate(x, y, z, m, T['potC'], T['potS'], g['mmax'], g['norder'], *eof_geo_args(g),
+                              g['ascale'], g['hscale'], g['cmap'])
+    assert relerr(c.cpu().numpy(), co) < TOL
+    assert relerr(s.cpu().numpy(), so) < TOL
+    E.contract(c, s)
+    out = E.force(x[:20000], y[:20000], z[:20000]).cpu().numpy()
+    ref = O.eof_force_particles(x[:20000], y[:20000], z[:20000], co, so, T['potC'], T['rforceC'], T['zforceC'],
+                                T['potS'], T['rforceS'], T['zforceS'], *eof_geo_args(g), g['mmax'], g['norder'],
+                                g['ascale'], g['hscale'], g['cmap'])
+    for i in range(6):
+        assert relerr(out[i], ref[i]) < TOL, i
+    # linearity (size-independent property): coefficients of a doubled-mass set are doubled,
+    # coefficients of a concatenated set are the sum
+    c2, s2 = E.accumulate(x, y, z, 2.0 * m)
+    assert relerr(c2.cpu().numpy(), 2.0 * co) < TOL
+    ca, sa = E.accumulate(x[:30000], y[:30000], z[:30000], m[:30000])
+    cb, sb = E.accumulate(x[30000:], y[30000:], z[30000:], m[30000:])
+    assert relerr((ca + cb).cpu().numpy(), co) < TOL
+    # empty input
+    c0, s0 = E.accumulate(x[:0], y[:0], z[:0], m[:0])
+    assert float(c0.abs().max()) == 0.0 and float(s0.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('lmax', [4, 6])
+def test_sl_accumulate_force_oracle_30k(ops, lmax):
+    meta = dict(sl_params=dict(lmax=lmax), kind='smooth', seed=0)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    x, y, z, m = S.hernquist_halo(30011, 1001)
+    c = H.accumulate(x, y, z, m)
+    co = O.sl_accumulate(x, y, z, m, p['lmax'], p['nmax'], ev, ef, xi, p0, p['cmap'], p['scale'])
+    assert relerr(c.cpu().numpy(), co) < TOL
+    H.contract(c)
+    out = H.force(x[:10000], y[:10000], z[:10000]).cpu().numpy()
+    ref = O.sl_all_eval_particles(x[:10000], y[:10000], z[:10000], co, p['lmax'], p['nmax'], ev, ef, xi, p0, d0,
+                                  p['cmap'], p['scale'])
+    for i in range(6):
+        assert relerr(out[i], ref[i]) < TOL, i
+    c0 = H.accumulate(x[:0], y[:0], z[:0], m[:0])
+    assert float(c0.abs().max()) == 0.0
+
+
+def test_generic_kernels_large_basis(ops):
+    """mmax > 6 / lmax > 6 take the generic (BFE_MAX_*) kernel instances."""
+    meta = dict(eof_params=dict(mmax=8, numx=20, numy=12, nmax=8, norder=5), kind='random', seed=5)
+    p, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    rng = np.random.default_rng(9)
+    x = rng.normal(0, 0.02, 3000); y = rng.normal(0, 0.02, 3000); z = rng.normal(0, 0.002, 3000); m = rng.random(3000)
+    c, s = E.accumulate(x, y, z, m)
+    co, so = O.eof_accumulate(x, y, z, m, T['potC'], T['potS'], g['mmax'], g['norder'], *eof_geo_args(g),
+                              g['ascale'], g['hscale'], g['cmap'])
+    assert relerr(c.cpu().numpy(), co) < TOL and relerr(s.cpu().numpy(), so) < TOL
+    E.contract(c, s)
+    out = E.force(x, y, z).cpu().numpy()
+    ref = O.eof_force_particles(x, y, z, co, so, T['potC'], T['rforceC'], T['zforceC'], T['potS'], T['rforceS'],
+                                T['zforceS'], *eof_geo_args(g), g['mmax'], g['norder'], g['ascale'], g['hscale'], g['cmap'])
+    for i in range(6):
+        assert relerr(out[i], ref[i]) < TOL, i
+    meta = dict(sl_params=dict(lmax=8, nmax=6, numr=300), kind='random', seed=6)
+    ps, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, ps, ev, ef, xi, p0, d0)
+    xh, yh, zh, mh = S.hernquist_halo(2000, 77)
+    ch = H.accumulate(xh, yh, zh, mh)
+    cho = O.sl_accumulate(xh, yh, zh, mh, ps['lmax'], ps['nmax'], ev, ef, xi, p0, ps['cmap'], ps['scale'])
+    assert relerr(ch.cpu().numpy(), cho) < TOL
+    H.contract(ch)
+    out = H.force(xh, yh, zh).cpu().numpy()
+    ref = O.sl_all_eval_particles(xh, yh, zh, cho, ps['lmax'], ps['nmax'], ev, ef, xi, p0, d0, ps['cmap'], ps['scale'])
+    for i in range(6):
+        assert relerr(out[i], ref[i]) < TOL, i
