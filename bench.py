@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""
+bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+metric   : particles/sec for BFE accumulate+force eval   (BASELINE.json:metric)
+workload : configs[1] -- EOF cylindrical disc mmax=6 norder=18, coefficient accumulation +
+           force evaluation on a 10^6-particle synthetic exponential disc per GPU.
+step     : one pass of the hot path over one particle set:
+             eof_accumulate (10^6 particles -> 2x7x18 coefficients)
+             [N>1: one NCCL allreduce of the 252 coefficients]
+             eof_contract   (coefficients x tables -> contracted grids)
+             eof_force      (p0,p,fr,fp,fz,R at the same 10^6 particles)
+value    : whole-job particles/s, inputs resident in HBM, CUDA-event time, max over ranks.
+e2e      : same metric through the reference-facing Python API (eof.make_coefficients_multi +
+           eof.accumulated_eval_particles) with HOST buffers: pinned host -> device copy of the
+           particle arrays and device -> host copy of the six output arrays inside the timed region.
+roofline : dominant kernel, algorithmic HBM bytes / CUDA-event duration vs MEASURED_PEAKS.json.
+cpu_baseline : the oracle (oracle/oracle_np.py, the NumPy restatement of the reference's
+           arithmetic, `kind: port`) on all host cores over a bounded sample of the same workload.
+
+--impl reference times that CPU port as the reference arm (the reference itself is pure
+Python under /root/reference, which does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'particles/sec for BFE accumulate+force eval'
+UNIT = 'particles/s'
+N_PART = 1000000
+WORKLOAD = 'EOF mmax=6 norder=18 numx=128 numy=64: accumulate + force eval, 10^6-particle exponential disc per GPU'
+BYTES_ACC = 32       # x,y,z,m read                          
+BYTES_FORCE = 72     # x,y,z read + p0,p,fr,fp,fz,R written  
+PBE_PER_PARTICLE = 234
+
+
+# ----------------------------------------------------------------------------- helpers
+def eof_setup():
+    from exptool_b200 import synthetic as S
+    from oracle import oracle_np as O
+    p, T = S.make_eof_tables({}, kind='smooth')
+    XMIN, XMAX, dX, YMIN, YMAX, dY = O.eof_set_table_params(RMAX=p['rmax'], RMIN=p['rmin'], ASCALE=p['ascale'],
+                                                            HSCALE=p['hscale'], NUMX=p['numx'], NUMY=p['numy'],
+                                                            CMAP=p['cmap'])
+    g = dict(XMIN=XMIN, dX=dX, YMIN=YMIN, dY=dY, numx=p['numx'], numy=p['numy'], mmax=p['mmax'], norder=p['norder'],
+             ascale=p['ascale'], hscale=p['hscale'], cmap=p['cmap'])
+    return p, T, g
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        try:
+            if self.proc:
+                self.proc.terminate()
+        except Exception:
+            pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            f = [t.strip() for t in s.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[3 + k].lower().startswith('active'):
+                    reasons.add(nme)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ----------------------------------------------------------------------------- CPU port (oracle)
+def _cpu_worker(args):
+    """One worker: accumulate + force on its chunk with the oracle.  Returns elapsed seconds."""
+    seed, n = args
+    from exptool_b200 import synthetic as S
+    from oracle import oracle_np as O
+    g = _CPU['g']; T = _CPU['T']
+    x, y, z, m = S.exponential_disc(n, seed)
+    geo = (g['XMIN'], g['dX'], g['YMIN'], g['dY'], g['numx'], g['numy'])
+    t0 = time.perf_counter()
+    c, s = O.eof_accumulate(x, y, z, m, T['potC'], T['potS'], g['mmax'], g['norder'], *geo,
+                            g['ascale'], g['hscale'], g['cmap'])
+    O.eof_force_particles(x, y, z, c, s, T['potC'], T['rforceC'], T['zforceC'], T['potS'], T['rforceS'],
+                          T['zforceS'], *geo, g['mmax'], g['norder'], g['ascale'], g['hscale'], g['cmap'])
+    return time.perf_counter() - t0
+
+
+_CPU = {}
+
+
+def cpu_port_run(n_total, cores, pool=None):
+    """accumulate+force of n_total particles split over `cores` processes; wall seconds."""
+    per = max(n_total // cores, 1)
+    jobs = [(7000 + i, per) for i in range(cores)]
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, jobs)
+    return time.perf_counter() - t0, per * cores
+
+
+def make_pool(cores):
+    import multiprocessing as mp
+    p, T, g = eof_setup()
+    _CPU['g'] = g; _CPU['T'] = T
+    ctx = mp.get_context('fork')
+    return ctx.Pool(cores)
+
+
+def cpu_baseline(target_seconds=12.0):
+    cores = os.cpu_count() or 1
+    pool = make_pool(cores)
+    try:
+        dt, n = cpu_port_run(2000 * cores, cores, pool)            # calibration (also warms the workers)
+        rate = n / dt
+        n_sample = int(min(max(rate * target_seconds, 4000 * cores), N_PART))
+        dt, n = cpu_port_run(n_sample, cores, pool)
+    finally:
+        pool.close(); pool.join()
+    return {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d of 10^6 particles (accumulate + force eval), oracle_np over %d processes, %.1f s'
+                      % (n, cores, dt)}
+
+
+def run_reference(args):
+    """Reference arm: the CPU port on all host cores, each step a bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    pool = make_pool(cores)
+    try:
+        dt, n = cpu_port_run(2000 * cores, cores, pool)
+        rate = n / dt
+        budget = 150.0 / max(args.steps + args.warmup, 1)         # whole run within a few minutes
+        n_step = int(min(max(rate * min(budget, 10.0), 2000 * cores), N_PART))
+        for _ in range(args.warmup):
+            cpu_port_run(n_step, cores, pool)
+        t = 0.0; done = 0
+        for _ in range(args.steps):
+            dt, n = cpu_port_run(n_step, cores, pool)
+            t += dt; done += n
+    finally:
+        pool.close(); pool.join()
+    value = done / t
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'particles_per_step': done // args.steps},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d particles per step (accumulate + force eval), oracle_np over %d processes'
+                                       % (done // args.steps, cores)},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from exptool_b200 import ops, synthetic as S, parallel
+    from exptool_b200.basis import eof as beof
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the GPU arm has no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    p, T, g = eof_setup()
+    E = ops.EOFTables(T['potC'], T['potS'], g['mmax'], g['norder'], g['XMIN'], g['dX'], g['YMIN'], g['dY'],
+                      g['numx'], g['numy'], g['ascale'], g['hscale'], g['cmap'],
+                      rforceC=T['rforceC'], zforceC=T['zforceC'], rforceS=T['rforceS'], zforceS=T['zforceS'])
+
+    # rotating particle sets: (32 B in + 48 B out) * 10^6 * NSETS > 2 x L2, so every step streams from HBM
+    NSETS = 6
+    sets = []
+    for k in range(NSETS):
+        x, y, z, m = S.exponential_disc(N_PART, 2002 + 100 * rank + k)
+        sets.append(tuple(ops.dev(a) for a in (x, y, z, m)))
+    outs = [torch.empty((6, N_PART), dtype=torch.float64, device=dev) for _ in range(NSETS)]
+    coefbuf = torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev)
+    lib = E.lib
+    from exptool_b200.ops import _ptr, _stream
+    from exptool_b200 import _lib as L
+
+    def step(k):
+        x, y, z, m = sets[k % NSETS]
+        o = outs[k % NSETS]
+        L.check(lib.bfe_eof_accumulate(E.h, N_PART, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _ptr(coefbuf[0]),
+                                       _ptr(coefbuf[1]), _stream()))
+        if world > 1:
+            dist.all_reduce(coefbuf)
+        L.check(lib.bfe_eof_contract(E.h, _ptr(coefbuf[0]), _ptr(coefbuf[1]), 0, g['mmax'], g['norder'], 0, _stream()))
+        L.check(lib.bfe_eof_force_contracted(E.h, N_PART, _ptr(x), _ptr(y), _ptr(z), *[_ptr(o[i]) for i in range(6)],
+                                             _stream()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - launches0
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total = float(tms.item())
+    ms_per_step = ms_total / args.steps
+    value = world * N_PART / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launching stream) for the roofline object
+    def time_kernel(fn, reps):
+        for k in range(3):
+            fn(k)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(reps):
+            fn(3 + k)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def k_acc(k):
+        x, y, z, m = sets[k % NSETS]
+        L.check(lib.bfe_eof_accumulate(E.h, N_PART, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _ptr(coefbuf[0]),
+                                       _ptr(coefbuf[1]), _stream()))
+
+    def k_con(k):
+        L.check(lib.bfe_eof_contract(E.h, _ptr(coefbuf[0]), _ptr(coefbuf[1]), 0, g['mmax'], g['norder'], 0, _stream()))
+
+    def k_force(k):
+        x, y, z, m = sets[k % NSETS]
+        o = outs[k % NSETS]
+        L.check(lib.bfe_eof_force_contracted(E.h, N_PART, _ptr(x), _ptr(y), _ptr(z), *[_ptr(o[i]) for i in range(6)],
+                                             _stream()))
+
+    reps = max(args.steps, 5)
+    t_acc, t_con, t_force = time_kernel(k_acc, reps), time_kernel(k_con, reps), time_kernel(k_force, reps)
+    if sampler:
+        sampler.stop()
+    peak, peak_src = measured_peaks()
+    kern = {'eof_accumulate_kernel': (t_acc, BYTES_ACC * N_PART), 'eof_force_kernel': (t_force, BYTES_FORCE * N_PART)}
+    dom = max(kern, key=lambda k: kern[k][0])
+    achieved = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
+    roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'kernel_ms': {'eof_accumulate_kernel': t_acc, 'eof_contract_kernel': t_con, 'eof_force_kernel': t_force},
+                'algorithmic_bytes_per_launch': kern[dom][1]}
+
+    # ---- e2e through the reference-facing API with host buffers (pinned), copies inside the timed region
+    hx, hy, hz, hm = [torch.from_numpy(a).pin_memory() for a in S.exponential_disc(N_PART, 4004 + rank)]
+    P = (hx, hy, hz, hm)
+    geo = (g['XMIN'], g['dX'], g['YMIN'], g['dY'], g['numx'], g['numy'])
+    tabs_acc = (T['potC'], T['potS'], g['mmax'], g['norder']) + geo + (g['ascale'], g['hscale'], g['cmap'])
+
+    def e2e_step():
+        c, s = beof.make_coefficients_multi(P, 1, *tabs_acc)
+        return beof.accumulated_eval_particles(P, c, s, potC=T['potC'], rforceC=T['rforceC'], zforceC=T['zforceC'],
+                                               potS=T['potS'], rforceS=T['rforceS'], zforceS=T['zforceS'],
+                                               rmin=g['XMIN'], dR=g['dX'], zmin=g['YMIN'], dZ=g['dY'], numx=g['numx'],
+                                               numy=g['numy'], MMAX=g['mmax'], NMAX=g['norder'], ASCALE=g['ascale'],
+                                               HSCALE=g['hscale'], CMAP=g['cmap'], verbose=0)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_PART * args.steps / float(te.item())
+    e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * 32 * N_PART - 8 * N_PART,
+           'd2h_bytes_per_step': 48 * N_PART + 2 * 8 * 126, 'ms_per_step': 1e3 * float(te.item()) / args.steps,
+           'api': 'eof.make_coefficients_multi + eof.accumulated_eval_particles, pinned host tensors in, NumPy arrays out'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        clocks = sampler.summary() if sampler else None
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'particles_per_gpu': N_PART,
+                           'l2': 'rotating %d particle sets (%.0f MB in+out) > 2x L2: every step streams from HBM'
+                                 % (NSETS, NSETS * 80e6 / 1e6),
+                           'parallelism': 'particles sharded over %d GPU(s), one 2 kB coefficient allreduce per step'
+                                          % world if world > 1 else 'single GPU'},
+                'pbe_per_s': value * PBE_PER_PARTICLE, 'e2e': e2e, 'gpu_launches': int(launches),
+                'roofline': roofline, 'clocks': clocks}
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -53,6 +53,7 @@ SIGNATURES = {
     'bfe_sl_force': (_INT, [_P, _I64] + [_P] * 3 + [_P, _INT, _INT, _INT] + [_P] * 6 + [_P]),
     'bfe_sl_force_eval_points': (_INT, [_P, _I64] + [_P] * 3 + [_INT] + [_P] * 5 + [_P]),
     'bfe_field_force_cart': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
+    'bfe_field_force_cyl': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
     'bfe_leapfrog': (_INT, [_P, _P, _I64, _I64, _DBL, _DBL, _P, _P, _I64, _INT, _INT, _P, _P]),
 }
 

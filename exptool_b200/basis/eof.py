@@ -265,12 +265,12 @@ def force_eval(r, z, phi, accum_cos, accum_sin, potC, rforceC, zforceC, potS, rf
                       rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
     if not perturb:
         E.contract(accum_cos, accum_sin, m1=0, m2=MMAX, nuse=NMAX, no_odd=no_odd)
-        fr, fp, fz, p, p0 = E.force_eval_points(r1, z1, p1).cpu().numpy()
+        fr, fp, fz, p, p0 = ops.to_host(E.force_eval_points(r1, z1, p1))
         return _scalar_or_array((fr, fp, fz, p, p0), scalar)
     E.contract(accum_cos, accum_sin, m1=1, m2=MMAX, nuse=NMAX, no_odd=no_odd)
-    fr, fp, fz, p, _ = E.force_eval_points(r1, z1, p1).cpu().numpy()
+    fr, fp, fz, p, _ = ops.to_host(E.force_eval_points(r1, z1, p1))
     E.contract(accum_cos, accum_sin, m1=0, m2=0, nuse=NMAX, no_odd=False)
-    fr0, _, fz0, _, p0 = E.force_eval_points(r1, z1, p1).cpu().numpy()
+    fr0, _, fz0, _, p0 = ops.to_host(E.force_eval_points(r1, z1, p1))
     return _scalar_or_array((fr, fp, fz, p, p0, fr0, fz0), scalar)
 
 
@@ -294,7 +294,7 @@ def accumulated_eval_particles(Particles, accum_cos, accum_sin, potC=0, rforceC=
     E = device_tables(potC, potS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
                       rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
     E.contract(accum_cos, accum_sin, m1=m1, m2=m2)
-    p0, p, fr, fp, fz, R = E.force(x, y, z).cpu().numpy()
+    p0, p, fr, fp, fz, R = ops.to_host(E.force(x, y, z))
     return p0, p, fr, fp, fz, R
 
 

@@ -166,7 +166,7 @@ def force_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax, evta
     scalar, r1, c1, p1 = _points(r, costh, phi)
     H = device_tables(xi, p0, d0, cmap, scale, evtable, eftable)
     H.contract(expcoef, l1=0, l2=lmax, nuse=nmax, no_odd=no_odd)
-    out = H.force_eval_points(r1, c1, p1, trig_index_l=True).cpu().numpy()
+    out = ops.to_host(H.force_eval_points(r1, c1, p1, trig_index_l=True))
     if scalar:
         return tuple(np.float64(v[0]) for v in out)
     return tuple(out)
@@ -180,7 +180,7 @@ def all_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax, evtabl
     scalar, r1, c1, p1 = _points(r, costh, phi)
     H = device_tables(xi, p0, d0, cmap, scale, evtable, eftable)
     H.contract(expcoef, l1=0, l2=lmax, nuse=nmax, no_odd=no_odd)
-    potr, pott, potp, pot1, pot0 = H.force_eval_points(r1, c1, p1, trig_index_l=False).cpu().numpy()
+    potr, pott, potp, pot1, pot0 = ops.to_host(H.force_eval_points(r1, c1, p1, trig_index_l=False))
     zero = np.zeros_like(pot0)
     out = (zero, zero, pot0, pot1, potr, pott, potp)
     if scalar:
@@ -196,7 +196,7 @@ def all_eval_particles(Particles, expcoef, sph_file, mod_file, verbose, L1=-1000
     H, _ = device_tables_from_files(sph_file, mod_file)
     x, y, z, _m = particle.particle_arrays(Particles)
     H.contract(expcoef, l1=L1, l2=L2, no_odd=NO_ODD)
-    pot0, pot1, potr, pott, potp, rr = H.force(x, y, z).cpu().numpy()
+    pot0, pot1, potr, pott, potp, rr = ops.to_host(H.force(x, y, z))
     zero = np.zeros_like(pot0)
     return zero, zero.copy(), pot0, pot1, potr, pott, potp, rr
 

@@ -333,14 +333,17 @@ struct CartForce {
     double fxd, fxh, fyd, fyh, fzd, fzh, pd, ph;
 };
 
-template <int MCAP, int LCAP>
+// CYL = true gives Fields.return_forces_cyl (potential.py:389-440) in the same 8 slots:
+// diskfr, frhalo, diskfp, -halofp, diskfz, fzhalo, -diskp, halop+halop0.
+template <int MCAP, int LCAP, bool CYL = false>
 __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const double* __restrict__ G, int gstride,
                                                     const SlGeom& gs, const double* __restrict__ A, int kpad,
                                                     const double* __restrict__ xi, const double* __restrict__ p0tab,
                                                     const double* __restrict__ fac,
                                                     double x, double y, double z, double crot, double srot) {
-    double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + 1.e-15;       // 455
-    double r3 = sqrt(BFE_ADD(BFE_MUL(r2, r2), BFE_MUL(z, z))) + 1.e-15;     // 456
+    const double eps = CYL ? 1.e-10 : 1.e-15;                               // 399-400 / 455-456
+    double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + eps;
+    double r3 = sqrt(BFE_ADD(BFE_MUL(r2, r2), BFE_MUL(z, z))) + eps;
     double costh = BFE_DIV(z, r3);                                          // 457
     double c1, s1;
     bfe_cossin_phi(x, y, c1, s1);                           // 458
@@ -355,6 +358,17 @@ __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const dou
     double halofr = h.potr, haloft = h.pott, halofp = h.potp;
     if (r3 < gs.xi0) { halofp = 0.0; diskfp = 0.0; }         // 483-485 (min(xi) = xi[0])
     CartForce o;
+    if (CYL) {
+        o.fxd = diskfr;
+        o.fxh = -1.0 * (r2 * halofr + z * haloft) / r3;      // 433
+        o.fyd = diskfp;
+        o.fyh = -1.0 * halofp;
+        o.fzd = diskfz;
+        o.fzh = -1.0 * (z * halofr - r2 * haloft) / r3;      // 435
+        o.pd = -1.0 * diskp;                                  // 440
+        o.ph = h.pot1 + h.pot0;
+        return o;
+    }
     double r2sq = r2 * r2, r3cu = r3 * r3 * r3;
     o.fxd = diskfr * (x / r2) - diskfp * (y / r2sq);
     o.fxh = -1.0 * (halofr * (x / r3) - haloft * (x * z / r3cu)) + halofp * (y / r2sq);

@@ -8,7 +8,7 @@
 #include <cstdio>
 #include <atomic>
 
-template <int MCAP, int LCAP>
+template <int MCAP, int LCAP, bool CYL>
 __global__ void __launch_bounds__(128)
 field_cart_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
                   SlGeom gs, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
@@ -16,8 +16,8 @@ field_cart_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
                   int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                   const double* __restrict__ z, double crot, double srot, double* __restrict__ out8) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        CartForce f = bfe_field_cart<MCAP, LCAP>(ge, G, gstride, gs, A, kpad, xi, p0tab, fac,
-                                                 __ldg(x + i), __ldg(y + i), __ldg(z + i), crot, srot);
+        CartForce f = bfe_field_cart<MCAP, LCAP, CYL>(ge, G, gstride, gs, A, kpad, xi, p0tab, fac,
+                                                      __ldg(x + i), __ldg(y + i), __ldg(z + i), crot, srot);
         out8[i] = f.fxd;
         out8[n + i] = f.fxh;
         out8[2 * n + i] = f.fyd;
@@ -93,8 +93,15 @@ leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
         else KERN<BFE_MAX_MMAX, BFE_MAX_LMAX><<<grid, 128, 0, stream>>>(__VA_ARGS__);                      \
     } while (0)
 
-extern "C" int bfe_field_force_cart(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y,
-                                    const double* z, double rotpos, double* out8, void* stream_) {
+#define FIELD_DISPATCH_CYL(CYL, ...)                                                                               \
+    do {                                                                                                          \
+        if (he->g.mmax <= 6 && hs->g.lmax <= 4)      field_cart_kernel<6, 4, CYL><<<grid, 128, 0, stream>>>(__VA_ARGS__); \
+        else if (he->g.mmax <= 6 && hs->g.lmax <= 6) field_cart_kernel<6, 6, CYL><<<grid, 128, 0, stream>>>(__VA_ARGS__); \
+        else field_cart_kernel<BFE_MAX_MMAX, BFE_MAX_LMAX, CYL><<<grid, 128, 0, stream>>>(__VA_ARGS__);            \
+    } while (0)
+
+static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
+                            double rotpos, double* out8, void* stream_, bool cyl) {
     if (!he || !hs || n < 0) return BFE_ERR_ARG;
     if (!he->contracted || !hs->contracted) return BFE_ERR_STATE;
     if (n == 0) return BFE_OK;
@@ -103,10 +110,24 @@ extern "C" int bfe_field_force_cart(bfe_eof* he, bfe_sl* hs, int64_t n, const do
     int64_t need = (n + 127) / 128, cap = (int64_t)he->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
     double crot = cos(rotpos), srot = sin(rotpos);
-    FIELD_DISPATCH(field_cart_kernel, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0,
-                   hs->fac, n, x, y, z, crot, srot, out8);
+    if (cyl)
+        FIELD_DISPATCH_CYL(true, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0, hs->fac, n,
+                           x, y, z, crot, srot, out8);
+    else
+        FIELD_DISPATCH_CYL(false, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0, hs->fac,
+                           n, x, y, z, crot, srot, out8);
     BFE_LAUNCH_CHECK("field_cart_kernel");
     return BFE_OK;
+}
+
+extern "C" int bfe_field_force_cart(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y,
+                                    const double* z, double rotpos, double* out8, void* stream) {
+    return field_force_impl(he, hs, n, x, y, z, rotpos, out8, stream, false);
+}
+
+extern "C" int bfe_field_force_cyl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y,
+                                   const double* z, double rotpos, double* out8, void* stream) {
+    return field_force_impl(he, hs, n, x, y, z, rotpos, out8, stream, true);
 }
 
 extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, double rotfreq,

@@ -41,6 +41,14 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def to_host(t):
+    """Device tensor -> NumPy array through a pinned staging buffer (async copy + one sync)."""
+    h = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
 def launch_count():
     return int(_lib.load().bfe_launch_count())
 
@@ -219,6 +227,16 @@ def field_force_cart(eof_tables, sl_tables, x, y, z, rotpos=0.0):
     out = torch.empty((8, n), dtype=torch.float64, device=x.device)
     _lib.check(eof_tables.lib.bfe_field_force_cart(eof_tables.h, sl_tables.h, n, _ptr(x), _ptr(y), _ptr(z),
                                                    float(rotpos), _ptr(out), _stream()))
+    return out
+
+
+def field_force_cyl(eof_tables, sl_tables, x, y, z, rotpos=0.0):
+    """Fields.return_forces_cyl (potential.py:389-440) at n points -> (8, n) device tensor."""
+    x, y, z = dev(x), dev(y), dev(z)
+    n = x.numel()
+    out = torch.empty((8, n), dtype=torch.float64, device=x.device)
+    _lib.check(eof_tables.lib.bfe_field_force_cyl(eof_tables.h, sl_tables.h, n, _ptr(x), _ptr(y), _ptr(z),
+                                                  float(rotpos), _ptr(out), _stream()))
     return out
 
 

@@ -152,6 +152,12 @@ int bfe_field_force_cart(bfe_eof* he, bfe_sl* hs, int64_t n,
                          const double* x, const double* y, const double* z, double rotpos,
                          double* out8, void* stream);
 
+/* Fields.return_forces_cyl (potential.py:389-440), same call shape; out8 rows are
+ * diskfr, frhalo, diskfp, -halofp, diskfz, fzhalo, -diskp, halop+halop0 (r2, r3 use +1e-10). */
+int bfe_field_force_cyl(bfe_eof* he, bfe_sl* hs, int64_t n,
+                        const double* x, const double* y, const double* z, double rotpos,
+                        double* out8, void* stream);
+
 /* integrate.leapfrog_integrate (integrate.py:53-190) for norbit independent orbits.
  * state6: 6 SoA rows of norbit (x,y,z,vx,vy,vz): initial state in, state at the last step out.
  * nint steps INCLUDING step 0 (the reference's arrays have nint entries).

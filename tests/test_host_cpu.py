@@ -1,0 +1,280 @@
+"""
+CPU-only tests (no GPU, no compute calls into libbfe.so): the C-ABI library loads and
+exports every symbol include/bfe.h declares; host-side readers / file formats; the
+sharding logic of parallel.py under gloo with world_size 2; the product path fails loudly
+without CUDA.
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, S, O, relerr
+
+
+def test_library_exports_every_declared_symbol():
+    from exptool_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = _lib.load()
+    with open(os.path.join(ROOT, 'include', 'bfe.h')) as f:
+        declared = sorted(set(re.findall(r'\b(bfe_[a-z0-9_]+)\s*\(', f.read())))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, name
+    for name in _lib.SIGNATURES:
+        assert name in declared, 'binding for undeclared symbol ' + name
+    # calls that need no GPU
+    assert lib.bfe_version() >= 100
+    assert lib.bfe_error_string(0) == b'ok'
+    assert b'argument' in lib.bfe_error_string(-1)
+    assert lib.bfe_launch_count() >= 0
+
+
+def test_struct_layout_matches_header():
+    """sizeof of the ctypes mirrors == sizeof of the C structs (compiled with gcc here)."""
+    from exptool_b200 import _lib
+    import ctypes as C
+    src = ('#include <stdio.h>\n#include "bfe.h"\nint main(){printf("%zu %zu\\n", sizeof(bfe_eof_params), '
+           'sizeof(bfe_sl_params));return 0;}\n')
+    with tempfile.TemporaryDirectory() as tmp:
+        cfile = os.path.join(tmp, 't.c')
+        with open(cfile, 'w') as f:
+            f.write(src)
+        exe = os.path.join(tmp, 't')
+        subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), cfile, '-o', exe])
+        a, b = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert C.sizeof(_lib.EofParams) == a
+    assert C.sizeof(_lib.SlParams) == b
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from exptool_b200 import ops
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        ops.dev(np.zeros(3))
+    from exptool_b200.basis import eof
+    p, T = S.make_eof_tables(dict(mmax=1, numx=4, numy=4, nmax=2, norder=2), kind='random')
+    P = S.ParticleSet(np.zeros(2), np.zeros(2), np.zeros(2), np.ones(2))
+    with pytest.raises(RuntimeError):
+        eof.accumulate(P, T['potC'], T['potS'], 1, 2, -1.0, 0.1, -1.0, 0.1, 4, 4, 0.01, 0.001, 1)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under exptool_b200/ may reference it."""
+    pkg = os.path.join(ROOT, 'exptool_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                with open(os.path.join(dirpath, fn)) as f:
+                    txt = f.read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', txt, re.M), fn
+                assert '/root/reference' not in txt, fn
+
+
+def test_eof_cache_reader_and_geometry():
+    from exptool_b200.basis import eof
+    for dens in (0, 1):
+        p, T = S.make_eof_tables(dict(mmax=3, numx=10, numy=6, nmax=8, norder=4, dens=dens), kind='random', seed=3)
+        with tempfile.TemporaryDirectory() as tmp:
+            f = S.write_eof_cache(os.path.join(tmp, 'c'), p, T)
+            rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, d = eof.eof_params(f)
+            assert (numx, numy, mmax, norder, cmap, d) == (10, 6, 3, 4, 1, dens)
+            tabs = eof.parse_eof(f)
+            D = eof.read_eof_file(f)
+        names = ('potC', 'rforceC', 'zforceC', 'densC', 'potS', 'rforceS', 'zforceS', 'densS')
+        for name, a in zip(names, tabs):
+            assert np.array_equal(a, T[name]), name
+            assert np.array_equal(D[name], T[name])
+    got = eof.set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=1)
+    ref = O.eof_set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=1)
+    assert np.allclose(np.array(got, dtype=float), np.array(ref), rtol=0, atol=0)
+    # SURVEY.md App. A.1 numbers
+    assert abs(float(got[0]) + 0.998002) < 1e-6 and abs(float(got[2]) - 0.0145775) < 1e-7
+    assert abs(float(got[3]) + 5.644903) < 1e-6 and abs(float(got[5]) - 0.1764032) < 1e-7
+
+
+def test_eof_new_style_header():
+    """new-style cache: magic 0xc0a57a1, length, YAML (eof.py:126-157, 257-259)."""
+    import yaml
+    from exptool_b200.basis import eof
+    p, T = S.make_eof_tables(dict(mmax=2, numx=6, numy=4, nmax=8, norder=3), kind='random', seed=4)
+    hdr = yaml.safe_dump(dict(mmax=p['mmax'], numx=p['numx'], numy=p['numy'], nmax=p['nmax'], norder=p['norder'],
+                              dens=False, cmap=1, rmin=p['rmin'], rmax=p['rmax'], ascl=p['ascale'], hscl=p['hscale'],
+                              cmass=1.0, time=0.0)).encode()
+    with tempfile.TemporaryDirectory() as tmp:
+        old = S.write_eof_cache(os.path.join(tmp, 'old'), p, T)
+        with open(old, 'rb') as f:
+            body = f.read()[76:]
+        new = os.path.join(tmp, 'new')
+        with open(new, 'wb') as f:
+            np.array([0xc0a57a1, len(hdr)], dtype='<i4').tofile(f)
+            f.write(hdr)
+            f.write(body)
+        assert eof.eof_params(new) == eof.eof_params(old)
+        for a, b in zip(eof.parse_eof(new), eof.parse_eof(old)):
+            assert np.array_equal(a, b)
+
+
+def test_sl_cache_reader_and_init_table():
+    from exptool_b200.utils import halo_methods
+    from helpers import hernquist_model_columns
+    p, ev, ef = S.make_sl_tables(dict(lmax=3, nmax=5, numr=80), kind='random', seed=8)
+    with tempfile.TemporaryDirectory() as tmp:
+        sf = S.write_sl_cache(os.path.join(tmp, 's'), p, ev, ef)
+        mf = S.write_hernquist_model(os.path.join(tmp, 'm'), a=p['scale'])
+        lmax, nmax, numr, cmap, rmin, rmax, scale, ltable, evtable, eftable = halo_methods.read_cached_table(sf)
+        assert halo_methods.parse_slgrid(sf)[:4] == (3, 5, 80, 1)
+        xi, r, p0, d0 = halo_methods.init_table(mf, numr, rmin, rmax, cmap, scale)
+    assert (lmax, nmax, numr, cmap) == (3, 5, 80, 1)
+    assert np.array_equal(evtable, ev) and np.array_equal(eftable, ef)
+    assert np.array_equal(ltable, np.arange(4))
+    R1, D1, P1 = hernquist_model_columns(p['scale'])
+    xo, ro, po, do = O.sl_init_table(R1, D1, P1, numr, rmin, rmax, cmap, scale)
+    assert np.array_equal(xi, xo) and relerr(p0, po) < 1e-15 and relerr(d0, do) < 1e-15
+
+
+def test_coefficient_dump_roundtrip_and_layout():
+    from exptool_b200.basis import eof, spheresl
+    rng = np.random.default_rng(0)
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, 'eofcoef')
+        objs = []
+        for k in range(3):
+            E = eof.EOF_Object()
+            E.time = np.float32(0.1 * k); E.filename = 'snap%d' % k; E.comp = 'star'; E.nbodies = 1000 + k
+            E.eof_file = '.eof.cache'; E.mmax = 6; E.nmax = 18
+            E.cos = rng.standard_normal((7, 18)); E.sin = rng.standard_normal((7, 18))
+            eof.save_eof_coefficients(f, E)
+            objs.append(E)
+        # 4 + k*(16(mmax+1)nmax + 224)
+        assert os.path.getsize(f) == 4 + 3 * (16 * 7 * 18 + 224)
+        last, D = eof.restore_eof_coefficients(f)
+        assert len(D) == 3 and last.nbodies == 1002
+        for E, (t, R) in zip(objs, D.items()):
+            assert np.array_equal(R.cos, E.cos) and np.array_equal(R.sin, E.sin) and R.mmax == 6 and R.nmax == 18
+        f2 = os.path.join(tmp, 'slcoef')
+        Sx = spheresl.SL_Object()
+        Sx.time = np.float32(0.5); Sx.filename = 'snap'; Sx.comp = 'dark'; Sx.nbodies = 7
+        Sx.sph_file = 'a'; Sx.model_file = 'b'; Sx.lmax = 4; Sx.nmax = 18
+        Sx.expcoef = rng.standard_normal((25, 18))
+        spheresl.save_sl_coefficients(f2, Sx)
+        spheresl.save_sl_coefficients(f2, Sx)
+        assert os.path.getsize(f2) == 4 + 2 * (8 * 25 * 18 + 324)      # App. B.4
+        last, D = spheresl.restore_sl_coefficients(f2)
+        assert np.array_equal(last.expcoef, Sx.expcoef) and last.lmax == 4
+
+
+def test_shard_bounds_match_reference_partition():
+    from exptool_b200 import parallel
+    for n, w in ((10, 3), (1000003, 8), (7, 8), (0, 2), (16, 1)):
+        b = parallel.shard_bounds(n, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        ref = O.partition_like_reference(n, w)
+        assert [x[0] for x in b] + [n] == ref
+        avg = n // w
+        assert all(hi - lo == avg for lo, hi in b[1:])         # rank 0 takes the remainder
+
+
+def test_particle_containers():
+    from exptool_b200.io import particle
+    x, y, z, m = (np.arange(3.0) + k for k in range(4))
+    H = particle.holder(); H.xpos, H.ypos, H.zpos, H.mass = x, y, z, m
+    P = particle.Particles(x, y, z, m)
+    for c in (H, P, (x, y, z, m), S.ParticleSet(x, y, z, m)):
+        a = particle.particle_arrays(c)
+        assert all(np.array_equal(u, v) for u, v in zip(a, (x, y, z, m)))
+    assert particle.particle_arrays((x, y, z))[3] is None
+    with pytest.raises(TypeError):
+        particle.particle_arrays(3)
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+from exptool_b200 import parallel, synthetic as S
+from oracle import oracle_np as O
+from helpers import eof_tables, sl_tables, eof_geo_args
+
+class FakeEOF:            # stands in for ops.EOFTables: same accumulate() contract, oracle arithmetic on the host
+    def __init__(s, T, g): s.T, s.g, s.mmax, s.norder = T, g, g['mmax'], g['norder']
+    def accumulate(s, x, y, z, m):
+        g = s.g
+        c, q = O.eof_accumulate(np.asarray(x), np.asarray(y), np.asarray(z), np.asarray(m), s.T['potC'], s.T['potS'],
+                                g['mmax'], g['norder'], *eof_geo_args(g), g['ascale'], g['hscale'], g['cmap'])
+        return torch.from_numpy(c), torch.from_numpy(q)
+
+class FakeSL:
+    def __init__(s, p, ev, ef, xi, p0): s.a = (p, ev, ef, xi, p0); s.nrow = (p['lmax']+1)**2; s.nmax = p['nmax']
+    def accumulate(s, x, y, z, m, no_odd=False):
+        p, ev, ef, xi, p0 = s.a
+        return torch.from_numpy(O.sl_accumulate(np.asarray(x), np.asarray(y), np.asarray(z), np.asarray(m), p['lmax'],
+                                                p['nmax'], ev, ef, xi, p0, p['cmap'], p['scale'], no_odd=no_odd))
+
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+meta = dict(eof_params=dict(mmax=2, numx=10, numy=8, nmax=8, norder=3), sl_params=dict(lmax=2, nmax=3, numr=50),
+            kind='random', seed=1)
+p, T, g = eof_tables(meta); E = FakeEOF(T, g)
+ps, ev, ef, xi, p0, d0 = sl_tables(meta); H = FakeSL(ps, ev, ef, xi, p0)
+x, y, z, m = S.exponential_disc(1001, 5)
+# (1) global arrays replicated on both ranks -> each takes its block, one allreduce
+c, s = parallel.eof_accumulate_sharded(E, x, y, z, m)
+c0, s0 = E.accumulate(x, y, z, m)
+assert float((c - c0).abs().max()) <= 1e-12 * float(c0.abs().max())
+assert float((s - s0).abs().max()) <= 1e-12 * float(s0.abs().max())
+lo, hi = parallel.my_shard(1001)
+assert (lo, hi) == ((0, 501) if rank == 0 else (501, 1001))
+# (2) already-sharded inputs (weak scaling) + the SL path
+xs, ys, zs, ms = (a[lo:hi] for a in (x, y, z, m))
+h = parallel.sl_accumulate_sharded(H, xs, ys, zs, ms, already_sharded=True)
+h0 = H.accumulate(x, y, z, m)
+assert float((h - h0).abs().max()) <= 1e-12 * float(h0.abs().max())
+# (3) time series: 3 snapshots, ONE allreduce of the [3, ncoef] block
+snaps = [((xs * (1 + 0.1 * k), ys, zs, ms), (xs, ys * (1 + 0.1 * k), zs, ms)) for k in range(3)]
+cs, ss, hs = parallel.accumulate_series(E, H, snaps)
+for k in range(3):
+    ck, sk = E.accumulate(x * (1 + 0.1 * k), y, z, m)
+    hk = H.accumulate(x, y * (1 + 0.1 * k), z, m)
+    assert float((cs[k] - ck).abs().max()) <= 1e-12 * float(ck.abs().max())
+    assert float((hs[k] - hk).abs().max()) <= 1e-12 * float(hk.abs().max())
+# (4) coefficient broadcast
+t = torch.full((4,), float(rank + 1), dtype=torch.float64)
+parallel.broadcast_(t, src=0)
+assert float(t.sum()) == 4.0
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_sharded_accumulate_gloo_world2():
+    import socket
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    with tempfile.TemporaryDirectory() as tmp:
+        script = os.path.join(tmp, 'w.py')
+        with open(script, 'w') as f:
+            f.write(GLOO_WORKER.format(root=ROOT, port=port))
+        procs = [subprocess.Popen([sys.executable, script, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                  text=True) for r in range(2)]
+        outs = []
+        for p in procs:
+            try:
+                out, _ = p.communicate(timeout=240)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                out, _ = p.communicate()
+            outs.append(out)
+        for r, (p, out) in enumerate(zip(procs, outs)):
+            assert p.returncode == 0, out[-3000:]
+            assert 'rank %d ok' % r in out
