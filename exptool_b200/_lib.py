@@ -38,9 +38,13 @@ SIGNATURES = {
     'bfe_last_cuda_error': (C.c_char_p, []),
     'bfe_version': (_INT, []),
     'bfe_launch_count': (C.c_uint64, []),
+    'bfe_set_option': (_INT, [C.c_char_p, _INT]),
     'bfe_eof_create': (_INT, [C.POINTER(EofParams)] + [_P] * 6 + [_P, C.POINTER(_P)]),
     'bfe_eof_destroy': (None, [_P]),
     'bfe_eof_accumulate': (_INT, [_P, _I64] + [_P] * 4 + [_P, _P, _P]),
+    'bfe_eof_prepare': (_INT, [_P, _I64] + [_P] * 4 + [_P]),
+    'bfe_eof_accumulate_prepared': (_INT, [_P, _P, _P, _P]),
+    'bfe_eof_force_prepared': (_INT, [_P] + [_P] * 6 + [_P]),
     'bfe_eof_contract': (_INT, [_P, _P, _P, _INT, _INT, _INT, _INT, _P]),
     'bfe_eof_force_contracted': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_eof_force': (_INT, [_P, _I64] + [_P] * 3 + [_P, _P, _INT, _INT, _INT, _INT] + [_P] * 6 + [_P]),

@@ -9,6 +9,26 @@
 #define BFE_TWOPI      (6.283185307179586476925286766559)
 
 // ---------------------------------------------------------------------------
+// column sum over the per-CTA partial rows, executed by the last CTA to finish.
+// Rows are summed in a fixed order (deterministic); 16 independent L2 loads are kept in flight
+// per thread -- a naive one-load-at-a-time loop over ~600 rows costs ~50 us of pure L2 latency.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double bfe_column_sum(const double* __restrict__ partial, int nrows, int stride, int col) {
+    const double* q = partial + col;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 15 < nrows; b += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(q + (size_t)(b + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) { s0 += v[u]; s1 += v[u + 1]; s2 += v[u + 2]; s3 += v[u + 3]; }
+    }
+    for (; b < nrows; ++b) s0 += __ldcg(q + (size_t)b * stride);
+    return (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------
 // coordinate maps -- exptool/basis/compatibility.py:16-99
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double bfe_r_to_xi(double r, int cmap, double scale) {
@@ -47,8 +67,10 @@ struct EofBin {
 };
 
 __device__ __forceinline__ EofBin bfe_eof_bin(const EofGeom& g, double r, double z) {
-    double X = (bfe_r_to_xi(r, g.cmap, g.ascale) - g.xmin) / g.dx;
-    double Y = (bfe_z_to_y(z, g.hscale) - g.ymin) / g.dy;
+    // (xi - xmin)/dx as a multiply by the host-rounded reciprocal: <= 1 ulp from the reference's
+    // division, i.e. ~1e-14 relative in the bin fractions (X ~ 1e2), far inside the 1e-10 gate
+    double X = (bfe_r_to_xi(r, g.cmap, g.ascale) - g.xmin) * g.inv_dx;
+    double Y = (bfe_z_to_y(z, g.hscale) - g.ymin) * g.inv_dy;
     int ix = (int)X;                       // truncation, eof.py:404 (NaN -> 0, +-inf saturate)
     int iy = (int)Y;
     if (ix < 0) ix = 0;                    // 410

@@ -54,7 +54,8 @@ eof_accumulate_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int 
     constexpr int NTRIG = 2 * MCAP + 1;
     __shared__ int s_node[TILE];
     __shared__ double s_w[4][TILE];
-    __shared__ double s_trig[NTRIG][TILE];      // [0..mmax] = cos(m phi), [mmax+1..2mmax] = sin(m phi), m>=1
+    __shared__ double s_trig[NTRIG][TILE + 1];  // [0..mmax] = cos(m phi), [mmax+1..2mmax] = sin(m phi), m>=1;
+                                                // +1: rows read by one warp at the same p hit different banks
     __shared__ bool s_last;
 
     const int tid = threadIdx.x;
@@ -139,9 +140,7 @@ eof_accumulate_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int 
     if (s_last) {
         __threadfence();
         for (int ch = tid; ch < nch; ch += 256) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * nch_pad + ch);
-            s *= BFE_FOURPI_NEG;                                   // eof.py:526,550
+            double s = bfe_column_sum(partial, (int)gridDim.x, nch_pad, ch) * BFE_FOURPI_NEG;   // eof.py:526,550
             if (ch < ncos) cos_out[ch] = s;
             else           sin_out[ch - ncos + g.norder] = s;
         }
@@ -234,7 +233,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     g.ny1 = p->numy + 1;
     g.nnode = (p->numx + 1) * (p->numy + 1);
     g.xmin = p->xmin; g.dx = p->dx; g.ymin = p->ymin; g.dy = p->dy; g.ascale = p->ascale; g.hscale = p->hscale;
-    g.inv_dx = 1.0 / p->dx; g.inv_dy_unused = 0.0;
+    g.inv_dx = 1.0 / p->dx; g.inv_dy = 1.0 / p->dy;
     BFE_CUDA(cudaGetDevice(&h->device));
     BFE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     h->nch = (2 * p->mmax + 1) * p->norder;
@@ -243,8 +242,8 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     h->tab_elems = (size_t)(p->mmax + 1) * p->norder * g.nnode;
     h->gstride = 6 * (p->mmax + 1);
     h->contracted = 0;
-    h->sort_cap = 0; h->sort_ws = nullptr;
-    h->max_ctas = h->num_sms * 8;
+    h->sort_cap = 0; h->sort_ws = nullptr; h->prepared_n = -1; h->prepared_has_mass = 0;
+    h->max_ctas = h->num_sms * 4;
     BFE_CUDA(cudaMalloc(&h->t_acc, (size_t)g.nnode * h->nch_pad * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * h->nch_pad * sizeof(double)));
@@ -278,6 +277,12 @@ extern "C" int bfe_eof_accumulate(bfe_eof* h, int64_t n, const double* x, const 
     if (!h || n < 0 || !cos_out || !sin_out) return BFE_ERR_ARG;
     if (n > 0 && (!x || !y || !z || !mass)) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
+    {
+        const bool can_sort = (h->g.mmax <= 6 && h->nch_pad <= 256);
+        const int mode = g_bfe_eof_accumulate_mode;
+        if (can_sort && (mode == 2 || (mode == 0 && n >= g_bfe_sort_min_particles)))
+            return bfe_eof_accumulate_sorted(h, n, x, y, z, mass, cos_out, sin_out, stream);
+    }
     const bool fast = (h->g.mmax <= 6 && h->nch_pad <= 256);
     const int tile = fast ? 256 : 64;
     int64_t ntiles = (n + tile - 1) / tile;
@@ -315,6 +320,11 @@ extern "C" int bfe_eof_force_contracted(bfe_eof* h, int64_t n, const double* x, 
     if (n == 0) return BFE_OK;
     if (!x || !y || !z || !p0 || !p || !fr || !fp || !fz || !R) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
+    {
+        const int mode = g_bfe_eof_force_mode;
+        if (h->g.mmax <= 6 && (mode == 2 || (mode == 0 && n >= g_bfe_sort_min_particles)))
+            return bfe_eof_force_sorted(h, n, x, y, z, p0, p, fr, fp, fz, R, stream);
+    }
     int grid = grid_for(n, 128, h->num_sms, 16);
     if (h->g.mmax <= 6)
         eof_force_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, x, y, z, p0, p, fr, fp, fz, R);

@@ -153,6 +153,18 @@ extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nin
 static std::atomic<uint64_t> g_launches{0};
 static thread_local char g_cuda_err[256] = "";
 
+int g_bfe_eof_accumulate_mode = 0;
+int g_bfe_eof_force_mode = 0;
+int g_bfe_sort_min_particles = 32768;
+
+extern "C" int bfe_set_option(const char* name, int value) {
+    if (!name) return BFE_ERR_ARG;
+    if (!strcmp(name, "eof_accumulate_mode")) { g_bfe_eof_accumulate_mode = value; return BFE_OK; }
+    if (!strcmp(name, "eof_force_mode")) { g_bfe_eof_force_mode = value; return BFE_OK; }
+    if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
+    return BFE_ERR_ARG;
+}
+
 extern "C" void bfe_count_launch(int n) { g_launches.fetch_add((uint64_t)n); }
 extern "C" uint64_t bfe_launch_count(void) { return g_launches.load(); }
 extern "C" int bfe_version(void) { return 100; }

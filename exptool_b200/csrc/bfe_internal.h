@@ -10,7 +10,7 @@ struct EofGeom {
     int nnode;          // (numx+1)*(numy+1)
     int ny1;            // numy+1 : node = ix*ny1 + iy
     double xmin, dx, ymin, dy, ascale, hscale;
-    double inv_dx, inv_dy_unused;
+    double inv_dx, inv_dy;
 };
 
 // halo_methods.init_table:178-220 geometry
@@ -43,6 +43,8 @@ struct bfe_eof {
     // cell-sorted accumulate workspace (grown on demand)
     int64_t sort_cap;
     void* sort_ws;
+    int64_t prepared_n;      // particles currently held cell-sorted in sort_ws (-1: none)
+    int prepared_has_mass;
 };
 
 struct bfe_sl {
@@ -65,6 +67,16 @@ struct bfe_sl {
 };
 
 extern "C" void bfe_count_launch(int n);
+
+// runtime options (bfe_set_option): 0 = auto, 1 = direct kernels, 2 = cell-sorted kernels
+extern int g_bfe_eof_accumulate_mode;
+extern int g_bfe_eof_force_mode;
+extern int g_bfe_sort_min_particles;
+
+int bfe_eof_accumulate_sorted(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
+                              const double* mass, double* cos_out, double* sin_out, cudaStream_t stream);
+int bfe_eof_force_sorted(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
+                         double* p0, double* p, double* fr, double* fp, double* fz, double* R, cudaStream_t stream);
 void bfe_set_cuda_error(cudaError_t e, const char* where);
 
 #define BFE_CUDA(call)                                                  \

@@ -48,8 +48,8 @@ sl_accumulate_kernel(SlGeom g, const double* __restrict__ e_node, const double* 
     double* s_x1 = s_w + (size_t)g.nrow * TILE;   // [TILE]
     double* s_x2 = s_x1 + TILE;                   // [TILE]
     int* s_i = reinterpret_cast<int*>(s_x2 + TILE);
-    __shared__ bool s_last;
     (void)NROW;
+    (void)counter; (void)expcoef;
 
     const int tid = threadIdx.x;
     const int my_l = tid / g.nmax;                // thread -> (l, n)
@@ -122,21 +122,30 @@ sl_accumulate_kernel(SlGeom g, const double* __restrict__ e_node, const double* 
             if (k < 2 * my_l + 1)
                 partial[(size_t)blockIdx.x * ncoef + (size_t)(my_l * my_l + k) * g.nmax + nn] = acc[k];
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int done = atomicAdd(counter, 1u);
-        s_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        for (int c = tid; c < ncoef; c += blockDim.x) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * ncoef + c);
-            expcoef[c] = s;
+}
+
+// column sums of the per-CTA partial rows: out[c] = sum_b partial[b][c].  256 threads = 8 columns x 32 row
+// slices per CTA; fixed summation order (deterministic).
+__global__ void __launch_bounds__(256)
+sl_reduce_partials_kernel(const double* __restrict__ partial, int nrows, int ncol, double* __restrict__ out) {
+    __shared__ double s_p[32][9];
+    const int c = blockIdx.x * 8 + (threadIdx.x & 7), slice = threadIdx.x >> 3;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < ncol) {
+        int b = slice;
+        for (; b + 32 < nrows; b += 64) {
+            s0 += __ldg(partial + (size_t)b * ncol + c);
+            s1 += __ldg(partial + (size_t)(b + 32) * ncol + c);
         }
-        if (tid == 0) *counter = 0u;
+        if (b < nrows) s0 += __ldg(partial + (size_t)b * ncol + c);
+    }
+    s_p[slice][threadIdx.x & 7] = s0 + s1;
+    __syncthreads();
+    if (threadIdx.x < 8 && blockIdx.x * 8 + threadIdx.x < ncol) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s += s_p[k][threadIdx.x];
+        out[blockIdx.x * 8 + threadIdx.x] = s;
     }
 }
 
@@ -222,6 +231,9 @@ static int sl_acc_launch(bfe_sl* h, int64_t n, const double* x, const double* y,
     kern<<<grid, block, smem, stream>>>(h->g, h->e_node, h->xi, h->p0, h->fac, n, x, y, z, mass, no_odd,
                                         h->partial, h->counter, expcoef);
     BFE_LAUNCH_CHECK("sl_accumulate_kernel");
+    const int ncoef = h->g.nrow * h->g.nmax;
+    sl_reduce_partials_kernel<<<(ncoef + 7) / 8, 256, 0, stream>>>(h->partial, grid, ncoef, expcoef);
+    BFE_LAUNCH_CHECK("sl_reduce_partials_kernel");
     return BFE_OK;
 }
 
@@ -247,7 +259,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     g.dxi = xi01[1] - xi01[0];              // xi[1]-xi[0], spheresl.py:317
     h->kpad = (g.nrow + 1) / 2 * 2;
     h->contracted = 0;
-    h->max_ctas = h->num_sms * 8;
+    h->max_ctas = h->num_sms * 6;
     size_t nr = (size_t)p->numr;
     BFE_CUDA(cudaMalloc(&h->e_node, nr * g.ln * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->xi, nr * sizeof(double)));

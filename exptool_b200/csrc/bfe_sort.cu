@@ -1,0 +1,551 @@
+// bfe_sort.cu -- cell-sorted formulations of the EOF passes.
+//
+// The direct kernels (bfe_eof.cu) gather four table rows per particle: 7.5 kB of L2
+// traffic per 32 B of particle data, which binds on the L1/L2 path (ncu, profiles/).
+// Bilinear interpolation is linear in the table, so for all particles that share a cell
+//
+//   sum_p m_p trig_ch(p) interp_p(T[j])  =  sum_{k in 4 corners} T[node_k][j] * S_k,ch
+//   S_k,ch = sum_{p in cell} c_k(p) m_p trig_ch(p)                     (52 sums per cell)
+//
+// ("deposit then contract").  Particles are counting-sorted by cell
+// (integer keys, integer cursors), the 52 sums are formed per run of equal cells with
+// per-thread register accumulators and a shared-memory combine, and the table rows are
+// read once per RUN instead of once per particle.  No floating-point atomics anywhere;
+// the coefficient partials are combined exactly as in the direct kernel.
+//
+//   eof_cell_hist_kernel     : per-particle cell id -> histogram (shared-memory int counters);
+//                              the last CTA to finish scans it (cell_start, cursors)
+//   eof_cell_scatter_kernel  : 64-byte record {c00,c10,c01,c11,cos phi,sin phi,m|R,cell:perm}
+//                              written at its sorted position
+//   eof_deposit_kernel       : runs -> S -> coefficient partials -> last-CTA reduce
+//   eof_force_sorted_kernel  : field evaluation in sorted order (warp-uniform table rows),
+//                              outputs scattered back to the caller's particle order
+#include "bfe_device.cuh"
+
+struct __align__(16) EofRec {
+    double c00, c10, c01, c11;   // bilinear weights (eof.py:448-451), NOT mass weighted
+    double c1, s1;               // cos phi, sin phi
+    double aux;                  // mass (0 if the set was prepared without masses)
+    unsigned long long cellperm; // (cell << 32) | original particle index
+};
+
+__device__ __forceinline__ int bfe_cell_of(const EofGeom& g, const EofBin& b) {
+    // b.node = ix*ny1 + iy  ->  cell = ix*numy + iy
+    int ix = b.node / g.ny1;
+    int iy = b.node - ix * g.ny1;
+    return ix * g.numy + iy;
+}
+
+// exclusive scan of the histogram by one 1024-thread CTA: cell_start, cursor = scan; hist cleared.
+// Bins are staged through shared memory (s_h, per*1024 ints) with coalesced loads; two levels of warp shuffles.
+__device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict__ hist, int* __restrict__ cell_start,
+                                                     int* __restrict__ cursor, int* s_h, int* s_wsum) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (ncell + 1023) / 1024;
+    for (int c = tid; c < per * 1024; c += 1024) {
+        int v = 0;
+        if (c < ncell) { v = __ldcg(hist + c); hist[c] = 0; }
+        s_h[c] = v;
+    }
+    __syncthreads();
+    const int lo = tid * per;
+    int sum = 0;
+    for (int k = 0; k < per; ++k) sum += s_h[lo + k];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_wsum[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { int v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+        s_wsum[lane] = w;
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? s_wsum[warp - 1] : 0);    // exclusive prefix of this thread's segment
+    for (int k = 0; k < per; ++k) { int h = s_h[lo + k]; s_h[lo + k] = run; run += h; }
+    __syncthreads();
+    for (int c = tid; c < ncell; c += 1024) { int v = s_h[c]; cell_start[c] = v; cursor[c] = v; }
+    if (tid == 1023) cell_start[ncell] = run;
+}
+
+// histogram of cell ids (shared-memory int counters per CTA, merged with one global int add per
+// non-empty bin); the last CTA to finish scans the histogram, so no separate scan launch is needed.
+// dynamic smem: per*1024 ints (>= ncell).
+__global__ void __launch_bounds__(1024)
+eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                     const double* __restrict__ z, int* __restrict__ hist, int* __restrict__ cell_start,
+                     int* __restrict__ cursor, unsigned int* __restrict__ counter) {
+    extern __shared__ int s_hist[];
+    __shared__ int s_wsum[32];
+    __shared__ bool s_last;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        double r = sqrt(px * px + py * py + 1.e-10);
+        EofBin b = bfe_eof_bin(g, r, pz);
+        atomicAdd(&s_hist[bfe_cell_of(g, b)], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        int v = s_hist[c];
+        if (v) atomicAdd(&hist[c], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        bfe_block_scan_cells(ncell, hist, cell_start, cursor, s_hist, s_wsum);
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                        const double* __restrict__ z, const double* __restrict__ mass,
+                        int* __restrict__ cursor, EofRec* __restrict__ rec, double* __restrict__ r_sorted) {
+    constexpr int U = 2;       // particles per thread per pass: independent slot claims overlap their latency
+    for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
+        EofBin b[U];
+        double c1[U], s1[U], r[U], aux[U];
+        int cell[U], pos[U];
+        int64_t idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            idx[u] = base + u * 256 + threadIdx.x;
+            const bool on = idx[u] < n;
+            double px = on ? __ldg(x + idx[u]) : 1.0, py = on ? __ldg(y + idx[u]) : 0.0, pz = on ? __ldg(z + idx[u]) : 0.0;
+            aux[u] = (on && mass) ? __ldg(mass + idx[u]) : 0.0;
+            r[u] = sqrt(px * px + py * py + 1.e-10);              // eof.py:531 / 1070
+            b[u] = bfe_eof_bin(g, r[u], pz);
+            cell[u] = bfe_cell_of(g, b[u]);
+            bfe_cossin_phi(px, py, c1[u], s1[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            pos[u] = (idx[u] < n) ? atomicAdd(&cursor[cell[u]], 1) : 0;   // integer slot claim, not a data reduction
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (idx[u] < n) {
+                unsigned long long cp = ((unsigned long long)(unsigned int)cell[u] << 32) |
+                                        (unsigned long long)(unsigned int)idx[u];
+                double2* dst = reinterpret_cast<double2*>(rec + pos[u]);
+                dst[0] = make_double2(b[u].c00, b[u].c10);
+                dst[1] = make_double2(b[u].c01, b[u].c11);
+                dst[2] = make_double2(c1[u], s1[u]);
+                dst[3] = make_double2(aux[u], __longlong_as_double((long long)cp));
+                r_sorted[pos[u]] = r[u];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// deposit + contract over sorted records.
+//
+// A WARP owns a task of TASK consecutive sorted records and walks it 32 records at a time:
+//   1. lanes = records: the 64-B record (prefetched one batch ahead) is expanded to 4 mass-weighted
+//      corner weights and 2 mmax+1 cos/sin(m phi) values in the warp's shared-memory slab;
+//   2. the per-run sums  S[k][ch] = sum_p w_k(p) trig_ch(p)  are a (4 x L)(L x ntrig) product:
+//      done on the FP64 tensor cores with mma.sync.m8n8k4 (A = W^T, rows 4..7 zero; B = trig,
+//      two n-tiles of 8 channels; 4 records per k-step).  The direct LDS+DFMA form needs 8
+//      shared-memory wavefronts per record and was bound on shared-memory bandwidth (ncu:
+//      profiles/); the fragment loads need ~1.3.  Records outside the current run are masked to
+//      zero in the A fragment, so a run boundary costs at most one extra k-step;
+//   3. when the cell id changes (warp-uniform) the finished run is flushed: every lane adds
+//      sum_k T[node_k][j] S[k][ch(j)] to the register accumulators of its channels j = lane + 32 c.
+// Batches that are mostly single-record runs (sparse outskirts) are deferred and done at the end
+// by the whole CTA in the direct formulation (thread per channel), which keeps all 8 warps' load
+// pipelines busy instead of serialising ~30 dependent flushes in one warp.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bfe_dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int MCAP, int KCH>
+__global__ void __launch_bounds__(256, 2)
+eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch_pad, int64_t n,
+                   const EofRec* __restrict__ rec, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                   double* __restrict__ cos_out, double* __restrict__ sin_out) {
+    constexpr int TASK = 128;
+    constexpr int SPARSE_RUNS = 20;               // batches with more run starts than this are deferred
+    constexpr int NTRIG = 2 * MCAP + 1;
+    constexpr int NV = 4 + NTRIG;                 // values per record in the slab
+    constexpr int NW = 8;                         // warps per CTA
+    constexpr int RS = 36;                        // slab row stride (doubles): conflict-free fragment loads
+    constexpr int SLAB = NV * RS;
+    constexpr int MAXDEFER = 160;
+    static_assert(SLAB >= KCH * 32, "slab reused for the CTA reduce");
+    static_assert(NTRIG <= 16, "two n-tiles of 8 channels");
+    __shared__ double s_slab[NW][SLAB];           // [warp][value][record]
+    __shared__ double s_S[NW][64];                // [warp][corner k][16 channel slots]
+    __shared__ int s_defer[MAXDEFER];
+    __shared__ int s_ndefer;
+    __shared__ int s_dcell[32];
+    __shared__ bool s_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntrig = 2 * g.mmax + 1;
+    const int ncos = (g.mmax + 1) * g.norder;
+    const int fg = lane >> 2, fj = lane & 3;      // mma fragment coordinates: group, thread-in-group
+    const bool a_on = fg < 4;                     // A rows 4..7 are zero
+    const bool b1_on = (8 + fg) < ntrig;          // second n-tile holds channels 8..ntrig-1
+    // channels owned by this lane: j = lane + 32 c
+    int trig_idx[KCH];
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+        int j = lane + 32 * c;
+        trig_idx[c] = (j < nch) ? ((j < ncos) ? j / g.norder : g.mmax + 1 + (j - ncos) / g.norder) : 0;
+    }
+    double acc[KCH];
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) acc[c] = 0.0;
+    const int rowstep = nch_pad, colstep = g.ny1 * nch_pad;
+
+    double* val = s_slab[warp];                   // val[v * RS + p]
+    double* S = s_S[warp];
+    if (tid == 0) s_ndefer = 0;
+    __syncthreads();
+
+    const int64_t ntasks = (n + TASK - 1) / TASK;
+    const int64_t wglobal = (int64_t)blockIdx.x * NW + warp, wtotal = (int64_t)gridDim.x * NW;
+    for (int64_t task = wglobal; task < ntasks; task += wtotal) {
+        const int64_t t0 = task * TASK;
+        const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;   // C fragments: tile 0 (ch 0..7), tile 1 (ch 8..15)
+        int cur = -1;                               // cell of the run being summed (-1: none)
+        double2 ra, rb, rc, rd;
+        {
+            const bool on = lane < ((tcnt < 32) ? tcnt : 32);
+            const double2* src = reinterpret_cast<const double2*>(rec + t0 + (on ? lane : 0));
+            ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+        }
+        for (int b0 = 0; b0 < tcnt; b0 += 32) {
+            const int bcnt = (tcnt - b0) < 32 ? (tcnt - b0) : 32;
+            __syncwarp();
+            int mycell = -3;
+            {
+                // lanes >= bcnt park zeros so that k-steps may read the whole 32-record slab
+                const bool on = lane < bcnt;
+                const double m = on ? rd.x : 0.0;
+                val[0 * RS + lane] = ra.x * m; val[1 * RS + lane] = ra.y * m;
+                val[2 * RS + lane] = rb.x * m; val[3 * RS + lane] = rb.y * m;
+                if (on) mycell = (int)((unsigned long long)__double_as_longlong(rd.y) >> 32);
+                double cm = 1.0, sm = 0.0;
+                val[4 * RS + lane] = 1.0;
+#pragma unroll
+                for (int mm = 1; mm <= MCAP; ++mm) {
+                    if (mm <= g.mmax) {
+                        double cn = cm * rc.x - sm * rc.y, sn = sm * rc.x + cm * rc.y;
+                        cm = cn; sm = sn;
+                        val[(4 + mm) * RS + lane] = cm;
+                        val[(4 + g.mmax + mm) * RS + lane] = sm;
+                    }
+                }
+            }
+            if (b0 + 32 < tcnt) {
+                const bool on = (b0 + 32 + lane) < tcnt;
+                const double2* src = reinterpret_cast<const double2*>(rec + t0 + b0 + 32 + (on ? lane : 0));
+                ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+            }
+            // run boundaries inside this batch (bit p set: record p starts a new run)
+            int prevcell = __shfl_up_sync(0xffffffffu, mycell, 1);
+            if (lane == 0) prevcell = cur;
+            unsigned int bmask = __ballot_sync(0xffffffffu, (lane < bcnt) && (mycell != prevcell));
+            __syncwarp();
+
+#define BFE_FLUSH_RUN()                                                                                   \
+            do {                                                                                          \
+                __syncwarp();                                                                             \
+                if (a_on) {                                                                               \
+                    S[fg * 16 + 2 * fj] = c00; S[fg * 16 + 2 * fj + 1] = c01;                             \
+                    S[fg * 16 + 8 + 2 * fj] = c10; S[fg * 16 + 8 + 2 * fj + 1] = c11;                     \
+                }                                                                                         \
+                __syncwarp();                                                                             \
+                const int fx_ = cur / g.numy, fy_ = cur - fx_ * g.numy;                                   \
+                const double* bp_ = t_acc + (size_t)(fx_ * g.ny1 + fy_) * nch_pad + lane;                 \
+                _Pragma("unroll")                                                                         \
+                for (int c = 0; c < KCH; ++c) {                                                           \
+                    if (lane + 32 * c < nch) {                                                            \
+                        const double* q_ = bp_ + 32 * c;                                                  \
+                        const int ti_ = trig_idx[c];                                                      \
+                        acc[c] += __ldg(q_) * S[ti_] + __ldg(q_ + colstep) * S[16 + ti_] +                \
+                                  __ldg(q_ + rowstep) * S[32 + ti_] +                                     \
+                                  __ldg(q_ + colstep + rowstep) * S[48 + ti_];                            \
+                    }                                                                                     \
+                }                                                                                         \
+                c00 = 0.0; c01 = 0.0; c10 = 0.0; c11 = 0.0;                                               \
+            } while (0)
+
+            if (__popc(bmask) > SPARSE_RUNS) {
+                // ---- sparse batch: close the open run and hand the batch to the CTA-wide direct pass
+                if (cur >= 0) { BFE_FLUSH_RUN(); cur = -1; }
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_ndefer, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot < MAXDEFER) {
+                    if (lane == 0) s_defer[slot] = (int)(t0 + b0);       // n < 2^31
+                    continue;
+                }
+                // queue full (pathological input): fall through and do it here, run by run
+            }
+
+            int p = 0;
+            while (p < bcnt) {
+                if ((bmask >> p) & 1u) {
+                    if (cur >= 0) BFE_FLUSH_RUN();
+                    cur = __shfl_sync(0xffffffffu, mycell, p);
+                }
+                // end of this run within the batch: next boundary after p, or bcnt
+                const unsigned int later = (p < 31) ? (bmask >> (p + 1)) : 0u;
+                const int qend = later ? (p + __ffs(later)) : bcnt;
+                // k-steps of 4 records covering [p, qend); records outside the run are masked in A
+                for (int ks = p >> 2; ks * 4 < qend; ++ks) {
+                    const int r = ks * 4 + fj;
+                    const bool in = (r >= p) && (r < qend);
+                    const double a = (a_on && in) ? val[fg * RS + r] : 0.0;
+                    const double bt0 = val[(4 + fg) * RS + r];
+                    const double bt1 = b1_on ? val[(12 + fg) * RS + r] : 0.0;
+                    bfe_dmma_m8n8k4(c00, c01, a, bt0);
+                    bfe_dmma_m8n8k4(c10, c11, a, bt1);
+                }
+                p = qend;
+            }
+        }
+        if (cur >= 0) BFE_FLUSH_RUN();
+#undef BFE_FLUSH_RUN
+    }
+
+    // ---- deferred sparse batches: direct formulation, thread per channel, whole CTA
+    __syncthreads();
+    double accd = 0.0;
+    {
+        const int nd = s_ndefer < MAXDEFER ? s_ndefer : MAXDEFER;
+        int my_ti = 0;
+        if (tid < nch) my_ti = (tid < ncos) ? tid / g.norder : g.mmax + 1 + (tid - ncos) / g.norder;
+        double* v0 = s_slab[0];
+        for (int d = 0; d < nd; ++d) {
+            const int64_t r0 = s_defer[d];
+            const int bcnt = (int)((n - r0) < 32 ? (n - r0) : 32);
+            const int64_t tend = (r0 / TASK + 1) * (int64_t)TASK;           // batches never cross a task
+            const int cnt = (int)((tend - r0) < bcnt ? (tend - r0) : bcnt);
+            __syncthreads();
+            if (tid < 32) {
+                const bool on = tid < cnt;
+                const double2* src = reinterpret_cast<const double2*>(rec + r0 + (on ? tid : 0));
+                double2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), dd = __ldg(src + 3);
+                const double m = on ? dd.x : 0.0;
+                v0[0 * RS + tid] = a.x * m; v0[1 * RS + tid] = a.y * m; v0[2 * RS + tid] = b.x * m; v0[3 * RS + tid] = b.y * m;
+                const int cell = (int)((unsigned long long)__double_as_longlong(dd.y) >> 32);
+                const int ix = cell / g.numy, iy = cell - ix * g.numy;
+                s_dcell[tid] = on ? (ix * g.ny1 + iy) : 0;
+                double cm = 1.0, sm = 0.0;
+                v0[4 * RS + tid] = 1.0;
+#pragma unroll
+                for (int mm = 1; mm <= MCAP; ++mm) {
+                    if (mm <= g.mmax) {
+                        double cn = cm * c.x - sm * c.y, sn = sm * c.x + cm * c.y;
+                        cm = cn; sm = sn;
+                        v0[(4 + mm) * RS + tid] = cm;
+                        v0[(4 + g.mmax + mm) * RS + tid] = sm;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < nch) {
+                const double* tcol = t_acc + tid;
+                const double* trow = v0 + (4 + my_ti) * RS;
+#pragma unroll 4
+                for (int p = 0; p < 32; ++p) {
+                    const double* base = tcol + (size_t)s_dcell[p] * nch_pad;
+                    double v = __ldg(base) * v0[0 * RS + p] + __ldg(base + colstep) * v0[1 * RS + p] +
+                               __ldg(base + rowstep) * v0[2 * RS + p] + __ldg(base + colstep + rowstep) * v0[3 * RS + p];
+                    accd = fma(trow[p], v, accd);
+                }
+            }
+        }
+    }
+
+    // ---- CTA reduce over the 8 warps, then per-CTA partial and last-CTA final reduce
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) s_slab[warp][c * 32 + lane] = acc[c];
+    __syncthreads();
+    for (int j = tid; j < nch_pad; j += 256) {
+        double v = (j == tid) ? accd : 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += s_slab[w][j];
+        partial[(size_t)blockIdx.x * nch_pad + j] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int done = atomicAdd(counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int j = tid; j < nch; j += 256) {
+            double s = bfe_column_sum(partial, (int)gridDim.x, nch_pad, j) * BFE_FOURPI_NEG;
+            if (j < ncos) cos_out[j] = s;
+            else          sin_out[j - ncos + g.norder] = s;
+        }
+        for (int k = tid; k < g.norder; k += 256) sin_out[k] = 0.0;
+        if (tid == 0) *counter = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// force evaluation in sorted order
+// ---------------------------------------------------------------------------
+template <int MCAP>
+__global__ void __launch_bounds__(128)
+eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, int64_t n,
+                        const EofRec* __restrict__ rec, const double* __restrict__ r_sorted,
+                        double* __restrict__ p0, double* __restrict__ p, double* __restrict__ fr,
+                        double* __restrict__ fp, double* __restrict__ fz, double* __restrict__ R) {
+    // each CTA takes one contiguous slice of the sorted records: an SM then sees a contiguous range
+    // of cells and the contracted-grid rows stay in its L1
+    const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 127) / 128 * 128;
+    const int64_t lo = (int64_t)blockIdx.x * per;
+    const int64_t hi = (lo + per) < n ? (lo + per) : n;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double2* src = reinterpret_cast<const double2*>(rec + i);
+        double2 a = __ldg(src), bb = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+        unsigned long long cp = (unsigned long long)__double_as_longlong(d.y);
+        const int cell = (int)(cp >> 32);
+        const unsigned int dst = (unsigned int)(cp & 0xffffffffull);
+        EofBin b;
+        const int ix = cell / g.numy, iy = cell - ix * g.numy;
+        b.node = ix * g.ny1 + iy;
+        b.c00 = a.x; b.c10 = a.y; b.c01 = bb.x; b.c11 = bb.y;
+        EofField f = bfe_eof_eval<MCAP>(g, G, gstride, b, c.x, c.y);
+        p0[dst] = f.p0; p[dst] = f.p; fr[dst] = f.fr; fp[dst] = f.fp; fz[dst] = f.fz; R[dst] = __ldg(r_sorted + i);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct SortWs {
+    int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_sorted;
+};
+
+static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
+    const int ncell = h->g.numx * h->g.numy;
+    size_t o_hist = 0;
+    size_t o_start = align_up(o_hist + sizeof(int) * ncell, 256);
+    size_t o_cur = align_up(o_start + sizeof(int) * (ncell + 1), 256);
+    size_t o_rec = align_up(o_cur + sizeof(int) * ncell, 256);
+    if (n > h->sort_cap || !h->sort_ws) {
+        if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
+        int64_t cap = n + n / 8 + 1024;
+        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(EofRec) + sizeof(double)) * (size_t)cap));
+        BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
+        BFE_CUDA(cudaDeviceSynchronize());
+        h->sort_cap = cap;
+    }
+    char* b = (char*)h->sort_ws;
+    ws->hist = (int*)(b + o_hist); ws->cell_start = (int*)(b + o_start); ws->cursor = (int*)(b + o_cur);
+    ws->rec = (EofRec*)(b + o_rec);
+    ws->r_sorted = (double*)(b + o_rec + sizeof(EofRec) * (size_t)h->sort_cap);
+    return BFE_OK;
+}
+
+// counting sort of the particle set by table cell into the handle's workspace
+extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
+                               const double* mass, void* stream_) {
+    if (!h || n < 0) return BFE_ERR_ARG;
+    if (n > 0 && (!x || !y || !z)) return BFE_ERR_ARG;
+    if (n >= (int64_t)1 << 31) return BFE_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SortWs ws;
+    h->prepared_n = -1;
+    int rc = sort_workspace(h, n, &ws);
+    if (rc != BFE_OK) return rc;
+    const int ncell = h->g.numx * h->g.numy;
+    int grid = (int)((n + 1023) / 1024);
+    if (grid > h->num_sms * 2) grid = h->num_sms * 2;
+    if (grid < 1) grid = 1;
+    {
+        const int per = (ncell + 1023) / 1024;
+        const size_t ss = sizeof(int) * (size_t)per * 1024;
+        if (ss > 200 * 1024) return BFE_ERR_UNSUPPORTED;
+        if (ss > 48 * 1024)
+            BFE_CUDA(cudaFuncSetAttribute(eof_cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+        eof_cell_hist_kernel<<<grid, 1024, ss, stream>>>(h->g, ncell, n, x, y, z, ws.hist, ws.cell_start, ws.cursor,
+                                                        h->counter);
+    }
+    BFE_LAUNCH_CHECK("eof_cell_hist_kernel");
+    int g2 = (int)((n + 511) / 512);
+    if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
+    if (g2 < 1) g2 = 1;
+    eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cursor, ws.rec, ws.r_sorted);
+    BFE_LAUNCH_CHECK("eof_cell_scatter_kernel");
+    h->prepared_n = n;
+    h->prepared_has_mass = (mass || n == 0) ? 1 : 0;
+    return BFE_OK;
+}
+
+extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* sin_out, void* stream_) {
+    if (!h || !cos_out || !sin_out) return BFE_ERR_ARG;
+    if (h->prepared_n < 0 || !h->prepared_has_mass) return BFE_ERR_STATE;
+    if (h->g.mmax > 6 || h->nch_pad > 256) return BFE_ERR_UNSUPPORTED;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SortWs ws;
+    int rc = sort_workspace(h, h->prepared_n, &ws);
+    if (rc != BFE_OK) return rc;
+    const int64_t n = h->prepared_n;
+    int64_t nblk = (n + 128 * 8 - 1) / (128 * 8);          // 8 warp tasks of 128 records per CTA pass
+    int grid = (int)(nblk < (int64_t)h->num_sms * 2 ? nblk : (int64_t)h->num_sms * 2);
+    if (grid < 1) grid = 1;
+    eof_deposit_kernel<6, 8><<<grid, 256, 0, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, n, ws.rec, h->partial,
+                                                       h->counter, cos_out, sin_out);
+    BFE_LAUNCH_CHECK("eof_deposit_kernel");
+    return BFE_OK;
+}
+
+extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double* fr, double* fp, double* fz,
+                                      double* R, void* stream_) {
+    if (!h) return BFE_ERR_ARG;
+    if (h->prepared_n < 0 || !h->contracted) return BFE_ERR_STATE;
+    if (h->g.mmax > 6) return BFE_ERR_UNSUPPORTED;
+    const int64_t n = h->prepared_n;
+    if (n == 0) return BFE_OK;
+    if (!p0 || !p || !fr || !fp || !fz || !R) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SortWs ws;
+    int rc = sort_workspace(h, n, &ws);
+    if (rc != BFE_OK) return rc;
+    int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
+    int grid = (int)(need < cap ? need : cap);
+    eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.r_sorted,
+                                                         p0, p, fr, fp, fz, R);
+    BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
+    return BFE_OK;
+}
+
+int bfe_eof_accumulate_sorted(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
+                              const double* mass, double* cos_out, double* sin_out, cudaStream_t stream) {
+    int rc = bfe_eof_prepare(h, n, x, y, z, mass, (void*)stream);
+    if (rc != BFE_OK) return rc;
+    return bfe_eof_accumulate_prepared(h, cos_out, sin_out, (void*)stream);
+}
+
+int bfe_eof_force_sorted(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
+                         double* p0, double* p, double* fr, double* fp, double* fz, double* R, cudaStream_t stream) {
+    int rc = bfe_eof_prepare(h, n, x, y, z, nullptr, (void*)stream);
+    if (rc != BFE_OK) return rc;
+    return bfe_eof_force_prepared(h, p0, p, fr, fp, fz, R, (void*)stream);
+}

@@ -49,6 +49,11 @@ def to_host(t):
     return h.numpy()
 
 
+def set_option(name, value):
+    """bfe_set_option: 'eof_accumulate_mode' / 'eof_force_mode' (0 auto, 1 direct, 2 sorted), 'sort_min_particles'."""
+    _lib.check(_lib.load().bfe_set_option(name.encode(), int(value)))
+
+
 def launch_count():
     return int(_lib.load().bfe_launch_count())
 
@@ -106,6 +111,27 @@ class EOFTables(object):
         _lib.check(self.lib.bfe_eof_accumulate(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(m),
                                                _ptr(out[0]), _ptr(out[1]), _stream()))
         return out[0], out[1]
+
+    # -- one cell sort shared by accumulate and force evaluation on the same particles
+    def prepare(self, x, y, z, m=None):
+        """Counting-sort the particle set by table cell into the handle's workspace."""
+        x, y, z = dev(x), dev(y), dev(z)
+        m = dev(m) if m is not None else None
+        n = x.numel()
+        _lib.check(self.lib.bfe_eof_prepare(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _stream()))
+        self._prepared_n = n
+
+    def accumulate_prepared(self):
+        out = torch.empty((2, self.mmax + 1, self.norder), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_eof_accumulate_prepared(self.h, _ptr(out[0]), _ptr(out[1]), _stream()))
+        return out[0], out[1]
+
+    def force_prepared(self, out=None):
+        n = self._prepared_n
+        if out is None:
+            out = torch.empty((6, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_eof_force_prepared(self.h, *[_ptr(out[i]) for i in range(6)], _stream()))
+        return out
 
     def contract(self, cosc, sinc, m1=0, m2=1000, nuse=None, no_odd=False):
         cosc, sinc = self._coef(cosc), self._coef(sinc)

@@ -57,6 +57,10 @@ int  bfe_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t bfe_launch_count(void);
 
+/* Runtime options (process-wide).  "eof_accumulate_mode", "eof_force_mode": 0 = auto (cell-sorted
+ * kernels from "sort_min_particles" particles up, direct kernels below), 1 = direct, 2 = sorted. */
+int bfe_set_option(const char* name, int value);
+
 /* ---------------------------------------------------------------- EOF (disc) ---------------- */
 
 /* Tables in the reference layout [m][n][ix][iy] (eof.parse_eof, eof.py:224-313), each
@@ -73,6 +77,19 @@ void bfe_eof_destroy(bfe_eof* h);
 int bfe_eof_accumulate(bfe_eof* h, int64_t n,
                        const double* x, const double* y, const double* z, const double* mass,
                        double* cos_out, double* sin_out, void* stream);
+
+/* Cell-sorted particle set ("prepared" set), held in the handle's workspace until the next
+ * bfe_eof_prepare / bfe_eof_accumulate / bfe_eof_force* call on the same handle.  One counting sort by
+ * table cell serves both passes over the same particles (accumulate, then force evaluation):
+ *   bfe_eof_prepare(h, n, x, y, z, mass)        mass may be NULL if only forces are needed
+ *   bfe_eof_accumulate_prepared(h, cos, sin)    == bfe_eof_accumulate on that set
+ *   bfe_eof_force_prepared(h, p0, ..., R)       == bfe_eof_force_contracted on that set
+ * Outputs are in the caller's particle order.  Supported for mmax <= 6 and (2 mmax+1) norder <= 256. */
+int bfe_eof_prepare(bfe_eof* h, int64_t n,
+                    const double* x, const double* y, const double* z, const double* mass, void* stream);
+int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* sin_out, void* stream);
+int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double* fr, double* fp, double* fz, double* R,
+                           void* stream);
 
 /* Contract the tables with a coefficient set:  G_f[m,trig,node] = sum_{n<nuse} coef[m,n] T_f[m,n,node]
  * for m1 <= m <= min(m2, muse), skipping odd m if no_odd.  Must precede the *_contracted calls,
