@@ -247,8 +247,8 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     BFE_CUDA(cudaMalloc(&h->t_acc, (size_t)g.nnode * h->nch_pad * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * h->nch_pad * sizeof(double)));
-    BFE_CUDA(cudaMalloc(&h->counter, sizeof(unsigned int)));
-    BFE_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream));
+    BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
+    BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
     h->t_force = nullptr;
     if (rforceC && zforceC && rforceS && zforceS) {
         BFE_CUDA(cudaMalloc(&h->t_force, 6 * h->tab_elems * sizeof(double)));

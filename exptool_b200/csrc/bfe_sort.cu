@@ -170,6 +170,52 @@ __device__ __forceinline__ void bfe_dmma_m8n8k4(double& c0, double& c1, double a
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, mbarrier completion) helpers
+__device__ __forceinline__ unsigned int bfe_smem_u32(const void* p) {
+    return (unsigned int)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void bfe_mbar_init(unsigned int bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bfe_mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bfe_bulk_g2s(unsigned int dst, const void* src, unsigned int bytes, unsigned int bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bfe_mbar_wait(unsigned int bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// Optional per-warp cycle counters (build with BFE_NVCC_FLAGS=-DBFE_PROFILE_DEPOSIT; profiles/deposit_cycles.py)
+#ifdef BFE_PROFILE_DEPOSIT
+__device__ long long* g_dbg = nullptr;
+extern "C" int bfe_debug_set(long long* p) { return (int)cudaMemcpyToSymbol(g_dbg, &p, sizeof(p)); }
+#define DBG_DECL long long dbg_t0 = clock64(), dbg_tk = 0, dbg_flush = 0, dbg_mma = 0, dbg_expand = 0, dbg_nflush = 0, dbg_nks = 0, dbg_wait = 0
+#define DBG_TICK() (dbg_tk = clock64())
+#define DBG_ADD(var) do { long long t_ = clock64(); var += t_ - dbg_tk; dbg_tk = t_; } while (0)
+#else
+#define DBG_DECL
+#define DBG_TICK()
+#define DBG_ADD(var)
+#endif
+
+struct DepositSmem {
+    static constexpr int NW = 8;                  // warps per CTA
+    static constexpr int RS = 36;                 // slab row stride (doubles): conflict-free fragment loads
+    static constexpr int TROW = 256;              // max padded channels per node row
+    static constexpr int MAXDEFER = 160;
+};
+
 template <int MCAP, int KCH>
 __global__ void __launch_bounds__(256, 2)
 eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch_pad, int64_t n,
@@ -179,17 +225,20 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
     constexpr int SPARSE_RUNS = 20;               // batches with more run starts than this are deferred
     constexpr int NTRIG = 2 * MCAP + 1;
     constexpr int NV = 4 + NTRIG;                 // values per record in the slab
-    constexpr int NW = 8;                         // warps per CTA
-    constexpr int RS = 36;                        // slab row stride (doubles): conflict-free fragment loads
+    constexpr int NW = DepositSmem::NW, RS = DepositSmem::RS, TROW = DepositSmem::TROW;
+    constexpr int MAXDEFER = DepositSmem::MAXDEFER;
     constexpr int SLAB = NV * RS;
-    constexpr int MAXDEFER = 160;
     static_assert(SLAB >= KCH * 32, "slab reused for the CTA reduce");
     static_assert(NTRIG <= 16, "two n-tiles of 8 channels");
-    __shared__ double s_slab[NW][SLAB];           // [warp][value][record]
-    __shared__ double s_S[NW][64];                // [warp][corner k][16 channel slots]
-    __shared__ int s_defer[MAXDEFER];
+    // dynamic shared memory carve-up (about 107 kB; two CTAs per SM)
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tbuf = reinterpret_cast<double*>(s_raw);                    // [NW][4][TROW] table rows of the open run
+    double* s_slab = s_tbuf + NW * 4 * TROW;                              // [NW][SLAB]
+    double* s_S = s_slab + NW * SLAB;                                     // [NW][64]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_S + NW * 64);   // [NW] mbarriers
+    int* s_defer = reinterpret_cast<int*>(s_bar + NW);                    // [MAXDEFER]
+    int* s_dcell = s_defer + MAXDEFER;                                    // [32]
     __shared__ int s_ndefer;
-    __shared__ int s_dcell[32];
     __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -209,15 +258,28 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
 #pragma unroll
     for (int c = 0; c < KCH; ++c) acc[c] = 0.0;
     const int rowstep = nch_pad, colstep = g.ny1 * nch_pad;
+    const unsigned int rowbytes = 2u * (unsigned int)nch_pad * 8u;        // nodes (ix,iy),(ix,iy+1) are contiguous
 
-    double* val = s_slab[warp];                   // val[v * RS + p]
-    double* S = s_S[warp];
+    double* val = s_slab + warp * SLAB;           // val[v * RS + p]
+    double* S = s_S + warp * 64;
+    double* tb = s_tbuf + warp * 4 * TROW;        // [T00 | T01] [T10 | T11], each nch_pad wide
+    const unsigned int bar = bfe_smem_u32(s_bar + warp);
+    const unsigned int tb_u32 = bfe_smem_u32(tb);
+    unsigned int bar_parity = 0;
     if (tid == 0) s_ndefer = 0;
+    if (lane == 0) bfe_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+    // warps pull tasks from a global counter (counter[1]); the last CTA resets it
+    unsigned int* task_counter = counter + 1;
     const int64_t ntasks = (n + TASK - 1) / TASK;
-    const int64_t wglobal = (int64_t)blockIdx.x * NW + warp, wtotal = (int64_t)gridDim.x * NW;
-    for (int64_t task = wglobal; task < ntasks; task += wtotal) {
+    DBG_DECL;
+    for (;;) {
+        int64_t task = 0;
+        if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntasks) break;
         const int64_t t0 = task * TASK;
         const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;   // C fragments: tile 0 (ch 0..7), tile 1 (ch 8..15)
@@ -231,11 +293,16 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
         for (int b0 = 0; b0 < tcnt; b0 += 32) {
             const int bcnt = (tcnt - b0) < 32 ? (tcnt - b0) : 32;
             __syncwarp();
+            DBG_TICK();
             int mycell = -3;
             {
                 // lanes >= bcnt park zeros so that k-steps may read the whole 32-record slab
                 const bool on = lane < bcnt;
                 const double m = on ? rd.x : 0.0;
+#ifdef BFE_PROFILE_DEPOSIT
+                if (__double_as_longlong(m) == 0x7ff8dead00000000ll) dbg_wait = 1;   // force the load to complete
+                DBG_ADD(dbg_wait);
+#endif
                 val[0 * RS + lane] = ra.x * m; val[1 * RS + lane] = ra.y * m;
                 val[2 * RS + lane] = rb.x * m; val[3 * RS + lane] = rb.y * m;
                 if (on) mycell = (int)((unsigned long long)__double_as_longlong(rd.y) >> 32);
@@ -261,6 +328,21 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
             if (lane == 0) prevcell = cur;
             unsigned int bmask = __ballot_sync(0xffffffffu, (lane < bcnt) && (mycell != prevcell));
             __syncwarp();
+            DBG_ADD(dbg_expand);
+
+            // open a run: one lane issues two TMA bulk copies that bring the run's four table rows into the
+            // warp's buffer while the tensor cores sum the run; the flush then reads them from shared memory
+#define BFE_OPEN_RUN(cellv)                                                                               \
+            do {                                                                                          \
+                cur = (cellv);                                                                            \
+                if (lane == 0) {                                                                          \
+                    const int ox_ = cur / g.numy, oy_ = cur - ox_ * g.numy;                               \
+                    const double* src_ = t_acc + (size_t)(ox_ * g.ny1 + oy_) * nch_pad;                   \
+                    bfe_mbar_expect_tx(bar, 2u * rowbytes);                                               \
+                    bfe_bulk_g2s(tb_u32, src_, rowbytes, bar);                                            \
+                    bfe_bulk_g2s(tb_u32 + 2u * TROW * 8u, src_ + colstep, rowbytes, bar);                 \
+                }                                                                                         \
+            } while (0)
 
 #define BFE_FLUSH_RUN()                                                                                   \
             do {                                                                                          \
@@ -269,29 +351,29 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
                     S[fg * 16 + 2 * fj] = c00; S[fg * 16 + 2 * fj + 1] = c01;                             \
                     S[fg * 16 + 8 + 2 * fj] = c10; S[fg * 16 + 8 + 2 * fj + 1] = c11;                     \
                 }                                                                                         \
+                bfe_mbar_wait(bar, bar_parity);                                                           \
+                bar_parity ^= 1u;                                                                         \
                 __syncwarp();                                                                             \
-                const int fx_ = cur / g.numy, fy_ = cur - fx_ * g.numy;                                   \
-                const double* bp_ = t_acc + (size_t)(fx_ * g.ny1 + fy_) * nch_pad + lane;                 \
                 _Pragma("unroll")                                                                         \
                 for (int c = 0; c < KCH; ++c) {                                                           \
-                    if (lane + 32 * c < nch) {                                                            \
-                        const double* q_ = bp_ + 32 * c;                                                  \
+                    const int j_ = lane + 32 * c;                                                         \
+                    if (j_ < nch) {                                                                       \
                         const int ti_ = trig_idx[c];                                                      \
-                        acc[c] += __ldg(q_) * S[ti_] + __ldg(q_ + colstep) * S[16 + ti_] +                \
-                                  __ldg(q_ + rowstep) * S[32 + ti_] +                                     \
-                                  __ldg(q_ + colstep + rowstep) * S[48 + ti_];                            \
+                        acc[c] += tb[j_] * S[ti_] + tb[2 * TROW + j_] * S[16 + ti_] +                     \
+                                  tb[rowstep + j_] * S[32 + ti_] + tb[2 * TROW + rowstep + j_] * S[48 + ti_]; \
                     }                                                                                     \
                 }                                                                                         \
+                __syncwarp();                                                                             \
                 c00 = 0.0; c01 = 0.0; c10 = 0.0; c11 = 0.0;                                               \
             } while (0)
 
             if (__popc(bmask) > SPARSE_RUNS) {
                 // ---- sparse batch: close the open run and hand the batch to the CTA-wide direct pass
-                if (cur >= 0) { BFE_FLUSH_RUN(); cur = -1; }
                 int slot = 0;
                 if (lane == 0) slot = atomicAdd(&s_ndefer, 1);
                 slot = __shfl_sync(0xffffffffu, slot, 0);
                 if (slot < MAXDEFER) {
+                    if (cur >= 0) { BFE_FLUSH_RUN(); cur = -1; }
                     if (lane == 0) s_defer[slot] = (int)(t0 + b0);       // n < 2^31
                     continue;
                 }
@@ -301,9 +383,18 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
             int p = 0;
             while (p < bcnt) {
                 if ((bmask >> p) & 1u) {
-                    if (cur >= 0) BFE_FLUSH_RUN();
-                    cur = __shfl_sync(0xffffffffu, mycell, p);
+                    DBG_TICK();
+                    if (cur >= 0) {
+                        BFE_FLUSH_RUN();
+#ifdef BFE_PROFILE_DEPOSIT
+                        dbg_nflush++;
+                        if (__double_as_longlong(acc[0]) == 0x7ff8dead00000000ll) dbg_wait = 1;
+#endif
+                    }
+                    BFE_OPEN_RUN(__shfl_sync(0xffffffffu, mycell, p));
+                    DBG_ADD(dbg_flush);
                 }
+                DBG_TICK();
                 // end of this run within the batch: next boundary after p, or bcnt
                 const unsigned int later = (p < 31) ? (bmask >> (p + 1)) : 0u;
                 const int qend = later ? (p + __ffs(later)) : bcnt;
@@ -316,14 +407,25 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
                     const double bt1 = b1_on ? val[(12 + fg) * RS + r] : 0.0;
                     bfe_dmma_m8n8k4(c00, c01, a, bt0);
                     bfe_dmma_m8n8k4(c10, c11, a, bt1);
+#ifdef BFE_PROFILE_DEPOSIT
+                    dbg_nks++;
+#endif
                 }
+#ifdef BFE_PROFILE_DEPOSIT
+                if (__double_as_longlong(c00) == 0x7ff8dead00000000ll) dbg_wait = 1;
+#endif
+                DBG_ADD(dbg_mma);
                 p = qend;
             }
         }
         if (cur >= 0) BFE_FLUSH_RUN();
 #undef BFE_FLUSH_RUN
+#undef BFE_OPEN_RUN
     }
 
+#ifdef BFE_PROFILE_DEPOSIT
+    long long dbg_main = clock64() - dbg_t0;
+#endif
     // ---- deferred sparse batches: direct formulation, thread per channel, whole CTA
     __syncthreads();
     double accd = 0.0;
@@ -331,7 +433,7 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
         const int nd = s_ndefer < MAXDEFER ? s_ndefer : MAXDEFER;
         int my_ti = 0;
         if (tid < nch) my_ti = (tid < ncos) ? tid / g.norder : g.mmax + 1 + (tid - ncos) / g.norder;
-        double* v0 = s_slab[0];
+        double* v0 = s_slab;
         for (int d = 0; d < nd; ++d) {
             const int64_t r0 = s_defer[d];
             const int bcnt = (int)((n - r0) < 32 ? (n - r0) : 32);
@@ -374,15 +476,22 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
         }
     }
 
+#ifdef BFE_PROFILE_DEPOSIT
+    if (lane == 0 && g_dbg) {
+        long long* d = g_dbg + (blockIdx.x * NW + warp) * 8;
+        d[0] = dbg_main; d[1] = clock64() - dbg_t0; d[2] = dbg_wait; d[3] = dbg_expand; d[4] = dbg_mma;
+        d[5] = dbg_flush; d[6] = dbg_nflush; d[7] = dbg_nks;
+    }
+#endif
     // ---- CTA reduce over the 8 warps, then per-CTA partial and last-CTA final reduce
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < KCH; ++c) s_slab[warp][c * 32 + lane] = acc[c];
+    for (int c = 0; c < KCH; ++c) s_slab[warp * SLAB + c * 32 + lane] = acc[c];
     __syncthreads();
     for (int j = tid; j < nch_pad; j += 256) {
         double v = (j == tid) ? accd : 0.0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) v += s_slab[w][j];
+        for (int w = 0; w < NW; ++w) v += s_slab[w * SLAB + j];
         partial[(size_t)blockIdx.x * nch_pad + j] = v;
     }
     __threadfence();
@@ -400,8 +509,15 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
             else          sin_out[j - ncos + g.norder] = s;
         }
         for (int k = tid; k < g.norder; k += 256) sin_out[k] = 0.0;
-        if (tid == 0) *counter = 0u;
+        if (tid == 0) { counter[0] = 0u; counter[1] = 0u; }
     }
+}
+
+static size_t deposit_smem_bytes() {
+    const int NV = 4 + 13;
+    size_t doubles = (size_t)DepositSmem::NW * 4 * DepositSmem::TROW + (size_t)DepositSmem::NW * NV * DepositSmem::RS +
+                     (size_t)DepositSmem::NW * 64;
+    return doubles * 8 + DepositSmem::NW * 8 + (DepositSmem::MAXDEFER + 32) * 4 + 128;
 }
 
 // ---------------------------------------------------------------------------
@@ -510,8 +626,16 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
     int64_t nblk = (n + 128 * 8 - 1) / (128 * 8);          // 8 warp tasks of 128 records per CTA pass
     int grid = (int)(nblk < (int64_t)h->num_sms * 2 ? nblk : (int64_t)h->num_sms * 2);
     if (grid < 1) grid = 1;
-    eof_deposit_kernel<6, 8><<<grid, 256, 0, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, n, ws.rec, h->partial,
-                                                       h->counter, cos_out, sin_out);
+    {
+        static bool attr_set = false;
+        const size_t smem = deposit_smem_bytes();
+        if (!attr_set) {
+            BFE_CUDA(cudaFuncSetAttribute(eof_deposit_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        eof_deposit_kernel<6, 8><<<grid, 256, smem, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, n, ws.rec, h->partial,
+                                                             h->counter, cos_out, sin_out);
+    }
     BFE_LAUNCH_CHECK("eof_deposit_kernel");
     return BFE_OK;
 }

@@ -41,6 +41,7 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     flags = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--use_fast_math=false'][:-1]
     flags += ['-Xptxas', '-v'] if verbose else []
+    flags += [f for f in os.environ.get('BFE_NVCC_FLAGS', '').split() if f]
     procs = []
     objs = []
     for s in SOURCES:
