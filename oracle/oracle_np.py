@@ -553,6 +553,33 @@ def fields_forces_cart(F, xval, yval, zval, rotpos=0.0):
     return fxdisk, fxhalo, fydisk, fyhalo, fzdisk, fzhalo, diskp, (halop + halop0)
 
 
+def fields_forces_cyl(F, xval, yval, zval, rotpos=0.0):
+    """
+    Fields.return_forces_cyl (potential.py:389-440), vectorised over points:
+    (diskfr, frhalo, diskfp, -halofp, diskfz, fzhalo, -diskp, halop+halop0); r2, r3 use +1e-10.
+    """
+    xval = np.atleast_1d(np.asarray(xval, np.float64)); yval = np.atleast_1d(np.asarray(yval, np.float64))
+    zval = np.atleast_1d(np.asarray(zval, np.float64))
+    r2val = np.sqrt(xval * xval + yval * yval) + 1.e-10
+    r3val = np.sqrt(r2val * r2val + zval * zval) + 1.e-10
+    costh = zval / r3val
+    phival = np.arctan2(yval, xval)
+    diskfr, diskfp, diskfz, diskp, diskp0 = eof_force_eval(
+        r2val, zval, phival + rotpos, F.cos, F.sin, F.potC, F.rforceC, F.zforceC,
+        F.potS, F.rforceS, F.zforceS, F.XMIN, F.dX, F.YMIN, F.dY, F.numx, F.numy,
+        F.disk_use_m, F.disk_use_n, F.ascale, F.hscale, F.cmapdisk, no_odd=F.no_odd)
+    halofr, haloft, halofp, halop, halop0 = sl_force_eval(
+        r3val, costh, phival + rotpos, F.halofac * F.expcoef, F.xihalo, F.p0halo, F.d0halo,
+        F.cmaphalo, F.scalehalo, F.halo_use_l, F.halo_use_n, F.evtablehalo, F.eftablehalo,
+        no_odd=F.no_odd)
+    guard = r3val < np.min(F.xihalo)                       # potential.py:427-429
+    halofp = np.where(guard, 0., halofp)
+    diskfp = np.where(guard, 0., diskfp)
+    frhalo = -1. * (r2val * halofr + zval * haloft) / r3val
+    fzhalo = -1. * (zval * halofr - r2val * haloft) / r3val
+    return diskfr, frhalo, diskfp, -1. * halofp, diskfz, fzhalo, -1. * diskp, (halop + halop0)
+
+
 # ---------------------------------------------------------------------------
 # leapfrog -- integrate.py:53-190
 # ---------------------------------------------------------------------------

@@ -10,3 +10,8 @@ for p in (HERE, ROOT):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run with -m gpu on the B200 box)')
+
+
+def pytest_collection_modifyitems(config, items):
+    import warnings
+    warnings.filterwarnings('ignore', category=SyntaxWarning)      # the reference's own docstrings

@@ -202,6 +202,8 @@ def case_field(name, eparams, sparams, kind, seed, ndisc, nhalo, npts, norb, nin
         pz = np.concatenate([zd[:npts - 4], [0.0, -0.2, 1e-5, 0.05]])
         rot = 0.83
         cart_full = np.array([[float(v) for v in F.return_forces_cart(px[i], py[i], pz[i], rotpos=rot)] for i in range(npts)])
+        # Fields.return_forces_cyl (potential.py:389-440)
+        cyl_full = np.array([[float(v) for v in F.return_forces_cyl(px[i], py[i], pz[i], rotpos=rot)] for i in range(npts)])
         F.set_field_parameters(no_odd=True, halo_l=2, halo_n=3, disk_m=2, disk_n=3)
         cart_trunc = np.array([[float(v) for v in F.return_forces_cart(px[i], py[i], pz[i], rotpos=-0.4)] for i in range(npts)])
         F.reset_field_parameters()
@@ -226,12 +228,16 @@ def case_field(name, eparams, sparams, kind, seed, ndisc, nhalo, npts, norb, nin
     np.savez_compressed(os.path.join(HERE, name + '.npz'),
                         meta=json.dumps(dict(eof_params=eparams, sl_params=sparams, kind=kind, seed=seed, geo=g,
                                              halofac=1.25, rot_full=rot, rot_trunc=-0.4, dt=dt, rotfreq=rotfreq, nint=nint)),
-                        cos=cosd, sin=sind, coef=coef, px=px, py=py, pz=pz, cart_full=cart_full, cart_trunc=cart_trunc,
+                        cos=cosd, sin=sind, coef=coef, px=px, py=py, pz=pz, cart_full=cart_full, cart_trunc=cart_trunc, cyl_full=cyl_full,
                         pos0=pos0, vel0=vel0, orbits=np.array(orbs), orbit_trunc=orb_trunc, timestep=ts)
     print('wrote', name)
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'field':
+    case_field('field_small', dict(mmax=4, numx=48, numy=32, nmax=8, norder=6), dict(lmax=4, nmax=6, numr=400),
+               'smooth', 31, 3000, 800, 48, 3, 250)
+    case_field('field_std', {}, dict(lmax=6), 'smooth', 32, 4000, 600, 24, 2, 120)
+elif __name__ == '__main__':
     # EOF: small random (adversarial, cmap 1 and 0), standard-geometry smooth
     case_eof('eof_small_random_cmap1', dict(SMALL_EOF, cmap=1), 'random', 11, 400, 0.02, 0.002)
     case_eof('eof_small_random_cmap0', dict(SMALL_EOF, cmap=0, rmax=2.0), 'random', 12, 400, 0.005, 0.002)

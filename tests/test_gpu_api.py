@@ -1,0 +1,209 @@
+"""
+GPU tests through the reference-facing Python API (exptool_b200.basis.{eof,spheresl,potential},
+exptool_b200.utils.integrate): same call shapes as the reference, compared with the golden
+vectors the unmodified reference produced.  Run with -m gpu on the B200.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, relerr, S
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+ORBIT_TOL = 1e-8
+
+
+@pytest.fixture(scope='module')
+def api():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail('GPU tests selected but CUDA is not available')
+    from exptool_b200.basis import eof, spheresl, potential
+    from exptool_b200.utils import integrate, halo_methods
+    from exptool_b200.io import particle
+    return dict(eof=eof, spheresl=spheresl, potential=potential, integrate=integrate, halo_methods=halo_methods,
+                particle=particle)
+
+
+def _eof_file(tmp, meta):
+    pe, T = S.make_eof_tables(meta['eof_params'], kind=meta['kind'], seed=meta['seed'])
+    return S.write_eof_cache(os.path.join(tmp, 'eof.cache'), pe, T)
+
+
+def _sl_files(tmp, meta, seed_offset=0):
+    ps, ev, ef = S.make_sl_tables(meta['sl_params'], kind=meta['kind'], seed=meta['seed'] + seed_offset)
+    sf = S.write_sl_cache(os.path.join(tmp, 'sl.cache'), ps, ev, ef)
+    mf = S.write_hernquist_model(os.path.join(tmp, 'sl.model'), a=ps['scale'])
+    return sf, mf
+
+
+@pytest.mark.parametrize('name', ['eof_small_random_cmap1', 'eof_small_random_cmap0', 'eof_std_smooth'])
+def test_eof_api(api, name):
+    eof, particle = api['eof'], api['particle']
+    d, meta = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        f = _eof_file(tmp, meta)
+        potC, rfC, zfC, dC, potS, rfS, zfS, dS = eof.parse_eof(f)
+        rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, dens = eof.eof_params(f)
+        XMIN, XMAX, dX, YMIN, YMAX, dY = eof.set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ascale, HSCALE=hscale,
+                                                              NUMX=numx, NUMY=numy, CMAP=cmap)
+        P = S.ParticleSet(d['x'], d['y'], d['z'], d['m'])
+        # eof.accumulate, both container branches (eof.py:525 / 582)
+        c, s = eof.accumulate(P, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap)
+        assert isinstance(c, np.ndarray) and c.shape == (mmax + 1, norder) and c.dtype == np.float64
+        assert relerr(c, d['cos']) < TOL and relerr(s, d['sin']) < TOL
+        H = particle.holder(); H.xpos, H.ypos, H.zpos, H.mass = d['x'], d['y'], d['z'], d['m']
+        c2, s2 = eof.accumulate(H, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap,
+                                no_odd=True)          # no_odd has no effect in the reference either
+        assert relerr(c2, d['cos']) < TOL
+        # eof.make_coefficients_multi / eof.compute_coefficients
+        c3, s3 = eof.make_coefficients_multi(P, 3, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale,
+                                             hscale, cmap)
+        assert relerr(c3, d['cos_multi3']) < TOL and relerr(s3, d['sin_multi3']) < TOL
+        EO = eof.compute_coefficients(P, f, verbose=0)
+        assert EO.mmax == mmax and EO.nmax == norder and EO.nbodies == d['x'].size
+        assert relerr(EO.cos, d['cos']) < TOL and relerr(EO.sin, d['sin']) < TOL
+        # NaN positions are moved to the origin (the reference's intent at eof.py:1190-1204)
+        xn = d['x'].copy(); xn[10] = np.nan
+        x0 = d['x'].copy(); y0 = d['y'].copy(); z0 = d['z'].copy(); x0[10] = y0[10] = z0[10] = 0.0
+        En = eof.compute_coefficients(S.ParticleSet(xn, d['y'], d['z'], d['m']), f, verbose=0)
+        E0 = eof.compute_coefficients(S.ParticleSet(x0, y0, z0, d['m']), f, verbose=0)
+        assert relerr(En.cos, E0.cos) < 1e-13
+        # eof.accumulated_eval_particles / compute_forces
+        nf = meta['nforce']
+        Pf = S.ParticleSet(d['x'][:nf], d['y'][:nf], d['z'][:nf], d['m'][:nf])
+        kw = dict(potC=potC, rforceC=rfC, zforceC=zfC, potS=potS, rforceS=rfS, zforceS=zfS, rmin=XMIN, dR=dX,
+                  zmin=YMIN, dZ=dY, numx=numx, numy=numy, MMAX=mmax, NMAX=norder, ASCALE=ascale, HSCALE=hscale,
+                  CMAP=cmap, verbose=0)
+        full = eof.accumulated_eval_particles(Pf, d['cos'], d['sin'], **kw)
+        win = eof.accumulated_eval_particles(Pf, d['cos'], d['sin'], m1=1, m2=2, **kw)
+        byfile = eof.accumulated_eval_particles(Pf, d['cos'], d['sin'], eof_file=f, verbose=0)
+        EO.cos, EO.sin = d['cos'], d['sin']
+        cf = eof.compute_forces(Pf, EO, verbose=0)
+        for i in range(6):
+            assert relerr(full[i], d['full'][i]) < TOL, i
+            assert relerr(win[i], d['win12'][i]) < TOL, i
+            assert relerr(byfile[i], d['full'][i]) < TOL, i
+            assert relerr(cf[i], d['full'][i]) < TOL, i
+        # eof.force_eval, scalar calls as the reference makes them, and batched
+        variants = dict(full=dict(MMAX=mmax, NMAX=norder), trunc=dict(MMAX=max(mmax - 1, 1), NMAX=max(norder - 1, 1)),
+                        noodd=dict(MMAX=mmax, NMAX=norder, no_odd=True), perturb=dict(MMAX=mmax, NMAX=norder, perturb=True))
+        geo = dict(rmin=XMIN, dR=dX, zmin=YMIN, dZ=dY, numx=numx, numy=numy, ASCALE=ascale, HSCALE=hscale, CMAP=cmap)
+        for vname, v in variants.items():
+            ref = d['fe_' + vname]
+            out = eof.force_eval(d['pt_r'], d['pt_z'], d['pt_phi'], d['cos'], d['sin'], potC, rfC, zfC, potS, rfS, zfS,
+                                 **geo, **v)
+            assert len(out) == ref.shape[1]
+            for i in range(ref.shape[1]):
+                assert relerr(out[i], ref[:, i]) < TOL, (vname, i)
+            one = eof.force_eval(float(d['pt_r'][3]), float(d['pt_z'][3]), float(d['pt_phi'][3]), d['cos'], d['sin'],
+                                 potC, rfC, zfC, potS, rfS, zfS, **geo, **v)
+            assert all(np.ndim(o) == 0 for o in one)
+            assert max(abs(float(one[i]) - ref[3, i]) for i in range(ref.shape[1])) <= TOL * np.max(np.abs(ref))
+        with pytest.raises(NotImplementedError):
+            eof.accumulate(P, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap, VAR=3)
+
+
+@pytest.mark.parametrize('name', ['sl_small_random_cmap1', 'sl_small_random_cmap0', 'sl_std_l4', 'sl_std_l6'])
+def test_spheresl_api(api, name):
+    spheresl, halo_methods, particle = api['spheresl'], api['halo_methods'], api['particle']
+    d, meta = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        sf, mf = _sl_files(tmp, meta)
+        H = particle.holder(); H.xpos, H.ypos, H.zpos, H.mass = d['x'], d['y'], d['z'], d['m']
+        c = spheresl.compute_coefficients_solitary(H, sf, mf, verbose=0)
+        assert c.shape == d['coef'].shape and relerr(c, d['coef']) < TOL
+        c2 = spheresl.compute_coefficients_solitary(H, sf, mf, verbose=0, no_odd=True)
+        assert relerr(c2, d['coef_noodd']) < TOL
+        SO = spheresl.compute_coefficients(S.ParticleSet(d['x'], d['y'], d['z'], d['m']), sf, mf, verbose=0)
+        assert SO.lmax == meta['lmax'] and SO.nmax == meta['nmax'] and relerr(SO.expcoef, d['coef']) < TOL
+        assert SO.expcoef.dtype == np.float64
+        nf = meta['nforce']
+        Pf = S.ParticleSet(d['x'][1:nf + 1], d['y'][1:nf + 1], d['z'][1:nf + 1], d['m'][1:nf + 1])
+        for key, kw in (('allp', {}), ('allp_win12', dict(L1=1, L2=2)), ('allp_noodd', dict(NO_ODD=True))):
+            out = spheresl.all_eval_particles(Pf, d['coef'], sf, mf, 0, **kw)
+            assert len(out) == 8
+            for j in (2, 3, 4, 5, 6, 7):
+                assert relerr(out[j], d[key][j]) < TOL, (key, j)
+        lmax, nmax, numr, cmap, rmin, rmax, scale, ltable, evtable, eftable = halo_methods.read_cached_table(sf)
+        xi, rarr, p0, d0 = halo_methods.init_table(mf, numr, rmin, rmax, cmap=cmap, scale=scale)
+        a = (d['pt_r'], d['pt_costh'], d['pt_phi'], d['coef'], xi, p0, d0, cmap, scale)
+        for key, (l, n, no_odd) in dict(fe_full=(lmax, nmax, False), fe_trunc=(max(lmax - 1, 1), max(nmax - 2, 1), False),
+                                        fe_noodd=(lmax, nmax, True)).items():
+            out = spheresl.force_eval(*a, l, n, evtable, eftable, no_odd=no_odd)
+            for i in range(5):
+                assert relerr(out[i], d[key][:, i]) < TOL, (key, i)
+        one = spheresl.force_eval(float(d['pt_r'][2]), float(d['pt_costh'][2]), float(d['pt_phi'][2]), d['coef'], xi, p0,
+                                  d0, cmap, scale, lmax, nmax, evtable, eftable)
+        assert all(np.ndim(o) == 0 for o in one)
+        out = spheresl.all_eval(*a, lmax, nmax, evtable, eftable)
+        for j in (2, 3, 4, 5, 6):
+            assert relerr(out[j], d['ae_full'][:, j]) < TOL, j
+
+
+@pytest.mark.parametrize('name', ['field_small', 'field_std'])
+def test_fields_and_leapfrog_api(api, name):
+    potential, integrate = api['potential'], api['integrate']
+    d, meta = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        ef = _eof_file(tmp, meta)
+        sf, mf = _sl_files(tmp, meta, seed_offset=1)
+        F = potential.make_fields(ef, sf, mf, d['cos'], d['sin'], d['coef'], halofac=meta['halofac'])
+        out = F.return_forces_cart(d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+        cyl = F.return_forces_cyl(d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+        for i in range(8):
+            assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+            assert relerr(cyl[i], d['cyl_full'][:, i]) < TOL, i
+        one = F.return_forces_cart(float(d['px'][5]), float(d['py'][5]), float(d['pz'][5]), rotpos=meta['rot_full'])
+        assert len(one) == 8 and all(np.ndim(o) == 0 for o in one)
+        F.set_field_parameters(no_odd=True, halo_l=2, halo_n=3, disk_m=2, disk_n=3)
+        out = F.return_forces_cart(d['px'], d['py'], d['pz'], rotpos=meta['rot_trunc'])
+        for i in range(8):
+            assert relerr(out[i], d['cart_trunc'][:, i]) < TOL, i
+        F.reset_field_parameters()
+        # integrate.leapfrog_integrate, one orbit at a time as the reference is called
+        nint, dt = meta['nint'], meta['dt']
+        keys = ('X', 'Y', 'Z', 'VX', 'VY', 'VZ', 'P', 'FX', 'FY', 'FZ', 'TX', 'TY', 'VTX', 'VTY', 'T')
+        for k in range(d['orbits'].shape[0]):
+            Orb = integrate.leapfrog_integrate(F, nint, dt, d['pos0'][:, k], d['vel0'][:, k], rotfreq=meta['rotfreq'],
+                                               force=True)
+            for j, key in enumerate(keys):
+                assert Orb[key].shape == (nint,)
+                assert relerr(Orb[key], d['orbits'][k, j]) < ORBIT_TOL, (k, key)
+        Ot = integrate.leapfrog_integrate(F, nint, dt, d['pos0'][:, 0], d['vel0'][:, 0], rotfreq=3.0, no_odd=True,
+                                          halo_l=2, halo_n=4, disk_m=4, disk_n=5)
+        assert 'FX' not in Ot
+        for j, key in enumerate(('X', 'Y', 'Z', 'VX', 'VY', 'VZ', 'P', 'TX', 'TY', 'VTX', 'VTY', 'T')):
+            assert relerr(Ot[key], d['orbit_trunc'][j]) < ORBIT_TOL, key
+        # batched form == the per-orbit calls; apse counting stops orbits early
+        F.reset_field_parameters()
+        B = integrate.leapfrog_integrate_batch(F, nint, dt, d['pos0'], d['vel0'], rotfreq=meta['rotfreq'])
+        for k in range(d['orbits'].shape[0]):
+            assert abs(B['X'][k] - d['orbits'][k, 0, -1]) <= ORBIT_TOL * np.max(np.abs(d['orbits'][k, 0]))
+        Oa = integrate.leapfrog_integrate(F, 4 * nint, dt, d['pos0'][:, 0], d['vel0'][:, 0], rotfreq=0.0, apse=True, ap_max=1)
+        X, Y = Oa['X'], Oa['Y']
+        r2 = X * X + Y * Y
+        n = len(X)
+        if n < 4 * nint:          # an apocentre was found: it is the step before the last one returned
+            assert r2[n - 2] > r2[n - 3] and r2[n - 2] > r2[n - 1]
+
+
+def test_fields_total_coefficients_in_memory(api):
+    potential = api['potential']
+    with tempfile.TemporaryDirectory() as tmp:
+        ef, sf, mf = S.write_fixture_files(tmp, eof_params=dict(mmax=2, numx=16, numy=12, nmax=8, norder=3),
+                                           sl_params=dict(lmax=2, nmax=4, numr=100))
+        F = potential.Fields('memory', ef, sf, mf, verbose=0)
+        with pytest.raises(NotImplementedError):
+            F.total_coefficients()
+        disc = S.ParticleSet(*S.exponential_disc(3000, 1))
+        halo = S.ParticleSet(*S.hernquist_halo(2000, 2))
+        F.total_coefficients(disc=disc, halo=halo, halofac=2.0)
+        F.prep_tables()
+        a = F.return_forces_cart(0.01, 0.002, 0.0005)
+        assert len(a) == 8 and all(np.isfinite(a))
+        assert F.EOF.cos.shape == (3, 3) and F.SL.expcoef.shape == (9, 4) and F.halofac == 2.0

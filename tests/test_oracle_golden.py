@@ -111,6 +111,9 @@ def test_fields_forces_cart(name):
     out = O.fields_forces_cart(F, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
     for i in range(8):
         assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+    out = O.fields_forces_cyl(F, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+    for i in range(8):
+        assert relerr(out[i], d['cyl_full'][:, i]) < TOL, i
     F.set_field_parameters(no_odd=True, halo_l=2, halo_n=3, disk_m=2, disk_n=3)
     out = O.fields_forces_cart(F, d['px'], d['py'], d['pz'], rotpos=meta['rot_trunc'])
     for i in range(8):

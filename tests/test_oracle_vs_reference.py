@@ -1,0 +1,69 @@
+"""
+Live cross-check of the oracle against the UNMODIFIED reference on fresh seeds
+(not the committed goldens).  Runs only where /root/reference exists (the build
+container); skipped on the GPU box.  CPU only.
+"""
+import io
+import os
+import contextlib
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import relerr, O, S
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason='reference tree not present')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return refshim.load()
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_eof_accumulate_and_force_fresh_seed(ref):
+    eof = ref['eof']
+    with tempfile.TemporaryDirectory() as tmp:
+        pe, T = S.make_eof_tables(dict(mmax=4, numx=24, numy=16, nmax=8, norder=5, cmap=1), kind='random', seed=77)
+        f = S.write_eof_cache(os.path.join(tmp, 'c'), pe, T)
+        tabs = quiet(eof.parse_eof, f)
+        rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, dens = eof.eof_params(f)
+        XMIN, XMAX, dX, YMIN, YMAX, dY = eof.set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ascale, HSCALE=hscale,
+                                                              NUMX=numx, NUMY=numy, CMAP=cmap)
+    x, y, z, m = S.exponential_disc(700, 4242)
+    P = S.ParticleSet(x, y, z, m)
+    c, s = eof.accumulate(P, tabs[0], tabs[4], mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap)
+    geo = (float(XMIN), float(dX), float(YMIN), float(dY), int(numx), int(numy))
+    co, so = O.eof_accumulate(x, y, z, m, T['potC'], T['potS'], int(mmax), int(norder), *geo, ascale, hscale, int(cmap))
+    assert relerr(co, c) < 1e-12 and relerr(so, s) < 1e-12
+    Pf = S.ParticleSet(x[:60], y[:60], z[:60], m[:60])
+    ref_out = eof.accumulated_eval_particles(Pf, c, s, potC=tabs[0], rforceC=tabs[1], zforceC=tabs[2], potS=tabs[4],
+                                             rforceS=tabs[5], zforceS=tabs[6], rmin=XMIN, dR=dX, zmin=YMIN, dZ=dY,
+                                             numx=numx, numy=numy, MMAX=mmax, NMAX=norder, ASCALE=ascale,
+                                             HSCALE=hscale, CMAP=cmap, verbose=0)
+    out = O.eof_force_particles(x[:60], y[:60], z[:60], c, s, T['potC'], T['rforceC'], T['zforceC'], T['potS'],
+                                T['rforceS'], T['zforceS'], *geo, int(mmax), int(norder), ascale, hscale, int(cmap))
+    for i in range(6):
+        assert relerr(out[i], ref_out[i]) < 1e-12, i
+
+
+def test_sl_accumulate_fresh_seed(ref):
+    spheresl, particle = ref['spheresl'], ref['particle']
+    from helpers import hernquist_model_columns
+    with tempfile.TemporaryDirectory() as tmp:
+        ps, ev, ef = S.make_sl_tables(dict(lmax=3, nmax=4, numr=120), kind='random', seed=91)
+        sf = S.write_sl_cache(os.path.join(tmp, 's'), ps, ev, ef)
+        mf = S.write_hernquist_model(os.path.join(tmp, 'm'), a=ps['scale'])
+        x, y, z, m = S.hernquist_halo(150, 515)
+        H = particle.holder(); H.xpos, H.ypos, H.zpos, H.mass = x, y, z, m
+        c = np.asarray(quiet(spheresl.compute_coefficients_solitary, H, sf, mf), dtype=np.float64)
+    R1, D1, P1 = hernquist_model_columns(ps['scale'])
+    xi, r, p0, d0 = O.sl_init_table(R1, D1, P1, ps['numr'], ps['rmin'], ps['rmax'], ps['cmap'], ps['scale'])
+    co = O.sl_accumulate(x, y, z, m, ps['lmax'], ps['nmax'], ev, ef, xi, p0, ps['cmap'], ps['scale'])
+    assert relerr(co, c) < 1e-12
