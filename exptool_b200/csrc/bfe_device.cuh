@@ -266,82 +266,103 @@ __device__ __forceinline__ SlBin bfe_sl_bin(const SlGeom& g, const double* __res
 }
 
 // ---------------------------------------------------------------------------
-// SL field from contracted rows.  A[i][k] = sum_n c[k,n] eftable[l(k),n,i]/sqrt(ev[l,n])
-// (node-major, row stride kpad).  Restates spheresl.py:1041-1086 / 1200-1228 / 1289-1339
-// with the sum over n done once per coefficient set.
+// SL field from contracted rows.  A[i][q] (double2, q = l(l+1)/2 + m) holds
+//   .x = sum_n c[l^2 + 2m-1 (or l^2 for m=0), n] eftable[l,n,i]/sqrt(ev[l,n])   (cosine row)
+//   .y = sum_n c[l^2 + 2m, n] ...                                              (sine row; 0 for m=0)
+// Restates spheresl.py:1041-1086 / 1200-1228 / 1289-1339 with the sum over n done once per
+// coefficient set.  The loops run m-outer / l-inner so that only two Legendre values of the
+// current column are live (dlegendre needs P_l^m and P_{l-1}^m of the SAME m, spheresl.py:763):
+// every P_l^m, dP_l^m is produced by exactly the reference's chain of rounded operations.
 // ---------------------------------------------------------------------------
 struct SlField {
     double pot0, pot1, potr, pott, potp;
 };
 
 template <int LCAP>
-__device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double* __restrict__ A, int kpad,
+__device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double2* __restrict__ A, int qstride,
                                                const double* __restrict__ p0tab, const double* __restrict__ fac,
                                                const SlBin& b, double costh, double c1, double s1,
                                                bool trig_index_l) {
-    LegTable<LCAP> P, D;
-    bfe_legendre<LCAP>(g.lmax, costh, P);
-    bfe_dlegendre<LCAP>(g.lmax, costh, P, D);
-
     // nodes: potential uses (i, i+1); derivative stencil uses (j-1, j, j+1), j = max(i,1)
     const int j = (b.i == 0) ? 1 : b.i;
-    const double* rowm = A + (size_t)(j - 1) * kpad;
-    const double* row0 = A + (size_t)j * kpad;
-    const double* rowp = A + (size_t)(j + 1) * kpad;
+    const double2* rowm = A + (size_t)(j - 1) * qstride;
+    const double2* row0 = A + (size_t)j * qstride;
+    const double2* rowp = A + (size_t)(j + 1) * qstride;
     const double pm = __ldg(p0tab + j - 1), pc = __ldg(p0tab + j), pp = __ldg(p0tab + j + 1);
-    // weights so that pot = wA*A[j-1] + wB*A[j] + wC*A[j+1]
+    // weights so that pot = (wA*A[j-1] + wB*A[j] + wC*A[j+1]) * P0
     double P0, wA, wB, wC;
     if (b.i == 0) { P0 = b.x1 * pm + b.x2 * pc; wA = b.x1; wB = b.x2; wC = 0.0; }
     else          { P0 = b.x1 * pc + b.x2 * pp; wA = 0.0; wB = b.x1; wC = b.x2; }
-    const double dA = (b.x2 - 0.5) * pm, dB = -2.0 * b.x2 * pc, dC = (b.x2 + 0.5) * pp;
+    wA *= P0; wB *= P0; wC *= P0;
+    const double dA = b.fac * (b.x2 - 0.5) * pm, dB = b.fac * (-2.0 * b.x2) * pc, dC = b.fac * (b.x2 + 0.5) * pp;
+
+    const double x = costh;
+    const double somx2 = sqrt(BFE_MUL(BFE_SUB(1.0, x), BFE_ADD(1.0, x)));     // spheresl.py:679
+    double xd = x;                                                            // 751-755
+    if (1.0 - fabs(xd) < 1.0e-8) xd = (xd > 0.0) ? (1.0 - 1.0e-8) : -(1.0 - 1.0e-8);
+    const double dsom = BFE_DIV(1.0, BFE_SUB(BFE_MUL(xd, xd), 1.0));          // 757
 
     SlField f;
-    f.pot1 = 0.0; f.pott = 0.0; f.potp = 0.0;
-    {
-        double am = __ldg(rowm), a0 = __ldg(row0), ap = __ldg(rowp);
-        double sp = (wA * am + wB * a0 + wC * ap) * P0;
-        double sd = b.fac * (dA * am + dB * a0 + dC * ap);
-        double f00 = __ldg(fac);
-        f.pot0 = f00 * sp;
-        f.potr = f00 * sd;
-    }
-    // cos/sin(l phi) by recurrence for the force_eval quirk; cos/sin(m phi) otherwise
-    double cl = 1.0, sl = 0.0;
+    f.pot0 = 0.0; f.pot1 = 0.0; f.potr = 0.0; f.pott = 0.0; f.potp = 0.0;
+    double pmm = 1.0, fact = 1.0;
+    double cm = 1.0, sm = 0.0;
 #pragma unroll
-    for (int l = 1; l <= LCAP; ++l) {
-        if (l <= g.lmax) {
-            { double cn = cl * c1 - sl * s1; double sn = sl * c1 + cl * s1; cl = cn; sl = sn; }
-            const int k0 = l * l;
-            {   // m = 0
-                double am = __ldg(rowm + k0), a0 = __ldg(row0 + k0), ap = __ldg(rowp + k0);
-                double sp = (wA * am + wB * a0 + wC * ap) * P0;
-                double sd = b.fac * (dA * am + dB * a0 + dC * ap);
-                double fl = __ldg(fac + l * (g.lmax + 1));
-                f.pot1 += fl * P.p[l][0] * sp;
-                f.potr += fl * P.p[l][0] * sd;
-                f.pott += fl * D.p[l][0] * sp;
+    for (int m = 0; m <= LCAP; ++m) {
+        if (m <= g.lmax) {
+            if (m > 0) {
+                pmm = BFE_MUL(pmm, BFE_MUL(-fact, somx2));                    // 682
+                fact += 2.0;
+                double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1;
+                cm = cn; sm = sn;
             }
-            double cm = 1.0, sm = 0.0;
+            double pl2 = 0.0, pl1 = pmm;                                       // P_{l-1}^m, P_l^m at l = m
+            double cl = cm, sl = sm;                                           // cos/sin(l phi) at l = m
 #pragma unroll
-            for (int m = 1; m <= l; ++m) {
-                { double cn = cm * c1 - sm * s1; double sn = sm * c1 + cm * s1; cm = cn; sm = sn; }
-                const double ct = trig_index_l ? cl : cm;
-                const double st = trig_index_l ? sl : sm;
-                const int kc = k0 + 2 * m - 1;
-                double amc = __ldg(rowm + kc), a0c = __ldg(row0 + kc), apc = __ldg(rowp + kc);
-                double ams = __ldg(rowm + kc + 1), a0s = __ldg(row0 + kc + 1), aps = __ldg(rowp + kc + 1);
-                double spc = (wA * amc + wB * a0c + wC * apc) * P0;
-                double sps = (wA * ams + wB * a0s + wC * aps) * P0;
-                double sdc = b.fac * (dA * amc + dB * a0c + dC * apc);
-                double sds = b.fac * (dA * ams + dB * a0s + dC * aps);
-                double Ap = spc * ct + sps * st;
-                double Ad = sdc * ct + sds * st;
-                double Bp = -spc * st + sps * ct;
-                double fl = __ldg(fac + l * (g.lmax + 1) + m);
-                f.pot1 += fl * P.p[l][m] * Ap;
-                f.potr += fl * P.p[l][m] * Ad;
-                f.pott += fl * D.p[l][m] * Ap;
-                f.potp += fl * P.p[l][m] * (double)m * Bp;
+            for (int l = m; l <= LCAP; ++l) {
+                if (l <= g.lmax) {
+                    double P, dP;
+                    if (l == m) {
+                        P = pmm;
+                        dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);          // 765
+                    } else {
+                        if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);                      // 689
+                        else P = BFE_DIV(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                                 BFE_MUL((double)(l + m - 1), pl2)), (double)(l - m));   // 693
+                        dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P),
+                                                   BFE_MUL((double)(l + m), pl1)));                       // 763
+                        pl2 = pl1; pl1 = P;
+                        double cn = cl * c1 - sl * s1, sn = sl * c1 + cl * s1;
+                        cl = cn; sl = sn;
+                    }
+                    const int q = (l * (l + 1)) / 2 + m;
+                    const double2 am = __ldg(rowm + q), a0 = __ldg(row0 + q), ap = __ldg(rowp + q);
+                    const double fl = __ldg(fac + l * (g.lmax + 1) + m);
+                    const double spc = wA * am.x + wB * a0.x + wC * ap.x;
+                    const double sdc = dA * am.x + dB * a0.x + dC * ap.x;
+                    if (m == 0) {
+                        if (l == 0) {
+                            f.pot0 = fl * spc;
+                            f.potr += fl * sdc;
+                        } else {
+                            f.pot1 += fl * P * spc;
+                            f.potr += fl * P * sdc;
+                            f.pott += fl * dP * spc;
+                        }
+                    } else {
+                        const double sps = wA * am.y + wB * a0.y + wC * ap.y;
+                        const double sds = dA * am.y + dB * a0.y + dC * ap.y;
+                        const double ct = trig_index_l ? cl : cm;
+                        const double st = trig_index_l ? sl : sm;
+                        const double Ap = spc * ct + sps * st;
+                        const double Ad = sdc * ct + sds * st;
+                        const double Bp = sps * ct - spc * st;
+                        const double fP = fl * P;
+                        f.pot1 += fP * Ap;
+                        f.potr += fP * Ad;
+                        f.pott += fl * dP * Ap;
+                        f.potp += fP * (double)m * Bp;
+                    }
+                }
             }
         }
     }
@@ -359,7 +380,7 @@ struct CartForce {
 // diskfr, frhalo, diskfp, -halofp, diskfz, fzhalo, -diskp, halop+halop0.
 template <int MCAP, int LCAP, bool CYL = false>
 __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const double* __restrict__ G, int gstride,
-                                                    const SlGeom& gs, const double* __restrict__ A, int kpad,
+                                                    const SlGeom& gs, const double2* __restrict__ A, int kpad,
                                                     const double* __restrict__ xi, const double* __restrict__ p0tab,
                                                     const double* __restrict__ fac,
                                                     double x, double y, double z, double crot, double srot) {

@@ -11,7 +11,7 @@
 template <int MCAP, int LCAP, bool CYL>
 __global__ void __launch_bounds__(128)
 field_cart_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
-                  SlGeom gs, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+                  SlGeom gs, const double2* __restrict__ A, int kpad, const double* __restrict__ xi,
                   const double* __restrict__ p0tab, const double* __restrict__ fac,
                   int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                   const double* __restrict__ z, double crot, double srot, double* __restrict__ out8) {
@@ -32,7 +32,7 @@ field_cart_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
 template <int MCAP, int LCAP>
 __global__ void __launch_bounds__(128)
 leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
-                SlGeom gs, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+                SlGeom gs, const double2* __restrict__ A, int kpad, const double* __restrict__ xi,
                 const double* __restrict__ p0tab, const double* __restrict__ fac,
                 int64_t norbit, int64_t nint, double dt, double rotfreq,
                 double* __restrict__ state6, double* __restrict__ traj, int64_t traj_stride,
@@ -111,10 +111,10 @@ static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x,
     int grid = (int)(need < cap ? need : cap);
     double crot = cos(rotpos), srot = sin(rotpos);
     if (cyl)
-        FIELD_DISPATCH_CYL(true, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0, hs->fac, n,
+        FIELD_DISPATCH_CYL(true, he->g, he->g_con, he->gstride, hs->g, reinterpret_cast<const double2*>(hs->a_con), hs->kpad, hs->xi, hs->p0, hs->fac, n,
                            x, y, z, crot, srot, out8);
     else
-        FIELD_DISPATCH_CYL(false, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0, hs->fac,
+        FIELD_DISPATCH_CYL(false, he->g, he->g_con, he->gstride, hs->g, reinterpret_cast<const double2*>(hs->a_con), hs->kpad, hs->xi, hs->p0, hs->fac,
                            n, x, y, z, crot, srot, out8);
     BFE_LAUNCH_CHECK("field_cart_kernel");
     return BFE_OK;
@@ -141,7 +141,7 @@ extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nin
     if (ap_max < 1) ap_max = 1;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = (int)((norbit + 127) / 128);
-    FIELD_DISPATCH(leapfrog_kernel, he->g, he->g_con, he->gstride, hs->g, hs->a_con, hs->kpad, hs->xi, hs->p0,
+    FIELD_DISPATCH(leapfrog_kernel, he->g, he->g_con, he->gstride, hs->g, reinterpret_cast<const double2*>(hs->a_con), hs->kpad, hs->xi, hs->p0,
                    hs->fac, norbit, nint, dt, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
     BFE_LAUNCH_CHECK("leapfrog_kernel");
     return BFE_OK;

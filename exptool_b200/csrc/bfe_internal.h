@@ -58,7 +58,7 @@ struct bfe_sl {
     double* d0;          // [numr]
     double* fac;         // factorial_return [(lmax+1)*(lmax+1)]
     double fac_host[(BFE_MAX_LMAX + 1) * (BFE_MAX_LMAX + 1)];
-    double* a_con;       // contracted rows, node-major [numr][kpad]
+    double* a_con;       // contracted rows, node-major [numr][kpad] of double2 (cos, sin), kpad = (l,m) pairs
     int kpad;
     int contracted;
     double* partial;     // [max_ctas][nrow*nmax]

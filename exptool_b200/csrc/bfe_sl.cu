@@ -149,29 +149,34 @@ sl_reduce_partials_kernel(const double* __restrict__ partial, int nrows, int nco
     }
 }
 
-// A[i][k] = sum_{n<nuse} c[k][n] * e_node[i][l(k)][n]; rows outside the l window are zero
+// A[i][q] (double2, q = l(l+1)/2 + m): .x = cosine row k = l^2 (m=0) or l^2+2m-1, .y = sine row k = l^2+2m.
+// A[i][q].{x,y} = sum_{n<nuse} c[k][n] * e_node[i][l][n]; rows outside the l window are zero.
+// grid: (ceil(numr/128), nrow); the m=0 sine slots stay zero from create().
 __global__ void sl_contract_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ expcoef,
-                                   int l1, int l2, int nuse, int no_odd, double* __restrict__ A, int kpad) {
+                                   int l1, int l2, int nuse, int no_odd, double* __restrict__ A, int qstride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
-    if (i >= g.numr) return;
+    if (i >= g.numr || k >= g.nrow) return;
     int l = (int)sqrt((double)k);
     while ((l + 1) * (l + 1) <= k) ++l;
     while (l * l > k) --l;
+    const int r = k - l * l;                       // 0: m=0 ; odd: cos m=(r+1)/2 ; even: sin m=r/2
+    const int m = (r + 1) / 2;
+    const int comp = (r > 0 && (r & 1) == 0) ? 1 : 0;
     double s = 0.0;
     bool use = (l == 0) || ((l >= l1) && (l <= l2) && !(no_odd && (l & 1)));
-    if (k < g.nrow && use) {
+    if (use) {
         const double* e = e_node + (size_t)i * g.ln + l * g.nmax;
         const double* c = expcoef + (size_t)k * g.nmax;
         const int nn = nuse < g.nmax ? nuse : g.nmax;
         for (int q = 0; q < nn; ++q) s = fma(__ldg(c + q), __ldg(e + q), s);
     }
-    A[(size_t)i * kpad + k] = s;
+    A[((size_t)i * qstride + (l * (l + 1)) / 2 + m) * 2 + comp] = s;
 }
 
 template <int LCAP>
 __global__ void __launch_bounds__(128)
-sl_force_kernel(SlGeom g, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+sl_force_kernel(SlGeom g, const double2* __restrict__ A, int kpad, const double* __restrict__ xi,
                 const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                 double* __restrict__ pot0, double* __restrict__ pot1, double* __restrict__ potr,
@@ -192,7 +197,7 @@ sl_force_kernel(SlGeom g, const double* __restrict__ A, int kpad, const double* 
 
 template <int LCAP>
 __global__ void __launch_bounds__(128)
-sl_points_kernel(SlGeom g, const double* __restrict__ A, int kpad, const double* __restrict__ xi,
+sl_points_kernel(SlGeom g, const double2* __restrict__ A, int kpad, const double* __restrict__ xi,
                  const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
                  const double* __restrict__ r, const double* __restrict__ costh, const double* __restrict__ phi,
                  int trig_index_l,
@@ -257,7 +262,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaStreamSynchronize(stream));
     g.xi0 = xi01[0];                        // np.min(xi), spheresl.py:319
     g.dxi = xi01[1] - xi01[0];              // xi[1]-xi[0], spheresl.py:317
-    h->kpad = (g.nrow + 1) / 2 * 2;
+    h->kpad = (p->lmax + 1) * (p->lmax + 2) / 2;     // (l,m) pairs per radial node, one double2 each
     h->contracted = 0;
     h->max_ctas = h->num_sms * 6;
     size_t nr = (size_t)p->numr;
@@ -266,11 +271,11 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->p0, nr * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->d0, nr * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->fac, sizeof(double) * (p->lmax + 1) * (p->lmax + 1)));
-    BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * 2 * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream));
-    BFE_CUDA(cudaMemsetAsync(h->a_con, 0, nr * h->kpad * sizeof(double), stream));
+    BFE_CUDA(cudaMemsetAsync(h->a_con, 0, nr * h->kpad * 2 * sizeof(double), stream));
     BFE_CUDA(cudaMemcpyAsync(h->xi, xi, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     BFE_CUDA(cudaMemcpyAsync(h->p0, p0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     if (d0) BFE_CUDA(cudaMemcpyAsync(h->d0, d0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -316,7 +321,7 @@ extern "C" int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2,
     if (!h || !expcoef) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nuse < 0) nuse = 0;
-    dim3 grd((h->g.numr + 127) / 128, h->kpad);
+    dim3 grd((h->g.numr + 127) / 128, h->g.nrow);
     sl_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->e_node, expcoef, l1, l2, nuse, no_odd, h->a_con, h->kpad);
     BFE_LAUNCH_CHECK("sl_contract_kernel");
     h->contracted = 1;
@@ -339,7 +344,7 @@ extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, co
     if (!x || !y || !z || !pot0 || !pot1 || !potr || !pott || !potp || !rr) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
-    SL_DISPATCH(sl_force_kernel, h->g, h->a_con, h->kpad, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott,
+    SL_DISPATCH(sl_force_kernel, h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott,
                 potp, rr);
     BFE_LAUNCH_CHECK("sl_force_kernel");
     return BFE_OK;
@@ -365,7 +370,7 @@ extern "C" int bfe_sl_force_eval_points(bfe_sl* h, int64_t n, const double* r, c
     if (!r || !costh || !phi || !potr || !pott || !potp || !pot1 || !pot0) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
-    SL_DISPATCH(sl_points_kernel, h->g, h->a_con, h->kpad, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l,
+    SL_DISPATCH(sl_points_kernel, h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l,
                 potr, pott, potp, pot1, pot0);
     BFE_LAUNCH_CHECK("sl_points_kernel");
     return BFE_OK;
