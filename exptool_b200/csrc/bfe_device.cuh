@@ -215,6 +215,41 @@ __device__ __forceinline__ void bfe_legendre(int lmax, double x, LegTable<LCAP>&
     }
 }
 
+// Same table with fused multiply-adds and reciprocal constants (a few ulp from the reference): used by
+// the accumulation kernels, which need no derivative and therefore no bit-matching.
+template <int LCAP>
+__device__ __forceinline__ void bfe_legendre_fast(int lmax, double x, LegTable<LCAP>& T) {
+    T.p[0][0] = 1.0;
+    double pll = 1.0;
+    const double somx2 = sqrt((1.0 - x) * (1.0 + x));
+    double fact = 1.0;
+#pragma unroll
+    for (int m = 1; m <= LCAP; ++m) {
+        if (m <= lmax) {
+            pll *= -fact * somx2;
+            T.p[m][m] = pll;
+            fact += 2.0;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < LCAP; ++m) {
+        if (m < lmax) {
+            double pl2 = T.p[m][m];
+            double pl1 = x * (2.0 * m + 1.0) * pl2;
+            T.p[m + 1][m] = pl1;
+#pragma unroll
+            for (int l = m + 2; l <= LCAP; ++l) {
+                if (l <= lmax) {
+                    double v = (x * (double)(2 * l - 1) * pl1 - (double)(l + m - 1) * pl2) * (1.0 / (double)(l - m));
+                    T.p[l][m] = v;
+                    pl2 = pl1;
+                    pl1 = v;
+                }
+            }
+        }
+    }
+}
+
 // derivative table, spheresl.py:751-768; p must already hold legendre(x)
 template <int LCAP>
 __device__ __forceinline__ void bfe_dlegendre(int lmax, double x, const LegTable<LCAP>& T, LegTable<LCAP>& D) {

@@ -156,11 +156,13 @@ static thread_local char g_cuda_err[256] = "";
 int g_bfe_eof_accumulate_mode = 0;
 int g_bfe_eof_force_mode = 0;
 int g_bfe_sort_min_particles = 32768;
+int g_bfe_sl_accumulate_mode = 0;
 
 extern "C" int bfe_set_option(const char* name, int value) {
     if (!name) return BFE_ERR_ARG;
     if (!strcmp(name, "eof_accumulate_mode")) { g_bfe_eof_accumulate_mode = value; return BFE_OK; }
     if (!strcmp(name, "eof_force_mode")) { g_bfe_eof_force_mode = value; return BFE_OK; }
+    if (!strcmp(name, "sl_accumulate_mode")) { g_bfe_sl_accumulate_mode = value; return BFE_OK; }
     if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
     return BFE_ERR_ARG;
 }

@@ -64,6 +64,9 @@ struct bfe_sl {
     double* partial;     // [max_ctas][nrow*nmax]
     unsigned int* counter;
     int max_ctas;
+    // radial-bin-sorted accumulate workspace (grown on demand)
+    int64_t sort_cap;
+    void* sort_ws;
 };
 
 extern "C" void bfe_count_launch(int n);
@@ -72,6 +75,11 @@ extern "C" void bfe_count_launch(int n);
 extern int g_bfe_eof_accumulate_mode;
 extern int g_bfe_eof_force_mode;
 extern int g_bfe_sort_min_particles;
+extern int g_bfe_sl_accumulate_mode;
+
+bool bfe_sl_sorted_supported(const bfe_sl* h);
+int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                             const double* mass, int no_odd, double* expcoef, cudaStream_t stream);
 
 int bfe_eof_accumulate_sorted(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
                               const double* mass, double* cos_out, double* sin_out, cudaStream_t stream);

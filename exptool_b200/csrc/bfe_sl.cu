@@ -70,7 +70,7 @@ sl_accumulate_kernel(SlGeom g, const double* __restrict__ e_node, const double* 
             double c1, s1;
             bfe_cossin_phi(px, py, c1, s1);                       // 613
             LegTable<LCAP> P;
-            bfe_legendre<LCAP>(g.lmax, costh, P);                 // 618
+            bfe_legendre_fast<LCAP>(g.lmax, costh, P);            // 618
             SlBin b = bfe_sl_bin(g, xi, r);                       // 623 -> 309-328
             double P0 = b.x1 * __ldg(p0tab + b.i) + b.x2 * __ldg(p0tab + b.i + 1);
             double W = BFE_FOURPI_NEG * pm * P0;
@@ -230,7 +230,11 @@ static int sl_acc_launch(bfe_sl* h, int64_t n, const double* x, const double* y,
     if (block > 256) return BFE_ERR_UNSUPPORTED;
     size_t smem = ((size_t)h->g.nrow * TILE + 2 * TILE) * sizeof(double) + TILE * sizeof(int);
     auto kern = sl_accumulate_kernel<LCAP, TILE>;
-    BFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr_smem = 0;                  // one per template instance; grows with nrow
+    if (smem > attr_smem) {
+        BFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
     int64_t ntiles = (n + TILE - 1) / TILE;
     int grid = (int)(ntiles < h->max_ctas ? (ntiles < 1 ? 1 : ntiles) : h->max_ctas);
     kern<<<grid, block, smem, stream>>>(h->g, h->e_node, h->xi, h->p0, h->fac, n, x, y, z, mass, no_odd,
@@ -273,8 +277,9 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->fac, sizeof(double) * (p->lmax + 1) * (p->lmax + 1)));
     BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * 2 * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
-    BFE_CUDA(cudaMalloc(&h->counter, sizeof(unsigned int)));
-    BFE_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream));
+    BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
+    BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
+    h->sort_cap = 0; h->sort_ws = nullptr;
     BFE_CUDA(cudaMemsetAsync(h->a_con, 0, nr * h->kpad * 2 * sizeof(double), stream));
     BFE_CUDA(cudaMemcpyAsync(h->xi, xi, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     BFE_CUDA(cudaMemcpyAsync(h->p0, p0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -303,6 +308,7 @@ extern "C" void bfe_sl_destroy(bfe_sl* h) {
     if (!h) return;
     cudaFree(h->e_node); cudaFree(h->xi); cudaFree(h->p0); cudaFree(h->d0); cudaFree(h->fac);
     cudaFree(h->a_con); cudaFree(h->partial); cudaFree(h->counter);
+    if (h->sort_ws) cudaFree(h->sort_ws);
     delete h;
 }
 
@@ -311,6 +317,12 @@ extern "C" int bfe_sl_accumulate(bfe_sl* h, int64_t n, const double* x, const do
     if (!h || n < 0 || !expcoef) return BFE_ERR_ARG;
     if (n > 0 && (!x || !y || !z || !mass)) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
+    {
+        const int mode = g_bfe_sl_accumulate_mode;
+        // the sorted pipeline has ~60 us of fixed cost (4 launches): it wins from a few 1e5 particles up
+        if (bfe_sl_sorted_supported(h) && (mode == 2 || (mode == 0 && n >= 8 * (int64_t)g_bfe_sort_min_particles)))
+            return bfe_sl_accumulate_sorted(h, n, x, y, z, mass, no_odd, expcoef, stream);
+    }
     if (h->g.lmax <= 4) return sl_acc_launch<4, 128>(h, n, x, y, z, mass, no_odd, expcoef, stream);
     if (h->g.lmax <= 6) return sl_acc_launch<6, 128>(h, n, x, y, z, mass, no_odd, expcoef, stream);
     return sl_acc_launch<BFE_MAX_LMAX, 32>(h, n, x, y, z, mass, no_odd, expcoef, stream);

@@ -1,0 +1,487 @@
+// bfe_sl_sort.cu -- radial-bin-sorted SL accumulation (spheresl.compute_coefficients_solitary,
+// spheresl.py:567-656), the SL counterpart of bfe_sort.cu.
+//
+// The direct kernel (bfe_sl.cu) reads two radial-node rows (2 x (lmax+1) nmax doubles, ~2 kB) per
+// particle from L2.  Linear interpolation is linear in the table, so for all particles of one radial
+// interval i
+//     expcoef[k,n] += D1[k] E[i][l(k)][n] + D2[k] E[i+1][l(k)][n],
+//     D1[k] = sum_p w_k(p) x1(p),  D2[k] = sum_p w_k(p) x2(p),
+//     w_k(p) = -4 pi m_p P0(p) f_lm P_l^m(cos theta_p) {1 | cos m phi_p | sin m phi_p}.
+// Particles are counting-sorted by radial interval (integer keys and cursors only), a warp sums D over a
+// run of equal intervals in registers and reads the two node rows once per RUN (TMA bulk copy,
+// prefetched when the run opens).  No floating-point atomics.
+//
+//   sl_bin_hist_kernel    : radial interval per particle -> histogram; last CTA scans it
+//   sl_bin_scatter_kernel : 64-B record {x1, x2, W = -4 pi m P0, cos theta, cos phi, sin phi, -, bin:perm}
+//   sl_deposit_kernel     : runs -> D -> coefficient partials
+//   sl_sorted_reduce_kernel : column sums of the per-CTA partials
+#include "bfe_device.cuh"
+#include "bfe_sortcore.cuh"
+
+struct __align__(16) SlRec {
+    double x1, x2;               // linear weights of nodes i, i+1 (spheresl.py:327-328)
+    double W;                    // -4 pi m (x1 p0[i] + x2 p0[i+1])
+    double costh;
+    double c1, s1;               // cos phi, sin phi
+    double pad;
+    unsigned long long binperm;  // (i << 32) | original particle index
+};
+
+struct SlPrep {
+    int i;
+    double x1, x2, W, costh, c1, s1;
+};
+
+__device__ __forceinline__ SlPrep bfe_sl_prep(const SlGeom& g, const double* __restrict__ xi,
+                                              const double* __restrict__ p0tab, double px, double py, double pz,
+                                              double pm) {
+    SlPrep o;
+    double r2 = BFE_ADD(BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py)), BFE_MUL(pz, pz));   // spheresl.py:610
+    double r = fmax(sqrt(r2), 1.0e-10);                                                // 611
+    o.costh = BFE_DIV(pz, r);                                                          // 612
+    bfe_cossin_phi(px, py, o.c1, o.s1);                                                // 613
+    SlBin b = bfe_sl_bin(g, xi, r);                                                    // 309-328
+    o.i = b.i; o.x1 = b.x1; o.x2 = b.x2;
+    double P0 = b.x1 * __ldg(p0tab + b.i) + b.x2 * __ldg(p0tab + b.i + 1);
+    o.W = BFE_FOURPI_NEG * pm * P0;
+    return o;
+}
+
+__global__ void __launch_bounds__(1024)
+sl_bin_hist_kernel(SlGeom g, const double* __restrict__ xi, int nbin, int64_t n, const double* __restrict__ x,
+                   const double* __restrict__ y, const double* __restrict__ z, int* __restrict__ hist,
+                   int* __restrict__ bin_start, int* __restrict__ cursor, unsigned int* __restrict__ counter) {
+    extern __shared__ int s_hist[];
+    __shared__ int s_wsum[32];
+    __shared__ bool s_last;
+    for (int c = threadIdx.x; c < nbin; c += blockDim.x) s_hist[c] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        double r2 = BFE_ADD(BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py)), BFE_MUL(pz, pz));
+        double r = fmax(sqrt(r2), 1.0e-10);
+        SlBin b = bfe_sl_bin(g, xi, r);
+        atomicAdd(&s_hist[b.i], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nbin; c += blockDim.x) {
+        int v = s_hist[c];
+        if (v) atomicAdd(&hist[c], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(counter, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        bfe_block_scan_cells(nbin, hist, bin_start, cursor, s_hist, s_wsum);
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sl_bin_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __restrict__ p0tab, int64_t n,
+                      const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                      const double* __restrict__ mass, int* __restrict__ cursor, SlRec* __restrict__ rec) {
+    constexpr int U = 2;
+    for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
+        SlPrep pr[U];
+        int pos[U];
+        int64_t idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            idx[u] = base + u * 256 + threadIdx.x;
+            const bool on = idx[u] < n;
+            double px = on ? __ldg(x + idx[u]) : 1.0, py = on ? __ldg(y + idx[u]) : 0.0, pz = on ? __ldg(z + idx[u]) : 0.0;
+            double pm = on ? __ldg(mass + idx[u]) : 0.0;
+            pr[u] = bfe_sl_prep(g, xi, p0tab, px, py, pz, pm);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) pos[u] = (idx[u] < n) ? atomicAdd(&cursor[pr[u].i], 1) : 0;   // integer slot claim
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (idx[u] < n) {
+                unsigned long long bp = ((unsigned long long)(unsigned int)pr[u].i << 32) |
+                                        (unsigned long long)(unsigned int)idx[u];
+                double2* dst = reinterpret_cast<double2*>(rec + pos[u]);
+                dst[0] = make_double2(pr[u].x1, pr[u].x2);
+                dst[1] = make_double2(pr[u].W, pr[u].costh);
+                dst[2] = make_double2(pr[u].c1, pr[u].s1);
+                dst[3] = make_double2(0.0, __longlong_as_double((long long)bp));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// deposit: a warp owns TASK consecutive sorted records (dynamic task queue).
+//   expand (lanes = records): P_l^m recurrence (explicitly rounded, as bfe_legendre), cos/sin(m phi),
+//     w_k for all (lmax+1)^2 rows into the warp's shared-memory slab, plus x1, x2;
+//   sum   (lanes = rows k, two per lane): D1[k] += w_k x1, D2[k] += w_k x2 over the run;
+//   flush (cell change, warp-uniform): lane j = lane + 32 c adds D1[k(j)] E[i][..] + D2[k(j)] E[i+1][..]
+//     to its register accumulators; the two node rows were fetched by one TMA bulk copy when the run opened.
+// ---------------------------------------------------------------------------
+#ifdef BFE_PROFILE_DEPOSIT
+__device__ long long* g_sl_dbg = nullptr;
+extern "C" int bfe_sl_debug_set(long long* p) { return (int)cudaMemcpyToSymbol(g_sl_dbg, &p, sizeof(p)); }
+#define SDBG_DECL long long sd_t0 = clock64(), sd_tk = 0, sd_expand = 0, sd_sum = 0, sd_flush = 0, sd_nflush = 0, sd_ntask = 0, sd_wait = 0
+#define SDBG_TICK() (sd_tk = clock64())
+#define SDBG_ADD(var) do { long long t_ = clock64(); var += t_ - sd_tk; sd_tk = t_; } while (0)
+#else
+#define SDBG_DECL
+#define SDBG_TICK()
+#define SDBG_ADD(var)
+#endif
+
+template <int LCAP, int KC>
+__global__ void __launch_bounds__(128, 3)
+sl_deposit_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ fac, int no_odd,
+                  int64_t n, const SlRec* __restrict__ rec, double* __restrict__ partial,
+                  unsigned int* __restrict__ counter, int use_tma) {
+    constexpr int TASK = 128;
+    constexpr int NW = 4;                          // warps per CTA
+    constexpr int NROWCAP = (LCAP + 1) * (LCAP + 1);
+    constexpr int RS = 33;                         // slab row stride: lanes = rows read one column conflict-free
+    constexpr int SLAB = (NROWCAP + 2) * RS;
+    constexpr int TB = 2 * (LCAP + 1) * 32;        // table rows of the open run: 2 nodes x ln (<= (LCAP+1)*32) doubles
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double* s_tb = reinterpret_cast<double*>(s_raw);                       // [NW][TB]
+    double* s_slab = s_tb + NW * TB;                                       // [NW][SLAB]
+    double* s_D = s_slab + NW * SLAB;                                      // [NW][2][64]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_D + NW * 128);
+    int* s_idx = reinterpret_cast<int*>(s_bar + NW);                      // [32*KC] coefficient j -> (row k << 16) | (l*nmax+n)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nrow = g.nrow, ln = g.ln, nmax = g.nmax;
+    const int ncoef = nrow * nmax;
+    for (int j = tid; j < 32 * KC; j += blockDim.x) {
+        int v = 0;
+        if (j < ncoef) {
+            const int k = j / nmax, nn = j - k * nmax;
+            int l = (int)sqrtf((float)k);
+            if ((l + 1) * (l + 1) <= k) ++l;
+            if (l * l > k) --l;
+            v = (k << 16) | (l * nmax + nn);
+        }
+        s_idx[j] = v;
+    }
+    const int kA = lane, kB = lane + 32;
+    const bool a_on = kA < nrow, b_on = kB < nrow;
+    double acc[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc[c] = 0.0;
+
+    double* val = s_slab + warp * SLAB;            // val[k * RS + p]; rows nrow, nrow+1 hold x1, x2
+    double* D = s_D + warp * 128;
+    double* tb = s_tb + warp * TB;
+    const unsigned int bar = bfe_smem_u32(s_bar + warp);
+    const unsigned int tb_u32 = bfe_smem_u32(tb);
+    const unsigned int rowbytes = 2u * (unsigned int)ln * 8u;
+    unsigned int bar_parity = 0;
+    if (lane == 0) bfe_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    unsigned int* task_counter = counter + 1;
+    const int64_t ntasks = (n + TASK - 1) / TASK;
+    SDBG_DECL;
+    for (;;) {
+        int64_t task = 0;
+        if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntasks) break;
+#ifdef BFE_PROFILE_DEPOSIT
+        sd_ntask++;
+#endif
+        const int64_t t0 = task * TASK;
+        const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
+        double dA1 = 0.0, dA2 = 0.0, dB1 = 0.0, dB2 = 0.0;
+        int cur = -1;
+        double2 ra, rb, rc, rd;
+        {
+            const bool on = lane < ((tcnt < 32) ? tcnt : 32);
+            const double2* src = reinterpret_cast<const double2*>(rec + t0 + (on ? lane : 0));
+            ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+        }
+        for (int b0 = 0; b0 < tcnt; b0 += 32) {
+            const int bcnt = (tcnt - b0) < 32 ? (tcnt - b0) : 32;
+            __syncwarp();
+            SDBG_TICK();
+            int mybin = -3;
+            {
+                const bool on = lane < bcnt;
+                const double W = on ? rb.x : 0.0;                  // zero weight parks harmless values
+#ifdef BFE_PROFILE_DEPOSIT
+                if (__double_as_longlong(W) == 0x7ff8dead00000000ll) sd_wait = 1;
+                SDBG_ADD(sd_wait);
+#endif
+                const double x = rb.y;
+                if (on) mybin = (int)((unsigned long long)__double_as_longlong(rd.y) >> 32);
+                val[nrow * RS + lane] = ra.x;
+                val[(nrow + 1) * RS + lane] = ra.y;
+                // P_l^m columns (m outer), spheresl.py:664-700.  Accumulation uses no derivative, so the
+                // recurrence is evaluated with fused multiply-adds and reciprocal constants (<= few ulp)
+                const double somx2 = sqrt((1.0 - x) * (1.0 + x));
+                double pmm = 1.0, fact = 1.0, cm = 1.0, sm = 0.0;
+#pragma unroll
+                for (int m = 0; m <= LCAP; ++m) {
+                    if (m <= g.lmax) {
+                        if (m > 0) {
+                            pmm = pmm * (-fact * somx2);
+                            fact += 2.0;
+                            double cn = cm * rc.x - sm * rc.y, sn = sm * rc.x + cm * rc.y;
+                            cm = cn; sm = sn;
+                        }
+                        double pl2 = 0.0, pl1 = pmm;
+#pragma unroll
+                        for (int l = m; l <= LCAP; ++l) {
+                            if (l <= g.lmax) {
+                                double P;
+                                if (l == m) P = pmm;
+                                else {
+                                    if (l == m + 1) P = x * (2.0 * m + 1.0) * pl1;
+                                    else P = (x * (double)(2 * l - 1) * pl1 - (double)(l + m - 1) * pl2) *
+                                             (1.0 / (double)(l - m));
+                                    pl2 = pl1; pl1 = P;
+                                }
+                                const bool skip = no_odd && (l & 1);          // spheresl.py:630-632
+                                const double fw = skip ? 0.0 : W * __ldg(fac + l * (g.lmax + 1) + m) * P;
+                                if (m == 0) val[(l * l) * RS + lane] = fw;
+                                else {
+                                    val[(l * l + 2 * m - 1) * RS + lane] = fw * cm;
+                                    val[(l * l + 2 * m) * RS + lane] = fw * sm;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (b0 + 32 < tcnt) {
+                const bool on = (b0 + 32 + lane) < tcnt;
+                const double2* src = reinterpret_cast<const double2*>(rec + t0 + b0 + 32 + (on ? lane : 0));
+                ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+            }
+            int prevbin = __shfl_up_sync(0xffffffffu, mybin, 1);
+            if (lane == 0) prevbin = cur;
+            unsigned int bmask = __ballot_sync(0xffffffffu, (lane < bcnt) && (mybin != prevbin));
+            __syncwarp();
+            SDBG_ADD(sd_expand);
+
+#define SL_OPEN_RUN(binv)                                                                                 \
+            do {                                                                                          \
+                cur = (binv);                                                                             \
+                if (use_tma && lane == 0) {                                                               \
+                    bfe_mbar_expect_tx(bar, rowbytes);                                                    \
+                    bfe_bulk_g2s(tb_u32, e_node + (size_t)cur * ln, rowbytes, bar);                       \
+                }                                                                                         \
+            } while (0)
+
+#define SL_FLUSH_RUN()                                                                                    \
+            do {                                                                                          \
+                __syncwarp();                                                                             \
+                if (a_on) { D[kA] = dA1; D[64 + kA] = dA2; }                                              \
+                if (b_on) { D[kB] = dB1; D[64 + kB] = dB2; }                                              \
+                const double* e0_;                                                                        \
+                if (use_tma) { bfe_mbar_wait(bar, bar_parity); bar_parity ^= 1u; e0_ = tb; }              \
+                else e0_ = e_node + (size_t)cur * ln;                                                     \
+                __syncwarp();                                                                             \
+                _Pragma("unroll")                                                                         \
+                for (int c = 0; c < KC; ++c) {                                                            \
+                    const int j_ = lane + 32 * c;                                                         \
+                    if (j_ < ncoef) {                                                                     \
+                        const int pk_ = s_idx[j_];                                                        \
+                        const int k_ = pk_ >> 16, eo_ = pk_ & 0xffff;                                     \
+                        acc[c] += D[k_] * e0_[eo_] + D[64 + k_] * e0_[ln + eo_];                          \
+                    }                                                                                     \
+                }                                                                                         \
+                __syncwarp();                                                                             \
+                dA1 = 0.0; dA2 = 0.0; dB1 = 0.0; dB2 = 0.0;                                               \
+            } while (0)
+
+            const double* wa = val + kA * RS;
+            const double* wb = val + (b_on ? kB : 0) * RS;
+            const double* x1v = val + nrow * RS;
+            const double* x2v = val + (nrow + 1) * RS;
+            int p = 0;
+            while (p < bcnt) {
+                if ((bmask >> p) & 1u) {
+                    SDBG_TICK();
+                    if (cur >= 0) {
+                        SL_FLUSH_RUN();
+#ifdef BFE_PROFILE_DEPOSIT
+                        sd_nflush++;
+                        if (__double_as_longlong(acc[0]) == 0x7ff8dead00000000ll) sd_wait = 1;
+#endif
+                    }
+                    SL_OPEN_RUN(__shfl_sync(0xffffffffu, mybin, p));
+                    SDBG_ADD(sd_flush);
+                }
+                SDBG_TICK();
+                const unsigned int later = (p < 31) ? (bmask >> (p + 1)) : 0u;
+                const int qend = later ? (p + __ffs(later)) : bcnt;
+                if (b_on) {
+#pragma unroll 4
+                    for (int i = p; i < qend; ++i) {
+                        const double u1 = x1v[i], u2 = x2v[i], w0 = wa[i], w1 = wb[i];
+                        dA1 = fma(w0, u1, dA1); dA2 = fma(w0, u2, dA2);
+                        dB1 = fma(w1, u1, dB1); dB2 = fma(w1, u2, dB2);
+                    }
+                } else if (a_on) {
+#pragma unroll 4
+                    for (int i = p; i < qend; ++i) {
+                        const double w0 = wa[i];
+                        dA1 = fma(w0, x1v[i], dA1);
+                        dA2 = fma(w0, x2v[i], dA2);
+                    }
+                }
+#ifdef BFE_PROFILE_DEPOSIT
+                if (__double_as_longlong(dA1 + dB1) == 0x7ff8dead00000000ll) sd_wait = 1;
+#endif
+                SDBG_ADD(sd_sum);
+                p = qend;
+            }
+        }
+        if (cur >= 0) SL_FLUSH_RUN();
+#undef SL_FLUSH_RUN
+#undef SL_OPEN_RUN
+    }
+
+#ifdef BFE_PROFILE_DEPOSIT
+    if (lane == 0 && g_sl_dbg) {
+        long long* d = g_sl_dbg + (blockIdx.x * NW + warp) * 8;
+        d[0] = clock64() - sd_t0; d[1] = sd_wait; d[2] = sd_expand; d[3] = sd_sum; d[4] = sd_flush; d[5] = sd_nflush;
+        d[6] = sd_ntask; d[7] = 0;
+    }
+#endif
+    // ---- CTA combine over the 4 warps (slab reused), per-CTA partial
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < KC; ++c) s_slab[warp * SLAB + c * 32 + lane] = acc[c];
+    __syncthreads();
+    for (int j = tid; j < ncoef; j += 128) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += s_slab[w * SLAB + j];
+        partial[(size_t)blockIdx.x * ncoef + j] = v;
+    }
+}
+
+// out[c] = sum_b partial[b][c]; the last launch of the pipeline also resets the task counter
+__global__ void __launch_bounds__(256)
+sl_sorted_reduce_kernel(const double* __restrict__ partial, int nrows, int ncol, double* __restrict__ out,
+                        unsigned int* __restrict__ counter) {
+    __shared__ double s_p[32][9];
+    const int c = blockIdx.x * 8 + (threadIdx.x & 7), slice = threadIdx.x >> 3;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < ncol) {
+        int b = slice;
+        for (; b + 32 < nrows; b += 64) {
+            s0 += __ldg(partial + (size_t)b * ncol + c);
+            s1 += __ldg(partial + (size_t)(b + 32) * ncol + c);
+        }
+        if (b < nrows) s0 += __ldg(partial + (size_t)b * ncol + c);
+    }
+    s_p[slice][threadIdx.x & 7] = s0 + s1;
+    __syncthreads();
+    if (threadIdx.x < 8 && blockIdx.x * 8 + threadIdx.x < ncol) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s += s_p[k][threadIdx.x];
+        out[blockIdx.x * 8 + threadIdx.x] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counter[1] = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static size_t sl_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct SlSortWs {
+    int* hist; int* bin_start; int* cursor; SlRec* rec;
+};
+
+static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
+    const int nbin = h->g.numr - 1;
+    size_t o_hist = 0;
+    size_t o_start = sl_align_up(o_hist + sizeof(int) * nbin, 256);
+    size_t o_cur = sl_align_up(o_start + sizeof(int) * (nbin + 1), 256);
+    size_t o_rec = sl_align_up(o_cur + sizeof(int) * nbin, 256);
+    if (n > h->sort_cap || !h->sort_ws) {
+        if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
+        int64_t cap = n + n / 8 + 1024;
+        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + sizeof(SlRec) * (size_t)cap));
+        BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
+        BFE_CUDA(cudaDeviceSynchronize());
+        h->sort_cap = cap;
+    }
+    char* b = (char*)h->sort_ws;
+    ws->hist = (int*)(b + o_hist); ws->bin_start = (int*)(b + o_start); ws->cursor = (int*)(b + o_cur);
+    ws->rec = (SlRec*)(b + o_rec);
+    return BFE_OK;
+}
+
+template <int LCAP, int KC>
+static int sl_deposit_launch(bfe_sl* h, int64_t n, const SlRec* rec, int no_odd, double* expcoef, cudaStream_t stream) {
+    constexpr int NW = 4;
+    const size_t smem = ((size_t)NW * (2 * (LCAP + 1) * 32) + (size_t)NW * ((LCAP + 1) * (LCAP + 1) + 2) * 33 +
+                         (size_t)NW * 128) * sizeof(double) + NW * sizeof(unsigned long long) + 32 * KC * sizeof(int) + 128;
+    auto kern = sl_deposit_kernel<LCAP, KC>;
+    static bool attr_set = false;                 // one flag per template instance
+    if (!attr_set) {
+        BFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int ncoef = h->g.nrow * h->g.nmax;
+    int64_t nblk = (n + 128 * NW - 1) / (128 * NW);
+    int grid = (int)(nblk < (int64_t)h->num_sms * 3 ? nblk : (int64_t)h->num_sms * 3);
+    if (grid < 1) grid = 1;
+    if (grid > h->max_ctas) grid = h->max_ctas;
+    const int use_tma = (h->g.ln % 2 == 0) ? 1 : 0;      // bulk copies need 16-byte aligned rows
+    kern<<<grid, 128, smem, stream>>>(h->g, h->e_node, h->fac, no_odd, n, rec, h->partial, h->counter, use_tma);
+    BFE_LAUNCH_CHECK("sl_deposit_kernel");
+    sl_sorted_reduce_kernel<<<(ncoef + 7) / 8, 256, 0, stream>>>(h->partial, grid, ncoef, expcoef, h->counter);
+    BFE_LAUNCH_CHECK("sl_sorted_reduce_kernel");
+    return BFE_OK;
+}
+
+bool bfe_sl_sorted_supported(const bfe_sl* h) {
+    const int ncoef = h->g.nrow * h->g.nmax;
+    if (h->g.lmax <= 4 && ncoef <= 32 * 15) return true;
+    if (h->g.lmax <= 6 && ncoef <= 32 * 28) return true;
+    return false;
+}
+
+int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                             const double* mass, int no_odd, double* expcoef, cudaStream_t stream) {
+    if (!bfe_sl_sorted_supported(h)) return BFE_ERR_UNSUPPORTED;
+    if (n >= (int64_t)1 << 31) return BFE_ERR_UNSUPPORTED;
+    SlSortWs ws;
+    int rc = sl_sort_workspace(h, n, &ws);
+    if (rc != BFE_OK) return rc;
+    const int nbin = h->g.numr - 1;
+    int grid = (int)((n + 1023) / 1024);
+    if (grid > h->num_sms * 2) grid = h->num_sms * 2;
+    if (grid < 1) grid = 1;
+    {
+        const int per = (nbin + 1023) / 1024;
+        const size_t ss = sizeof(int) * (size_t)per * 1024;
+        if (ss > 200 * 1024) return BFE_ERR_UNSUPPORTED;
+        if (ss > 48 * 1024)
+            BFE_CUDA(cudaFuncSetAttribute(sl_bin_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+        sl_bin_hist_kernel<<<grid, 1024, ss, stream>>>(h->g, h->xi, nbin, n, x, y, z, ws.hist, ws.bin_start, ws.cursor,
+                                                      h->counter);
+    }
+    BFE_LAUNCH_CHECK("sl_bin_hist_kernel");
+    int g2 = (int)((n + 511) / 512);
+    if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
+    if (g2 < 1) g2 = 1;
+    sl_bin_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, h->xi, h->p0, n, x, y, z, mass, ws.cursor, ws.rec);
+    BFE_LAUNCH_CHECK("sl_bin_scatter_kernel");
+    if (h->g.lmax <= 4 && h->g.nrow * h->g.nmax <= 32 * 15)
+        return sl_deposit_launch<4, 15>(h, n, ws.rec, no_odd, expcoef, stream);
+    return sl_deposit_launch<6, 28>(h, n, ws.rec, no_odd, expcoef, stream);
+}

@@ -57,8 +57,9 @@ int  bfe_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 uint64_t bfe_launch_count(void);
 
-/* Runtime options (process-wide).  "eof_accumulate_mode", "eof_force_mode": 0 = auto (cell-sorted
- * kernels from "sort_min_particles" particles up, direct kernels below), 1 = direct, 2 = sorted. */
+/* Runtime options (process-wide).  "eof_accumulate_mode", "eof_force_mode", "sl_accumulate_mode":
+ * 0 = auto (bin-sorted kernels from "sort_min_particles" particles up, direct kernels below),
+ * 1 = direct, 2 = sorted. */
 int bfe_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------- EOF (disc) ---------------- */

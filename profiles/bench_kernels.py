@@ -45,7 +45,10 @@ res['eof_prepare'] = timeit(lambda k: E.prepare(*disc[k % NS]))
 res['eof_accumulate_prepared'] = timeit(lambda k: E.accumulate_prepared())
 res['eof_force_prepared'] = timeit(lambda k: E.force_prepared())
 res['eof_contract'] = timeit(lambda k: E.contract(c, s))
-res['sl_accumulate'] = timeit(lambda k: H.accumulate(*halo[k % NS]))
+for mode, name in ((1, 'direct'), (2, 'sorted')):
+    ops.set_option('sl_accumulate_mode', mode)
+    res['sl_accumulate_' + name] = timeit(lambda k: H.accumulate(*halo[k % NS]))
+ops.set_option('sl_accumulate_mode', 0)
 res['sl_contract'] = timeit(lambda k: H.contract(ch))
 res['sl_force'] = timeit(lambda k: H.force(*halo[k % NS][:3]))
 res['field_cart_disc_points'] = timeit(lambda k: ops.field_force_cart(E, H, *disc[k % NS][:3], rotpos=0.3))

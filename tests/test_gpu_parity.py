@@ -93,8 +93,15 @@ def test_eof_force_golden(ops, eof_mode, name):
             assert relerr(out[i], ref[:, i]) < TOL, (vname, i)
 
 
+@pytest.fixture(params=['direct', 'sorted'])
+def sl_mode(ops, request):
+    ops.set_option('sl_accumulate_mode', 1 if request.param == 'direct' else 2)
+    yield request.param
+    ops.set_option('sl_accumulate_mode', 0)
+
+
 @pytest.mark.parametrize('name', SL_CASES)
-def test_sl_accumulate_golden(ops, name):
+def test_sl_accumulate_golden(ops, sl_mode, name):
     d, meta = load_golden(name)
     p, ev, ef, xi, p0, d0 = sl_tables(meta)
     H = make_sl(ops, p, ev, ef, xi, p0, d0)
@@ -243,7 +250,7 @@ def test_eof_prepared_set_matches_separate_calls(ops):
 
 
 @pytest.mark.parametrize('lmax', [4, 6])
-def test_sl_accumulate_force_oracle_30k(ops, lmax):
+def test_sl_accumulate_force_oracle_30k(ops, sl_mode, lmax):
     meta = dict(sl_params=dict(lmax=lmax), kind='smooth', seed=0)
     p, ev, ef, xi, p0, d0 = sl_tables(meta)
     H = make_sl(ops, p, ev, ef, xi, p0, d0)
