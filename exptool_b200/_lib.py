@@ -59,6 +59,7 @@ SIGNATURES = {
     'bfe_field_force_cart': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
     'bfe_field_force_cyl': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
     'bfe_leapfrog': (_INT, [_P, _P, _I64, _I64, _DBL, _DBL, _P, _P, _I64, _INT, _INT, _P, _P]),
+    'bfe_leapfrog_dt': (_INT, [_P, _P, _I64, _I64, _P, _DBL, _P, _P, _I64, _INT, _INT, _P, _P]),
 }
 
 _lib = None

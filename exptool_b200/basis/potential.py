@@ -37,6 +37,7 @@ class Fields():
         self.mutual_center = mutual_center
         self.verbose = verbose
         self.halofac = 1.0
+        self.time = 0.0
         self._E = None
         self._H = None
         self._contract_key = None
@@ -87,7 +88,8 @@ class Fields():
             self.SL.model_file, self.numrhalo, self.rminhalo, self.rmaxhalo, cmap=self.cmaphalo, scale=self.scalehalo)
         self.halo_use_l = self.lmaxhalo
         self.halo_use_n = self.nmaxhalo
-        self._build_device()
+        self._E = self._H = None           # device handles are (re)built on first use
+        self._contract_key = None
 
     def _build_device(self):
         self._E = ops.EOFTables(self.potC, self.potS, self.mmax, self.norder, self.XMIN, self.dX, self.YMIN, self.dY,
@@ -117,7 +119,9 @@ class Fields():
     def device_handles(self):
         """(ops.EOFTables, ops.SLTables) holding the contraction for the current parameters."""
         if self._E is None or self._H is None:
-            raise RuntimeError('potential.Fields: must first call total_coefficients and prep_tables.')
+            if not hasattr(self, 'potC') or not hasattr(self, 'xihalo'):
+                raise RuntimeError('potential.Fields: must first call total_coefficients and prep_tables.')
+            self._build_device()
         try:
             x = self.no_odd
         except AttributeError:
@@ -160,6 +164,90 @@ class Fields():
         diskfr, frhalo, diskfp, -halofp, diskfz, fzhalo, -diskp, halop+halop0.
         '''
         return self._eval(ops.field_force_cyl, xval, yval, zval, rotpos)
+
+
+    # -- frozen-field file (potential.py:738-958), byte-compatible ---------------
+    def save_field(self, filename=''):
+        '''
+        Fields.save_field (potential.py:738-958): everything needed to evaluate the field, in the
+        reference's byte layout.  Geometry scalars are stored as float32 exactly
+        as the reference does, so a restored field differs from the original at ~1e-6 relative.
+        '''
+        if filename == '':
+            print('potential.Fields.save_field: No filename specified.')
+        with open(filename, 'wb') as f:
+            for sname in (self.filename, self.eof_file, self.sph_file, self.model_file):
+                np.array([sname], dtype='S100').tofile(f)
+            for v in (self.nhalo, self.transform, self.no_odd, self.centering, self.mutual_center, self.verbose):
+                np.array([v], dtype='i4').tofile(f)
+            np.array([self.time], dtype='f4').tofile(f)
+            for v in (self.numx, self.numy, self.mmax, self.norder, self.cmapdisk, self.densdisk):
+                np.array([v], dtype='i4').tofile(f)
+            for v in (self.rmindisk, self.rmaxdisk, self.ascale, self.hscale, self.XMIN, self.dX, self.YMIN, self.dY,
+                      getattr(self, 'xcen_disk', 0.), getattr(self, 'ycen_disk', 0.), getattr(self, 'zcen_disk', 0.)):
+                np.array([v], dtype='f4').tofile(f)
+            np.array(np.asarray(self.EOF.cos).reshape(-1, ), dtype='f8').tofile(f)
+            np.array(np.asarray(self.EOF.sin).reshape(-1, ), dtype='f8').tofile(f)
+            for t in (self.potC, self.rforceC, self.zforceC, self.densC, self.potS, self.rforceS, self.zforceS, self.densS):
+                np.array(t.reshape(-1, ), dtype='f8').tofile(f)
+            for v in (self.halofac, self.rminhalo, self.rmaxhalo, self.scalehalo, getattr(self, 'xcen_halo', 0.),
+                      getattr(self, 'ycen_halo', 0.), getattr(self, 'zcen_halo', 0.)):
+                np.array([v], dtype='f4').tofile(f)
+            for v in (self.numrhalo, self.cmaphalo, self.lmaxhalo, self.nmaxhalo):
+                np.array([v], dtype='i4').tofile(f)
+            ltable = getattr(self, 'ltablehalo', getattr(self, 'ltable', np.arange(self.lmaxhalo + 1.)))
+            for t in (self.xihalo, self.p0halo, self.d0halo, ltable, self.evtablehalo, self.eftablehalo,
+                      np.asarray(self.SL.expcoef, dtype=np.float64)):
+                np.array(np.asarray(t).reshape(-1, ), dtype='f8').tofile(f)
+
+
+def restore_field(filename=''):
+    '''
+    potential.restore_field (potential.py:968-1040): rebuild a Fields instance from a frozen-field file.
+    Attribute names and types follow the reference (strings come back as bytes, scalars as NumPy types).
+    '''
+    with open(filename, 'rb') as f:
+        [infile, eof_file, sph_file, model_file] = np.fromfile(f, dtype='S100', count=4)
+        [nhalo, transform, no_odd, centering, mutual_center, verbose] = np.fromfile(f, dtype='i4', count=6)
+        [time] = np.fromfile(f, dtype='f4', count=1)
+        F = Fields(infile, eof_file, sph_file, model_file, nhalo=nhalo, transform=transform, no_odd=no_odd,
+                   centering=centering, mutual_center=mutual_center, verbose=verbose)
+        F.time = time
+        [F.numx, F.numy, F.mmax, F.norder, F.cmapdisk, F.densdisk] = np.fromfile(f, dtype='i4', count=6)
+        [F.rmindisk, F.rmaxdisk, F.ascale, F.hscale, F.XMIN, F.dX, F.YMIN, F.dY, F.xcen_disk, F.ycen_disk,
+         F.zcen_disk] = np.fromfile(f, dtype='f4', count=11)
+        F.EOF = eof.EOF_Object()
+        nc = (F.mmax + 1) * F.norder
+        F.EOF.cos = np.fromfile(f, dtype='f8', count=nc).reshape([(F.mmax + 1), F.norder])
+        F.EOF.sin = np.fromfile(f, dtype='f8', count=nc).reshape([(F.mmax + 1), F.norder])
+        shape = [(F.mmax + 1), F.norder, (F.numx + 1), (F.numy + 1)]
+        nt = int(np.prod(shape))
+        for name in ('potC', 'rforceC', 'zforceC', 'densC', 'potS', 'rforceS', 'zforceS', 'densS'):
+            setattr(F, name, np.fromfile(f, dtype='f8', count=nt).reshape(shape))
+        [F.halofac, F.rminhalo, F.rmaxhalo, F.scalehalo, F.xcen_halo, F.ycen_halo, F.zcen_halo] = \
+            np.fromfile(f, dtype='f4', count=7)
+        [F.numrhalo, F.cmaphalo, F.lmaxhalo, F.nmaxhalo] = np.fromfile(f, dtype='i4', count=4)
+        F.xihalo = np.fromfile(f, dtype='f8', count=F.numrhalo)
+        F.p0halo = np.fromfile(f, dtype='f8', count=F.numrhalo)
+        F.d0halo = np.fromfile(f, dtype='f8', count=F.numrhalo)
+        F.ltable = np.fromfile(f, dtype='f8', count=(F.lmaxhalo + 1))
+        F.ltablehalo = F.ltable
+        F.evtablehalo = np.fromfile(f, dtype='f8', count=(F.lmaxhalo + 1) * F.nmaxhalo).reshape(
+            [(F.lmaxhalo + 1), F.nmaxhalo])
+        F.eftablehalo = np.fromfile(f, dtype='f8', count=(F.lmaxhalo + 1) * F.nmaxhalo * F.numrhalo).reshape(
+            [(F.lmaxhalo + 1), F.nmaxhalo, F.numrhalo])
+        F.SL = spheresl.SL_Object()
+        F.SL.expcoef = np.fromfile(f, dtype='f8', count=(F.lmaxhalo + 1) * (F.lmaxhalo + 1) * F.nmaxhalo).reshape(
+            [(F.lmaxhalo + 1) * (F.lmaxhalo + 1), F.nmaxhalo])
+    F.disk_use_m = F.mmax
+    F.disk_use_n = F.norder
+    F.halo_use_l = F.lmaxhalo
+    F.halo_use_n = F.nmaxhalo
+    F.SL.model_file = F.model_file
+    F.SL.sph_file = F.sph_file
+    F.EOF.eof_file = F.eof_file
+    F.EOF.mmax = F.mmax
+    return F
 
 
 def make_fields(eof_file, sph_file, model_file, cos, sin, expcoef, halofac=1.0, verbose=0):

@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(128)
 leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
                 SlGeom gs, const double2* __restrict__ A, int kpad, const double* __restrict__ xi,
                 const double* __restrict__ p0tab, const double* __restrict__ fac,
-                int64_t norbit, int64_t nint, double dt, double rotfreq,
+                int64_t norbit, int64_t nint, double dt, const double* __restrict__ dt_orbit, double rotfreq,
                 double* __restrict__ state6, double* __restrict__ traj, int64_t traj_stride,
                 int apse, int ap_max, int* __restrict__ nsteps_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= norbit) return;
+    if (dt_orbit) dt = dt_orbit[i];                          // per-orbit step (integrate_grid, integrate.py:871)
     double px = state6[i], py = state6[norbit + i], pz = state6[2 * norbit + i];
     double vx = state6[3 * norbit + i], vy = state6[4 * norbit + i], vz = state6[5 * norbit + i];
     const double w = BFE_TWOPI * rotfreq;                    // barpos = 2 pi rotfreq (k dt), integrate.py:94-97
@@ -130,9 +131,9 @@ extern "C" int bfe_field_force_cyl(bfe_eof* he, bfe_sl* hs, int64_t n, const dou
     return field_force_impl(he, hs, n, x, y, z, rotpos, out8, stream, true);
 }
 
-extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, double rotfreq,
-                            double* state6, double* traj, int64_t traj_stride, int apse, int ap_max,
-                            int32_t* nsteps_out, void* stream_) {
+static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,
+                         double rotfreq, double* state6, double* traj, int64_t traj_stride, int apse, int ap_max,
+                         int32_t* nsteps_out, void* stream_) {
     if (!he || !hs || norbit < 0 || nint < 1) return BFE_ERR_ARG;
     if (!he->contracted || !hs->contracted) return BFE_ERR_STATE;
     if (norbit == 0) return BFE_OK;
@@ -142,9 +143,24 @@ extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nin
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = (int)((norbit + 127) / 128);
     FIELD_DISPATCH(leapfrog_kernel, he->g, he->g_con, he->gstride, hs->g, reinterpret_cast<const double2*>(hs->a_con), hs->kpad, hs->xi, hs->p0,
-                   hs->fac, norbit, nint, dt, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
+                   hs->fac, norbit, nint, dt, dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
     BFE_LAUNCH_CHECK("leapfrog_kernel");
     return BFE_OK;
+}
+
+extern "C" int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, double rotfreq,
+                            double* state6, double* traj, int64_t traj_stride, int apse, int ap_max,
+                            int32_t* nsteps_out, void* stream) {
+    return leapfrog_impl(he, hs, norbit, nint, dt, nullptr, rotfreq, state6, traj, traj_stride, apse, ap_max,
+                         nsteps_out, stream);
+}
+
+extern "C" int bfe_leapfrog_dt(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, const double* dt_orbit,
+                               double rotfreq, double* state6, double* traj, int64_t traj_stride, int apse,
+                               int ap_max, int32_t* nsteps_out, void* stream) {
+    if (!dt_orbit) return BFE_ERR_ARG;
+    return leapfrog_impl(he, hs, norbit, nint, 0.0, dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max,
+                         nsteps_out, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -282,7 +282,16 @@ def leapfrog(eof_tables, sl_tables, pos0, vel0, nint, dt, rotfreq=0.0, traj_stri
         nsave = (int(nint) - 1) // int(traj_stride) + 1
         traj = torch.zeros((nsave, 10, norb), dtype=torch.float64, device=state.device)
     nsteps = torch.empty((norb,), dtype=torch.int32, device=state.device)
-    _lib.check(eof_tables.lib.bfe_leapfrog(eof_tables.h, sl_tables.h, norb, int(nint), float(dt), float(rotfreq),
-                                           _ptr(state), _ptr(traj), int(traj_stride) if traj is not None else 1,
-                                           int(bool(apse)), int(ap_max), _ptr(nsteps), _stream()))
+    stride = int(traj_stride) if traj is not None else 1
+    if np.ndim(dt) == 0 and not isinstance(dt, torch.Tensor):
+        _lib.check(eof_tables.lib.bfe_leapfrog(eof_tables.h, sl_tables.h, norb, int(nint), float(dt), float(rotfreq),
+                                               _ptr(state), _ptr(traj), stride, int(bool(apse)), int(ap_max),
+                                               _ptr(nsteps), _stream()))
+    else:
+        dts = dev(dt).reshape(-1)                  # one step size per orbit
+        if dts.numel() != norb:
+            raise ValueError('dt must be a scalar or have one entry per orbit')
+        _lib.check(eof_tables.lib.bfe_leapfrog_dt(eof_tables.h, sl_tables.h, norb, int(nint), _ptr(dts),
+                                                  float(rotfreq), _ptr(state), _ptr(traj), stride,
+                                                  int(bool(apse)), int(ap_max), _ptr(nsteps), _stream()))
     return state, traj, nsteps

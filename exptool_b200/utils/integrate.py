@@ -6,8 +6,11 @@ The time loop runs in one CUDA kernel (csrc/bfe_field.cu: leapfrog_kernel), one
 thread per orbit with the phase-space state in registers; the host only sets the
 field truncation, launches, and formats the Orbits dictionary.
 
-Not mirrored: orbit-grid drivers, compute_timestep, orbit text files
-(SURVEY.md section 8f rank 2).
+compute_timestep, the four integrate_grid* drivers and the orbit-map text format
+ are mirrored too: a whole (radius, velocity[, z, vz]) grid is one
+batched time-step estimate plus one leapfrog launch with a step size per orbit.
+Not mirrored: the multiprocessing wrappers (do_integrate_multi, run_time*), which only fan
+the grid out over processes.
 """
 import time
 
@@ -99,3 +102,162 @@ def leapfrog_integrate_batch(FieldInstance, nint, dt, initpos, initvel, rotfreq=
     if traj is not None:
         out['TRAJ'] = traj.cpu().numpy()
     return out
+
+
+# ---------------------------------------------------------------------------
+# time-step heuristic and orbit grids -- integrate.py:217-272, 760-922
+# ---------------------------------------------------------------------------
+def compute_timestep(FieldInstance, start_pos, start_vel, dyn_res=100., verbose=False):
+    '''
+    integrate.compute_timestep (integrate.py:217-272): min of the four EXP criteria / dyn_res.
+    start_pos, start_vel: [x,y,z] (scalars -> float) or (3, norbit) arrays -> array of dt.
+    The reference's `dfz*hfz` product (249, 251; a sum is meant) is reproduced.
+    '''
+    eps = 1.e-10
+    pos = np.asarray(start_pos, dtype=np.float64)
+    vel = np.asarray(start_vel, dtype=np.float64)
+    scalar = pos.ndim == 1
+    pos = pos.reshape(3, -1)
+    vel = vel.reshape(3, -1)
+    vtot = np.sum(vel ** 2., axis=0) ** 0.5 + eps
+    dfx, hfx, dfy, hfy, dfz, hfz, dp, hp = FieldInstance.return_forces_cart(pos[0], pos[1], pos[2])
+    dtr = pos[0] * (dfx + hfx) + pos[1] * (dfy + hfy) + pos[2] * (dfz * hfz)
+    atot = ((dfx + hfx) ** 2. + (dfy + hfy) ** 2. + (dfz * hfz) ** 2.0) ** 0.5 + eps
+    ptot = np.abs(dp + hp)
+    T = [1.0 / np.sqrt(vtot + eps), np.sqrt(vtot / (atot + eps)), ptot / (np.abs(dtr) + eps),
+         np.sqrt(ptot / (atot * atot + eps))]
+    dt = np.min(np.array(T), axis=0) / dyn_res
+    if scalar:
+        return dt[0]
+    return dt
+
+
+def _grid_orbits(F, pos0, vel0, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max):
+    """shared body of the grid drivers: per-orbit dt, one leapfrog launch, host-side bar-frame rotation"""
+    E, H = _handles(F, no_odd, halo_l, -1, disk_m, -1)
+    dts = np.maximum(compute_timestep(F, pos0, vel0, dyn_res=dyn_res), dt)       # integrate.py:871
+    state, traj, nsteps = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=rotfreq, traj_stride=1,
+                                       apse=False, ap_max=ap_max)
+    traj = ops.to_host(traj)                                   # (nint, 10, norb)
+    times = np.arange(0, nint, 1)[:, None] * dts[None, :]       # (nint, norb)
+    barpos = 2. * np.pi * rotfreq * times
+    X, Y, VX, VY = traj[:, 0], traj[:, 1], traj[:, 3], traj[:, 4]
+    TX = np.empty_like(X); TY = np.empty_like(Y)
+    neg = np.min(barpos, axis=0) < 0.                            # integrate.py:180-188, per orbit
+    tx, ty = transform(X, Y, barpos)
+    cx, cy = clock_transform(X, Y, barpos)
+    TX = np.where(neg[None, :], tx, cx)
+    TY = np.where(neg[None, :], ty, cy)
+    return traj, TX, TY, times
+
+
+def _integrate_grid_2d(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, launch_y):
+    rads = np.asarray(rads, dtype=np.float64); vels = np.asarray(vels, dtype=np.float64)
+    R, V = np.meshgrid(rads, vels, indexing='ij')
+    n = R.size
+    pos0 = np.zeros((3, n)); vel0 = np.zeros((3, n))
+    pos0[1 if launch_y else 0] = R.reshape(-1)
+    vel0[1] = V.reshape(-1)
+    traj, TX, TY, times = _grid_orbits(F, pos0, vel0, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max)
+    Oarray = np.zeros([rads.size, vels.size, 7, nint])
+    for k, a in enumerate((traj[:, 0], traj[:, 1], TX, TY, traj[:, 3], traj[:, 4], times)):
+        Oarray[:, :, k, :] = a.T.reshape(rads.size, vels.size, nint)
+    return Oarray
+
+
+def integrate_grid(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, verbose):
+    '''integrate.integrate_grid (integrate.py:848-883): Oarray[rad, vel, (X,Y,TX,TY,VX,VY,T), nint], launched
+    from the x axis with dt as the minimum step.'''
+    return _integrate_grid_2d(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, False)
+
+
+def integrate_grid_launchy(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, verbose):
+    '''integrate.integrate_grid_launchy (integrate.py:886-922): same, launched from the y axis.'''
+    return _integrate_grid_2d(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, True)
+
+
+def _integrate_grid_3d(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, zs, vzs, launch_y):
+    if (zs is None) or (vzs is None):
+        print('ERROR: 3D orbit specified, but no z or vz values passed!')
+        return None
+    rads, vels, zs, vzs = (np.asarray(a, dtype=np.float64) for a in (rads, vels, zs, vzs))
+    R, V, Z, VZ = np.meshgrid(rads, vels, zs, vzs, indexing='ij')
+    n = R.size
+    pos0 = np.zeros((3, n)); vel0 = np.zeros((3, n))
+    pos0[1 if launch_y else 0] = R.reshape(-1)
+    pos0[2] = Z.reshape(-1)
+    vel0[1] = V.reshape(-1)
+    vel0[2] = VZ.reshape(-1)
+    traj, TX, TY, times = _grid_orbits(F, pos0, vel0, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max)
+    Oarray = np.zeros([rads.size, vels.size, zs.size, vzs.size, 9, nint])
+    for k, a in enumerate((traj[:, 0], traj[:, 1], traj[:, 2], TX, TY, traj[:, 3], traj[:, 4], traj[:, 5], times)):
+        Oarray[:, :, :, :, k, :] = a.T.reshape(rads.size, vels.size, zs.size, vzs.size, nint)
+    return Oarray
+
+
+def integrate_grid_3D(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, zs, vzs, verbose):
+    '''integrate.integrate_grid_3D (integrate.py:760-801): Oarray[rad,vel,z,vz,(X,Y,Z,TX,TY,VX,VY,VZ,T),nint]'''
+    return _integrate_grid_3d(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, zs, vzs, False)
+
+
+def integrate_grid_3D_launchy(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, zs, vzs, verbose):
+    '''integrate.integrate_grid_3D_launchy (integrate.py:803-845)'''
+    return _integrate_grid_3d(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, zs, vzs, True)
+
+
+# ---------------------------------------------------------------------------
+# orbit-map text files -- integrate.py:513-569, 970-1038 (one line per orbit)
+# ---------------------------------------------------------------------------
+def print_orbit_array(f, OrbitArray):
+    '''integrate.print_orbit_array (513-537): `nsteps R0 V0 dT x.. y.. tx.. ty.. vx.. vy..`'''
+    for rad in range(0, OrbitArray.shape[0]):
+        for vel in range(0, OrbitArray.shape[1]):
+            nsteps = OrbitArray.shape[-1]
+            print(nsteps, OrbitArray[rad, vel, 0, 0], OrbitArray[rad, vel, 5, 0], OrbitArray[rad, vel, -1, 1],
+                  end=' ', file=f)
+            for row in range(6):
+                for x in range(0, nsteps):
+                    print(OrbitArray[rad, vel, row, x], end=' ', file=f)
+            print('', file=f)
+
+
+def print_orbit_array_3D(f, OrbitArray):
+    '''integrate.print_orbit_array_3D (539-569)'''
+    for rad in range(0, OrbitArray.shape[0]):
+        for vel in range(0, OrbitArray.shape[1]):
+            for z in range(0, OrbitArray.shape[2]):
+                for vz in range(0, OrbitArray.shape[3]):
+                    nsteps = OrbitArray.shape[-1]
+                    O = OrbitArray[rad, vel, z, vz]
+                    print(nsteps, O[0, 0], O[6, 0], O[2, 0], O[7, 0], O[-1, 1], end=' ', file=f)
+                    for row in range(8):
+                        for x in range(0, nsteps):
+                            print(O[row, x], end=' ', file=f)
+                    print('', file=f)
+
+
+def read_integrations(infile):
+    '''integrate.read_integrations (970-1001)'''
+    D = {k: {} for k in ('R_0', 'V_0', 'dT', 'X', 'Y', 'TX', 'TY', 'VX', 'VY')}
+    with open(infile, 'r') as f:
+        for linenum, line in enumerate(f):
+            d = [float(q) for q in line.split()]
+            npoints = int(d[0])
+            D['R_0'][linenum] = d[1]; D['V_0'][linenum] = d[2]; D['dT'][linenum] = d[3]
+            for k, key in enumerate(('X', 'Y', 'TX', 'TY', 'VX', 'VY')):
+                D[key][linenum] = d[(k * npoints) + 4:((k + 1) * npoints) + 4]
+    return D
+
+
+def read_integrations_3D(infile):
+    '''integrate.read_integrations_3D (1003-1038)'''
+    D = {k: {} for k in ('R_0', 'V_0', 'Z_0', 'VZ_0', 'dT', 'X', 'Y', 'Z', 'TX', 'TY', 'VX', 'VY', 'VZ')}
+    with open(infile, 'r') as f:
+        for linenum, line in enumerate(f):
+            d = [float(q) for q in line.split()]
+            npoints = int(d[0])
+            D['R_0'][linenum] = d[1]; D['V_0'][linenum] = d[2]; D['Z_0'][linenum] = d[3]
+            D['VZ_0'][linenum] = d[4]; D['dT'][linenum] = d[5]
+            for k, key in enumerate(('X', 'Y', 'Z', 'TX', 'TY', 'VX', 'VY', 'VZ')):
+                D[key][linenum] = d[(k * npoints) + 6:((k + 1) * npoints) + 6]
+    return D

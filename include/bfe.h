@@ -187,6 +187,12 @@ int bfe_leapfrog(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double d
                  double* state6, double* traj, int64_t traj_stride,
                  int apse, int ap_max, int32_t* nsteps_out, void* stream);
 
+/* Same with one step size per orbit (dt_orbit[norbit], device): the orbit grids of integrate.integrate_grid*
+ * (integrate.py:760-922) give every orbit dt = max(compute_timestep(...), dt). */
+int bfe_leapfrog_dt(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, const double* dt_orbit, double rotfreq,
+                    double* state6, double* traj, int64_t traj_stride,
+                    int apse, int ap_max, int32_t* nsteps_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

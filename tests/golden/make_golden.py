@@ -225,11 +225,35 @@ def case_field(name, eparams, sparams, kind, seed, ndisc, nhalo, npts, norb, nin
                                           halo_l=2, halo_n=4, disk_m=4, disk_n=5)
         orb_trunc = np.array([Ot[key] for key in ('X', 'Y', 'Z', 'VX', 'VY', 'VZ', 'P', 'TX', 'TY', 'VTX', 'VTY', 'T')])
         ts = np.array([integrate.compute_timestep(F, pos0[:, k], vel0[:, k]) for k in range(norb)])
+        # orbit grids (integrate.py:760-922) and the orbit-map text format (513-537)
+        F.reset_field_parameters()
+        vc0 = np.sqrt(max(-0.01 * float(sum(F.return_forces_cart(0.01, 0.0, 0.0)[:2])), 1e-12))
+        rads = np.array([0.006, 0.012, 0.02]); vels = np.array([0.6, 0.9]) * vc0
+        grid = quiet(integrate.integrate_grid, rads, vels, F, 40, 1.0e-5, rotfreq, False, -1, -1, 100., 1000, 0)
+        grid_y = quiet(integrate.integrate_grid_launchy, rads[:2], vels[:1], F, 30, 1.0e-5, 3.0, False, -1, -1, 50., 1000, 0)
+        zs = np.array([0.0, 0.002]); vzs = np.array([0.05 * vc0])
+        grid3 = quiet(integrate.integrate_grid_3D, rads[:2], vels, F, 24, 1.0e-5, rotfreq, False, -1, -1, 100., 1000, zs, vzs, 0)
+        buf = io.StringIO(); integrate.print_orbit_array(buf, grid[:1, :1, :, :5]); orbit_txt = buf.getvalue()
+        # frozen-field file (potential.py:738-1040): hash of the reference-written bytes + forces after restore
+        import hashlib
+        F.time = 0.25; F.xcen_disk = F.ycen_disk = F.zcen_disk = 0.; F.xcen_halo = F.ycen_halo = F.zcen_halo = 0.
+        F.filename = 'snap'; F.eof_file = 'eof.cache'; F.sph_file = 'sl.cache'; F.model_file = 'sl.model'
+        ff = os.path.join(tmp, 'frozen.field')
+        F.save_field(ff)
+        with open(ff, 'rb') as fh:
+            field_sha = hashlib.sha256(fh.read()).hexdigest()
+        field_size = os.path.getsize(ff)
+        FR = potential.restore_field(ff)
+        FR.set_field_parameters()
+        cart_restored = np.array([[float(v) for v in FR.return_forces_cart(px[i], py[i], pz[i], rotpos=rot)] for i in range(npts)])
     np.savez_compressed(os.path.join(HERE, name + '.npz'),
                         meta=json.dumps(dict(eof_params=eparams, sl_params=sparams, kind=kind, seed=seed, geo=g,
                                              halofac=1.25, rot_full=rot, rot_trunc=-0.4, dt=dt, rotfreq=rotfreq, nint=nint)),
                         cos=cosd, sin=sind, coef=coef, px=px, py=py, pz=pz, cart_full=cart_full, cart_trunc=cart_trunc, cyl_full=cyl_full,
-                        pos0=pos0, vel0=vel0, orbits=np.array(orbs), orbit_trunc=orb_trunc, timestep=ts)
+                        pos0=pos0, vel0=vel0, orbits=np.array(orbs), orbit_trunc=orb_trunc, timestep=ts,
+                        grid_rads=rads, grid_vels=vels, grid=grid, grid_y=grid_y, grid_zs=zs, grid_vzs=vzs, grid3=grid3,
+                        orbit_txt=np.array(orbit_txt), field_sha=np.array(field_sha), field_size=np.array(field_size),
+                        cart_restored=cart_restored)
     print('wrote', name)
 
 

@@ -207,3 +207,47 @@ def test_fields_total_coefficients_in_memory(api):
         a = F.return_forces_cart(0.01, 0.002, 0.0005)
         assert len(a) == 8 and all(np.isfinite(a))
         assert F.EOF.cos.shape == (3, 3) and F.SL.expcoef.shape == (9, 4) and F.halofac == 2.0
+
+
+@pytest.mark.parametrize('name', ['field_small', 'field_std'])
+def test_frozen_field_timestep_and_grids(api, name):
+    """restore_field -> forces; compute_timestep; integrate_grid* against the reference's own outputs."""
+    potential, integrate = api['potential'], api['integrate']
+    d, meta = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        ef = _eof_file(tmp, meta)
+        sf, mf = _sl_files(tmp, meta, seed_offset=1)
+        F = potential.make_fields(ef, sf, mf, d['cos'], d['sin'], d['coef'], halofac=meta['halofac'])
+        ff = os.path.join(tmp, 'frozen.field')
+        F.save_field(ff)
+        R = potential.restore_field(ff)
+        R.set_field_parameters()
+        out = R.return_forces_cart(d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+        for i in range(8):
+            assert relerr(out[i], d['cart_restored'][:, i]) < TOL, i
+        # the float32 geometry makes the restored field differ from the original at ~1e-6 (App. C #15)
+        assert 1e-9 < relerr(out[0], d['cart_full'][:, 0]) < 1e-3
+        # compute_timestep: scalar calls and batched.  (The golden values were taken while the reference Fields
+        # still held the truncation of the preceding leapfrog call -- leapfrog_integrate sets the field
+        # parameters and never resets them, integrate.py:89.)
+        F.set_field_parameters(no_odd=True, halo_l=2, halo_n=4, disk_m=4, disk_n=5)
+        for k in range(d['pos0'].shape[1]):
+            dt = integrate.compute_timestep(F, d['pos0'][:, k], d['vel0'][:, k])
+            assert abs(dt - d['timestep'][k]) <= 1e-10 * d['timestep'][k]
+        dts = integrate.compute_timestep(F, d['pos0'], d['vel0'])
+        assert relerr(dts, d['timestep']) < 1e-10
+        F.reset_field_parameters()
+        # orbit grids
+        rads, vels = d['grid_rads'], d['grid_vels']
+        g = integrate.integrate_grid(rads, vels, F, 40, 1.0e-5, meta['rotfreq'], False, -1, -1, 100., 1000, 0)
+        assert g.shape == d['grid'].shape
+        for k in range(7):
+            assert relerr(g[:, :, k], d['grid'][:, :, k]) < ORBIT_TOL, k
+        gy = integrate.integrate_grid_launchy(rads[:2], vels[:1], F, 30, 1.0e-5, 3.0, False, -1, -1, 50., 1000, 0)
+        for k in range(7):
+            assert relerr(gy[:, :, k], d['grid_y'][:, :, k]) < ORBIT_TOL, k
+        g3 = integrate.integrate_grid_3D(rads[:2], vels, F, 24, 1.0e-5, meta['rotfreq'], False, -1, -1, 100., 1000,
+                                         d['grid_zs'], d['grid_vzs'], 0)
+        assert g3.shape == d['grid3'].shape
+        for k in range(9):
+            assert relerr(g3[..., k, :], d['grid3'][..., k, :]) < ORBIT_TOL, k

@@ -278,3 +278,64 @@ def test_sharded_accumulate_gloo_world2():
         for r, (p, out) in enumerate(zip(procs, outs)):
             assert p.returncode == 0, out[-3000:]
             assert 'rank %d ok' % r in out
+
+
+def _fields_from_golden(tmp, d, meta):
+    """exptool_b200 Fields holding the golden coefficient set, built without a GPU (device handles are lazy)."""
+    from exptool_b200.basis import potential
+    pe, T = S.make_eof_tables(meta['eof_params'], kind=meta['kind'], seed=meta['seed'])
+    ef = S.write_eof_cache(os.path.join(tmp, 'eof.cache'), pe, T)
+    ps, ev, efn = S.make_sl_tables(meta['sl_params'], kind=meta['kind'], seed=meta['seed'] + 1)
+    sf = S.write_sl_cache(os.path.join(tmp, 'sl.cache'), ps, ev, efn)
+    mf = S.write_hernquist_model(os.path.join(tmp, 'sl.model'), a=ps['scale'])
+    return potential.make_fields(ef, sf, mf, d['cos'], d['sin'], d['coef'], halofac=meta['halofac'])
+
+
+@pytest.mark.parametrize('name', ['field_small', 'field_std'])
+def test_frozen_field_file_is_byte_compatible(name):
+    """Fields.save_field writes exactly the bytes the reference writes (sha256 recorded in the golden);
+    restore_field reads them back with the float32-truncated geometry (potential.py:828-849)."""
+    import hashlib
+    from helpers import load_golden
+    from exptool_b200.basis import potential
+    d, meta = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        F = _fields_from_golden(tmp, d, meta)
+        F.time = 0.25
+        F.filename = 'snap'; F.eof_file = 'eof.cache'; F.sph_file = 'sl.cache'; F.model_file = 'sl.model'
+        ff = os.path.join(tmp, 'frozen.field')
+        F.save_field(ff)
+        assert os.path.getsize(ff) == int(d['field_size'])
+        with open(ff, 'rb') as fh:
+            assert hashlib.sha256(fh.read()).hexdigest() == str(d['field_sha'])
+        R = potential.restore_field(ff)
+    assert R.eof_file == b'eof.cache' and R.SL.sph_file == b'sl.cache' and int(R.nhalo) == 1000000
+    assert (int(R.mmax), int(R.norder), int(R.lmaxhalo), int(R.nmaxhalo)) == (F.mmax, F.norder, F.lmaxhalo, F.nmaxhalo)
+    assert np.array_equal(R.potC, F.potC) and np.array_equal(R.zforceS, F.zforceS) and np.array_equal(R.eftablehalo, F.eftablehalo)
+    assert np.array_equal(R.EOF.cos, d['cos']) and np.array_equal(R.SL.expcoef, d['coef'])
+    assert R.XMIN == np.float32(F.XMIN) and R.dY == np.float32(F.dY) and R.halofac == np.float32(meta['halofac'])
+    assert abs(float(R.XMIN) - float(F.XMIN)) > 0          # the f4 truncation is real (App. C #15)
+
+
+def test_orbit_map_text_format_roundtrip():
+    from helpers import load_golden
+    from exptool_b200.utils import integrate
+    import io
+    d, meta = load_golden('field_small')
+    buf = io.StringIO()
+    integrate.print_orbit_array(buf, d['grid'][:1, :1, :, :5])
+    assert buf.getvalue() == str(d['orbit_txt'])              # same characters as the reference's writer
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, 'omap.txt')
+        with open(fn, 'w') as f:
+            integrate.print_orbit_array(f, d['grid'])
+        D = integrate.read_integrations(fn)
+        g = d['grid']
+        assert len(D['X']) == g.shape[0] * g.shape[1]
+        assert np.allclose(D['X'][3], g[1, 1, 0]) and np.allclose(D['VY'][3], g[1, 1, 5]) and D['dT'][3] == g[1, 1, 6, 1]
+        fn3 = os.path.join(tmp, 'omap3.txt')
+        with open(fn3, 'w') as f:
+            integrate.print_orbit_array_3D(f, d['grid3'])
+        D3 = integrate.read_integrations_3D(fn3)
+        g3 = d['grid3']
+        assert np.allclose(D3['Z'][1], g3[0, 0, 1, 0, 2]) and np.allclose(D3['VZ'][1], g3[0, 0, 1, 0, 7])
