@@ -297,3 +297,67 @@ def test_generic_kernels_large_basis(ops):
     ref = O.sl_all_eval_particles(xh, yh, zh, cho, ps['lmax'], ps['nmax'], ev, ef, xi, p0, d0, ps['cmap'], ps['scale'])
     for i in range(6):
         assert relerr(out[i], ref[i]) < TOL, i
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json's full sizes (configs[0], configs[1]) against the C restatement of the oracle
+# ---------------------------------------------------------------------------
+def test_config_c2_eof_1e6_accumulate_force(ops):
+    """configs[1]: EOF mmax=6 norder=18, accumulate + force eval on a 10^6-particle exponential disc."""
+    from oracle import oracle_c as OC
+    meta = dict(eof_params={}, kind='smooth', seed=0)
+    p, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    x, y, z, m = S.exponential_disc(1000000, 2002)
+    co, so = OC.eof_accumulate(x, y, z, m, T['potC'], T['potS'], g)
+    fo = OC.eof_force(x, y, z, co, so, T, g)
+    for mode in (1, 2):                       # direct and cell-sorted kernel families
+        ops.set_option('eof_accumulate_mode', mode); ops.set_option('eof_force_mode', mode)
+        c, s = E.accumulate(x, y, z, m)
+        assert relerr(c.cpu().numpy(), co) < TOL and relerr(s.cpu().numpy(), so) < TOL, mode
+        E.contract(co, so)
+        f = E.force(x, y, z).cpu().numpy()
+        for i in range(6):
+            assert relerr(f[i], fo[i]) < TOL, (mode, i)
+    ops.set_option('eof_accumulate_mode', 0); ops.set_option('eof_force_mode', 0)
+    # the benchmark's own call sequence: one cell sort for both passes
+    E.prepare(x, y, z, m)
+    c, s = E.accumulate_prepared()
+    E.contract(c, s)
+    f = E.force_prepared().cpu().numpy()
+    assert relerr(c.cpu().numpy(), co) < TOL
+    for i in range(6):
+        assert relerr(f[i], fo[i]) < TOL, i
+    # size-independent properties: linearity in the masses, additivity over a split of the set
+    c2, s2 = E.accumulate(x, y, z, 3.0 * m)
+    assert relerr(c2.cpu().numpy(), 3.0 * co) < TOL
+    ca, sa = E.accumulate(x[:400000], y[:400000], z[:400000], m[:400000])
+    cb, sb = E.accumulate(x[400000:], y[400000:], z[400000:], m[400000:])
+    assert relerr((ca + cb).cpu().numpy(), co) < TOL and relerr((sa + sb).cpu().numpy(), so) < TOL
+    # a permutation of the particles changes only the summation order
+    perm = np.random.default_rng(1).permutation(x.size)
+    cp, sp = E.accumulate(x[perm], y[perm], z[perm], m[perm])
+    assert relerr(cp.cpu().numpy(), co) < 1e-12
+
+
+def test_config_c1_sl_1e5_accumulate_force(ops):
+    """configs[0]: SL lmax=4 nmax=18, accumulation + force eval on a 10^5-particle Hernquist halo."""
+    from oracle import oracle_c as OC
+    meta = dict(sl_params=dict(lmax=4), kind='smooth', seed=0)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    x, y, z, m = S.hernquist_halo(100000, 1001)
+    co = OC.sl_accumulate(x, y, z, m, p['lmax'], p['nmax'], ev, ef, xi, p0, p['cmap'], p['scale'])
+    for mode in (1, 2):
+        ops.set_option('sl_accumulate_mode', mode)
+        c = H.accumulate(x, y, z, m)
+        assert relerr(c.cpu().numpy(), co) < TOL, mode
+    ops.set_option('sl_accumulate_mode', 0)
+    H.contract(co)
+    f = H.force(x[:20000], y[:20000], z[:20000]).cpu().numpy()
+    ref = O.sl_all_eval_particles(x[:20000], y[:20000], z[:20000], co, p['lmax'], p['nmax'], ev, ef, xi, p0, d0,
+                                  p['cmap'], p['scale'])
+    for i in range(6):
+        assert relerr(f[i], ref[i]) < TOL, i
+    c2 = H.accumulate(x, y, z, 2.0 * m)
+    assert relerr(c2.cpu().numpy(), 2.0 * co) < TOL
