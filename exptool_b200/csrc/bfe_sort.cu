@@ -77,7 +77,8 @@ eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__
 __global__ void __launch_bounds__(256)
 eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                         const double* __restrict__ z, const double* __restrict__ mass,
-                        int* __restrict__ cursor, EofRec* __restrict__ rec, double* __restrict__ r_sorted) {
+                        int* __restrict__ cursor, EofRec* __restrict__ rec, int* __restrict__ inv,
+                        double* __restrict__ r_orig) {
     constexpr int U = 2;       // particles per thread per pass: independent slot claims overlap their latency
     for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
         EofBin b[U];
@@ -108,7 +109,8 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
                 dst[1] = make_double2(b[u].c01, b[u].c11);
                 dst[2] = make_double2(c1[u], s1[u]);
                 dst[3] = make_double2(aux[u], __longlong_as_double((long long)cp));
-                r_sorted[pos[u]] = r[u];
+                inv[idx[u]] = pos[u];             // original index -> sorted slot (coalesced)
+                r_orig[idx[u]] = r[u];
             }
         }
     }
@@ -457,14 +459,16 @@ static size_t deposit_smem_bytes() {
 }
 
 // ---------------------------------------------------------------------------
-// force evaluation in sorted order
+// force evaluation in sorted order: thread per sorted record, a warp's lanes share the contracted-grid
+// rows (warp-uniform addresses).  Results go to a 48-byte AoS slot in SORTED order (coalesced); a second
+// kernel in the caller's particle order gathers them through the inverse permutation and writes the six
+// SoA outputs coalesced.  (Scattering six 8-byte stores per thread straight from this kernel cost more
+// than the evaluation itself: partial-sector writes and their fills, ncu profiles/.)
 // ---------------------------------------------------------------------------
 template <int MCAP>
 __global__ void __launch_bounds__(128)
 eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, int64_t n,
-                        const EofRec* __restrict__ rec, const double* __restrict__ r_sorted,
-                        double* __restrict__ p0, double* __restrict__ p, double* __restrict__ fr,
-                        double* __restrict__ fp, double* __restrict__ fz, double* __restrict__ R) {
+                        const EofRec* __restrict__ rec, double2* __restrict__ tmp) {
     // each CTA takes one contiguous slice of the sorted records: an SM then sees a contiguous range
     // of cells and the contracted-grid rows stay in its L1
     const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 127) / 128 * 128;
@@ -475,13 +479,27 @@ eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, in
         double2 a = __ldg(src), bb = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
         unsigned long long cp = (unsigned long long)__double_as_longlong(d.y);
         const int cell = (int)(cp >> 32);
-        const unsigned int dst = (unsigned int)(cp & 0xffffffffull);
         EofBin b;
         const int ix = cell / g.numy, iy = cell - ix * g.numy;
         b.node = ix * g.ny1 + iy;
         b.c00 = a.x; b.c10 = a.y; b.c01 = bb.x; b.c11 = bb.y;
         EofField f = bfe_eof_eval<MCAP>(g, G, gstride, b, c.x, c.y);
-        p0[dst] = f.p0; p[dst] = f.p; fr[dst] = f.fr; fp[dst] = f.fp; fz[dst] = f.fz; R[dst] = __ldg(r_sorted + i);
+        double2* dst = tmp + 3 * i;
+        dst[0] = make_double2(f.p0, f.p);
+        dst[1] = make_double2(f.fr, f.fp);
+        dst[2] = make_double2(f.fz, 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __restrict__ r_orig,
+                        const double2* __restrict__ tmp, double* __restrict__ p0, double* __restrict__ p,
+                        double* __restrict__ fr, double* __restrict__ fp, double* __restrict__ fz,
+                        double* __restrict__ R) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2* src = tmp + 3 * (int64_t)__ldg(inv + i);
+        const double2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        p0[i] = a.x; p[i] = a.y; fr[i] = b.x; fp[i] = b.y; fz[i] = c.x; R[i] = __ldg(r_orig + i);
     }
 }
 
@@ -491,7 +509,7 @@ eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, in
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SortWs {
-    int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_sorted;
+    int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_orig; double2* tmp; int* inv;
 };
 
 static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
@@ -502,8 +520,9 @@ static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
     size_t o_rec = align_up(o_cur + sizeof(int) * ncell, 256);
     if (n > h->sort_cap || !h->sort_ws) {
         if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
-        int64_t cap = n + n / 8 + 1024;
-        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(EofRec) + sizeof(double)) * (size_t)cap));
+        int64_t cap = (n + n / 8 + 1024 + 15) / 16 * 16;      // multiple of 16: keeps every sub-array 16-B aligned
+        // per particle: 64-B record, R (8 B), 48-B force slot, inverse permutation (4 B)
+        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)cap));
         BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
         BFE_CUDA(cudaDeviceSynchronize());
         h->sort_cap = cap;
@@ -511,7 +530,9 @@ static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
     char* b = (char*)h->sort_ws;
     ws->hist = (int*)(b + o_hist); ws->cell_start = (int*)(b + o_start); ws->cursor = (int*)(b + o_cur);
     ws->rec = (EofRec*)(b + o_rec);
-    ws->r_sorted = (double*)(b + o_rec + sizeof(EofRec) * (size_t)h->sort_cap);
+    ws->r_orig = (double*)(b + o_rec + sizeof(EofRec) * (size_t)h->sort_cap);
+    ws->tmp = (double2*)(b + o_rec + (sizeof(EofRec) + sizeof(double)) * (size_t)h->sort_cap);
+    ws->inv = (int*)(b + o_rec + (sizeof(EofRec) + sizeof(double) + 48) * (size_t)h->sort_cap);
     return BFE_OK;
 }
 
@@ -543,7 +564,7 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     int g2 = (int)((n + 511) / 512);
     if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
     if (g2 < 1) g2 = 1;
-    eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cursor, ws.rec, ws.r_sorted);
+    eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cursor, ws.rec, ws.inv, ws.r_orig);
     BFE_LAUNCH_CHECK("eof_cell_scatter_kernel");
     h->prepared_n = n;
     h->prepared_has_mass = (mass || n == 0) ? 1 : 0;
@@ -590,9 +611,12 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
     if (rc != BFE_OK) return rc;
     int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
-    eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.r_sorted,
-                                                         p0, p, fr, fp, fz, R);
+    eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
     BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
+    int64_t need2 = (n + 255) / 256, cap2 = (int64_t)h->num_sms * 8;
+    eof_force_gather_kernel<<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, stream>>>(n, ws.inv, ws.r_orig, ws.tmp, p0, p,
+                                                                                  fr, fp, fz, R);
+    BFE_LAUNCH_CHECK("eof_force_gather_kernel");
     return BFE_OK;
 }
 
