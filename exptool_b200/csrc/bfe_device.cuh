@@ -55,7 +55,11 @@ __device__ __forceinline__ double bfe_d_xi_to_r(double xi, int cmap, double scal
 __device__ __forceinline__ double bfe_z_to_y(double z, double hscale) {
     // compatibility.py:91 (epsilon 1e-8: the live Python value, not accumulate.c's 1e-10)
     double az = fabs(z);
-    return (z / (az + 1.0e-8)) * asinh(fabs(z / hscale));
+    double u = fabs(z / hscale);
+    // asinh(u), u >= 0.  Only (y - ymin)/dy with y - ymin = O(1..10) is ever used, so ABSOLUTE accuracy ~1e-16 is
+    // what matters: log(u + sqrt(u^2+1)) delivers it without asinh()'s small-argument branches (about half the cost).
+    double ash = (u < 1.0e150) ? log(u + sqrt(fma(u, u, 1.0))) : asinh(u);
+    return (z / (az + 1.0e-8)) * ash;
 }
 
 // ---------------------------------------------------------------------------
