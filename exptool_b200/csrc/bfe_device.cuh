@@ -67,6 +67,7 @@ __device__ __forceinline__ double bfe_z_to_y(double z, double hscale) {
 // ---------------------------------------------------------------------------
 struct EofBin {
     int node;              // ix*(numy+1)+iy ; the other corners are +1, +ny1, +ny1+1
+    int cell;              // ix*numy+iy
     double c00, c10, c01, c11;
 };
 
@@ -89,6 +90,7 @@ __device__ __forceinline__ EofBin bfe_eof_bin(const EofGeom& g, double r, double
     double dely1 = Y - (double)iy;
     EofBin b;
     b.node = ix * g.ny1 + iy;
+    b.cell = ix * g.numy + iy;
     b.c00 = delx0 * dely0;
     b.c10 = delx1 * dely0;
     b.c01 = delx0 * dely1;
@@ -158,6 +160,76 @@ __device__ __forceinline__ EofField bfe_eof_eval(const EofGeom& g, const double*
                 f.fp += (double)m * (sm * vpc - cm * vps);
             }
             // advance to (m+1) phi
+            double cn = cm * c1 - sm * s1;
+            double sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+    }
+    return f;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative ("staged") evaluation.
+//
+// With one point per lane and scattered positions, every LDG.128 of a table row touches 32 different
+// 128-byte lines and costs ~32 L1 tag cycles; 84 of them per point bound the direct kernels (ncu,
+// profiles/).  Here the rows a point needs are stored as ONE contiguous block per cell (EOF:
+// G4[cell][m][corner][3 x double2]; SL: A3[j][(m,l)][3 nodes]), the WARP copies the 32 blocks of its
+// 32 points with coalesced 16-byte loads (each instruction covers 512 contiguous-ish bytes: ~5 lines
+// instead of 32) into a shared-memory stage, and each lane then reads its own block back conflict-free.
+// All 32 lanes must call these functions together (pass a clamped, valid index for idle lanes).
+// ---------------------------------------------------------------------------
+#define BFE_STAGE_DOUBLE2 (32 * 21 + 8)      // per-warp stage: 32 points x up to 21 chunks (stride kept odd)
+
+template <int NCH>
+__device__ __forceinline__ void bfe_warp_stage(const double2* __restrict__ table, size_t blk_chunks, int first_chunk,
+                                               int my_block, double2* __restrict__ st, int lane) {
+    constexpr int STRIDE = NCH | 1;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) {
+        const int c = lane + 32 * t;
+        const int owner = c / NCH, piece = c - owner * NCH;
+        const int oblk = __shfl_sync(0xffffffffu, my_block, owner);
+        st[owner * STRIDE + piece] = __ldg(table + (size_t)oblk * blk_chunks + first_chunk + piece);
+    }
+    __syncwarp();
+}
+
+template <int MCAP>
+__device__ __forceinline__ EofField bfe_eof_eval_staged(const EofGeom& g, const double2* __restrict__ G4,
+                                                        const EofBin& b, double c1, double s1,
+                                                        double2* __restrict__ st, int lane) {
+    EofField f;
+    f.p0 = 0.0; f.p = 0.0; f.fr = 0.0; f.fp = 0.0; f.fz = 0.0;
+    double cm = 1.0, sm = 0.0;
+    const size_t blk = (size_t)12 * (g.mmax + 1);
+    const double2* my = st + lane * 13;
+#pragma unroll
+    for (int m = 0; m <= MCAP; ++m) {
+        if (m <= g.mmax) {
+            bfe_warp_stage<12>(G4, blk, 12 * m, b.cell, st, lane);
+            // corners 00, 10, 01, 11; three double2 each: (pc,ps), (rc,rs), (zc,zs)
+            const double2 a0 = my[0], a1 = my[1], a2 = my[2];
+            const double2 b0 = my[3], b1 = my[4], b2 = my[5];
+            const double2 c0 = my[6], c1v = my[7], c2 = my[8];
+            const double2 d0 = my[9], d1 = my[10], d2 = my[11];
+            double vpc = a0.x * b.c00 + b0.x * b.c10 + c0.x * b.c01 + d0.x * b.c11;
+            double vps = a0.y * b.c00 + b0.y * b.c10 + c0.y * b.c01 + d0.y * b.c11;
+            double vrc = a1.x * b.c00 + b1.x * b.c10 + c1v.x * b.c01 + d1.x * b.c11;
+            double vrs = a1.y * b.c00 + b1.y * b.c10 + c1v.y * b.c01 + d1.y * b.c11;
+            double vzc = a2.x * b.c00 + b2.x * b.c10 + c2.x * b.c01 + d2.x * b.c11;
+            double vzs = a2.y * b.c00 + b2.y * b.c10 + c2.y * b.c01 + d2.y * b.c11;
+            if (m == 0) {
+                f.p0 = vpc;
+                f.fr = vrc;
+                f.fz = vzc;
+            } else {
+                f.p  += cm * vpc + sm * vps;
+                f.fr += cm * vrc + sm * vrs;
+                f.fz += cm * vzc + sm * vzs;
+                f.fp += (double)m * (sm * vpc - cm * vps);
+            }
             double cn = cm * c1 - sm * s1;
             double sn = sm * c1 + cm * s1;
             cm = cn; sm = sn;
@@ -408,6 +480,109 @@ __device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double2* _
     return f;
 }
 
+// Staged SL evaluation; valid only when g.lmax == LCAP (compile-time chunk counts).
+// A3[j][chunk], chunk = 3*(offm(m) + l - m) + node, node 0,1,2 = rows j-1, j, j+1; offm(m) = sum_{m'<m}(LCAP-m'+1).
+template <int LCAP>
+__device__ __forceinline__ SlField bfe_sl_eval_staged(const SlGeom& g, const double2* __restrict__ A3,
+                                                      const double* __restrict__ p0tab, const double* __restrict__ fac,
+                                                      const SlBin& b, double costh, double c1, double s1,
+                                                      bool trig_index_l, double2* __restrict__ st, int lane) {
+    constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
+    const int j = (b.i == 0) ? 1 : b.i;
+    const double pm = __ldg(p0tab + j - 1), pc = __ldg(p0tab + j), pp = __ldg(p0tab + j + 1);
+    double P0, wA, wB, wC;
+    if (b.i == 0) { P0 = b.x1 * pm + b.x2 * pc; wA = b.x1; wB = b.x2; wC = 0.0; }
+    else          { P0 = b.x1 * pc + b.x2 * pp; wA = 0.0; wB = b.x1; wC = b.x2; }
+    wA *= P0; wB *= P0; wC *= P0;
+    const double dA = b.fac * (b.x2 - 0.5) * pm, dB = b.fac * (-2.0 * b.x2) * pc, dC = b.fac * (b.x2 + 0.5) * pp;
+
+    const double x = costh;
+    const double somx2 = sqrt(BFE_MUL(BFE_SUB(1.0, x), BFE_ADD(1.0, x)));
+    double xd = x;
+    if (1.0 - fabs(xd) < 1.0e-8) xd = (xd > 0.0) ? (1.0 - 1.0e-8) : -(1.0 - 1.0e-8);
+    const double dsom = BFE_DIV(1.0, BFE_SUB(BFE_MUL(xd, xd), 1.0));
+
+    SlField f;
+    f.pot0 = 0.0; f.pot1 = 0.0; f.potr = 0.0; f.pott = 0.0; f.potp = 0.0;
+    double pmm = 1.0, fact = 1.0;
+    double cm = 1.0, sm = 0.0;
+    int offm = 0;
+#pragma unroll
+    for (int m = 0; m <= LCAP; ++m) {
+        constexpr int dummy = 0; (void)dummy;
+        const int nl = LCAP - m + 1;                       // l values in this column (compile time after unrolling)
+        // stage this column: 3*nl chunks per point
+        {
+            const int NCHr = 3 * nl, STRIDE = NCHr | 1;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 3 * (LCAP + 1); ++t) {
+                if (t < NCHr) {
+                    const int c = lane + 32 * t;
+                    const int owner = c / NCHr, piece = c - owner * NCHr;
+                    const int oj = __shfl_sync(0xffffffffu, j, owner);
+                    st[owner * STRIDE + piece] = __ldg(A3 + (size_t)oj * (3 * NPAIR) + 3 * offm + piece);
+                }
+            }
+            __syncwarp();
+        }
+        const double2* my = st + lane * ((3 * nl) | 1);
+        if (m > 0) {
+            pmm = BFE_MUL(pmm, BFE_MUL(-fact, somx2));
+            fact += 2.0;
+            double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+        double pl2 = 0.0, pl1 = pmm;
+        double cl = cm, sl = sm;
+#pragma unroll
+        for (int l = m; l <= LCAP; ++l) {
+            double P, dP;
+            if (l == m) {
+                P = pmm;
+                dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);
+            } else {
+                if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);
+                else P = BFE_DIV(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                         BFE_MUL((double)(l + m - 1), pl2)), (double)(l - m));
+                dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P), BFE_MUL((double)(l + m), pl1)));
+                pl2 = pl1; pl1 = P;
+                double cn = cl * c1 - sl * s1, sn = sl * c1 + cl * s1;
+                cl = cn; sl = sn;
+            }
+            const double2 am = my[3 * (l - m)], a0 = my[3 * (l - m) + 1], ap = my[3 * (l - m) + 2];
+            const double fl = __ldg(fac + l * (LCAP + 1) + m);
+            const double spc = wA * am.x + wB * a0.x + wC * ap.x;
+            const double sdc = dA * am.x + dB * a0.x + dC * ap.x;
+            if (m == 0) {
+                if (l == 0) {
+                    f.pot0 = fl * spc;
+                    f.potr += fl * sdc;
+                } else {
+                    f.pot1 += fl * P * spc;
+                    f.potr += fl * P * sdc;
+                    f.pott += fl * dP * spc;
+                }
+            } else {
+                const double sps = wA * am.y + wB * a0.y + wC * ap.y;
+                const double sds = dA * am.y + dB * a0.y + dC * ap.y;
+                const double ct = trig_index_l ? cl : cm;
+                const double stt = trig_index_l ? sl : sm;
+                const double Ap = spc * ct + sps * stt;
+                const double Ad = sdc * ct + sds * stt;
+                const double Bp = sps * ct - spc * stt;
+                const double fP = fl * P;
+                f.pot1 += fP * Ap;
+                f.potr += fP * Ad;
+                f.pott += fl * dP * Ap;
+                f.potp += fP * (double)m * Bp;
+            }
+        }
+        offm += nl;
+    }
+    return f;
+}
+
 // ---------------------------------------------------------------------------
 // Fields.return_forces_cart -- potential.py:455-497
 // ---------------------------------------------------------------------------
@@ -448,6 +623,51 @@ __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const dou
         o.fzd = diskfz;
         o.fzh = -1.0 * (z * halofr - r2 * haloft) / r3;      // 435
         o.pd = -1.0 * diskp;                                  // 440
+        o.ph = h.pot1 + h.pot0;
+        return o;
+    }
+    double r2sq = r2 * r2, r3cu = r3 * r3 * r3;
+    o.fxd = diskfr * (x / r2) - diskfp * (y / r2sq);
+    o.fxh = -1.0 * (halofr * (x / r3) - haloft * (x * z / r3cu)) + halofp * (y / r2sq);
+    o.fyd = diskfr * (y / r2) + diskfp * (x / r2sq);
+    o.fyh = -1.0 * (halofr * (y / r3) - haloft * (y * z / r3cu)) - halofp * (x / r2sq);
+    o.fzd = diskfz;
+    o.fzh = -1.0 * (halofr * (z / r3) + haloft * (r2sq / r3cu));
+    o.pd = diskp;
+    o.ph = h.pot1 + h.pot0;
+    return o;
+}
+
+template <int MCAP, int LCAP, bool CYL>
+__device__ __forceinline__ CartForce bfe_field_cart_staged(const EofGeom& ge, const double2* __restrict__ G4,
+                                                           const SlGeom& gs, const double2* __restrict__ A3,
+                                                           const double* __restrict__ xi, const double* __restrict__ p0tab,
+                                                           const double* __restrict__ fac, double x, double y, double z,
+                                                           double crot, double srot, double2* __restrict__ st, int lane) {
+    const double eps = CYL ? 1.e-10 : 1.e-15;
+    double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + eps;
+    double r3 = sqrt(BFE_ADD(BFE_MUL(r2, r2), BFE_MUL(z, z))) + eps;
+    double costh = BFE_DIV(z, r3);
+    double c1, s1;
+    bfe_cossin_phi(x, y, c1, s1);
+    double cr = c1 * crot - s1 * srot;
+    double sr = s1 * crot + c1 * srot;
+    EofBin eb = bfe_eof_bin(ge, r2, z);
+    EofField d = bfe_eof_eval_staged<MCAP>(ge, G4, eb, cr, sr, st, lane);
+    SlBin sb = bfe_sl_bin(gs, xi, r3);
+    SlField h = bfe_sl_eval_staged<LCAP>(gs, A3, p0tab, fac, sb, costh, cr, sr, true, st, lane);
+    double diskfr = d.fr, diskfp = d.fp, diskfz = d.fz, diskp = d.p + d.p0;
+    double halofr = h.potr, haloft = h.pott, halofp = h.potp;
+    if (r3 < gs.xi0) { halofp = 0.0; diskfp = 0.0; }
+    CartForce o;
+    if (CYL) {
+        o.fxd = diskfr;
+        o.fxh = -1.0 * (r2 * halofr + z * haloft) / r3;
+        o.fyd = diskfp;
+        o.fyh = -1.0 * halofp;
+        o.fzd = diskfz;
+        o.fzh = -1.0 * (z * halofr - r2 * haloft) / r3;
+        o.pd = -1.0 * diskp;
         o.ph = h.pot1 + h.pot0;
         return o;
     }

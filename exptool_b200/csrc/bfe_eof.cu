@@ -193,6 +193,67 @@ eof_force_kernel(EofGeom g, const double* __restrict__ G, int gstride, int64_t n
     }
 }
 
+// g_con [node][m][6] -> G4 [cell][m][corner][3 double2]
+__global__ void eof_expand_g4_kernel(EofGeom g, const double* __restrict__ G, int gstride, double2* __restrict__ G4) {
+    const int per = 12 * (g.mmax + 1);
+    const int64_t total = (int64_t)g.numx * g.numy * per;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int cell = (int)(t / per), c = (int)(t - (int64_t)cell * per);
+        const int m = c / 12, r = c - m * 12, corner = r / 3, part = r - corner * 3;
+        const int ix = cell / g.numy, iy = cell - ix * g.numy;
+        const int node = ix * g.ny1 + iy + ((corner & 1) ? g.ny1 : 0) + ((corner & 2) ? 1 : 0);   // 00,10,01,11
+        const double* src = G + (size_t)node * gstride + m * 6 + part * 2;
+        G4[t] = make_double2(src[0], src[1]);
+    }
+}
+
+// warp-cooperative versions (bfe_eof_eval_staged): lanes of a warp take 32 consecutive points
+template <int MCAP>
+__global__ void __launch_bounds__(128)
+eof_force_staged_kernel(EofGeom g, const double2* __restrict__ G4, int64_t n,
+                        const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                        double* __restrict__ p0, double* __restrict__ p, double* __restrict__ fr,
+                        double* __restrict__ fp, double* __restrict__ fz, double* __restrict__ R) {
+    __shared__ double2 s_stage[4][BFE_STAGE_DOUBLE2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* st = s_stage[warp];
+    const int64_t wglobal = (int64_t)blockIdx.x * 4 + warp, wtotal = (int64_t)gridDim.x * 4;
+    for (int64_t base = wglobal * 32; base < n; base += wtotal * 32) {
+        const int64_t i = base + lane;
+        const bool on = i < n;
+        const int64_t ii = on ? i : n - 1;
+        double px = __ldg(x + ii), py = __ldg(y + ii), pz = __ldg(z + ii);
+        double r = sqrt(px * px + py * py + 1.e-10);              // eof.py:1070
+        EofBin b = bfe_eof_bin(g, r, pz);
+        double c1, s1;
+        bfe_cossin_phi(px, py, c1, s1);
+        EofField f = bfe_eof_eval_staged<MCAP>(g, G4, b, c1, s1, st, lane);
+        if (on) { p0[i] = f.p0; p[i] = f.p; fr[i] = f.fr; fp[i] = f.fp; fz[i] = f.fz; R[i] = r; }
+    }
+}
+
+template <int MCAP>
+__global__ void __launch_bounds__(128)
+eof_points_staged_kernel(EofGeom g, const double2* __restrict__ G4, int64_t n,
+                         const double* __restrict__ r, const double* __restrict__ z, const double* __restrict__ phi,
+                         double* __restrict__ fr, double* __restrict__ fp, double* __restrict__ fz,
+                         double* __restrict__ p, double* __restrict__ p0) {
+    __shared__ double2 s_stage[4][BFE_STAGE_DOUBLE2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* st = s_stage[warp];
+    const int64_t wglobal = (int64_t)blockIdx.x * 4 + warp, wtotal = (int64_t)gridDim.x * 4;
+    for (int64_t base = wglobal * 32; base < n; base += wtotal * 32) {
+        const int64_t i = base + lane;
+        const bool on = i < n;
+        const int64_t ii = on ? i : n - 1;
+        EofBin b = bfe_eof_bin(g, __ldg(r + ii), __ldg(z + ii));
+        double c1, s1;
+        sincos(__ldg(phi + ii), &s1, &c1);
+        EofField f = bfe_eof_eval_staged<MCAP>(g, G4, b, c1, s1, st, lane);
+        if (on) { fr[i] = f.fr; fp[i] = f.fp; fz[i] = f.fz; p[i] = f.p + f.p0; p0[i] = f.p0; }
+    }
+}
+
 // eof.force_eval at (r, z, phi) points: returns fr, fp, fz (m=0 included), p+p0, p0
 template <int MCAP>
 __global__ void __launch_bounds__(128)
@@ -246,6 +307,8 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     h->max_ctas = h->num_sms * 4;
     BFE_CUDA(cudaMalloc(&h->t_acc, (size_t)g.nnode * h->nch_pad * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->g4, (size_t)g.numx * g.numy * 12 * (p->mmax + 1) * 2 * sizeof(double)));
+    h->g4_valid = 0;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * h->nch_pad * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
@@ -266,7 +329,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
 
 extern "C" void bfe_eof_destroy(bfe_eof* h) {
     if (!h) return;
-    cudaFree(h->t_acc); cudaFree(h->g_con); cudaFree(h->partial); cudaFree(h->counter);
+    cudaFree(h->t_acc); cudaFree(h->g_con); cudaFree(h->g4); cudaFree(h->partial); cudaFree(h->counter);
     if (h->t_force) cudaFree(h->t_force);
     if (h->sort_ws) cudaFree(h->sort_ws);
     delete h;
@@ -309,6 +372,16 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
                                                  h->g_con, h->gstride);
     BFE_LAUNCH_CHECK("eof_contract_kernel");
     h->contracted = 1;
+    h->g4_valid = 0;
+    return BFE_OK;
+}
+
+int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream) {
+    if (h->g4_valid) return BFE_OK;
+    eof_expand_g4_kernel<<<h->num_sms * 8, 256, 0, stream>>>(h->g, h->g_con, h->gstride,
+                                                            reinterpret_cast<double2*>(h->g4));
+    BFE_LAUNCH_CHECK("eof_expand_g4_kernel");
+    h->g4_valid = 1;
     return BFE_OK;
 }
 
@@ -326,7 +399,12 @@ extern "C" int bfe_eof_force_contracted(bfe_eof* h, int64_t n, const double* x, 
             return bfe_eof_force_sorted(h, n, x, y, z, p0, p, fr, fp, fz, R, stream);
     }
     int grid = grid_for(n, 128, h->num_sms, 16);
-    if (h->g.mmax <= 6)
+    if (h->g.mmax <= 6 && g_bfe_staged_eval) {
+        int rc = bfe_eof_ensure_g4(h, stream);
+        if (rc != BFE_OK) return rc;
+        eof_force_staged_kernel<6><<<grid, 128, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->g4), n, x, y, z,
+                                                            p0, p, fr, fp, fz, R);
+    } else if (h->g.mmax <= 6)
         eof_force_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, x, y, z, p0, p, fr, fp, fz, R);
     else
         eof_force_kernel<BFE_MAX_MMAX><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, x, y, z, p0, p, fr,
@@ -351,7 +429,12 @@ extern "C" int bfe_eof_force_eval_points(bfe_eof* h, int64_t n, const double* r,
     if (!r || !z || !phi || !fr || !fp || !fz || !p || !p0) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = grid_for(n, 128, h->num_sms, 16);
-    if (h->g.mmax <= 6)
+    if (h->g.mmax <= 6 && g_bfe_staged_eval) {
+        int rc = bfe_eof_ensure_g4(h, stream);
+        if (rc != BFE_OK) return rc;
+        eof_points_staged_kernel<6><<<grid, 128, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->g4), n, r, z, phi,
+                                                             fr, fp, fz, p, p0);
+    } else if (h->g.mmax <= 6)
         eof_points_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, r, z, phi, fr, fp, fz, p, p0);
     else
         eof_points_kernel<BFE_MAX_MMAX><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, r, z, phi, fr, fp,

@@ -36,6 +36,10 @@ struct bfe_eof {
     double* g_con;
     int gstride;         // 6*(mmax+1)
     int contracted;
+    // the same contraction as one contiguous block per CELL: G4[cell][m][corner 00,10,01,11][3 x double2]
+    // (built on demand from g_con for the warp-cooperative kernels)
+    double* g4;
+    int g4_valid;
     // accumulate workspace
     double* partial;     // [max_ctas][nch_pad]
     unsigned int* counter;
@@ -61,6 +65,9 @@ struct bfe_sl {
     double* a_con;       // contracted rows, node-major [numr][kpad] of double2 (cos, sin), kpad = (l,m) pairs
     int kpad;
     int contracted;
+    // the same rows as one contiguous block per radial index j: A3[j][(m,l)][rows j-1, j, j+1] (double2)
+    double* a3;
+    int a3_valid;
     double* partial;     // [max_ctas][nrow*nmax]
     unsigned int* counter;
     int max_ctas;
@@ -86,6 +93,9 @@ int bfe_eof_accumulate_sorted(bfe_eof* h, int64_t n, const double* x, const doub
 int bfe_eof_force_sorted(bfe_eof* h, int64_t n, const double* x, const double* y, const double* z,
                          double* p0, double* p, double* fr, double* fp, double* fz, double* R, cudaStream_t stream);
 void bfe_set_cuda_error(cudaError_t e, const char* where);
+int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream);     // build G4 from g_con if stale
+int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream);       // build A3 from a_con if stale
+extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0
 
 #define BFE_CUDA(call)                                                  \
     do {                                                                \

@@ -174,6 +174,76 @@ __global__ void sl_contract_kernel(SlGeom g, const double* __restrict__ e_node, 
     A[((size_t)i * qstride + (l * (l + 1)) / 2 + m) * 2 + comp] = s;
 }
 
+// a_con [i][q = l(l+1)/2 + m] -> A3 [j][3*(offm(m) + l - m) + node], node 0,1,2 = rows j-1, j, j+1 (valid for 1 <= j <= numr-2)
+__global__ void sl_expand_a3_kernel(SlGeom g, const double2* __restrict__ A, int qstride, double2* __restrict__ A3) {
+    const int npair = qstride;
+    const int64_t total = (int64_t)g.numr * npair * 3;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t / (3 * npair)), c = (int)(t - (int64_t)j * 3 * npair);
+        const int qm = c / 3, node = c - qm * 3;
+        // (m, l) from the column-major pair index qm
+        int m = 0, off = 0;
+        while (qm >= off + (g.lmax - m + 1)) { off += g.lmax - m + 1; ++m; }
+        const int l = m + (qm - off);
+        const int row = j - 1 + node;
+        double2 v = make_double2(0.0, 0.0);
+        if (row >= 0 && row < g.numr) v = A[(size_t)row * qstride + (l * (l + 1)) / 2 + m];
+        A3[t] = v;
+    }
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+sl_force_staged_kernel(SlGeom g, const double2* __restrict__ A3, const double* __restrict__ xi,
+                       const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
+                       const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                       double* __restrict__ pot0, double* __restrict__ pot1, double* __restrict__ potr,
+                       double* __restrict__ pott, double* __restrict__ potp, double* __restrict__ rr) {
+    __shared__ double2 s_stage[4][BFE_STAGE_DOUBLE2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* st = s_stage[warp];
+    const int64_t wglobal = (int64_t)blockIdx.x * 4 + warp, wtotal = (int64_t)gridDim.x * 4;
+    for (int64_t base = wglobal * 32; base < n; base += wtotal * 32) {
+        const int64_t i = base + lane;
+        const bool on = i < n;
+        const int64_t ii = on ? i : n - 1;
+        double px = __ldg(x + ii), py = __ldg(y + ii), pz = __ldg(z + ii);
+        double rxy2 = BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py));
+        double r = sqrt(BFE_ADD(rxy2, BFE_MUL(pz, pz)));          // spheresl.py:1257 (no epsilon)
+        double rxy = sqrt(rxy2);
+        double costh = BFE_DIV(pz, r);
+        double c1, s1;
+        bfe_cossin_phi(px, py, c1, s1);
+        SlBin b = bfe_sl_bin(g, xi, r);
+        SlField f = bfe_sl_eval_staged<LCAP>(g, A3, p0tab, fac, b, costh, c1, s1, false, st, lane);
+        if (on) { pot0[i] = f.pot0; pot1[i] = f.pot1; potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; rr[i] = rxy; }
+    }
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+sl_points_staged_kernel(SlGeom g, const double2* __restrict__ A3, const double* __restrict__ xi,
+                        const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
+                        const double* __restrict__ r, const double* __restrict__ costh, const double* __restrict__ phi,
+                        int trig_index_l,
+                        double* __restrict__ potr, double* __restrict__ pott, double* __restrict__ potp,
+                        double* __restrict__ pot1, double* __restrict__ pot0) {
+    __shared__ double2 s_stage[4][BFE_STAGE_DOUBLE2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2* st = s_stage[warp];
+    const int64_t wglobal = (int64_t)blockIdx.x * 4 + warp, wtotal = (int64_t)gridDim.x * 4;
+    for (int64_t base = wglobal * 32; base < n; base += wtotal * 32) {
+        const int64_t i = base + lane;
+        const bool on = i < n;
+        const int64_t ii = on ? i : n - 1;
+        double c1, s1;
+        sincos(__ldg(phi + ii), &s1, &c1);
+        SlBin b = bfe_sl_bin(g, xi, __ldg(r + ii));
+        SlField f = bfe_sl_eval_staged<LCAP>(g, A3, p0tab, fac, b, __ldg(costh + ii), c1, s1, trig_index_l != 0, st, lane);
+        if (on) { potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; pot1[i] = f.pot1; pot0[i] = f.pot0; }
+    }
+}
+
 template <int LCAP>
 __global__ void __launch_bounds__(128)
 sl_force_kernel(SlGeom g, const double2* __restrict__ A, int kpad, const double* __restrict__ xi,
@@ -276,6 +346,8 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->d0, nr * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->fac, sizeof(double) * (p->lmax + 1) * (p->lmax + 1)));
     BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * 2 * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->a3, nr * h->kpad * 3 * 2 * sizeof(double)));
+    h->a3_valid = 0;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
@@ -307,7 +379,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
 extern "C" void bfe_sl_destroy(bfe_sl* h) {
     if (!h) return;
     cudaFree(h->e_node); cudaFree(h->xi); cudaFree(h->p0); cudaFree(h->d0); cudaFree(h->fac);
-    cudaFree(h->a_con); cudaFree(h->partial); cudaFree(h->counter);
+    cudaFree(h->a_con); cudaFree(h->a3); cudaFree(h->partial); cudaFree(h->counter);
     if (h->sort_ws) cudaFree(h->sort_ws);
     delete h;
 }
@@ -337,6 +409,16 @@ extern "C" int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2,
     sl_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->e_node, expcoef, l1, l2, nuse, no_odd, h->a_con, h->kpad);
     BFE_LAUNCH_CHECK("sl_contract_kernel");
     h->contracted = 1;
+    h->a3_valid = 0;
+    return BFE_OK;
+}
+
+int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream) {
+    if (h->a3_valid) return BFE_OK;
+    sl_expand_a3_kernel<<<h->num_sms * 4, 256, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad,
+                                                           reinterpret_cast<double2*>(h->a3));
+    BFE_LAUNCH_CHECK("sl_expand_a3_kernel");
+    h->a3_valid = 1;
     return BFE_OK;
 }
 
@@ -356,6 +438,19 @@ extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, co
     if (!x || !y || !z || !pot0 || !pot1 || !potr || !pott || !potp || !rr) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    if (g_bfe_staged_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
+        int rc = bfe_sl_ensure_a3(h, stream);
+        if (rc != BFE_OK) return rc;
+        const double2* A3 = reinterpret_cast<const double2*>(h->a3);
+        if (h->g.lmax == 4)
+            sl_force_staged_kernel<4><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1,
+                                                               potr, pott, potp, rr);
+        else
+            sl_force_staged_kernel<6><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1,
+                                                               potr, pott, potp, rr);
+        BFE_LAUNCH_CHECK("sl_force_staged_kernel");
+        return BFE_OK;
+    }
     SL_DISPATCH(sl_force_kernel, h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott,
                 potp, rr);
     BFE_LAUNCH_CHECK("sl_force_kernel");
@@ -382,6 +477,19 @@ extern "C" int bfe_sl_force_eval_points(bfe_sl* h, int64_t n, const double* r, c
     if (!r || !costh || !phi || !potr || !pott || !potp || !pot1 || !pot0) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    if (g_bfe_staged_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
+        int rc = bfe_sl_ensure_a3(h, stream);
+        if (rc != BFE_OK) return rc;
+        const double2* A3 = reinterpret_cast<const double2*>(h->a3);
+        if (h->g.lmax == 4)
+            sl_points_staged_kernel<4><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, r, costh, phi,
+                                                                trig_index_l, potr, pott, potp, pot1, pot0);
+        else
+            sl_points_staged_kernel<6><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, r, costh, phi,
+                                                                trig_index_l, potr, pott, potp, pot1, pot0);
+        BFE_LAUNCH_CHECK("sl_points_staged_kernel");
+        return BFE_OK;
+    }
     SL_DISPATCH(sl_points_kernel, h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l,
                 potr, pott, potp, pot1, pot0);
     BFE_LAUNCH_CHECK("sl_points_kernel");
