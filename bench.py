@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
@@ -304,25 +304,51 @@ def run_gpu(args):
         o = outs[k % NSETS]
         L.check(lib.bfe_eof_force_prepared(E.h, *[_ptr(o[i]) for i in range(6)], _stream()))
 
-    reps = max(args.steps, 5)
+    reps = max(min(args.steps, 50), 5)
     t_prep, t_acc = time_kernel(k_prep, reps), time_kernel(k_acc, reps)
     t_con, t_force = time_kernel(k_con, reps), time_kernel(k_force, reps)
+    # live duration of every kernel of the step: CUDA events recorded inside the library around each launch
+    # (bfe_set_option "time_kernels"), averaged over whole steps on rotating particle sets
+    KNAMES = ['eof_cell_hist_kernel', 'eof_cell_scatter_kernel', 'eof_deposit_kernel', 'eof_contract_kernel',
+              'eof_force_sorted_kernel', 'eof_force_gather_kernel']
+    ops.set_option('time_kernels', 1)
+    ksum = {k: 0.0 for k in KNAMES}
+    for k in range(reps):
+        step(k)
+        for nme in KNAMES:
+            ksum[nme] += ops.kernel_time_ms(nme)
+    ops.set_option('time_kernels', 0)
+    kms = {k: v / reps for k, v in ksum.items()}
     if sampler:
         sampler.stop()
     peak, peak_src = measured_peaks()
-    # algorithmic HBM bytes per launch: prepare = 3 kernels reading x,y,z (+m) twice and writing
-    # 72-B records; deposit reads the records; force reads the records and writes six outputs.
-    kern = {'eof_prepare (hist+scan+scatter)': (t_prep, (24 + 32 + 72) * N_PART),
-            'eof_deposit_kernel': (t_acc, 64 * N_PART),
-            'eof_force_sorted_kernel': (t_force, (72 + 48) * N_PART)}
-    dom = max(kern, key=lambda k: kern[k][0])
-    achieved = kern[dom][1] / (kern[dom][0] * 1e-3) / 1e9
-    step_alg = (BYTES_ACC + BYTES_FORCE) * N_PART            # SURVEY.md section 8d: 104 B / particle for the whole step
+    # algorithmic HBM bytes per particle of the pass a kernel belongs to:
+    # accumulate 32 B (x,y,z,m), force 72 B (x,y,z + six outputs); the contraction reads the six tables once.
+    alg = {'eof_cell_hist_kernel': BYTES_ACC * N_PART, 'eof_cell_scatter_kernel': BYTES_ACC * N_PART,
+           'eof_deposit_kernel': BYTES_ACC * N_PART, 'eof_contract_kernel': 6 * 7 * 18 * 129 * 65 * 8,
+           'eof_force_sorted_kernel': BYTES_FORCE * N_PART, 'eof_force_gather_kernel': BYTES_FORCE * N_PART}
+    dom = max(kms, key=lambda k: kms[k])
+    achieved = alg[dom] / (kms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')       # dram bytes per launch, ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
+    step_alg = (BYTES_ACC + BYTES_FORCE) * N_PART            # 104 B / particle for the whole step
+    t_accpass = kms['eof_cell_hist_kernel'] + kms['eof_cell_scatter_kernel'] + kms['eof_deposit_kernel']
+    t_forcepass = kms['eof_force_sorted_kernel'] + kms['eof_force_gather_kernel']
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'kernel_ms': {'eof_prepare': t_prep, 'eof_deposit_kernel': t_acc, 'eof_contract_kernel': t_con,
-                              'eof_force_sorted_kernel': t_force},
-                'algorithmic_bytes_per_launch': kern[dom][1],
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg[dom],
+                'kernel_ms': kms,
+                'api_call_ms': {'bfe_eof_prepare': t_prep, 'bfe_eof_accumulate_prepared': t_acc,
+                                'bfe_eof_contract': t_con, 'bfe_eof_force_prepared': t_force},
+                'passes': {'accumulate (hist+scatter+deposit)': {'ms': t_accpass, 'algorithmic_bytes': BYTES_ACC * N_PART,
+                                                                'achieved': BYTES_ACC * N_PART / (t_accpass * 1e-3) / 1e9,
+                                                                'frac': BYTES_ACC * N_PART / (t_accpass * 1e-3) / 1e9 / peak},
+                           'force (force_sorted+gather)': {'ms': t_forcepass, 'algorithmic_bytes': BYTES_FORCE * N_PART,
+                                                           'achieved': BYTES_FORCE * N_PART / (t_forcepass * 1e-3) / 1e9,
+                                                           'frac': BYTES_FORCE * N_PART / (t_forcepass * 1e-3) / 1e9 / peak}},
                 'step': {'algorithmic_bytes': step_alg, 'achieved': step_alg / (ms_per_step * 1e-3) / 1e9,
                          'frac': step_alg / (ms_per_step * 1e-3) / 1e9 / peak}}
 

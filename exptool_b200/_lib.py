@@ -39,6 +39,7 @@ SIGNATURES = {
     'bfe_version': (_INT, []),
     'bfe_launch_count': (C.c_uint64, []),
     'bfe_set_option': (_INT, [C.c_char_p, _INT]),
+    'bfe_kernel_time_ms': (C.c_double, [C.c_char_p]),
     'bfe_eof_create': (_INT, [C.POINTER(EofParams)] + [_P] * 6 + [_P, C.POINTER(_P)]),
     'bfe_eof_destroy': (None, [_P]),
     'bfe_eof_accumulate': (_INT, [_P, _I64] + [_P] * 4 + [_P, _P, _P]),

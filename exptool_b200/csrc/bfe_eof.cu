@@ -368,8 +368,10 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nuse < 0) nuse = 0;
     dim3 grd((h->g.nnode + 127) / 128, (h->g.mmax + 1) * 6);
+    const int kt = bfe_kt_begin("eof_contract_kernel", stream);
     eof_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->t_force, h->tab_elems, cosc, sinc, m1, m2, nuse, no_odd,
                                                  h->g_con, h->gstride);
+    bfe_kt_end(kt, stream);
     BFE_LAUNCH_CHECK("eof_contract_kernel");
     h->contracted = 1;
     h->g4_valid = 0;

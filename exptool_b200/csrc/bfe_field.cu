@@ -214,15 +214,59 @@ int g_bfe_eof_force_mode = 0;
 int g_bfe_sort_min_particles = 32768;
 int g_bfe_sl_accumulate_mode = 0;
 int g_bfe_staged_eval = 1;
+static int g_bfe_time_kernels = 0;
 
 extern "C" int bfe_set_option(const char* name, int value) {
     if (!name) return BFE_ERR_ARG;
     if (!strcmp(name, "eof_accumulate_mode")) { g_bfe_eof_accumulate_mode = value; return BFE_OK; }
     if (!strcmp(name, "eof_force_mode")) { g_bfe_eof_force_mode = value; return BFE_OK; }
+    if (!strcmp(name, "time_kernels")) { g_bfe_time_kernels = value; return BFE_OK; }
     if (!strcmp(name, "staged_eval")) { g_bfe_staged_eval = value; return BFE_OK; }
     if (!strcmp(name, "sl_accumulate_mode")) { g_bfe_sl_accumulate_mode = value; return BFE_OK; }
     if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
     return BFE_ERR_ARG;
+}
+
+// ---- optional per-kernel event timing
+struct BfeKernelTimer { char name[48]; cudaEvent_t a, b; bool made, used; };
+static BfeKernelTimer g_kt[24];
+static int g_kt_n = 0;
+
+int bfe_kt_begin(const char* name, cudaStream_t stream) {
+    if (!g_bfe_time_kernels) return -1;
+    int slot = -1;
+    for (int i = 0; i < g_kt_n; ++i) if (!strcmp(g_kt[i].name, name)) { slot = i; break; }
+    if (slot < 0) {
+        if (g_kt_n >= 24) return -1;
+        slot = g_kt_n++;
+        strncpy(g_kt[slot].name, name, 47); g_kt[slot].name[47] = 0;
+        g_kt[slot].made = false; g_kt[slot].used = false;
+    }
+    if (!g_kt[slot].made) {
+        if (cudaEventCreate(&g_kt[slot].a) != cudaSuccess || cudaEventCreate(&g_kt[slot].b) != cudaSuccess) return -1;
+        g_kt[slot].made = true;
+    }
+    cudaEventRecord(g_kt[slot].a, stream);
+    return slot;
+}
+
+void bfe_kt_end(int slot, cudaStream_t stream) {
+    if (slot < 0) return;
+    cudaEventRecord(g_kt[slot].b, stream);
+    g_kt[slot].used = true;
+}
+
+// duration (ms) of the most recent launch of `name` recorded while "time_kernels" was on; < 0 if none.
+extern "C" double bfe_kernel_time_ms(const char* name) {
+    if (!name) return -1.0;
+    for (int i = 0; i < g_kt_n; ++i)
+        if (!strcmp(g_kt[i].name, name) && g_kt[i].used) {
+            float ms = -1.f;
+            if (cudaEventSynchronize(g_kt[i].b) != cudaSuccess) return -1.0;
+            if (cudaEventElapsedTime(&ms, g_kt[i].a, g_kt[i].b) != cudaSuccess) return -1.0;
+            return (double)ms;
+        }
+    return -1.0;
 }
 
 extern "C" void bfe_count_launch(int n) { g_launches.fetch_add((uint64_t)n); }

@@ -97,6 +97,11 @@ int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream);     // build G4 from g_c
 int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream);       // build A3 from a_con if stale
 extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0
 
+// Optional per-kernel CUDA-event timing (option "time_kernels"): bench.py's roofline object reads the live
+// duration of every kernel of the step with bfe_kernel_time_ms().  Off by default (no events recorded).
+int bfe_kt_begin(const char* name, cudaStream_t stream);     // returns a slot or -1 when disabled
+void bfe_kt_end(int slot, cudaStream_t stream);
+
 #define BFE_CUDA(call)                                                  \
     do {                                                                \
         cudaError_t _e = (call);                                        \

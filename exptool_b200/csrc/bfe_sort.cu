@@ -557,14 +557,18 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
         if (ss > 200 * 1024) return BFE_ERR_UNSUPPORTED;
         if (ss > 48 * 1024)
             BFE_CUDA(cudaFuncSetAttribute(eof_cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+        const int kt = bfe_kt_begin("eof_cell_hist_kernel", stream);
         eof_cell_hist_kernel<<<grid, 1024, ss, stream>>>(h->g, ncell, n, x, y, z, ws.hist, ws.cell_start, ws.cursor,
                                                         h->counter);
+        bfe_kt_end(kt, stream);
     }
     BFE_LAUNCH_CHECK("eof_cell_hist_kernel");
     int g2 = (int)((n + 511) / 512);
     if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
     if (g2 < 1) g2 = 1;
+    const int kt2 = bfe_kt_begin("eof_cell_scatter_kernel", stream);
     eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cursor, ws.rec, ws.inv, ws.r_orig);
+    bfe_kt_end(kt2, stream);
     BFE_LAUNCH_CHECK("eof_cell_scatter_kernel");
     h->prepared_n = n;
     h->prepared_has_mass = (mass || n == 0) ? 1 : 0;
@@ -590,8 +594,10 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
             BFE_CUDA(cudaFuncSetAttribute(eof_deposit_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
         }
+        const int kt = bfe_kt_begin("eof_deposit_kernel", stream);
         eof_deposit_kernel<6, 8><<<grid, 256, smem, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, n, ws.rec, h->partial,
                                                              h->counter, cos_out, sin_out);
+        bfe_kt_end(kt, stream);
     }
     BFE_LAUNCH_CHECK("eof_deposit_kernel");
     return BFE_OK;
@@ -611,11 +617,15 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
     if (rc != BFE_OK) return rc;
     int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
+    const int kt = bfe_kt_begin("eof_force_sorted_kernel", stream);
     eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
+    bfe_kt_end(kt, stream);
     BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
     int64_t need2 = (n + 255) / 256, cap2 = (int64_t)h->num_sms * 8;
+    const int kt3 = bfe_kt_begin("eof_force_gather_kernel", stream);
     eof_force_gather_kernel<<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, stream>>>(n, ws.inv, ws.r_orig, ws.tmp, p0, p,
                                                                                   fr, fp, fz, R);
+    bfe_kt_end(kt3, stream);
     BFE_LAUNCH_CHECK("eof_force_gather_kernel");
     return BFE_OK;
 }

@@ -54,6 +54,11 @@ def set_option(name, value):
     _lib.check(_lib.load().bfe_set_option(name.encode(), int(value)))
 
 
+def kernel_time_ms(name):
+    """Duration of the latest launch of kernel `name` recorded while option 'time_kernels' was on (ms; < 0: none)."""
+    return float(_lib.load().bfe_kernel_time_ms(name.encode()))
+
+
 def launch_count():
     return int(_lib.load().bfe_launch_count())
 

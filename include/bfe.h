@@ -62,6 +62,11 @@ uint64_t bfe_launch_count(void);
  * 1 = direct, 2 = sorted. */
 int bfe_set_option(const char* name, int value);
 
+/* With option "time_kernels" = 1 the EOF step kernels are bracketed by CUDA events on their stream;
+ * bfe_kernel_time_ms(name) synchronises on and returns the duration (ms) of the latest launch of that kernel
+ * (e.g. "eof_deposit_kernel"), or a negative value if none was recorded. */
+double bfe_kernel_time_ms(const char* name);
+
 /* ---------------------------------------------------------------- EOF (disc) ---------------- */
 
 /* Tables in the reference layout [m][n][ix][iy] (eof.parse_eof, eof.py:224-313), each
