@@ -309,8 +309,9 @@ def run_gpu(args):
     t_con, t_force = time_kernel(k_con, reps), time_kernel(k_force, reps)
     # live duration of every kernel of the step: CUDA events recorded inside the library around each launch
     # (bfe_set_option "time_kernels"), averaged over whole steps on rotating particle sets
-    KNAMES = ['eof_cell_hist_kernel', 'eof_cell_scatter_kernel', 'eof_deposit_kernel', 'eof_contract_kernel',
-              'eof_force_sorted_kernel', 'eof_force_gather_kernel']
+    KNAMES = ['eof_cell_hist_kernel', 'eof_cell_scatter_kernel', 'eof_segsum_kernel', 'eof_node_contract_kernel',
+              'eof_contract_kernel',
+              'eof_force_sorted_kernel', 'eof_force_sorted_mma_kernel', 'eof_force_gather_kernel']
     ops.set_option('time_kernels', 1)
     ksum = {k: 0.0 for k in KNAMES}
     for k in range(reps):
@@ -318,15 +319,17 @@ def run_gpu(args):
         for nme in KNAMES:
             ksum[nme] += ops.kernel_time_ms(nme)
     ops.set_option('time_kernels', 0)
-    kms = {k: v / reps for k, v in ksum.items()}
+    kms = {k: v / reps for k, v in ksum.items() if v > 0.0}      # kernels that did not run report -1
     if sampler:
         sampler.stop()
     peak, peak_src = measured_peaks()
     # algorithmic HBM bytes per particle of the pass a kernel belongs to:
     # accumulate 32 B (x,y,z,m), force 72 B (x,y,z + six outputs); the contraction reads the six tables once.
     alg = {'eof_cell_hist_kernel': BYTES_ACC * N_PART, 'eof_cell_scatter_kernel': BYTES_ACC * N_PART,
-           'eof_deposit_kernel': BYTES_ACC * N_PART, 'eof_contract_kernel': 6 * 7 * 18 * 129 * 65 * 8,
-           'eof_force_sorted_kernel': BYTES_FORCE * N_PART, 'eof_force_gather_kernel': BYTES_FORCE * N_PART}
+           'eof_segsum_kernel': BYTES_ACC * N_PART, 'eof_node_contract_kernel': 129 * 65 * 256 * 8,
+           'eof_contract_kernel': 6 * 7 * 18 * 129 * 65 * 8,
+           'eof_force_sorted_kernel': BYTES_FORCE * N_PART, 'eof_force_sorted_mma_kernel': BYTES_FORCE * N_PART,
+           'eof_force_gather_kernel': BYTES_FORCE * N_PART}
     dom = max(kms, key=lambda k: kms[k])
     achieved = alg[dom] / (kms[dom] * 1e-3) / 1e9
     traffic = None
@@ -335,15 +338,16 @@ def run_gpu(args):
         with open(tpath) as f:
             traffic = json.load(f).get(dom)
     step_alg = (BYTES_ACC + BYTES_FORCE) * N_PART            # 104 B / particle for the whole step
-    t_accpass = kms['eof_cell_hist_kernel'] + kms['eof_cell_scatter_kernel'] + kms['eof_deposit_kernel']
-    t_forcepass = kms['eof_force_sorted_kernel'] + kms['eof_force_gather_kernel']
+    t_accpass = (kms['eof_cell_hist_kernel'] + kms['eof_cell_scatter_kernel'] + kms['eof_segsum_kernel'] +
+                 kms['eof_node_contract_kernel'])
+    t_forcepass = sum(v for k, v in kms.items() if k.startswith('eof_force_'))
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg[dom],
                 'kernel_ms': kms,
                 'api_call_ms': {'bfe_eof_prepare': t_prep, 'bfe_eof_accumulate_prepared': t_acc,
                                 'bfe_eof_contract': t_con, 'bfe_eof_force_prepared': t_force},
-                'passes': {'accumulate (hist+scatter+deposit)': {'ms': t_accpass, 'algorithmic_bytes': BYTES_ACC * N_PART,
+                'passes': {'accumulate (hist+scatter+segsum+node_contract)': {'ms': t_accpass, 'algorithmic_bytes': BYTES_ACC * N_PART,
                                                                 'achieved': BYTES_ACC * N_PART / (t_accpass * 1e-3) / 1e9,
                                                                 'frac': BYTES_ACC * N_PART / (t_accpass * 1e-3) / 1e9 / peak},
                            'force (force_sorted+gather)': {'ms': t_forcepass, 'algorithmic_bytes': BYTES_FORCE * N_PART,

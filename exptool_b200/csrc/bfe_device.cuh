@@ -98,6 +98,46 @@ __device__ __forceinline__ EofBin bfe_eof_bin(const EofGeom& g, double r, double
     return b;
 }
 
+// Cell id only (no weights), for the histogram pass of the cell sort: the index arithmetic is done in FP32 and
+// accepted only when the result is provably the FP64 one -- X and Y further than a rigorous error bound from
+// every integer (cell edge) and finite.  Otherwise (about 1 particle in 10^3, plus NaN / overflow / denormal
+// inputs) the caller recomputes with bfe_eof_bin.  Error budget of the FP32 chain: inputs 6e-8 relative,
+// sqrt / divide / log <= 2 ulp each, so |xi_f - xi| <= 2e-7 max(1,|xi|) and likewise for y; the bound below
+// carries a factor 4 on top and the FP32 rounding of the final scale-and-shift.
+__device__ __forceinline__ bool bfe_eof_cell_fast(const EofGeom& g, double px, double py, double pz, int& cell) {
+    const float xf = (float)px, yf = (float)py, zf = (float)pz;
+    const float r = sqrtf(fmaf(xf, xf, fmaf(yf, yf, 1.e-10f)));
+    float xi;
+    if (g.cmap == 1) {
+        const float q = r / (float)g.ascale;
+        xi = (q - 1.0f) / (q + 1.0f);
+    } else if (g.cmap == 2) {
+        xi = logf(r);
+    } else {
+        xi = r;
+    }
+    const float az = fabsf(zf);
+    const float u = az / fabsf((float)g.hscale);
+    const float ash = logf(u + sqrtf(fmaf(u, u, 1.0f)));
+    const float yy = (zf / (az + 1.0e-8f)) * ash;
+    const float idx = (float)g.inv_dx, idy = (float)g.inv_dy;
+    const float X = (xi - (float)g.xmin) * idx;
+    const float Y = (yy - (float)g.ymin) * idy;
+    const float tolx = 8.0e-7f * fabsf(idx) * fmaxf(1.0f, fmaxf(fabsf(xi), fabsf((float)g.xmin))) + 4.0e-7f * fabsf(X) + 1.0e-6f;
+    const float toly = 8.0e-7f * fabsf(idy) * fmaxf(1.0f, fmaxf(fabsf(yy), fabsf((float)g.ymin))) + 4.0e-7f * fabsf(Y) + 1.0e-6f;
+    // finite, inside float's comfortable range, and away from every cell edge by more than the bound
+    bool ok = (fabsf(X) < 1.0e9f) && (fabsf(Y) < 1.0e9f) && (r > 1.0e-30f) && (r < 1.0e18f) && (az < 1.0e18f);
+    int ix, iy;
+    if (X < -tolx) ix = 0;
+    else if (X > (float)g.numx + tolx) ix = g.numx - 1;
+    else { ix = (int)X; ok = ok && (fabsf(X - rintf(X)) > tolx); if (ix >= g.numx) ix = g.numx - 1; if (ix < 0) ix = 0; }
+    if (Y < -toly) iy = 0;
+    else if (Y > (float)g.numy + toly) iy = g.numy - 1;
+    else { iy = (int)Y; ok = ok && (fabsf(Y - rintf(Y)) > toly); if (iy >= g.numy) iy = g.numy - 1; if (iy < 0) iy = 0; }
+    cell = ix * g.numy + iy;
+    return ok;      // NaN anywhere makes a comparison above false -> not ok
+}
+
 // cos(phi), sin(phi) of phi = atan2(y, x) without the atan2 (eof.py:532, spheresl.py:613).
 __device__ __forceinline__ void bfe_cossin_phi(double x, double y, double& c, double& s) {
     double h2 = x * x + y * y;

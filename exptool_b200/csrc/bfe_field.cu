@@ -214,6 +214,7 @@ int g_bfe_eof_force_mode = 0;
 int g_bfe_sort_min_particles = 32768;
 int g_bfe_sl_accumulate_mode = 0;
 int g_bfe_staged_eval = 1;
+int g_bfe_force_mma = 1;
 static int g_bfe_time_kernels = 0;
 
 extern "C" int bfe_set_option(const char* name, int value) {
@@ -222,6 +223,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "eof_force_mode")) { g_bfe_eof_force_mode = value; return BFE_OK; }
     if (!strcmp(name, "time_kernels")) { g_bfe_time_kernels = value; return BFE_OK; }
     if (!strcmp(name, "staged_eval")) { g_bfe_staged_eval = value; return BFE_OK; }
+    if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
     if (!strcmp(name, "sl_accumulate_mode")) { g_bfe_sl_accumulate_mode = value; return BFE_OK; }
     if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
     return BFE_ERR_ARG;

@@ -95,6 +95,7 @@ int bfe_eof_force_sorted(bfe_eof* h, int64_t n, const double* x, const double* y
 void bfe_set_cuda_error(cudaError_t e, const char* where);
 int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream);     // build G4 from g_con if stale
 int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream);       // build A3 from a_con if stale
+extern int g_bfe_force_mma;                                 // option "force_mma": sorted force eval on DMMA (1, default) / per lane (0)
 extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0
 
 // Optional per-kernel CUDA-event timing (option "time_kernels"): bench.py's roofline object reads the live

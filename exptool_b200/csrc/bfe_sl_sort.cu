@@ -100,17 +100,15 @@ sl_bin_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __r
             pr[u] = bfe_sl_prep(g, xi, p0tab, px, py, pz, pm);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) pos[u] = (idx[u] < n) ? atomicAdd(&cursor[pr[u].i], 1) : 0;   // integer slot claim
+        for (int u = 0; u < U; ++u) pos[u] = (idx[u] < n) ? atomicAdd(&cursor[(size_t)pr[u].i * BFE_CURSOR_STRIDE], 1) : 0;   // integer slot claim
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (idx[u] < n) {
                 unsigned long long bp = ((unsigned long long)(unsigned int)pr[u].i << 32) |
                                         (unsigned long long)(unsigned int)idx[u];
-                double2* dst = reinterpret_cast<double2*>(rec + pos[u]);
-                dst[0] = make_double2(pr[u].x1, pr[u].x2);
-                dst[1] = make_double2(pr[u].W, pr[u].costh);
-                dst[2] = make_double2(pr[u].c1, pr[u].s1);
-                dst[3] = make_double2(0.0, __longlong_as_double((long long)bp));
+                char* dst = reinterpret_cast<char*>(rec + pos[u]);       // two full-sector stores per record
+                bfe_st256(dst, pr[u].x1, pr[u].x2, pr[u].W, pr[u].costh);
+                bfe_st256(dst + 32, pr[u].c1, pr[u].s1, 0.0, __longlong_as_double((long long)bp));
             }
         }
     }
@@ -409,7 +407,7 @@ static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
     size_t o_hist = 0;
     size_t o_start = sl_align_up(o_hist + sizeof(int) * nbin, 256);
     size_t o_cur = sl_align_up(o_start + sizeof(int) * (nbin + 1), 256);
-    size_t o_rec = sl_align_up(o_cur + sizeof(int) * nbin, 256);
+    size_t o_rec = sl_align_up(o_cur + sizeof(int) * nbin * BFE_CURSOR_STRIDE, 256);
     if (n > h->sort_cap || !h->sort_ws) {
         if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
         int64_t cap = n + n / 8 + 1024;

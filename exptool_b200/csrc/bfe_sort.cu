@@ -8,17 +8,18 @@
 //   S_k,ch = sum_{p in cell} c_k(p) m_p trig_ch(p)                     (52 sums per cell)
 //
 // ("deposit then contract").  Particles are counting-sorted by cell
-// (integer keys, integer cursors), the 52 sums are formed per run of equal cells with
-// per-thread register accumulators and a shared-memory combine, and the table rows are
-// read once per RUN instead of once per particle.  No floating-point atomics anywhere;
-// the coefficient partials are combined exactly as in the direct kernel.
+// (integer keys, integer cursors), the 52 sums are formed per run of equal cells on the
+// FP64 tensor cores, and the table rows are read once per CELL instead of once per
+// particle.  No floating-point atomics anywhere.
 //
 //   eof_cell_hist_kernel     : per-particle cell id -> histogram (shared-memory int counters);
 //                              the last CTA to finish scans it (cell_start, cursors)
 //   eof_cell_scatter_kernel  : 64-byte record {c00,c10,c01,c11,cos phi,sin phi,m|R,cell:perm}
 //                              written at its sorted position
-//   eof_deposit_kernel       : runs -> S -> coefficient partials -> last-CTA reduce
-//   eof_force_sorted_kernel  : field evaluation in sorted order (warp-uniform table rows),
+//   eof_segsum_kernel        : runs -> S (one 8x8 FP64 tensor-core tile per run segment, stored to global)
+//   eof_node_contract_kernel : S, table rows -> coefficient partials -> last-CTA reduce
+//   eof_force_sorted_mma_kernel : field evaluation in sorted order on the FP64 tensor cores
+//   eof_force_sorted_kernel  : the same per lane (warp-uniform table rows; option force_mma = 0),
 //                              outputs scattered back to the caller's particle order
 #include "bfe_device.cuh"
 #include "bfe_sortcore.cuh"
@@ -49,11 +50,26 @@ eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__
     __shared__ bool s_last;
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
-        double r = sqrt(px * px + py * py + 1.e-10);
-        EofBin b = bfe_eof_bin(g, r, pz);
-        atomicAdd(&s_hist[bfe_cell_of(g, b)], 1);
+    // two particles per thread per pass: six independent loads in flight
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+        const int64_t i2 = i + stride;
+        const bool two = i2 < n;
+        const double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        const double qx = two ? __ldg(x + i2) : 1.0, qy = two ? __ldg(y + i2) : 0.0, qz = two ? __ldg(z + i2) : 0.0;
+        int cell, cell2;
+        if (!bfe_eof_cell_fast(g, px, py, pz, cell)) {            // near a cell edge / unusual input: exact FP64 index
+            double r = sqrt(px * px + py * py + 1.e-10);
+            cell = bfe_eof_bin(g, r, pz).cell;
+        }
+        atomicAdd(&s_hist[cell], 1);
+        if (two) {
+            if (!bfe_eof_cell_fast(g, qx, qy, qz, cell2)) {
+                double r = sqrt(qx * qx + qy * qy + 1.e-10);
+                cell2 = bfe_eof_bin(g, r, qz).cell;
+            }
+            atomicAdd(&s_hist[cell2], 1);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
@@ -79,140 +95,93 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
                         const double* __restrict__ z, const double* __restrict__ mass,
                         int* __restrict__ cursor, EofRec* __restrict__ rec, int* __restrict__ inv,
                         double* __restrict__ r_orig) {
-    constexpr int U = 2;       // particles per thread per pass: independent slot claims overlap their latency
+    // Two particles per thread per pass.  Order of work per pass: (1) all eight loads, (2) the cell id by the FP32
+    // fast path (exact by construction, FP64 fallback near edges), (3) the integer slot claims, (4) the FP64 bin
+    // fractions, weights and cos/sin phi WHILE the claims are in flight (they were 1/3 of this kernel's stall
+    // samples when issued after the FP64 arithmetic, ncu profiles/), (5) the record stores.
+    constexpr int U = 2;
     for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
-        EofBin b[U];
-        double c1[U], s1[U], r[U], aux[U];
-        int cell[U], pos[U];
+        double px[U], py[U], pz[U], aux[U];
         int64_t idx[U];
+        int cell[U], pos[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             idx[u] = base + u * 256 + threadIdx.x;
             const bool on = idx[u] < n;
-            double px = on ? __ldg(x + idx[u]) : 1.0, py = on ? __ldg(y + idx[u]) : 0.0, pz = on ? __ldg(z + idx[u]) : 0.0;
+            px[u] = on ? __ldg(x + idx[u]) : 1.0; py[u] = on ? __ldg(y + idx[u]) : 0.0; pz[u] = on ? __ldg(z + idx[u]) : 0.0;
             aux[u] = (on && mass) ? __ldg(mass + idx[u]) : 0.0;
-            r[u] = sqrt(px * px + py * py + 1.e-10);              // eof.py:531 / 1070
-            b[u] = bfe_eof_bin(g, r[u], pz);
-            cell[u] = bfe_cell_of(g, b[u]);
-            bfe_cossin_phi(px, py, c1[u], s1[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!bfe_eof_cell_fast(g, px[u], py[u], pz[u], cell[u])) {
+                const double r = sqrt(px[u] * px[u] + py[u] * py[u] + 1.e-10);
+                cell[u] = bfe_eof_bin(g, r, pz[u]).cell;
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            pos[u] = (idx[u] < n) ? atomicAdd(&cursor[cell[u]], 1) : 0;   // integer slot claim, not a data reduction
+            pos[u] = (idx[u] < n) ? atomicAdd(&cursor[(size_t)cell[u] * BFE_CURSOR_STRIDE], 1) : 0;   // integer slot claim, not a data reduction
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            const double r = sqrt(px[u] * px[u] + py[u] * py[u] + 1.e-10);   // eof.py:531 / 1070
+            const EofBin b = bfe_eof_bin(g, r, pz[u]);                        // b.cell == cell[u]
+            double c1, s1;
+            bfe_cossin_phi(px[u], py[u], c1, s1);
             if (idx[u] < n) {
                 unsigned long long cp = ((unsigned long long)(unsigned int)cell[u] << 32) |
                                         (unsigned long long)(unsigned int)idx[u];
-                double2* dst = reinterpret_cast<double2*>(rec + pos[u]);
-                dst[0] = make_double2(b[u].c00, b[u].c10);
-                dst[1] = make_double2(b[u].c01, b[u].c11);
-                dst[2] = make_double2(c1[u], s1[u]);
-                dst[3] = make_double2(aux[u], __longlong_as_double((long long)cp));
+                char* dst = reinterpret_cast<char*>(rec + pos[u]);       // two full-sector stores per record
+                bfe_st256(dst, b.c00, b.c10, b.c01, b.c11);
+                bfe_st256(dst + 32, c1, s1, aux[u], __longlong_as_double((long long)cp));
                 inv[idx[u]] = pos[u];             // original index -> sorted slot (coalesced)
-                r_orig[idx[u]] = r[u];
+                r_orig[idx[u]] = r;
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// deposit + contract over sorted records.
+// deposit + contract over sorted records, in two kernels.
 //
-// A WARP owns a task of TASK consecutive sorted records and walks it 32 records at a time:
-//   1. lanes = records: the 64-B record (prefetched one batch ahead) is expanded to 4 mass-weighted
-//      corner weights and 2 mmax+1 cos/sin(m phi) values in the warp's shared-memory slab;
-//   2. the per-run sums  S[k][ch] = sum_p w_k(p) trig_ch(p)  are a (4 x L)(L x ntrig) product:
-//      done on the FP64 tensor cores with mma.sync.m8n8k4 (A = W^T, rows 4..7 zero; B = trig,
-//      two n-tiles of 8 channels; 4 records per k-step).  The direct LDS+DFMA form needs 8
-//      shared-memory wavefronts per record and was bound on shared-memory bandwidth (ncu:
-//      profiles/); the fragment loads need ~1.3.  Records outside the current run are masked to
-//      zero in the A fragment, so a run boundary costs at most one extra k-step;
-//   3. when the cell id changes (warp-uniform) the finished run is flushed: every lane adds
-//      sum_k T[node_k][j] S[k][ch(j)] to the register accumulators of its channels j = lane + 32 c.
-// Batches that are mostly single-record runs (sparse outskirts) are deferred and done at the end
-// by the whole CTA in the direct formulation (thread per channel), which keeps all 8 warps' load
-// pipelines busy instead of serialising ~30 dependent flushes in one warp.
+// eof_segsum_kernel -- a WARP owns a task of 128 consecutive sorted records (dynamic task queue) and walks it
+// 32 records at a time:
+//   1. lanes = records: the 64-B record (prefetched one batch ahead) is expanded in the warp's shared-memory
+//      slab to 8 A rows (the 4 mass-weighted corner weights w_k, and w_k cos 4phi) and 7 B rows
+//      (cos/sin phi, 2phi, 3phi and sin 4phi; the eighth column is the constant 1);
+//   2. the per-run sums are a (8 x L)(L x 8) product done on the FP64 tensor cores, ONE mma.sync.m8n8k4 per
+//      4 records: D[k][.] = sum_p w_k {1, c1, s1, c2, s2, c3, s3, s4} and D[4+k][.] = the same with w_k c4,
+//      from which the harmonics 4..6 follow by the product formulas (cos 4x cos x = (cos 5x + cos 3x)/2, ...):
+//      all 64 outputs of the tile carry information, 52 sums come out of it.  Records outside the current run
+//      are masked to zero in the A fragment, so a run boundary costs at most one extra k-step;
+//   3. when the cell id changes (warp-uniform) the tile is stored (512 B, coalesced) to the segment slot
+//      cell + task -- unique and monotone along the sorted array -- and the accumulators are cleared.
+// eof_node_contract_kernel -- thread per (m,n,trig) channel j: for every non-empty cell the segment tiles of
+// the cell are summed, the 52 sums S[k][ch] derived, and  acc_j += sum_k T[node_k][j] S[k][ch(j)]  with the four
+// node rows read coalesced; per-CTA partials, last-CTA reduce (4 row groups x 16 rows in flight).
+// The first version of this pass (one kernel: runs flushed into 234 register accumulators by the summing
+// warp, table rows by TMA) was bound by the flushes of short runs: slowest warp 90 k cycles against a median
+// of 48 k, plus a 14 us serial epilogue (per-warp cycle counters, profiles/r01_summary.md section 11).
+// No floating-point atomics anywhere.
 // ---------------------------------------------------------------------------
-// Optional per-warp cycle counters (build with BFE_NVCC_FLAGS=-DBFE_PROFILE_DEPOSIT; profiles/deposit_cycles.py)
-#ifdef BFE_PROFILE_DEPOSIT
-__device__ long long* g_dbg = nullptr;
-extern "C" int bfe_debug_set(long long* p) { return (int)cudaMemcpyToSymbol(g_dbg, &p, sizeof(p)); }
-#define DBG_DECL long long dbg_t0 = clock64(), dbg_tk = 0, dbg_flush = 0, dbg_mma = 0, dbg_expand = 0, dbg_nflush = 0, dbg_nks = 0, dbg_wait = 0
-#define DBG_TICK() (dbg_tk = clock64())
-#define DBG_ADD(var) do { long long t_ = clock64(); var += t_ - dbg_tk; dbg_tk = t_; } while (0)
-#else
-#define DBG_DECL
-#define DBG_TICK()
-#define DBG_ADD(var)
-#endif
-
-struct DepositSmem {
+struct SegSum {
+    static constexpr int TASK = 128;              // records per warp task
     static constexpr int NW = 8;                  // warps per CTA
     static constexpr int RS = 36;                 // slab row stride (doubles): conflict-free fragment loads
-    static constexpr int TROW = 256;              // max padded channels per node row
-    static constexpr int MAXDEFER = 160;
+    static constexpr int NROW = 15;               // 8 A rows + 7 B rows
 };
 
-template <int MCAP, int KCH>
-__global__ void __launch_bounds__(256, 2)
-eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch_pad, int64_t n,
-                   const EofRec* __restrict__ rec, double* __restrict__ partial, unsigned int* __restrict__ counter,
-                   double* __restrict__ cos_out, double* __restrict__ sin_out) {
-    constexpr int TASK = 128;
-    constexpr int SPARSE_RUNS = 20;               // batches with more run starts than this are deferred
-    constexpr int NTRIG = 2 * MCAP + 1;
-    constexpr int NV = 4 + NTRIG;                 // values per record in the slab
-    constexpr int NW = DepositSmem::NW, RS = DepositSmem::RS, TROW = DepositSmem::TROW;
-    constexpr int MAXDEFER = DepositSmem::MAXDEFER;
-    constexpr int SLAB = NV * RS;
-    static_assert(SLAB >= KCH * 32, "slab reused for the CTA reduce");
-    static_assert(NTRIG <= 16, "two n-tiles of 8 channels");
-    // dynamic shared memory carve-up (about 107 kB; two CTAs per SM)
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    double* s_tbuf = reinterpret_cast<double*>(s_raw);                    // [NW][4][TROW] table rows of the open run
-    double* s_slab = s_tbuf + NW * 4 * TROW;                              // [NW][SLAB]
-    double* s_S = s_slab + NW * SLAB;                                     // [NW][64]
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_S + NW * 64);   // [NW] mbarriers
-    int* s_defer = reinterpret_cast<int*>(s_bar + NW);                    // [MAXDEFER]
-    int* s_dcell = s_defer + MAXDEFER;                                    // [32]
-    __shared__ int s_ndefer;
-    __shared__ bool s_last;
-
+__global__ void __launch_bounds__(256, 4)
+eof_segsum_kernel(int64_t n, const EofRec* __restrict__ rec, double* __restrict__ seg,
+                  unsigned int* __restrict__ counter) {
+    constexpr int TASK = SegSum::TASK, NW = SegSum::NW, RS = SegSum::RS, SLAB = SegSum::NROW * SegSum::RS;
+    __shared__ double s_slab[NW * SLAB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntrig = 2 * g.mmax + 1;
-    const int ncos = (g.mmax + 1) * g.norder;
     const int fg = lane >> 2, fj = lane & 3;      // mma fragment coordinates: group, thread-in-group
-    const bool a_on = fg < 4;                     // A rows 4..7 are zero
-    const bool b1_on = (8 + fg) < ntrig;          // second n-tile holds channels 8..ntrig-1
-    // channels owned by this lane: j = lane + 32 c
-    int trig_idx[KCH];
-#pragma unroll
-    for (int c = 0; c < KCH; ++c) {
-        int j = lane + 32 * c;
-        trig_idx[c] = (j < nch) ? ((j < ncos) ? j / g.norder : g.mmax + 1 + (j - ncos) / g.norder) : 0;
-    }
-    double acc[KCH];
-#pragma unroll
-    for (int c = 0; c < KCH; ++c) acc[c] = 0.0;
-    const int rowstep = nch_pad, colstep = g.ny1 * nch_pad;
-    const unsigned int rowbytes = 2u * (unsigned int)nch_pad * 8u;        // nodes (ix,iy),(ix,iy+1) are contiguous
-
-    double* val = s_slab + warp * SLAB;           // val[v * RS + p]
-    double* S = s_S + warp * 64;
-    double* tb = s_tbuf + warp * 4 * TROW;        // [T00 | T01] [T10 | T11], each nch_pad wide
-    const unsigned int bar = bfe_smem_u32(s_bar + warp);
-    const unsigned int tb_u32 = bfe_smem_u32(tb);
-    unsigned int bar_parity = 0;
-    if (tid == 0) s_ndefer = 0;
-    if (lane == 0) bfe_mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    // warps pull tasks from a global counter (counter[1]); the last CTA resets it
+    double* val = s_slab + warp * SLAB;           // val[row * RS + record]
+    const double* arow = val + fg * RS;           // A[row fg][.]
+    const double* brow = val + (7 + fg) * RS;     // B[.][col fg] (col 0 is the constant 1)
     unsigned int* task_counter = counter + 1;
     const int64_t ntasks = (n + TASK - 1) / TASK;
-    DBG_DECL;
     for (;;) {
         int64_t task = 0;
         if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
@@ -220,119 +189,53 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
         if (task >= ntasks) break;
         const int64_t t0 = task * TASK;
         const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
-        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;   // C fragments: tile 0 (ch 0..7), tile 1 (ch 8..15)
-        int cur = -1;                               // cell of the run being summed (-1: none)
+        double d0 = 0.0, d1 = 0.0;                // D[fg][2 fj], D[fg][2 fj + 1]
+        int cur = -1;                             // cell of the run being summed (-1: none)
         double2 ra, rb, rc, rd;
         {
             const bool on = lane < ((tcnt < 32) ? tcnt : 32);
-            const double2* src = reinterpret_cast<const double2*>(rec + t0 + (on ? lane : 0));
-            ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+            const char* src = reinterpret_cast<const char*>(rec + t0 + (on ? lane : 0));
+            bfe_ld256_nc(src, ra.x, ra.y, rb.x, rb.y); bfe_ld256_nc(src + 32, rc.x, rc.y, rd.x, rd.y);
         }
         for (int b0 = 0; b0 < tcnt; b0 += 32) {
             const int bcnt = (tcnt - b0) < 32 ? (tcnt - b0) : 32;
             __syncwarp();
-            DBG_TICK();
             int mycell = -3;
             {
-                // lanes >= bcnt park zeros so that k-steps may read the whole 32-record slab
+                // lanes >= bcnt park zero weights so that k-steps may read the whole 32-record slab
                 const bool on = lane < bcnt;
                 const double m = on ? rd.x : 0.0;
-#ifdef BFE_PROFILE_DEPOSIT
-                if (__double_as_longlong(m) == 0x7ff8dead00000000ll) dbg_wait = 1;   // force the load to complete
-                DBG_ADD(dbg_wait);
-#endif
-                val[0 * RS + lane] = ra.x * m; val[1 * RS + lane] = ra.y * m;
-                val[2 * RS + lane] = rb.x * m; val[3 * RS + lane] = rb.y * m;
+                const double c1 = rc.x, s1 = rc.y;
+                const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * c1 * s1;
+                const double c3 = c2 * c1 - s2 * s1, s3 = s2 * c1 + c2 * s1;
+                const double c4 = c2 * c2 - s2 * s2, s4 = 2.0 * c2 * s2;
+                const double w0 = ra.x * m, w1 = ra.y * m, w2 = rb.x * m, w3 = rb.y * m;
+                val[0 * RS + lane] = w0; val[1 * RS + lane] = w1; val[2 * RS + lane] = w2; val[3 * RS + lane] = w3;
+                val[4 * RS + lane] = w0 * c4; val[5 * RS + lane] = w1 * c4;
+                val[6 * RS + lane] = w2 * c4; val[7 * RS + lane] = w3 * c4;
+                val[8 * RS + lane] = c1; val[9 * RS + lane] = s1; val[10 * RS + lane] = c2; val[11 * RS + lane] = s2;
+                val[12 * RS + lane] = c3; val[13 * RS + lane] = s3; val[14 * RS + lane] = s4;
                 if (on) mycell = (int)((unsigned long long)__double_as_longlong(rd.y) >> 32);
-                double cm = 1.0, sm = 0.0;
-                val[4 * RS + lane] = 1.0;
-#pragma unroll
-                for (int mm = 1; mm <= MCAP; ++mm) {
-                    if (mm <= g.mmax) {
-                        double cn = cm * rc.x - sm * rc.y, sn = sm * rc.x + cm * rc.y;
-                        cm = cn; sm = sn;
-                        val[(4 + mm) * RS + lane] = cm;
-                        val[(4 + g.mmax + mm) * RS + lane] = sm;
-                    }
-                }
             }
             if (b0 + 32 < tcnt) {
                 const bool on = (b0 + 32 + lane) < tcnt;
-                const double2* src = reinterpret_cast<const double2*>(rec + t0 + b0 + 32 + (on ? lane : 0));
-                ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+                const char* src = reinterpret_cast<const char*>(rec + t0 + b0 + 32 + (on ? lane : 0));
+                bfe_ld256_nc(src, ra.x, ra.y, rb.x, rb.y); bfe_ld256_nc(src + 32, rc.x, rc.y, rd.x, rd.y);
             }
             // run boundaries inside this batch (bit p set: record p starts a new run)
             int prevcell = __shfl_up_sync(0xffffffffu, mycell, 1);
             if (lane == 0) prevcell = cur;
-            unsigned int bmask = __ballot_sync(0xffffffffu, (lane < bcnt) && (mycell != prevcell));
+            const unsigned int bmask = __ballot_sync(0xffffffffu, (lane < bcnt) && (mycell != prevcell));
             __syncwarp();
-            DBG_ADD(dbg_expand);
-
-            // open a run: one lane issues two TMA bulk copies that bring the run's four table rows into the
-            // warp's buffer while the tensor cores sum the run; the flush then reads them from shared memory
-#define BFE_OPEN_RUN(cellv)                                                                               \
-            do {                                                                                          \
-                cur = (cellv);                                                                            \
-                if (lane == 0) {                                                                          \
-                    const int ox_ = cur / g.numy, oy_ = cur - ox_ * g.numy;                               \
-                    const double* src_ = t_acc + (size_t)(ox_ * g.ny1 + oy_) * nch_pad;                   \
-                    bfe_mbar_expect_tx(bar, 2u * rowbytes);                                               \
-                    bfe_bulk_g2s(tb_u32, src_, rowbytes, bar);                                            \
-                    bfe_bulk_g2s(tb_u32 + 2u * TROW * 8u, src_ + colstep, rowbytes, bar);                 \
-                }                                                                                         \
-            } while (0)
-
-#define BFE_FLUSH_RUN()                                                                                   \
-            do {                                                                                          \
-                __syncwarp();                                                                             \
-                if (a_on) {                                                                               \
-                    S[fg * 16 + 2 * fj] = c00; S[fg * 16 + 2 * fj + 1] = c01;                             \
-                    S[fg * 16 + 8 + 2 * fj] = c10; S[fg * 16 + 8 + 2 * fj + 1] = c11;                     \
-                }                                                                                         \
-                bfe_mbar_wait(bar, bar_parity);                                                           \
-                bar_parity ^= 1u;                                                                         \
-                __syncwarp();                                                                             \
-                _Pragma("unroll")                                                                         \
-                for (int c = 0; c < KCH; ++c) {                                                           \
-                    const int j_ = lane + 32 * c;                                                         \
-                    if (j_ < nch) {                                                                       \
-                        const int ti_ = trig_idx[c];                                                      \
-                        acc[c] += tb[j_] * S[ti_] + tb[2 * TROW + j_] * S[16 + ti_] +                     \
-                                  tb[rowstep + j_] * S[32 + ti_] + tb[2 * TROW + rowstep + j_] * S[48 + ti_]; \
-                    }                                                                                     \
-                }                                                                                         \
-                __syncwarp();                                                                             \
-                c00 = 0.0; c01 = 0.0; c10 = 0.0; c11 = 0.0;                                               \
-            } while (0)
-
-            if (__popc(bmask) > SPARSE_RUNS) {
-                // ---- sparse batch: close the open run and hand the batch to the CTA-wide direct pass
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(&s_ndefer, 1);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot < MAXDEFER) {
-                    if (cur >= 0) { BFE_FLUSH_RUN(); cur = -1; }
-                    if (lane == 0) s_defer[slot] = (int)(t0 + b0);       // n < 2^31
-                    continue;
-                }
-                // queue full (pathological input): fall through and do it here, run by run
-            }
-
             int p = 0;
             while (p < bcnt) {
                 if ((bmask >> p) & 1u) {
-                    DBG_TICK();
                     if (cur >= 0) {
-                        BFE_FLUSH_RUN();
-#ifdef BFE_PROFILE_DEPOSIT
-                        dbg_nflush++;
-                        if (__double_as_longlong(acc[0]) == 0x7ff8dead00000000ll) dbg_wait = 1;
-#endif
+                        reinterpret_cast<double2*>(seg + ((size_t)cur + (size_t)task) * 64)[lane] = make_double2(d0, d1);
+                        d0 = 0.0; d1 = 0.0;
                     }
-                    BFE_OPEN_RUN(__shfl_sync(0xffffffffu, mycell, p));
-                    DBG_ADD(dbg_flush);
+                    cur = __shfl_sync(0xffffffffu, mycell, p);
                 }
-                DBG_TICK();
                 // end of this run within the batch: next boundary after p, or bcnt
                 const unsigned int later = (p < 31) ? (bmask >> (p + 1)) : 0u;
                 const int qend = later ? (p + __ffs(later)) : bcnt;
@@ -340,122 +243,166 @@ eof_deposit_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch
                 for (int ks = p >> 2; ks * 4 < qend; ++ks) {
                     const int r = ks * 4 + fj;
                     const bool in = (r >= p) && (r < qend);
-                    const double a = (a_on && in) ? val[fg * RS + r] : 0.0;
-                    const double bt0 = val[(4 + fg) * RS + r];
-                    const double bt1 = b1_on ? val[(12 + fg) * RS + r] : 0.0;
-                    bfe_dmma_m8n8k4(c00, c01, a, bt0);
-                    bfe_dmma_m8n8k4(c10, c11, a, bt1);
-#ifdef BFE_PROFILE_DEPOSIT
-                    dbg_nks++;
-#endif
+                    const double a = in ? arow[r] : 0.0;
+                    const double b = fg ? brow[r] : 1.0;
+                    bfe_dmma_m8n8k4(d0, d1, a, b);
                 }
-#ifdef BFE_PROFILE_DEPOSIT
-                if (__double_as_longlong(c00) == 0x7ff8dead00000000ll) dbg_wait = 1;
-#endif
-                DBG_ADD(dbg_mma);
                 p = qend;
             }
         }
-        if (cur >= 0) BFE_FLUSH_RUN();
-#undef BFE_FLUSH_RUN
-#undef BFE_OPEN_RUN
+        if (cur >= 0)
+            reinterpret_cast<double2*>(seg + ((size_t)cur + (size_t)task) * 64)[lane] = make_double2(d0, d1);
     }
-
-#ifdef BFE_PROFILE_DEPOSIT
-    long long dbg_main = clock64() - dbg_t0;
-#endif
-    // ---- deferred sparse batches: direct formulation, thread per channel, whole CTA
+    // the last CTA to finish re-arms the task queue
     __syncthreads();
-    double accd = 0.0;
-    {
-        const int nd = s_ndefer < MAXDEFER ? s_ndefer : MAXDEFER;
-        int my_ti = 0;
-        if (tid < nch) my_ti = (tid < ncos) ? tid / g.norder : g.mmax + 1 + (tid - ncos) / g.norder;
-        double* v0 = s_slab;
-        for (int d = 0; d < nd; ++d) {
-            const int64_t r0 = s_defer[d];
-            const int bcnt = (int)((n - r0) < 32 ? (n - r0) : 32);
-            const int64_t tend = (r0 / TASK + 1) * (int64_t)TASK;           // batches never cross a task
-            const int cnt = (int)((tend - r0) < bcnt ? (tend - r0) : bcnt);
-            __syncthreads();
-            if (tid < 32) {
-                const bool on = tid < cnt;
-                const double2* src = reinterpret_cast<const double2*>(rec + r0 + (on ? tid : 0));
-                double2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), dd = __ldg(src + 3);
-                const double m = on ? dd.x : 0.0;
-                v0[0 * RS + tid] = a.x * m; v0[1 * RS + tid] = a.y * m; v0[2 * RS + tid] = b.x * m; v0[3 * RS + tid] = b.y * m;
-                const int cell = (int)((unsigned long long)__double_as_longlong(dd.y) >> 32);
-                const int ix = cell / g.numy, iy = cell - ix * g.numy;
-                s_dcell[tid] = on ? (ix * g.ny1 + iy) : 0;
-                double cm = 1.0, sm = 0.0;
-                v0[4 * RS + tid] = 1.0;
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) { counter[0] = 0u; counter[1] = 0u; }
+    }
+}
+
+// one of the 52 sums S[k][ti] from a raw 8x8 tile R (row-major): ti = m for cos(m phi), mmax + m for sin(m phi)
+__device__ __forceinline__ double bfe_seg_derive(const double* __restrict__ R, int k, int ti, int mmax) {
+    const bool is_sin = ti > mmax;
+    const int m = is_sin ? (ti - mmax) : ti;
+    const double* lo = R + k * 8;                 // sum_p w_k {1, c1, s1, c2, s2, c3, s3, s4}
+    const double* hi = R + (4 + k) * 8;           // the same with w_k c4
+    if (!is_sin) {
+        switch (m) {
+            case 0: return lo[0];
+            case 1: return lo[1];
+            case 2: return lo[3];
+            case 3: return lo[5];
+            case 4: return hi[0];
+            case 5: return 2.0 * hi[1] - lo[5];
+            default: return 2.0 * hi[3] - lo[3];
+        }
+    }
+    switch (m) {
+        case 1: return lo[2];
+        case 2: return lo[4];
+        case 3: return lo[6];
+        case 4: return lo[7];
+        case 5: return 2.0 * hi[2] + lo[6];
+        default: return 2.0 * hi[4] + lo[4];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+eof_node_contract_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int nch_pad, int ncell,
+                         const int* __restrict__ cell_start, const double* __restrict__ seg,
+                         double* __restrict__ partial, unsigned int* __restrict__ counter,
+                         double* __restrict__ cos_out, double* __restrict__ sin_out) {
+    constexpr int CB = 8;                         // cells staged per pass
+    constexpr int TASK = SegSum::TASK;
+    __shared__ double s_raw[CB][64];
+    __shared__ double s_S[CB][4][16];
+    __shared__ int s_node[CB];
+    __shared__ double s_red[4][256];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int ncos = (g.mmax + 1) * g.norder;
+    const int ntrig = 2 * g.mmax + 1;
+    int my_ti = 0;
+    if (tid < nch) my_ti = (tid < ncos) ? tid / g.norder : g.mmax + 1 + (tid - ncos) / g.norder;
+    const int rowstep = nch_pad, colstep = g.ny1 * nch_pad;
+    double acc = 0.0;
+    const int nblk = (ncell + CB - 1) / CB;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        // ---- sum the segment tiles of each cell of this block (thread = one tile entry of one cell)
 #pragma unroll
-                for (int mm = 1; mm <= MCAP; ++mm) {
-                    if (mm <= g.mmax) {
-                        double cn = cm * c.x - sm * c.y, sn = sm * c.x + cm * c.y;
-                        cm = cn; sm = sn;
-                        v0[(4 + mm) * RS + tid] = cm;
-                        v0[(4 + g.mmax + mm) * RS + tid] = sm;
+        for (int h = 0; h < 2; ++h) {
+            const int cs = (tid >> 6) + 4 * h, ent = tid & 63;
+            const int cell = blk * CB + cs;
+            double v = 0.0;
+            int node = -1;
+            if (cell < ncell) {
+                const int s = __ldg(cell_start + cell), e = __ldg(cell_start + cell + 1);
+                if (e > s) {
+                    const int ix = cell / g.numy, iy = cell - ix * g.numy;
+                    node = ix * g.ny1 + iy;
+                    const int ta = s / TASK, tb = (e - 1) / TASK;
+                    const double* sp = seg + ((size_t)cell + (size_t)ta) * 64 + ent;
+                    for (int t = ta; t <= tb; t += 8, sp += 8 * 64) {           // 8 independent loads in flight
+                        double u[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) u[q] = (t + q <= tb) ? __ldcg(sp + q * 64) : 0.0;
+                        v += ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
                     }
                 }
             }
-            __syncthreads();
-            if (tid < nch) {
-                const double* tcol = t_acc + tid;
-                const double* trow = v0 + (4 + my_ti) * RS;
-#pragma unroll 4
-                for (int p = 0; p < 32; ++p) {
-                    const double* base = tcol + (size_t)s_dcell[p] * nch_pad;
-                    double v = __ldg(base) * v0[0 * RS + p] + __ldg(base + colstep) * v0[1 * RS + p] +
-                               __ldg(base + rowstep) * v0[2 * RS + p] + __ldg(base + colstep + rowstep) * v0[3 * RS + p];
-                    accd = fma(trow[p], v, accd);
-                }
+            s_raw[cs][ent] = v;
+            if (ent == 0) s_node[cs] = node;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < CB * 52; idx += 256) {
+            const int cs = idx / 52, q = idx - cs * 52;
+            const int k = q / 13, ti = q - k * 13;
+            s_S[cs][k][ti] = (ti < ntrig) ? bfe_seg_derive(&s_raw[cs][0], k, ti, g.mmax) : 0.0;
+        }
+        __syncthreads();
+        if (tid < nch) {
+            const double* tcol = t_acc + tid;
+            double t00[CB], t10[CB], t01[CB], t11[CB];
+#pragma unroll
+            for (int cs = 0; cs < CB; ++cs) {
+                const int node = s_node[cs];
+                if (node >= 0) {
+                    const double* base = tcol + (size_t)node * nch_pad;
+                    t00[cs] = __ldg(base); t10[cs] = __ldg(base + colstep);
+                    t01[cs] = __ldg(base + rowstep); t11[cs] = __ldg(base + colstep + rowstep);
+                } else { t00[cs] = 0.0; t10[cs] = 0.0; t01[cs] = 0.0; t11[cs] = 0.0; }
+            }
+#pragma unroll
+            for (int cs = 0; cs < CB; ++cs) {
+                if (s_node[cs] >= 0)
+                    acc += t00[cs] * s_S[cs][0][my_ti] + t10[cs] * s_S[cs][1][my_ti] +
+                           t01[cs] * s_S[cs][2][my_ti] + t11[cs] * s_S[cs][3][my_ti];
             }
         }
+        __syncthreads();
     }
-
-#ifdef BFE_PROFILE_DEPOSIT
-    if (lane == 0 && g_dbg) {
-        long long* d = g_dbg + (blockIdx.x * NW + warp) * 8;
-        d[0] = dbg_main; d[1] = clock64() - dbg_t0; d[2] = dbg_wait; d[3] = dbg_expand; d[4] = dbg_mma;
-        d[5] = dbg_flush; d[6] = dbg_nflush; d[7] = dbg_nks;
-    }
-#endif
-    // ---- CTA reduce over the 8 warps, then per-CTA partial and last-CTA final reduce
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < KCH; ++c) s_slab[warp * SLAB + c * 32 + lane] = acc[c];
-    __syncthreads();
-    for (int j = tid; j < nch_pad; j += 256) {
-        double v = (j == tid) ? accd : 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) v += s_slab[w * SLAB + j];
-        partial[(size_t)blockIdx.x * nch_pad + j] = v;
-    }
+    // ---- per-CTA partial, last CTA reduces in fixed order: 64 column groups (4 columns) x 4 row groups
+    for (int j = tid; j < nch_pad; j += 256) partial[(size_t)blockIdx.x * nch_pad + j] = (j == tid) ? acc : 0.0;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        unsigned int done = atomicAdd(counter, 1u);
+        const unsigned int done = atomicAdd(counter, 1u);
         s_last = (done == gridDim.x - 1);
     }
     __syncthreads();
     if (s_last) {
         __threadfence();
-        for (int j = tid; j < nch; j += 256) {
-            double s = bfe_column_sum(partial, (int)gridDim.x, nch_pad, j) * BFE_FOURPI_NEG;
-            if (j < ncos) cos_out[j] = s;
-            else          sin_out[j - ncos + g.norder] = s;
+        const int cg = tid & 63, rg = tid >> 6;
+        double4 sum = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (cg * 4 < nch_pad) {
+            const double2* q = reinterpret_cast<const double2*>(partial + cg * 4);
+            const size_t st = (size_t)nch_pad / 2;            // row stride in double2
+            const int nrows = (int)gridDim.x;
+            for (int r0 = rg; r0 < nrows; r0 += 4 * 16) {
+                double2 va[16], vb[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int r = r0 + 4 * u;
+                    if (r < nrows) { va[u] = __ldcg(q + (size_t)r * st); vb[u] = __ldcg(q + (size_t)r * st + 1); }
+                    else { va[u] = make_double2(0.0, 0.0); vb[u] = make_double2(0.0, 0.0); }
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) { sum.x += va[u].x; sum.y += va[u].y; sum.z += vb[u].x; sum.w += vb[u].y; }
+            }
+        }
+        s_red[rg][cg * 4 + 0] = sum.x; s_red[rg][cg * 4 + 1] = sum.y;
+        s_red[rg][cg * 4 + 2] = sum.z; s_red[rg][cg * 4 + 3] = sum.w;
+        __syncthreads();
+        if (tid < nch) {
+            const double v = ((s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid])) * BFE_FOURPI_NEG;
+            if (tid < ncos) cos_out[tid] = v;
+            else            sin_out[tid - ncos + g.norder] = v;
         }
         for (int k = tid; k < g.norder; k += 256) sin_out[k] = 0.0;
-        if (tid == 0) { counter[0] = 0u; counter[1] = 0u; }
+        if (tid == 0) counter[0] = 0u;
     }
-}
-
-static size_t deposit_smem_bytes() {
-    const int NV = 4 + 13;
-    size_t doubles = (size_t)DepositSmem::NW * 4 * DepositSmem::TROW + (size_t)DepositSmem::NW * NV * DepositSmem::RS +
-                     (size_t)DepositSmem::NW * 64;
-    return doubles * 8 + DepositSmem::NW * 8 + (DepositSmem::MAXDEFER + 32) * 4 + 128;
 }
 
 // ---------------------------------------------------------------------------
@@ -491,6 +438,153 @@ eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, in
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same evaluation on the FP64 tensor cores.  For the records of one cell the 42 interpolated grid values
+// V[p][c] = sum_k w_k(p) G[node_k][c] are a (particles x 4 corners)(4 x 42) product: mma.sync.m8n8k4 with
+// rows = 8 consecutive sorted records, k = the four corners, 6 n-tiles of 8 columns.  The B fragments (6 doubles
+// per lane) are loaded once per RUN of equal cells; a group of 8 records that straddles runs is done run by run
+// with the A rows of the other runs masked to zero, all into the same accumulators (each row belongs to exactly
+// one run).  Per record the per-lane kernel above moves 1344 B of grid rows into registers (84 LDG.128, L1
+// data-return bound, ncu profiles/); here it is 32 B of weights.
+// Column layout: tile t holds field t/2 (potential, radial, vertical) and harmonics m = 4 (t%2) + col/2 as
+// (cos, sin) pairs, so a lane's two accumulators of a tile are one (cos, sin) pair of ONE harmonic and every
+// lane needs the trig factors of just two harmonics (m = j and m = 4 + j, j = lane % 4).  The five outputs of
+// a record are then spread over the 4 lanes of its row and combined with two butterfly shuffles.
+// ---------------------------------------------------------------------------
+// The records are streamed through shared memory by TMA bulk copies (cp.async.bulk + mbarrier), 32 records
+// (2 kB) per copy, double-buffered per warp: with register prefetch one group ahead a warp had only 512 B in
+// flight and the kernel ran at 1.1 TB/s of record reads (latency-bound, ncu profiles/).
+template <int MCAP>
+__global__ void __launch_bounds__(128)
+eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride, int64_t n,
+                            const EofRec* __restrict__ rec, double2* __restrict__ tmp) {
+    static_assert(MCAP <= 6, "harmonics 0..6 fit the 8 pair slots of two n-tiles");
+    constexpr int NWARP = 4, CHUNK = 32;                              // records per bulk copy
+    __shared__ __align__(128) double s_buf[NWARP][2][CHUNK * 8];
+    __shared__ unsigned long long s_bar[NWARP][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = lane >> 2, jj = lane & 3;
+    const int64_t nwarp = (int64_t)gridDim.x * NWARP;
+    const int64_t wid = (int64_t)blockIdx.x * NWARP + warp;
+    const int64_t per = ((n + nwarp - 1) / nwarp + CHUNK - 1) / CHUNK * CHUNK;   // contiguous range per warp, whole chunks
+    const int64_t lo = wid * per;
+    if (lo >= n) return;                                              // whole warp
+    const int cnt = (int)(((lo + per) < n ? (lo + per) : n) - lo);    // records of this warp (> 0)
+    const int nchunk = (cnt + CHUNK - 1) / CHUNK;
+    const unsigned int bar0 = bfe_smem_u32(&s_bar[warp][0]), bar1 = bfe_smem_u32(&s_bar[warp][1]);
+    const unsigned int buf0 = bfe_smem_u32(&s_buf[warp][0][0]), buf1 = bfe_smem_u32(&s_buf[warp][1][0]);
+    if (lane == 0) {
+        bfe_mbar_init(bar0, 1);
+        bfe_mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (c < nchunk) {
+                const unsigned int bytes = (unsigned int)(((cnt - c * CHUNK) < CHUNK ? (cnt - c * CHUNK) : CHUNK) * 64);
+                bfe_mbar_expect_tx(c ? bar1 : bar0, bytes);
+                bfe_bulk_g2s(c ? buf1 : buf0, rec + lo + c * CHUNK, bytes, c ? bar1 : bar0);
+            }
+        }
+    }
+    __syncwarp();
+    // B fragment of this lane: B[k = jj][col = row] of tile t  ->  G[node_k][m*6 + field*2 + cs]
+    const int koff = ((jj & 1) ? g.ny1 : 0) + ((jj & 2) ? 1 : 0);    // record order c00, c10, c01, c11
+    int boff[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const int m = 4 * (t & 1) + (row >> 1), field = t >> 1, cs = row & 1;
+        boff[t] = (m <= g.mmax) ? (m * 6 + field * 2 + cs) : -1;
+    }
+    const double mlo = (double)jj, mhi = (4 + jj <= g.mmax) ? (double)(4 + jj) : 0.0;
+    const bool hi_on = (4 + jj) <= g.mmax;
+    const bool bit0 = jj & 1, bit1 = jj & 2;
+    double B[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) B[t] = 0.0;
+    int curcell = -1;
+    double2* dst = tmp + 3 * (lo + row) + jj;
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const int par = ch & 1;
+        bfe_mbar_wait(par ? bar1 : bar0, (unsigned int)((ch >> 1) & 1));
+        const double* sb = &s_buf[warp][par][row * 8];
+        const int ccnt = (cnt - ch * CHUNK) < CHUNK ? (cnt - ch * CHUNK) : CHUNK;
+#pragma unroll 1
+        for (int gi = 0; gi < CHUNK / 8; ++gi) {
+            if (gi * 8 >= ccnt) break;                                // warp-uniform
+            const bool on = (gi * 8 + row) < ccnt;
+            const double* rp = sb + gi * 64;
+            const double w = on ? rp[jj] : 0.0;
+            const double2 cs1 = on ? *reinterpret_cast<const double2*>(rp + 4) : make_double2(1.0, 0.0);
+            const int cell = on ? reinterpret_cast<const int*>(rp)[15] : -1;      // high word of cellperm
+            double d[6][2];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) { d[t][0] = 0.0; d[t][1] = 0.0; }
+            if (__all_sync(0xffffffffu, cell == curcell)) {
+                // the whole group continues the open run
+#pragma unroll
+                for (int t = 0; t < 6; ++t) bfe_dmma_m8n8k4(d[t][0], d[t][1], w, B[t]);
+            } else {
+                unsigned int todo = __ballot_sync(0xffffffffu, on);
+                while (todo) {
+                    const int c = __shfl_sync(0xffffffffu, cell, __ffs(todo) - 1);
+                    if (c != curcell) {
+                        curcell = c;
+                        const int ix = c / g.numy, iy = c - ix * g.numy;
+                        const double* gp = G + (size_t)(ix * g.ny1 + iy + koff) * gstride;
+#pragma unroll
+                        for (int t = 0; t < 6; ++t) B[t] = (boff[t] >= 0) ? __ldg(gp + boff[t]) : 0.0;
+                    }
+                    const bool mine = cell == c;
+                    const double a = mine ? w : 0.0;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) bfe_dmma_m8n8k4(d[t][0], d[t][1], a, B[t]);
+                    todo &= ~__ballot_sync(0xffffffffu, mine);
+                }
+            }
+            // trig factors of harmonics jj and 4 + jj as powers of z = cos phi + i sin phi: z^jj = z^(bit0) (z^2)^(bit1)
+            const double c2 = cs1.x * cs1.x - cs1.y * cs1.y, s2 = 2.0 * cs1.x * cs1.y;
+            const double c4 = c2 * c2 - s2 * s2, s4 = 2.0 * c2 * s2;
+            const double ac = bit0 ? cs1.x : 1.0, as = bit0 ? cs1.y : 0.0;
+            const double clo = bit1 ? (ac * c2 - as * s2) : ac, slo = bit1 ? (as * c2 + ac * s2) : as;
+            const double chi = c4 * clo - s4 * slo, shi = s4 * clo + c4 * slo;
+            // tiles 0,1: potential pairs; 2,3: radial force; 4,5: vertical force
+            double pp = (jj == 0) ? 0.0 : (clo * d[0][0] + slo * d[0][1]);        // m = 0 goes to p0, not p
+            double fp = mlo * (slo * d[0][0] - clo * d[0][1]);
+            double fr = clo * d[2][0] + slo * d[2][1];
+            double fz = clo * d[4][0] + slo * d[4][1];
+            if (hi_on) {
+                pp += chi * d[1][0] + shi * d[1][1];
+                fp += mhi * (shi * d[1][0] - chi * d[1][1]);
+                fr += chi * d[3][0] + shi * d[3][1];
+                fz += chi * d[5][0] + shi * d[5][1];
+            }
+#pragma unroll
+            for (int off = 1; off <= 2; off <<= 1) {
+                pp += __shfl_xor_sync(0xffffffffu, pp, off);
+                fp += __shfl_xor_sync(0xffffffffu, fp, off);
+                fr += __shfl_xor_sync(0xffffffffu, fr, off);
+                fz += __shfl_xor_sync(0xffffffffu, fz, off);
+            }
+            const double p0 = __shfl_sync(0xffffffffu, d[0][0], lane & ~3);
+            if (on && jj < 3) {
+                double2 v;
+                if (jj == 0) v = make_double2(p0, pp);
+                else if (jj == 1) v = make_double2(fr, fp);
+                else v = make_double2(fz, 0.0);
+                *dst = v;
+            }
+            dst += 24;
+        }
+        dst += 24 * (CHUNK / 8 - (ccnt + 7) / 8);                     // (only the last chunk can be short)
+        __syncwarp();                                                 // every lane is done reading this buffer
+        if (lane == 0 && ch + 2 < nchunk) {
+            const int c = ch + 2;
+            const unsigned int bytes = (unsigned int)(((cnt - c * CHUNK) < CHUNK ? (cnt - c * CHUNK) : CHUNK) * 64);
+            bfe_mbar_expect_tx(par ? bar1 : bar0, bytes);
+            bfe_bulk_g2s(par ? buf1 : buf0, rec + lo + (int64_t)c * CHUNK, bytes, par ? bar1 : bar0);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __restrict__ r_orig,
                         const double2* __restrict__ tmp, double* __restrict__ p0, double* __restrict__ p,
@@ -509,7 +603,7 @@ eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SortWs {
-    int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_orig; double2* tmp; int* inv;
+    int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_orig; double2* tmp; int* inv; double* seg;
 };
 
 static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
@@ -517,12 +611,14 @@ static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
     size_t o_hist = 0;
     size_t o_start = align_up(o_hist + sizeof(int) * ncell, 256);
     size_t o_cur = align_up(o_start + sizeof(int) * (ncell + 1), 256);
-    size_t o_rec = align_up(o_cur + sizeof(int) * ncell, 256);
+    size_t o_rec = align_up(o_cur + sizeof(int) * ncell * BFE_CURSOR_STRIDE, 256);
     if (n > h->sort_cap || !h->sort_ws) {
         if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
         int64_t cap = (n + n / 8 + 1024 + 15) / 16 * 16;      // multiple of 16: keeps every sub-array 16-B aligned
-        // per particle: 64-B record, R (8 B), 48-B force slot, inverse permutation (4 B)
-        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)cap));
+        // per particle: 64-B record, R (8 B), 48-B force slot, inverse permutation (4 B); then the segment
+        // tiles (512 B per cell and per 128-record task)
+        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)cap +
+                                             512 * ((size_t)ncell + (size_t)cap / SegSum::TASK + 2)));
         BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
         BFE_CUDA(cudaDeviceSynchronize());
         h->sort_cap = cap;
@@ -533,6 +629,7 @@ static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
     ws->r_orig = (double*)(b + o_rec + sizeof(EofRec) * (size_t)h->sort_cap);
     ws->tmp = (double2*)(b + o_rec + (sizeof(EofRec) + sizeof(double)) * (size_t)h->sort_cap);
     ws->inv = (int*)(b + o_rec + (sizeof(EofRec) + sizeof(double) + 48) * (size_t)h->sort_cap);
+    ws->seg = (double*)(b + o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)h->sort_cap);
     return BFE_OK;
 }
 
@@ -548,8 +645,8 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     int rc = sort_workspace(h, n, &ws);
     if (rc != BFE_OK) return rc;
     const int ncell = h->g.numx * h->g.numy;
-    int grid = (int)((n + 1023) / 1024);
-    if (grid > h->num_sms * 2) grid = h->num_sms * 2;
+    int grid = (int)((n + 2047) / 2048);
+    if (grid > h->num_sms) grid = h->num_sms;        // one 1024-thread CTA per SM: the per-CTA merge is paid once per SM
     if (grid < 1) grid = 1;
     {
         const int per = (ncell + 1023) / 1024;
@@ -584,22 +681,26 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
     int rc = sort_workspace(h, h->prepared_n, &ws);
     if (rc != BFE_OK) return rc;
     const int64_t n = h->prepared_n;
-    int64_t nblk = (n + 128 * 8 - 1) / (128 * 8);          // 8 warp tasks of 128 records per CTA pass
-    int grid = (int)(nblk < (int64_t)h->num_sms * 2 ? nblk : (int64_t)h->num_sms * 2);
-    if (grid < 1) grid = 1;
+    const int ncell = h->g.numx * h->g.numy;
     {
-        static bool attr_set = false;
-        const size_t smem = deposit_smem_bytes();
-        if (!attr_set) {
-            BFE_CUDA(cudaFuncSetAttribute(eof_deposit_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-        const int kt = bfe_kt_begin("eof_deposit_kernel", stream);
-        eof_deposit_kernel<6, 8><<<grid, 256, smem, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, n, ws.rec, h->partial,
-                                                             h->counter, cos_out, sin_out);
+        int64_t nblk = (n + SegSum::TASK * SegSum::NW - 1) / (SegSum::TASK * SegSum::NW);
+        int grid = (int)(nblk < (int64_t)h->num_sms * 4 ? nblk : (int64_t)h->num_sms * 4);
+        if (grid < 1) grid = 1;
+        const int kt = bfe_kt_begin("eof_segsum_kernel", stream);
+        eof_segsum_kernel<<<grid, 256, 0, stream>>>(n, ws.rec, ws.seg, h->counter);
+        bfe_kt_end(kt, stream);
+        BFE_LAUNCH_CHECK("eof_segsum_kernel");
+    }
+    {
+        int grid = (ncell + 7) / 8;
+        if (grid > h->num_sms * 2) grid = h->num_sms * 2;
+        if (grid > h->max_ctas) grid = h->max_ctas;
+        const int kt = bfe_kt_begin("eof_node_contract_kernel", stream);
+        eof_node_contract_kernel<<<grid, 256, 0, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, ncell, ws.cell_start, ws.seg,
+                                                         h->partial, h->counter, cos_out, sin_out);
         bfe_kt_end(kt, stream);
     }
-    BFE_LAUNCH_CHECK("eof_deposit_kernel");
+    BFE_LAUNCH_CHECK("eof_node_contract_kernel");
     return BFE_OK;
 }
 
@@ -617,10 +718,20 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
     if (rc != BFE_OK) return rc;
     int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
-    const int kt = bfe_kt_begin("eof_force_sorted_kernel", stream);
-    eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
-    bfe_kt_end(kt, stream);
-    BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
+    if (g_bfe_force_mma) {
+        // one resident wave: 6 CTAs of 4 warps per SM (78 registers, 17.5 kB of record buffers each)
+        int64_t need_m = (n + 127) / 128, cap_m = (int64_t)h->num_sms * 6;
+        grid = (int)(need_m < cap_m ? need_m : cap_m);
+        const int kt = bfe_kt_begin("eof_force_sorted_mma_kernel", stream);
+        eof_force_sorted_mma_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
+        bfe_kt_end(kt, stream);
+        BFE_LAUNCH_CHECK("eof_force_sorted_mma_kernel");
+    } else {
+        const int kt = bfe_kt_begin("eof_force_sorted_kernel", stream);
+        eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
+        bfe_kt_end(kt, stream);
+        BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
+    }
     int64_t need2 = (n + 255) / 256, cap2 = (int64_t)h->num_sms * 8;
     const int kt3 = bfe_kt_begin("eof_force_gather_kernel", stream);
     eof_force_gather_kernel<<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, stream>>>(n, ws.inv, ws.r_orig, ws.tmp, p0, p,

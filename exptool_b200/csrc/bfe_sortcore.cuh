@@ -4,16 +4,36 @@
 #pragma once
 #include "bfe_device.cuh"
 
+// Slot-claim cursors live one per 32-byte L2 sector: same-sector atomics serialise in the L2 (hot cells of a
+// disc / cusp sit next to each other in the bin order), ncu + A/B timing in profiles/r01_summary.md section 11.
+#define BFE_CURSOR_STRIDE 8
+
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256), 32-byte aligned addresses: one full sector per lane
+__device__ __forceinline__ void bfe_st256(void* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void bfe_ld256_nc(const void* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 // exclusive scan of the histogram by one 1024-thread CTA: cell_start, cursor = scan; hist cleared.
 // Bins are staged through shared memory (s_h, per*1024 ints) with coalesced loads; two levels of warp shuffles.
 __device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict__ hist, int* __restrict__ cell_start,
                                                      int* __restrict__ cursor, int* s_h, int* s_wsum) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (ncell + 1023) / 1024;
-    for (int c = tid; c < per * 1024; c += 1024) {
-        int v = 0;
-        if (c < ncell) { v = __ldcg(hist + c); hist[c] = 0; }
-        s_h[c] = v;
+    // eight independent L2 loads in flight per thread (one load at a time costs `per` L2 round trips: ncu showed
+    // the SM that runs this scan active 9 us longer than the others)
+    for (int c0 = tid; c0 < per * 1024; c0 += 8 * 1024) {
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int c = c0 + u * 1024; v[u] = (c < ncell) ? __ldcg(hist + c) : 0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 1024;
+            if (c < ncell) hist[c] = 0;
+            if (c < per * 1024) s_h[c] = v[u];
+        }
     }
     __syncthreads();
     const int lo = tid * per;
@@ -34,7 +54,7 @@ __device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict_
     int run = incl - sum + (warp > 0 ? s_wsum[warp - 1] : 0);    // exclusive prefix of this thread's segment
     for (int k = 0; k < per; ++k) { int h = s_h[lo + k]; s_h[lo + k] = run; run += h; }
     __syncthreads();
-    for (int c = tid; c < ncell; c += 1024) { int v = s_h[c]; cell_start[c] = v; cursor[c] = v; }
+    for (int c = tid; c < ncell; c += 1024) { int v = s_h[c]; cell_start[c] = v; cursor[(size_t)c * BFE_CURSOR_STRIDE] = v; }
     if (tid == 1023) cell_start[ncell] = run;
 }
 

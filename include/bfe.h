@@ -64,7 +64,7 @@ int bfe_set_option(const char* name, int value);
 
 /* With option "time_kernels" = 1 the EOF step kernels are bracketed by CUDA events on their stream;
  * bfe_kernel_time_ms(name) synchronises on and returns the duration (ms) of the latest launch of that kernel
- * (e.g. "eof_deposit_kernel"), or a negative value if none was recorded. */
+ * (e.g. "eof_segsum_kernel"), or a negative value if none was recorded. */
 double bfe_kernel_time_ms(const char* name);
 
 /* ---------------------------------------------------------------- EOF (disc) ---------------- */

@@ -40,15 +40,18 @@ def make_sl(ops, p, ev, ef, xi, p0, d0):
     return ops.SLTables(p['lmax'], p['nmax'], p['numr'], p['cmap'], p['scale'], ev, ef, xi, p0, d0)
 
 
-@pytest.fixture(params=['direct', 'sorted'])
+@pytest.fixture(params=['direct', 'sorted', 'sorted_lane'])
 def eof_mode(ops, request):
-    """run the EOF tests through both kernel families (bfe_set_option)"""
+    """run the EOF tests through both kernel families (bfe_set_option); 'sorted' evaluates the sorted set on
+    the FP64 tensor cores (default), 'sorted_lane' with the per-lane kernel"""
     v = 1 if request.param == 'direct' else 2
     ops.set_option('eof_accumulate_mode', v)
     ops.set_option('eof_force_mode', v)
-    yield request.param
+    ops.set_option('force_mma', 0 if request.param == 'sorted_lane' else 1)
+    yield 'direct' if v == 1 else 'sorted'
     ops.set_option('eof_accumulate_mode', 0)
     ops.set_option('eof_force_mode', 0)
+    ops.set_option('force_mma', 1)
 
 
 @pytest.mark.parametrize('name', EOF_CASES)
@@ -247,6 +250,58 @@ def test_eof_prepared_set_matches_separate_calls(ops):
         E.accumulate_prepared()
     f3 = E.force_prepared().cpu().numpy()
     assert np.array_equal(f3[5], f2[5])
+
+
+def test_eof_sorted_cell_edges(ops):
+    """Particles placed ON and within 1e-4..1e-15 (relative) of the table's cell edges, on the z = 0 plane, at the
+    origin and outside the table: the histogram pass indexes cells in FP32 with an FP64 fallback near edges, the
+    scatter pass in FP64 -- any disagreement between the two would misfile records.  Sorted == direct == oracle."""
+    meta = dict(eof_params={}, kind='smooth', seed=0)
+    p, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    rng = np.random.default_rng(77)
+    kx = rng.integers(0, g['numx'] + 1, 60000).astype(np.float64)
+    ky = rng.integers(0, g['numy'] + 1, 60000).astype(np.float64)
+    eps = 10.0 ** rng.uniform(-15.5, -4, 60000) * rng.choice([-1.0, 0.0, 1.0], 60000)
+    on_x = rng.random(60000) < 0.6            # which coordinate sits on an edge
+    X = np.where(on_x, kx, kx + rng.random(60000))
+    Y = np.where(on_x, ky + rng.random(60000), ky)
+    xi = g['XMIN'] + X * g['dX']
+    yy = g['YMIN'] + Y * g['dY']
+    if g['cmap'] == 1:
+        xi = np.clip(xi, -0.999999, 0.999999)
+        r = g['ascale'] * (1.0 + xi) / (1.0 - xi)
+    elif g['cmap'] == 2:
+        r = np.exp(xi)
+    else:
+        r = xi
+    zz = g['hscale'] * np.sinh(yy)
+    r = np.abs(r * (1.0 + np.where(on_x, eps, 0.0)))
+    zz = zz * (1.0 + np.where(on_x, 0.0, eps))
+    phi = rng.uniform(0, 2 * np.pi, 60000)
+    x = r * np.cos(phi); y = r * np.sin(phi); z = zz.copy()
+    z[:2000] = rng.choice([0.0, 1e-300, -1e-300, 1e-12, -1e-9, 1e-8], 2000)       # the y = 0 edge between two rows
+    x[2000:2010] = 0.0; y[2000:2010] = 0.0                                         # axis
+    x[2010:2020] *= 1e3; z[2020:2030] *= 1e3                                       # far outside the table
+    m = rng.uniform(0.5, 1.5, 60000) / 60000
+    ops.set_option('eof_accumulate_mode', 1); ops.set_option('eof_force_mode', 1)
+    c1, s1 = E.accumulate(x, y, z, m)
+    E.contract(c1, s1)
+    f1 = E.force(x, y, z).cpu().numpy()
+    ops.set_option('eof_accumulate_mode', 2); ops.set_option('eof_force_mode', 2)
+    try:
+        c2, s2 = E.accumulate(x, y, z, m)
+        E.contract(c1, s1)
+        f2 = E.force(x, y, z).cpu().numpy()
+    finally:
+        ops.set_option('eof_accumulate_mode', 0); ops.set_option('eof_force_mode', 0)
+    assert relerr(c2.cpu().numpy(), c1.cpu().numpy()) < 1e-12
+    assert relerr(s2.cpu().numpy(), s1.cpu().numpy()) < 1e-12
+    for i in range(6):
+        assert relerr(f2[i], f1[i]) < 1e-12, i
+    co, so = O.eof_accumulate(x, y, z, m, T['potC'], T['potS'], g['mmax'], g['norder'], *eof_geo_args(g),
+                              g['ascale'], g['hscale'], g['cmap'])
+    assert relerr(c1.cpu().numpy(), co) < TOL and relerr(s1.cpu().numpy(), so) < TOL
 
 
 @pytest.mark.parametrize('lmax', [4, 6])
