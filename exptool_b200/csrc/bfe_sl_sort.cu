@@ -55,6 +55,8 @@ sl_bin_hist_kernel(SlGeom g, const double* __restrict__ xi, int nbin, int64_t n,
     __shared__ int s_wsum[32];
     __shared__ bool s_last;
     for (int c = threadIdx.x; c < nbin; c += blockDim.x) s_hist[c] = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nbin; c += gridDim.x * blockDim.x)
+        cursor[(size_t)c * BFE_CURSOR_STRIDE] = 0;      // slot-claim counters for the scatter kernel
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
@@ -77,7 +79,7 @@ sl_bin_hist_kernel(SlGeom g, const double* __restrict__ xi, int nbin, int64_t n,
     __syncthreads();
     if (s_last) {
         __threadfence();
-        bfe_block_scan_cells(nbin, hist, bin_start, cursor, s_hist, s_wsum);
+        bfe_block_scan_cells(nbin, hist, bin_start, s_hist, s_wsum);
         if (threadIdx.x == 0) *counter = 0u;
     }
 }
@@ -85,7 +87,8 @@ sl_bin_hist_kernel(SlGeom g, const double* __restrict__ xi, int nbin, int64_t n,
 __global__ void __launch_bounds__(256)
 sl_bin_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __restrict__ p0tab, int64_t n,
                       const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                      const double* __restrict__ mass, int* __restrict__ cursor, SlRec* __restrict__ rec) {
+                      const double* __restrict__ mass, const int* __restrict__ bin_start, int* __restrict__ cursor,
+                      SlRec* __restrict__ rec) {
     constexpr int U = 2;
     for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
         SlPrep pr[U];
@@ -100,7 +103,7 @@ sl_bin_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __r
             pr[u] = bfe_sl_prep(g, xi, p0tab, px, py, pz, pm);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) pos[u] = (idx[u] < n) ? atomicAdd(&cursor[(size_t)pr[u].i * BFE_CURSOR_STRIDE], 1) : 0;   // integer slot claim
+        for (int u = 0; u < U; ++u) pos[u] = (idx[u] < n) ? (__ldg(bin_start + pr[u].i) + atomicAdd(&cursor[(size_t)pr[u].i * BFE_CURSOR_STRIDE], 1)) : 0;   // integer slot claim
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (idx[u] < n) {
@@ -477,7 +480,7 @@ int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double
     int g2 = (int)((n + 511) / 512);
     if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
     if (g2 < 1) g2 = 1;
-    sl_bin_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, h->xi, h->p0, n, x, y, z, mass, ws.cursor, ws.rec);
+    sl_bin_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, h->xi, h->p0, n, x, y, z, mass, ws.bin_start, ws.cursor, ws.rec);
     BFE_LAUNCH_CHECK("sl_bin_scatter_kernel");
     if (h->g.lmax <= 4 && h->g.nrow * h->g.nmax <= 32 * 15)
         return sl_deposit_launch<4, 15>(h, n, ws.rec, no_odd, expcoef, stream);

@@ -22,6 +22,35 @@
 //   eof_force_sorted_kernel  : the same per lane (warp-uniform table rows; option force_mma = 0),
 //                              outputs scattered back to the caller's particle order
 #include "bfe_device.cuh"
+
+// Optional device-side timeline (build with BFE_NVCC_FLAGS=-DBFE_TRACE; profiles/trace_step.py): thread 0 of
+// every CTA logs %globaltimer at the phase boundaries of the step's kernels.
+#ifdef BFE_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+extern "C" int bfe_debug_set_trace(unsigned long long* p, unsigned int cap) {
+    cudaError_t e = cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+    return (int)e;
+}
+__device__ __forceinline__ void bfe_trace(int kid, int phase) {
+    if (threadIdx.x == 0 && g_trace) {
+        unsigned long long t; unsigned int sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        const unsigned long long slot = atomicAdd(g_trace, 1ull);
+        if (slot < g_trace_cap) {
+            g_trace[2 + 2 * slot] = ((unsigned long long)kid << 56) | ((unsigned long long)phase << 48) |
+                                    ((unsigned long long)sm << 32) | (unsigned long long)blockIdx.x;
+            g_trace[3 + 2 * slot] = t;
+        }
+    }
+}
+#define BFE_TRACE_PT(kid, phase) bfe_trace(kid, phase)
+#else
+#define BFE_TRACE_PT(kid, phase)
+#endif
+
 #include "bfe_sortcore.cuh"
 
 struct __align__(16) EofRec {
@@ -48,8 +77,13 @@ eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__
     extern __shared__ int s_hist[];
     __shared__ int s_wsum[32];
     __shared__ bool s_last;
+    BFE_TRACE_PT(0, 0);
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
+    // this CTA's slice of the slot-claim counters (used by the scatter kernel) is cleared here, in parallel
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x)
+        cursor[(size_t)c * BFE_CURSOR_STRIDE] = 0;
     __syncthreads();
+    BFE_TRACE_PT(0, 1);
     // two particles per thread per pass: six independent loads in flight
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
@@ -72,34 +106,42 @@ eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__
         }
     }
     __syncthreads();
+    BFE_TRACE_PT(0, 2);
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
         int v = s_hist[c];
         if (v) atomicAdd(&hist[c], v);
     }
+    BFE_TRACE_PT(0, 3);
     __threadfence();
     __syncthreads();
+    BFE_TRACE_PT(0, 4);
     if (threadIdx.x == 0) {
         unsigned int done = atomicAdd(counter, 1u);
         s_last = (done == gridDim.x - 1);
     }
     __syncthreads();
+    BFE_TRACE_PT(0, 5);
     if (s_last) {
         __threadfence();
-        bfe_block_scan_cells(ncell, hist, cell_start, cursor, s_hist, s_wsum);
+        BFE_TRACE_PT(0, 6);
+        bfe_block_scan_cells(ncell, hist, cell_start, s_hist, s_wsum);
         if (threadIdx.x == 0) *counter = 0u;
+        __syncthreads();
+        BFE_TRACE_PT(0, 7);
     }
 }
 
 __global__ void __launch_bounds__(256)
 eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                         const double* __restrict__ z, const double* __restrict__ mass,
-                        int* __restrict__ cursor, EofRec* __restrict__ rec, int* __restrict__ inv,
-                        double* __restrict__ r_orig) {
+                        const int* __restrict__ cell_start, int* __restrict__ cursor, EofRec* __restrict__ rec,
+                        int* __restrict__ inv, double* __restrict__ r_orig) {
     // Two particles per thread per pass.  Order of work per pass: (1) all eight loads, (2) the cell id by the FP32
     // fast path (exact by construction, FP64 fallback near edges), (3) the integer slot claims, (4) the FP64 bin
     // fractions, weights and cos/sin phi WHILE the claims are in flight (they were 1/3 of this kernel's stall
     // samples when issued after the FP64 arithmetic, ncu profiles/), (5) the record stores.
     constexpr int U = 2;
+    BFE_TRACE_PT(1, 0);
     for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
         double px[U], py[U], pz[U], aux[U];
         int64_t idx[U];
@@ -120,7 +162,7 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            pos[u] = (idx[u] < n) ? atomicAdd(&cursor[(size_t)cell[u] * BFE_CURSOR_STRIDE], 1) : 0;   // integer slot claim, not a data reduction
+            pos[u] = (idx[u] < n) ? (__ldg(cell_start + cell[u]) + atomicAdd(&cursor[(size_t)cell[u] * BFE_CURSOR_STRIDE], 1)) : 0;   // integer slot claim, not a data reduction
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const double r = sqrt(px[u] * px[u] + py[u] * py[u] + 1.e-10);   // eof.py:531 / 1070
@@ -138,6 +180,7 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
             }
         }
     }
+    BFE_TRACE_PT(1, 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -182,11 +225,13 @@ eof_segsum_kernel(int64_t n, const EofRec* __restrict__ rec, double* __restrict_
     const double* brow = val + (7 + fg) * RS;     // B[.][col fg] (col 0 is the constant 1)
     unsigned int* task_counter = counter + 1;
     const int64_t ntasks = (n + TASK - 1) / TASK;
+    BFE_TRACE_PT(2, 0);
     for (;;) {
         int64_t task = 0;
         if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= ntasks) break;
+        task = ntasks - 1 - task;                 // last task first: the short runs of the sparse outskirts are at the end
         const int64_t t0 = task * TASK;
         const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
         double d0 = 0.0, d1 = 0.0;                // D[fg][2 fj], D[fg][2 fj + 1]
@@ -254,39 +299,32 @@ eof_segsum_kernel(int64_t n, const EofRec* __restrict__ rec, double* __restrict_
             reinterpret_cast<double2*>(seg + ((size_t)cur + (size_t)task) * 64)[lane] = make_double2(d0, d1);
     }
     // the last CTA to finish re-arms the task queue
+    BFE_TRACE_PT(2, 1);
     __syncthreads();
+    BFE_TRACE_PT(2, 2);
     if (tid == 0) {
         __threadfence();
         const unsigned int done = atomicAdd(counter, 1u);
         if (done == gridDim.x - 1) { counter[0] = 0u; counter[1] = 0u; }
     }
+    BFE_TRACE_PT(2, 3);
 }
 
-// one of the 52 sums S[k][ti] from a raw 8x8 tile R (row-major): ti = m for cos(m phi), mmax + m for sin(m phi)
-__device__ __forceinline__ double bfe_seg_derive(const double* __restrict__ R, int k, int ti, int mmax) {
-    const bool is_sin = ti > mmax;
-    const int m = is_sin ? (ti - mmax) : ti;
-    const double* lo = R + k * 8;                 // sum_p w_k {1, c1, s1, c2, s2, c3, s3, s4}
-    const double* hi = R + (4 + k) * 8;           // the same with w_k c4
+// A sum S[k][ch] from a raw 8x8 tile R (row-major; rows 0-3 = sum_p w_k {1, c1, s1, c2, s2, c3, s3, s4}, rows
+// 4-7 the same with w_k c4):  S = c_lo R[k][i_lo] + c_hi R[4+k][i_hi], the selectors depending only on the harmonic.
+struct SegSel { int i_lo, i_hi; double c_lo, c_hi; };
+__device__ __forceinline__ SegSel bfe_seg_selector(int m, bool is_sin) {
+    SegSel s; s.i_lo = 0; s.i_hi = 0; s.c_lo = 1.0; s.c_hi = 0.0;
     if (!is_sin) {
-        switch (m) {
-            case 0: return lo[0];
-            case 1: return lo[1];
-            case 2: return lo[3];
-            case 3: return lo[5];
-            case 4: return hi[0];
-            case 5: return 2.0 * hi[1] - lo[5];
-            default: return 2.0 * hi[3] - lo[3];
-        }
+        if (m <= 3) s.i_lo = (m == 0) ? 0 : (2 * m - 1);                     // 1, c1, c2, c3
+        else if (m == 4) { s.c_lo = 0.0; s.c_hi = 1.0; s.i_hi = 0; }          // sum w c4
+        else { s.c_hi = 2.0; s.i_hi = 2 * (m - 4) - 1; s.c_lo = -1.0; s.i_lo = 2 * (8 - m) - 1; }   // c5 = 2 c4 c1 - c3, c6 = 2 c4 c2 - c2
+    } else {
+        if (m <= 3) s.i_lo = 2 * m;                                           // s1, s2, s3
+        else if (m == 4) s.i_lo = 7;                                          // s4
+        else { s.c_hi = 2.0; s.i_hi = 2 * (m - 4); s.c_lo = 1.0; s.i_lo = 2 * (8 - m); }            // s5 = 2 c4 s1 + s3, s6 = 2 c4 s2 + s2
     }
-    switch (m) {
-        case 1: return lo[2];
-        case 2: return lo[4];
-        case 3: return lo[6];
-        case 4: return lo[7];
-        case 5: return 2.0 * hi[2] + lo[6];
-        default: return 2.0 * hi[4] + lo[4];
-    }
+    return s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -296,113 +334,133 @@ eof_node_contract_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, i
                          double* __restrict__ cos_out, double* __restrict__ sin_out) {
     constexpr int CB = 8;                         // cells staged per pass
     constexpr int TASK = SegSum::TASK;
+    constexpr int GROUP = 16;                     // CTAs per first-level reduce group
     __shared__ double s_raw[CB][64];
-    __shared__ double s_S[CB][4][16];
-    __shared__ int s_node[CB];
-    __shared__ double s_red[4][256];
-    __shared__ bool s_last;
+    __shared__ int s_flag[2];
     const int tid = threadIdx.x;
     const int ncos = (g.mmax + 1) * g.norder;
-    const int ntrig = 2 * g.mmax + 1;
-    int my_ti = 0;
-    if (tid < nch) my_ti = (tid < ncos) ? tid / g.norder : g.mmax + 1 + (tid - ncos) / g.norder;
+    // this thread's channel j = tid: harmonic and the selectors of its sums
+    SegSel sel = bfe_seg_selector(0, false);
+    if (tid < nch) {
+        const bool is_sin = tid >= ncos;
+        const int m = is_sin ? (1 + (tid - ncos) / g.norder) : (tid / g.norder);
+        sel = bfe_seg_selector(m, is_sin);
+    }
     const int rowstep = nch_pad, colstep = g.ny1 * nch_pad;
+    const double* tcol = t_acc + (tid < nch ? tid : 0);
     double acc = 0.0;
     const int nblk = (ncell + CB - 1) / CB;
+    BFE_TRACE_PT(3, 0);
     for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        // The CB cells of a block are nblk apart (same iy, ix 16 apart for the 128 x 64 table): consecutive cells
+        // are all hot or all empty, and with 8-cell blocks handed out with a stride that is a multiple of 8 a
+        // quarter of the CTAs got every hot block (device timeline: slowest CTA 15 us, median 6 us).
+        // Every thread reads the run offsets itself (broadcast loads), so the table rows of the non-empty cells
+        // can be requested at once, together with the segment tiles.
+        int cs0[CB], cs1[CB];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+            const int cell = c * nblk + blk;
+            cs0[c] = (cell < ncell) ? __ldg(cell_start + cell) : 0;
+            cs1[c] = (cell < ncell) ? __ldg(cell_start + cell + 1) : 0;
+        }
+        double t00[CB], t10[CB], t01[CB], t11[CB];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+            if (cs1[c] > cs0[c]) {
+                const int cell = c * nblk + blk;
+                const int ix = cell / g.numy, iy = cell - ix * g.numy;
+                const double* base = tcol + (size_t)(ix * g.ny1 + iy) * nch_pad;
+                t00[c] = __ldg(base); t10[c] = __ldg(base + colstep);
+                t01[c] = __ldg(base + rowstep); t11[c] = __ldg(base + colstep + rowstep);
+            } else { t00[c] = 0.0; t10[c] = 0.0; t01[c] = 0.0; t11[c] = 0.0; }
+        }
         // ---- sum the segment tiles of each cell of this block (thread = one tile entry of one cell)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int cs = (tid >> 6) + 4 * h, ent = tid & 63;
-            const int cell = blk * CB + cs;
-            double v = 0.0;
-            int node = -1;
-            if (cell < ncell) {
-                const int s = __ldg(cell_start + cell), e = __ldg(cell_start + cell + 1);
-                if (e > s) {
-                    const int ix = cell / g.numy, iy = cell - ix * g.numy;
-                    node = ix * g.ny1 + iy;
-                    const int ta = s / TASK, tb = (e - 1) / TASK;
-                    const double* sp = seg + ((size_t)cell + (size_t)ta) * 64 + ent;
-                    for (int t = ta; t <= tb; t += 8, sp += 8 * 64) {           // 8 independent loads in flight
-                        double u[8];
+            const int c = (tid >> 6) + 4 * h, ent = tid & 63;
+            const int cell = c * nblk + blk;
+            int s = 0, e = 0;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) u[q] = (t + q <= tb) ? __ldcg(sp + q * 64) : 0.0;
-                        v += ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
-                    }
+            for (int q = 0; q < CB; ++q) if (q == c) { s = cs0[q]; e = cs1[q]; }
+            double v = 0.0;
+            if (e > s) {
+                const int ta = s / TASK, tb = (e - 1) / TASK;
+                const double* sp = seg + ((size_t)cell + (size_t)ta) * 64 + ent;
+                for (int t = ta; t <= tb; t += 8, sp += 8 * 64) {               // 8 independent loads in flight
+                    double u[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) u[q] = (t + q <= tb) ? __ldcg(sp + q * 64) : 0.0;
+                    v += ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
                 }
             }
-            s_raw[cs][ent] = v;
-            if (ent == 0) s_node[cs] = node;
+            s_raw[c][ent] = v;
         }
         __syncthreads();
-        for (int idx = tid; idx < CB * 52; idx += 256) {
-            const int cs = idx / 52, q = idx - cs * 52;
-            const int k = q / 13, ti = q - k * 13;
-            s_S[cs][k][ti] = (ti < ntrig) ? bfe_seg_derive(&s_raw[cs][0], k, ti, g.mmax) : 0.0;
-        }
-        __syncthreads();
-        if (tid < nch) {
-            const double* tcol = t_acc + tid;
-            double t00[CB], t10[CB], t01[CB], t11[CB];
 #pragma unroll
-            for (int cs = 0; cs < CB; ++cs) {
-                const int node = s_node[cs];
-                if (node >= 0) {
-                    const double* base = tcol + (size_t)node * nch_pad;
-                    t00[cs] = __ldg(base); t10[cs] = __ldg(base + colstep);
-                    t01[cs] = __ldg(base + rowstep); t11[cs] = __ldg(base + colstep + rowstep);
-                } else { t00[cs] = 0.0; t10[cs] = 0.0; t01[cs] = 0.0; t11[cs] = 0.0; }
-            }
-#pragma unroll
-            for (int cs = 0; cs < CB; ++cs) {
-                if (s_node[cs] >= 0)
-                    acc += t00[cs] * s_S[cs][0][my_ti] + t10[cs] * s_S[cs][1][my_ti] +
-                           t01[cs] * s_S[cs][2][my_ti] + t11[cs] * s_S[cs][3][my_ti];
+        for (int c = 0; c < CB; ++c) {
+            if (cs1[c] > cs0[c]) {
+                const double* lo = &s_raw[c][sel.i_lo];
+                const double* hi = &s_raw[c][32 + sel.i_hi];
+                const double S0 = sel.c_lo * lo[0] + sel.c_hi * hi[0], S1 = sel.c_lo * lo[8] + sel.c_hi * hi[8];
+                const double S2 = sel.c_lo * lo[16] + sel.c_hi * hi[16], S3 = sel.c_lo * lo[24] + sel.c_hi * hi[24];
+                acc += t00[c] * S0 + t10[c] * S1 + t01[c] * S2 + t11[c] * S3;
             }
         }
         __syncthreads();
     }
-    // ---- per-CTA partial, last CTA reduces in fixed order: 64 column groups (4 columns) x 4 row groups
-    for (int j = tid; j < nch_pad; j += 256) partial[(size_t)blockIdx.x * nch_pad + j] = (j == tid) ? acc : 0.0;
+    // ---- two-level reduce of the per-CTA partials in fixed order (deterministic): the last CTA of each group of
+    // 16 sums its group's rows, the last group to finish sums the group rows.  A single last CTA reading all 296
+    // rows through one SM cost ~12 us of serial tail (ncu: sm__cycles_active max vs avg).
+    BFE_TRACE_PT(3, 1);
+    const int ngroups = ((int)gridDim.x + GROUP - 1) / GROUP;
+    const int grp = blockIdx.x / GROUP;
+    const int gfirst = grp * GROUP;
+    const int gsize = ((int)gridDim.x - gfirst) < GROUP ? ((int)gridDim.x - gfirst) : GROUP;
+    double* grow = partial + (size_t)gridDim.x * nch_pad;                 // [ngroups][nch_pad]
+    if (tid < nch_pad) partial[(size_t)blockIdx.x * nch_pad + tid] = (tid < nch) ? acc : 0.0;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag[0] = (atomicAdd(counter + 64 + grp, 1u) == (unsigned int)(gsize - 1));
+    __syncthreads();
+    BFE_TRACE_PT(3, 2);
+    if (!s_flag[0]) return;
+    __threadfence();
+    if (tid < nch_pad) {
+        double v[GROUP];
+#pragma unroll
+        for (int r = 0; r < GROUP; ++r) v[r] = (r < gsize) ? __ldcg(partial + (size_t)(gfirst + r) * nch_pad + tid) : 0.0;
+        double sum = 0.0;
+#pragma unroll
+        for (int r = 0; r < GROUP; ++r) sum += v[r];
+        grow[(size_t)grp * nch_pad + tid] = sum;
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned int done = atomicAdd(counter, 1u);
-        s_last = (done == gridDim.x - 1);
+        counter[64 + grp] = 0u;
+        s_flag[1] = (atomicAdd(counter, 1u) == (unsigned int)(ngroups - 1));
     }
     __syncthreads();
-    if (s_last) {
-        __threadfence();
-        const int cg = tid & 63, rg = tid >> 6;
-        double4 sum = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (cg * 4 < nch_pad) {
-            const double2* q = reinterpret_cast<const double2*>(partial + cg * 4);
-            const size_t st = (size_t)nch_pad / 2;            // row stride in double2
-            const int nrows = (int)gridDim.x;
-            for (int r0 = rg; r0 < nrows; r0 += 4 * 16) {
-                double2 va[16], vb[16];
+    BFE_TRACE_PT(3, 3);
+    if (!s_flag[1]) return;
+    __threadfence();
+    if (tid < nch) {
+        double sum = 0.0;
+        for (int r0 = 0; r0 < ngroups; r0 += 16) {
+            double v[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int r = r0 + 4 * u;
-                    if (r < nrows) { va[u] = __ldcg(q + (size_t)r * st); vb[u] = __ldcg(q + (size_t)r * st + 1); }
-                    else { va[u] = make_double2(0.0, 0.0); vb[u] = make_double2(0.0, 0.0); }
-                }
+            for (int r = 0; r < 16; ++r) v[r] = (r0 + r < ngroups) ? __ldcg(grow + (size_t)(r0 + r) * nch_pad + tid) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) { sum.x += va[u].x; sum.y += va[u].y; sum.z += vb[u].x; sum.w += vb[u].y; }
-            }
+            for (int r = 0; r < 16; ++r) sum += v[r];
         }
-        s_red[rg][cg * 4 + 0] = sum.x; s_red[rg][cg * 4 + 1] = sum.y;
-        s_red[rg][cg * 4 + 2] = sum.z; s_red[rg][cg * 4 + 3] = sum.w;
-        __syncthreads();
-        if (tid < nch) {
-            const double v = ((s_red[0][tid] + s_red[1][tid]) + (s_red[2][tid] + s_red[3][tid])) * BFE_FOURPI_NEG;
-            if (tid < ncos) cos_out[tid] = v;
-            else            sin_out[tid - ncos + g.norder] = v;
-        }
-        for (int k = tid; k < g.norder; k += 256) sin_out[k] = 0.0;
-        if (tid == 0) counter[0] = 0u;
+        sum *= BFE_FOURPI_NEG;
+        if (tid < ncos) cos_out[tid] = sum;
+        else            sin_out[tid - ncos + g.norder] = sum;
     }
+    for (int k = tid; k < g.norder; k += 256) sin_out[k] = 0.0;
+    if (tid == 0) counter[0] = 0u;
+    BFE_TRACE_PT(3, 4);
 }
 
 // ---------------------------------------------------------------------------
@@ -453,37 +511,56 @@ eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, in
 // ---------------------------------------------------------------------------
 // The records are streamed through shared memory by TMA bulk copies (cp.async.bulk + mbarrier), 32 records
 // (2 kB) per copy, double-buffered per warp: with register prefetch one group ahead a warp had only 512 B in
-// flight and the kernel ran at 1.1 TB/s of record reads (latency-bound, ncu profiles/).
+// flight (latency-bound, ncu profiles/).  Work is handed out dynamically in tickets of 128 records, LAST
+// ticket first: the sparse outskirts of the sorted array (short runs, one dependent B-fragment load each) are
+// at its end, and with a static split the warps that got them finished 50 % after the average.
 template <int MCAP>
 __global__ void __launch_bounds__(128)
 eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride, int64_t n,
-                            const EofRec* __restrict__ rec, double2* __restrict__ tmp) {
+                            const EofRec* __restrict__ rec, double2* __restrict__ tmp,
+                            unsigned int* __restrict__ counter) {
     static_assert(MCAP <= 6, "harmonics 0..6 fit the 8 pair slots of two n-tiles");
-    constexpr int NWARP = 4, CHUNK = 32;                              // records per bulk copy
+    constexpr int NWARP = 4, CHUNK = 32, TICKET = 128;
+    constexpr int SPARSE_RUNS = 6;                 // run starts per 32-record chunk above which the chunk is gathered
     __shared__ __align__(128) double s_buf[NWARP][2][CHUNK * 8];
     __shared__ unsigned long long s_bar[NWARP][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = lane >> 2, jj = lane & 3;
-    const int64_t nwarp = (int64_t)gridDim.x * NWARP;
-    const int64_t wid = (int64_t)blockIdx.x * NWARP + warp;
-    const int64_t per = ((n + nwarp - 1) / nwarp + CHUNK - 1) / CHUNK * CHUNK;   // contiguous range per warp, whole chunks
-    const int64_t lo = wid * per;
-    if (lo >= n) return;                                              // whole warp
-    const int cnt = (int)(((lo + per) < n ? (lo + per) : n) - lo);    // records of this warp (> 0)
-    const int nchunk = (cnt + CHUNK - 1) / CHUNK;
     const unsigned int bar0 = bfe_smem_u32(&s_bar[warp][0]), bar1 = bfe_smem_u32(&s_bar[warp][1]);
     const unsigned int buf0 = bfe_smem_u32(&s_buf[warp][0][0]), buf1 = bfe_smem_u32(&s_buf[warp][1][0]);
+    const int ntick = (int)((n + TICKET - 1) / TICKET);
+    unsigned int* ticket_counter = counter + 1;
+    BFE_TRACE_PT(5, 0);
+    // producer state (meaningful in lane 0): current ticket, next chunk within it, and the two issued chunks
+    int pf_tick = -1, pf_sub = 0, pf_nsub = 0;
+    int qb0 = 0, qc0 = 0, qb1 = 0, qc1 = 0;        // record base / count of the chunk in buffer 0 / 1 (count 0: none)
+    auto issue = [&](int par) {                    // lane 0 only
+        if (pf_sub >= pf_nsub) {
+            const int t = (int)atomicAdd(ticket_counter, 1u);
+            if (t < ntick) {
+                pf_tick = ntick - 1 - t;
+                const int64_t left = n - (int64_t)pf_tick * TICKET;
+                pf_nsub = (int)(((left < TICKET ? left : TICKET) + CHUNK - 1) / CHUNK);
+                pf_sub = 0;
+            } else { pf_nsub = 0; pf_sub = 0; pf_tick = -1; }
+        }
+        int base = 0, cnt = 0;
+        if (pf_tick >= 0 && pf_sub < pf_nsub) {
+            base = pf_tick * TICKET + pf_sub * CHUNK;
+            const int64_t left = n - (int64_t)base;
+            cnt = (int)(left < CHUNK ? left : CHUNK);
+            ++pf_sub;
+            const unsigned int bytes = (unsigned int)cnt * 64u;
+            bfe_mbar_expect_tx(par ? bar1 : bar0, bytes);
+            bfe_bulk_g2s(par ? buf1 : buf0, rec + base, bytes, par ? bar1 : bar0);
+        }
+        if (par) { qb1 = base; qc1 = cnt; } else { qb0 = base; qc0 = cnt; }
+    };
     if (lane == 0) {
         bfe_mbar_init(bar0, 1);
         bfe_mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            if (c < nchunk) {
-                const unsigned int bytes = (unsigned int)(((cnt - c * CHUNK) < CHUNK ? (cnt - c * CHUNK) : CHUNK) * 64);
-                bfe_mbar_expect_tx(c ? bar1 : bar0, bytes);
-                bfe_bulk_g2s(c ? buf1 : buf0, rec + lo + c * CHUNK, bytes, c ? bar1 : bar0);
-            }
-        }
+        issue(0);
+        issue(1);
     }
     __syncwarp();
     // B fragment of this lane: B[k = jj][col = row] of tile t  ->  G[node_k][m*6 + field*2 + cs]
@@ -501,12 +578,40 @@ eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride
 #pragma unroll
     for (int t = 0; t < 6; ++t) B[t] = 0.0;
     int curcell = -1;
-    double2* dst = tmp + 3 * (lo + row) + jj;
-    for (int ch = 0; ch < nchunk; ++ch) {
-        const int par = ch & 1;
-        bfe_mbar_wait(par ? bar1 : bar0, (unsigned int)((ch >> 1) & 1));
+    unsigned int ph0 = 0u, ph1 = 0u;
+    for (int par = 0;; par ^= 1) {
+        const int cbase = __shfl_sync(0xffffffffu, par ? qb1 : qb0, 0);
+        const int ccnt = __shfl_sync(0xffffffffu, par ? qc1 : qc0, 0);
+        if (ccnt == 0) break;
+        if (par) { bfe_mbar_wait(bar1, ph1); ph1 ^= 1u; } else { bfe_mbar_wait(bar0, ph0); ph0 ^= 1u; }
+        // chunks made of short runs (sparse outskirts): every run would cost one dependent B-fragment load, ~0.5 us
+        // each, serialised in this warp.  Such chunks are evaluated lane per record with the gather formulation
+        // instead: 84 independent 16-B loads per lane, all in flight together.
+        {
+            const int* rl = reinterpret_cast<const int*>(&s_buf[warp][par][(lane < ccnt ? lane : 0) * 8]);
+            const int mycell = rl[15];
+            const int prev = __shfl_up_sync(0xffffffffu, mycell, 1);
+            const unsigned int starts = __ballot_sync(0xffffffffu, (lane < ccnt) && (lane == 0 || mycell != prev));
+            if (__popc(starts) > SPARSE_RUNS) {
+                if (lane < ccnt) {
+                    const double* r8 = &s_buf[warp][par][lane * 8];
+                    EofBin b;
+                    const int ix = mycell / g.numy, iy = mycell - ix * g.numy;
+                    b.node = ix * g.ny1 + iy; b.cell = mycell;
+                    b.c00 = r8[0]; b.c10 = r8[1]; b.c01 = r8[2]; b.c11 = r8[3];
+                    const EofField f = bfe_eof_eval<MCAP>(g, G, gstride, b, r8[4], r8[5]);
+                    double2* o = tmp + 3 * ((int64_t)cbase + lane);
+                    o[0] = make_double2(f.p0, f.p);
+                    o[1] = make_double2(f.fr, f.fp);
+                    o[2] = make_double2(f.fz, 0.0);
+                }
+                __syncwarp();
+                if (lane == 0) issue(par);
+                continue;
+            }
+        }
         const double* sb = &s_buf[warp][par][row * 8];
-        const int ccnt = (cnt - ch * CHUNK) < CHUNK ? (cnt - ch * CHUNK) : CHUNK;
+        double2* dst = tmp + 3 * ((int64_t)cbase + row) + jj;
 #pragma unroll 1
         for (int gi = 0; gi < CHUNK / 8; ++gi) {
             if (gi * 8 >= ccnt) break;                                // warp-uniform
@@ -574,14 +679,17 @@ eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride
             }
             dst += 24;
         }
-        dst += 24 * (CHUNK / 8 - (ccnt + 7) / 8);                     // (only the last chunk can be short)
         __syncwarp();                                                 // every lane is done reading this buffer
-        if (lane == 0 && ch + 2 < nchunk) {
-            const int c = ch + 2;
-            const unsigned int bytes = (unsigned int)(((cnt - c * CHUNK) < CHUNK ? (cnt - c * CHUNK) : CHUNK) * 64);
-            bfe_mbar_expect_tx(par ? bar1 : bar0, bytes);
-            bfe_bulk_g2s(par ? buf1 : buf0, rec + lo + (int64_t)c * CHUNK, bytes, par ? bar1 : bar0);
-        }
+        if (lane == 0) issue(par);
+    }
+    // the last CTA to finish re-arms the ticket counter
+    BFE_TRACE_PT(5, 1);
+    __syncthreads();
+    BFE_TRACE_PT(5, 2);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) { counter[0] = 0u; counter[1] = 0u; }
     }
 }
 
@@ -590,11 +698,13 @@ eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __
                         const double2* __restrict__ tmp, double* __restrict__ p0, double* __restrict__ p,
                         double* __restrict__ fr, double* __restrict__ fp, double* __restrict__ fz,
                         double* __restrict__ R) {
+    BFE_TRACE_PT(6, 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double2* src = tmp + 3 * (int64_t)__ldg(inv + i);
         const double2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
         p0[i] = a.x; p[i] = a.y; fr[i] = b.x; fp[i] = b.y; fz[i] = c.x; R[i] = __ldg(r_orig + i);
     }
+    BFE_TRACE_PT(6, 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -664,7 +774,8 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
     if (g2 < 1) g2 = 1;
     const int kt2 = bfe_kt_begin("eof_cell_scatter_kernel", stream);
-    eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cursor, ws.rec, ws.inv, ws.r_orig);
+    eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cell_start, ws.cursor, ws.rec, ws.inv,
+                                                    ws.r_orig);
     bfe_kt_end(kt2, stream);
     BFE_LAUNCH_CHECK("eof_cell_scatter_kernel");
     h->prepared_n = n;
@@ -693,8 +804,9 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
     }
     {
         int grid = (ncell + 7) / 8;
-        if (grid > h->num_sms * 2) grid = h->num_sms * 2;
+        if (grid > h->num_sms * 2) grid = h->num_sms * 2;      // <= 64 reduce groups of 16 CTAs
         if (grid > h->max_ctas) grid = h->max_ctas;
+        if (grid > 64 * 16) grid = 64 * 16;
         const int kt = bfe_kt_begin("eof_node_contract_kernel", stream);
         eof_node_contract_kernel<<<grid, 256, 0, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, ncell, ws.cell_start, ws.seg,
                                                          h->partial, h->counter, cos_out, sin_out);
@@ -719,11 +831,11 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
     int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
     if (g_bfe_force_mma) {
-        // one resident wave: 6 CTAs of 4 warps per SM (78 registers, 17.5 kB of record buffers each)
-        int64_t need_m = (n + 127) / 128, cap_m = (int64_t)h->num_sms * 6;
+        // one resident wave: 5 CTAs of 4 warps per SM (88 registers, 17.5 kB of record buffers each)
+        int64_t need_m = (n + 511) / 512, cap_m = (int64_t)h->num_sms * 5;
         grid = (int)(need_m < cap_m ? need_m : cap_m);
         const int kt = bfe_kt_begin("eof_force_sorted_mma_kernel", stream);
-        eof_force_sorted_mma_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
+        eof_force_sorted_mma_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp, h->counter);
         bfe_kt_end(kt, stream);
         BFE_LAUNCH_CHECK("eof_force_sorted_mma_kernel");
     } else {

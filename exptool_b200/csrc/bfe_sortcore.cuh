@@ -3,9 +3,14 @@
 // MMA, TMA bulk copy + mbarrier helpers.
 #pragma once
 #include "bfe_device.cuh"
+#ifndef BFE_TRACE_PT
+#define BFE_TRACE_PT(kid, phase)
+#endif
 
-// Slot-claim cursors live one per 32-byte L2 sector: same-sector atomics serialise in the L2 (hot cells of a
+// Slot-claim counters live one per 32-byte L2 sector: same-sector atomics serialise in the L2 (hot cells of a
 // disc / cusp sit next to each other in the bin order), ncu + A/B timing in profiles/r01_summary.md section 11.
+// They are zeroed by all CTAs of the histogram kernel (a slice each): 8192 one-sector stores from the single
+// scanning CTA cost 4 us of serial tail (device timeline, profiles/trace_step.py).
 #define BFE_CURSOR_STRIDE 8
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256), 32-byte aligned addresses: one full sector per lane
@@ -16,10 +21,10 @@ __device__ __forceinline__ void bfe_ld256_nc(const void* p, double& a, double& b
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
-// exclusive scan of the histogram by one 1024-thread CTA: cell_start, cursor = scan; hist cleared.
+// exclusive scan of the histogram by one 1024-thread CTA: cell_start = scan; hist cleared.
 // Bins are staged through shared memory (s_h, per*1024 ints) with coalesced loads; two levels of warp shuffles.
 __device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict__ hist, int* __restrict__ cell_start,
-                                                     int* __restrict__ cursor, int* s_h, int* s_wsum) {
+                                                     int* s_h, int* s_wsum) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (ncell + 1023) / 1024;
     // eight independent L2 loads in flight per thread (one load at a time costs `per` L2 round trips: ncu showed
@@ -36,6 +41,7 @@ __device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict_
         }
     }
     __syncthreads();
+    BFE_TRACE_PT(0, 8);
     const int lo = tid * per;
     int sum = 0;
     for (int k = 0; k < per; ++k) sum += s_h[lo + k];
@@ -44,6 +50,7 @@ __device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict_
     for (int off = 1; off < 32; off <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
+    BFE_TRACE_PT(0, 9);
     if (warp == 0) {
         int w = s_wsum[lane];
 #pragma unroll
@@ -52,9 +59,11 @@ __device__ __forceinline__ void bfe_block_scan_cells(int ncell, int* __restrict_
     }
     __syncthreads();
     int run = incl - sum + (warp > 0 ? s_wsum[warp - 1] : 0);    // exclusive prefix of this thread's segment
+    BFE_TRACE_PT(0, 10);
     for (int k = 0; k < per; ++k) { int h = s_h[lo + k]; s_h[lo + k] = run; run += h; }
     __syncthreads();
-    for (int c = tid; c < ncell; c += 1024) { int v = s_h[c]; cell_start[c] = v; cursor[(size_t)c * BFE_CURSOR_STRIDE] = v; }
+    BFE_TRACE_PT(0, 11);
+    for (int c = tid; c < ncell; c += 1024) cell_start[c] = s_h[c];
     if (tid == 1023) cell_start[ncell] = run;
 }
 
