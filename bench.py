@@ -368,8 +368,7 @@ def run_gpu(args):
         else:
             # weak scaling: this rank's own 10^6 particles; partial coefficients summed with one allreduce
             Eh = beof.device_tables(*tabs_acc)
-            cd, sd = parallel.eof_accumulate_sharded(Eh, hx, hy, hz, hm, already_sharded=True)
-            c, s = cd.cpu().numpy(), sd.cpu().numpy()
+            c, s = parallel.eof_accumulate_host(Eh, hx, hy, hz, hm, already_sharded=True)
         return beof.accumulated_eval_particles(P, c, s, potC=T['potC'], rforceC=T['rforceC'], zforceC=T['zforceC'],
                                                potS=T['potS'], rforceS=T['rforceS'], zforceS=T['zforceS'],
                                                rmin=g['XMIN'], dR=g['dX'], zmin=g['YMIN'], dZ=g['dY'], numx=g['numx'],
@@ -390,8 +389,9 @@ def run_gpu(args):
     e2e_value = world * N_PART * args.steps / float(te.item())
     e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * 32 * N_PART - 8 * N_PART,
            'd2h_bytes_per_step': 48 * N_PART + 2 * 8 * 126, 'ms_per_step': 1e3 * float(te.item()) / args.steps,
-           'api': ('eof.make_coefficients_multi' if world == 1 else 'parallel.eof_accumulate_sharded') +
-                  ' + eof.accumulated_eval_particles, pinned host tensors in, NumPy arrays out'}
+           'api': ('eof.make_coefficients_multi' if world == 1 else 'parallel.eof_accumulate_host') +
+                  ' + eof.accumulated_eval_particles, pinned host tensors in, NumPy arrays out; chunked '
+                  'H2D | kernels | D2H pipeline on three streams inside each call'}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -46,6 +46,8 @@ SIGNATURES = {
     'bfe_eof_prepare': (_INT, [_P, _I64] + [_P] * 4 + [_P]),
     'bfe_eof_accumulate_prepared': (_INT, [_P, _P, _P, _P]),
     'bfe_eof_force_prepared': (_INT, [_P] + [_P] * 6 + [_P]),
+    'bfe_eof_accumulate_host': (_INT, [_P, _I64] + [_P] * 4 + [_P, _P, _P]),
+    'bfe_eof_force_host': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_eof_contract': (_INT, [_P, _P, _P, _INT, _INT, _INT, _INT, _P]),
     'bfe_eof_force_contracted': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_eof_force': (_INT, [_P, _I64] + [_P] * 3 + [_P, _P, _INT, _INT, _INT, _INT] + [_P] * 6 + [_P]),

@@ -167,8 +167,7 @@ def accumulate(ParticleInstance, potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUM
         raise NotImplementedError('eof.accumulate: VAR sub-sampling is outside the B200 hot path')
     x, y, z, m = particle.particle_arrays(ParticleInstance)
     E = device_tables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP)
-    c, s = E.accumulate(x, y, z, m)
-    return c.cpu().numpy(), s.cpu().numpy()
+    return E.accumulate_host(x, y, z, m)
 
 
 def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy,
@@ -186,12 +185,12 @@ def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, 
     from .. import parallel
     x, y, z, m = particle.particle_arrays(ParticleInstance)
     E = device_tables(potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap)
-    c, s = parallel.eof_accumulate_sharded(E, x, y, z, m)
+    c, s = parallel.eof_accumulate_host(E, x, y, z, m)
     if verbose:
         dt = time.time() - t1
         print('eof.make_coefficients_multi: Accumulation took {0:3.2f} seconds, or {1:4.2f} microseconds per orbit.'
               .format(dt, 1.e6 * dt / max(len(x), 1)))
-    return c.cpu().numpy(), s.cpu().numpy()
+    return c, s
 
 
 class EOF_Object(object):
@@ -294,7 +293,7 @@ def accumulated_eval_particles(Particles, accum_cos, accum_sin, potC=0, rforceC=
     E = device_tables(potC, potS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
                       rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
     E.contract(accum_cos, accum_sin, m1=m1, m2=m2)
-    p0, p, fr, fp, fz, R = ops.to_host(E.force(x, y, z))
+    p0, p, fr, fp, fz, R = E.force_host(x, y, z)
     return p0, p, fr, fp, fz, R
 
 

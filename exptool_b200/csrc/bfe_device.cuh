@@ -5,6 +5,11 @@
 #pragma once
 #include "bfe_internal.h"
 
+// programmatic dependent launch (see bfe_launch, bfe_internal.h): no-ops when the kernel was launched without
+// the attribute.  bfe_pdl_wait() must precede the first global-memory access of a kernel of the chain.
+__device__ __forceinline__ void bfe_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void bfe_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #define BFE_FOURPI_NEG (-12.566370614359172953850573533118)
 #define BFE_TWOPI      (6.283185307179586476925286766559)
 

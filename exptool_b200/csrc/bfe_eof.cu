@@ -160,6 +160,8 @@ __global__ void eof_contract_kernel(EofGeom g, const double* __restrict__ t_forc
                                     double* __restrict__ G, int gstride) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y / 6, q = blockIdx.y % 6;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     if (node >= g.nnode) return;
     const int field = q >> 1, trig = q & 1;
     double s = 0.0;
@@ -316,6 +318,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     h->gstride = 6 * (p->mmax + 1);
     h->contracted = 0;
     h->sort_cap = 0; h->sort_ws = nullptr; h->prepared_n = -1; h->prepared_has_mass = 0;
+    h->host_pipe = nullptr;
     h->max_ctas = h->num_sms * 4;
     BFE_CUDA(cudaMalloc(&h->t_acc, (size_t)g.nnode * h->nch_pad * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
@@ -344,6 +347,7 @@ extern "C" void bfe_eof_destroy(bfe_eof* h) {
     cudaFree(h->t_acc); cudaFree(h->g_con); cudaFree(h->g4); cudaFree(h->partial); cudaFree(h->counter);
     if (h->t_force) cudaFree(h->t_force);
     if (h->sort_ws) cudaFree(h->sort_ws);
+    bfe_host_pipe_destroy(h->host_pipe);
     delete h;
 }
 
@@ -381,8 +385,8 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
     if (nuse < 0) nuse = 0;
     dim3 grd((h->g.nnode + 127) / 128, (h->g.mmax + 1) * 6);
     const int kt = bfe_kt_begin("eof_contract_kernel", stream);
-    eof_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->t_force, h->tab_elems, cosc, sinc, m1, m2, nuse, no_odd,
-                                                 h->g_con, h->gstride);
+    BFE_CUDA(bfe_launch(eof_contract_kernel, grd, dim3(128), 0, stream, h->t_force, 6 * h->tab_elems * sizeof(double),
+                        h->g, h->t_force, h->tab_elems, cosc, sinc, m1, m2, nuse, no_odd, h->g_con, h->gstride));
     bfe_kt_end(kt, stream);
     BFE_LAUNCH_CHECK("eof_contract_kernel");
     h->contracted = 1;

@@ -216,6 +216,25 @@ int g_bfe_sl_accumulate_mode = 0;
 int g_bfe_staged_eval = 1;
 int g_bfe_force_mma = 1;
 static int g_bfe_time_kernels = 0;
+int g_bfe_pdl = 1;
+int g_bfe_l2_persist = 0;
+size_t g_bfe_l2_window_max = 0;
+
+// persisting-L2 set-aside for the table windows (device-wide limit, set once per process and device)
+int bfe_l2_persist_setup(size_t want_bytes) {
+    static int done_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return BFE_ERR_CUDA;
+    if (done_dev == dev) return BFE_OK;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return BFE_ERR_CUDA;
+    size_t cap = (size_t)prop.persistingL2CacheMaxSize;
+    g_bfe_l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    size_t sz = want_bytes < cap ? want_bytes : cap;
+    if (sz > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, sz) != cudaSuccess) { cudaGetLastError(); return BFE_ERR_CUDA; }
+    done_dev = dev;
+    return BFE_OK;
+}
 
 extern "C" int bfe_set_option(const char* name, int value) {
     if (!name) return BFE_ERR_ARG;
@@ -224,6 +243,13 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "time_kernels")) { g_bfe_time_kernels = value; return BFE_OK; }
     if (!strcmp(name, "staged_eval")) { g_bfe_staged_eval = value; return BFE_OK; }
     if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
+    if (!strcmp(name, "pdl")) { g_bfe_pdl = value; return BFE_OK; }
+    if (!strcmp(name, "host_chunk")) { g_bfe_host_chunk = value; return BFE_OK; }
+    if (!strcmp(name, "l2_persist")) {
+        g_bfe_l2_persist = value;
+        if (value > 0) return bfe_l2_persist_setup((size_t)96 << 20);
+        return BFE_OK;
+    }
     if (!strcmp(name, "sl_accumulate_mode")) { g_bfe_sl_accumulate_mode = value; return BFE_OK; }
     if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
     return BFE_ERR_ARG;

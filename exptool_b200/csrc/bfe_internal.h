@@ -49,6 +49,7 @@ struct bfe_eof {
     void* sort_ws;
     int64_t prepared_n;      // particles currently held cell-sorted in sort_ws (-1: none)
     int prepared_has_mass;
+    void* host_pipe;         // staging buffers / streams of the host-array entry points (bfe_host.cu), lazily made
 };
 
 struct bfe_sl {
@@ -102,6 +103,44 @@ extern int g_bfe_staged_eval;                               // option "staged_ev
 // duration of every kernel of the step with bfe_kernel_time_ms().  Off by default (no events recorded).
 int bfe_kt_begin(const char* name, cudaStream_t stream);     // returns a slot or -1 when disabled
 void bfe_kt_end(int slot, cudaStream_t stream);
+
+// Launch helper of the cell-sorted step (bfe_sort.cu, eof_contract_kernel).
+//  * option "pdl" (default 1): programmatic dependent launch -- the next kernel of the stream is scheduled while
+//    this one drains and runs its prologue up to bfe_pdl_wait() (griddepcontrol.wait), which returns once every
+//    earlier kernel of the chain has completed and flushed.  Removes the ~4 us launch gap at each of the seven
+//    kernel boundaries of a step (device timeline, profiles/trace_step.py).
+//  * option "l2_persist" (default 0/1 see bfe_field.cu): an access-policy window marks a table (t_force, t_acc,
+//    g_con) persisting in the L2 set-aside so the 80 MB/step particle stream does not evict it.
+void bfe_host_pipe_destroy(void* pipe);
+extern int g_bfe_host_chunk;                               // option "host_chunk"
+extern int g_bfe_pdl;
+extern int g_bfe_l2_persist;
+extern size_t g_bfe_l2_window_max;                         // cudaDeviceProp::accessPolicyMaxWindowSize
+template <typename... KArgs, typename... Args>
+inline cudaError_t bfe_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              const void* win_ptr, size_t win_bytes, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    unsigned int na = 0;
+    if (g_bfe_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (g_bfe_l2_persist > 0 && g_bfe_l2_window_max > 0 && win_ptr && win_bytes) {
+        at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(win_ptr);
+        at[na].val.accessPolicyWindow.num_bytes = win_bytes < g_bfe_l2_window_max ? win_bytes : g_bfe_l2_window_max;
+        at[na].val.accessPolicyWindow.hitRatio = 1.0f;
+        at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+int bfe_l2_persist_setup(size_t want_bytes);                // sets cudaLimitPersistingL2CacheSize once (device-wide)
 
 #define BFE_CUDA(call)                                                  \
     do {                                                                \

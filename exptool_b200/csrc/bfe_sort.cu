@@ -79,6 +79,8 @@ eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__
     __shared__ bool s_last;
     BFE_TRACE_PT(0, 0);
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
+    bfe_pdl_wait();                               // everything above overlaps the previous kernel's tail
+    bfe_pdl_trigger();
     // this CTA's slice of the slot-claim counters (used by the scatter kernel) is cleared here, in parallel
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x)
         cursor[(size_t)c * BFE_CURSOR_STRIDE] = 0;
@@ -141,6 +143,8 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
     // fractions, weights and cos/sin phi WHILE the claims are in flight (they were 1/3 of this kernel's stall
     // samples when issued after the FP64 arithmetic, ncu profiles/), (5) the record stores.
     constexpr int U = 2;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     BFE_TRACE_PT(1, 0);
     for (int64_t base = (int64_t)blockIdx.x * (256 * U); base < n; base += (int64_t)gridDim.x * (256 * U)) {
         double px[U], py[U], pz[U], aux[U];
@@ -225,6 +229,8 @@ eof_segsum_kernel(int64_t n, const EofRec* __restrict__ rec, double* __restrict_
     const double* brow = val + (7 + fg) * RS;     // B[.][col fg] (col 0 is the constant 1)
     unsigned int* task_counter = counter + 1;
     const int64_t ntasks = (n + TASK - 1) / TASK;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     BFE_TRACE_PT(2, 0);
     for (;;) {
         int64_t task = 0;
@@ -350,6 +356,8 @@ eof_node_contract_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, i
     const double* tcol = t_acc + (tid < nch ? tid : 0);
     double acc = 0.0;
     const int nblk = (ncell + CB - 1) / CB;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     BFE_TRACE_PT(3, 0);
     for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         // The CB cells of a block are nblk apart (same iy, ix 16 apart for the 128 x 64 table): consecutive cells
@@ -477,6 +485,8 @@ eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, in
     // each CTA takes one contiguous slice of the sorted records: an SM then sees a contiguous range
     // of cells and the contracted-grid rows stay in its L1
     const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 127) / 128 * 128;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     const int64_t lo = (int64_t)blockIdx.x * per;
     const int64_t hi = (lo + per) < n ? (lo + per) : n;
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -559,6 +569,10 @@ eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride
         bfe_mbar_init(bar0, 1);
         bfe_mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    if (lane == 0) {
         issue(0);
         issue(1);
     }
@@ -698,6 +712,8 @@ eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __
                         const double2* __restrict__ tmp, double* __restrict__ p0, double* __restrict__ p,
                         double* __restrict__ fr, double* __restrict__ fp, double* __restrict__ fz,
                         double* __restrict__ R) {
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     BFE_TRACE_PT(6, 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double2* src = tmp + 3 * (int64_t)__ldg(inv + i);
@@ -765,8 +781,8 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
         if (ss > 48 * 1024)
             BFE_CUDA(cudaFuncSetAttribute(eof_cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
         const int kt = bfe_kt_begin("eof_cell_hist_kernel", stream);
-        eof_cell_hist_kernel<<<grid, 1024, ss, stream>>>(h->g, ncell, n, x, y, z, ws.hist, ws.cell_start, ws.cursor,
-                                                        h->counter);
+        BFE_CUDA(bfe_launch(eof_cell_hist_kernel, dim3(grid), dim3(1024), ss, stream, nullptr, 0, h->g, ncell, n, x, y, z,
+                            ws.hist, ws.cell_start, ws.cursor, h->counter));
         bfe_kt_end(kt, stream);
     }
     BFE_LAUNCH_CHECK("eof_cell_hist_kernel");
@@ -774,8 +790,8 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
     if (g2 < 1) g2 = 1;
     const int kt2 = bfe_kt_begin("eof_cell_scatter_kernel", stream);
-    eof_cell_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, n, x, y, z, mass, ws.cell_start, ws.cursor, ws.rec, ws.inv,
-                                                    ws.r_orig);
+    BFE_CUDA(bfe_launch(eof_cell_scatter_kernel, dim3(g2), dim3(256), 0, stream, nullptr, 0, h->g, n, x, y, z, mass,
+                        ws.cell_start, ws.cursor, ws.rec, ws.inv, ws.r_orig));
     bfe_kt_end(kt2, stream);
     BFE_LAUNCH_CHECK("eof_cell_scatter_kernel");
     h->prepared_n = n;
@@ -798,7 +814,7 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
         int grid = (int)(nblk < (int64_t)h->num_sms * 4 ? nblk : (int64_t)h->num_sms * 4);
         if (grid < 1) grid = 1;
         const int kt = bfe_kt_begin("eof_segsum_kernel", stream);
-        eof_segsum_kernel<<<grid, 256, 0, stream>>>(n, ws.rec, ws.seg, h->counter);
+        BFE_CUDA(bfe_launch(eof_segsum_kernel, dim3(grid), dim3(256), 0, stream, nullptr, 0, n, ws.rec, ws.seg, h->counter));
         bfe_kt_end(kt, stream);
         BFE_LAUNCH_CHECK("eof_segsum_kernel");
     }
@@ -808,8 +824,9 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
         if (grid > h->max_ctas) grid = h->max_ctas;
         if (grid > 64 * 16) grid = 64 * 16;
         const int kt = bfe_kt_begin("eof_node_contract_kernel", stream);
-        eof_node_contract_kernel<<<grid, 256, 0, stream>>>(h->g, h->t_acc, h->nch, h->nch_pad, ncell, ws.cell_start, ws.seg,
-                                                         h->partial, h->counter, cos_out, sin_out);
+        BFE_CUDA(bfe_launch(eof_node_contract_kernel, dim3(grid), dim3(256), 0, stream, h->t_acc,
+                            (size_t)h->g.nnode * h->nch_pad * sizeof(double), h->g, h->t_acc, h->nch, h->nch_pad, ncell,
+                            ws.cell_start, ws.seg, h->partial, h->counter, cos_out, sin_out));
         bfe_kt_end(kt, stream);
     }
     BFE_LAUNCH_CHECK("eof_node_contract_kernel");
@@ -835,19 +852,22 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
         int64_t need_m = (n + 511) / 512, cap_m = (int64_t)h->num_sms * 5;
         grid = (int)(need_m < cap_m ? need_m : cap_m);
         const int kt = bfe_kt_begin("eof_force_sorted_mma_kernel", stream);
-        eof_force_sorted_mma_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp, h->counter);
+        BFE_CUDA(bfe_launch(eof_force_sorted_mma_kernel<6>, dim3(grid), dim3(128), 0, stream, h->g_con,
+                            (size_t)h->g.nnode * h->gstride * sizeof(double), h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp,
+                            h->counter));
         bfe_kt_end(kt, stream);
         BFE_LAUNCH_CHECK("eof_force_sorted_mma_kernel");
     } else {
         const int kt = bfe_kt_begin("eof_force_sorted_kernel", stream);
-        eof_force_sorted_kernel<6><<<grid, 128, 0, stream>>>(h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp);
+        BFE_CUDA(bfe_launch(eof_force_sorted_kernel<6>, dim3(grid), dim3(128), 0, stream, h->g_con,
+                            (size_t)h->g.nnode * h->gstride * sizeof(double), h->g, h->g_con, h->gstride, n, ws.rec, ws.tmp));
         bfe_kt_end(kt, stream);
         BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
     }
     int64_t need2 = (n + 255) / 256, cap2 = (int64_t)h->num_sms * 8;
     const int kt3 = bfe_kt_begin("eof_force_gather_kernel", stream);
-    eof_force_gather_kernel<<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, stream>>>(n, ws.inv, ws.r_orig, ws.tmp, p0, p,
-                                                                                  fr, fp, fz, R);
+    BFE_CUDA(bfe_launch(eof_force_gather_kernel, dim3((int)(need2 < cap2 ? need2 : cap2)), dim3(256), 0, stream, nullptr, 0,
+                        n, ws.inv, ws.r_orig, ws.tmp, p0, p, fr, fp, fz, R));
     bfe_kt_end(kt3, stream);
     BFE_LAUNCH_CHECK("eof_force_gather_kernel");
     return BFE_OK;

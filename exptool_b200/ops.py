@@ -162,6 +162,45 @@ class EOFTables(object):
                                                      *[_ptr(out[i]) for i in range(6)], _stream()))
         return out
 
+    # -- host-array entry points (chunked copy / compute pipeline inside libbfe, bfe_host.cu)
+    def accumulate_host(self, x, y, z, m, reduce=None):
+        """
+        eof.accumulate for HOST particle arrays -> (cos, sin) NumPy (mmax+1, norder).  `reduce`, if given, is
+        applied to the (2, mmax+1, norder) device tensor before it is copied out (multi-GPU allreduce).
+        Device tensors are accepted too (one-shot path).
+        """
+        hx, hy, hz, hm = [_host_tensor(a) for a in (x, y, z, m)]
+        n = hx.numel()
+        if not (hy.numel() == n and hz.numel() == n and hm.numel() == n):
+            raise ValueError('particle arrays differ in length')
+        buf = torch.empty((2, self.mmax + 1, self.norder), dtype=torch.float64, device=self.device)
+        if hx.is_cuda:
+            dx, dy, dz, dm = dev(hx), dev(hy), dev(hz), dev(hm)
+            _lib.check(self.lib.bfe_eof_accumulate(self.h, n, _ptr(dx), _ptr(dy), _ptr(dz), _ptr(dm),
+                                                   _ptr(buf[0]), _ptr(buf[1]), _stream()))
+        else:
+            _lib.check(self.lib.bfe_eof_accumulate_host(self.h, n, _ptr(hx), _ptr(hy), _ptr(hz), _ptr(hm),
+                                                        _ptr(buf[0]), _ptr(buf[1]), _stream()))
+        if reduce is not None:
+            reduce(buf)
+        h = to_host(buf)               # synchronises the stream: the host inputs may be released after this
+        return h[0], h[1]
+
+    def force_host(self, x, y, z):
+        """
+        eof.accumulated_eval_particles for HOST particle arrays -> (6, n) NumPy array p0, p, fr, fp, fz, R
+        (uses the held contraction).  The result lives in pinned memory from torch's caching host allocator.
+        """
+        hx, hy, hz = [_host_tensor(a) for a in (x, y, z)]
+        n = hx.numel()
+        if hx.is_cuda:
+            return to_host(self.force(hx, hy, hz))
+        h = pinned_empty((6, n))
+        _lib.check(self.lib.bfe_eof_force_host(self.h, n, _ptr(hx), _ptr(hy), _ptr(hz),
+                                               *[_ptr(h[i]) for i in range(6)], _stream()))
+        torch.cuda.current_stream().synchronize()
+        return h.numpy()
+
     def force_eval_points(self, r, z, phi):
         """eof.force_eval outputs fr, fp, fz, p (incl. m=0), p0 at cylindrical points."""
         r, z, phi = dev(r), dev(z), dev(phi)
@@ -170,6 +209,25 @@ class EOFTables(object):
         _lib.check(self.lib.bfe_eof_force_eval_points(self.h, n, _ptr(r), _ptr(z), _ptr(phi),
                                                       *[_ptr(out[i]) for i in range(5)], _stream()))
         return out
+
+
+# ---------------------------------------------------------------------------
+# host-array helpers (the reference-facing API takes and returns HOST arrays; the chunked
+# H2D | kernels | D2H pipeline itself lives in libbfe: bfe_eof_accumulate_host / bfe_eof_force_host)
+# ---------------------------------------------------------------------------
+def _host_tensor(a):
+    """FP64 contiguous tensor view of ndarray / tensor (copy only if dtype/layout requires)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+        if t.dtype != torch.float64 or not t.is_contiguous():
+            t = t.to(torch.float64).contiguous()
+        return t
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+
+
+def pinned_empty(shape, dtype=torch.float64):
+    """Pinned host tensor from torch's caching host allocator (first use pays cudaHostAlloc, later ones are free)."""
+    return torch.empty(shape, dtype=dtype, device='cpu', pin_memory=True)
 
 
 class SLTables(object):

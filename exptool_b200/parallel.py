@@ -95,6 +95,18 @@ def eof_accumulate_sharded(E, x, y, z, m, already_sharded=False):
     return c, s
 
 
+def eof_accumulate_host(E, x, y, z, m, already_sharded=False):
+    """
+    eof_accumulate_sharded for HOST particle arrays, returning NumPy (cos, sin): this rank's block goes through
+    the chunked copy/compute pipeline (ops.EOFTables.accumulate_host) and the allreduce runs on the device
+    before the single small copy out.
+    """
+    if is_distributed() and not already_sharded:
+        lo, hi = my_shard(len(x))
+        x, y, z, m = _slice(x, lo, hi), _slice(y, lo, hi), _slice(z, lo, hi), _slice(m, lo, hi)
+    return E.accumulate_host(x, y, z, m, reduce=allreduce_sum_ if is_distributed() else None)
+
+
 def sl_accumulate_sharded(H, x, y, z, m, no_odd=False, already_sharded=False):
     """SL coefficients of the global particle set (see eof_accumulate_sharded)."""
     if is_distributed() and not already_sharded:

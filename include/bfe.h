@@ -97,6 +97,21 @@ int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* sin_out, vo
 int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double* fr, double* fp, double* fz, double* R,
                            void* stream);
 
+/* Host-array entry points: the same two passes for particle arrays in HOST memory (what the reference's Python
+ * functions receive and return: eof.accumulate eof.py:492, eof.accumulated_eval_particles eof.py:989).  The set is
+ * cut into chunks and copy-in, kernels and copy-out run as a three-stage pipeline on internal streams (pinned
+ * host memory gives asynchronous DMA; pageable memory is accepted and copies synchronously).
+ *   bfe_eof_accumulate_host: hx..hm host arrays of n doubles; cos_out / sin_out are DEVICE buffers (so a
+ *       multi-GPU caller can allreduce before copying 2 kB out), complete in stream order.
+ *   bfe_eof_force_host: hx, hy, hz host inputs; hp0..hR host outputs of n doubles each, complete once `stream`
+ *       has been synchronised.  Uses the held contraction (bfe_eof_contract). */
+int bfe_eof_accumulate_host(bfe_eof* h, int64_t n,
+                            const double* hx, const double* hy, const double* hz, const double* hm,
+                            double* cos_out, double* sin_out, void* stream);
+int bfe_eof_force_host(bfe_eof* h, int64_t n,
+                       const double* hx, const double* hy, const double* hz,
+                       double* hp0, double* hp, double* hfr, double* hfp, double* hfz, double* hR, void* stream);
+
 /* Contract the tables with a coefficient set:  G_f[m,trig,node] = sum_{n<nuse} coef[m,n] T_f[m,n,node]
  * for m1 <= m <= min(m2, muse), skipping odd m if no_odd.  Must precede the *_contracted calls,
  * bfe_field_force_cart and bfe_leapfrog.  cosc/sinc: (mmax+1)*norder doubles. */

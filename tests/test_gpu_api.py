@@ -251,3 +251,39 @@ def test_frozen_field_timestep_and_grids(api, name):
         assert g3.shape == d['grid3'].shape
         for k in range(9):
             assert relerr(g3[..., k, :], d['grid3'][..., k, :]) < ORBIT_TOL, k
+
+
+def test_eof_host_pipeline_matches_device(api):
+    """The chunked H2D | kernels | D2H pipeline behind the host-array API (ops.EOFTables.accumulate_host /
+    force_host, used by eof.make_coefficients_multi and eof.accumulated_eval_particles for large sets) gives
+    the results of the one-shot device path, for pinned tensors and for plain NumPy inputs, ragged last chunk."""
+    import torch
+    from exptool_b200 import ops
+    eof = api['eof']
+    d, meta = load_golden('eof_std_smooth')
+    from helpers import eof_tables, eof_geo_args
+    pe, T, g = eof_tables(meta)
+    n = 3 * 131072 + 1234
+    x, y, z, m = S.exponential_disc(n, 97)
+    tabs = (T['potC'], T['potS'], g['mmax'], g['norder']) + eof_geo_args(g) + (g['ascale'], g['hscale'], g['cmap'])
+    E = eof.device_tables(*tabs, rforceC=T['rforceC'], zforceC=T['zforceC'], rforceS=T['rforceS'], zforceS=T['zforceS'])
+    cd, sd = E.accumulate(x, y, z, m)
+    cd, sd = cd.cpu().numpy(), sd.cpu().numpy()
+    c1, s1 = eof.make_coefficients_multi((x, y, z, m), 1, *tabs)
+    pin = tuple(torch.from_numpy(a).pin_memory() for a in (x, y, z, m))
+    c2, s2 = eof.make_coefficients_multi(pin, 1, *tabs)
+    for c, s in ((c1, s1), (c2, s2)):
+        assert isinstance(c, np.ndarray) and c.shape == cd.shape
+        assert relerr(c, cd) < 1e-13 and relerr(s, sd) < 1e-13
+    E.contract(cd, sd)
+    ref = E.force(x, y, z).cpu().numpy()
+    kw = dict(potC=T['potC'], rforceC=T['rforceC'], zforceC=T['zforceC'], potS=T['potS'], rforceS=T['rforceS'],
+              zforceS=T['zforceS'], rmin=g['XMIN'], dR=g['dX'], zmin=g['YMIN'], dZ=g['dY'], numx=g['numx'],
+              numy=g['numy'], MMAX=g['mmax'], NMAX=g['norder'], ASCALE=g['ascale'], HSCALE=g['hscale'],
+              CMAP=g['cmap'], verbose=0)
+    for P in ((x, y, z, m), pin):
+        out = eof.accumulated_eval_particles(P, cd, sd, **kw)
+        assert len(out) == 6
+        for k in range(6):
+            assert isinstance(out[k], np.ndarray) and out[k].shape == (n,)
+            assert relerr(out[k], ref[k]) < 1e-13
