@@ -232,29 +232,53 @@ def run_gpu(args):
         x, y, z, m = S.exponential_disc(N_PART, 2002 + 100 * rank + k)
         sets.append(tuple(ops.dev(a) for a in (x, y, z, m)))
     outs = [torch.empty((6, N_PART), dtype=torch.float64, device=dev) for _ in range(NSETS)]
-    coefbuf = torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev)
     lib = E.lib
     from exptool_b200.ops import _ptr, _stream
     from exptool_b200 import _lib as L
+    import ctypes as C
+    # Steps are independent particle sets (snapshots of a series), so NSTREAMS of them are kept in flight: each
+    # stream has its own handle clone (shared device tables; own contraction, sorted-set workspace and counters)
+    # and its own coefficient buffer.  A step is still prepare -> accumulate -> [allreduce] -> contract -> force
+    # on ONE stream; the second stream fills the launch gaps, tails and latency-bound phases of the first
+    # (profiles/dual_stream.py: 1 stream 174 us/step, 2 streams 138, 3 streams 133).
+    NSTREAMS = max(1, args.streams)
+    Es = [E] + [E.clone() for _ in range(NSTREAMS - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
+    coefbufs = [torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev) for _ in range(NSTREAMS)]
+    coefbuf = coefbufs[0]
 
-    def step(k):
+    def step_on(k, Ei, coef, torch_stream):
         # one cell sort of the particle set serves both passes (include/bfe.h: bfe_eof_prepare)
         x, y, z, m = sets[k % NSETS]
         o = outs[k % NSETS]
-        L.check(lib.bfe_eof_prepare(E.h, N_PART, _ptr(x), _ptr(y), _ptr(z), _ptr(m), _stream()))
-        L.check(lib.bfe_eof_accumulate_prepared(E.h, _ptr(coefbuf[0]), _ptr(coefbuf[1]), _stream()))
+        st = C.c_void_p(torch_stream.cuda_stream)
+        L.check(lib.bfe_eof_prepare(Ei.h, N_PART, _ptr(x), _ptr(y), _ptr(z), _ptr(m), st))
+        L.check(lib.bfe_eof_accumulate_prepared(Ei.h, _ptr(coef[0]), _ptr(coef[1]), st))
         if world > 1:
-            dist.all_reduce(coefbuf)
-        L.check(lib.bfe_eof_contract(E.h, _ptr(coefbuf[0]), _ptr(coefbuf[1]), 0, g['mmax'], g['norder'], 0, _stream()))
-        L.check(lib.bfe_eof_force_prepared(E.h, *[_ptr(o[i]) for i in range(6)], _stream()))
+            with torch.cuda.stream(torch_stream):
+                dist.all_reduce(coef)
+        L.check(lib.bfe_eof_contract(Ei.h, _ptr(coef[0]), _ptr(coef[1]), 0, g['mmax'], g['norder'], 0, st))
+        L.check(lib.bfe_eof_force_prepared(Ei.h, *[_ptr(o[i]) for i in range(6)], st))
+
+    def step(k):                                   # single-stream step on the current stream (kernel timing legs)
+        step_on(k, E, coefbuf, torch.cuda.current_stream())
+
+    def run_steps(k0, nsteps):
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
+        for k in range(k0, k0 + nsteps):
+            i = k % NSTREAMS
+            step_on(k, Es[i], coefbufs[i], streams[i])
+        for st in streams:
+            cur.wait_stream(st)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        step(k)
+    run_steps(0, args.warmup)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -264,8 +288,7 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for k in range(args.steps):
-        step(args.warmup + k)
+    run_steps(args.warmup, args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -276,6 +299,18 @@ def run_gpu(args):
     ms_total = float(tms.item())
     ms_per_step = ms_total / args.steps
     value = world * N_PART / (ms_per_step * 1e-3)
+
+    # the same K steps one at a time on one stream: the latency of a step (and the throughput without overlap)
+    for k in range(3):
+        step(k)
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for k in range(args.steps):
+        step(3 + k)
+    l1.record()
+    barrier()
+    ms_single = l0.elapsed_time(l1) / args.steps
 
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline object
     def time_kernel(fn, reps):
@@ -375,20 +410,26 @@ def run_gpu(args):
                                                numy=g['numy'], MMAX=g['mmax'], NMAX=g['norder'], ASCALE=g['ascale'],
                                                HSCALE=g['hscale'], CMAP=g['cmap'], verbose=0)
 
+    res = None
     for _ in range(max(args.warmup, 3)):
-        e2e_step()
-    barrier()
+        res = e2e_step()                      # keep the previous result alive, as the timed loop does: the pinned
+    barrier()                                 # result buffers (two alternate) then come from the allocator's cache
     t0 = time.perf_counter()
+    per_call = []
     for _ in range(args.steps):
-        res = e2e_step()
+        tc = time.perf_counter()
+        res = e2e_step()                      # returns NumPy arrays: each call ends with its own stream sync
+        per_call.append(time.perf_counter() - tc)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    sys.stderr.write('e2e per-call ms: ' + ' '.join('%.2f' % (1e3 * t) for t in per_call) + '\n')
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N_PART * args.steps / float(te.item())
     e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * 32 * N_PART - 8 * N_PART,
            'd2h_bytes_per_step': 48 * N_PART + 2 * 8 * 126, 'ms_per_step': 1e3 * float(te.item()) / args.steps,
+           'ms_per_step_median': 1e3 * float(np.median(per_call)),
            'api': ('eof.make_coefficients_multi' if world == 1 else 'parallel.eof_accumulate_host') +
                   ' + eof.accumulated_eval_particles, pinned host tensors in, NumPy arrays out; chunked '
                   'H2D | kernels | D2H pipeline on three streams inside each call'}
@@ -405,8 +446,12 @@ def run_gpu(args):
                 'config': {'workload': WORKLOAD, 'particles_per_gpu': N_PART,
                            'l2': 'rotating %d particle sets (%.0f MB in+out) > 2x L2: every step streams from HBM'
                                  % (NSETS, NSETS * 80e6 / 1e6),
+                           'streams': NSTREAMS,
+                           'in_flight': '%d independent particle sets in flight on %d CUDA streams (cloned handles, '
+                                        'shared tables); a step is serial on its stream' % (NSTREAMS, NSTREAMS),
                            'parallelism': 'particles sharded over %d GPU(s), one 2 kB coefficient allreduce per step'
                                           % world if world > 1 else 'single GPU'},
+                'single_stream': {'ms_per_step': ms_single, 'value': world * N_PART / (ms_single * 1e-3)},
                 'pbe_per_s': value * PBE_PER_PARTICLE, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'clocks': clocks}
         if cpu is not None:
@@ -423,6 +468,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--streams', type=int, default=2, help='independent particle sets in flight (CUDA streams)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

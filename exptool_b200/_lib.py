@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbfe.so')
+LIB_PATH = os.environ.get('BFE_LIB') or os.path.join(_HERE, 'libbfe.so')      # BFE_LIB: A/B builds (profiles/)
 
 
 class BfeError(RuntimeError):
@@ -42,6 +42,7 @@ SIGNATURES = {
     'bfe_kernel_time_ms': (C.c_double, [C.c_char_p]),
     'bfe_eof_create': (_INT, [C.POINTER(EofParams)] + [_P] * 6 + [_P, C.POINTER(_P)]),
     'bfe_eof_destroy': (None, [_P]),
+    'bfe_eof_clone': (_INT, [_P, _P, C.POINTER(_P)]),
     'bfe_eof_accumulate': (_INT, [_P, _I64] + [_P] * 4 + [_P, _P, _P]),
     'bfe_eof_prepare': (_INT, [_P, _I64] + [_P] * 4 + [_P]),
     'bfe_eof_accumulate_prepared': (_INT, [_P, _P, _P, _P]),

@@ -319,6 +319,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     h->contracted = 0;
     h->sort_cap = 0; h->sort_ws = nullptr; h->prepared_n = -1; h->prepared_has_mass = 0;
     h->host_pipe = nullptr;
+    h->owns_tables = 1;
     h->max_ctas = h->num_sms * 4;
     BFE_CUDA(cudaMalloc(&h->t_acc, (size_t)g.nnode * h->nch_pad * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
@@ -342,10 +343,32 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     return BFE_OK;
 }
 
+// A second handle on the SAME device tables with its own contraction, workspaces and counters, so that two
+// independent particle sets (e.g. consecutive snapshots of a time series) can be in flight on two streams
+// and fill each other's launch gaps, tails and latency-bound phases.  The parent must outlive its clones.
+extern "C" int bfe_eof_clone(const bfe_eof* src, void* stream_, bfe_eof** out) {
+    if (!src || !out) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    bfe_eof* h = new bfe_eof(*src);
+    h->owns_tables = 0;
+    h->contracted = 0; h->g4_valid = 0;
+    h->sort_cap = 0; h->sort_ws = nullptr; h->prepared_n = -1; h->prepared_has_mass = 0;
+    h->host_pipe = nullptr;
+    h->g_con = nullptr; h->g4 = nullptr; h->partial = nullptr; h->counter = nullptr;
+    const EofGeom& g = h->g;
+    BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->g4, (size_t)g.numx * g.numy * 12 * (g.mmax + 1) * 2 * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->partial, (size_t)(h->max_ctas + 64) * h->nch_pad * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->counter, 128 * sizeof(unsigned int)));
+    BFE_CUDA(cudaMemsetAsync(h->counter, 0, 128 * sizeof(unsigned int), stream));
+    *out = h;
+    return BFE_OK;
+}
+
 extern "C" void bfe_eof_destroy(bfe_eof* h) {
     if (!h) return;
-    cudaFree(h->t_acc); cudaFree(h->g_con); cudaFree(h->g4); cudaFree(h->partial); cudaFree(h->counter);
-    if (h->t_force) cudaFree(h->t_force);
+    if (h->owns_tables) { cudaFree(h->t_acc); if (h->t_force) cudaFree(h->t_force); }
+    cudaFree(h->g_con); cudaFree(h->g4); cudaFree(h->partial); cudaFree(h->counter);
     if (h->sort_ws) cudaFree(h->sort_ws);
     bfe_host_pipe_destroy(h->host_pipe);
     delete h;

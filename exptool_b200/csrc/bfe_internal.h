@@ -49,6 +49,7 @@ struct bfe_eof {
     void* sort_ws;
     int64_t prepared_n;      // particles currently held cell-sorted in sort_ws (-1: none)
     int prepared_has_mass;
+    int owns_tables;         // 0 for a clone (bfe_eof_clone): t_acc / t_force belong to the parent handle
     void* host_pipe;         // staging buffers / streams of the host-array entry points (bfe_host.cu), lazily made
 };
 

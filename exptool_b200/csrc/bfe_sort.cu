@@ -524,8 +524,52 @@ eof_force_sorted_kernel(EofGeom g, const double* __restrict__ G, int gstride, in
 // flight (latency-bound, ncu profiles/).  Work is handed out dynamically in tickets of 128 records, LAST
 // ticket first: the sparse outskirts of the sorted array (short runs, one dependent B-fragment load each) are
 // at its end, and with a static split the warps that got them finished 50 % after the average.
+// Epilogue of one group of 8 records: the lane (row, jj) holds the interpolated (cos, sin) pairs of harmonics jj
+// and 4 + jj for the three fields (d[2 f][.] / d[2 f + 1][.]).  Trig factors as powers of z = cos phi + i sin phi,
+// the lane's share of the four sums, then a TRANSPOSED 4-lane reduction: after the xor-1 step even lanes hold
+// (p, fz) and odd lanes (fr, fp), after the xor-2 step lane 0 holds p, lane 1 fr, lane 2 fz, lane 3 fp -- three
+// 64-bit shuffles instead of the eight of a butterfly on all four values, and every lane stores its own piece.
+struct ForceLaneConst { double mlo, mhi; bool hi_on, bit0, bit1; int jj; };
+__device__ __forceinline__ void bfe_force_group_epilogue(const double (&d)[6][2], double2 cs1, const ForceLaneConst& k,
+                                                         bool on, double* __restrict__ slot) {
+    const double c2 = cs1.x * cs1.x - cs1.y * cs1.y, s2 = 2.0 * cs1.x * cs1.y;
+    const double c4 = c2 * c2 - s2 * s2, s4 = 2.0 * c2 * s2;
+    const double ac = k.bit0 ? cs1.x : 1.0, as = k.bit0 ? cs1.y : 0.0;
+    const double clo = k.bit1 ? (ac * c2 - as * s2) : ac, slo = k.bit1 ? (as * c2 + ac * s2) : as;
+    const double chi = c4 * clo - s4 * slo, shi = s4 * clo + c4 * slo;
+    // tiles 0,1: potential pairs; 2,3: radial force; 4,5: vertical force
+    double pp = (k.jj == 0) ? 0.0 : (clo * d[0][0] + slo * d[0][1]);        // m = 0 goes to p0, not p
+    double fp = k.mlo * (slo * d[0][0] - clo * d[0][1]);
+    double fr = clo * d[2][0] + slo * d[2][1];
+    double fz = clo * d[4][0] + slo * d[4][1];
+    if (k.hi_on) {
+        pp += chi * d[1][0] + shi * d[1][1];
+        fp += k.mhi * (shi * d[1][0] - chi * d[1][1]);
+        fr += chi * d[3][0] + shi * d[3][1];
+        fz += chi * d[5][0] + shi * d[5][1];
+    }
+    const double ra = __shfl_xor_sync(0xffffffffu, k.bit0 ? pp : fr, 1);
+    const double rb = __shfl_xor_sync(0xffffffffu, k.bit0 ? fz : fp, 1);
+    const double ka = (k.bit0 ? fr : pp) + ra;          // even lanes: p, odd lanes: fr   (sums over a lane pair)
+    const double kb = (k.bit0 ? fp : fz) + rb;          // even lanes: fz, odd lanes: fp
+    const double rc = __shfl_xor_sync(0xffffffffu, k.bit1 ? ka : kb, 2);
+    const double fin = (k.bit1 ? kb : ka) + rc;         // lane 0: p, 1: fr, 2: fz, 3: fp
+    if (on) {
+        // slot = {p0, p, fr, fp, fz, 0}: all 48 bytes are written (a sector left partly unwritten costs a DRAM
+        // read-modify-write when it is evicted)
+        if (!k.bit0) *reinterpret_cast<double2*>(slot + 2 * k.jj) = k.bit1 ? make_double2(fin, 0.0) : make_double2(d[0][0], fin);
+        else slot[k.bit1 ? 3 : 2] = fin;
+    }
+}
+
+#ifndef BFE_FMMA_CTAS
+#define BFE_FMMA_CTAS 5          // resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 CTAS))
+#endif
+#ifndef BFE_FMMA_UNROLL
+#define BFE_FMMA_UNROLL 2        // groups of the uniform-chunk path unrolled together
+#endif
 template <int MCAP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BFE_FMMA_CTAS)
 eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride, int64_t n,
                             const EofRec* __restrict__ rec, double2* __restrict__ tmp,
                             unsigned int* __restrict__ counter) {
@@ -537,28 +581,40 @@ eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = lane >> 2, jj = lane & 3;
     const unsigned int bar0 = bfe_smem_u32(&s_bar[warp][0]), bar1 = bfe_smem_u32(&s_bar[warp][1]);
     const unsigned int buf0 = bfe_smem_u32(&s_buf[warp][0][0]), buf1 = bfe_smem_u32(&s_buf[warp][1][0]);
-    const int ntick = (int)((n + TICKET - 1) / TICKET);
+    // Guided tickets: records [nsmall_rec, n) go out in tickets of 128 (4 chunks), LAST ticket first (the sparse
+    // outskirts of the sorted array -- short runs, slow chunks -- are at its end); the dense head [0, nsmall_rec)
+    // goes out last in single chunks, two per warp of the grid, so that the finish line is one chunk (~0.9 us)
+    // wide instead of one ticket (device timeline: last CTA 16 us after the median with uniform tickets).
+    const int64_t head = (int64_t)gridDim.x * NWARP * 2 * CHUNK;
+    const int64_t nsmall_rec = (head < n ? head : n) / TICKET * TICKET;
+    const int nsmall = (int)(nsmall_rec / CHUNK);
+    const int nbig = (int)((n - nsmall_rec + TICKET - 1) / TICKET);
+    const int ntick = nbig + nsmall;
     unsigned int* ticket_counter = counter + 1;
     BFE_TRACE_PT(5, 0);
-    // producer state (meaningful in lane 0): current ticket, next chunk within it, and the two issued chunks
-    int pf_tick = -1, pf_sub = 0, pf_nsub = 0;
+    // producer state (meaningful in lane 0): next record / chunks left of the current ticket, the two issued chunks
+    int64_t pf_next = 0;
+    int pf_left = 0;
     int qb0 = 0, qc0 = 0, qb1 = 0, qc1 = 0;        // record base / count of the chunk in buffer 0 / 1 (count 0: none)
     auto issue = [&](int par) {                    // lane 0 only
-        if (pf_sub >= pf_nsub) {
+        if (pf_left == 0) {
             const int t = (int)atomicAdd(ticket_counter, 1u);
-            if (t < ntick) {
-                pf_tick = ntick - 1 - t;
-                const int64_t left = n - (int64_t)pf_tick * TICKET;
-                pf_nsub = (int)(((left < TICKET ? left : TICKET) + CHUNK - 1) / CHUNK);
-                pf_sub = 0;
-            } else { pf_nsub = 0; pf_sub = 0; pf_tick = -1; }
+            if (t < nbig) {
+                pf_next = nsmall_rec + (int64_t)(nbig - 1 - t) * TICKET;
+                const int64_t left = n - pf_next;
+                pf_left = (int)(((left < TICKET ? left : TICKET) + CHUNK - 1) / CHUNK);
+            } else if (t < ntick) {
+                pf_next = (int64_t)(nsmall - 1 - (t - nbig)) * CHUNK;
+                pf_left = 1;
+            }
         }
         int base = 0, cnt = 0;
-        if (pf_tick >= 0 && pf_sub < pf_nsub) {
-            base = pf_tick * TICKET + pf_sub * CHUNK;
-            const int64_t left = n - (int64_t)base;
+        if (pf_left > 0) {
+            base = (int)pf_next;
+            const int64_t left = n - pf_next;
             cnt = (int)(left < CHUNK ? left : CHUNK);
-            ++pf_sub;
+            pf_next += CHUNK;
+            --pf_left;
             const unsigned int bytes = (unsigned int)cnt * 64u;
             bfe_mbar_expect_tx(par ? bar1 : bar0, bytes);
             bfe_bulk_g2s(par ? buf1 : buf0, rec + base, bytes, par ? bar1 : bar0);
@@ -585,113 +641,93 @@ eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride
         const int m = 4 * (t & 1) + (row >> 1), field = t >> 1, cs = row & 1;
         boff[t] = (m <= g.mmax) ? (m * 6 + field * 2 + cs) : -1;
     }
-    const double mlo = (double)jj, mhi = (4 + jj <= g.mmax) ? (double)(4 + jj) : 0.0;
-    const bool hi_on = (4 + jj) <= g.mmax;
-    const bool bit0 = jj & 1, bit1 = jj & 2;
+    ForceLaneConst kc;
+    kc.jj = jj; kc.mlo = (double)jj; kc.mhi = (4 + jj <= g.mmax) ? (double)(4 + jj) : 0.0;
+    kc.hi_on = (4 + jj) <= g.mmax; kc.bit0 = jj & 1; kc.bit1 = jj & 2;
     double B[6];
 #pragma unroll
     for (int t = 0; t < 6; ++t) B[t] = 0.0;
     int curcell = -1;
+    auto load_B = [&](int c) {
+        curcell = c;
+        const int ix = c / g.numy, iy = c - ix * g.numy;
+        const double* gp = G + (size_t)(ix * g.ny1 + iy + koff) * gstride;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) B[t] = (boff[t] >= 0) ? __ldg(gp + boff[t]) : 0.0;
+    };
     unsigned int ph0 = 0u, ph1 = 0u;
     for (int par = 0;; par ^= 1) {
         const int cbase = __shfl_sync(0xffffffffu, par ? qb1 : qb0, 0);
         const int ccnt = __shfl_sync(0xffffffffu, par ? qc1 : qc0, 0);
         if (ccnt == 0) break;
         if (par) { bfe_mbar_wait(bar1, ph1); ph1 ^= 1u; } else { bfe_mbar_wait(bar0, ph0); ph0 ^= 1u; }
+        const int* rl = reinterpret_cast<const int*>(&s_buf[warp][par][(lane < ccnt ? lane : 0) * 8]);
+        const int mycell = rl[15];
+        const int prev = __shfl_up_sync(0xffffffffu, mycell, 1);
+        const unsigned int starts = __ballot_sync(0xffffffffu, (lane < ccnt) && (lane == 0 || mycell != prev));
         // chunks made of short runs (sparse outskirts): every run would cost one dependent B-fragment load, ~0.5 us
         // each, serialised in this warp.  Such chunks are evaluated lane per record with the gather formulation
         // instead: 84 independent 16-B loads per lane, all in flight together.
-        {
-            const int* rl = reinterpret_cast<const int*>(&s_buf[warp][par][(lane < ccnt ? lane : 0) * 8]);
-            const int mycell = rl[15];
-            const int prev = __shfl_up_sync(0xffffffffu, mycell, 1);
-            const unsigned int starts = __ballot_sync(0xffffffffu, (lane < ccnt) && (lane == 0 || mycell != prev));
-            if (__popc(starts) > SPARSE_RUNS) {
-                if (lane < ccnt) {
-                    const double* r8 = &s_buf[warp][par][lane * 8];
-                    EofBin b;
-                    const int ix = mycell / g.numy, iy = mycell - ix * g.numy;
-                    b.node = ix * g.ny1 + iy; b.cell = mycell;
-                    b.c00 = r8[0]; b.c10 = r8[1]; b.c01 = r8[2]; b.c11 = r8[3];
-                    const EofField f = bfe_eof_eval<MCAP>(g, G, gstride, b, r8[4], r8[5]);
-                    double2* o = tmp + 3 * ((int64_t)cbase + lane);
-                    o[0] = make_double2(f.p0, f.p);
-                    o[1] = make_double2(f.fr, f.fp);
-                    o[2] = make_double2(f.fz, 0.0);
-                }
-                __syncwarp();
-                if (lane == 0) issue(par);
-                continue;
+        if (__popc(starts) > SPARSE_RUNS) {
+            if (lane < ccnt) {
+                const double* r8 = &s_buf[warp][par][lane * 8];
+                EofBin b;
+                const int ix = mycell / g.numy, iy = mycell - ix * g.numy;
+                b.node = ix * g.ny1 + iy; b.cell = mycell;
+                b.c00 = r8[0]; b.c10 = r8[1]; b.c01 = r8[2]; b.c11 = r8[3];
+                const EofField f = bfe_eof_eval<MCAP>(g, G, gstride, b, r8[4], r8[5]);
+                double2* o = tmp + 3 * ((int64_t)cbase + lane);
+                o[0] = make_double2(f.p0, f.p);
+                o[1] = make_double2(f.fr, f.fp);
+                o[2] = make_double2(f.fz, 0.0);
             }
+            __syncwarp();
+            if (lane == 0) issue(par);
+            continue;
         }
         const double* sb = &s_buf[warp][par][row * 8];
-        double2* dst = tmp + 3 * ((int64_t)cbase + row) + jj;
+        double* slot = reinterpret_cast<double*>(tmp + 3 * ((int64_t)cbase + row));
+        if (ccnt == CHUNK && (starts >> 1) == 0u) {
+            // ---- the common case (92 % of the chunks of a 10^6-particle disc): 32 records of ONE cell.  No
+            // per-group run tests, no tail predicates, and the four groups are independent instruction streams
+            // for the scheduler (unrolled).
+            const int c0 = __shfl_sync(0xffffffffu, mycell, 0);
+            if (c0 != curcell) load_B(c0);
+            constexpr int kUnroll = BFE_FMMA_UNROLL;
+#pragma unroll kUnroll
+            for (int gi = 0; gi < CHUNK / 8; ++gi) {
+                const double* rp = sb + gi * 64;
+                const double w = rp[jj];
+                const double2 cs1 = *reinterpret_cast<const double2*>(rp + 4);
+                double d[6][2];
+#pragma unroll
+                for (int t = 0; t < 6; ++t) { d[t][0] = 0.0; d[t][1] = 0.0; bfe_dmma_m8n8k4(d[t][0], d[t][1], w, B[t]); }
+                bfe_force_group_epilogue(d, cs1, kc, true, slot + gi * 48);
+            }
+        } else {
 #pragma unroll 1
-        for (int gi = 0; gi < CHUNK / 8; ++gi) {
-            if (gi * 8 >= ccnt) break;                                // warp-uniform
-            const bool on = (gi * 8 + row) < ccnt;
-            const double* rp = sb + gi * 64;
-            const double w = on ? rp[jj] : 0.0;
-            const double2 cs1 = on ? *reinterpret_cast<const double2*>(rp + 4) : make_double2(1.0, 0.0);
-            const int cell = on ? reinterpret_cast<const int*>(rp)[15] : -1;      // high word of cellperm
-            double d[6][2];
+            for (int gi = 0; gi < CHUNK / 8; ++gi) {
+                if (gi * 8 >= ccnt) break;                                // warp-uniform
+                const bool on = (gi * 8 + row) < ccnt;
+                const double* rp = sb + gi * 64;
+                const double w = on ? rp[jj] : 0.0;
+                const double2 cs1 = on ? *reinterpret_cast<const double2*>(rp + 4) : make_double2(1.0, 0.0);
+                const int cell = on ? reinterpret_cast<const int*>(rp)[15] : -1;      // high word of cellperm
+                double d[6][2];
 #pragma unroll
-            for (int t = 0; t < 6; ++t) { d[t][0] = 0.0; d[t][1] = 0.0; }
-            if (__all_sync(0xffffffffu, cell == curcell)) {
-                // the whole group continues the open run
-#pragma unroll
-                for (int t = 0; t < 6; ++t) bfe_dmma_m8n8k4(d[t][0], d[t][1], w, B[t]);
-            } else {
+                for (int t = 0; t < 6; ++t) { d[t][0] = 0.0; d[t][1] = 0.0; }
                 unsigned int todo = __ballot_sync(0xffffffffu, on);
                 while (todo) {
                     const int c = __shfl_sync(0xffffffffu, cell, __ffs(todo) - 1);
-                    if (c != curcell) {
-                        curcell = c;
-                        const int ix = c / g.numy, iy = c - ix * g.numy;
-                        const double* gp = G + (size_t)(ix * g.ny1 + iy + koff) * gstride;
-#pragma unroll
-                        for (int t = 0; t < 6; ++t) B[t] = (boff[t] >= 0) ? __ldg(gp + boff[t]) : 0.0;
-                    }
+                    if (c != curcell) load_B(c);
                     const bool mine = cell == c;
                     const double a = mine ? w : 0.0;
 #pragma unroll
                     for (int t = 0; t < 6; ++t) bfe_dmma_m8n8k4(d[t][0], d[t][1], a, B[t]);
                     todo &= ~__ballot_sync(0xffffffffu, mine);
                 }
+                bfe_force_group_epilogue(d, cs1, kc, on, slot + gi * 48);
             }
-            // trig factors of harmonics jj and 4 + jj as powers of z = cos phi + i sin phi: z^jj = z^(bit0) (z^2)^(bit1)
-            const double c2 = cs1.x * cs1.x - cs1.y * cs1.y, s2 = 2.0 * cs1.x * cs1.y;
-            const double c4 = c2 * c2 - s2 * s2, s4 = 2.0 * c2 * s2;
-            const double ac = bit0 ? cs1.x : 1.0, as = bit0 ? cs1.y : 0.0;
-            const double clo = bit1 ? (ac * c2 - as * s2) : ac, slo = bit1 ? (as * c2 + ac * s2) : as;
-            const double chi = c4 * clo - s4 * slo, shi = s4 * clo + c4 * slo;
-            // tiles 0,1: potential pairs; 2,3: radial force; 4,5: vertical force
-            double pp = (jj == 0) ? 0.0 : (clo * d[0][0] + slo * d[0][1]);        // m = 0 goes to p0, not p
-            double fp = mlo * (slo * d[0][0] - clo * d[0][1]);
-            double fr = clo * d[2][0] + slo * d[2][1];
-            double fz = clo * d[4][0] + slo * d[4][1];
-            if (hi_on) {
-                pp += chi * d[1][0] + shi * d[1][1];
-                fp += mhi * (shi * d[1][0] - chi * d[1][1]);
-                fr += chi * d[3][0] + shi * d[3][1];
-                fz += chi * d[5][0] + shi * d[5][1];
-            }
-#pragma unroll
-            for (int off = 1; off <= 2; off <<= 1) {
-                pp += __shfl_xor_sync(0xffffffffu, pp, off);
-                fp += __shfl_xor_sync(0xffffffffu, fp, off);
-                fr += __shfl_xor_sync(0xffffffffu, fr, off);
-                fz += __shfl_xor_sync(0xffffffffu, fz, off);
-            }
-            const double p0 = __shfl_sync(0xffffffffu, d[0][0], lane & ~3);
-            if (on && jj < 3) {
-                double2 v;
-                if (jj == 0) v = make_double2(p0, pp);
-                else if (jj == 1) v = make_double2(fr, fp);
-                else v = make_double2(fz, 0.0);
-                *dst = v;
-            }
-            dst += 24;
         }
         __syncwarp();                                                 // every lane is done reading this buffer
         if (lane == 0) issue(par);
@@ -848,8 +884,13 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
     int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
     if (g_bfe_force_mma) {
-        // one resident wave: 5 CTAs of 4 warps per SM (88 registers, 17.5 kB of record buffers each)
-        int64_t need_m = (n + 511) / 512, cap_m = (int64_t)h->num_sms * 5;
+        // one resident wave (occupancy queried once: registers and 16.4 kB of record buffers per CTA)
+        static int occ = 0;
+        if (!occ) {
+            BFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eof_force_sorted_mma_kernel<6>, 128, 0));
+            if (occ < 1) occ = 1;
+        }
+        int64_t need_m = (n + 511) / 512, cap_m = (int64_t)h->num_sms * occ;
         grid = (int)(need_m < cap_m ? need_m : cap_m);
         const int kt = bfe_kt_begin("eof_force_sorted_mma_kernel", stream);
         BFE_CUDA(bfe_launch(eof_force_sorted_mma_kernel<6>, dim3(grid), dim3(128), 0, stream, h->g_con,

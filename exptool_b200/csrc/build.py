@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-OUT = os.path.join(PKG, 'libbfe.so')
+OUT = os.environ.get('BFE_BUILD_OUT') or os.path.join(PKG, 'libbfe.so')     # BFE_BUILD_OUT + BFE_NVCC_FLAGS: variant builds
 SOURCES = ['bfe_eof.cu', 'bfe_sl.cu', 'bfe_field.cu', 'bfe_sort.cu', 'bfe_sl_sort.cu', 'bfe_host.cu']
 HEADERS = ['bfe_device.cuh', 'bfe_sortcore.cuh', 'bfe_internal.h', os.path.join('..', '..', 'include', 'bfe.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     nvcc = nvcc_path()
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build', os.path.basename(OUT).replace('.so', '') if os.environ.get('BFE_BUILD_OUT') else '')
     os.makedirs(objdir, exist_ok=True)
     flags = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--use_fast_math=false'][:-1]
     flags += ['-Xptxas', '-v'] if verbose else []

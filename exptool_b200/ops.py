@@ -106,6 +106,20 @@ class EOFTables(object):
         except Exception:
             pass
 
+    def clone(self):
+        """
+        A second handle on the same device tables with its own contraction, workspaces and counters
+        (bfe_eof_clone): two particle sets can then be in flight on two streams.  Keeps the parent alive.
+        """
+        import copy
+        other = copy.copy(self)
+        h = C.c_void_p()
+        _lib.check(self.lib.bfe_eof_clone(self.h, _stream(), C.byref(h)))
+        other.h = h
+        other._parent = self
+        other._prepared_n = None
+        return other
+
     def accumulate(self, x, y, z, m):
         """eof.accumulate (eof.py:492-551) -> (cos, sin) device tensors (mmax+1, norder)."""
         x, y, z, m = dev(x), dev(y), dev(z), dev(m)

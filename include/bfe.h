@@ -76,6 +76,9 @@ int bfe_eof_create(const bfe_eof_params* p,
                    const double* potS, const double* rforceS, const double* zforceS,
                    void* stream, bfe_eof** out);
 void bfe_eof_destroy(bfe_eof* h);
+/* A second handle on the same device tables with its own contraction, sorted-set workspace and counters: two
+ * independent particle sets can then be processed concurrently on two streams.  `src` must outlive the clone. */
+int bfe_eof_clone(const bfe_eof* src, void* stream, bfe_eof** out);
 
 /* eof.accumulate (eof.py:492-551) for n particles:
  *   cos_out[m*norder+n] = sum_p -4pi cos(m phi_p) m_p interp_p(potC[m,n]),  sin_out likewise.
