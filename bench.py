@@ -217,6 +217,12 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # keep stdout to the one JSON line: libraries (NCCL's version banner) write to fd 1, so fd 1 is pointed at
+        # stderr for the run and the JSON line goes to a private duplicate of the original stdout
+        sys.stdout.flush()
+        _json_fd = os.dup(1)
+        os.dup2(2, 1)
+        globals()['_JSON_OUT'] = os.fdopen(_json_fd, 'w')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
 
@@ -247,18 +253,35 @@ def run_gpu(args):
     coefbufs = [torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev) for _ in range(NSTREAMS)]
     coefbuf = coefbufs[0]
 
+    # ctypes arguments are built once (a c_void_p per pointer per call costs ~1 us of host time each)
+    set_ptrs = [tuple(_ptr(t) for t in ts) for ts in sets]
+    out_ptrs = [tuple(_ptr(o[i]) for i in range(6)) for o in outs]
+    coef_ptrs = {id(cb): (_ptr(cb[0]), _ptr(cb[1])) for cb in coefbufs}
+    stream_ptrs = {}
+    mmax_, norder_ = g['mmax'], g['norder']
+
+    # one NCCL communicator per stream (their allreduces then do not queue behind each other on one NCCL stream)
+    pgs = {}
+    if world > 1 and NSTREAMS > 1 and args.pg_per_stream:
+        for st_ in streams:
+            pgs[st_.cuda_stream] = dist.new_group(list(range(world)))
+
     def step_on(k, Ei, coef, torch_stream):
         # one cell sort of the particle set serves both passes (include/bfe.h: bfe_eof_prepare)
-        x, y, z, m = sets[k % NSETS]
-        o = outs[k % NSETS]
-        st = C.c_void_p(torch_stream.cuda_stream)
-        L.check(lib.bfe_eof_prepare(Ei.h, N_PART, _ptr(x), _ptr(y), _ptr(z), _ptr(m), st))
-        L.check(lib.bfe_eof_accumulate_prepared(Ei.h, _ptr(coef[0]), _ptr(coef[1]), st))
+        px, py, pz, pm = set_ptrs[k % NSETS]
+        c0, c1 = coef_ptrs[id(coef)]
+        st = stream_ptrs.get(torch_stream.cuda_stream)
+        if st is None:
+            st = stream_ptrs.setdefault(torch_stream.cuda_stream, C.c_void_p(torch_stream.cuda_stream))
+        rc = lib.bfe_eof_prepare(Ei.h, N_PART, px, py, pz, pm, st)
+        rc = rc or lib.bfe_eof_accumulate_prepared(Ei.h, c0, c1, st)
         if world > 1:
             with torch.cuda.stream(torch_stream):
-                dist.all_reduce(coef)
-        L.check(lib.bfe_eof_contract(Ei.h, _ptr(coef[0]), _ptr(coef[1]), 0, g['mmax'], g['norder'], 0, st))
-        L.check(lib.bfe_eof_force_prepared(Ei.h, *[_ptr(o[i]) for i in range(6)], st))
+                dist.all_reduce(coef, group=pgs.get(torch_stream.cuda_stream))
+        rc = rc or lib.bfe_eof_contract(Ei.h, c0, c1, 0, mmax_, norder_, 0, st)
+        rc = rc or lib.bfe_eof_force_prepared(Ei.h, *out_ptrs[k % NSETS], st)
+        if rc:
+            L.check(rc)
 
     def step(k):                                   # single-stream step on the current stream (kernel timing legs)
         step_on(k, E, coefbuf, torch.cuda.current_stream())
@@ -288,7 +311,9 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    th0 = time.perf_counter()
     run_steps(args.warmup, args.steps)
+    host_issue_ms = 1e3 * (time.perf_counter() - th0) / args.steps      # CPU time to enqueue one step
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -451,12 +476,15 @@ def run_gpu(args):
                                         'shared tables); a step is serial on its stream' % (NSTREAMS, NSTREAMS),
                            'parallelism': 'particles sharded over %d GPU(s), one 2 kB coefficient allreduce per step'
                                           % world if world > 1 else 'single GPU'},
+                'host_issue_ms_per_step': host_issue_ms,
                 'single_stream': {'ms_per_step': ms_single, 'value': world * N_PART / (ms_single * 1e-3)},
                 'pbe_per_s': value * PBE_PER_PARTICLE, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'clocks': clocks}
         if cpu is not None:
             line['cpu_baseline'] = cpu
-        print(json.dumps(line), flush=True)
+        out = globals().get('_JSON_OUT') or sys.stdout
+        out.write(json.dumps(line) + '\n')
+        out.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -469,6 +497,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--streams', type=int, default=2, help='independent particle sets in flight (CUDA streams)')
+    ap.add_argument('--pg-per-stream', type=int, default=0, help='N>1: one NCCL communicator per stream (1) or shared (0)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -7,8 +7,7 @@ reference; the arithmetic runs in libbfe.so on the current CUDA device
 are host-side NumPy, as in the reference.
 
 Not mirrored (outside the path): wake grids, phase /
-pattern-speed post-processing, variance (VAR) jackknife sums, plotting, density
-evaluation.
+pattern-speed post-processing, variance (VAR) jackknife sums, plotting.
 """
 import time
 from collections import OrderedDict
@@ -280,21 +279,34 @@ def accumulated_eval_particles(Particles, accum_cos, accum_sin, potC=0, rforceC=
     eof.accumulated_eval_particles (eof.py:989-1144): p0, p, fr, fp, fz, R, one value per particle.
     p excludes m=0; fr, fz include it; only m1 <= m <= m2 contribute.
     '''
+    dens = 0                                                       # eof.py:1039
+    densC = densS = None
     if eof_file != '':
         potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS = parse_eof(eof_file)
         rmin, rmax, numx, numy, MMAX, NMAX, ASCALE, HSCALE, CMAP, dens = eof_params(eof_file)
         rmin, rmax, dR, zmin, zmax, dZ = set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ASCALE, HSCALE=HSCALE,
                                                           NUMX=numx, NUMY=numy, CMAP=CMAP)
-    if density:
+    if density and dens == 0:
+        # eof.py:1048-1050 (the reference only resets the flag when verbose > 0 and then fails on the missing
+        # density tables; here the flag is always dropped)
         if verbose > 0:
-            print('eof.accumulated_eval_particles: cannot compute density (outside the B200 hot path). moving on without...')
+            print('eof.accumulated_eval_particles: cannot compute density (functions not specified). moving on without...')
         density = False
     x, y, z, _ = particle.particle_arrays(Particles)
     E = device_tables(potC, potS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
                       rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
     E.contract(accum_cos, accum_sin, m1=m1, m2=m2)
     p0, p, fr, fp, fz, R = E.force_host(x, y, z)
-    return p0, p, fr, fp, fz, R
+    if not density:
+        return p0, p, fr, fp, fz, R
+    # density (eof.py:1106, 1122, 1136-1138): d0, d are the sums that give p0, p with densC / densS in place of
+    # potC / potS -- the same contraction and interpolation kernels run on a second table handle built from the
+    # density tables (its force tables are unused placeholders)
+    D = device_tables(densC, densS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
+                      rforceC=densC, zforceC=densC, rforceS=densS, zforceS=densS)
+    D.contract(accum_cos, accum_sin, m1=m1, m2=m2)
+    d0, d = D.force_host(x, y, z)[:2]
+    return p0, p, d0, d, fr, fp, fz, R
 
 
 def compute_forces(PSPInput, EOF_Object, verbose=1, nprocs=-1, m1=0, m2=1000, density=False):

@@ -159,15 +159,17 @@ def partition_like_reference(n, divisions):
 # ---------------------------------------------------------------------------
 def eof_force_particles(x, y, z, accum_cos, accum_sin, potC, rforceC, zforceC,
                         potS, rforceS, zforceS, rmin, dR, zmin, dZ, numx, numy,
-                        MMAX, NMAX, ASCALE, HSCALE, CMAP, m1=0, m2=1000, chunk=16384):
+                        MMAX, NMAX, ASCALE, HSCALE, CMAP, m1=0, m2=1000, chunk=16384, densC=None, densS=None):
     """
     eof.accumulated_eval_particles (eof.py:989-1144), vectorised over particles.
     Returns p0, p, fr, fp, fz, R with p excluding m=0 (1129-1134), fr/fz including
     it, R = sqrt(x^2+y^2+1e-10) (1070), window m1 <= m <= m2 (1094).
+    With densC/densS (density=True, eof.py:1106,1122,1136-1138) returns p0, p, d0, d, fr, fp, fz, R.
     """
     x = np.asarray(x, np.float64); y = np.asarray(y, np.float64); z = np.asarray(z, np.float64)
     n = x.size
     p0 = np.zeros(n); p = np.zeros(n); fr = np.zeros(n); fp = np.zeros(n); fz = np.zeros(n)
+    d0 = np.zeros(n); d = np.zeros(n)
     R = (x * x + y * y + 1.e-10) ** 0.5
     PHI = np.arctan2(y, x)
     for lo in range(0, n, chunk):
@@ -185,6 +187,7 @@ def eof_force_particles(x, y, z, accum_cos, accum_sin, potC, rforceC, zforceC,
             vr = np.sum(ac * _interp(rforceC[mm, :NMAX], ix, iy, *c), axis=0)
             vz = np.sum(ac * _interp(zforceC[mm, :NMAX], ix, iy, *c), axis=0)
             pm = ccos * vp
+            dm = ccos * np.sum(ac * _interp(densC[mm, :NMAX], ix, iy, *c), axis=0) if densC is not None else 0.0
             fr[sl] += ccos * vr
             fz[sl] += ccos * vz
             fp[sl] += ssin * mm * vp
@@ -194,12 +197,18 @@ def eof_force_particles(x, y, z, accum_cos, accum_sin, potC, rforceC, zforceC,
                 wr = np.sum(asn * _interp(rforceS[mm, :NMAX], ix, iy, *c), axis=0)
                 wz = np.sum(asn * _interp(zforceS[mm, :NMAX], ix, iy, *c), axis=0)
                 pm = pm + ssin * wp
+                if densS is not None:
+                    dm = dm + ssin * np.sum(asn * _interp(densS[mm, :NMAX], ix, iy, *c), axis=0)
                 fr[sl] += ssin * wr
                 fz[sl] += ssin * wz
                 fp[sl] += -ccos * mm * wp
                 p[sl] += pm
+                d[sl] += dm
             else:
                 p0[sl] = pm
+                d0[sl] = dm
+    if densC is not None:
+        return p0, p, d0, d, fr, fp, fz, R
     return p0, p, fr, fp, fz, R
 
 

@@ -257,7 +257,30 @@ def case_field(name, eparams, sparams, kind, seed, ndisc, nhalo, npts, norb, nin
     print('wrote', name)
 
 
-if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'field':
+def case_eof_density(name, eparams, kind, seed, npart, rscale, zscale):
+    """eof.accumulated_eval_particles(density=True, eof_file=...) (eof.py:1041-1050, 1106, 1122, 1136-1142) on a
+    cache file written with dens=1: p0, p, d0, d, fr, fp, fz, R."""
+    rng = np.random.default_rng(seed + 100)
+    with tempfile.TemporaryDirectory() as tmp:
+        f, tabs, g = eof_setup(tmp, eparams, kind, seed)
+        potC, rfC, zfC, dC, potS, rfS, zfS, dS = tabs
+        x, y, z, m = edge_particles(rng, npart, rscale, zscale)
+        P = S.ParticleSet(x, y, z, m)
+        cosd, sind = eof.accumulate(P, potC, potS, g['mmax'], g['norder'], g['XMIN'], g['dX'], g['YMIN'], g['dY'],
+                                    g['numx'], g['numy'], g['ascale'], g['hscale'], g['cmap'])
+        full = quiet(eof.accumulated_eval_particles, P, cosd, sind, density=True, eof_file=f, verbose=0)
+        win = quiet(eof.accumulated_eval_particles, P, cosd, sind, m1=1, m2=2, density=True, eof_file=f, verbose=0)
+        assert len(full) == 8
+    np.savez_compressed(os.path.join(HERE, name + '.npz'),
+                        meta=json.dumps(dict(eof_params=eparams, kind=kind, seed=seed, geo=g)),
+                        x=x, y=y, z=z, m=m, cos=cosd, sin=sind, full=np.array(full), win12=np.array(win))
+    print('wrote', name)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'density':
+    case_eof_density('eof_dens_random', dict(SMALL_EOF, cmap=1, dens=1), 'random', 14, 300, 0.02, 0.002)
+    case_eof_density('eof_dens_smooth', dict(mmax=4, numx=48, numy=32, nmax=8, norder=6, dens=1), 'smooth', 15, 300, 0.015, 0.001)
+elif __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'field':
     case_field('field_small', dict(mmax=4, numx=48, numy=32, nmax=8, norder=6), dict(lmax=4, nmax=6, numr=400),
                'smooth', 31, 3000, 800, 48, 3, 250)
     case_field('field_std', {}, dict(lmax=6), 'smooth', 32, 4000, 600, 24, 2, 120)

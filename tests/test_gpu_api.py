@@ -287,3 +287,25 @@ def test_eof_host_pipeline_matches_device(api):
         for k in range(6):
             assert isinstance(out[k], np.ndarray) and out[k].shape == (n,)
             assert relerr(out[k], ref[k]) < 1e-13
+
+
+@pytest.mark.parametrize('name', ['eof_dens_random', 'eof_dens_smooth'])
+def test_eof_density_api(api, name):
+    """eof.accumulated_eval_particles(density=True, eof_file=...) against the reference's own output on a dens=1
+    cache file: p0, p, d0, d, fr, fp, fz, R (eof.py:1136-1142)."""
+    eof = api['eof']
+    d, meta = load_golden(name)
+    with tempfile.TemporaryDirectory() as tmp:
+        f = _eof_file(tmp, meta)
+        assert eof.eof_params(f)[9] == 1
+        P = S.ParticleSet(d['x'], d['y'], d['z'], d['m'])
+        full = eof.accumulated_eval_particles(P, d['cos'], d['sin'], density=True, eof_file=f, verbose=0)
+        win = eof.accumulated_eval_particles(P, d['cos'], d['sin'], m1=1, m2=2, density=True, eof_file=f, verbose=0)
+        assert len(full) == 8 and len(win) == 8
+        for i in range(8):
+            assert isinstance(full[i], np.ndarray) and full[i].shape == d['x'].shape
+            assert relerr(full[i], d['full'][i]) < TOL, i
+            assert relerr(win[i], d['win12'][i]) < TOL, i
+        # without density tables the flag is dropped and the six standard outputs come back (eof.py:1048-1050)
+        six = eof.accumulated_eval_particles(P, d['cos'], d['sin'], eof_file=f, verbose=0)
+        assert len(six) == 6 and relerr(six[1], d['full'][1]) < TOL

@@ -136,3 +136,20 @@ def test_leapfrog(name):
                                      no_odd=True, halo_l=2, halo_n=4, disk_m=4, disk_n=5, keep_trajectory=True)
     for j, key in enumerate(('X', 'Y', 'Z', 'VX', 'VY', 'VZ', 'P')):
         assert relerr(traj[key][:, 0], d['orbit_trunc'][j]) < 1e-9, key
+
+
+@pytest.mark.parametrize('name', ['eof_dens_random', 'eof_dens_smooth'])
+def test_eof_density_particles(name):
+    """density=True outputs (eof.py:1106, 1122, 1136-1142) of the unmodified reference on a dens=1 cache file."""
+    d, meta = load_golden(name)
+    p, T, g = eof_tables(meta)
+    assert p['dens'] == 1
+    args = (d['x'], d['y'], d['z'], d['cos'], d['sin'], T['potC'], T['rforceC'], T['zforceC'],
+            T['potS'], T['rforceS'], T['zforceS'], *eof_geo_args(g), g['mmax'], g['norder'],
+            g['ascale'], g['hscale'], g['cmap'])
+    full = O.eof_force_particles(*args, densC=T['densC'], densS=T['densS'])
+    win = O.eof_force_particles(*args, m1=1, m2=2, densC=T['densC'], densS=T['densS'])
+    assert len(full) == 8
+    for i in range(8):
+        assert relerr(full[i], d['full'][i]) < TOL, i
+        assert relerr(win[i], d['win12'][i]) < TOL, i
