@@ -63,6 +63,9 @@ SIGNATURES = {
     'bfe_field_force_cart': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
     'bfe_field_force_cyl': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
     'bfe_leapfrog': (_INT, [_P, _P, _I64, _I64, _DBL, _DBL, _P, _P, _I64, _INT, _INT, _P, _P]),
+    'bfe_bar_fourier': (_INT, [_I64, _P, _P, _DBL, _DBL, _P, _P]),
+    'bfe_affine_xy': (_INT, [_I64, _DBL, _DBL, _DBL, _DBL] + [_P] * 6 + [_P]),
+    'bfe_inner_com': (_INT, [_I64] + [_P] * 7 + [_I64, _P, _P]),
     'bfe_leapfrog_dt': (_INT, [_P, _P, _I64, _I64, _P, _DBL, _P, _P, _I64, _INT, _INT, _P, _P]),
 }
 

@@ -212,18 +212,27 @@ def compute_coefficients(PSPInput, eof_file, verbose=1, no_odd=False, nprocs_max
     1190-1204; its own `if nanvals > 0` raises on NumPy >= 2.2).
     '''
     x, y, z, m = particle.particle_arrays(PSPInput)
-    x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64); z = np.asarray(z, dtype=np.float64)
-    nanvals = np.where(np.isnan(x) | np.isnan(y) | np.isnan(z))[0]
-    if nanvals.size > 0:
-        print('eof.compute_coefficients: NaN values found in output file {}.'.format(getattr(PSPInput, 'filename', None)))
-        if not nanblock:
-            x = x.copy(); y = y.copy(); z = z.copy()
-            x[nanvals] = 0.; y[nanvals] = 0.; z[nanvals] = 0.
+    on_device = isinstance(x, ops.torch.Tensor) and x.is_cuda
+    if on_device:
+        # device-resident snapshot (Fields.total_coefficients after the transforms): same NaN rule on the device
+        bad = ops.torch.isnan(x) | ops.torch.isnan(y) | ops.torch.isnan(z)
+        if bool(bad.any()):
+            print('eof.compute_coefficients: NaN values found in output file {}.'.format(getattr(PSPInput, 'filename', None)))
+            if not nanblock:
+                x, y, z = [ops.torch.where(bad, ops.torch.zeros_like(a), a) for a in (x, y, z)]
+    else:
+        x = np.asarray(x, dtype=np.float64); y = np.asarray(y, dtype=np.float64); z = np.asarray(z, dtype=np.float64)
+        nanvals = np.where(np.isnan(x) | np.isnan(y) | np.isnan(z))[0]
+        if nanvals.size > 0:
+            print('eof.compute_coefficients: NaN values found in output file {}.'.format(getattr(PSPInput, 'filename', None)))
+            if not nanblock:
+                x = x.copy(); y = y.copy(); z = z.copy()
+                x[nanvals] = 0.; y[nanvals] = 0.; z[nanvals] = 0.
     EOF_Out = EOF_Object()
     EOF_Out.time = getattr(PSPInput, 'time', None)
     EOF_Out.filename = getattr(PSPInput, 'filename', None)
     EOF_Out.comp = getattr(PSPInput, 'comp', None)
-    EOF_Out.nbodies = np.asarray(m).size
+    EOF_Out.nbodies = int(m.numel()) if isinstance(m, ops.torch.Tensor) else np.asarray(m).size
     EOF_Out.eof_file = eof_file
     potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS = parse_eof(eof_file)
     rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, dens = eof_params(eof_file, verbose=(verbose > 1))

@@ -6,9 +6,10 @@ of one snapshot and return the combined force at points.
 The device state is two table handles (ops.EOFTables / ops.SLTables) holding the
 coefficient contraction for the current truncation (set_field_parameters).
 
-Not mirrored: PSP snapshot ingest inside total_coefficients (pass in-memory
-particle sets instead), centering / BarTransform, rotation curves, resonance
-helpers, EnergyKappa.
+total_coefficients reads the PSP snapshot (exptool_b200.io.psp_io), applies the
+bar-frame rotation and the centring on the device and accumulates both bases
+(SURVEY.md section 8f rank 3).  Not mirrored: rotation curves, resonance helpers,
+EnergyKappa.
 """
 import numpy as np
 
@@ -45,22 +46,55 @@ class Fields():
     # -- coefficients ---------------------------------------------------------
     def total_coefficients(self, disc=None, halo=None, halofac=None):
         '''
-        Fields.total_coefficients (potential.py:98-252).  The reference reads the disc and
-        halo components from a PSP file; snapshot ingest is outside the path, so the
-        particle sets are passed in (`holder`, `.data` container or (x,y,z,m) tuple).
-        halofac = N_total_halo / N_used_halo (potential.py:143); 1 if all halo particles are given.
+        Fields.total_coefficients (potential.py:98-252): read the 'star' and 'dark' components of the PSP file
+        `self.filename` (or take the particle sets passed as disc= / halo=: `holder`, `.data` container or
+        (x,y,z,m) tuple), optionally rotate both into the bar frame (transform, pattern.BarTransform) and
+        recentre them on the mass-weighted centre of the 10^4 innermost disc particles (centering,
+        mutual_center), then accumulate the EOF and SL coefficients.  The snapshot is uploaded once; the
+        transforms, the centre search and the accumulation all run on the device-resident arrays.
+        halofac = N_halo / N_halo = 1 in the reference (potential.py:143); pass halofac= to override.
         '''
-        if disc is None or halo is None:
-            raise NotImplementedError('Fields.total_coefficients: PSP snapshot ingest is outside the B200 hot path; '
-                                      'pass disc= and halo= particle sets')
-        if self.transform or self.centering:
-            raise NotImplementedError('Fields.total_coefficients: transform/centering are outside the B200 hot path')
-        self.xcen_disk = self.ycen_disk = self.zcen_disk = 0.
-        self.xcen_halo = self.ycen_halo = self.zcen_halo = 0.
-        if halofac is not None:
-            self.halofac = float(halofac)
-        self.EOF = eof.compute_coefficients(disc, self.eof_file, verbose=self.verbose, no_odd=self.no_odd)
-        self.SL = spheresl.compute_coefficients(halo, self.sph_file, self.model_file, verbose=self.verbose,
+        from ..io import particle
+        torch = ops.torch
+        if disc is None:
+            disc = particle.Input(self.filename, comp='star', verbose=self.verbose)
+        if halo is None:
+            halo = particle.Input(self.filename, comp='dark', verbose=self.verbose)
+        self.time = getattr(disc, 'time', self.time)
+        xd, yd, zd, md = [ops.dev(a) for a in particle.particle_arrays(disc)]
+        xh, yh, zh, mh = [ops.dev(a) for a in particle.particle_arrays(halo)]
+        self.halofac = 1.0 if halofac is None else float(halofac)
+        if self.transform:
+            # pattern.py:104: bar angle from the disc (0 < R < 1), the same rotation for the halo (potential.py:147)
+            self.bar_angle = -1. * ops.bar_fourier_angle(xd, yd, minr=0., maxr=1.)
+            if self.verbose > 1:
+                print('potential.Fields.total_coefficients: Using bar_angle {0:4.3f}'.format(self.bar_angle))
+            xd, yd = ops.affine_xy(xd, yd, angle=self.bar_angle)
+            xh, yh = ops.affine_xy(xh, yh, angle=self.bar_angle)
+        if self.centering:
+            print('potential.Fields.total_coefficients: Computing centering (centering=True)')
+            ncenter = 10000
+            self.xcen_disk, self.ycen_disk, self.zcen_disk = ops.inner_center_of_mass(xd, yd, zd, md, ncenter)
+            if self.mutual_center:
+                print('potential.Fields.total_coefficients: Using computed disk center for halo (mutual_center=True)')
+                self.xcen_halo, self.ycen_halo, self.zcen_halo = self.xcen_disk, self.ycen_disk, self.zcen_disk
+            else:
+                # potential.py:190-200: the DISC ranking indexes the halo arrays (replicated)
+                self.xcen_halo, self.ycen_halo, self.zcen_halo = ops.inner_center_of_mass(
+                    xd, yd, zd, md, ncenter, values=(xh, yh, zh, mh))
+            print('potential.Fields.total_coefficients: (x,y,z) = {0:6.5f},{1:6.5f},{2:6.5f}'
+                  .format(float(self.xcen_disk), float(self.ycen_disk), float(self.zcen_disk)))
+            xd, yd, zd = ops.affine_xy(xd, yd, zd, center=(self.xcen_disk, self.ycen_disk, self.zcen_disk))
+            xh, yh, zh = ops.affine_xy(xh, yh, zh, center=(self.xcen_halo, self.ycen_halo, self.zcen_halo))
+        else:
+            self.xcen_disk = self.ycen_disk = self.zcen_disk = 0.
+            self.xcen_halo = self.ycen_halo = self.zcen_halo = 0.
+        D = particle.Particles(xd, yd, zd, md, time=self.time, filename=getattr(disc, 'filename', self.filename),
+                               comp=getattr(disc, 'comp', 'star'))
+        Hh = particle.Particles(xh, yh, zh, mh, time=self.time, filename=getattr(halo, 'filename', self.filename),
+                                comp=getattr(halo, 'comp', 'dark'))
+        self.EOF = eof.compute_coefficients(D, self.eof_file, verbose=self.verbose, no_odd=self.no_odd)
+        self.SL = spheresl.compute_coefficients(Hh, self.sph_file, self.model_file, verbose=self.verbose,
                                                 no_odd=self.no_odd)
         self._contract_key = None
 

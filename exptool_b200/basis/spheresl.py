@@ -133,7 +133,7 @@ def compute_coefficients(PSPInput, sph_file, mod_file, verbose=1, no_odd=False):
     SL_Out.filename = getattr(PSPInput, 'filename', None)
     SL_Out.comp = getattr(PSPInput, 'comp', None)
     x, y, z, m = particle.particle_arrays(PSPInput)
-    SL_Out.nbodies = np.asarray(m).size
+    SL_Out.nbodies = int(m.numel()) if isinstance(m, ops.torch.Tensor) else np.asarray(m).size
     SL_Out.sph_file = sph_file
     SL_Out.model_file = mod_file
     H, T = device_tables_from_files(sph_file, mod_file)

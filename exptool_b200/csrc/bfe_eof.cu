@@ -157,7 +157,7 @@ eof_accumulate_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int 
 __global__ void eof_contract_kernel(EofGeom g, const double* __restrict__ t_force, size_t tab_elems,
                                     const double* __restrict__ cosc, const double* __restrict__ sinc,
                                     int m1, int m2, int nuse, int no_odd,
-                                    double* __restrict__ G, int gstride) {
+                                    double* __restrict__ G, int gstride, int deep) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y / 6, q = blockIdx.y % 6;
     bfe_pdl_wait();
@@ -170,10 +170,22 @@ __global__ void eof_contract_kernel(EofGeom g, const double* __restrict__ t_forc
         const double* T = t_force + (size_t)(trig * 3 + field) * tab_elems + (size_t)m * g.norder * g.nnode + node;
         const double* c = (trig ? sinc : cosc) + m * g.norder;
         const int nn = nuse < g.norder ? nuse : g.norder;
-        // six independent table loads in flight per thread (the one-accumulator loop exposed one DRAM
-        // latency per term: long-scoreboard 40 cycles per issue, 34 % of DRAM peak in ncu)
+        // U independent table loads in flight per thread (the one-accumulator loop exposed one DRAM latency per
+        // term: long-scoreboard 40 cycles per issue, 34 % of DRAM peak in ncu)
         double s1 = 0.0, s2 = 0.0;
         int k = 0;
+        if (deep) {
+            for (; k + 8 < nn; k += 9) {
+                double t[9];
+#pragma unroll
+                for (int u = 0; u < 9; ++u) t[u] = __ldg(T + (size_t)(k + u) * g.nnode);
+#pragma unroll
+                for (int u = 0; u < 9; u += 3) {
+                    s = fma(__ldg(c + k + u), t[u], s); s1 = fma(__ldg(c + k + u + 1), t[u + 1], s1);
+                    s2 = fma(__ldg(c + k + u + 2), t[u + 2], s2);
+                }
+            }
+        }
         for (; k + 5 < nn; k += 6) {
             double t[6];
 #pragma unroll
@@ -409,7 +421,7 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
     dim3 grd((h->g.nnode + 127) / 128, (h->g.mmax + 1) * 6);
     const int kt = bfe_kt_begin("eof_contract_kernel", stream);
     BFE_CUDA(bfe_launch(eof_contract_kernel, grd, dim3(128), 0, stream, h->t_force, 6 * h->tab_elems * sizeof(double),
-                        h->g, h->t_force, h->tab_elems, cosc, sinc, m1, m2, nuse, no_odd, h->g_con, h->gstride));
+                        h->g, h->t_force, h->tab_elems, cosc, sinc, m1, m2, nuse, no_odd, h->g_con, h->gstride, g_bfe_contract_deep));
     bfe_kt_end(kt, stream);
     BFE_LAUNCH_CHECK("eof_contract_kernel");
     h->contracted = 1;

@@ -217,6 +217,7 @@ int g_bfe_staged_eval = 1;
 int g_bfe_force_mma = 1;
 static int g_bfe_time_kernels = 0;
 int g_bfe_pdl = 1;
+int g_bfe_contract_deep = 0;
 int g_bfe_l2_persist = 0;
 size_t g_bfe_l2_window_max = 0;
 
@@ -244,6 +245,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "staged_eval")) { g_bfe_staged_eval = value; return BFE_OK; }
     if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
     if (!strcmp(name, "pdl")) { g_bfe_pdl = value; return BFE_OK; }
+    if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }
     if (!strcmp(name, "host_chunk")) { g_bfe_host_chunk = value; return BFE_OK; }
     if (!strcmp(name, "l2_persist")) {
         g_bfe_l2_persist = value;

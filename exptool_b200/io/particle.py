@@ -1,8 +1,41 @@
 """
 particle.py -- the particle container types the hot path accepts
-(exptool/io/particle.py:142-157).  Readers (psp_io / spl_io) are out of scope.
+(exptool/io/particle.py:142-157) and the `Input` front end of the PSP reader
+(exptool/io/particle.py:16-112).  The SPL (split-file) reader is out of scope.
 """
 import numpy as np
+
+from . import psp_io
+
+
+class Input():
+    """particle.Input (particle.py:16-112): PSP 'OUT.' snapshots -> .header, .time, .filename, .comp and either
+    `.data` (dict) or, with legacy=True, the .xpos/.ypos/... attributes."""
+
+    def __init__(self, filename, comp=None, legacy=False, verbose=0):
+        if 'SPL.' in filename:
+            raise ValueError('File type not supported for file "{}" (SPL split files are outside the path)'.format(filename))
+        self.style = 'OUT'
+        I = psp_io.Input(filename, comp=comp, verbose=verbose)
+        self.header = I.header
+        self.filename = I.filename
+        self.time = I.time
+        if I.comp is None:
+            return
+        if legacy:
+            self.mass = I.data['m']
+            self.xpos = I.data['x']
+            self.ypos = I.data['y']
+            self.zpos = I.data['z']
+            self.xvel = I.data['vx']
+            self.yvel = I.data['vy']
+            self.zvel = I.data['vz']
+            self.pote = I.data['potE']
+            if I.header[I.comp]['parameters']['indexing']:
+                self.id = I.data['id']
+        else:
+            self.data = I.data
+        self.comp = I.comp
 
 
 class holder(object):

@@ -372,3 +372,47 @@ def leapfrog(eof_tables, sl_tables, pos0, vel0, nint, dt, rotfreq=0.0, traj_stri
                                                   float(rotfreq), _ptr(state), _ptr(traj), stride,
                                                   int(bool(apse)), int(ap_max), _ptr(nsteps), _stream()))
     return state, traj, nsteps
+
+
+# ---------------------------------------------------------------------------
+# pre-accumulation transforms of a device-resident snapshot
+# ---------------------------------------------------------------------------
+def bar_fourier_angle(x, y, minr=0.0, maxr=1.0):
+    """pattern.BarTransform.bar_fourier_compute (pattern.py:155-169): atan2(sum sin 2phi, sum cos 2phi) / 2
+    over minr < R < maxr.  x, y device (or host) arrays; returns a Python float (one 16-byte copy out)."""
+    x, y = dev(x), dev(y)
+    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().bfe_bar_fourier(x.numel(), _ptr(x), _ptr(y), float(minr), float(maxr), _ptr(out), _stream()))
+    a, b = out.cpu().tolist()
+    return float(np.arctan2(b, a) / 2.0)
+
+
+def affine_xy(x, y, z=None, angle=0.0, center=(0.0, 0.0, 0.0), out=None):
+    """(x, y) rotated counter-clockwise by `angle`, then shifted by -center; z shifted (pattern.py:118-139,
+    potential.py:213-219).  Returns new device tensors (or writes `out` = (xo, yo[, zo]))."""
+    x, y = dev(x), dev(y)
+    z = dev(z) if z is not None else None
+    if out is None:
+        out = (torch.empty_like(x), torch.empty_like(y)) + ((torch.empty_like(z),) if z is not None else ())
+    _lib.check(_lib.load().bfe_affine_xy(x.numel(), float(angle), float(center[0]), float(center[1]), float(center[2]),
+                                         _ptr(x), _ptr(y), _ptr(z), _ptr(out[0]), _ptr(out[1]),
+                                         _ptr(out[2]) if z is not None else C.c_void_p(0), _stream()))
+    return out
+
+
+def inner_center_of_mass(x, y, z, m, ncenter=10000, values=None):
+    """Mass-weighted centre of the `ncenter` innermost particles (potential.py:158-176) -> (xc, yc, zc) floats.
+    `values` = (vx, vy, vz, vm): sum these arrays at the selected indices instead (the reference ranks the disc
+    and indexes the halo arrays with the result, potential.py:190-200); they must have at least len(x) entries."""
+    x, y, z = dev(x), dev(y), dev(z)
+    if values is None:
+        vx, vy, vz, vm = x, y, z, dev(m)
+    else:
+        vx, vy, vz, vm = [dev(a) for a in values]
+        if min(vx.numel(), vy.numel(), vz.numel(), vm.numel()) < x.numel():
+            raise IndexError('inner_center_of_mass: value arrays are shorter than the ranked set')
+    out = torch.empty(4, dtype=torch.float64, device=x.device)
+    _lib.check(_lib.load().bfe_inner_com(x.numel(), _ptr(x), _ptr(y), _ptr(z), _ptr(vx), _ptr(vy), _ptr(vz), _ptr(vm),
+                                         int(ncenter), _ptr(out), _stream()))
+    sx, sy, sz, sm = out.cpu().tolist()
+    return sx / sm, sy / sm, sz / sm

@@ -261,3 +261,34 @@ def write_fixture_files(dirname, eof_params=None, sl_params=None, kind='smooth',
     sl_file = write_sl_cache(os.path.join(dirname, 'SLGridSph.cache.' + tag), ps, ev, ef)
     model_file = write_hernquist_model(os.path.join(dirname, 'SLGridSph.model'), a=ps['scale'])
     return eof_file, sl_file, model_file
+
+
+def barred_snapshot(seed, ndisc, nhalo, bar_angle=0.6, bar_strength=0.35, center=(0.0021, -0.0013, 0.0004),
+                    unequal_mass=True):
+    """
+    Synthetic two-component snapshot for the ingest path (Fields.total_coefficients): an exponential disc with an
+    m = 2 distortion (a fraction `bar_strength` of the particles is squeezed towards the axis at `bar_angle`)
+    and a Hernquist halo, both displaced by `center`, with velocities and potential energies so that every PSP
+    field is populated.  Returns {'star': data, 'dark': data} with data = dict(m,x,y,z,vx,vy,vz,potE).
+    """
+    rng = np.random.default_rng(seed)
+    x, y, z, m = exponential_disc(ndisc, seed + 1)
+    R = np.hypot(x, y); phi = np.arctan2(y, x)
+    squeeze = rng.random(ndisc) < bar_strength
+    phi = np.where(squeeze, bar_angle + 0.35 * (phi - bar_angle) * 0.5 + np.pi * rng.integers(0, 2, ndisc), phi)
+    x, y = R * np.cos(phi), R * np.sin(phi)
+    if unequal_mass:
+        m = m * rng.uniform(0.5, 1.5, ndisc)
+    vc = np.sqrt(R / (R + 0.01)) * 1.2
+    out = {}
+    out['star'] = dict(m=m, x=x + center[0], y=y + center[1], z=z + center[2],
+                       vx=-vc * np.sin(phi) + rng.normal(0, 0.05, ndisc), vy=vc * np.cos(phi) + rng.normal(0, 0.05, ndisc),
+                       vz=rng.normal(0, 0.02, ndisc), potE=-1.0 / (R + 0.01))
+    xh, yh, zh, mh = hernquist_halo(nhalo, seed + 2)
+    if unequal_mass:
+        mh = mh * rng.uniform(0.5, 1.5, nhalo)
+    rh = np.sqrt(xh * xh + yh * yh + zh * zh)
+    out['dark'] = dict(m=mh, x=xh + center[0], y=yh + center[1], z=zh + center[2],
+                       vx=rng.normal(0, 0.3, nhalo), vy=rng.normal(0, 0.3, nhalo), vz=rng.normal(0, 0.3, nhalo),
+                       potE=-1.0 / (rh + 0.0667))
+    return out

@@ -216,6 +216,22 @@ int bfe_leapfrog_dt(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, const
                     double* state6, double* traj, int64_t traj_stride,
                     int apse, int ap_max, int32_t* nsteps_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pre-accumulation transforms of a device-resident snapshot (Fields.total_coefficients, potential.py:120-226).
+ * bfe_bar_fourier : out2[0] = sum cos 2phi, out2[1] = sum sin 2phi over minr < (x^2+y^2)^0.5 < maxr  (device doubles);
+ *                   bar angle = -atan2(out2[1], out2[0]) / 2                     (analysis/pattern.py:104, 155-169)
+ * bfe_affine_xy   : xo = x cos a - y sin a - cx, yo = x sin a + y cos a - cy, zo = z - cz (z, zo may both be NULL);
+ *                   in place allowed (xo == x ...)                               (pattern.py:118-139, potential.py:213-219)
+ * bfe_inner_com   : out4 = sums of vx m, vy m, vz m, m over the indices of the `ncenter` smallest (x^2+y^2+z^2)^0.5
+ *                   (potential.py:158-176: rrank.argsort()[0:ncenter]; pass vx = x ... for a set's own centre; the
+ *                   reference applies the DISC ranking to the halo arrays, potential.py:190-200); device doubles  */
+int bfe_bar_fourier(int64_t n, const double* x, const double* y, double minr, double maxr, double* out2, void* stream);
+int bfe_affine_xy(int64_t n, double angle, double cx, double cy, double cz,
+                  const double* x, const double* y, const double* z, double* xo, double* yo, double* zo, void* stream);
+int bfe_inner_com(int64_t n, const double* x, const double* y, const double* z,
+                  const double* vx, const double* vy, const double* vz, const double* m,
+                  int64_t ncenter, double* out4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

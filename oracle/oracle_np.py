@@ -632,3 +632,29 @@ def leapfrog(F, nint, dt, pos0, vel0, rotfreq=0., no_odd=False, halo_l=-1, halo_
         a0 = a1
         record(step)
     return pos, vel, pot, traj
+
+
+# ---------------------------------------------------------------------------
+# pre-accumulation transforms
+# ---------------------------------------------------------------------------
+def bar_fourier_angle(posx, posy, minr=0., maxr=1.):
+    """pattern.BarTransform.bar_fourier_compute (analysis/pattern.py:155-169)."""
+    rr = (posx * posx + posy * posy) ** 0.5
+    w = np.where((rr > minr) & (rr < maxr))[0]
+    aval = np.sum(np.cos(2. * np.arctan2(posy[w], posx[w])))
+    bval = np.sum(np.sin(2. * np.arctan2(posy[w], posx[w])))
+    return np.arctan2(bval, aval) / 2.
+
+
+def bar_rotate(x, y, bar_angle):
+    """pattern.BarTransform.calculate_transform_and_return (pattern.py:118-121)."""
+    return x * np.cos(bar_angle) - y * np.sin(bar_angle), x * np.sin(bar_angle) + y * np.cos(bar_angle)
+
+
+def inner_center(xr, yr, zr, xv, yv, zv, mv, ncenter=10000):
+    """Fields.total_coefficients centring (potential.py:158-176, 190-200): rank by (x^2+y^2+z^2)^0.5 of the
+    r-arrays, mass-weighted mean of the v-arrays over the first ncenter indices."""
+    rrank = (xr * xr + yr * yr + zr * zr) ** 0.5
+    c = rrank.argsort()[0:ncenter]
+    return (np.sum(xv[c] * mv[c]) / np.sum(mv[c]), np.sum(yv[c] * mv[c]) / np.sum(mv[c]),
+            np.sum(zv[c] * mv[c]) / np.sum(mv[c]))

@@ -198,8 +198,8 @@ def test_fields_total_coefficients_in_memory(api):
         ef, sf, mf = S.write_fixture_files(tmp, eof_params=dict(mmax=2, numx=16, numy=12, nmax=8, norder=3),
                                            sl_params=dict(lmax=2, nmax=4, numr=100))
         F = potential.Fields('memory', ef, sf, mf, verbose=0)
-        with pytest.raises(NotImplementedError):
-            F.total_coefficients()
+        with pytest.raises(IOError):
+            F.total_coefficients()                         # no such PSP file (the reference fails the same way)
         disc = S.ParticleSet(*S.exponential_disc(3000, 1))
         halo = S.ParticleSet(*S.hernquist_halo(2000, 2))
         F.total_coefficients(disc=disc, halo=halo, halofac=2.0)
