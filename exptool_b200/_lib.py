@@ -59,6 +59,13 @@ SIGNATURES = {
     'bfe_sl_contract': (_INT, [_P, _P, _INT, _INT, _INT, _INT, _P]),
     'bfe_sl_force_contracted': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_sl_force': (_INT, [_P, _I64] + [_P] * 3 + [_P, _INT, _INT, _INT] + [_P] * 6 + [_P]),
+    'bfe_eof_return_bins': (_INT, [C.POINTER(EofParams), _I64] + [_P] * 6 + [_P]),
+    'bfe_eof_get_pot': (_INT, [_P, _I64, _P, _P, C.c_double, _P, _P, _P]),
+    'bfe_sl_radial_matrices': (_INT, [_P, _I64, _P, _P, _P, _P, _P]),
+    'bfe_legendre_tables': (_INT, [_INT, _I64, _P, _P, _P, _P]),
+    'bfe_sl_contract_density': (_INT, [_P, _P, _INT, _INT, _INT, _INT, _P]),
+    'bfe_sl_density_contracted': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 2 + [_P]),
+    'bfe_sl_density_eval_points': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 2 + [_P]),
     'bfe_sl_force_eval_points': (_INT, [_P, _I64] + [_P] * 3 + [_INT] + [_P] * 5 + [_P]),
     'bfe_field_force_cart': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),
     'bfe_field_force_cyl': (_INT, [_P, _P, _I64] + [_P] * 3 + [_DBL, _P, _P]),

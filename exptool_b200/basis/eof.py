@@ -152,6 +152,41 @@ def clear_table_cache():
 
 
 # ---------------------------------------------------------------------------
+# per-point building blocks -- eof.py:354-457 (evaluated on the device like everything else)
+# ---------------------------------------------------------------------------
+def return_bins(r, z, rmin=0, dR=0, zmin=0, dZ=0, numx=0, numy=0, ASCALE=0.01, HSCALE=0.001, CMAP=0):
+    '''
+    eof.return_bins (eof.py:354-427): X, Y (exact table coordinates), ix, iy (truncated bins).
+    The lower edge clamps ix and X; the upper edge clamps ix only, so X extrapolates (414-415).
+    Scalars in give 0-d arrays out, as in the reference.
+    '''
+    scalar = np.ndim(r) == 0
+    r1 = np.atleast_1d(np.asarray(r, dtype=np.float64))
+    z1 = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    X, Y, ix, iy = ops.eof_return_bins(r1, z1, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP)
+    X, Y = ops.to_host(X), ops.to_host(Y)
+    ix, iy = ops.to_host(ix).astype(int), ops.to_host(iy).astype(int)
+    if scalar:
+        return np.squeeze(X), np.squeeze(Y), np.squeeze(ix), np.squeeze(iy)
+    return X, Y, ix, iy
+
+
+def get_pot(r, z, cos_array, sin_array, rmin=0, dR=0, zmin=0, dZ=0, numx=0, numy=0, fac=1.0, MMAX=6, NMAX=18,
+            ASCALE=0.01, HSCALE=0.001, CMAP=0):
+    '''
+    eof.get_pot (eof.py:430-457): bilinear interpolation of every (m, n) cosine and sine table at the
+    points -> Vc, Vs of shape (m, n, npoints).  The m=0 sine plane is taken as zero (parse_eof, eof.py:293).
+    '''
+    cos_array = np.asarray(cos_array); sin_array = np.asarray(sin_array)
+    r1 = np.atleast_1d(np.asarray(r, dtype=np.float64))
+    z1 = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    E = device_tables(cos_array, sin_array, cos_array.shape[0] - 1, cos_array.shape[1], rmin, dR, zmin, dZ, numx, numy,
+                      ASCALE, HSCALE, CMAP)
+    Vc, Vs = E.get_pot(r1, z1, fac=fac)
+    return ops.to_host(Vc), ops.to_host(Vs)
+
+
+# ---------------------------------------------------------------------------
 # accumulation -- eof.py:492-640, 1415-1455, 1158-1260
 # ---------------------------------------------------------------------------
 def accumulate(ParticleInstance, potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP,
@@ -281,6 +316,32 @@ def force_eval(r, z, phi, accum_cos, accum_sin, potC, rforceC, zforceC, potS, rf
     return _scalar_or_array((fr, fp, fz, p, p0, fr0, fz0), scalar)
 
 
+def accumulated_eval(r, z, phi, accum_cos, accum_sin, potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS,
+                     rmin=0, dR=0, zmin=0, dZ=0, numx=0, numy=0, fac=1.0, MMAX=6, NMAX=18, ASCALE=0.0, HSCALE=0.0,
+                     CMAP=0, no_odd=False):
+    '''
+    eof.accumulated_eval (eof.py:874-929): p0, p, fr, fp, fz, d0, d at a point (or equal-length arrays of
+    points).  Here p and d are the TOTAL sums (m=0 included; p0, d0 are the m=0 parts), and no_odd skips
+    odd m entirely (896-897).  Density tables that are scalars / None give d0 = d = 0.
+    '''
+    scalar = np.ndim(r) == 0
+    r1 = np.atleast_1d(np.asarray(r, dtype=np.float64))
+    z1 = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    p1 = np.atleast_1d(np.asarray(phi, dtype=np.float64))
+    E = device_tables(potC, potS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
+                      rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)
+    E.contract(accum_cos, accum_sin, m1=0, m2=MMAX, nuse=NMAX, no_odd=no_odd)
+    fr, fp, fz, p, p0 = ops.to_host(E.force_eval_points(r1, z1, p1))
+    if np.ndim(densC) == 4 and np.ndim(densS) == 4:
+        D = device_tables(densC, densS, MMAX, NMAX, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP,
+                          rforceC=densC, zforceC=densC, rforceS=densS, zforceS=densS)
+        D.contract(accum_cos, accum_sin, m1=0, m2=MMAX, nuse=NMAX, no_odd=no_odd)
+        _, _, _, d, d0 = ops.to_host(D.force_eval_points(r1, z1, p1))
+    else:
+        d0 = np.zeros_like(p0); d = np.zeros_like(p0)
+    return _scalar_or_array((p0, p, fr, fp, fz, d0, d), scalar)
+
+
 def accumulated_eval_particles(Particles, accum_cos, accum_sin, potC=0, rforceC=0, zforceC=0, potS=0, rforceS=0,
                                zforceS=0, rmin=0, dR=0, zmin=0, dZ=0, numx=0, numy=0, MMAX=6, NMAX=18, ASCALE=0.0,
                                HSCALE=0.0, CMAP=0, m1=0, m2=1000, verbose=1, density=False, eof_file=''):
@@ -328,6 +389,52 @@ def compute_forces(PSPInput, EOF_Object, verbose=1, nprocs=-1, m1=0, m2=1000, de
                                       rforceS, zforceS, rmin=XMIN, dR=dX, zmin=YMIN, dZ=dY, numx=numx, numy=numy,
                                       MMAX=mmax, NMAX=norder, ASCALE=ascale, HSCALE=hscale, CMAP=cmap, m1=m1, m2=m2,
                                       verbose=verbose, density=density)
+
+
+# ---------------------------------------------------------------------------
+# the reference's process fan-out helpers (eof.py:1333-1455, 1521-1590), kept call-compatible.  The reference
+# cuts the particle set into `nprocs` blocks for a multiprocessing.Pool; here the blocks are consecutive device
+# launches (or ranks, see parallel.py), and the partition is the reference's own.
+# ---------------------------------------------------------------------------
+def redistribute_particles(ParticleInstance, divisions):
+    '''eof.redistribute_particles (eof.py:1333-1362): block 0 takes the remainder.'''
+    x, y, z, m = particle.particle_arrays(ParticleInstance)
+    from .. import parallel
+    holders = []
+    for lo, hi in parallel.shard_bounds(len(x), divisions):
+        h = particle.holder()
+        h.xpos, h.ypos, h.zpos, h.mass = x[lo:hi], y[lo:hi], z[lo:hi], m[lo:hi]
+        holders.append(h)
+    return holders
+
+
+def multi_accumulate(holding, nprocs, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap,
+                     verbose=0, no_odd=False, VAR=False):
+    '''eof.multi_accumulate (eof.py:1371-1412): list of (accum_cos, accum_sin), one pair per block.'''
+    return [accumulate(holding[i], potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap,
+                       verbose=verbose if i == 0 else 0, no_odd=no_odd, VAR=VAR) for i in range(nprocs)]
+
+
+def mix_outputs(MultiOutput, density=False):
+    '''
+    eof.mix_outputs (eof.py:1547-1590): concatenate per-block outputs in block order.  (The reference's
+    density branch never advances its write offset, eof.py:1567-1575; the blocks are concatenated here.)
+    '''
+    ncol = 8 if density else 6
+    return tuple(np.concatenate([np.asarray(MultiOutput[i][c], dtype=np.float64) for i in range(len(MultiOutput))])
+                 for c in range(ncol))
+
+
+def find_forces_multi(ParticleInstance, nprocs, a_cos, a_sin, potC, rforceC, zforceC, potS, rforceS, zforceS, XMIN, dX,
+                      YMIN, dY, numx, numy, mmax, norder, ascale, hscale, cmap, m1=0, m2=1000, verbose=0, density=False):
+    '''
+    eof.find_forces_multi (eof.py:1521-1541).  As in the reference the m window passed in is ignored
+    (0..1000 is hard-coded at 1528).  One device pass over the whole set replaces the Pool.
+    '''
+    return accumulated_eval_particles(ParticleInstance, a_cos, a_sin, potC=potC, rforceC=rforceC, zforceC=zforceC,
+                                      potS=potS, rforceS=rforceS, zforceS=zforceS, rmin=XMIN, dR=dX, zmin=YMIN, dZ=dY,
+                                      numx=numx, numy=numy, MMAX=mmax, NMAX=norder, ASCALE=ascale, HSCALE=hscale,
+                                      CMAP=cmap, m1=0, m2=1000, verbose=verbose, density=density)
 
 
 # ---------------------------------------------------------------------------

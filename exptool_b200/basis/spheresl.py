@@ -67,6 +67,8 @@ def device_tables_from_files(sph_file, model_file):
 
 
 def _fingerprint(a):
+    if a is None:
+        return None
     a = np.asarray(a)
     flat = a.reshape(-1)
     step = max(1, flat.size // 509)
@@ -76,7 +78,7 @@ def _fingerprint(a):
 def device_tables(xi, p0, d0, cmap, scale, evtable, eftable):
     """ops.SLTables for host arrays (full table extent; lmax/nmax truncation happens at contraction)."""
     evtable = np.asarray(evtable); eftable = np.asarray(eftable)
-    key = (_fingerprint(xi), _fingerprint(p0), _fingerprint(evtable), _fingerprint(eftable), int(cmap), float(scale),
+    key = (_fingerprint(xi), _fingerprint(p0), _fingerprint(d0), _fingerprint(evtable), _fingerprint(eftable), int(cmap), float(scale),
            _dev_id())
     H = _ARRAY_CACHE.get(key)
     if H is None:
@@ -92,6 +94,58 @@ def device_tables(xi, p0, d0, cmap, scale, evtable, eftable):
 def clear_table_cache():
     _FILE_CACHE.clear()
     _ARRAY_CACHE.clear()
+
+
+# ---------------------------------------------------------------------------
+# per-point building blocks -- spheresl.py:106-160, 301-335, 664-770 (device evaluations)
+# ---------------------------------------------------------------------------
+def _radial(x, lmax, nmax, evtable, eftable, xi, d0, p0, cmap, scale, dens, force, pot):
+    scalar = np.ndim(x) == 0
+    r1 = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    H = device_tables(xi, p0, d0, cmap, scale, np.asarray(evtable)[:lmax + 1, :nmax], np.asarray(eftable)[:lmax + 1, :nmax])
+    outs = H.radial_matrices(r1, dens=dens, force=force, pot=pot)
+    res = []
+    for o in outs:
+        if o is None:
+            continue
+        a = ops.to_host(o)
+        res.append(a[:, :, 0].copy() if scalar else a)
+    return res
+
+
+def get_halo_dens_pot_force(x, lmax, nmax, evtable, eftable, xi, d0, p0, cmap, scale):
+    '''spheresl.get_halo_dens_pot_force (spheresl.py:106-160): dens, force, pot matrices (lmax+1, nmax) at radius x
+    (or (lmax+1, nmax, n) for an array of radii).  Return order dens, force, pot (160).'''
+    return tuple(_radial(x, lmax, nmax, evtable, eftable, xi, d0, p0, cmap, scale, True, True, True))
+
+
+def get_halo_pot_matrix(x_in, lmax, nmax, evtable, eftable, xi, p0, cmap, scale):
+    '''spheresl.get_halo_pot_matrix (spheresl.py:301-335)'''
+    return _radial(x_in, lmax, nmax, evtable, eftable, xi, None, p0, cmap, scale, False, False, True)[0]
+
+
+def get_halo_dens(x, lmax, nmax, evtable, eftable, xi, d0, cmap, scale):
+    '''spheresl.get_halo_dens (spheresl.py:163-189): the density matrix alone (p0 is not used by it).'''
+    return _radial(x, lmax, nmax, evtable, eftable, xi, d0, np.zeros_like(np.asarray(d0, dtype=np.float64)), cmap, scale,
+                   True, False, False)[0]
+
+
+def legendre_R(lmax, x):
+    '''spheresl.legendre_R (spheresl.py:664-700): P_l^m(x) as (lmax+1, lmax+1) (or (.., .., n) for an array x)'''
+    scalar = np.ndim(x) == 0
+    P, _ = ops.legendre_tables(lmax, np.atleast_1d(np.asarray(x, dtype=np.float64)), derivative=False)
+    P = ops.to_host(P)
+    return P[:, :, 0].copy() if scalar else P
+
+
+def dlegendre_R(lmax, x):
+    '''spheresl.dlegendre_R (spheresl.py:706-770): (P, dP)'''
+    scalar = np.ndim(x) == 0
+    P, dP = ops.legendre_tables(lmax, np.atleast_1d(np.asarray(x, dtype=np.float64)), derivative=True)
+    P, dP = ops.to_host(P), ops.to_host(dP)
+    if scalar:
+        return P[:, :, 0].copy(), dP[:, :, 0].copy()
+    return P, dP
 
 
 # ---------------------------------------------------------------------------
@@ -175,14 +229,16 @@ def force_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax, evta
 def all_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax, evtable, eftable, no_odd=False, verbose=0):
     '''
     spheresl.all_eval (spheresl.py:987-1102): den0, den1, pot0, pot1, potr, pott, potp with
-    cos/sin(m phi).  den0/den1 are outside the path and returned as 0.
+    cos/sin(m phi).  As in the reference den1 is the TOTAL density (monopole included, 1046)
+    and both densities carry densfac = 0.25/pi (1092).
     '''
     scalar, r1, c1, p1 = _points(r, costh, phi)
     H = device_tables(xi, p0, d0, cmap, scale, evtable, eftable)
     H.contract(expcoef, l1=0, l2=lmax, nuse=nmax, no_odd=no_odd)
     potr, pott, potp, pot1, pot0 = ops.to_host(H.force_eval_points(r1, c1, p1, trig_index_l=False))
-    zero = np.zeros_like(pot0)
-    out = (zero, zero, pot0, pot1, potr, pott, potp)
+    H.contract_density(expcoef, l1=0, l2=lmax, nuse=nmax, no_odd=no_odd)
+    den0, den1 = ops.to_host(H.density_eval_points(r1, c1, p1))
+    out = (den0, den1, pot0, pot1, potr, pott, potp)
     if scalar:
         return tuple(np.float64(v[0]) for v in out)
     return out
@@ -191,14 +247,17 @@ def all_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax, evtabl
 def all_eval_particles(Particles, expcoef, sph_file, mod_file, verbose, L1=-1000, L2=1000, NO_ODD=False):
     '''
     spheresl.all_eval_particles (spheresl.py:1240-1362):
-    den0, den1, pot0, pot1, potr, pott, potp, rr per particle (den0/den1 returned as 0).
+    den0, den1, pot0, pot1, potr, pott, potp, rr per particle.  The density outputs follow the
+    reference line by line: den1 excludes the monopole (1271), its m=0 terms are weighted by
+    legs[1][0] (1323), and densfac = 0.25*pi (1351).
     '''
     H, _ = device_tables_from_files(sph_file, mod_file)
     x, y, z, _m = particle.particle_arrays(Particles)
     H.contract(expcoef, l1=L1, l2=L2, no_odd=NO_ODD)
     pot0, pot1, potr, pott, potp, rr = ops.to_host(H.force(x, y, z))
-    zero = np.zeros_like(pot0)
-    return zero, zero.copy(), pot0, pot1, potr, pott, potp, rr
+    H.contract_density(expcoef, l1=L1, l2=L2, no_odd=NO_ODD)
+    den0, den1 = ops.to_host(H.density(x, y, z))
+    return den0, den1, pot0, pot1, potr, pott, potp, rr
 
 
 def eval_particles(ParticleInstance, expcoef, sph_file, mod_file, nprocs=-1, l1=0, l2=1000, verbose=1, no_odd=False):

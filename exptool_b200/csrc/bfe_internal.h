@@ -62,6 +62,10 @@ struct bfe_sl {
     double* xi;          // [numr]
     double* p0;          // [numr]
     double* d0;          // [numr]
+    int have_d0;         // bfe_sl_create was given the model density table
+    double* ev;          // eigenvalues [(lmax+1)*nmax] (density rows are ef*sqrt(ev), spheresl.py:148)
+    double* ad_con;      // contracted DENSITY rows, same layout as a_con (allocated on first use)
+    int dens_contracted;
     double* fac;         // factorial_return [(lmax+1)*(lmax+1)]
     double fac_host[(BFE_MAX_LMAX + 1) * (BFE_MAX_LMAX + 1)];
     double* a_con;       // contracted rows, node-major [numr][kpad] of double2 (cos, sin), kpad = (l,m) pairs

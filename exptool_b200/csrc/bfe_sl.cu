@@ -153,7 +153,8 @@ sl_reduce_partials_kernel(const double* __restrict__ partial, int nrows, int nco
 // A[i][q].{x,y} = sum_{n<nuse} c[k][n] * e_node[i][l][n]; rows outside the l window are zero.
 // grid: (ceil(numr/128), nrow); the m=0 sine slots stay zero from create().
 __global__ void sl_contract_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ expcoef,
-                                   int l1, int l2, int nuse, int no_odd, double* __restrict__ A, int qstride) {
+                                   int l1, int l2, int nuse, int no_odd, double* __restrict__ A, int qstride,
+                                   const double* __restrict__ scale_ln) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (i >= g.numr || k >= g.nrow) return;
@@ -169,7 +170,12 @@ __global__ void sl_contract_kernel(SlGeom g, const double* __restrict__ e_node, 
         const double* e = e_node + (size_t)i * g.ln + l * g.nmax;
         const double* c = expcoef + (size_t)k * g.nmax;
         const int nn = nuse < g.nmax ? nuse : g.nmax;
-        for (int q = 0; q < nn; ++q) s = fma(__ldg(c + q), __ldg(e + q), s);
+        if (scale_ln) {                            // density rows: e_node * ev = ef * sqrt(ev)   (spheresl.py:148)
+            const double* w = scale_ln + l * g.nmax;
+            for (int q = 0; q < nn; ++q) s = fma(__ldg(c + q) * __ldg(w + q), __ldg(e + q), s);
+        } else {
+            for (int q = 0; q < nn; ++q) s = fma(__ldg(c + q), __ldg(e + q), s);
+        }
     }
     A[((size_t)i * qstride + (l * (l + 1)) / 2 + m) * 2 + comp] = s;
 }
@@ -283,6 +289,70 @@ sl_points_kernel(SlGeom g, const double2* __restrict__ A, int kpad, const double
 }
 
 // ---------------------------------------------------------------------------
+// Density outputs den0, den1 of spheresl.all_eval (points, 987-1102) and spheresl.all_eval_particles
+// (particles, 1240-1362) from contracted density rows  Ad[i][q] = sum_n c[k][n] ef[l,n,i] sqrt(ev[l,n]):
+//   dens contribution = (x1 Ad[i] + x2 Ad[i+1]) * (x1 d0[i] + x2 d0[i+1])        (spheresl.py:148)
+// The two functions differ and each is reproduced as written:
+//   all_eval            den1 starts from the monopole (1046), m=0 term legs[l][0] (1071), densfac 0.25/pi (1092)
+//   all_eval_particles  den1 starts from 0 (1271),   m=0 term legs[1][0] (1323),      densfac 0.25*pi (1351)
+// POINTS = true: inputs are (r, costh, phi); false: (x, y, z) with r = sqrt(x^2+y^2+z^2) (1257).
+// ---------------------------------------------------------------------------
+template <int LCAP, bool POINTS>
+__global__ void __launch_bounds__(128)
+sl_density_kernel(SlGeom g, const double2* __restrict__ Ad, int qstride, const double* __restrict__ xi,
+                  const double* __restrict__ d0tab, const double* __restrict__ fac, int64_t n,
+                  const double* __restrict__ a, const double* __restrict__ b_, const double* __restrict__ c,
+                  double* __restrict__ den0, double* __restrict__ den1) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double r, costh, c1, s1;
+        if (POINTS) {
+            r = __ldg(a + i); costh = __ldg(b_ + i);
+            sincos(__ldg(c + i), &s1, &c1);
+        } else {
+            const double px = __ldg(a + i), py = __ldg(b_ + i), pz = __ldg(c + i);
+            r = sqrt(BFE_ADD(BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py)), BFE_MUL(pz, pz)));
+            costh = BFE_DIV(pz, r);
+            bfe_cossin_phi(px, py, c1, s1);
+        }
+        const SlBin b = bfe_sl_bin(g, xi, r);
+        const double D0 = b.x1 * __ldg(d0tab + b.i) + b.x2 * __ldg(d0tab + b.i + 1);
+        const double w1 = b.x1 * D0, w2 = b.x2 * D0;
+        const double2* row0 = Ad + (size_t)b.i * qstride;
+        const double2* row1 = row0 + qstride;
+        LegTable<LCAP> T;
+        bfe_legendre<LCAP>(g.lmax, costh, T);
+        const double mono = __ldg(fac) * (w1 * __ldg(row0).x + w2 * __ldg(row1).x);
+        double sum = POINTS ? mono : 0.0;
+        const double p10 = (g.lmax >= 1) ? T.p[1][0] : 0.0;
+        double cm = 1.0, sm = 0.0;
+#pragma unroll
+        for (int m = 0; m <= LCAP; ++m) {
+            if (m <= g.lmax) {
+                if (m > 0) { const double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1; cm = cn; sm = sn; }
+#pragma unroll
+                for (int l = (m > 1 ? m : 1); l <= LCAP; ++l) {
+                    if (l <= g.lmax) {
+                        const int q = (l * (l + 1)) / 2 + m;
+                        const double2 a0 = __ldg(row0 + q), a1 = __ldg(row1 + q);
+                        const double fl = __ldg(fac + l * (g.lmax + 1) + m);
+                        const double sc = w1 * a0.x + w2 * a1.x;
+                        if (m == 0) {
+                            sum += fl * (POINTS ? T.p[l][0] : p10) * sc;
+                        } else {
+                            const double ss = w1 * a0.y + w2 * a1.y;
+                            sum += fl * T.p[l][m] * (sc * cm + ss * sm);
+                        }
+                    }
+                }
+            }
+        }
+        const double densfac = POINTS ? 0.25 / M_PI : 0.25 * M_PI;
+        den0[i] = mono * densfac;
+        den1[i] = sum * densfac;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static int sl_grid_for(int64_t n, int block, int num_sms, int per_sm) {
@@ -344,6 +414,10 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->xi, nr * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->p0, nr * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->d0, nr * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->ev, (size_t)g.ln * sizeof(double)));
+    h->have_d0 = d0 ? 1 : 0;
+    h->ad_con = nullptr;
+    h->dens_contracted = 0;
     BFE_CUDA(cudaMalloc(&h->fac, sizeof(double) * (p->lmax + 1) * (p->lmax + 1)));
     BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * 2 * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->a3, nr * h->kpad * 3 * 2 * sizeof(double)));
@@ -356,6 +430,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMemcpyAsync(h->xi, xi, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     BFE_CUDA(cudaMemcpyAsync(h->p0, p0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     if (d0) BFE_CUDA(cudaMemcpyAsync(h->d0, d0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    BFE_CUDA(cudaMemcpyAsync(h->ev, evtable, (size_t)g.ln * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     // factorial_return, spheresl.py:823-863 (lgamma for scipy.special.gammaln)
     for (int l = 0; l <= p->lmax; ++l)
         for (int m = 0; m <= p->lmax; ++m) {
@@ -379,6 +454,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
 extern "C" void bfe_sl_destroy(bfe_sl* h) {
     if (!h) return;
     cudaFree(h->e_node); cudaFree(h->xi); cudaFree(h->p0); cudaFree(h->d0); cudaFree(h->fac);
+    cudaFree(h->ev); if (h->ad_con) cudaFree(h->ad_con);
     cudaFree(h->a_con); cudaFree(h->a3); cudaFree(h->partial); cudaFree(h->counter);
     if (h->sort_ws) cudaFree(h->sort_ws);
     delete h;
@@ -406,7 +482,7 @@ extern "C" int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2,
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nuse < 0) nuse = 0;
     dim3 grd((h->g.numr + 127) / 128, h->g.nrow);
-    sl_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->e_node, expcoef, l1, l2, nuse, no_odd, h->a_con, h->kpad);
+    sl_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->e_node, expcoef, l1, l2, nuse, no_odd, h->a_con, h->kpad, nullptr);
     BFE_LAUNCH_CHECK("sl_contract_kernel");
     h->contracted = 1;
     h->a3_valid = 0;
@@ -494,4 +570,51 @@ extern "C" int bfe_sl_force_eval_points(bfe_sl* h, int64_t n, const double* r, c
                 potr, pott, potp, pot1, pot0);
     BFE_LAUNCH_CHECK("sl_points_kernel");
     return BFE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// density outputs
+// ---------------------------------------------------------------------------
+extern "C" int bfe_sl_contract_density(bfe_sl* h, const double* expcoef, int l1, int l2, int nuse, int no_odd,
+                                       void* stream_) {
+    if (!h || !expcoef) return BFE_ERR_ARG;
+    if (!h->have_d0) return BFE_ERR_STATE;           // created without the model density table
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!h->ad_con) {
+        const size_t bytes = (size_t)h->g.numr * h->kpad * 2 * sizeof(double);
+        BFE_CUDA(cudaMalloc(&h->ad_con, bytes));
+        BFE_CUDA(cudaMemsetAsync(h->ad_con, 0, bytes, stream));     // m=0 sine slots stay zero
+    }
+    if (nuse < 0) nuse = 0;
+    dim3 grd((h->g.numr + 127) / 128, h->g.nrow);
+    sl_contract_kernel<<<grd, 128, 0, stream>>>(h->g, h->e_node, expcoef, l1, l2, nuse, no_odd, h->ad_con, h->kpad, h->ev);
+    BFE_LAUNCH_CHECK("sl_contract_kernel");
+    h->dens_contracted = 1;
+    return BFE_OK;
+}
+
+template <bool POINTS>
+static int sl_density_launch(bfe_sl* h, int64_t n, const double* a, const double* b, const double* c,
+                             double* den0, double* den1, cudaStream_t stream) {
+    if (!h || n < 0) return BFE_ERR_ARG;
+    if (!h->dens_contracted) return BFE_ERR_STATE;
+    if (n == 0) return BFE_OK;
+    if (!a || !b || !c || !den0 || !den1) return BFE_ERR_ARG;
+    int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    const double2* Ad = reinterpret_cast<const double2*>(h->ad_con);
+    if (h->g.lmax <= 4)      sl_density_kernel<4, POINTS><<<grid, 128, 0, stream>>>(h->g, Ad, h->kpad, h->xi, h->d0, h->fac, n, a, b, c, den0, den1);
+    else if (h->g.lmax <= 6) sl_density_kernel<6, POINTS><<<grid, 128, 0, stream>>>(h->g, Ad, h->kpad, h->xi, h->d0, h->fac, n, a, b, c, den0, den1);
+    else                     sl_density_kernel<BFE_MAX_LMAX, POINTS><<<grid, 128, 0, stream>>>(h->g, Ad, h->kpad, h->xi, h->d0, h->fac, n, a, b, c, den0, den1);
+    BFE_LAUNCH_CHECK("sl_density_kernel");
+    return BFE_OK;
+}
+
+extern "C" int bfe_sl_density_contracted(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,
+                                         double* den0, double* den1, void* stream) {
+    return sl_density_launch<false>(h, n, x, y, z, den0, den1, (cudaStream_t)stream);
+}
+
+extern "C" int bfe_sl_density_eval_points(bfe_sl* h, int64_t n, const double* r, const double* costh,
+                                          const double* phi, double* den0, double* den1, void* stream) {
+    return sl_density_launch<true>(h, n, r, costh, phi, den0, den1, (cudaStream_t)stream);
 }

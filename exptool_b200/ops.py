@@ -106,6 +106,15 @@ class EOFTables(object):
         except Exception:
             pass
 
+    def get_pot(self, r, z, fac=1.0):
+        """eof.get_pot (eof.py:430-457): Vc, Vs as (mmax+1, norder, n) device tensors."""
+        r, z = dev(r), dev(z)
+        n = r.numel()
+        Vc = torch.empty((self.mmax + 1, self.norder, n), dtype=torch.float64, device=self.device)
+        Vs = torch.empty_like(Vc)
+        _lib.check(self.lib.bfe_eof_get_pot(self.h, n, _ptr(r), _ptr(z), float(fac), _ptr(Vc), _ptr(Vs), _stream()))
+        return Vc, Vs
+
     def clone(self):
         """
         A second handle on the same device tables with its own contraction, workspaces and counters
@@ -312,6 +321,41 @@ class SLTables(object):
                                                     *[_ptr(out[i]) for i in range(6)], _stream()))
         return out
 
+    def radial_matrices(self, r, dens=True, force=True, pot=True):
+        """spheresl.get_halo_dens_pot_force (spheresl.py:106-160) at n radii: (dens, force, pot), each
+        (lmax+1, nmax, n) or None when not requested."""
+        r = dev(r)
+        n = r.numel()
+        outs = [torch.empty((self.lmax + 1, self.nmax, n), dtype=torch.float64, device=self.device) if want else None
+                for want in (dens, force, pot)]
+        _lib.check(self.lib.bfe_sl_radial_matrices(self.h, n, _ptr(r), *[_ptr(o) for o in outs], _stream()))
+        return tuple(outs)
+
+    def contract_density(self, expcoef, l1=-1000, l2=1000, nuse=None, no_odd=False):
+        """Density rows sum_n c ef sqrt(ev) (spheresl.py:148); needs d0 at construction."""
+        c = self._coef(expcoef)
+        nuse = self.nmax if nuse is None else int(nuse)
+        _lib.check(self.lib.bfe_sl_contract_density(self.h, _ptr(c), max(int(l1), 0), min(int(l2), self.lmax), nuse,
+                                                    int(bool(no_odd)), _stream()))
+
+    def density(self, x, y, z):
+        """den0, den1 of spheresl.all_eval_particles (spheresl.py:1271,1323,1351) -> (2, n)."""
+        x, y, z = dev(x), dev(y), dev(z)
+        n = x.numel()
+        out = torch.empty((2, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_sl_density_contracted(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(out[0]), _ptr(out[1]),
+                                                      _stream()))
+        return out
+
+    def density_eval_points(self, r, costh, phi):
+        """den0, den1 of spheresl.all_eval (spheresl.py:1046,1071,1092) -> (2, n)."""
+        r, costh, phi = dev(r), dev(costh), dev(phi)
+        n = r.numel()
+        out = torch.empty((2, n), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.bfe_sl_density_eval_points(self.h, n, _ptr(r), _ptr(costh), _ptr(phi), _ptr(out[0]),
+                                                       _ptr(out[1]), _stream()))
+        return out
+
     def force_eval_points(self, r, costh, phi, trig_index_l=True):
         """spheresl.force_eval (trig_index_l) / all_eval outputs potr, pott, potp, pot1, pot0."""
         r, costh, phi = dev(r), dev(costh), dev(phi)
@@ -416,3 +460,28 @@ def inner_center_of_mass(x, y, z, m, ncenter=10000, values=None):
                                          int(ncenter), _ptr(out), _stream()))
     sx, sy, sz, sm = out.cpu().tolist()
     return sx / sm, sy / sm, sz / sm
+
+
+def eof_return_bins(r, z, rmin, dR, zmin, dZ, numx, numy, ascale, hscale, cmap):
+    """eof.return_bins (eof.py:354-427) -> X, Y (float64), ix, iy (int64) device tensors."""
+    r, z = dev(r), dev(z)
+    n = r.numel()
+    params = _lib.EofParams(0, 1, int(numx), int(numy), int(cmap), 0, float(rmin), float(dR), float(zmin), float(dZ),
+                            float(ascale), float(hscale))
+    X = torch.empty(n, dtype=torch.float64, device=r.device)
+    Y = torch.empty_like(X)
+    ix = torch.empty(n, dtype=torch.int64, device=r.device)
+    iy = torch.empty_like(ix)
+    _lib.check(_lib.load().bfe_eof_return_bins(C.byref(params), n, _ptr(r), _ptr(z), _ptr(X), _ptr(Y), _ptr(ix), _ptr(iy),
+                                               _stream()))
+    return X, Y, ix, iy
+
+
+def legendre_tables(lmax, x, derivative=True):
+    """spheresl.legendre_R / dlegendre_R (spheresl.py:664-770) at n arguments: P, dP as (lmax+1, lmax+1, n)."""
+    x = dev(x)
+    n = x.numel()
+    P = torch.empty((lmax + 1, lmax + 1, n), dtype=torch.float64, device=x.device)
+    dP = torch.empty_like(P) if derivative else None
+    _lib.check(_lib.load().bfe_legendre_tables(int(lmax), n, _ptr(x), _ptr(P), _ptr(dP), _stream()))
+    return P, dP

@@ -206,6 +206,62 @@ def integrate_grid_3D_launchy(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, 
 
 
 # ---------------------------------------------------------------------------
+# the reference's process fan-out over radii -- integrate.py:290-333, 440-507.  Every orbit of the grid is one
+# thread of one leapfrog launch here (across ranks when torch.distributed is up: the radii are block-partitioned
+# exactly like redistribute_arrays, each rank integrates its block and the f4 blocks are gathered).
+# ---------------------------------------------------------------------------
+def redistribute_arrays(rads, divisions):
+    '''integrate.redistribute_arrays (integrate.py:440-463): block 0 takes the remainder.'''
+    from .. import parallel
+    rads = np.asarray(rads)
+    return [rads[lo:hi] for lo, hi in parallel.shard_bounds(rads.size, divisions)]
+
+
+def re_form_orbit_arrays(array):
+    '''integrate.re_form_orbit_arrays (integrate.py:469-489): concatenate along the radius axis, cast to f4.'''
+    return np.concatenate([np.asarray(a) for a in array], axis=0).astype('f4')
+
+
+def re_form_orbit_arrays_3D(array):
+    '''integrate.re_form_orbit_arrays_3D (integrate.py:491-507)'''
+    return np.concatenate([np.asarray(a) for a in array], axis=0).astype('f4')
+
+
+def do_integrate_multi(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max,
+                       verbose=0, nprocs=-1, threedee=False, zs=None, vzs=None, launch='x'):
+    '''
+    integrate.do_integrate_multi (integrate.py:290-333): the orbit grid as one f4 array
+    [rad, vel, 7, nint] (or [rad, vel, z, vz, 9, nint] with threedee).  `nprocs` is accepted for call
+    compatibility; the whole grid is one device launch per rank.
+    '''
+    import time
+    from .. import parallel
+    rads = np.asarray(rads, dtype=np.float64); vels = np.asarray(vels, dtype=np.float64)
+    t1 = time.time()
+    rank, ws = parallel.world()
+    mine = redistribute_arrays(rads, ws)[rank] if ws > 1 else rads
+    launch_y = (launch == 'y')
+    if threedee:
+        if (zs is None) or (vzs is None):
+            print('ERROR: 3D orbit specified, but no z or vz values passed!')
+            return None
+        block = _integrate_grid_3d(mine, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, zs, vzs,
+                                   launch_y)
+    else:
+        block = _integrate_grid_2d(mine, vels, F, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_res, ap_max, launch_y)
+    block = block.astype('f4')
+    if ws > 1:
+        import torch.distributed as dist
+        blocks = [None] * ws
+        dist.all_gather_object(blocks, block)
+        block = re_form_orbit_arrays_3D(blocks) if threedee else re_form_orbit_arrays(blocks)
+    if verbose > 0:
+        print('Total integration calculation took {0:3.2f} seconds, or {1:3.2f} seconds per orbit.'
+              .format(time.time() - t1, (time.time() - t1) / max(float(rads.size * vels.size), 1.)))
+    return block
+
+
+# ---------------------------------------------------------------------------
 # orbit-map text files -- integrate.py:513-569, 970-1038 (one line per orbit)
 # ---------------------------------------------------------------------------
 def print_orbit_array(f, OrbitArray):

@@ -184,6 +184,46 @@ int bfe_sl_force_eval_points(bfe_sl* h, int64_t n,
                              double* potr, double* pott, double* potp, double* pot1, double* pot0,
                              void* stream);
 
+/* Density outputs den0, den1 (a20; SURVEY.md App. C #8: the two reference functions differ and each is
+ * reproduced as written).  bfe_sl_contract_density forms the density rows
+ * sum_n expcoef[k,n] eftable[l,n,i] sqrt(ev[l,n]) (get_halo_dens_pot_force, spheresl.py:148) with the same
+ * truncation arguments as bfe_sl_contract; the handle must have been created with d0.
+ * bfe_sl_density_contracted: spheresl.all_eval_particles (spheresl.py:1271,1323,1351) per particle:
+ *   den1 without the monopole, m=0 terms weighted by legs[1][0], densfac = 0.25*pi.
+ * bfe_sl_density_eval_points: spheresl.all_eval (spheresl.py:1046,1071,1092) at (r, costh, phi):
+ *   den1 includes the monopole, densfac = 0.25/pi. */
+int bfe_sl_contract_density(bfe_sl* h, const double* expcoef, int l1, int l2, int nuse,
+                            int no_odd, void* stream);
+int bfe_sl_density_contracted(bfe_sl* h, int64_t n,
+                              const double* x, const double* y, const double* z,
+                              double* den0, double* den1, void* stream);
+int bfe_sl_density_eval_points(bfe_sl* h, int64_t n,
+                               const double* r, const double* costh, const double* phi,
+                               double* den0, double* den1, void* stream);
+
+/* ---------------------------------------------------------------- building blocks ----------- */
+/* The per-point pieces the kernels above evaluate inline, callable with the meaning of the reference's own
+ * helper functions.  Outputs are point-minor (trailing axis = the n points), like the reference's arrays. */
+
+/* eof.return_bins (eof.py:354-427): X, Y fractional bins, ix, iy truncated and clamped bins (int64).
+ * Lower edge clamps X; the upper edge clamps ix only (X extrapolates, eof.py:414-415).  No handle needed. */
+int bfe_eof_return_bins(const bfe_eof_params* p, int64_t n, const double* r, const double* z,
+                        double* X, double* Y, long long* ix, long long* iy, void* stream);
+
+/* eof.get_pot (eof.py:430-457) on the handle's potC / potS: Vc, Vs of (mmax+1)*norder*n doubles,
+ * [m][n][point]; the m=0 plane of Vs is zero (parse_eof leaves potS[0] zero, eof.py:293). */
+int bfe_eof_get_pot(bfe_eof* h, int64_t n, const double* r, const double* z, double fac,
+                    double* Vc, double* Vs, void* stream);
+
+/* spheresl.get_halo_dens_pot_force (spheresl.py:106-160) / get_halo_pot_matrix (301-335) at n radii:
+ * dens, force, pot of (lmax+1)*nmax*n doubles, [l][n][point]; any of the three may be NULL. */
+int bfe_sl_radial_matrices(bfe_sl* h, int64_t n, const double* r,
+                           double* dens, double* force, double* pot, void* stream);
+
+/* spheresl.legendre_R / dlegendre_R (spheresl.py:664-770) at n arguments: P (and dP unless NULL) of
+ * (lmax+1)*(lmax+1)*n doubles, [l][m][point], entries m > l zero, non-finite entries zero. */
+int bfe_legendre_tables(int lmax, int64_t n, const double* x, double* P, double* dP, void* stream);
+
 /* ---------------------------------------------------------------- combined field ------------ */
 
 /* Fields.return_forces_cart (potential.py:445-497) at n points in a frame rotated by rotpos:

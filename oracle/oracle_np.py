@@ -250,6 +250,50 @@ def eof_force_eval(r, z, phi, accum_cos, accum_sin, potC, rforceC, zforceC,
     return fr + fr0, fp, fz + fz0, p + p0, p0
 
 
+def eof_get_pot(r, z, cos_array, sin_array, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP, fac=1.0):
+    """eof.get_pot (eof.py:430-457) -> Vc, Vs of shape (m, n, N)."""
+    r = np.atleast_1d(np.asarray(r, np.float64)); z = np.atleast_1d(np.asarray(z, np.float64))
+    X, Y, ix, iy = eof_return_bins(r.copy(), z, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP)
+    c = _bilinear_weights(X, Y, ix, iy)
+    return fac * _interp(cos_array, ix, iy, *c), fac * _interp(sin_array, ix, iy, *c)
+
+
+def eof_accumulated_eval(r, z, phi, accum_cos, accum_sin, potC, rforceC, zforceC, densC, potS, rforceS, zforceS,
+                         densS, rmin, dR, zmin, dZ, numx, numy, MMAX, NMAX, ASCALE, HSCALE, CMAP, no_odd=False):
+    """
+    eof.accumulated_eval (eof.py:874-929), vectorised over points: (p0, p, fr, fp, fz, d0, d) with p, d the
+    TOTAL sums (m = 0 included, 925-927) and no_odd skipping odd m (896-897).
+    """
+    r = np.atleast_1d(np.asarray(r, np.float64)); z = np.atleast_1d(np.asarray(z, np.float64))
+    phi = np.atleast_1d(np.asarray(phi, np.float64))
+    X, Y, ix, iy = eof_return_bins(r.copy(), z, rmin, dR, zmin, dZ, numx, numy, ASCALE, HSCALE, CMAP)
+    c = _bilinear_weights(X, Y, ix, iy)
+    n = r.size
+    p = np.zeros(n); fr = np.zeros(n); fz = np.zeros(n); fp = np.zeros(n); d = np.zeros(n)
+    p0 = np.zeros(n); d0 = np.zeros(n)
+    for mm in range(0, MMAX + 1):
+        if (mm % 2 != 0) and no_odd:
+            continue
+        ccos = np.cos(phi * mm); ssin = np.sin(phi * mm)
+        ac = accum_cos[mm, :, None]; asn = accum_sin[mm, :, None]
+        vp = np.sum(ac * _interp(potC[mm], ix, iy, *c), axis=0)
+        p += ccos * vp
+        fr += ccos * np.sum(ac * _interp(rforceC[mm], ix, iy, *c), axis=0)
+        fz += ccos * np.sum(ac * _interp(zforceC[mm], ix, iy, *c), axis=0)
+        d += ccos * np.sum(ac * _interp(densC[mm], ix, iy, *c), axis=0)
+        fp += ssin * mm * vp
+        if mm > 0:
+            wp = np.sum(asn * _interp(potS[mm], ix, iy, *c), axis=0)
+            p += ssin * wp
+            fr += ssin * np.sum(asn * _interp(rforceS[mm], ix, iy, *c), axis=0)
+            fz += ssin * np.sum(asn * _interp(zforceS[mm], ix, iy, *c), axis=0)
+            d += ssin * np.sum(asn * _interp(densS[mm], ix, iy, *c), axis=0)
+            fp += -ccos * mm * wp
+        if mm == 0:
+            p0 = p.copy(); d0 = d.copy()
+    return p0, p, fr, fp, fz, d0, d
+
+
 # ---------------------------------------------------------------------------
 # SL tables -- halo_methods.py:178-220 (uses SciPy's own splrep/splev, as the
 # reference does; see SURVEY.md section 8c "run SciPy itself")
@@ -457,16 +501,55 @@ def _sl_field_sums(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
     return pot0, pot1, potr, pott, potp
 
 
+def _sl_density_sums(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
+                     evtable, eftable, l_lo, l_hi, no_odd, particles_variant):
+    """
+    Density outputs of the SL evaluation, quirks per function:
+      all_eval (spheresl.py:1041-1092): den1 starts from the monopole (1046), m=0 term uses
+        legs[l][0] (1071), densfac = 0.25/pi (1092);
+      all_eval_particles (1289-1351): den1 starts from 0 (1271), its m=0 term uses legs[1][0]
+        (1323), densfac = 0.25*pi (1351).
+    Returns (den0, den1).
+    """
+    factorial = factorial_return(lmax)
+    dend, _dpot, _potd = sl_dens_pot_force(r, lmax, nmax, evtable, eftable, xi, d0, p0, cmap, scale)
+    legs = legendre_R(lmax, costh)
+    c = expcoef[:, :nmax]
+    den0 = np.sum(factorial[0, 0] * c[0][:, None] * dend[0], axis=0)
+    den1 = np.zeros_like(den0) if particles_variant else den0.copy()
+    loffset = 1
+    for l in range(1, lmax + 1):
+        if (l > l_hi) or (l < l_lo) or ((l % 2 != 0) and no_odd):
+            loffset += 2 * l + 1
+            continue
+        moffset = 0
+        for m in range(l + 1):
+            f = factorial[l, m]
+            if m == 0:
+                leg = legs[1, 0] if particles_variant else legs[l, 0]
+                den1 += f * leg * np.sum(c[loffset + moffset][:, None] * dend[l], axis=0)
+                moffset += 1
+            else:
+                cosm = np.cos(phi * m); sinm = np.sin(phi * m)
+                cc = c[loffset + moffset][:, None]; cs = c[loffset + moffset + 1][:, None]
+                den1 += f * legs[l, m] * (np.sum(cc * dend[l], axis=0) * cosm + np.sum(cs * dend[l], axis=0) * sinm)
+                moffset += 2
+        loffset += 2 * l + 1
+    densfac = 0.25 * np.pi if particles_variant else 0.25 / np.pi
+    return den0 * densfac, den1 * densfac
+
+
 def sl_all_eval_particles(x, y, z, expcoef, lmax, nmax, evtable, eftable, xi, p0, d0,
-                          cmap, scale, L1=-1000, L2=1000, NO_ODD=False, chunk=16384):
+                          cmap, scale, L1=-1000, L2=1000, NO_ODD=False, chunk=16384, density=False):
     """
     spheresl.all_eval_particles (1240-1362): pot0, pot1, potr, pott, potp, rr with
-    r = sqrt(x^2+y^2+z^2) (no epsilon, 1257), trig cos/sin(m phi).  Density
-    outputs (den0, den1) are out of scope and not returned.
+    r = sqrt(x^2+y^2+z^2) (no epsilon, 1257), trig cos/sin(m phi).  With density=True the
+    tuple is the reference's own (den0, den1, pot0, pot1, potr, pott, potp, rr).
     """
     x = np.asarray(x, np.float64); y = np.asarray(y, np.float64); z = np.asarray(z, np.float64)
     n = x.size
     out = [np.zeros(n) for _ in range(5)]
+    den = [np.zeros(n) for _ in range(2)]
     rr = (x * x + y * y) ** 0.5
     for lo in range(0, n, chunk):
         sl = slice(lo, lo + chunk)
@@ -478,7 +561,14 @@ def sl_all_eval_particles(x, y, z, expcoef, lmax, nmax, evtable, eftable, xi, p0
                              evtable, eftable, L1, L2, NO_ODD, False)
         for o, v in zip(out, res):
             o[sl] = v
+        if density:
+            dres = _sl_density_sums(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
+                                    evtable, eftable, L1, L2, NO_ODD, True)
+            for o, v in zip(den, dres):
+                o[sl] = v
     pot0, pot1, potr, pott, potp = out
+    if density:
+        return den[0], den[1], pot0, pot1, potr, pott, potp, rr
     return pot0, pot1, potr, pott, potp, rr
 
 
@@ -499,12 +589,18 @@ def sl_force_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
 
 
 def sl_all_eval(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
-                evtable, eftable, no_odd=False):
-    """spheresl.all_eval (987-1102) potential part, for full lmax/nmax: (pot0,pot1,potr,pott,potp)."""
+                evtable, eftable, no_odd=False, density=False):
+    """spheresl.all_eval (987-1102) for full lmax/nmax: (pot0,pot1,potr,pott,potp), or with density=True
+    the reference's own (den0,den1,pot0,pot1,potr,pott,potp)."""
     r = np.atleast_1d(np.asarray(r, np.float64)); costh = np.atleast_1d(np.asarray(costh, np.float64))
     phi = np.atleast_1d(np.asarray(phi, np.float64))
-    return _sl_field_sums(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
+    pots = _sl_field_sums(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
                           evtable, eftable, -1000, 1000, no_odd, False)
+    if not density:
+        return pots
+    dens = _sl_density_sums(r, costh, phi, expcoef, xi, p0, d0, cmap, scale, lmax, nmax,
+                            evtable, eftable, -1000, 1000, no_odd, False)
+    return dens + tuple(pots)
 
 
 # ---------------------------------------------------------------------------

@@ -127,7 +127,7 @@ def test_spheresl_api(api, name):
         for key, kw in (('allp', {}), ('allp_win12', dict(L1=1, L2=2)), ('allp_noodd', dict(NO_ODD=True))):
             out = spheresl.all_eval_particles(Pf, d['coef'], sf, mf, 0, **kw)
             assert len(out) == 8
-            for j in (2, 3, 4, 5, 6, 7):
+            for j in range(8):            # incl. den0, den1 with the function's own quirks (App. C #8)
                 assert relerr(out[j], d[key][j]) < TOL, (key, j)
         lmax, nmax, numr, cmap, rmin, rmax, scale, ltable, evtable, eftable = halo_methods.read_cached_table(sf)
         xi, rarr, p0, d0 = halo_methods.init_table(mf, numr, rmin, rmax, cmap=cmap, scale=scale)
@@ -141,7 +141,7 @@ def test_spheresl_api(api, name):
                                   d0, cmap, scale, lmax, nmax, evtable, eftable)
         assert all(np.ndim(o) == 0 for o in one)
         out = spheresl.all_eval(*a, lmax, nmax, evtable, eftable)
-        for j in (2, 3, 4, 5, 6):
+        for j in range(7):                # den0, den1 (total density), pot0, pot1, potr, pott, potp
             assert relerr(out[j], d['ae_full'][:, j]) < TOL, j
 
 
@@ -309,3 +309,52 @@ def test_eof_density_api(api, name):
         # without density tables the flag is dropped and the six standard outputs come back (eof.py:1048-1050)
         six = eof.accumulated_eval_particles(P, d['cos'], d['sin'], eof_file=f, verbose=0)
         assert len(six) == 6 and relerr(six[1], d['full'][1]) < TOL
+
+
+def test_building_blocks_api(api):
+    """a5 return_bins, a6 get_pot, a11 accumulated_eval, a14/a15 radial matrices, a16 Legendre tables: the
+    reference's helper functions, evaluated on the device, against the unmodified reference (blocks_small.npz)."""
+    eof, spheresl, halo_methods = api['eof'], api['spheresl'], api['halo_methods']
+    d, meta = load_golden('blocks_small')
+    g = meta['geo']
+    with tempfile.TemporaryDirectory() as tmp:
+        f = _eof_file(tmp, meta)
+        potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS = eof.parse_eof(f)
+        geo = dict(rmin=g['XMIN'], dR=g['dX'], zmin=g['YMIN'], dZ=g['dY'], numx=g['numx'], numy=g['numy'],
+                   ASCALE=g['ascale'], HSCALE=g['hscale'], CMAP=g['cmap'])
+        X, Y, ix, iy = eof.return_bins(d['r'], d['z'], **geo)
+        assert relerr(X, d['X']) < TOL and relerr(Y, d['Y']) < TOL
+        assert np.array_equal(ix, d['ix']) and np.array_equal(iy, d['iy'])
+        one = eof.return_bins(float(d['r'][9]), float(d['z'][9]), **geo)
+        assert all(np.ndim(o) == 0 for o in one)
+        assert np.allclose([float(o) for o in one], d['bins_scalar'], rtol=1e-12, atol=0)
+        Vc, Vs = eof.get_pot(d['r'], d['z'], potC, potS, fac=1.0, MMAX=g['mmax'], NMAX=g['norder'], **geo)
+        assert Vc.shape == d['Vc'].shape and relerr(Vc, d['Vc']) < TOL and relerr(Vs, d['Vs']) < TOL
+        a = (d['r'], d['z'], d['phi'], d['cosc'], d['sinc'], potC, rforceC, zforceC, densC, potS, rforceS, zforceS, densS)
+        kw = dict(geo, MMAX=g['mmax'], NMAX=g['norder'])
+        for key, no_odd in (('ae', False), ('ae_noodd', True)):
+            out = eof.accumulated_eval(*a, no_odd=no_odd, **kw)
+            assert len(out) == 7
+            for j in range(7):
+                assert relerr(out[j], d[key][:, j]) < TOL, (key, j)
+        one = eof.accumulated_eval(float(d['r'][3]), float(d['z'][3]), float(d['phi'][3]), *a[3:], **kw)
+        assert all(np.ndim(o) == 0 for o in one) and abs(float(one[1]) - d['ae'][3, 1]) <= TOL * np.max(np.abs(d['ae'][:, 1]))
+        # the fan-out helpers keep the reference's partition and concatenate in block order
+        P = S.ParticleSet(d['r'], d['z'], d['phi'], np.ones_like(d['r']))
+        hold = eof.redistribute_particles(P, 3)
+        assert [len(h.xpos) for h in hold] == [14, 13, 13] and np.array_equal(np.concatenate([h.xpos for h in hold]), d['r'])
+        sf, mf = _sl_files(tmp, meta, seed_offset=1)
+        lmax, nmax, numr, cmap, rmin, rmax, scale, ltable, evtable, eftable = halo_methods.read_cached_table(sf)
+        xi, rarr, p0, d0 = halo_methods.init_table(mf, numr, rmin, rmax, cmap=cmap, scale=scale)
+        dens, force, pot = spheresl.get_halo_dens_pot_force(d['rad'], lmax, nmax, evtable, eftable, xi, d0, p0, cmap, scale)
+        for got, key in ((dens, 'dens'), (force, 'force'), (pot, 'pot')):
+            assert relerr(np.moveaxis(got, 2, 0), d[key]) < TOL, key
+        potm = spheresl.get_halo_pot_matrix(float(d['rad'][10]), lmax, nmax, evtable, eftable, xi, p0, cmap, scale)
+        assert potm.shape == (lmax + 1, nmax) and relerr(potm, d['potm'][10]) < TOL
+        densm = spheresl.get_halo_dens(d['rad'], lmax, nmax, evtable, eftable, xi, d0, cmap, scale)
+        assert relerr(np.moveaxis(densm, 2, 0), d['densm']) < TOL
+    L = meta['leg_lmax']
+    P, dP = spheresl.dlegendre_R(L, d['cth'])
+    assert relerr(np.moveaxis(P, 2, 0), d['P2']) < 1e-14 and relerr(np.moveaxis(dP, 2, 0), d['dP']) < TOL
+    P1 = spheresl.legendre_R(L, float(d['cth'][8]))
+    assert P1.shape == (L + 1, L + 1) and relerr(P1, d['P'][8]) < 1e-14

@@ -127,6 +127,10 @@ def test_sl_force_golden(ops, name):
         ref = d[key]          # den0,den1,pot0,pot1,potr,pott,potp,rr
         for i, j in enumerate((2, 3, 4, 5, 6, 7)):
             assert relerr(out[i], ref[j]) < TOL, (key, j)
+        H.contract_density(d['coef'], **kw)
+        den = H.density(xs, ys, zs).cpu().numpy()
+        for j in range(2):
+            assert relerr(den[j], ref[j]) < TOL, (key, 'den', j)
     L, N = p['lmax'], p['nmax']
     for key, (l, n, no_odd) in dict(fe_full=(L, N, False), fe_trunc=(max(L - 1, 1), max(N - 2, 1), False),
                                     fe_noodd=(L, N, True)).items():
@@ -138,6 +142,10 @@ def test_sl_force_golden(ops, name):
     out = H.force_eval_points(d['pt_r'], d['pt_costh'], d['pt_phi'], trig_index_l=False).cpu().numpy()
     for i, j in enumerate((4, 5, 6, 3, 2)):     # ae_full: den0,den1,pot0,pot1,potr,pott,potp
         assert relerr(out[i], d['ae_full'][:, j]) < TOL, j
+    H.contract_density(d['coef'])
+    den = H.density_eval_points(d['pt_r'], d['pt_costh'], d['pt_phi']).cpu().numpy()
+    for j in range(2):
+        assert relerr(den[j], d['ae_full'][:, j]) < TOL, ('den', j)
 
 
 def _field_handles(ops, meta, d):

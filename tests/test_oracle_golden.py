@@ -86,6 +86,10 @@ def test_sl_eval_particles(name):
         ref = d[key]          # den0,den1,pot0,pot1,potr,pott,potp,rr
         for i, j in enumerate((2, 3, 4, 5, 6, 7)):
             assert relerr(out[i], ref[j]) < TOL, (key, j)
+        # density outputs with the function's own quirks (spheresl.py:1323 legs[1][m], 1351 densfac = pi/4)
+        outd = O.sl_all_eval_particles(*a, density=True, **kw)
+        for j in range(8):
+            assert relerr(outd[j], ref[j]) < TOL, (key, 'density', j)
 
 
 @pytest.mark.parametrize('name', SL_CASES)
@@ -102,6 +106,9 @@ def test_sl_force_eval(name):
     out = O.sl_all_eval(*a, L, N, ev, ef)     # den0,den1,pot0,pot1,potr,pott,potp
     for i, j in enumerate((2, 3, 4, 5, 6)):
         assert relerr(out[i], d['ae_full'][:, j]) < TOL, j
+    outd = O.sl_all_eval(*a, L, N, ev, ef, density=True)     # den1 includes the monopole (spheresl.py:1046)
+    for j in range(7):
+        assert relerr(outd[j], d['ae_full'][:, j]) < TOL, ('density', j)
 
 
 @pytest.mark.parametrize('name', FIELD_CASES)
@@ -153,3 +160,45 @@ def test_eof_density_particles(name):
     for i in range(8):
         assert relerr(full[i], d['full'][i]) < TOL, i
         assert relerr(win[i], d['win12'][i]) < TOL, i
+
+
+# ---------------------------------------------------------------------------
+# per-point building blocks (a5, a6, a11 accumulated_eval, a14-a16): tests/golden/blocks_small.npz
+# ---------------------------------------------------------------------------
+def _blocks():
+    d, meta = load_golden('blocks_small')
+    pe, T, g = eof_tables(meta)
+    geo = (g['XMIN'], g['dX'], g['YMIN'], g['dY'], g['numx'], g['numy'])
+    return d, meta, T, g, geo
+
+
+def test_blocks_eof_bins_and_get_pot():
+    d, meta, T, g, geo = _blocks()
+    X, Y, ix, iy = O.eof_return_bins(d['r'].copy(), d['z'], *geo, g['ascale'], g['hscale'], g['cmap'])
+    assert relerr(X, d['X']) < 1e-14 and relerr(Y, d['Y']) < 1e-14
+    assert np.array_equal(ix, d['ix']) and np.array_equal(iy, d['iy'])
+    Vc, Vs = O.eof_get_pot(d['r'], d['z'], T['potC'], T['potS'], *geo, g['ascale'], g['hscale'], g['cmap'])
+    assert relerr(Vc, d['Vc']) < TOL and relerr(Vs, d['Vs']) < TOL
+
+
+def test_blocks_eof_accumulated_eval():
+    d, meta, T, g, geo = _blocks()
+    a = (d['r'], d['z'], d['phi'], d['cosc'], d['sinc'], T['potC'], T['rforceC'], T['zforceC'], T['densC'], T['potS'],
+         T['rforceS'], T['zforceS'], T['densS'], *geo, g['mmax'], g['norder'], g['ascale'], g['hscale'], g['cmap'])
+    for key, no_odd in (('ae', False), ('ae_noodd', True)):
+        out = O.eof_accumulated_eval(*a, no_odd=no_odd)
+        for j in range(7):
+            assert relerr(out[j], d[key][:, j]) < TOL, (key, j)
+
+
+def test_blocks_sl_radial_and_legendre():
+    d, meta = load_golden('blocks_small')
+    p, ev, ef, xi, p0, d0 = sl_tables(meta, seed_offset=1)
+    dens, force, pot = O.sl_dens_pot_force(d['rad'], p['lmax'], p['nmax'], ev, ef, xi, d0, p0, p['cmap'], p['scale'])
+    for got, key in ((dens, 'dens'), (force, 'force'), (pot, 'pot'), (pot, 'potm'), (dens, 'densm')):
+        assert relerr(np.moveaxis(got, 2, 0), d[key]) < TOL, key
+    L = meta['leg_lmax']
+    P, dP = O.dlegendre_R(L, d['cth'])
+    assert relerr(np.moveaxis(P, 2, 0), d['P']) < 1e-14
+    assert relerr(np.moveaxis(P, 2, 0), d['P2']) < 1e-14
+    assert relerr(np.moveaxis(dP, 2, 0), d['dP']) < 1e-12
