@@ -158,7 +158,7 @@ def cpu_setup():
     from oracle import oracle_c as OC
     p, T, g = eof_setup()
     _CPU['g'] = g; _CPU['T'] = T
-    return OC.threads()
+    return OC.use_all_cores()          # not OMP_NUM_THREADS: torchrun sets that to 1 for its workers
 
 
 def cpu_baseline(target_seconds=12.0):

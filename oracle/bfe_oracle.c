@@ -62,6 +62,15 @@ static inline double interp(const double* T, int ny1, int ix, int iy, const doub
     return p[0] * c[0] + p[ny1] * c[1] + p[1] * c[2] + p[ny1 + 1] * c[3];
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must still use every host core */
+void bfe_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int bfe_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -37,6 +37,17 @@ def threads():
     return int(load().bfe_oracle_threads())
 
 
+def use_all_cores():
+    """Run the OpenMP loops on every core this process may use, whatever OMP_NUM_THREADS says (torchrun sets it
+    to 1 for its workers).  Returns the thread count now in force."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().bfe_oracle_set_threads(int(n))
+    return threads()
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
