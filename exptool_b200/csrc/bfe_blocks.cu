@@ -16,8 +16,8 @@ __global__ void __launch_bounds__(256)
 eof_bins_kernel(EofGeom g, int64_t n, const double* __restrict__ r, const double* __restrict__ z,
                 double* __restrict__ X, double* __restrict__ Y, long long* __restrict__ ix, long long* __restrict__ iy) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double xv = (bfe_r_to_xi(__ldg(r + i), g.cmap, g.ascale) - g.xmin) * g.inv_dx;      // eof.py:394
-        double yv = (bfe_z_to_y(__ldg(z + i), g.hscale) - g.ymin) * g.inv_dy;               // 395
+        double xv = (bfe_r_to_xi(__ldg(r + i), g.cmap, g.inv_ascale) - g.xmin) * g.inv_dx;      // eof.py:394
+        double yv = (bfe_z_to_y(__ldg(z + i), g.inv_hscale) - g.ymin) * g.inv_dy;               // 395
         int jx = (int)xv, jy = (int)yv;                                                     // truncation, 404-405
         if (jx < 0) jx = 0;                                                                 // 410
         if (xv < 0.0) xv = 0.0;                                                             // 412
@@ -132,6 +132,7 @@ extern "C" int bfe_eof_return_bins(const bfe_eof_params* p, int64_t n, const dou
     g.ny1 = p->numy + 1; g.nnode = (p->numx + 1) * (p->numy + 1);
     g.xmin = p->xmin; g.dx = p->dx; g.ymin = p->ymin; g.dy = p->dy; g.ascale = p->ascale; g.hscale = p->hscale;
     g.inv_dx = 1.0 / p->dx; g.inv_dy = 1.0 / p->dy;
+    g.inv_ascale = 1.0 / p->ascale; g.inv_hscale = 1.0 / p->hscale;
     eof_bins_kernel<<<blocks_grid(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream_>>>(g, n, r, z, X, Y, ix, iy);
     BFE_LAUNCH_CHECK("eof_bins_kernel");
     return BFE_OK;

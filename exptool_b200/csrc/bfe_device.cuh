@@ -36,11 +36,11 @@ __device__ __forceinline__ double bfe_column_sum(const double* __restrict__ part
 // ---------------------------------------------------------------------------
 // coordinate maps -- exptool/basis/compatibility.py:16-99
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double bfe_r_to_xi(double r, int cmap, double scale) {
-    // compatibility.py:30-43 ; negatives map to 0
+__device__ __forceinline__ double bfe_r_to_xi(double r, int cmap, double inv_scale) {
+    // compatibility.py:30-43 ; negatives map to 0.  r/scale is a multiply by the host-rounded reciprocal.
     double out;
     if (cmap == 1) {
-        double q = r / scale;
+        double q = r * inv_scale;
         out = (q - 1.0) / (q + 1.0);
     } else if (cmap == 2) {
         out = log(r);
@@ -50,17 +50,17 @@ __device__ __forceinline__ double bfe_r_to_xi(double r, int cmap, double scale) 
     return (r < 0.0) ? 0.0 : out;
 }
 
-__device__ __forceinline__ double bfe_d_xi_to_r(double xi, int cmap, double scale) {
+__device__ __forceinline__ double bfe_d_xi_to_r(double xi, int cmap, double inv_scale) {
     // compatibility.py:73-80
-    if (cmap == 1) return 0.5 * (1.0 - xi) * (1.0 - xi) / scale;
+    if (cmap == 1) return 0.5 * (1.0 - xi) * (1.0 - xi) * inv_scale;
     if (cmap == 2) return exp(-xi);
     return 1.0;
 }
 
-__device__ __forceinline__ double bfe_z_to_y(double z, double hscale) {
+__device__ __forceinline__ double bfe_z_to_y(double z, double inv_hscale) {
     // compatibility.py:91 (epsilon 1e-8: the live Python value, not accumulate.c's 1e-10)
     double az = fabs(z);
-    double u = fabs(z / hscale);
+    double u = fabs(z * inv_hscale);
     // asinh(u), u >= 0.  Only (y - ymin)/dy with y - ymin = O(1..10) is ever used, so ABSOLUTE accuracy ~1e-16 is
     // what matters: log(u + sqrt(u^2+1)) delivers it without asinh()'s small-argument branches (about half the cost).
     double ash = (u < 1.0e150) ? log(u + sqrt(fma(u, u, 1.0))) : asinh(u);
@@ -79,8 +79,8 @@ struct EofBin {
 __device__ __forceinline__ EofBin bfe_eof_bin(const EofGeom& g, double r, double z) {
     // (xi - xmin)/dx as a multiply by the host-rounded reciprocal: <= 1 ulp from the reference's
     // division, i.e. ~1e-14 relative in the bin fractions (X ~ 1e2), far inside the 1e-10 gate
-    double X = (bfe_r_to_xi(r, g.cmap, g.ascale) - g.xmin) * g.inv_dx;
-    double Y = (bfe_z_to_y(z, g.hscale) - g.ymin) * g.inv_dy;
+    double X = (bfe_r_to_xi(r, g.cmap, g.inv_ascale) - g.xmin) * g.inv_dx;
+    double Y = (bfe_z_to_y(z, g.inv_hscale) - g.ymin) * g.inv_dy;
     int ix = (int)X;                       // truncation, eof.py:404 (NaN -> 0, +-inf saturate)
     int iy = (int)Y;
     if (ix < 0) ix = 0;                    // 410
@@ -300,6 +300,21 @@ struct LegTable {
 #define BFE_SUB(a, b) __dadd_rn((a), -(b))
 #define BFE_DIV(a, b) __ddiv_rn((a), (b))
 
+// a / k for a small positive integer k that is a compile-time constant after unrolling, with the SAME result as
+// __ddiv_rn(a, k) at a fraction of its cost: powers of two are exact scalings; for the odd part d, with
+// y = RN(1/d):  q = RN(a y),  r = a - d q (exact in one FMA),  RN(q + r y) is the correctly rounded quotient
+// (Markstein's theorem; checked against a/k on 4.2e5 random operands for d = 3..15, tests/golden notes).
+__device__ __forceinline__ double bfe_div_int(double a, int k) {
+    double scale = 1.0;
+    int d = k;
+    while ((d & 1) == 0 && d > 1) { d >>= 1; scale *= 0.5; }
+    if (d == 1) return a * scale;
+    const double dd = (double)d, y = 1.0 / dd;
+    const double q = a * y;
+    const double r = fma(-dd, q, a);
+    return fma(r, y, q) * scale;
+}
+
 template <int LCAP>
 __device__ __forceinline__ void bfe_legendre(int lmax, double x, LegTable<LCAP>& T) {
     T.p[0][0] = 1.0;
@@ -326,7 +341,7 @@ __device__ __forceinline__ void bfe_legendre(int lmax, double x, LegTable<LCAP>&
                     // (x*(2*l-1)*pl1-(l+m-1)*pl2)/(l-m)                   // 693
                     double a = BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1);
                     double b = BFE_MUL((double)(l + m - 1), pl2);
-                    double v = BFE_DIV(BFE_SUB(a, b), (double)(l - m));
+                    double v = bfe_div_int(BFE_SUB(a, b), l - m);
                     T.p[l][m] = v;
                     pl2 = pl1;
                     pl1 = v;
@@ -403,21 +418,21 @@ struct SlBin {
 };
 
 __device__ __forceinline__ SlBin bfe_sl_bin(const SlGeom& g, const double* __restrict__ xi, double r) {
-    double x = bfe_r_to_xi(r, g.cmap, g.scale);
+    double x = bfe_r_to_xi(r, g.cmap, g.inv_scale);
     if (g.cmap == 1) {
         if (x < -1.0) x = -1.0;
         if (x >= 1.0) x = 1.0 - 1.0e-08;
     }
-    double fi = floor((x - g.xi0) / g.dxi);
+    double fi = floor((x - g.xi0) * g.inv_dxi);
     int i;
     if (!(fi >= 0.0)) i = 0;
     else if (fi > (double)(g.numr - 2)) i = g.numr - 2;
     else i = (int)fi;
     SlBin b;
     b.i = i;
-    b.x1 = (__ldg(xi + i + 1) - x) / g.dxi;
-    b.x2 = (x - __ldg(xi + i)) / g.dxi;
-    b.fac = bfe_d_xi_to_r(x, g.cmap, g.scale) / g.dxi;
+    b.x1 = (__ldg(xi + i + 1) - x) * g.inv_dxi;
+    b.x2 = (x - __ldg(xi + i)) * g.inv_dxi;
+    b.fac = bfe_d_xi_to_r(x, g.cmap, g.inv_scale) * g.inv_dxi;
     return b;
 }
 
@@ -482,8 +497,8 @@ __device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double2* _
                         dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);          // 765
                     } else {
                         if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);                      // 689
-                        else P = BFE_DIV(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
-                                                 BFE_MUL((double)(l + m - 1), pl2)), (double)(l - m));   // 693
+                        else P = bfe_div_int(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                                     BFE_MUL((double)(l + m - 1), pl2)), l - m);         // 693
                         dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P),
                                                    BFE_MUL((double)(l + m), pl1)));                       // 763
                         pl2 = pl1; pl1 = P;
@@ -524,6 +539,9 @@ __device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double2* _
     }
     return f;
 }
+
+// interval blocks of A3 are padded to an even number of double2 (32-byte alignment for the 256-bit loads below)
+#define BFE_A3_STRIDE(npair) ((3 * (npair) + 1) & ~1)
 
 // Staged SL evaluation; valid only when g.lmax == LCAP (compile-time chunk counts).
 // A3[j][chunk], chunk = 3*(offm(m) + l - m) + node, node 0,1,2 = rows j-1, j, j+1; offm(m) = sum_{m'<m}(LCAP-m'+1).
@@ -566,7 +584,7 @@ __device__ __forceinline__ SlField bfe_sl_eval_staged(const SlGeom& g, const dou
                     const int c = lane + 32 * t;
                     const int owner = c / NCHr, piece = c - owner * NCHr;
                     const int oj = __shfl_sync(0xffffffffu, j, owner);
-                    st[owner * STRIDE + piece] = __ldg(A3 + (size_t)oj * (3 * NPAIR) + 3 * offm + piece);
+                    st[owner * STRIDE + piece] = __ldg(A3 + (size_t)oj * BFE_A3_STRIDE(NPAIR) + 3 * offm + piece);
                 }
             }
             __syncwarp();
@@ -588,8 +606,8 @@ __device__ __forceinline__ SlField bfe_sl_eval_staged(const SlGeom& g, const dou
                 dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);
             } else {
                 if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);
-                else P = BFE_DIV(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
-                                         BFE_MUL((double)(l + m - 1), pl2)), (double)(l - m));
+                else P = bfe_div_int(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                             BFE_MUL((double)(l + m - 1), pl2)), l - m);
                 dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P), BFE_MUL((double)(l + m), pl1)));
                 pl2 = pl1; pl1 = P;
                 double cn = cl * c1 - sl * s1, sn = sl * c1 + cl * s1;
@@ -629,11 +647,200 @@ __device__ __forceinline__ SlField bfe_sl_eval_staged(const SlGeom& g, const dou
 }
 
 // ---------------------------------------------------------------------------
+// Per-lane evaluation from the per-cell / per-interval BLOCKS (G4, A3) with 256-bit loads.
+//
+// The per-lane kernels above are bound by the L1 tag stage: every divergent load instruction costs ~32 tag
+// cycles whatever its width (ncu, profiles/).  G4[cell] (EOF: 192 B per harmonic) and A3[j] (SL: one 48-B entry
+// per (m,l), consecutive in the evaluation order) are contiguous and 32-byte aligned, so the same operands come in
+// with HALF the load instructions as 32-byte (LDG.E.256) loads; all of a point's loads are independent of each
+// other (addresses = block base + constant), so they are in flight together.  Arithmetic is unchanged.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bfe_ldg256(const double2* p, double2& a, double2& b) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+
+template <int MCAP>
+__device__ __forceinline__ EofField bfe_eof_eval_blk(const EofGeom& g, const double2* __restrict__ G4,
+                                                     const EofBin& b, double c1, double s1) {
+    const double2* base = G4 + (size_t)b.cell * (size_t)(12 * (g.mmax + 1));
+    EofField f;
+    f.p0 = 0.0; f.p = 0.0; f.fr = 0.0; f.fp = 0.0; f.fz = 0.0;
+    double cm = 1.0, sm = 0.0;
+#pragma unroll
+    for (int m = 0; m <= MCAP; ++m) {
+        if (m <= g.mmax) {
+            // corners 00, 10, 01, 11; three double2 each: (pc,ps), (rc,rs), (zc,zs)
+            const double2* q = base + 12 * m;
+            double2 a0, a1, a2, b0, b1, b2, c0, c1v, c2, d0, d1, d2;
+            bfe_ldg256(q, a0, a1); bfe_ldg256(q + 2, a2, b0); bfe_ldg256(q + 4, b1, b2);
+            bfe_ldg256(q + 6, c0, c1v); bfe_ldg256(q + 8, c2, d0); bfe_ldg256(q + 10, d1, d2);
+            double vpc = a0.x * b.c00 + b0.x * b.c10 + c0.x * b.c01 + d0.x * b.c11;
+            double vps = a0.y * b.c00 + b0.y * b.c10 + c0.y * b.c01 + d0.y * b.c11;
+            double vrc = a1.x * b.c00 + b1.x * b.c10 + c1v.x * b.c01 + d1.x * b.c11;
+            double vrs = a1.y * b.c00 + b1.y * b.c10 + c1v.y * b.c01 + d1.y * b.c11;
+            double vzc = a2.x * b.c00 + b2.x * b.c10 + c2.x * b.c01 + d2.x * b.c11;
+            double vzs = a2.y * b.c00 + b2.y * b.c10 + c2.y * b.c01 + d2.y * b.c11;
+            if (m == 0) {
+                f.p0 = vpc;
+                f.fr = vrc;
+                f.fz = vzc;
+            } else {
+                f.p  += cm * vpc + sm * vps;
+                f.fr += cm * vrc + sm * vrs;
+                f.fz += cm * vzc + sm * vzs;
+                f.fp += (double)m * (sm * vpc - cm * vps);
+            }
+            double cn = cm * c1 - sm * s1;
+            double sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+    }
+    return f;
+}
+
+// valid only when g.lmax == LCAP (LCAP = 6: 84 double2 = 1344 B per interval; LCAP = 4: 45 padded to 46)
+template <int LCAP>
+__device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double2* __restrict__ A3,
+                                                   const double* __restrict__ p0tab, const double* __restrict__ fac,
+                                                   const SlBin& b, double costh, double c1, double s1,
+                                                   bool trig_index_l) {
+    constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
+    const int j = (b.i == 0) ? 1 : b.i;
+    const double2* base = A3 + (size_t)j * BFE_A3_STRIDE(NPAIR);
+    const double pm = __ldg(p0tab + j - 1), pc = __ldg(p0tab + j), pp = __ldg(p0tab + j + 1);
+    double P0, wA, wB, wC;
+    if (b.i == 0) { P0 = b.x1 * pm + b.x2 * pc; wA = b.x1; wB = b.x2; wC = 0.0; }
+    else          { P0 = b.x1 * pc + b.x2 * pp; wA = 0.0; wB = b.x1; wC = b.x2; }
+    wA *= P0; wB *= P0; wC *= P0;
+    const double dA = b.fac * (b.x2 - 0.5) * pm, dB = b.fac * (-2.0 * b.x2) * pc, dC = b.fac * (b.x2 + 0.5) * pp;
+
+    const double x = costh;
+    const double somx2 = sqrt(BFE_MUL(BFE_SUB(1.0, x), BFE_ADD(1.0, x)));
+    double xd = x;
+    if (1.0 - fabs(xd) < 1.0e-8) xd = (xd > 0.0) ? (1.0 - 1.0e-8) : -(1.0 - 1.0e-8);
+    const double dsom = BFE_DIV(1.0, BFE_SUB(BFE_MUL(xd, xd), 1.0));
+
+    SlField f;
+    f.pot0 = 0.0; f.pot1 = 0.0; f.potr = 0.0; f.pott = 0.0; f.potp = 0.0;
+    double pmm = 1.0, fact = 1.0;
+    double cm = 1.0, sm = 0.0;
+    int offm = 0;
+#pragma unroll
+    for (int m = 0; m <= LCAP; ++m) {
+        const int nl = LCAP - m + 1;                       // entries of this column (compile time after unrolling)
+        // the column's 3*nl double2 start at double2 index 3*offm of the block: fetch the covering 32-byte pairs
+        double2 v[3 * (LCAP + 1) + 1];
+        {
+            const int first = 3 * offm, count = 3 * nl;
+            const int pa = first / 2, pb = (first + count - 1) / 2;
+#pragma unroll
+            for (int pi = 0; pi < (3 * (LCAP + 1)) / 2 + 1; ++pi) {
+                const int pr = pa + pi;
+                if (pr <= pb) {
+                    double2 lo, hi;
+                    bfe_ldg256(base + 2 * pr, lo, hi);
+                    if (2 * pr >= first) v[2 * pr - first] = lo;
+                    if (2 * pr + 1 < first + count) v[2 * pr + 1 - first] = hi;
+                }
+            }
+        }
+        if (m > 0) {
+            pmm = BFE_MUL(pmm, BFE_MUL(-fact, somx2));
+            fact += 2.0;
+            double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+        double pl2 = 0.0, pl1 = pmm;
+        double cl = cm, sl = sm;
+#pragma unroll
+        for (int l = m; l <= LCAP; ++l) {
+            double P, dP;
+            if (l == m) {
+                P = pmm;
+                dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);
+            } else {
+                if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);
+                else P = bfe_div_int(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                             BFE_MUL((double)(l + m - 1), pl2)), l - m);
+                dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P), BFE_MUL((double)(l + m), pl1)));
+                pl2 = pl1; pl1 = P;
+                double cn = cl * c1 - sl * s1, sn = sl * c1 + cl * s1;
+                cl = cn; sl = sn;
+            }
+            const double2 am = v[3 * (l - m)], a0 = v[3 * (l - m) + 1], ap = v[3 * (l - m) + 2];
+            const double fl = __ldg(fac + l * (LCAP + 1) + m);
+            const double spc = wA * am.x + wB * a0.x + wC * ap.x;
+            const double sdc = dA * am.x + dB * a0.x + dC * ap.x;
+            if (m == 0) {
+                if (l == 0) {
+                    f.pot0 = fl * spc;
+                    f.potr += fl * sdc;
+                } else {
+                    f.pot1 += fl * P * spc;
+                    f.potr += fl * P * sdc;
+                    f.pott += fl * dP * spc;
+                }
+            } else {
+                const double sps = wA * am.y + wB * a0.y + wC * ap.y;
+                const double sds = dA * am.y + dB * a0.y + dC * ap.y;
+                const double ct = trig_index_l ? cl : cm;
+                const double stt = trig_index_l ? sl : sm;
+                const double Ap = spc * ct + sps * stt;
+                const double Ad = sdc * ct + sds * stt;
+                const double Bp = sps * ct - spc * stt;
+                const double fP = fl * P;
+                f.pot1 += fP * Ap;
+                f.potr += fP * Ad;
+                f.pott += fl * dP * Ap;
+                f.potp += fP * (double)m * Bp;
+            }
+        }
+        offm += nl;
+    }
+    return f;
+}
+
+// ---------------------------------------------------------------------------
 // Fields.return_forces_cart -- potential.py:455-497
 // ---------------------------------------------------------------------------
 struct CartForce {
     double fxd, fxh, fyd, fyh, fzd, fzh, pd, ph;
 };
+
+// potential.py:475-497 (Cartesian) / 425-440 (cylindrical): disc + halo field components -> the 8 outputs.
+// The ten quotients by r2, r2^2, r3, r3^3 are formed from two reciprocals (a few ulp from the reference's
+// separate divisions: these are plain products, nothing downstream amplifies them).
+template <bool CYL>
+__device__ __forceinline__ CartForce bfe_cart_combine(const EofField& d, const SlField& h, double x, double y, double z,
+                                                      double r2, double r3, double xi0) {
+    double diskfr = d.fr, diskfp = d.fp, diskfz = d.fz, diskp = d.p + d.p0;
+    double halofr = h.potr, haloft = h.pott, halofp = h.potp;
+    if (r3 < xi0) { halofp = 0.0; diskfp = 0.0; }            // 483-485 (min(xi) = xi[0])
+    CartForce o;
+    const double ir3 = 1.0 / r3;
+    if (CYL) {
+        o.fxd = diskfr;
+        o.fxh = -1.0 * (r2 * halofr + z * haloft) * ir3;      // 433
+        o.fyd = diskfp;
+        o.fyh = -1.0 * halofp;
+        o.fzd = diskfz;
+        o.fzh = -1.0 * (z * halofr - r2 * haloft) * ir3;      // 435
+        o.pd = -1.0 * diskp;                                  // 440
+        o.ph = h.pot1 + h.pot0;
+        return o;
+    }
+    const double ir2 = 1.0 / r2;
+    const double ir2sq = ir2 * ir2, ir3cu = ir3 * ir3 * ir3;
+    o.fxd = diskfr * (x * ir2) - diskfp * (y * ir2sq);
+    o.fxh = -1.0 * (halofr * (x * ir3) - haloft * (x * z * ir3cu)) + halofp * (y * ir2sq);
+    o.fyd = diskfr * (y * ir2) + diskfp * (x * ir2sq);
+    o.fyh = -1.0 * (halofr * (y * ir3) - haloft * (y * z * ir3cu)) - halofp * (x * ir2sq);
+    o.fzd = diskfz;
+    o.fzh = -1.0 * (halofr * (z * ir3) + haloft * (r2 * r2 * ir3cu));
+    o.pd = diskp;
+    o.ph = h.pot1 + h.pot0;
+    return o;
+}
 
 // CYL = true gives Fields.return_forces_cyl (potential.py:389-440) in the same 8 slots:
 // diskfr, frhalo, diskfp, -halofp, diskfz, fzhalo, -diskp, halop+halop0.
@@ -656,31 +863,29 @@ __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const dou
     EofField d = bfe_eof_eval<MCAP>(ge, G, gstride, eb, cr, sr);
     SlBin sb = bfe_sl_bin(gs, xi, r3);
     SlField h = bfe_sl_eval<LCAP>(gs, A, kpad, p0tab, fac, sb, costh, cr, sr, true);
-    double diskfr = d.fr, diskfp = d.fp, diskfz = d.fz, diskp = d.p + d.p0;
-    double halofr = h.potr, haloft = h.pott, halofp = h.potp;
-    if (r3 < gs.xi0) { halofp = 0.0; diskfp = 0.0; }         // 483-485 (min(xi) = xi[0])
-    CartForce o;
-    if (CYL) {
-        o.fxd = diskfr;
-        o.fxh = -1.0 * (r2 * halofr + z * haloft) / r3;      // 433
-        o.fyd = diskfp;
-        o.fyh = -1.0 * halofp;
-        o.fzd = diskfz;
-        o.fzh = -1.0 * (z * halofr - r2 * haloft) / r3;      // 435
-        o.pd = -1.0 * diskp;                                  // 440
-        o.ph = h.pot1 + h.pot0;
-        return o;
-    }
-    double r2sq = r2 * r2, r3cu = r3 * r3 * r3;
-    o.fxd = diskfr * (x / r2) - diskfp * (y / r2sq);
-    o.fxh = -1.0 * (halofr * (x / r3) - haloft * (x * z / r3cu)) + halofp * (y / r2sq);
-    o.fyd = diskfr * (y / r2) + diskfp * (x / r2sq);
-    o.fyh = -1.0 * (halofr * (y / r3) - haloft * (y * z / r3cu)) - halofp * (x / r2sq);
-    o.fzd = diskfz;
-    o.fzh = -1.0 * (halofr * (z / r3) + haloft * (r2sq / r3cu));
-    o.pd = diskp;
-    o.ph = h.pot1 + h.pot0;
-    return o;
+    return bfe_cart_combine<CYL>(d, h, x, y, z, r2, r3, gs.xi0);
+}
+
+// The same with the block evaluations above (G4 / A3, 256-bit loads); valid for g.lmax == LCAP.
+template <int MCAP, int LCAP, bool CYL = false>
+__device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const double2* __restrict__ G4,
+                                                        const SlGeom& gs, const double2* __restrict__ A3,
+                                                        const double* __restrict__ xi, const double* __restrict__ p0tab,
+                                                        const double* __restrict__ fac,
+                                                        double x, double y, double z, double crot, double srot) {
+    const double eps = CYL ? 1.e-10 : 1.e-15;
+    double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + eps;
+    double r3 = sqrt(BFE_ADD(BFE_MUL(r2, r2), BFE_MUL(z, z))) + eps;
+    double costh = BFE_DIV(z, r3);
+    double c1, s1;
+    bfe_cossin_phi(x, y, c1, s1);
+    double cr = c1 * crot - s1 * srot;
+    double sr = s1 * crot + c1 * srot;
+    EofBin eb = bfe_eof_bin(ge, r2, z);
+    SlBin sb = bfe_sl_bin(gs, xi, r3);
+    EofField d = bfe_eof_eval_blk<MCAP>(ge, G4, eb, cr, sr);
+    SlField h = bfe_sl_eval_blk<LCAP>(gs, A3, p0tab, fac, sb, costh, cr, sr, true);
+    return bfe_cart_combine<CYL>(d, h, x, y, z, r2, r3, gs.xi0);
 }
 
 template <int MCAP, int LCAP, bool CYL>
@@ -701,29 +906,5 @@ __device__ __forceinline__ CartForce bfe_field_cart_staged(const EofGeom& ge, co
     EofField d = bfe_eof_eval_staged<MCAP>(ge, G4, eb, cr, sr, st, lane);
     SlBin sb = bfe_sl_bin(gs, xi, r3);
     SlField h = bfe_sl_eval_staged<LCAP>(gs, A3, p0tab, fac, sb, costh, cr, sr, true, st, lane);
-    double diskfr = d.fr, diskfp = d.fp, diskfz = d.fz, diskp = d.p + d.p0;
-    double halofr = h.potr, haloft = h.pott, halofp = h.potp;
-    if (r3 < gs.xi0) { halofp = 0.0; diskfp = 0.0; }
-    CartForce o;
-    if (CYL) {
-        o.fxd = diskfr;
-        o.fxh = -1.0 * (r2 * halofr + z * haloft) / r3;
-        o.fyd = diskfp;
-        o.fyh = -1.0 * halofp;
-        o.fzd = diskfz;
-        o.fzh = -1.0 * (z * halofr - r2 * haloft) / r3;
-        o.pd = -1.0 * diskp;
-        o.ph = h.pot1 + h.pot0;
-        return o;
-    }
-    double r2sq = r2 * r2, r3cu = r3 * r3 * r3;
-    o.fxd = diskfr * (x / r2) - diskfp * (y / r2sq);
-    o.fxh = -1.0 * (halofr * (x / r3) - haloft * (x * z / r3cu)) + halofp * (y / r2sq);
-    o.fyd = diskfr * (y / r2) + diskfp * (x / r2sq);
-    o.fyh = -1.0 * (halofr * (y / r3) - haloft * (y * z / r3cu)) - halofp * (x / r2sq);
-    o.fzd = diskfz;
-    o.fzh = -1.0 * (halofr * (z / r3) + haloft * (r2sq / r3cu));
-    o.pd = diskp;
-    o.ph = h.pot1 + h.pot0;
-    return o;
+    return bfe_cart_combine<CYL>(d, h, x, y, z, r2, r3, gs.xi0);
 }

@@ -321,6 +321,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     g.nnode = (p->numx + 1) * (p->numy + 1);
     g.xmin = p->xmin; g.dx = p->dx; g.ymin = p->ymin; g.dy = p->dy; g.ascale = p->ascale; g.hscale = p->hscale;
     g.inv_dx = 1.0 / p->dx; g.inv_dy = 1.0 / p->dy;
+    g.inv_ascale = 1.0 / p->ascale; g.inv_hscale = 1.0 / p->hscale;
     BFE_CUDA(cudaGetDevice(&h->device));
     BFE_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     h->nch = (2 * p->mmax + 1) * p->norder;
@@ -429,6 +430,40 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
     return BFE_OK;
 }
 
+// per-lane evaluation on the per-cell blocks G4 with 256-bit loads (bfe_eof_eval_blk): half the load instructions
+// of eof_force_kernel / eof_points_kernel, no shared-memory stage
+template <int MCAP>
+__global__ void __launch_bounds__(128)
+eof_force_blk_kernel(EofGeom g, const double2* __restrict__ G4, int64_t n,
+                     const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                     double* __restrict__ p0, double* __restrict__ p, double* __restrict__ fr,
+                     double* __restrict__ fp, double* __restrict__ fz, double* __restrict__ R) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        double r = sqrt(px * px + py * py + 1.e-10);              // eof.py:1070
+        EofBin b = bfe_eof_bin(g, r, pz);
+        double c1, s1;
+        bfe_cossin_phi(px, py, c1, s1);                           // eof.py:1068
+        EofField f = bfe_eof_eval_blk<MCAP>(g, G4, b, c1, s1);
+        p0[i] = f.p0; p[i] = f.p; fr[i] = f.fr; fp[i] = f.fp; fz[i] = f.fz; R[i] = r;
+    }
+}
+
+template <int MCAP>
+__global__ void __launch_bounds__(128)
+eof_points_blk_kernel(EofGeom g, const double2* __restrict__ G4, int64_t n,
+                      const double* __restrict__ r, const double* __restrict__ z, const double* __restrict__ phi,
+                      double* __restrict__ fr, double* __restrict__ fp, double* __restrict__ fz,
+                      double* __restrict__ p, double* __restrict__ p0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        EofBin b = bfe_eof_bin(g, __ldg(r + i), __ldg(z + i));
+        double c1, s1;
+        sincos(__ldg(phi + i), &s1, &c1);
+        EofField f = bfe_eof_eval_blk<MCAP>(g, G4, b, c1, s1);
+        fr[i] = f.fr; fp[i] = f.fp; fz[i] = f.fz; p[i] = f.p + f.p0; p0[i] = f.p0;
+    }
+}
+
 int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream) {
     if (h->g4_valid) return BFE_OK;
     eof_expand_g4_kernel<<<h->num_sms * 8, 256, 0, stream>>>(h->g, h->g_con, h->gstride,
@@ -452,7 +487,14 @@ extern "C" int bfe_eof_force_contracted(bfe_eof* h, int64_t n, const double* x, 
             return bfe_eof_force_sorted(h, n, x, y, z, p0, p, fr, fp, fz, R, stream);
     }
     int grid = grid_for(n, 128, h->num_sms, 16);
-    if (h->g.mmax <= 6 && g_bfe_staged_eval) {
+    // EOF alone: the warp-staged copy wins (176 vs 186 us per 10^6 points, profiles/blk_ab.py); the 256-bit per-lane
+    // variant is the choice when staging is switched off
+    if (h->g.mmax <= 6 && g_bfe_blk_eval && !g_bfe_staged_eval) {
+        int rc = bfe_eof_ensure_g4(h, stream);
+        if (rc != BFE_OK) return rc;
+        eof_force_blk_kernel<6><<<grid, 128, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->g4), n, x, y, z,
+                                                         p0, p, fr, fp, fz, R);
+    } else if (h->g.mmax <= 6 && g_bfe_staged_eval) {
         int rc = bfe_eof_ensure_g4(h, stream);
         if (rc != BFE_OK) return rc;
         eof_force_staged_kernel<6><<<grid, 128, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->g4), n, x, y, z,
@@ -482,7 +524,12 @@ extern "C" int bfe_eof_force_eval_points(bfe_eof* h, int64_t n, const double* r,
     if (!r || !z || !phi || !fr || !fp || !fz || !p || !p0) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = grid_for(n, 128, h->num_sms, 16);
-    if (h->g.mmax <= 6 && g_bfe_staged_eval) {
+    if (h->g.mmax <= 6 && g_bfe_blk_eval && !g_bfe_staged_eval) {
+        int rc = bfe_eof_ensure_g4(h, stream);
+        if (rc != BFE_OK) return rc;
+        eof_points_blk_kernel<6><<<grid, 128, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->g4), n, r, z, phi,
+                                                          fr, fp, fz, p, p0);
+    } else if (h->g.mmax <= 6 && g_bfe_staged_eval) {
         int rc = bfe_eof_ensure_g4(h, stream);
         if (rc != BFE_OK) return rc;
         eof_points_staged_kernel<6><<<grid, 128, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->g4), n, r, z, phi,

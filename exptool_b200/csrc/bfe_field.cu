@@ -108,6 +108,75 @@ leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
     if (nsteps_out) nsteps_out[i] = (int)step;
 }
 
+// per-lane variants on the per-cell / per-interval blocks with 256-bit loads (bfe_field_cart_blk): half the load
+// instructions of the kernels above, no shared-memory stage; valid for mmax <= MCAP, lmax == LCAP == 6
+template <int MCAP, int LCAP, bool CYL>
+__global__ void __launch_bounds__(128)
+field_cart_blk_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
+                      const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
+                      int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                      const double* __restrict__ z, double crot, double srot, double* __restrict__ out8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        CartForce f = bfe_field_cart_blk<MCAP, LCAP, CYL>(ge, G4, gs, A3, xi, p0tab, fac,
+                                                          __ldg(x + i), __ldg(y + i), __ldg(z + i), crot, srot);
+        out8[i] = f.fxd; out8[n + i] = f.fxh; out8[2 * n + i] = f.fyd; out8[3 * n + i] = f.fyh;
+        out8[4 * n + i] = f.fzd; out8[5 * n + i] = f.fzh; out8[6 * n + i] = f.pd; out8[7 * n + i] = f.ph;
+    }
+}
+
+template <int MCAP, int LCAP>
+__global__ void __launch_bounds__(128)
+leapfrog_blk_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
+                    const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
+                    int64_t norbit, int64_t nint, double dt, const double* __restrict__ dt_orbit, double rotfreq,
+                    double* __restrict__ state6, double* __restrict__ traj, int64_t traj_stride,
+                    int apse, int ap_max, int* __restrict__ nsteps_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= norbit) return;
+    if (dt_orbit) dt = dt_orbit[i];
+    double px = state6[i], py = state6[norbit + i], pz = state6[2 * norbit + i];
+    double vx = state6[3 * norbit + i], vy = state6[4 * norbit + i], vz = state6[5 * norbit + i];
+    const double w = BFE_TWOPI * rotfreq;
+    const double hdt2 = 0.5 * (dt * dt);
+    double srot, crot;
+    sincos(w * (0.0 * dt), &srot, &crot);
+    CartForce f = bfe_field_cart_blk<MCAP, LCAP>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+    double ax = f.fxd + f.fxh, ay = f.fyd + f.fyh, az = f.fzd + f.fzh, pot = f.pd + f.ph;
+    if (traj) {
+        double* t = traj + i;
+        t[0] = px; t[norbit] = py; t[2 * norbit] = pz; t[3 * norbit] = vx; t[4 * norbit] = vy; t[5 * norbit] = vz;
+        t[6 * norbit] = pot; t[7 * norbit] = ax; t[8 * norbit] = ay; t[9 * norbit] = az;
+    }
+    int n_aps = 0;
+    double rs0 = 0.0, rs1 = px * px + py * py;
+    int64_t step = 1;
+    while (n_aps < ap_max && step < nint) {
+        px = px + (vx * dt) + (ax * hdt2);
+        py = py + (vy * dt) + (ay * hdt2);
+        pz = pz + (vz * dt) + (az * hdt2);
+        sincos(w * ((double)step * dt), &srot, &crot);
+        f = bfe_field_cart_blk<MCAP, LCAP>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+        double bx = f.fxd + f.fxh, by = f.fyd + f.fyh, bz = f.fzd + f.fzh;
+        pot = f.pd + f.ph;
+        vx = vx + (0.5 * (ax + bx) * dt);
+        vy = vy + (0.5 * (ay + by) * dt);
+        vz = vz + (0.5 * (az + bz) * dt);
+        ax = bx; ay = by; az = bz;
+        double rs2 = px * px + py * py;
+        if (apse && step > 1 && rs1 > rs0 && rs1 > rs2) ++n_aps;
+        rs0 = rs1; rs1 = rs2;
+        if (traj && (step % traj_stride) == 0) {
+            double* t = traj + (step / traj_stride) * 10 * norbit + i;
+            t[0] = px; t[norbit] = py; t[2 * norbit] = pz; t[3 * norbit] = vx; t[4 * norbit] = vy;
+            t[5 * norbit] = vz; t[6 * norbit] = pot; t[7 * norbit] = ax; t[8 * norbit] = ay; t[9 * norbit] = az;
+        }
+        ++step;
+    }
+    state6[i] = px; state6[norbit + i] = py; state6[2 * norbit + i] = pz;
+    state6[3 * norbit + i] = vx; state6[4 * norbit + i] = vy; state6[5 * norbit + i] = vz;
+    if (nsteps_out) nsteps_out[i] = (int)step;
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -135,6 +204,20 @@ static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x,
     int64_t need = (n + 127) / 128, cap = (int64_t)he->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
     double crot = cos(rotpos), srot = sin(rotpos);
+    if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
+        int rc = bfe_eof_ensure_g4(he, stream);
+        if (rc == BFE_OK) rc = bfe_sl_ensure_a3(hs, stream);
+        if (rc != BFE_OK) return rc;
+        const double2* G4 = reinterpret_cast<const double2*>(he->g4);
+        const double2* A3 = reinterpret_cast<const double2*>(hs->a3);
+#define FIELD_BLK(L, C) field_cart_blk_kernel<6, L, C><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, \
+                                                                              hs->fac, n, x, y, z, crot, srot, out8)
+        if (hs->g.lmax == 4) { if (cyl) FIELD_BLK(4, true); else FIELD_BLK(4, false); }
+        else                 { if (cyl) FIELD_BLK(6, true); else FIELD_BLK(6, false); }
+#undef FIELD_BLK
+        BFE_LAUNCH_CHECK("field_cart_blk_kernel");
+        return BFE_OK;
+    }
     if (g_bfe_staged_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
         int rc = bfe_eof_ensure_g4(he, stream);
         if (rc == BFE_OK) rc = bfe_sl_ensure_a3(hs, stream);
@@ -180,6 +263,21 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     if (ap_max < 1) ap_max = 1;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = (int)((norbit + 127) / 128);
+    if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
+        int rc = bfe_eof_ensure_g4(he, stream);
+        if (rc == BFE_OK) rc = bfe_sl_ensure_a3(hs, stream);
+        if (rc != BFE_OK) return rc;
+        const double2* G4 = reinterpret_cast<const double2*>(he->g4);
+        const double2* A3 = reinterpret_cast<const double2*>(hs->a3);
+        if (hs->g.lmax == 4)
+            leapfrog_blk_kernel<6, 4><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, nint, dt,
+                                                               dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
+        else
+            leapfrog_blk_kernel<6, 6><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, nint, dt,
+                                                               dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
+        BFE_LAUNCH_CHECK("leapfrog_blk_kernel");
+        return BFE_OK;
+    }
     // the per-lane kernel is used for orbits: consecutive steps of one orbit re-read the same table rows, which the
     // per-lane loads find in L1, whereas the warp-staged variant re-copies them every step (measured 15 % slower)
     FIELD_DISPATCH(leapfrog_kernel, he->g, he->g_con, he->gstride, hs->g, reinterpret_cast<const double2*>(hs->a_con), hs->kpad, hs->xi, hs->p0,
@@ -214,6 +312,7 @@ int g_bfe_eof_force_mode = 0;
 int g_bfe_sort_min_particles = 32768;
 int g_bfe_sl_accumulate_mode = 0;
 int g_bfe_staged_eval = 1;
+int g_bfe_blk_eval = 1;
 int g_bfe_force_mma = 1;
 static int g_bfe_time_kernels = 0;
 int g_bfe_pdl = 1;
@@ -243,6 +342,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "eof_force_mode")) { g_bfe_eof_force_mode = value; return BFE_OK; }
     if (!strcmp(name, "time_kernels")) { g_bfe_time_kernels = value; return BFE_OK; }
     if (!strcmp(name, "staged_eval")) { g_bfe_staged_eval = value; return BFE_OK; }
+    if (!strcmp(name, "blk_eval")) { g_bfe_blk_eval = value; return BFE_OK; }
     if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
     if (!strcmp(name, "pdl")) { g_bfe_pdl = value; return BFE_OK; }
     if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }

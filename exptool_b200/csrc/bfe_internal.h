@@ -11,6 +11,7 @@ struct EofGeom {
     int ny1;            // numy+1 : node = ix*ny1 + iy
     double xmin, dx, ymin, dy, ascale, hscale;
     double inv_dx, inv_dy;
+    double inv_ascale, inv_hscale;   // host-rounded reciprocals: r/ascale and z/hscale become multiplies (<= 1 ulp)
 };
 
 // halo_methods.init_table:178-220 geometry
@@ -19,6 +20,7 @@ struct SlGeom {
     int nrow;           // (lmax+1)^2
     int ln;             // (lmax+1)*nmax
     double scale, xi0, dxi;
+    double inv_scale, inv_dxi;       // host-rounded reciprocals (<= 1 ulp from the reference's divisions)
 };
 
 struct bfe_eof {
@@ -102,6 +104,7 @@ void bfe_set_cuda_error(cudaError_t e, const char* where);
 int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream);     // build G4 from g_con if stale
 int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream);       // build A3 from a_con if stale
 extern int g_bfe_force_mma;                                 // option "force_mma": sorted force eval on DMMA (1, default) / per lane (0)
+extern int g_bfe_blk_eval;                                  // option "blk_eval": per-lane block evaluation with 256-bit loads
 extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0
 
 // Optional per-kernel CUDA-event timing (option "time_kernels"): bench.py's roofline object reads the live

@@ -180,21 +180,64 @@ __global__ void sl_contract_kernel(SlGeom g, const double* __restrict__ e_node, 
     A[((size_t)i * qstride + (l * (l + 1)) / 2 + m) * 2 + comp] = s;
 }
 
-// a_con [i][q = l(l+1)/2 + m] -> A3 [j][3*(offm(m) + l - m) + node], node 0,1,2 = rows j-1, j, j+1 (valid for 1 <= j <= numr-2)
+// a_con [i][q = l(l+1)/2 + m] -> A3 [j][3*(offm(m) + l - m) + node], node 0,1,2 = rows j-1, j, j+1 (valid for 1 <= j <= numr-2);
+// the block of one j is BFE_A3_STRIDE(npair) double2 long (padded to a multiple of 32 bytes)
 __global__ void sl_expand_a3_kernel(SlGeom g, const double2* __restrict__ A, int qstride, double2* __restrict__ A3) {
     const int npair = qstride;
-    const int64_t total = (int64_t)g.numr * npair * 3;
+    const int stride = BFE_A3_STRIDE(npair);
+    const int64_t total = (int64_t)g.numr * stride;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(t / (3 * npair)), c = (int)(t - (int64_t)j * 3 * npair);
-        const int qm = c / 3, node = c - qm * 3;
-        // (m, l) from the column-major pair index qm
-        int m = 0, off = 0;
-        while (qm >= off + (g.lmax - m + 1)) { off += g.lmax - m + 1; ++m; }
-        const int l = m + (qm - off);
-        const int row = j - 1 + node;
+        const int j = (int)(t / stride), c = (int)(t - (int64_t)j * stride);
         double2 v = make_double2(0.0, 0.0);
-        if (row >= 0 && row < g.numr) v = A[(size_t)row * qstride + (l * (l + 1)) / 2 + m];
+        if (c < 3 * npair) {
+            const int qm = c / 3, node = c - qm * 3;
+            // (m, l) from the column-major pair index qm
+            int m = 0, off = 0;
+            while (qm >= off + (g.lmax - m + 1)) { off += g.lmax - m + 1; ++m; }
+            const int l = m + (qm - off);
+            const int row = j - 1 + node;
+            if (row >= 0 && row < g.numr) v = A[(size_t)row * qstride + (l * (l + 1)) / 2 + m];
+        }
         A3[t] = v;
+    }
+}
+
+// per-lane block evaluation with 256-bit loads (bfe_sl_eval_blk); valid for g.lmax == LCAP
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+sl_force_blk_kernel(SlGeom g, const double2* __restrict__ A3, const double* __restrict__ xi,
+                    const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
+                    const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                    double* __restrict__ pot0, double* __restrict__ pot1, double* __restrict__ potr,
+                    double* __restrict__ pott, double* __restrict__ potp, double* __restrict__ rr) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        double rxy2 = BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py));
+        double r = sqrt(BFE_ADD(rxy2, BFE_MUL(pz, pz)));          // spheresl.py:1257 (no epsilon)
+        double rxy = sqrt(rxy2);
+        double costh = BFE_DIV(pz, r);
+        double c1, s1;
+        bfe_cossin_phi(px, py, c1, s1);
+        SlBin b = bfe_sl_bin(g, xi, r);
+        SlField f = bfe_sl_eval_blk<LCAP>(g, A3, p0tab, fac, b, costh, c1, s1, false);
+        pot0[i] = f.pot0; pot1[i] = f.pot1; potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; rr[i] = rxy;
+    }
+}
+
+template <int LCAP>
+__global__ void __launch_bounds__(128)
+sl_points_blk_kernel(SlGeom g, const double2* __restrict__ A3, const double* __restrict__ xi,
+                     const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
+                     const double* __restrict__ r, const double* __restrict__ costh, const double* __restrict__ phi,
+                     int trig_index_l,
+                     double* __restrict__ potr, double* __restrict__ pott, double* __restrict__ potp,
+                     double* __restrict__ pot1, double* __restrict__ pot0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double c1, s1;
+        sincos(__ldg(phi + i), &s1, &c1);
+        SlBin b = bfe_sl_bin(g, xi, __ldg(r + i));
+        SlField f = bfe_sl_eval_blk<LCAP>(g, A3, p0tab, fac, b, __ldg(costh + i), c1, s1, trig_index_l != 0);
+        potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; pot1[i] = f.pot1; pot0[i] = f.pot0;
     }
 }
 
@@ -406,6 +449,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaStreamSynchronize(stream));
     g.xi0 = xi01[0];                        // np.min(xi), spheresl.py:319
     g.dxi = xi01[1] - xi01[0];              // xi[1]-xi[0], spheresl.py:317
+    g.inv_scale = 1.0 / g.scale; g.inv_dxi = 1.0 / g.dxi;
     h->kpad = (p->lmax + 1) * (p->lmax + 2) / 2;     // (l,m) pairs per radial node, one double2 each
     h->contracted = 0;
     h->max_ctas = h->num_sms * 6;
@@ -420,7 +464,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     h->dens_contracted = 0;
     BFE_CUDA(cudaMalloc(&h->fac, sizeof(double) * (p->lmax + 1) * (p->lmax + 1)));
     BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * 2 * sizeof(double)));
-    BFE_CUDA(cudaMalloc(&h->a3, nr * h->kpad * 3 * 2 * sizeof(double)));
+    BFE_CUDA(cudaMalloc(&h->a3, nr * (size_t)BFE_A3_STRIDE(h->kpad) * 2 * sizeof(double)));
     h->a3_valid = 0;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
@@ -514,6 +558,15 @@ extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, co
     if (!x || !y || !z || !pot0 || !pot1 || !potr || !pott || !potp || !rr) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    if (g_bfe_blk_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
+        int rc = bfe_sl_ensure_a3(h, stream);
+        if (rc != BFE_OK) return rc;
+        const double2* A3 = reinterpret_cast<const double2*>(h->a3);
+        if (h->g.lmax == 4) sl_force_blk_kernel<4><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott, potp, rr);
+        else                sl_force_blk_kernel<6><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott, potp, rr);
+        BFE_LAUNCH_CHECK("sl_force_blk_kernel");
+        return BFE_OK;
+    }
     if (g_bfe_staged_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
         int rc = bfe_sl_ensure_a3(h, stream);
         if (rc != BFE_OK) return rc;
@@ -553,6 +606,15 @@ extern "C" int bfe_sl_force_eval_points(bfe_sl* h, int64_t n, const double* r, c
     if (!r || !costh || !phi || !potr || !pott || !potp || !pot1 || !pot0) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
+    if (g_bfe_blk_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
+        int rc = bfe_sl_ensure_a3(h, stream);
+        if (rc != BFE_OK) return rc;
+        const double2* A3 = reinterpret_cast<const double2*>(h->a3);
+        if (h->g.lmax == 4) sl_points_blk_kernel<4><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l, potr, pott, potp, pot1, pot0);
+        else                sl_points_blk_kernel<6><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l, potr, pott, potp, pot1, pot0);
+        BFE_LAUNCH_CHECK("sl_points_blk_kernel");
+        return BFE_OK;
+    }
     if (g_bfe_staged_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
         int rc = bfe_sl_ensure_a3(h, stream);
         if (rc != BFE_OK) return rc;
