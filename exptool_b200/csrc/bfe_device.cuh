@@ -807,6 +807,146 @@ struct CartForce {
     double fxd, fxh, fyd, fyh, fzd, fzh, pd, ph;
 };
 
+// ---------------------------------------------------------------------------
+// FP32-TABLE mode (option "table_fp32"; BASELINE north_star: "<= 1e-5 where FP32 table interpolation is used").
+// The contracted blocks are stored as float (G4f: 24 floats per (cell, m); A3f: 8 floats per (m,l) entry, see below), read
+// with the same 256-bit loads -- 8 values each, so HALF the L1 tag cycles of the FP64 blocks, which is what bounds
+// these kernels (ncu l1tex 92 %, profiles/r01_ncu_full_blk_kernels.csv).  Only the table VALUES are rounded to
+// float (6e-8 relative); bins, weights, Legendre functions, trig factors and all sums stay FP64.
+// ---------------------------------------------------------------------------
+#define BFE_A3F_STRIDE(npair) (8 * (npair))
+
+__device__ __forceinline__ void bfe_ldg256f(const float* p, float* v) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+
+template <int MCAP>
+__device__ __forceinline__ EofField bfe_eof_eval_blk32(const EofGeom& g, const float* __restrict__ G4f,
+                                                       const EofBin& b, double c1, double s1) {
+    const float* base = G4f + (size_t)b.cell * (size_t)(24 * (g.mmax + 1));
+    EofField f;
+    f.p0 = 0.0; f.p = 0.0; f.fr = 0.0; f.fp = 0.0; f.fz = 0.0;
+    double cm = 1.0, sm = 0.0;
+#pragma unroll
+    for (int m = 0; m <= MCAP; ++m) {
+        if (m <= g.mmax) {
+            // v[corner*6 + field*2 + cs], corners 00, 10, 01, 11
+            float v[24];
+            bfe_ldg256f(base + 24 * m, v); bfe_ldg256f(base + 24 * m + 8, v + 8); bfe_ldg256f(base + 24 * m + 16, v + 16);
+            double vpc = (double)v[0] * b.c00 + (double)v[6] * b.c10 + (double)v[12] * b.c01 + (double)v[18] * b.c11;
+            double vps = (double)v[1] * b.c00 + (double)v[7] * b.c10 + (double)v[13] * b.c01 + (double)v[19] * b.c11;
+            double vrc = (double)v[2] * b.c00 + (double)v[8] * b.c10 + (double)v[14] * b.c01 + (double)v[20] * b.c11;
+            double vrs = (double)v[3] * b.c00 + (double)v[9] * b.c10 + (double)v[15] * b.c01 + (double)v[21] * b.c11;
+            double vzc = (double)v[4] * b.c00 + (double)v[10] * b.c10 + (double)v[16] * b.c01 + (double)v[22] * b.c11;
+            double vzs = (double)v[5] * b.c00 + (double)v[11] * b.c10 + (double)v[17] * b.c01 + (double)v[23] * b.c11;
+            if (m == 0) {
+                f.p0 = vpc;
+                f.fr = vrc;
+                f.fz = vzc;
+            } else {
+                f.p  += cm * vpc + sm * vps;
+                f.fr += cm * vrc + sm * vrs;
+                f.fz += cm * vzc + sm * vzs;
+                f.fp += (double)m * (sm * vpc - cm * vps);
+            }
+            double cn = cm * c1 - sm * s1;
+            double sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+    }
+    return f;
+}
+
+// A3f block of radial interval i (0 <= i <= numr-2), one 32-byte entry per (m,l) in evaluation order:
+//   { a_i.x, a_i.y, a_{i+1}.x, a_{i+1}.y, D1.x, D1.y, D2.x, D2.y },   u_k = p0[k] a_k,  j = max(i, 1),
+//   D1 = (u_{j+1} - u_{j-1}) / 2,   D2 = u_{j-1} - 2 u_j + u_{j+1}
+// so that the derivative stencil of get_halo_dens_pot_force (spheresl.py:153-155)
+//   (x2 - 1/2) u_{j-1} - 2 x2 u_j + (x2 + 1/2) u_{j+1}  =  x2 D2 + D1
+// is formed from differences taken in FP64 BEFORE the rounding to float: storing the three node values as
+// floats and differencing afterwards amplifies their 6e-8 rounding by the ~1e3-1e4 cancellation of the stencil
+// (measured 3e-4 in the radial force; profiles/r01_blk_ab.json).
+template <int LCAP>
+__device__ __forceinline__ SlField bfe_sl_eval_blk32(const SlGeom& g, const float* __restrict__ A3f,
+                                                     const double* __restrict__ p0tab, const double* __restrict__ fac,
+                                                     const SlBin& b, double costh, double c1, double s1,
+                                                     bool trig_index_l) {
+    constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
+    const float* base = A3f + (size_t)b.i * (8 * NPAIR);
+    const double P0 = b.x1 * __ldg(p0tab + b.i) + b.x2 * __ldg(p0tab + b.i + 1);
+    const double wlo = b.x1 * P0, whi = b.x2 * P0, fx2 = b.fac * b.x2;
+
+    const double x = costh;
+    const double somx2 = sqrt(BFE_MUL(BFE_SUB(1.0, x), BFE_ADD(1.0, x)));
+    double xd = x;
+    if (1.0 - fabs(xd) < 1.0e-8) xd = (xd > 0.0) ? (1.0 - 1.0e-8) : -(1.0 - 1.0e-8);
+    const double dsom = BFE_DIV(1.0, BFE_SUB(BFE_MUL(xd, xd), 1.0));
+
+    SlField f;
+    f.pot0 = 0.0; f.pot1 = 0.0; f.potr = 0.0; f.pott = 0.0; f.potp = 0.0;
+    double pmm = 1.0, fact = 1.0;
+    double cm = 1.0, sm = 0.0;
+    int offm = 0;
+#pragma unroll
+    for (int m = 0; m <= LCAP; ++m) {
+        const int nl = LCAP - m + 1;
+        if (m > 0) {
+            pmm = BFE_MUL(pmm, BFE_MUL(-fact, somx2));
+            fact += 2.0;
+            double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+        double pl2 = 0.0, pl1 = pmm;
+        double cl = cm, sl = sm;
+#pragma unroll
+        for (int l = m; l <= LCAP; ++l) {
+            double P, dP;
+            if (l == m) {
+                P = pmm;
+                dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);
+            } else {
+                if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);
+                else P = bfe_div_int(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                             BFE_MUL((double)(l + m - 1), pl2)), l - m);
+                dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P), BFE_MUL((double)(l + m), pl1)));
+                pl2 = pl1; pl1 = P;
+                double cn = cl * c1 - sl * s1, sn = sl * c1 + cl * s1;
+                cl = cn; sl = sn;
+            }
+            float e[8];
+            bfe_ldg256f(base + 8 * (offm + l - m), e);
+            const double fl = __ldg(fac + l * (LCAP + 1) + m);
+            const double spc = wlo * (double)e[0] + whi * (double)e[2];
+            const double sdc = fx2 * (double)e[6] + b.fac * (double)e[4];
+            if (m == 0) {
+                if (l == 0) {
+                    f.pot0 = fl * spc;
+                    f.potr += fl * sdc;
+                } else {
+                    f.pot1 += fl * P * spc;
+                    f.potr += fl * P * sdc;
+                    f.pott += fl * dP * spc;
+                }
+            } else {
+                const double sps = wlo * (double)e[1] + whi * (double)e[3];
+                const double sds = fx2 * (double)e[7] + b.fac * (double)e[5];
+                const double ct = trig_index_l ? cl : cm;
+                const double stt = trig_index_l ? sl : sm;
+                const double Ap = spc * ct + sps * stt;
+                const double Ad = sdc * ct + sds * stt;
+                const double Bp = sps * ct - spc * stt;
+                const double fP = fl * P;
+                f.pot1 += fP * Ap;
+                f.potr += fP * Ad;
+                f.pott += fl * dP * Ap;
+                f.potp += fP * (double)m * Bp;
+            }
+        }
+        offm += nl;
+    }
+    return f;
+}
+
 // potential.py:475-497 (Cartesian) / 425-440 (cylindrical): disc + halo field components -> the 8 outputs.
 // The ten quotients by r2, r2^2, r3, r3^3 are formed from two reciprocals (a few ulp from the reference's
 // separate divisions: these are plain products, nothing downstream amplifies them).
@@ -867,9 +1007,9 @@ __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const dou
 }
 
 // The same with the block evaluations above (G4 / A3, 256-bit loads); valid for g.lmax == LCAP.
-template <int MCAP, int LCAP, bool CYL = false>
-__device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const double2* __restrict__ G4,
-                                                        const SlGeom& gs, const double2* __restrict__ A3,
+template <int MCAP, int LCAP, bool CYL = false, bool F32 = false>
+__device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const void* __restrict__ G4,
+                                                        const SlGeom& gs, const void* __restrict__ A3,
                                                         const double* __restrict__ xi, const double* __restrict__ p0tab,
                                                         const double* __restrict__ fac,
                                                         double x, double y, double z, double crot, double srot) {
@@ -883,8 +1023,15 @@ __device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const
     double sr = s1 * crot + c1 * srot;
     EofBin eb = bfe_eof_bin(ge, r2, z);
     SlBin sb = bfe_sl_bin(gs, xi, r3);
-    EofField d = bfe_eof_eval_blk<MCAP>(ge, G4, eb, cr, sr);
-    SlField h = bfe_sl_eval_blk<LCAP>(gs, A3, p0tab, fac, sb, costh, cr, sr, true);
+    EofField d;
+    SlField h;
+    if constexpr (F32) {
+        d = bfe_eof_eval_blk32<MCAP>(ge, static_cast<const float*>(G4), eb, cr, sr);
+        h = bfe_sl_eval_blk32<LCAP>(gs, static_cast<const float*>(A3), p0tab, fac, sb, costh, cr, sr, true);
+    } else {
+        d = bfe_eof_eval_blk<MCAP>(ge, static_cast<const double2*>(G4), eb, cr, sr);
+        h = bfe_sl_eval_blk<LCAP>(gs, static_cast<const double2*>(A3), p0tab, fac, sb, costh, cr, sr, true);
+    }
     return bfe_cart_combine<CYL>(d, h, x, y, z, r2, r3, gs.xi0);
 }
 

@@ -233,6 +233,19 @@ __global__ void eof_expand_g4_kernel(EofGeom g, const double* __restrict__ G, in
     }
 }
 
+// g_con [node][m][6] -> G4f [cell][m][corner][6 floats]  (table_fp32 mode)
+__global__ void eof_expand_g4f_kernel(EofGeom g, const double* __restrict__ G, int gstride, float* __restrict__ G4f) {
+    const int per = 24 * (g.mmax + 1);
+    const int64_t total = (int64_t)g.numx * g.numy * per;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int cell = (int)(t / per), c = (int)(t - (int64_t)cell * per);
+        const int m = c / 24, r = c - m * 24, corner = r / 6, part = r - corner * 6;
+        const int ix = cell / g.numy, iy = cell - ix * g.numy;
+        const int node = ix * g.ny1 + iy + ((corner & 1) ? g.ny1 : 0) + ((corner & 2) ? 1 : 0);   // 00,10,01,11
+        G4f[t] = (float)G[(size_t)node * gstride + m * 6 + part];
+    }
+}
+
 // warp-cooperative versions (bfe_eof_eval_staged): lanes of a warp take 32 consecutive points
 template <int MCAP>
 __global__ void __launch_bounds__(128)
@@ -338,6 +351,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     BFE_CUDA(cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->g4, (size_t)g.numx * g.numy * 12 * (p->mmax + 1) * 2 * sizeof(double)));
     h->g4_valid = 0;
+    h->g4f = nullptr; h->g4f_valid = 0;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)(h->max_ctas + 64) * h->nch_pad * sizeof(double)));   // + group rows of the two-level reduce
     BFE_CUDA(cudaMalloc(&h->counter, 128 * sizeof(unsigned int)));      // [0] last-CTA, [1] task queue, [64..] reduce groups
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 128 * sizeof(unsigned int), stream));
@@ -364,7 +378,7 @@ extern "C" int bfe_eof_clone(const bfe_eof* src, void* stream_, bfe_eof** out) {
     cudaStream_t stream = (cudaStream_t)stream_;
     bfe_eof* h = new bfe_eof(*src);
     h->owns_tables = 0;
-    h->contracted = 0; h->g4_valid = 0;
+    h->contracted = 0; h->g4_valid = 0; h->g4f = nullptr; h->g4f_valid = 0;
     h->sort_cap = 0; h->sort_ws = nullptr; h->prepared_n = -1; h->prepared_has_mass = 0;
     h->host_pipe = nullptr;
     h->g_con = nullptr; h->g4 = nullptr; h->partial = nullptr; h->counter = nullptr;
@@ -382,6 +396,7 @@ extern "C" void bfe_eof_destroy(bfe_eof* h) {
     if (!h) return;
     if (h->owns_tables) { cudaFree(h->t_acc); if (h->t_force) cudaFree(h->t_force); }
     cudaFree(h->g_con); cudaFree(h->g4); cudaFree(h->partial); cudaFree(h->counter);
+    if (h->g4f) cudaFree(h->g4f);
     if (h->sort_ws) cudaFree(h->sort_ws);
     bfe_host_pipe_destroy(h->host_pipe);
     delete h;
@@ -427,6 +442,7 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
     BFE_LAUNCH_CHECK("eof_contract_kernel");
     h->contracted = 1;
     h->g4_valid = 0;
+    h->g4f_valid = 0;
     return BFE_OK;
 }
 
@@ -462,6 +478,15 @@ eof_points_blk_kernel(EofGeom g, const double2* __restrict__ G4, int64_t n,
         EofField f = bfe_eof_eval_blk<MCAP>(g, G4, b, c1, s1);
         fr[i] = f.fr; fp[i] = f.fp; fz[i] = f.fz; p[i] = f.p + f.p0; p0[i] = f.p0;
     }
+}
+
+int bfe_eof_ensure_g4f(bfe_eof* h, cudaStream_t stream) {
+    if (h->g4f_valid) return BFE_OK;
+    if (!h->g4f) BFE_CUDA(cudaMalloc(&h->g4f, (size_t)h->g.numx * h->g.numy * 24 * (h->g.mmax + 1) * sizeof(float)));
+    eof_expand_g4f_kernel<<<h->num_sms * 8, 256, 0, stream>>>(h->g, h->g_con, h->gstride, h->g4f);
+    BFE_LAUNCH_CHECK("eof_expand_g4f_kernel");
+    h->g4f_valid = 1;
+    return BFE_OK;
 }
 
 int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream) {

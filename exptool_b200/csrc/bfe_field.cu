@@ -110,23 +110,23 @@ leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
 
 // per-lane variants on the per-cell / per-interval blocks with 256-bit loads (bfe_field_cart_blk): half the load
 // instructions of the kernels above, no shared-memory stage; valid for mmax <= MCAP, lmax == LCAP == 6
-template <int MCAP, int LCAP, bool CYL>
+template <int MCAP, int LCAP, bool CYL, bool F32>
 __global__ void __launch_bounds__(128)
-field_cart_blk_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
+field_cart_blk_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
                       const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
                       int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                       const double* __restrict__ z, double crot, double srot, double* __restrict__ out8) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        CartForce f = bfe_field_cart_blk<MCAP, LCAP, CYL>(ge, G4, gs, A3, xi, p0tab, fac,
-                                                          __ldg(x + i), __ldg(y + i), __ldg(z + i), crot, srot);
+        CartForce f = bfe_field_cart_blk<MCAP, LCAP, CYL, F32>(ge, G4, gs, A3, xi, p0tab, fac,
+                                                               __ldg(x + i), __ldg(y + i), __ldg(z + i), crot, srot);
         out8[i] = f.fxd; out8[n + i] = f.fxh; out8[2 * n + i] = f.fyd; out8[3 * n + i] = f.fyh;
         out8[4 * n + i] = f.fzd; out8[5 * n + i] = f.fzh; out8[6 * n + i] = f.pd; out8[7 * n + i] = f.ph;
     }
 }
 
-template <int MCAP, int LCAP>
+template <int MCAP, int LCAP, bool F32>
 __global__ void __launch_bounds__(128)
-leapfrog_blk_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
+leapfrog_blk_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
                     const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
                     int64_t norbit, int64_t nint, double dt, const double* __restrict__ dt_orbit, double rotfreq,
                     double* __restrict__ state6, double* __restrict__ traj, int64_t traj_stride,
@@ -140,7 +140,7 @@ leapfrog_blk_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const
     const double hdt2 = 0.5 * (dt * dt);
     double srot, crot;
     sincos(w * (0.0 * dt), &srot, &crot);
-    CartForce f = bfe_field_cart_blk<MCAP, LCAP>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+    CartForce f = bfe_field_cart_blk<MCAP, LCAP, false, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
     double ax = f.fxd + f.fxh, ay = f.fyd + f.fyh, az = f.fzd + f.fzh, pot = f.pd + f.ph;
     if (traj) {
         double* t = traj + i;
@@ -155,7 +155,7 @@ leapfrog_blk_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const
         py = py + (vy * dt) + (ay * hdt2);
         pz = pz + (vz * dt) + (az * hdt2);
         sincos(w * ((double)step * dt), &srot, &crot);
-        f = bfe_field_cart_blk<MCAP, LCAP>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+        f = bfe_field_cart_blk<MCAP, LCAP, false, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
         double bx = f.fxd + f.fxh, by = f.fyd + f.fyh, bz = f.fzd + f.fzh;
         pot = f.pd + f.ph;
         vx = vx + (0.5 * (ax + bx) * dt);
@@ -205,15 +205,18 @@ static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x,
     int grid = (int)(need < cap ? need : cap);
     double crot = cos(rotpos), srot = sin(rotpos);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
-        int rc = bfe_eof_ensure_g4(he, stream);
-        if (rc == BFE_OK) rc = bfe_sl_ensure_a3(hs, stream);
+        const bool f32 = g_bfe_table_fp32 != 0;
+        int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
+        if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
         if (rc != BFE_OK) return rc;
-        const double2* G4 = reinterpret_cast<const double2*>(he->g4);
-        const double2* A3 = reinterpret_cast<const double2*>(hs->a3);
-#define FIELD_BLK(L, C) field_cart_blk_kernel<6, L, C><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, \
-                                                                              hs->fac, n, x, y, z, crot, srot, out8)
-        if (hs->g.lmax == 4) { if (cyl) FIELD_BLK(4, true); else FIELD_BLK(4, false); }
-        else                 { if (cyl) FIELD_BLK(6, true); else FIELD_BLK(6, false); }
+        const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
+        const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+#define FIELD_BLK(L, C, F) field_cart_blk_kernel<6, L, C, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, \
+                                                                                    hs->fac, n, x, y, z, crot, srot, out8)
+#define FIELD_BLK2(L, C) do { if (f32) FIELD_BLK(L, C, true); else FIELD_BLK(L, C, false); } while (0)
+        if (hs->g.lmax == 4) { if (cyl) FIELD_BLK2(4, true); else FIELD_BLK2(4, false); }
+        else                 { if (cyl) FIELD_BLK2(6, true); else FIELD_BLK2(6, false); }
+#undef FIELD_BLK2
 #undef FIELD_BLK
         BFE_LAUNCH_CHECK("field_cart_blk_kernel");
         return BFE_OK;
@@ -264,17 +267,17 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = (int)((norbit + 127) / 128);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
-        int rc = bfe_eof_ensure_g4(he, stream);
-        if (rc == BFE_OK) rc = bfe_sl_ensure_a3(hs, stream);
+        const bool f32 = g_bfe_table_fp32 != 0;
+        int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
+        if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
         if (rc != BFE_OK) return rc;
-        const double2* G4 = reinterpret_cast<const double2*>(he->g4);
-        const double2* A3 = reinterpret_cast<const double2*>(hs->a3);
-        if (hs->g.lmax == 4)
-            leapfrog_blk_kernel<6, 4><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, nint, dt,
-                                                               dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
-        else
-            leapfrog_blk_kernel<6, 6><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, nint, dt,
-                                                               dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out);
+        const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
+        const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+#define LEAP_BLK(L, F) leapfrog_blk_kernel<6, L, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, \
+                                                                           nint, dt, dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out)
+        if (hs->g.lmax == 4) { if (f32) LEAP_BLK(4, true); else LEAP_BLK(4, false); }
+        else                 { if (f32) LEAP_BLK(6, true); else LEAP_BLK(6, false); }
+#undef LEAP_BLK
         BFE_LAUNCH_CHECK("leapfrog_blk_kernel");
         return BFE_OK;
     }
@@ -313,6 +316,7 @@ int g_bfe_sort_min_particles = 32768;
 int g_bfe_sl_accumulate_mode = 0;
 int g_bfe_staged_eval = 1;
 int g_bfe_blk_eval = 1;
+int g_bfe_table_fp32 = 0;
 int g_bfe_force_mma = 1;
 static int g_bfe_time_kernels = 0;
 int g_bfe_pdl = 1;
@@ -343,6 +347,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "time_kernels")) { g_bfe_time_kernels = value; return BFE_OK; }
     if (!strcmp(name, "staged_eval")) { g_bfe_staged_eval = value; return BFE_OK; }
     if (!strcmp(name, "blk_eval")) { g_bfe_blk_eval = value; return BFE_OK; }
+    if (!strcmp(name, "table_fp32")) { g_bfe_table_fp32 = value; return BFE_OK; }
     if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
     if (!strcmp(name, "pdl")) { g_bfe_pdl = value; return BFE_OK; }
     if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }

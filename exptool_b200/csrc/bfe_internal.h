@@ -42,6 +42,8 @@ struct bfe_eof {
     // (built on demand from g_con for the warp-cooperative kernels)
     double* g4;
     int g4_valid;
+    float* g4f;          // FP32 copy of G4 for the table_fp32 mode (allocated on first use)
+    int g4f_valid;
     // accumulate workspace
     double* partial;     // [max_ctas][nch_pad]
     unsigned int* counter;
@@ -76,6 +78,8 @@ struct bfe_sl {
     // the same rows as one contiguous block per radial index j: A3[j][(m,l)][rows j-1, j, j+1] (double2)
     double* a3;
     int a3_valid;
+    float* a3f;          // FP32 copy of A3 for the table_fp32 mode (allocated on first use)
+    int a3f_valid;
     double* partial;     // [max_ctas][nrow*nmax]
     unsigned int* counter;
     int max_ctas;
@@ -104,6 +108,9 @@ void bfe_set_cuda_error(cudaError_t e, const char* where);
 int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream);     // build G4 from g_con if stale
 int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream);       // build A3 from a_con if stale
 extern int g_bfe_force_mma;                                 // option "force_mma": sorted force eval on DMMA (1, default) / per lane (0)
+extern int g_bfe_table_fp32;                                // option "table_fp32": float contracted tables in the per-point field kernels
+int bfe_eof_ensure_g4f(bfe_eof* h, cudaStream_t stream);
+int bfe_sl_ensure_a3f(bfe_sl* h, cudaStream_t stream);
 extern int g_bfe_blk_eval;                                  // option "blk_eval": per-lane block evaluation with 256-bit loads
 extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0
 

@@ -202,10 +202,34 @@ __global__ void sl_expand_a3_kernel(SlGeom g, const double2* __restrict__ A, int
     }
 }
 
+// float blocks of the table_fp32 mode: A3f[i][8*(offm(m) + l - m) + ...], layout and rationale at bfe_sl_eval_blk32
+__global__ void sl_expand_a3f_kernel(SlGeom g, const double2* __restrict__ A, int qstride, const double* __restrict__ p0,
+                                     float* __restrict__ A3f) {
+    const int npair = qstride;
+    const int64_t total = (int64_t)(g.numr - 1) * npair;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / npair), qm = (int)(t - (int64_t)i * npair);
+        int m = 0, off = 0;
+        while (qm >= off + (g.lmax - m + 1)) { off += g.lmax - m + 1; ++m; }
+        const int l = m + (qm - off);
+        const int q = (l * (l + 1)) / 2 + m;
+        const int j = (i == 0) ? 1 : i;
+        const double2 alo = A[(size_t)i * qstride + q], ahi = A[(size_t)(i + 1) * qstride + q];
+        const double2 am = A[(size_t)(j - 1) * qstride + q], a0 = A[(size_t)j * qstride + q], ap = A[(size_t)(j + 1) * qstride + q];
+        const double pm = p0[j - 1], pc = p0[j], pp = p0[j + 1];
+        const double umx = pm * am.x, u0x = pc * a0.x, upx = pp * ap.x;
+        const double umy = pm * am.y, u0y = pc * a0.y, upy = pp * ap.y;
+        float* o = A3f + (size_t)t * 8;
+        o[0] = (float)alo.x; o[1] = (float)alo.y; o[2] = (float)ahi.x; o[3] = (float)ahi.y;
+        o[4] = (float)(0.5 * (upx - umx)); o[5] = (float)(0.5 * (upy - umy));
+        o[6] = (float)((umx - u0x) + (upx - u0x)); o[7] = (float)((umy - u0y) + (upy - u0y));
+    }
+}
+
 // per-lane block evaluation with 256-bit loads (bfe_sl_eval_blk); valid for g.lmax == LCAP
-template <int LCAP>
+template <int LCAP, bool F32>
 __global__ void __launch_bounds__(128)
-sl_force_blk_kernel(SlGeom g, const double2* __restrict__ A3, const double* __restrict__ xi,
+sl_force_blk_kernel(SlGeom g, const void* __restrict__ A3, const double* __restrict__ xi,
                     const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
                     const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                     double* __restrict__ pot0, double* __restrict__ pot1, double* __restrict__ potr,
@@ -219,7 +243,9 @@ sl_force_blk_kernel(SlGeom g, const double2* __restrict__ A3, const double* __re
         double c1, s1;
         bfe_cossin_phi(px, py, c1, s1);
         SlBin b = bfe_sl_bin(g, xi, r);
-        SlField f = bfe_sl_eval_blk<LCAP>(g, A3, p0tab, fac, b, costh, c1, s1, false);
+        SlField f;
+        if constexpr (F32) f = bfe_sl_eval_blk32<LCAP>(g, static_cast<const float*>(A3), p0tab, fac, b, costh, c1, s1, false);
+        else               f = bfe_sl_eval_blk<LCAP>(g, static_cast<const double2*>(A3), p0tab, fac, b, costh, c1, s1, false);
         pot0[i] = f.pot0; pot1[i] = f.pot1; potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; rr[i] = rxy;
     }
 }
@@ -466,6 +492,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->a_con, nr * h->kpad * 2 * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->a3, nr * (size_t)BFE_A3_STRIDE(h->kpad) * 2 * sizeof(double)));
     h->a3_valid = 0;
+    h->a3f = nullptr; h->a3f_valid = 0;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
@@ -498,7 +525,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
 extern "C" void bfe_sl_destroy(bfe_sl* h) {
     if (!h) return;
     cudaFree(h->e_node); cudaFree(h->xi); cudaFree(h->p0); cudaFree(h->d0); cudaFree(h->fac);
-    cudaFree(h->ev); if (h->ad_con) cudaFree(h->ad_con);
+    cudaFree(h->ev); if (h->ad_con) cudaFree(h->ad_con); if (h->a3f) cudaFree(h->a3f);
     cudaFree(h->a_con); cudaFree(h->a3); cudaFree(h->partial); cudaFree(h->counter);
     if (h->sort_ws) cudaFree(h->sort_ws);
     delete h;
@@ -530,6 +557,16 @@ extern "C" int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2,
     BFE_LAUNCH_CHECK("sl_contract_kernel");
     h->contracted = 1;
     h->a3_valid = 0;
+    h->a3f_valid = 0;
+    return BFE_OK;
+}
+
+int bfe_sl_ensure_a3f(bfe_sl* h, cudaStream_t stream) {
+    if (h->a3f_valid) return BFE_OK;
+    if (!h->a3f) BFE_CUDA(cudaMalloc(&h->a3f, (size_t)h->g.numr * BFE_A3F_STRIDE(h->kpad) * sizeof(float)));
+    sl_expand_a3f_kernel<<<h->num_sms * 4, 256, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->p0, h->a3f);
+    BFE_LAUNCH_CHECK("sl_expand_a3f_kernel");
+    h->a3f_valid = 1;
     return BFE_OK;
 }
 
@@ -559,11 +596,14 @@ extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, co
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
     if (g_bfe_blk_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
-        int rc = bfe_sl_ensure_a3(h, stream);
+        const bool f32 = g_bfe_table_fp32 != 0;
+        int rc = f32 ? bfe_sl_ensure_a3f(h, stream) : bfe_sl_ensure_a3(h, stream);
         if (rc != BFE_OK) return rc;
-        const double2* A3 = reinterpret_cast<const double2*>(h->a3);
-        if (h->g.lmax == 4) sl_force_blk_kernel<4><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott, potp, rr);
-        else                sl_force_blk_kernel<6><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott, potp, rr);
+        const void* A3 = f32 ? (const void*)h->a3f : (const void*)h->a3;
+#define SL_BLK(L, F) sl_force_blk_kernel<L, F><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott, potp, rr)
+        if (h->g.lmax == 4) { if (f32) SL_BLK(4, true); else SL_BLK(4, false); }
+        else                { if (f32) SL_BLK(6, true); else SL_BLK(6, false); }
+#undef SL_BLK
         BFE_LAUNCH_CHECK("sl_force_blk_kernel");
         return BFE_OK;
     }

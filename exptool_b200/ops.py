@@ -50,7 +50,9 @@ def to_host(t):
 
 
 def set_option(name, value):
-    """bfe_set_option: 'eof_accumulate_mode' / 'eof_force_mode' (0 auto, 1 direct, 2 sorted), 'sort_min_particles'."""
+    """bfe_set_option: 'eof_accumulate_mode' / 'eof_force_mode' (0 auto, 1 direct, 2 sorted), 'sort_min_particles',
+    'staged_eval' / 'blk_eval' (per-point kernel variants), 'table_fp32' (1: the contracted tables of the per-point
+    field kernels -- Fields.return_forces_*, leapfrog, SL evaluation -- are held as float: ~1e-7 relative, faster)."""
     _lib.check(_lib.load().bfe_set_option(name.encode(), int(value)))
 
 

@@ -71,6 +71,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--scale', type=float, default=1.0)
     ap.add_argument('--configs', default='1,2,3,4,5')
+    ap.add_argument('--table-fp32', type=int, default=0, help='1: option table_fp32 (float contracted tables in the per-point field kernels)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -79,11 +80,12 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     want = set(int(c) for c in args.configs.split(','))
+    ops.set_option('table_fp32', args.table_fp32)
     E = eof_handle()
 
     def emit(d):
         if rank == 0:
-            d.update(n_gpus=world, dtype='f64', data='synthetic')
+            d.update(n_gpus=world, dtype='f64', data='synthetic', tables='fp32' if args.table_fp32 else 'fp64')
             print(json.dumps(d), flush=True)
 
     # C1: SL lmax=4 nmax=18, accumulate + force eval, 1e5 Hernquist particles

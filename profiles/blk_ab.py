@@ -42,8 +42,8 @@ x, y = pos0[0], pos0[1]
 R = torch.sqrt(x * x + y * y) + 1e-6
 vel0 = torch.stack([-y / R, x / R, torch.zeros_like(x)]) * 1.5
 res, outs = {}, {}
-for name, staged, blk in (('per_lane', 0, 0), ('staged', 1, 0), ('blk256', 0, 1)):
-    ops.set_option('staged_eval', staged); ops.set_option('blk_eval', blk)
+for name, staged, blk, f32 in (('per_lane', 0, 0, 0), ('staged', 1, 0, 0), ('blk256', 1, 1, 0), ('blk256_fp32_tables', 1, 1, 1)):
+    ops.set_option('staged_eval', staged); ops.set_option('blk_eval', blk); ops.set_option('table_fp32', f32)
     r_ = {}
     r_['field_cart_disc_us'] = timeit(lambda k: ops.field_force_cart(E, H, *disc[k % NS][:3], rotpos=0.3))
     r_['field_cart_halo_us'] = timeit(lambda k: ops.field_force_cart(E, H, *halo[k % NS][:3], rotpos=0.3))
@@ -58,7 +58,8 @@ for name, staged, blk in (('per_lane', 0, 0), ('staged', 1, 0), ('blk256', 0, 1)
     st, tr, ns = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
     outs[name] = (ops.field_force_cart(E, H, *disc[1][:3], rotpos=0.3).cpu().numpy(),
                   ops.field_force_cart(E, H, *halo[1][:3], rotpos=0.3).cpu().numpy(), st.cpu().numpy())
-ops.set_option('staged_eval', 1); ops.set_option('blk_eval', 0)
+ops.set_option('staged_eval', 1); ops.set_option('blk_eval', 1); ops.set_option('table_fp32', 0)
 def rel(a, b): return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 res['blk_vs_per_lane_relerr'] = [rel(outs['blk256'][i], outs['per_lane'][i]) for i in range(3)]
+res['fp32_tables_vs_fp64_relerr'] = [rel(outs['blk256_fp32_tables'][i], outs['per_lane'][i]) for i in range(3)]
 print(json.dumps(dict(n=n, norbit=norb, nint=nint, res=res), indent=1))

@@ -197,6 +197,45 @@ def test_leapfrog_golden(ops, name):
         assert relerr(traj[:, j, 0], d['orbit_trunc'][j]) < ORBIT_TOL, j
 
 
+FP32_TABLE_TOL = 1e-5      # BASELINE.json north_star: "<= 1e-5 where FP32 table interpolation is used"
+
+
+@pytest.mark.parametrize('name', FIELD_CASES)
+def test_fp32_table_mode(ops, name):
+    """Option table_fp32: the contracted tables of the per-point field kernels are stored as float (half the
+    L1 tag cycles); everything else stays FP64.  Same goldens, the tolerance north_star states for this mode."""
+    d, meta = load_golden(name)
+    E, H, g, ps = _field_handles(ops, meta, d)
+    E.contract(d['cos'], d['sin'])
+    H.contract(meta['halofac'] * d['coef'])
+    ops.set_option('table_fp32', 1)
+    try:
+        out = ops.field_force_cart(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full']).cpu().numpy()
+        errs = [relerr(out[i], d['cart_full'][:, i]) for i in range(8)]
+        assert max(errs) < FP32_TABLE_TOL, errs
+        assert max(errs) > 1e-12, 'FP32 tables not in use?'
+        nint = meta['nint']
+        state, traj, nsteps = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, meta['dt'], rotfreq=meta['rotfreq'],
+                                           traj_stride=1)
+        traj = traj.cpu().numpy()
+        ref = d['orbits']
+        for k in range(ref.shape[0]):
+            for j in range(6):          # phase-space coordinates after nint steps of accumulated table rounding
+                assert relerr(traj[:, j, k], ref[k, j]) < 10 * FP32_TABLE_TOL, (k, j)
+        if ps['lmax'] in (4, 6):
+            sl = H.force(d['px'], d['py'], d['pz']).cpu().numpy()
+            ops.set_option('table_fp32', 0)
+            sl64 = H.force(d['px'], d['py'], d['pz']).cpu().numpy()
+            for i in range(5):
+                assert relerr(sl[i], sl64[i]) < FP32_TABLE_TOL, i
+    finally:
+        ops.set_option('table_fp32', 0)
+    # back in FP64 mode the contraction is re-expanded and parity is the FP64 one again
+    out = ops.field_force_cart(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full']).cpu().numpy()
+    for i in range(8):
+        assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+
+
 # ---------------------------------------------------------------------------
 # larger seeded inputs against the oracle (sizes the oracle finishes in seconds)
 # ---------------------------------------------------------------------------
