@@ -501,3 +501,88 @@ def restore_eof_coefficients(infile):
             except Exception:
                 pass
     return EOF_Out, EOF_Dict
+
+
+# ---------------------------------------------------------------------------
+# coefficient time-series consumers -- eof.py:1920-2108 (host NumPy post-processing of the (time -> EOF_Object)
+# dictionaries that restore_eof_coefficients / a series of accumulations produce)
+# ---------------------------------------------------------------------------
+def reorganize_eof_dict(EOFDict):
+    '''
+    eof.reorganize_eof_dict (eof.py:1920-1958): {'time', 'total'[m] (t, n) = cos^2 + sin^2, 'sum'[m] (t,),
+    'cos'[m] (n, t), 'sin'[m] (n, t)}, all in time order.  The basis size is read from EOFDict[0] as in the
+    reference (the dictionary must have a key 0).
+    '''
+    mmax, nmax = EOFDict[0].mmax, EOFDict[0].nmax
+    keys = list(EOFDict.keys())
+    cos = np.array([np.asarray(EOFDict[k].cos, dtype=np.float64)[:mmax + 1, :nmax] for k in keys])   # (t, m, n)
+    sin = np.array([np.asarray(EOFDict[k].sin, dtype=np.float64)[:mmax + 1, :nmax] for k in keys])
+    times = np.array([EOFDict[k].time for k in keys], dtype=np.float64)
+    order = times.argsort()
+    power = cos ** 2. + sin ** 2.
+    CDict = {'time': times[order], 'total': {}, 'sum': {}, 'cos': {}, 'sin': {}}
+    for mm in range(mmax + 1):
+        CDict['total'][mm] = power[order, mm, :]
+        CDict['sum'][mm] = np.sum(power[:, mm, :], axis=1)[order]
+        CDict['cos'][mm] = cos[order, mm, :].T          # (n, t): the reference's mixed index + .T (eof.py:1955-1956)
+        CDict['sin'][mm] = sin[order, mm, :].T
+    return CDict
+
+
+def calculate_eof_phase(EOFDict, filter=True, smooth_box=101, smooth_order=2, tol=-1.5 * np.pi, nonan=False,
+                        signal_threshold=0.005):
+    '''
+    eof.calculate_eof_phase (eof.py:1961-2108): per-(m, n) phase arctan2(sin, cos), relative amplitude ('signal',
+    normalised by sum |cos[0]|), unwrapped phase and its finite-difference rate ('speed'), the same for the
+    n-summed coefficients ('netphase', 'netspeed'), and the fraction of increasing phase steps ('direction').
+    Kept from the reference: the +pi in-place shift that unwrap_phase applies to a series with negative values
+    also lands in DC['phase'] / DC['netphase']; |unwrapped phase| is differenced; the first speed equals the second.
+    '''
+    from ..utils import utils
+    keys = list(EOFDict.keys())
+    first = EOFDict[keys[0]]
+    mmax, nmax = first.mmax, first.nmax
+    cos = np.array([np.asarray(EOFDict[k].cos, dtype=np.float64)[:mmax + 1, :nmax] for k in keys])   # (t, m, n)
+    sin = np.array([np.asarray(EOFDict[k].sin, dtype=np.float64)[:mmax + 1, :nmax] for k in keys])
+    times = np.array([EOFDict[k].time for k in keys], dtype=np.float64)
+    order = times.argsort()
+    nt = len(keys)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        phases = np.arctan2(sin, cos)
+        signal = np.sqrt(cos * cos + sin * sin) / np.sum(np.sqrt(cos[:, 0, :] * cos[:, 0, :]), axis=1)[:, None, None]
+    netph = np.arctan2(np.sum(sin, axis=2), np.sum(cos, axis=2))
+    DC = {'time': times[order], 'phase': {}, 'netphase': {}, 'unphase': {}, 'speed': {}, 'netspeed': {},
+          'signal': {}, 'direction': {}}
+    dtime = np.ediff1d(DC['time'], to_begin=100.)
+    for mm in range(1, mmax + 1):
+        DC['phase'][mm] = phases[order, mm, :].copy()
+        DC['netphase'][mm] = netph[order, mm].copy()
+        DC['signal'][mm] = signal[order, mm, :].copy()
+    for mm in range(1, mmax + 1):
+        DC['speed'][mm] = np.zeros([nt, nmax])
+        DC['unphase'][mm] = np.zeros([nt, nmax])
+        DC['direction'][mm] = np.zeros(nmax)
+        for nn in range(nmax):
+            col = DC['phase'][mm][:, nn]                    # a view: unwrap_phase may shift it by +pi in place
+            DC['direction'][mm][nn] = float(np.where(np.ediff1d(col) > 0.)[0].size) / float(col.size)
+            tmp_unphase = np.abs(utils.unwrap_phase(DC['time'], col))
+            if not nonan:
+                good = DC['signal'][mm][:, nn] > signal_threshold
+                bad = DC['signal'][mm][:, nn] < signal_threshold
+                DC['unphase'][mm][good, nn] = tmp_unphase[good]
+                DC['unphase'][mm][bad, nn] = np.nan
+            else:
+                DC['unphase'][mm][:, nn] = tmp_unphase
+            series = DC['unphase'][mm][:, nn]
+            if filter:
+                series = utils.savitzky_golay(series, smooth_box, smooth_order)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                DC['speed'][mm][:, nn] = np.ediff1d(series, to_begin=0.) / dtime
+            DC['speed'][mm][0, nn] = DC['speed'][mm][1, nn]
+        net = utils.unwrap_phase(DC['time'], DC['netphase'][mm])
+        if filter:
+            net = utils.savitzky_golay(net, smooth_box, smooth_order)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            DC['netspeed'][mm] = np.ediff1d(net, to_begin=0.) / dtime
+        DC['netspeed'][mm][0] = DC['netspeed'][mm][1]
+    return DC
