@@ -266,6 +266,27 @@ def run_gpu(args):
         for st_ in streams:
             pgs[st_.cuda_stream] = dist.new_group(list(range(world)))
 
+    # the per-step coefficient sum: one kernel over NVLink peer memory per stream (bfe_peer_allreduce), NCCL if
+    # the peer buffers cannot be set up on this box
+    peers = {}
+    allreduce_kind = 'none'
+    if world > 1:
+        allreduce_kind = 'nccl'
+        if args.allreduce == 'peer':
+            try:
+                for st_ in streams + [torch.cuda.current_stream()]:
+                    peers[st_.cuda_stream] = parallel.PeerAllreduce(1024)
+                allreduce_kind = 'peer-memory kernel (bfe_peer_allreduce)'
+            except Exception as e_:
+                peers = {}
+                if rank == 0:
+                    print('bench: peer-memory allreduce unavailable (%s); NCCL' % (e_,), file=sys.stderr)
+        flag = torch.tensor([1.0 if peers else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks or none
+        if float(flag.item()) == 0.0:
+            peers = {}
+            allreduce_kind = 'nccl'
+
     def step_on(k, Ei, coef, torch_stream):
         # one cell sort of the particle set serves both passes (include/bfe.h: bfe_eof_prepare)
         px, py, pz, pm = set_ptrs[k % NSETS]
@@ -276,8 +297,12 @@ def run_gpu(args):
         rc = lib.bfe_eof_prepare(Ei.h, N_PART, px, py, pz, pm, st)
         rc = rc or lib.bfe_eof_accumulate_prepared(Ei.h, c0, c1, st)
         if world > 1:
-            with torch.cuda.stream(torch_stream):
-                dist.all_reduce(coef, group=pgs.get(torch_stream.cuda_stream))
+            pa = peers.get(torch_stream.cuda_stream)
+            if pa is not None:
+                rc = rc or lib.bfe_peer_allreduce(pa.h, c0, 2 * (mmax_ + 1) * norder_, st)
+            else:
+                with torch.cuda.stream(torch_stream):
+                    dist.all_reduce(coef, group=pgs.get(torch_stream.cuda_stream))
         rc = rc or lib.bfe_eof_contract(Ei.h, c0, c1, 0, mmax_, norder_, 0, st)
         rc = rc or lib.bfe_eof_force_prepared(Ei.h, *out_ptrs[k % NSETS], st)
         if rc:
@@ -474,6 +499,7 @@ def run_gpu(args):
                            'streams': NSTREAMS,
                            'in_flight': '%d independent particle sets in flight on %d CUDA streams (cloned handles, '
                                         'shared tables); a step is serial on its stream' % (NSTREAMS, NSTREAMS),
+                           'allreduce': allreduce_kind,
                            'parallelism': 'particles sharded over %d GPU(s), one 2 kB coefficient allreduce per step'
                                           % world if world > 1 else 'single GPU'},
                 'host_issue_ms_per_step': host_issue_ms,
@@ -496,9 +522,13 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--streams', type=int, default=2, help='independent particle sets in flight (CUDA streams)')
+    ap.add_argument('--streams', type=int, default=3, help='independent particle sets in flight (CUDA streams)')
+    ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
+                    help='N>1: per-step coefficient sum by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--pg-per-stream', type=int, default=0, help='N>1: one NCCL communicator per stream (1) or shared (0)')
     args = ap.parse_args()
+    if args.allreduce == 'nccl':
+        os.environ['BFE_PEER_ALLREDUCE'] = '0'          # the API-level (e2e) coefficient sum follows the same choice
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == 'reference':

@@ -59,6 +59,14 @@ SIGNATURES = {
     'bfe_sl_contract': (_INT, [_P, _P, _INT, _INT, _INT, _INT, _P]),
     'bfe_sl_force_contracted': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_sl_force': (_INT, [_P, _I64] + [_P] * 3 + [_P, _INT, _INT, _INT] + [_P] * 6 + [_P]),
+    'bfe_peer_buffer_create': (_INT, [_I64, C.POINTER(_P), C.c_char_p]),
+    'bfe_peer_buffer_open': (_INT, [C.c_char_p, C.POINTER(_P)]),
+    'bfe_peer_buffer_close': (_INT, [_P]),
+    'bfe_peer_buffer_destroy': (_INT, [_P]),
+    'bfe_peer_create': (_INT, [_INT, _INT, _I64, C.POINTER(_P), C.POINTER(_P)]),
+    'bfe_peer_destroy': (None, [_P]),
+    'bfe_peer_allreduce': (_INT, [_P, _P, _I64, _P]),
+    'bfe_peer_error': (_INT, [_P, _P, C.POINTER(C.c_uint64)]),
     'bfe_eof_return_bins': (_INT, [C.POINTER(EofParams), _I64] + [_P] * 6 + [_P]),
     'bfe_eof_get_pot': (_INT, [_P, _I64, _P, _P, C.c_double, _P, _P, _P]),
     'bfe_sl_radial_matrices': (_INT, [_P, _I64, _P, _P, _P, _P, _P]),

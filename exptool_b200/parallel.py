@@ -48,10 +48,99 @@ def my_shard(n):
     return shard_bounds(n, ws)[rank]
 
 
+class PeerAllreduce(object):
+    """
+    The coefficient sum as one kernel over NVLink peer memory (include/bfe.h: bfe_peer_*): every rank maps every
+    other rank's exchange buffer through CUDA IPC; torch.distributed only carries the 64-byte handles once.
+    One instance per stream of collectives (calls must come in the same order on every rank).
+    """
+
+    def __init__(self, ncoef_max=4096):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = world()
+        self.ncoef_max = int(ncoef_max)
+        self.h = None
+        local = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.bfe_peer_buffer_create(self.ncoef_max, C.byref(local), handle))
+        self.local = local
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw)
+        self.opened = []
+        ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = local.value
+            else:
+                p = C.c_void_p()
+                _lib.check(self.lib.bfe_peer_buffer_open(handles[r], C.byref(p)))
+                self.opened.append(p)
+                ptrs[r] = p.value
+        h = C.c_void_p()
+        _lib.check(self.lib.bfe_peer_create(self.rank, self.world, self.ncoef_max, ptrs, C.byref(h)))
+        self.h = h
+        dist.barrier()                      # every buffer is zeroed and mapped before the first push
+
+    def allreduce_(self, t, stream=None):
+        """in-place sum over ranks of a contiguous FP64 device tensor with numel <= ncoef_max"""
+        import ctypes as C
+        from . import _lib
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= self.ncoef_max):
+            raise ValueError('PeerAllreduce needs a contiguous FP64 device tensor of at most %d values' % self.ncoef_max)
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(self.lib.bfe_peer_allreduce(self.h, C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(st)))
+        return t
+
+    def first_failed_sequence(self):
+        import ctypes as C
+        from . import _lib
+        v = C.c_uint64(0)
+        _lib.check(self.lib.bfe_peer_error(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if self.h:
+            torch.cuda.synchronize()
+            self.lib.bfe_peer_destroy(self.h)
+            self.h = None
+            for p in self.opened:
+                self.lib.bfe_peer_buffer_close(p)
+            self.lib.bfe_peer_buffer_destroy(self.local)
+
+
+_PEER = {'obj': None, 'failed': False}
+
+
+def _peer_allreduce_for(t):
+    """the process-wide PeerAllreduce for small coefficient blocks on the current stream, or None (-> NCCL)"""
+    import os
+    if _PEER['failed'] or os.environ.get('BFE_PEER_ALLREDUCE', '1') == '0':
+        return None
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() <= 4096):
+        return None
+    if dist.get_backend() != 'nccl':
+        return None
+    if _PEER['obj'] is None:
+        try:
+            _PEER['obj'] = PeerAllreduce(4096)
+        except Exception as e:                         # no peer access / IPC on this box: NCCL does the sum
+            _PEER['failed'] = True
+            import sys
+            print('exptool_b200.parallel: peer-memory allreduce unavailable (%s); using NCCL' % (e,), file=sys.stderr)
+            return None
+    return _PEER['obj']
+
+
 def allreduce_sum_(t):
-    """In-place sum over ranks of a coefficient tensor (no-op on one rank)."""
+    """In-place sum over ranks of a coefficient tensor (no-op on one rank).  Small FP64 device blocks go through
+    the peer-memory kernel (PeerAllreduce) on NCCL jobs, everything else through torch.distributed."""
     if not is_distributed():
         return t
+    peer = _peer_allreduce_for(t)
+    if peer is not None:
+        return peer.allreduce_(t)
     if dist.get_backend() == 'gloo' and t.is_cuda:
         h = t.cpu()
         dist.all_reduce(h, op=dist.ReduceOp.SUM)

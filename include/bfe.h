@@ -201,6 +201,25 @@ int bfe_sl_density_eval_points(bfe_sl* h, int64_t n,
                                const double* r, const double* costh, const double* phi,
                                double* den0, double* den1, void* stream);
 
+/* ---------------------------------------------------------------- multi-GPU coefficient sum -- */
+/* The one exchange step of the path: the sum of the partial coefficient blocks over the GPUs of a node
+ * (np.sum(np.array(a_coeffs), axis=0) over Pool workers, eof.py:1440, spheresl.py:471), as ONE kernel over
+ * NVLink peer memory: push to every rank's exchange buffer, flag, wait, fixed-order sum (bit-identical on all
+ * ranks).  One process per GPU: every rank creates its buffer, the 64-byte IPC handles are exchanged by the
+ * host side (torch.distributed), every rank opens the others' and builds a bfe_peer over the `world` pointers.
+ * Calls on one bfe_peer must be issued in the same order on every rank (like any collective); n <= ncoef_max. */
+typedef struct bfe_peer bfe_peer;
+int bfe_peer_buffer_create(int64_t ncoef_max, void** local_ptr, unsigned char* handle64);
+int bfe_peer_buffer_open(const unsigned char* handle64, void** peer_ptr);
+int bfe_peer_buffer_close(void* peer_ptr);
+int bfe_peer_buffer_destroy(void* local_ptr);
+int bfe_peer_create(int rank, int world, int64_t ncoef_max, void* const* bufs, bfe_peer** out);
+void bfe_peer_destroy(bfe_peer* p);
+/* data[0..n) (device, this rank's partial sums) := sum over ranks, in place, on `stream`. */
+int bfe_peer_allreduce(bfe_peer* p, double* data, int64_t n, void* stream);
+/* first sequence number whose wait gave up after 20 s (0: none). */
+int bfe_peer_error(bfe_peer* p, void* stream, unsigned long long* first_failed_seq);
+
 /* ---------------------------------------------------------------- building blocks ----------- */
 /* The per-point pieces the kernels above evaluate inline, callable with the meaning of the reference's own
  * helper functions.  Outputs are point-minor (trailing axis = the n points), like the reference's arrays. */

@@ -55,9 +55,35 @@ def main():
     cs, ss, _ = parallel.accumulate_series(E, None, snaps)
     ck, sk = E.accumulate(x * 1.02, y, z, m)
     assert relerr(cs[2].cpu().numpy(), ck.cpu().numpy()) < 1e-12
+    # the coefficient sum above went through the peer-memory kernel (bfe_peer_allreduce), not NCCL
+    assert parallel._PEER['obj'] is not None and not parallel._PEER['failed'], 'peer-memory allreduce not in use'
+    # the kernel against NCCL on random blocks; two instances on two streams, 300 back-to-back sums each
+    # (exercises the parity double-buffering of the exchange slots and two collectives in flight)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(100 + rank)
+    peers = [parallel.PeerAllreduce(1024) for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    blocks = [torch.randn(300, 702, dtype=torch.float64, device='cuda', generator=gen) for _ in range(2)]
+    want = [b.clone() for b in blocks]
+    for w in want:
+        dist.all_reduce(w)
+    torch.cuda.synchronize()
+    for it in range(300):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                peers[k].allreduce_(blocks[k][it])
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert peers[k].first_failed_sequence() == 0
+        err = float((blocks[k] - want[k]).abs().max() / want[k].abs().max())
+        assert err < 1e-14, err
+        ref = blocks[k].clone(); parallel.broadcast_(ref, src=0)
+        assert torch.equal(ref, blocks[k]), 'peer sums differ between ranks'
+    for pa in peers:
+        pa.close()
     dist.barrier()
     if rank == 0:
-        print('dist_check ok: world=%d coef err %.2e force err %.2e' % (world, e, ef_))
+        print('dist_check ok: world=%d coef err %.2e force err %.2e; peer-memory allreduce == NCCL to %.1e, identical on all ranks'
+              % (world, e, ef_, err))
     dist.destroy_process_group()
 
 
