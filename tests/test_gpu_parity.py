@@ -463,3 +463,48 @@ def test_config_c1_sl_1e5_accumulate_force(ops):
         assert relerr(f[i], ref[i]) < TOL, i
     c2 = H.accumulate(x, y, z, 2.0 * m)
     assert relerr(c2.cpu().numpy(), 2.0 * co) < TOL
+
+
+def test_peer_allreduce_protocol_single_gpu(ops):
+    """bfe_peer_allreduce (the coefficient sum over NVLink peer memory) with three "ranks" emulated on ONE GPU: three
+    exchange buffers in this process, one bfe_peer per rank over the same three pointers, the three kernels launched on
+    three streams (they must be co-resident: one CTA each).  200 back-to-back sums exercise the sequence / parity
+    protocol; the result must be the rank-order sum, bit-identical for every rank, with no timeout."""
+    import ctypes as C
+    import torch
+    from exptool_b200 import _lib
+    lib = _lib.load()
+    W, NMAX, N, ITERS = 3, 512, 252, 200
+    bufs = (C.c_void_p * W)()
+    for r in range(W):
+        p = C.c_void_p(); handle = C.create_string_buffer(64)
+        _lib.check(lib.bfe_peer_buffer_create(NMAX, C.byref(p), handle))
+        bufs[r] = p.value
+    peers = []
+    for r in range(W):
+        h = C.c_void_p()
+        _lib.check(lib.bfe_peer_create(r, W, NMAX, bufs, C.byref(h)))
+        peers.append(h)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(3)
+    data = torch.randn(W, ITERS, N, dtype=torch.float64, device='cuda', generator=gen)
+    want = torch.zeros(ITERS, N, dtype=torch.float64, device='cuda')
+    for r in range(W):                       # rank order, as the kernel sums
+        want += data[r]
+    streams = [torch.cuda.Stream() for _ in range(W)]
+    torch.cuda.synchronize()
+    for it in range(ITERS):
+        for r in range(W):
+            _lib.check(lib.bfe_peer_allreduce(peers[r], C.c_void_p(data[r, it].data_ptr()), N,
+                                              C.c_void_p(streams[r].cuda_stream)))
+    torch.cuda.synchronize()
+    for r in range(W):
+        v = C.c_uint64(1)
+        _lib.check(lib.bfe_peer_error(peers[r], C.c_void_p(0), C.byref(v)))
+        assert v.value == 0, 'rank %d timed out at sequence %d' % (r, v.value)
+        assert torch.equal(data[r], want), r
+    # argument checks
+    assert lib.bfe_peer_allreduce(peers[0], C.c_void_p(data[0, 0].data_ptr()), NMAX + 1, C.c_void_p(0)) != 0
+    for h in peers:
+        lib.bfe_peer_destroy(h)
+    for r in range(W):
+        _lib.check(lib.bfe_peer_buffer_destroy(C.c_void_p(bufs[r])))
