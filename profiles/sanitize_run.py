@@ -19,15 +19,41 @@ for lmax in (4, 6):
         c, s = E.accumulate(*d); ch = H.accumulate(*h)
         E.contract(c, s); H.contract(ch)
         E.force(*d[:3]); H.force(*h[:3])
-    for staged in (0, 1):
-        ops.set_option('staged_eval', staged)
+    pos0 = np.stack(d[:3])[:, :777]; vel0 = np.zeros_like(pos0); vel0[1] = 1.0
+    # per-point kernel variants: per-lane rows, warp-staged, per-lane blocks with 256-bit loads, FP32 tables
+    for staged, blk, f32 in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (1, 1, 1)):
+        ops.set_option('staged_eval', staged); ops.set_option('blk_eval', blk); ops.set_option('table_fp32', f32)
         ops.set_option('eof_force_mode', 1)
         E.force(*d[:3]); H.force(*h[:3])
         E.force_eval_points(np.abs(d[0]) + 1e-3, d[2], d[1]); H.force_eval_points(np.abs(h[0]) + 1e-3, np.clip(h[2], -1, 1), h[1])
         ops.field_force_cart(E, H, *d[:3], rotpos=0.2); ops.field_force_cyl(E, H, *h[:3], rotpos=0.2)
+        ops.leapfrog(E, H, pos0, vel0, 12, 3e-4, rotfreq=-5.0, traj_stride=3, apse=True, ap_max=2)
+        ops.leapfrog(E, H, pos0, vel0, 9, np.full(777, 2e-4), rotfreq=1.0, traj_stride=1)
+    ops.set_option('staged_eval', 1); ops.set_option('blk_eval', 1); ops.set_option('table_fp32', 0); ops.set_option('eof_force_mode', 0)
     E.prepare(*d); E.accumulate_prepared(); E.force_prepared()
-    pos0 = np.stack(d[:3])[:, :777]; vel0 = np.zeros_like(pos0); vel0[1] = 1.0
-    ops.leapfrog(E, H, pos0, vel0, 12, 3e-4, rotfreq=-5.0, traj_stride=3, apse=True, ap_max=2)
-    ops.leapfrog(E, H, pos0, vel0, 9, np.full(777, 2e-4), rotfreq=1.0, traj_stride=1)
+    # density outputs, building blocks
+    H.contract_density(ch); H.density(*h[:3]); H.density_eval_points(np.abs(h[0]) + 1e-3, np.clip(h[2], -1, 1), h[1])
+    H.radial_matrices(np.abs(h[0]) + 1e-6); ops.legendre_tables(lmax, np.clip(h[2], -1, 1))
+    E.get_pot(np.abs(d[0]) + 1e-3, d[2])
+    ops.eof_return_bins(np.abs(d[0]) + 1e-3, d[2], g['XMIN'], g['dX'], g['YMIN'], g['dY'], g['numx'], g['numy'], g['ascale'], g['hscale'], g['cmap'])
+# the peer-memory sum with two emulated ranks on this GPU
+import ctypes as C
+from exptool_b200 import _lib
+lib = _lib.load()
+bufs = (C.c_void_p * 2)()
+for r in range(2):
+    pp_ = C.c_void_p(); hd = C.create_string_buffer(64)
+    _lib.check(lib.bfe_peer_buffer_create(300, C.byref(pp_), hd)); bufs[r] = pp_.value
+prs = []
+for r in range(2):
+    hh = C.c_void_p(); _lib.check(lib.bfe_peer_create(r, 2, 300, bufs, C.byref(hh))); prs.append(hh)
+dat = torch.randn(2, 8, 252, dtype=torch.float64, device='cuda')
+sts = [torch.cuda.Stream() for _ in range(2)]
+torch.cuda.synchronize()
+for it in range(8):
+    for r in range(2):
+        _lib.check(lib.bfe_peer_allreduce(prs[r], C.c_void_p(dat[r, it].data_ptr()), 252, C.c_void_p(sts[r].cuda_stream)))
+torch.cuda.synchronize()
+assert torch.equal(dat[0], dat[1])
 torch.cuda.synchronize()
 print('sanitize_run done')
