@@ -1,22 +1,24 @@
 """
 particle.py -- the particle container types the hot path accepts
 (exptool/io/particle.py:142-157) and the `Input` front end of the PSP reader
-(exptool/io/particle.py:16-112).  The SPL (split-file) reader is out of scope.
+(exptool/io/particle.py:16-112): "OUT." files go to psp_io, "SPL." split files to spl_io.
 """
 import numpy as np
 
-from . import psp_io
+from . import psp_io, spl_io
 
 
 class Input():
-    """particle.Input (particle.py:16-112): PSP 'OUT.' snapshots -> .header, .time, .filename, .comp and either
+    """particle.Input (particle.py:16-112): PSP 'OUT.' and split 'SPL.' snapshots -> .header, .time, .filename, .comp and either
     `.data` (dict) or, with legacy=True, the .xpos/.ypos/... attributes."""
 
     def __init__(self, filename, comp=None, legacy=False, verbose=0):
-        if 'SPL.' in filename:
-            raise ValueError('File type not supported for file "{}" (SPL split files are outside the path)'.format(filename))
-        self.style = 'OUT'
-        I = psp_io.Input(filename, comp=comp, verbose=verbose)
+        if 'SPL.' in filename:                     # particle.py:68-77
+            self.style = 'SPL'
+            I = spl_io.Input(filename, comp=comp, verbose=verbose)
+        else:
+            self.style = 'OUT'
+            I = psp_io.Input(filename, comp=comp, verbose=verbose)
         self.header = I.header
         self.filename = I.filename
         self.time = I.time
