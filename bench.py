@@ -426,7 +426,17 @@ def run_gpu(args):
     t_accpass = (kms['eof_cell_hist_kernel'] + kms['eof_cell_scatter_kernel'] + kms['eof_segsum_kernel'] +
                  kms['eof_node_contract_kernel'])
     t_forcepass = sum(v for k, v in kms.items() if k.startswith('eof_force_'))
-    roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+    # The executed FP64 work of the dominant kernel next to its HBM figure: per sorted record
+    # 6 DMMA m8n8k4 per 8 records = 384 flop on the tensor pipe + ~57 flop per lane x 4 lanes = 228 flop of vector
+    # FP64 (trig powers, harmonic sums, transposed reduce); nominal B200 FP64 peak 148 SMs x 64 lanes x 2 x 1.965 GHz.
+    FP64_FLOP = {'eof_force_sorted_mma_kernel': 384 + 228}
+    fp64 = None
+    if dom in FP64_FLOP:
+        tf = FP64_FLOP[dom] * N_PART / (kms[dom] * 1e-3) / 1e12
+        fp64 = {'flop_per_particle': FP64_FLOP[dom], 'achieved_tflops': tf, 'peak_tflops': 37.2,
+                'peak_source': 'nominal: 148 SMs x 64 FP64 lanes x 2 x 1.965 GHz', 'frac': tf / 37.2,
+                'ncu': 'FP64 pipe 23 % + DMMA pipe 28 % active, issue slots 52 % (profiles/r01_ncu_full_step_kernels_v2.csv)'}
+    roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'fp64': fp64,
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg[dom],
                 'kernel_ms': kms,

@@ -508,3 +508,54 @@ def test_peer_allreduce_protocol_single_gpu(ops):
         lib.bfe_peer_destroy(h)
     for r in range(W):
         _lib.check(lib.bfe_peer_buffer_destroy(C.c_void_p(bufs[r])))
+
+
+def test_degenerate_sizes_every_entry_point(ops):
+    """Empty, single and ragged (n = 33: one warp + 1) inputs through every evaluation entry point, in each per-point
+    kernel variant: shapes are kept, nothing is written out of bounds, and n = 1 / n = 33 equal the same points taken
+    from a larger call (the kernels have no dependence on the launch size)."""
+    import torch
+    meta = dict(eof_params=dict(mmax=4, numx=24, numy=16, nmax=8, norder=5), sl_params=dict(lmax=4, nmax=6, numr=200),
+                kind='smooth', seed=3)
+    pe, T, g = eof_tables(meta)
+    ps, ev, ef, xi, p0, d0 = sl_tables(meta, seed_offset=1)
+    E, H = make_eof(ops, T, g), make_sl(ops, ps, ev, ef, xi, p0, d0)
+    x, y, z, m = S.exponential_disc(200, 5)
+    c, s = E.accumulate(x, y, z, m)
+    ch = H.accumulate(x, y, z, m)
+    E.contract(c, s); H.contract(ch); H.contract_density(ch)
+    r = np.sqrt(x * x + y * y) + 1e-6
+    cth = np.clip(z / np.sqrt(r * r + z * z), -1, 1)
+    phi = np.arctan2(y, x)
+    try:
+        for staged, blk, f32 in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)):
+            ops.set_option('staged_eval', staged); ops.set_option('blk_eval', blk); ops.set_option('table_fp32', f32)
+            ops.set_option('eof_force_mode', 1)
+            full = dict(ef=E.force(x, y, z), ep=E.force_eval_points(r, z, phi), sf=H.force(x, y, z),
+                        sp=H.force_eval_points(r, cth, phi, trig_index_l=True),
+                        fc=ops.field_force_cart(E, H, x, y, z, rotpos=0.4), fy=ops.field_force_cyl(E, H, x, y, z, rotpos=0.4),
+                        dn=H.density(x, y, z), dp=H.density_eval_points(r, cth, phi))
+            for n in (0, 1, 33):
+                sl = slice(0, n)
+                got = dict(ef=E.force(x[sl], y[sl], z[sl]), ep=E.force_eval_points(r[sl], z[sl], phi[sl]),
+                           sf=H.force(x[sl], y[sl], z[sl]), sp=H.force_eval_points(r[sl], cth[sl], phi[sl], trig_index_l=True),
+                           fc=ops.field_force_cart(E, H, x[sl], y[sl], z[sl], rotpos=0.4),
+                           fy=ops.field_force_cyl(E, H, x[sl], y[sl], z[sl], rotpos=0.4),
+                           dn=H.density(x[sl], y[sl], z[sl]), dp=H.density_eval_points(r[sl], cth[sl], phi[sl]))
+                for k in full:
+                    assert got[k].shape == (full[k].shape[0], n), (k, n)
+                    assert torch.equal(got[k], full[k][:, :n]), (k, n, staged, blk, f32)
+            st, tr, ns = ops.leapfrog(E, H, np.stack([x, y, z])[:, :0], np.zeros((3, 0)), 5, 1e-3)
+            assert st.shape == (6, 0)
+            st1, _, _ = ops.leapfrog(E, H, np.stack([x, y, z])[:, :1], np.zeros((3, 1)), 5, 1e-3)
+            st33, _, _ = ops.leapfrog(E, H, np.stack([x, y, z])[:, :33], np.zeros((3, 33)), 5, 1e-3)
+            assert torch.equal(st1[:, 0], st33[:, 0])
+    finally:
+        ops.set_option('staged_eval', 1); ops.set_option('blk_eval', 1); ops.set_option('table_fp32', 0)
+        ops.set_option('eof_force_mode', 0)
+    # building blocks on empty input
+    Vc, Vs = E.get_pot(r[:0], z[:0])
+    assert Vc.shape == (g['mmax'] + 1, g['norder'], 0)
+    assert all(o.shape[-1] == 0 for o in H.radial_matrices(r[:0]))
+    P, dP = ops.legendre_tables(4, cth[:0])
+    assert P.shape == (5, 5, 0)
