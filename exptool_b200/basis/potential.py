@@ -26,7 +26,10 @@ class Fields():
     '''
 
     def __init__(self, infile, eof_file, sph_file, model_file, nhalo=1000000, transform=False, no_odd=False,
-                 centering=False, mutual_center=False, verbose=1):
+                 centering=False, mutual_center=False, verbose=1, table_fp32=False):
+        # table_fp32 (extension; BASELINE north_star's "<= 1e-5 where FP32 table interpolation is used"): hold the
+        # contracted tables of return_forces_* / orbit integration as float -- ~1.5x faster, forces ~6e-8 from FP64
+        self.table_fp32 = bool(table_fp32)
         self.filename = infile
         self.eof_file = eof_file
         self.sph_file = sph_file
@@ -173,13 +176,18 @@ class Fields():
             self._contract_key = key
         return self._E, self._H
 
+    def precision(self):
+        """context manager for this instance's table precision around device calls (ops.table_precision)"""
+        return ops.table_precision(getattr(self, 'table_fp32', False))
+
     # -- forces ---------------------------------------------------------------
     def _eval(self, fn, xval, yval, zval, rotpos):
         scalar = np.ndim(xval) == 0
         E, H = self.device_handles()
-        out = ops.to_host(fn(E, H, np.atleast_1d(np.asarray(xval, dtype=np.float64)),
-                             np.atleast_1d(np.asarray(yval, dtype=np.float64)),
-                             np.atleast_1d(np.asarray(zval, dtype=np.float64)), rotpos=float(rotpos)))
+        with self.precision():
+            out = ops.to_host(fn(E, H, np.atleast_1d(np.asarray(xval, dtype=np.float64)),
+                                 np.atleast_1d(np.asarray(yval, dtype=np.float64)),
+                                 np.atleast_1d(np.asarray(zval, dtype=np.float64)), rotpos=float(rotpos)))
         if scalar:
             return tuple(np.float64(v[0]) for v in out)
         return tuple(out)
@@ -284,13 +292,13 @@ def restore_field(filename=''):
     return F
 
 
-def make_fields(eof_file, sph_file, model_file, cos, sin, expcoef, halofac=1.0, verbose=0):
+def make_fields(eof_file, sph_file, model_file, cos, sin, expcoef, halofac=1.0, verbose=0, table_fp32=False):
     """
     Build a Fields object from files and an existing coefficient set (what the
     reference does by hand after restore_*_coefficients: set .EOF/.SL/.halofac,
     then prep_tables).
     """
-    F = Fields('memory', eof_file, sph_file, model_file, verbose=verbose)
+    F = Fields('memory', eof_file, sph_file, model_file, verbose=verbose, table_fp32=table_fp32)
     F.EOF = eof.EOF_Object()
     F.EOF.eof_file = eof_file
     F.EOF.cos = np.asarray(cos, dtype=np.float64)

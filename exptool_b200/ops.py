@@ -56,6 +56,23 @@ def set_option(name, value):
     _lib.check(_lib.load().bfe_set_option(name.encode(), int(value)))
 
 
+class table_precision(object):
+    """Context manager: option 'table_fp32' on for the enclosed per-point field calls, off again afterwards."""
+
+    def __init__(self, fp32):
+        self.fp32 = bool(fp32)
+
+    def __enter__(self):
+        if self.fp32:
+            set_option('table_fp32', 1)
+        return self
+
+    def __exit__(self, *exc):
+        if self.fp32:
+            set_option('table_fp32', 0)
+        return False
+
+
 def kernel_time_ms(name):
     """Duration of the latest launch of kernel `name` recorded while option 'time_kernels' was on (ms; < 0: none)."""
     return float(_lib.load().bfe_kernel_time_ms(name.encode()))

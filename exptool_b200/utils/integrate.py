@@ -47,6 +47,11 @@ def _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n):
     return FieldInstance.device_handles()
 
 
+def _precision(FieldInstance):
+    """the Fields instance's table precision (table_fp32) around a device call"""
+    return ops.table_precision(getattr(FieldInstance, 'table_fp32', False))
+
+
 def leapfrog_integrate(FieldInstance, nint, dt, initpos, initvel, rotfreq=0., no_odd=False,
                        halo_l=-1, halo_n=-1, disk_m=-1, disk_n=-1, verbose=0, force=False, ap_max=1000, apse=False):
     '''
@@ -57,8 +62,9 @@ def leapfrog_integrate(FieldInstance, nint, dt, initpos, initvel, rotfreq=0., no
     E, H = _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n)
     pos0 = np.asarray(initpos, dtype=np.float64).reshape(3, 1)
     vel0 = np.asarray(initvel, dtype=np.float64).reshape(3, 1)
-    state, traj, nsteps = ops.leapfrog(E, H, pos0, vel0, nint, dt, rotfreq=rotfreq, traj_stride=1,
-                                       apse=apse, ap_max=ap_max)
+    with _precision(FieldInstance):
+        state, traj, nsteps = ops.leapfrog(E, H, pos0, vel0, nint, dt, rotfreq=rotfreq, traj_stride=1,
+                                           apse=apse, ap_max=ap_max)
     step = int(nsteps.cpu().numpy()[0])
     traj = traj.cpu().numpy()[:step, :, 0]
     times = np.arange(0, nint, 1) * dt
@@ -93,8 +99,9 @@ def leapfrog_integrate_batch(FieldInstance, nint, dt, initpos, initvel, rotfreq=
     (no communication; outputs stay sharded).
     '''
     E, H = _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n)
-    state, traj, nsteps = ops.leapfrog(E, H, initpos, initvel, nint, dt, rotfreq=rotfreq, traj_stride=traj_stride,
-                                       apse=apse, ap_max=ap_max)
+    with _precision(FieldInstance):
+        state, traj, nsteps = ops.leapfrog(E, H, initpos, initvel, nint, dt, rotfreq=rotfreq, traj_stride=traj_stride,
+                                           apse=apse, ap_max=ap_max)
     if return_device:
         return dict(STATE=state, TRAJ=traj, NSTEPS=nsteps)
     s = state.cpu().numpy()
@@ -136,8 +143,9 @@ def _grid_orbits(F, pos0, vel0, nint, dt, rotfreq, no_odd, halo_l, disk_m, dyn_r
     """shared body of the grid drivers: per-orbit dt, one leapfrog launch, host-side bar-frame rotation"""
     E, H = _handles(F, no_odd, halo_l, -1, disk_m, -1)
     dts = np.maximum(compute_timestep(F, pos0, vel0, dyn_res=dyn_res), dt)       # integrate.py:871
-    state, traj, nsteps = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=rotfreq, traj_stride=1,
-                                       apse=False, ap_max=ap_max)
+    with _precision(F):
+        state, traj, nsteps = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=rotfreq, traj_stride=1,
+                                           apse=False, ap_max=ap_max)
     traj = ops.to_host(traj)                                   # (nint, 10, norb)
     times = np.arange(0, nint, 1)[:, None] * dts[None, :]       # (nint, norb)
     barpos = 2. * np.pi * rotfreq * times

@@ -358,3 +358,23 @@ def test_building_blocks_api(api):
     assert relerr(np.moveaxis(P, 2, 0), d['P2']) < 1e-14 and relerr(np.moveaxis(dP, 2, 0), d['dP']) < TOL
     P1 = spheresl.legendre_R(L, float(d['cth'][8]))
     assert P1.shape == (L + 1, L + 1) and relerr(P1, d['P'][8]) < 1e-14
+
+
+def test_fields_table_fp32_option(api):
+    """potential.Fields(table_fp32=True): the FP32-table mode through the reference-facing API; the option is scoped
+    to that instance's calls (a second, FP64 instance keeps full parity in between)."""
+    potential, integrate = api['potential'], api['integrate']
+    d, meta = load_golden('field_small')
+    with tempfile.TemporaryDirectory() as tmp:
+        ef = _eof_file(tmp, meta); sf, mf = _sl_files(tmp, meta, seed_offset=1)
+        Fs = [potential.make_fields(ef, sf, mf, d['cos'], d['sin'], d['coef'], halofac=meta['halofac'], table_fp32=fp32)
+              for fp32 in (True, False)]
+        F32, F64 = Fs
+        a = F32.return_forces_cart(d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+        b = F64.return_forces_cart(d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+        e32 = max(relerr(a[i], d['cart_full'][:, i]) for i in range(8))
+        e64 = max(relerr(b[i], d['cart_full'][:, i]) for i in range(8))
+        assert e64 < TOL and 1e-12 < e32 < 1e-5, (e32, e64)
+        o32 = integrate.leapfrog_integrate_batch(F32, 50, meta['dt'], d['pos0'], d['vel0'], rotfreq=meta['rotfreq'])
+        o64 = integrate.leapfrog_integrate_batch(F64, 50, meta['dt'], d['pos0'], d['vel0'], rotfreq=meta['rotfreq'])
+        assert 0 < relerr(o32['X'], o64['X']) < 1e-4
