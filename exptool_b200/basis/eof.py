@@ -6,8 +6,7 @@ reference; the arithmetic runs in libbfe.so on the current CUDA device
 (exptool_b200.ops -> include/bfe.h).  Table readers and coefficient-file I/O
 are host-side NumPy, as in the reference.
 
-Not mirrored (outside the path): wake grids, phase /
-pattern-speed post-processing, variance (VAR) jackknife sums, plotting.
+Not mirrored (outside the path): wake grids, plotting.
 """
 import time
 from collections import OrderedDict
@@ -194,14 +193,38 @@ def accumulate(ParticleInstance, potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUM
     '''
     eof.accumulate (eof.py:492-640) -> accum_cos, accum_sin, each (MMAX+1, NMAX) float64.
     `no_odd` is accepted and, as in the reference (mask computed at 545-548 but never
-    applied), has no effect.  VAR (jackknife sub-sampling with unseeded np.random,
-    554-574) is outside the path.
+    applied), has no effect.  VAR > 0 adds the jackknife partitions (554-574): the return is then
+    accum_cos, accum_sin, accum_cos2, accum_sin2 (see _accumulate_with_variance).
     '''
-    if VAR:
-        raise NotImplementedError('eof.accumulate: VAR sub-sampling is outside the B200 hot path')
     x, y, z, m = particle.particle_arrays(ParticleInstance)
     E = device_tables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP)
-    return E.accumulate_host(x, y, z, m)
+    if not VAR:
+        return E.accumulate_host(x, y, z, m)
+    return _accumulate_with_variance(E, x, y, z, m, int(VAR), MMAX, NMAX)
+
+
+def _accumulate_with_variance(E, x, y, z, m, nvar, MMAX, NMAX):
+    '''
+    The VAR branch of eof.accumulate (eof.py:554-574 / 617-637): besides the coefficients, `VAR` jackknife
+    partitions, each the coefficient sum over floor(sqrt(N)) particles drawn WITH replacement by
+    np.random.randint from NumPy's global generator -- the same calls in the same order as the reference, so a
+    caller who seeds np.random gets the reference's partitions.  Returns accum_cos, accum_sin,
+    accum_cos2 (VAR, M+1, N), accum_sin2 (VAR, M+1, N).
+    '''
+    xd, yd, zd, md = ops.dev(x), ops.dev(y), ops.dev(z), ops.dev(m)
+    c, s = E.accumulate(xd, yd, zd, md)
+    n = int(xd.numel())
+    cos2 = np.zeros([nvar, MMAX + 1, NMAX]); sin2 = np.zeros([nvar, MMAX + 1, NMAX])
+    parts = []
+    for T in range(nvar):
+        use = np.random.randint(n, size=int(np.floor(np.sqrt(n))))                  # eof.py:567
+        idx = ops.torch.from_numpy(use).to(xd.device)
+        parts.append(ops.torch.stack(E.accumulate(xd[idx], yd[idx], zd[idx], md[idx])))
+    allp = ops.to_host(ops.torch.stack(parts)) if parts else np.zeros((0, 2, MMAX + 1, NMAX))
+    for T in range(nvar):
+        cos2[T] = allp[T, 0]; sin2[T] = allp[T, 1]
+    cs = ops.to_host(ops.torch.stack([c, s]))
+    return cs[0], cs[1], cos2, sin2
 
 
 def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy,
@@ -214,7 +237,10 @@ def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, 
     (exptool_b200.parallel).  `nprocs` is accepted for call compatibility.
     '''
     if VAR:
-        raise NotImplementedError('eof.make_coefficients_multi: VAR is outside the B200 hot path')
+        # the reference sums per-worker tuples of unequal shapes here (np.array(a_coeffs), eof.py:1440), which NumPy
+        # >= 1.24 rejects; the partitions are drawn over the whole set instead, as in the single-process branch
+        return accumulate(ParticleInstance, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale,
+                          cmap, verbose=verbose, no_odd=no_odd, VAR=VAR)
     t1 = time.time()
     from .. import parallel
     x, y, z, m = particle.particle_arrays(ParticleInstance)
@@ -275,10 +301,11 @@ def compute_coefficients(PSPInput, eof_file, verbose=1, no_odd=False, nprocs_max
                                                       NUMX=numx, NUMY=numy, CMAP=cmap)
     EOF_Out.mmax = mmax
     EOF_Out.nmax = norder
-    a_cos, a_sin = make_coefficients_multi((x, y, z, m), 1, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy,
-                                           ascale, hscale, cmap, verbose=verbose, no_odd=no_odd, VAR=VAR)
-    EOF_Out.cos = a_cos
-    EOF_Out.sin = a_sin
+    res = make_coefficients_multi((x, y, z, m), 1, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy,
+                                  ascale, hscale, cmap, verbose=verbose, no_odd=no_odd, VAR=VAR)
+    EOF_Out.cos, EOF_Out.sin = res[0], res[1]
+    if VAR:                                           # eof.py:1254-1256
+        EOF_Out.cos2, EOF_Out.sin2 = res[2], res[3]
     return EOF_Out
 
 

@@ -104,8 +104,20 @@ def test_eof_api(api, name):
                                  potC, rfC, zfC, potS, rfS, zfS, **geo, **v)
             assert all(np.ndim(o) == 0 for o in one)
             assert max(abs(float(one[i]) - ref[3, i]) for i in range(ref.shape[1])) <= TOL * np.max(np.abs(ref))
-        with pytest.raises(NotImplementedError):
-            eof.accumulate(P, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap, VAR=3)
+        if name == 'eof_small_random_cmap1':
+            # VAR: jackknife partitions drawn with NumPy's global generator exactly as the reference draws them
+            v = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'eof_var.npz'))
+            vm = __import__('json').loads(str(v['meta']))
+            for cont, key in ((H, 'holder'), (P, 'data')):
+                np.random.seed(vm['seed'])
+                cv, sv, cv2, sv2 = eof.accumulate(cont, potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale,
+                                                  hscale, cmap, VAR=vm['nvar'])
+                assert cv2.shape == (vm['nvar'], mmax + 1, norder)
+                assert relerr(cv, v['cos']) < TOL and relerr(sv, v['sin']) < TOL
+                assert relerr(cv2, v['cos2_' + key]) < TOL and relerr(sv2, v['sin2_' + key]) < TOL
+            np.random.seed(vm['seed'])
+            EV = eof.compute_coefficients(P, f, verbose=0, VAR=vm['nvar'])
+            assert relerr(EV.cos2, v['cos2_data']) < TOL
 
 
 @pytest.mark.parametrize('name', ['sl_small_random_cmap1', 'sl_small_random_cmap0', 'sl_std_l4', 'sl_std_l6'])
