@@ -314,6 +314,7 @@ int g_bfe_eof_accumulate_mode = 0;
 int g_bfe_eof_force_mode = 0;
 int g_bfe_sort_min_particles = 32768;
 int g_bfe_sl_accumulate_mode = 0;
+int g_bfe_sl_deposit_mode = 0;
 int g_bfe_staged_eval = 1;
 int g_bfe_blk_eval = 1;
 int g_bfe_table_fp32 = 0;
@@ -358,6 +359,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
         return BFE_OK;
     }
     if (!strcmp(name, "sl_accumulate_mode")) { g_bfe_sl_accumulate_mode = value; return BFE_OK; }
+    if (!strcmp(name, "sl_deposit_mode")) { g_bfe_sl_deposit_mode = value; return BFE_OK; }
     if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
     return BFE_ERR_ARG;
 }

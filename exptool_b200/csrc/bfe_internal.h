@@ -95,6 +95,7 @@ extern int g_bfe_eof_accumulate_mode;
 extern int g_bfe_eof_force_mode;
 extern int g_bfe_sort_min_particles;
 extern int g_bfe_sl_accumulate_mode;
+extern int g_bfe_sl_deposit_mode;     // option "sl_deposit_mode": 0/1 shared-memory slab kernel (default), 2 register formulation
 
 bool bfe_sl_sorted_supported(const bfe_sl* h);
 int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double* y, const double* z,

@@ -370,6 +370,220 @@ sl_deposit_kernel(SlGeom g, const double* __restrict__ e_node, const double* __r
     }
 }
 
+// ---------------------------------------------------------------------------
+// deposit, register formulation (option sl_deposit_mode = 2; NOT the default: measured 349 -> 405 us per 4e6 particles
+// at lmax 4 and 574 -> 549 us at lmax 6 for the whole accumulate, profiles/sl_probe.py -- at 222-253 registers only 8
+// warps fit an SM and the serial Legendre recurrences leave the FP64 pipe at 18 %: ncu warps_active 10 %, stalls "wait"
+// 1.8 and long scoreboard 2.6 per issue).  ncu of the kernel above (4e6 particles, lmax 6): l1tex 63 %, FP64 pipe
+// 23 % -- it is bound by the shared-memory slab (49 stores per record, 4 loads per 4 FMAs in the sum phase), not
+// by arithmetic.  Here a LANE keeps the run sums of its own records in registers:
+//     d1[r] += (f_lm P_l^m trig)(p) * (W x1)(p),   d2[r] += ... * (W x2)(p)        (one FMA each, no memory traffic)
+// for the rows r of the azimuthal orders [MLO, MHI] of its warp -- lmax <= 4: one warp covers all 25 rows
+// (50 accumulators); lmax <= 6: the 49 rows are split over two kinds of warps (m = 0..2: 29 rows, m = 3..6: 20 rows),
+// each kind pulling every task from its own queue.  Runs are ~n/numr records long, so the sums leave the registers
+// rarely: when the radial interval changes (warp-uniform test; records are sorted) the 2 NR x 32 lane sums are
+// reduced through a shared-memory slab, contracted with the two node rows of the interval (read from L2, coalesced)
+// into the warp's coefficient partials (shared memory), and cleared.  A batch that straddles intervals is taken
+// interval by interval with the other lanes' weights zeroed.  No floating-point atomics.
+// ---------------------------------------------------------------------------
+template <int LCAP, int MLO, int MHI>
+struct SlLaneRows {
+    __host__ __device__ static constexpr int count() {
+        int c = 0;
+        for (int m = MLO; m <= MHI; ++m) c += (LCAP - m + 1) * (m ? 2 : 1);
+        return c;
+    }
+};
+
+template <int LCAP, int MLO, int MHI, int NR>
+__device__ __forceinline__ void sl_lane_accumulate(const SlGeom& g, const double* __restrict__ fac, int no_odd,
+                                                   double wx1, double wx2, double x, double c1, double s1,
+                                                   double (&d1)[NR], double (&d2)[NR]) {
+    const double somx2 = sqrt((1.0 - x) * (1.0 + x));
+    double pmm = 1.0, fact = 1.0, cm = 1.0, sm = 0.0;
+    int r = 0;
+#pragma unroll
+    for (int m = 0; m <= MHI; ++m) {
+        if (m > 0) {
+            pmm = pmm * (-fact * somx2);
+            fact += 2.0;
+            const double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+        if (m >= MLO) {
+            double pl2 = 0.0, pl1 = pmm;
+#pragma unroll
+            for (int l = m; l <= LCAP; ++l) {
+                double fP = 0.0;
+                if (l <= g.lmax) {                                        // warp-uniform
+                    double P;
+                    if (l == m) P = pmm;
+                    else {
+                        if (l == m + 1) P = x * (2.0 * m + 1.0) * pl1;
+                        else P = (x * (double)(2 * l - 1) * pl1 - (double)(l + m - 1) * pl2) * (1.0 / (double)(l - m));
+                        pl2 = pl1; pl1 = P;
+                    }
+                    const bool skip = no_odd && (l & 1);                  // spheresl.py:630-632
+                    fP = skip ? 0.0 : __ldg(fac + l * (g.lmax + 1) + m) * P;
+                }
+                if (m == 0) {
+                    d1[r] = fma(fP, wx1, d1[r]); d2[r] = fma(fP, wx2, d2[r]); ++r;
+                } else {
+                    const double a = fP * cm, b = fP * sm;
+                    d1[r] = fma(a, wx1, d1[r]); d2[r] = fma(a, wx2, d2[r]); ++r;
+                    d1[r] = fma(b, wx1, d1[r]); d2[r] = fma(b, wx2, d2[r]); ++r;
+                }
+            }
+        }
+    }
+}
+
+// body of one warp of the register-formulation kernel for the azimuthal orders [MLO, MHI]
+template <int LCAP, int MLO, int MHI>
+__device__ __forceinline__ void sl_lane_warp(const SlGeom& g, const double* __restrict__ e_node,
+                                             const double* __restrict__ fac, int no_odd, int64_t n,
+                                             const SlRec* __restrict__ rec, unsigned int* __restrict__ queue,
+                                             double* __restrict__ slab, double* __restrict__ Dk,
+                                             double* __restrict__ acc_s, const int* __restrict__ s_idx, int lane) {
+    constexpr int NR = SlLaneRows<LCAP, MLO, MHI>::count();
+    constexpr int TASK = 1024, RS = 33;
+    const int ncoef = g.nrow * g.nmax, ln = g.ln;
+    double d1[NR], d2[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { d1[r] = 0.0; d2[r] = 0.0; }
+    int cur = -1;
+
+    auto flush = [&]() {
+        // lane sums -> slab[row][lane]; lane q then sums rows q, q+32, ... over the 32 columns
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { slab[r * RS + lane] = d1[r]; slab[(NR + r) * RS + lane] = d2[r]; d1[r] = 0.0; d2[r] = 0.0; }
+        __syncwarp();
+        for (int q = lane; q < 2 * NR; q += 32) {
+            const double* rowp = slab + q * RS;
+            double s0 = 0.0, s1_ = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) { s0 += rowp[c]; s1_ += rowp[c + 1]; }
+            // row index r of this warp's list -> table row k (same enumeration as sl_lane_accumulate)
+            int rr = (q < NR) ? q : q - NR, k = 0, cnt = 0;
+            for (int m = MLO; m <= MHI; ++m)
+                for (int l = m; l <= LCAP; ++l) {
+                    const int nrow_lm = m ? 2 : 1;
+                    if (rr >= cnt && rr < cnt + nrow_lm) k = (m == 0) ? l * l : l * l + 2 * m - 1 + (rr - cnt);
+                    cnt += nrow_lm;
+                }
+            Dk[(q < NR ? 0 : 64) + k] = s0 + s1_;
+        }
+        __syncwarp();
+        const double* e0 = e_node + (size_t)cur * ln;
+        for (int j = lane; j < ncoef; j += 32) {
+            const int pk = s_idx[j];
+            const int mm = (pk >> 26) & 31;
+            if (mm >= MLO && mm <= MHI) {
+                const int k = (pk >> 16) & 1023, eo = pk & 0xffff;
+                acc_s[j] += Dk[k] * __ldg(e0 + eo) + Dk[64 + k] * __ldg(e0 + ln + eo);
+            }
+        }
+        __syncwarp();
+    };
+
+    const int64_t ntasks = (n + TASK - 1) / TASK;
+    for (;;) {
+        int64_t task = 0;
+        if (lane == 0) task = (int64_t)atomicAdd(queue, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntasks) break;
+        task = ntasks - 1 - task;                      // sparse outer intervals (short runs, many flushes) first
+        const int64_t t0 = task * TASK;
+        const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
+        // records two batches ahead are kept in flight (a batch is ~600 cycles of arithmetic, less than a DRAM round trip)
+        double2 ra, rb, rc, rd, na, nb, nc, nd;
+        {
+            const bool on = lane < tcnt;
+            const double2* src = reinterpret_cast<const double2*>(rec + t0 + (on ? lane : 0));
+            ra = __ldg(src); rb = __ldg(src + 1); rc = __ldg(src + 2); rd = __ldg(src + 3);
+            const bool on1 = (32 + lane) < tcnt;
+            const double2* src1 = reinterpret_cast<const double2*>(rec + t0 + (on1 ? 32 + lane : 0));
+            na = __ldg(src1); nb = __ldg(src1 + 1); nc = __ldg(src1 + 2); nd = __ldg(src1 + 3);
+        }
+        for (int b0 = 0; b0 < tcnt; b0 += 32) {
+            const bool on = (b0 + lane) < tcnt;
+            const double x1 = ra.x, x2 = ra.y, W = on ? rb.x : 0.0, x = rb.y, c1 = rc.x, s1 = rc.y;
+            const int mybin = on ? (int)((unsigned long long)__double_as_longlong(rd.y) >> 32) : -1;
+            ra = na; rb = nb; rc = nc; rd = nd;
+            if (b0 + 64 < tcnt) {
+                const bool on2 = (b0 + 64 + lane) < tcnt;
+                const double2* src = reinterpret_cast<const double2*>(rec + t0 + b0 + 64 + (on2 ? lane : 0));
+                na = __ldg(src); nb = __ldg(src + 1); nc = __ldg(src + 2); nd = __ldg(src + 3);
+            }
+            if (__all_sync(0xffffffffu, !on || mybin == cur)) {
+                sl_lane_accumulate<LCAP, MLO, MHI, NR>(g, fac, no_odd, W * x1, W * x2, x, c1, s1, d1, d2);
+            } else {
+                unsigned int todo = __ballot_sync(0xffffffffu, on);
+                while (todo) {
+                    const int b = __shfl_sync(0xffffffffu, mybin, __ffs(todo) - 1);
+                    if (b != cur) { if (cur >= 0) flush(); cur = b; }
+                    const bool mine = on && (mybin == b);
+                    const double Wm = mine ? W : 0.0;
+                    sl_lane_accumulate<LCAP, MLO, MHI, NR>(g, fac, no_odd, Wm * x1, Wm * x2, x, c1, s1, d1, d2);
+                    todo &= ~__ballot_sync(0xffffffffu, mine);
+                }
+            }
+        }
+    }
+    if (cur >= 0) flush();
+}
+
+template <int LCAP, int NSPLIT>
+__global__ void __launch_bounds__(128, 2)
+sl_deposit_lane_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ fac, int no_odd,
+                       int64_t n, const SlRec* __restrict__ rec, double* __restrict__ partial,
+                       unsigned int* __restrict__ counter) {
+    constexpr int NW = 4, RS = 33;
+    constexpr int MSPLIT = 2;                                        // lmax 6: warps of kind 0 take m = 0..2, kind 1 m = 3..6
+    constexpr int NR0 = (NSPLIT == 1) ? SlLaneRows<LCAP, 0, LCAP>::count() : SlLaneRows<LCAP, 0, MSPLIT>::count();
+    constexpr int SLAB = 2 * NR0 * RS;                               // kind 0 has the larger row set
+    extern __shared__ __align__(16) unsigned char s_raw2[];
+    double* s_slab = reinterpret_cast<double*>(s_raw2);              // [NW][SLAB]
+    double* s_Dk = s_slab + NW * SLAB;                               // [NW][128]
+    double* s_acc = s_Dk + NW * 128;                                 // [NW][ncoef_pad]
+    const int ncoef = g.nrow * g.nmax, ncoef_pad = (ncoef + 31) & ~31;
+    int* s_idx = reinterpret_cast<int*>(s_acc + NW * ncoef_pad);     // [ncoef_pad]: (m << 26) | (k << 16) | (l*nmax + n)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < ncoef_pad; j += blockDim.x) {
+        int v = 0;
+        if (j < ncoef) {
+            const int k = j / g.nmax, nn = j - k * g.nmax;
+            int l = (int)sqrtf((float)k);
+            if ((l + 1) * (l + 1) <= k) ++l;
+            if (l * l > k) --l;
+            const int m = (k - l * l + 1) / 2;
+            v = (m << 26) | (k << 16) | (l * g.nmax + nn);
+        }
+        s_idx[j] = v;
+    }
+    for (int j = tid; j < NW * ncoef_pad; j += blockDim.x) s_acc[j] = 0.0;
+    for (int j = tid; j < NW * 128; j += blockDim.x) s_Dk[j] = 0.0;
+    __syncthreads();
+    double* slab = s_slab + warp * SLAB;
+    double* Dk = s_Dk + warp * 128;
+    double* acc_s = s_acc + warp * ncoef_pad;
+    if (NSPLIT == 1) {
+        sl_lane_warp<LCAP, 0, LCAP>(g, e_node, fac, no_odd, n, rec, counter + 1, slab, Dk, acc_s, s_idx, lane);
+    } else if ((warp & 1) == 0) {
+        sl_lane_warp<LCAP, 0, MSPLIT>(g, e_node, fac, no_odd, n, rec, counter + 1, slab, Dk, acc_s, s_idx, lane);
+    } else {
+        sl_lane_warp<LCAP, MSPLIT + 1, LCAP>(g, e_node, fac, no_odd, n, rec, counter + 2, slab, Dk, acc_s, s_idx, lane);
+    }
+    __syncthreads();
+    for (int j = tid; j < ncoef; j += 128) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += s_acc[w * ncoef_pad + j];
+        partial[(size_t)blockIdx.x * ncoef + j] = v;
+    }
+}
+
 // out[c] = sum_b partial[b][c]; the last launch of the pipeline also resets the task counter
 __global__ void __launch_bounds__(256)
 sl_sorted_reduce_kernel(const double* __restrict__ partial, int nrows, int ncol, double* __restrict__ out,
@@ -393,7 +607,7 @@ sl_sorted_reduce_kernel(const double* __restrict__ partial, int nrows, int ncol,
         for (int k = 0; k < 32; ++k) s += s_p[k][threadIdx.x];
         out[blockIdx.x * 8 + threadIdx.x] = s;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) counter[1] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { counter[1] = 0u; counter[2] = 0u; }
 }
 
 // ---------------------------------------------------------------------------
@@ -449,6 +663,30 @@ static int sl_deposit_launch(bfe_sl* h, int64_t n, const SlRec* rec, int no_odd,
     return BFE_OK;
 }
 
+template <int LCAP, int NSPLIT>
+static int sl_deposit_lane_launch(bfe_sl* h, int64_t n, const SlRec* rec, int no_odd, double* expcoef, cudaStream_t stream) {
+    constexpr int NW = 4, RS = 33;
+    constexpr int NR0 = (NSPLIT == 1) ? SlLaneRows<LCAP, 0, LCAP>::count() : SlLaneRows<LCAP, 0, 2>::count();
+    const int ncoef = h->g.nrow * h->g.nmax, ncoef_pad = (ncoef + 31) & ~31;
+    const size_t smem = ((size_t)NW * 2 * NR0 * RS + (size_t)NW * 128 + (size_t)NW * ncoef_pad) * sizeof(double) +
+                        (size_t)ncoef_pad * sizeof(int) + 64;
+    auto kern = sl_deposit_lane_kernel<LCAP, NSPLIT>;
+    static size_t attr_smem = 0;                   // one per template instance
+    if (smem > attr_smem) {
+        BFE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    int64_t nblk = (n + 1024 * NW - 1) / (1024 * NW) * NSPLIT;
+    int grid = (int)(nblk < (int64_t)h->num_sms * 2 ? nblk : (int64_t)h->num_sms * 2);
+    if (grid < 1) grid = 1;
+    if (grid > h->max_ctas) grid = h->max_ctas;
+    kern<<<grid, 128, smem, stream>>>(h->g, h->e_node, h->fac, no_odd, n, rec, h->partial, h->counter);
+    BFE_LAUNCH_CHECK("sl_deposit_lane_kernel");
+    sl_sorted_reduce_kernel<<<(ncoef + 7) / 8, 256, 0, stream>>>(h->partial, grid, ncoef, expcoef, h->counter);
+    BFE_LAUNCH_CHECK("sl_sorted_reduce_kernel");
+    return BFE_OK;
+}
+
 bool bfe_sl_sorted_supported(const bfe_sl* h) {
     const int ncoef = h->g.nrow * h->g.nmax;
     if (h->g.lmax <= 4 && ncoef <= 32 * 15) return true;
@@ -482,6 +720,10 @@ int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double
     if (g2 < 1) g2 = 1;
     sl_bin_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, h->xi, h->p0, n, x, y, z, mass, ws.bin_start, ws.cursor, ws.rec);
     BFE_LAUNCH_CHECK("sl_bin_scatter_kernel");
+    if (g_bfe_sl_deposit_mode == 2) {             // register formulation (option sl_deposit_mode = 2); default: slab kernel
+        if (h->g.lmax <= 4) return sl_deposit_lane_launch<4, 1>(h, n, ws.rec, no_odd, expcoef, stream);
+        return sl_deposit_lane_launch<6, 2>(h, n, ws.rec, no_odd, expcoef, stream);
+    }
     if (h->g.lmax <= 4 && h->g.nrow * h->g.nmax <= 32 * 15)
         return sl_deposit_launch<4, 15>(h, n, ws.rec, no_odd, expcoef, stream);
     return sl_deposit_launch<6, 28>(h, n, ws.rec, no_odd, expcoef, stream);

@@ -559,3 +559,21 @@ def test_degenerate_sizes_every_entry_point(ops):
     assert all(o.shape[-1] == 0 for o in H.radial_matrices(r[:0]))
     P, dP = ops.legendre_tables(4, cth[:0])
     assert P.shape == (5, 5, 0)
+
+
+@pytest.mark.parametrize('lmax', [4, 6])
+def test_sl_register_deposit_option(ops, lmax):
+    """option sl_deposit_mode = 2 (lane-register run sums) gives the slab kernel's coefficients, incl. no_odd"""
+    p, ev, ef, xi, p0, d0 = sl_tables(dict(sl_params=dict(lmax=lmax), kind='smooth', seed=0))
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    x, y, z, m = S.hernquist_halo(70001, 9)
+    ops.set_option('sl_accumulate_mode', 2)
+    try:
+        for no_odd in (False, True):
+            ops.set_option('sl_deposit_mode', 1)
+            a = H.accumulate(x, y, z, m, no_odd=no_odd).cpu().numpy()
+            ops.set_option('sl_deposit_mode', 2)
+            b = H.accumulate(x, y, z, m, no_odd=no_odd).cpu().numpy()
+            assert relerr(b, a) < 1e-13, (lmax, no_odd)
+    finally:
+        ops.set_option('sl_accumulate_mode', 0); ops.set_option('sl_deposit_mode', 0)
