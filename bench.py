@@ -248,6 +248,7 @@ def run_gpu(args):
     # on ONE stream; the second stream fills the launch gaps, tails and latency-bound phases of the first
     # (profiles/dual_stream.py: 1 stream 174 us/step, 2 streams 138, 3 streams 133).
     NSTREAMS = max(1, args.streams)
+    ops.set_option('grid_pct', args.grid_pct)
     Es = [E] + [E.clone() for _ in range(NSTREAMS - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
     coefbufs = [torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev) for _ in range(NSTREAMS)]
@@ -535,6 +536,7 @@ def main():
     ap.add_argument('--streams', type=int, default=3, help='independent particle sets in flight (CUDA streams)')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
                     help='N>1: per-step coefficient sum by the peer-memory kernel (default) or NCCL')
+    ap.add_argument('--grid-pct', type=int, default=100, help='share of the SMs the persistent grids of the step are sized for')
     ap.add_argument('--pg-per-stream', type=int, default=0, help='N>1: one NCCL communicator per stream (1) or shared (0)')
     args = ap.parse_args()
     if args.allreduce == 'nccl':

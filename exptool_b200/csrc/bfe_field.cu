@@ -321,6 +321,7 @@ int g_bfe_table_fp32 = 0;
 int g_bfe_force_mma = 1;
 static int g_bfe_time_kernels = 0;
 int g_bfe_pdl = 1;
+int g_bfe_grid_pct = 100;
 int g_bfe_contract_deep = 0;
 int g_bfe_l2_persist = 0;
 size_t g_bfe_l2_window_max = 0;
@@ -351,6 +352,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "table_fp32")) { g_bfe_table_fp32 = value; return BFE_OK; }
     if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
     if (!strcmp(name, "pdl")) { g_bfe_pdl = value; return BFE_OK; }
+    if (!strcmp(name, "grid_pct")) { if (value < 1 || value > 100) return BFE_ERR_ARG; g_bfe_grid_pct = value; return BFE_OK; }
     if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }
     if (!strcmp(name, "host_chunk")) { g_bfe_host_chunk = value; return BFE_OK; }
     if (!strcmp(name, "l2_persist")) {

@@ -131,6 +131,7 @@ void bfe_host_pipe_destroy(void* pipe);
 extern int g_bfe_host_chunk;                               // option "host_chunk"
 extern int g_bfe_contract_deep;                            // option "contract_deep": 9 (1) or 6 (0) table loads in flight
 extern int g_bfe_pdl;
+extern int g_bfe_grid_pct;                                 // option "grid_pct" (default 100)
 extern int g_bfe_l2_persist;
 extern size_t g_bfe_l2_window_max;                         // cudaDeviceProp::accessPolicyMaxWindowSize
 template <typename... KArgs, typename... Args>

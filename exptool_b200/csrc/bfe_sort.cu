@@ -763,6 +763,9 @@ eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __
 // host side
 // ---------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// option "grid_pct": the persistent grids of the sorted step sized for this share of the SMs, so that the kernels of
+// another stream fit beside them (several particle sets in flight)
+static inline int bfe_eff_sms(const bfe_eof* h) { int v = h->num_sms * g_bfe_grid_pct / 100; return v < 1 ? 1 : v; }
 
 struct SortWs {
     int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_orig; double2* tmp; int* inv; double* seg;
@@ -808,7 +811,7 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     if (rc != BFE_OK) return rc;
     const int ncell = h->g.numx * h->g.numy;
     int grid = (int)((n + 2047) / 2048);
-    if (grid > h->num_sms) grid = h->num_sms;        // one 1024-thread CTA per SM: the per-CTA merge is paid once per SM
+    if (grid > bfe_eff_sms(h)) grid = bfe_eff_sms(h);        // one 1024-thread CTA per SM: the per-CTA merge is paid once per SM
     if (grid < 1) grid = 1;
     {
         const int per = (ncell + 1023) / 1024;
@@ -823,7 +826,7 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     }
     BFE_LAUNCH_CHECK("eof_cell_hist_kernel");
     int g2 = (int)((n + 511) / 512);
-    if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
+    if (g2 > bfe_eff_sms(h) * 8) g2 = bfe_eff_sms(h) * 8;
     if (g2 < 1) g2 = 1;
     const int kt2 = bfe_kt_begin("eof_cell_scatter_kernel", stream);
     BFE_CUDA(bfe_launch(eof_cell_scatter_kernel, dim3(g2), dim3(256), 0, stream, nullptr, 0, h->g, n, x, y, z, mass,
@@ -847,7 +850,7 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
     const int ncell = h->g.numx * h->g.numy;
     {
         int64_t nblk = (n + SegSum::TASK * SegSum::NW - 1) / (SegSum::TASK * SegSum::NW);
-        int grid = (int)(nblk < (int64_t)h->num_sms * 4 ? nblk : (int64_t)h->num_sms * 4);
+        int grid = (int)(nblk < (int64_t)bfe_eff_sms(h) * 4 ? nblk : (int64_t)bfe_eff_sms(h) * 4);
         if (grid < 1) grid = 1;
         const int kt = bfe_kt_begin("eof_segsum_kernel", stream);
         BFE_CUDA(bfe_launch(eof_segsum_kernel, dim3(grid), dim3(256), 0, stream, nullptr, 0, n, ws.rec, ws.seg, h->counter));
@@ -856,7 +859,7 @@ extern "C" int bfe_eof_accumulate_prepared(bfe_eof* h, double* cos_out, double* 
     }
     {
         int grid = (ncell + 7) / 8;
-        if (grid > h->num_sms * 2) grid = h->num_sms * 2;      // <= 64 reduce groups of 16 CTAs
+        if (grid > bfe_eff_sms(h) * 2) grid = bfe_eff_sms(h) * 2;      // <= 64 reduce groups of 16 CTAs
         if (grid > h->max_ctas) grid = h->max_ctas;
         if (grid > 64 * 16) grid = 64 * 16;
         const int kt = bfe_kt_begin("eof_node_contract_kernel", stream);
@@ -881,7 +884,7 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
     SortWs ws;
     int rc = sort_workspace(h, n, &ws);
     if (rc != BFE_OK) return rc;
-    int64_t need = (n + 127) / 128, cap = (int64_t)h->num_sms * 16;
+    int64_t need = (n + 127) / 128, cap = (int64_t)bfe_eff_sms(h) * 16;
     int grid = (int)(need < cap ? need : cap);
     if (g_bfe_force_mma) {
         // one resident wave (occupancy queried once: registers and 16.4 kB of record buffers per CTA)
@@ -890,7 +893,7 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
             BFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eof_force_sorted_mma_kernel<6>, 128, 0));
             if (occ < 1) occ = 1;
         }
-        int64_t need_m = (n + 511) / 512, cap_m = (int64_t)h->num_sms * occ;
+        int64_t need_m = (n + 511) / 512, cap_m = (int64_t)bfe_eff_sms(h) * occ;
         grid = (int)(need_m < cap_m ? need_m : cap_m);
         const int kt = bfe_kt_begin("eof_force_sorted_mma_kernel", stream);
         BFE_CUDA(bfe_launch(eof_force_sorted_mma_kernel<6>, dim3(grid), dim3(128), 0, stream, h->g_con,
@@ -905,7 +908,7 @@ extern "C" int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double*
         bfe_kt_end(kt, stream);
         BFE_LAUNCH_CHECK("eof_force_sorted_kernel");
     }
-    int64_t need2 = (n + 255) / 256, cap2 = (int64_t)h->num_sms * 8;
+    int64_t need2 = (n + 255) / 256, cap2 = (int64_t)bfe_eff_sms(h) * 8;
     const int kt3 = bfe_kt_begin("eof_force_gather_kernel", stream);
     BFE_CUDA(bfe_launch(eof_force_gather_kernel, dim3((int)(need2 < cap2 ? need2 : cap2)), dim3(256), 0, stream, nullptr, 0,
                         n, ws.inv, ws.r_orig, ws.tmp, p0, p, fr, fp, fz, R));
