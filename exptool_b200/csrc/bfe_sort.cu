@@ -73,7 +73,7 @@ __device__ __forceinline__ int bfe_cell_of(const EofGeom& g, const EofBin& b) {
 __global__ void __launch_bounds__(1024)
 eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                      const double* __restrict__ z, int* __restrict__ hist, int* __restrict__ cell_start,
-                     int* __restrict__ cursor, unsigned int* __restrict__ counter) {
+                     int* __restrict__ cursor, unsigned int* __restrict__ counter, int* __restrict__ cellid) {
     extern __shared__ int s_hist[];
     __shared__ int s_wsum[32];
     __shared__ bool s_last;
@@ -99,12 +99,14 @@ eof_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__
             cell = bfe_eof_bin(g, r, pz).cell;
         }
         atomicAdd(&s_hist[cell], 1);
+        cellid[i] = cell;                 // kept for the scatter kernel (the inverse-permutation array, overwritten there)
         if (two) {
             if (!bfe_eof_cell_fast(g, qx, qy, qz, cell2)) {
                 double r = sqrt(qx * qx + qy * qy + 1.e-10);
                 cell2 = bfe_eof_bin(g, r, qz).cell;
             }
             atomicAdd(&s_hist[cell2], 1);
+            cellid[i2] = cell2;
         }
     }
     __syncthreads();
@@ -138,8 +140,8 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
                         const double* __restrict__ z, const double* __restrict__ mass,
                         const int* __restrict__ cell_start, int* __restrict__ cursor, EofRec* __restrict__ rec,
                         int* __restrict__ inv, double* __restrict__ r_orig) {
-    // Two particles per thread per pass.  Order of work per pass: (1) all eight loads, (2) the cell id by the FP32
-    // fast path (exact by construction, FP64 fallback near edges), (3) the integer slot claims, (4) the FP64 bin
+    // Two particles per thread per pass.  Order of work per pass: (1) all eight loads, (2) the cell id the histogram
+    // kernel left in inv[] (FP32 fast path, exact by construction, FP64 fallback near edges), (3) the integer slot claims, (4) the FP64 bin
     // fractions, weights and cos/sin phi WHILE the claims are in flight (they were 1/3 of this kernel's stall
     // samples when issued after the FP64 arithmetic, ncu profiles/), (5) the record stores.
     constexpr int U = 2;
@@ -158,12 +160,7 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
             aux[u] = (on && mass) ? __ldg(mass + idx[u]) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!bfe_eof_cell_fast(g, px[u], py[u], pz[u], cell[u])) {
-                const double r = sqrt(px[u] * px[u] + py[u] * py[u] + 1.e-10);
-                cell[u] = bfe_eof_bin(g, r, pz[u]).cell;
-            }
-        }
+        for (int u = 0; u < U; ++u) cell[u] = (idx[u] < n) ? inv[idx[u]] : 0;   // cell id left here by the histogram kernel
 #pragma unroll
         for (int u = 0; u < U; ++u)
             pos[u] = (idx[u] < n) ? (__ldg(cell_start + cell[u]) + atomicAdd(&cursor[(size_t)cell[u] * BFE_CURSOR_STRIDE], 1)) : 0;   // integer slot claim, not a data reduction
@@ -821,7 +818,7 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
             BFE_CUDA(cudaFuncSetAttribute(eof_cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
         const int kt = bfe_kt_begin("eof_cell_hist_kernel", stream);
         BFE_CUDA(bfe_launch(eof_cell_hist_kernel, dim3(grid), dim3(1024), ss, stream, nullptr, 0, h->g, ncell, n, x, y, z,
-                            ws.hist, ws.cell_start, ws.cursor, h->counter));
+                            ws.hist, ws.cell_start, ws.cursor, h->counter, ws.inv));
         bfe_kt_end(kt, stream);
     }
     BFE_LAUNCH_CHECK("eof_cell_hist_kernel");
