@@ -204,6 +204,10 @@ static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x,
     int64_t need = (n + 127) / 128, cap = (int64_t)he->num_sms * 16;
     int grid = (int)(need < cap ? need : cap);
     double crot = cos(rotpos), srot = sin(rotpos);
+    // large point sets: evaluated in table-cell order (bfe_orbit_sort.cu), results returned in the caller's order
+    if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6) && g_bfe_field_sort_min > 0 &&
+        n >= g_bfe_field_sort_min && n < ((int64_t)1 << 31))
+        return bfe_field_force_sorted(he, hs, n, x, y, z, crot, srot, out8, cyl, stream);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
         const bool f32 = g_bfe_table_fp32 != 0;
         int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
@@ -266,6 +270,10 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     if (ap_max < 1) ap_max = 1;
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = (int)((norbit + 127) / 128);
+    // large batches without trajectory / apocentre bookkeeping: orbits kept cell-coherent by a re-sort every K steps
+    if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6) && !traj && !apse &&
+        g_bfe_orbit_resort > 0 && norbit >= g_bfe_orbit_sort_min && nint > 2 * (int64_t)g_bfe_orbit_resort)
+        return bfe_leapfrog_sorted(he, hs, norbit, nint, dt, dt_orbit, rotfreq, state6, nsteps_out, stream);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
         const bool f32 = g_bfe_table_fp32 != 0;
         int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
@@ -352,6 +360,10 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "table_fp32")) { g_bfe_table_fp32 = value; return BFE_OK; }
     if (!strcmp(name, "force_mma")) { g_bfe_force_mma = value; return BFE_OK; }
     if (!strcmp(name, "pdl")) { g_bfe_pdl = value; return BFE_OK; }
+    if (!strcmp(name, "field_sort_chunk")) { g_bfe_field_sort_chunk = value; return BFE_OK; }
+    if (!strcmp(name, "field_sort_min")) { g_bfe_field_sort_min = value; return BFE_OK; }
+    if (!strcmp(name, "orbit_resort")) { g_bfe_orbit_resort = value; return BFE_OK; }
+    if (!strcmp(name, "orbit_sort_min")) { g_bfe_orbit_sort_min = value; return BFE_OK; }
     if (!strcmp(name, "grid_pct")) { if (value < 1 || value > 100) return BFE_ERR_ARG; g_bfe_grid_pct = value; return BFE_OK; }
     if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }
     if (!strcmp(name, "host_chunk")) { g_bfe_host_chunk = value; return BFE_OK; }

@@ -55,6 +55,8 @@ struct bfe_eof {
     int prepared_has_mass;
     int owns_tables;         // 0 for a clone (bfe_eof_clone): t_acc / t_force belong to the parent handle
     void* host_pipe;         // staging buffers / streams of the host-array entry points (bfe_host.cu), lazily made
+    void* orbit_ws;          // workspace of the cell-sorted leapfrog path (bfe_orbit_sort.cu), grown on demand
+    int64_t orbit_cap;
 };
 
 struct bfe_sl {
@@ -131,6 +133,14 @@ void bfe_host_pipe_destroy(void* pipe);
 extern int g_bfe_host_chunk;                               // option "host_chunk"
 extern int g_bfe_contract_deep;                            // option "contract_deep": 9 (1) or 6 (0) table loads in flight
 extern int g_bfe_pdl;
+extern int g_bfe_orbit_resort;                             // option "orbit_resort": steps between re-sorts of a large orbit batch (0: off)
+extern int g_bfe_orbit_sort_min;                           // option "orbit_sort_min": smallest batch on the sorted path
+extern int g_bfe_field_sort_chunk;                         // option "field_sort_chunk"
+extern int g_bfe_field_sort_min;                           // option "field_sort_min"
+int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
+                           double crot, double srot, double* out8, bool cyl, cudaStream_t stream);
+int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,
+                        double rotfreq, double* state6, int32_t* nsteps_out, cudaStream_t stream);
 extern int g_bfe_grid_pct;                                 // option "grid_pct" (default 100)
 extern int g_bfe_l2_persist;
 extern size_t g_bfe_l2_window_max;                         // cudaDeviceProp::accessPolicyMaxWindowSize

@@ -577,3 +577,48 @@ def test_sl_register_deposit_option(ops, lmax):
             assert relerr(b, a) < 1e-13, (lmax, no_odd)
     finally:
         ops.set_option('sl_accumulate_mode', 0); ops.set_option('sl_deposit_mode', 0)
+
+
+@pytest.mark.parametrize('name', FIELD_CASES)
+def test_cell_sorted_field_and_leapfrog_paths(ops, name):
+    """The cell-ordered paths for large point sets / orbit batches (bfe_orbit_sort.cu), forced onto the small golden
+    cases: Fields.return_forces_cart/_cyl in chunks of 7 points, leapfrog re-sorted every 4 steps.  Same goldens, and
+    bit-identical to the paths in the caller's order (the per-point arithmetic is the same function)."""
+    import torch
+    d, meta = load_golden(name)
+    E, H, g, ps = _field_handles(ops, meta, d)
+    E.contract(d['cos'], d['sin'])
+    H.contract(meta['halofac'] * d['coef'])
+    if ps['lmax'] not in (4, 6):
+        pytest.skip('block kernels cover lmax 4 and 6')
+    plain_c = ops.field_force_cart(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+    plain_y = ops.field_force_cyl(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+    nint = meta['nint']
+    plain_s, _, plain_n = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, meta['dt'], rotfreq=meta['rotfreq'])
+    dts = np.full(d['pos0'].shape[1], meta['dt']) * (1.0 + 0.1 * np.arange(d['pos0'].shape[1]))
+    plain_d, _, _ = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, dts, rotfreq=meta['rotfreq'])
+    try:
+        ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 7)
+        ops.set_option('orbit_sort_min', 1); ops.set_option('orbit_resort', 4)
+        for f32 in (0, 1):
+            ops.set_option('table_fp32', f32)
+            sc = ops.field_force_cart(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+            sy = ops.field_force_cyl(E, H, d['px'], d['py'], d['pz'], rotpos=meta['rot_full'])
+            ss, _, sn = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, meta['dt'], rotfreq=meta['rotfreq'])
+            sd, _, _ = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, dts, rotfreq=meta['rotfreq'])
+            if f32 == 0:
+                assert torch.equal(sc, plain_c) and torch.equal(sy, plain_y)
+                assert torch.equal(ss, plain_s) and torch.equal(sn, plain_n) and torch.equal(sd, plain_d)
+                out = sc.cpu().numpy()
+                for i in range(8):
+                    assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+                st = ss.cpu().numpy()
+                for k in range(d['orbits'].shape[0]):
+                    for j in range(6):
+                        assert abs(st[j, k] - d['orbits'][k, j, -1]) <= ORBIT_TOL * np.max(np.abs(d['orbits'][k, j])), (k, j)
+            else:
+                assert relerr(sc.cpu().numpy(), plain_c.cpu().numpy()) < FP32_TABLE_TOL
+                assert relerr(ss.cpu().numpy(), plain_s.cpu().numpy()) < 10 * FP32_TABLE_TOL
+    finally:
+        ops.set_option('field_sort_min', 0); ops.set_option('field_sort_chunk', 4 << 20)
+        ops.set_option('orbit_sort_min', 65536); ops.set_option('orbit_resort', 16); ops.set_option('table_fp32', 0)
