@@ -47,7 +47,7 @@ for f32 in (0, 1):
     ops.set_option('orbit_resort', 0)
     t, ref = timeit()
     res['fp32tab%d_plain' % f32] = t
-    for K in (2, 4, 8):
+    for K in (4, 8, 16, 32, 64):
         ops.set_option('orbit_resort', K)
         t, out = timeit()
         res['fp32tab%d_resort_%d' % (f32, K)] = t
