@@ -272,7 +272,8 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     int grid = (int)((norbit + 127) / 128);
     // large batches without trajectory / apocentre bookkeeping: orbits kept cell-coherent by a re-sort every K steps
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6) && !traj && !apse &&
-        g_bfe_orbit_resort > 0 && norbit >= g_bfe_orbit_sort_min && nint > 2 * (int64_t)g_bfe_orbit_resort)
+        g_bfe_orbit_resort > 0 && norbit >= g_bfe_orbit_sort_min && norbit < ((int64_t)1 << 31) &&
+        nint > 2 * (int64_t)g_bfe_orbit_resort && nint < ((int64_t)1 << 31))
         return bfe_leapfrog_sorted(he, hs, norbit, nint, dt, dt_orbit, rotfreq, state6, nsteps_out, stream);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
         const bool f32 = g_bfe_table_fp32 != 0;
