@@ -263,6 +263,19 @@ def test_frozen_field_timestep_and_grids(api, name):
         assert g3.shape == d['grid3'].shape
         for k in range(9):
             assert relerr(g3[..., k, :], d['grid3'][..., k, :]) < ORBIT_TOL, k
+        # do_integrate_multi (integrate.py:290-333): the same grids gathered as one float32 array
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            gm = integrate.do_integrate_multi(rads, vels, F, 40, 1.0e-5, meta['rotfreq'], False, -1, -1, 100., 1000, nprocs=3)
+            gm3 = integrate.do_integrate_multi(rads[:2], vels, F, 24, 1.0e-5, meta['rotfreq'], False, -1, -1, 100., 1000,
+                                               threedee=True, zs=d['grid_zs'], vzs=d['grid_vzs'])
+            gmy = integrate.do_integrate_multi(rads[:2], vels[:1], F, 30, 1.0e-5, 3.0, False, -1, -1, 50., 1000, launch='y')
+        assert gm.dtype == np.float32 and np.array_equal(gm, g.astype('f4'))
+        assert gm3.dtype == np.float32 and np.array_equal(gm3, g3.astype('f4'))
+        assert np.array_equal(gmy, gy.astype('f4'))
+        parts = integrate.redistribute_arrays(np.arange(11), 3)
+        assert [len(p_) for p_ in parts] == [5, 3, 3] and np.array_equal(np.concatenate(parts), np.arange(11))
+        assert integrate.re_form_orbit_arrays([g[:1], g[1:]]).shape == g.shape
 
 
 def test_eof_host_pipeline_matches_device(api):
