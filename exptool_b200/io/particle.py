@@ -3,8 +3,6 @@ particle.py -- the particle container types the hot path accepts
 (exptool/io/particle.py:142-157) and the `Input` front end of the PSP reader
 (exptool/io/particle.py:16-112): "OUT." files go to psp_io, "SPL." split files to spl_io.
 """
-import numpy as np
-
 from . import psp_io, spl_io
 
 
