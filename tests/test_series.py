@@ -86,3 +86,29 @@ def test_savitzky_golay_reproduces_polynomials_and_scipy():
     rng = np.random.default_rng(0)
     z = np.cumsum(rng.standard_normal(300))
     assert np.allclose(utils.savitzky_golay(z, 15, 3)[8:-8], savgol_filter(z, 15, 3)[8:-8], atol=1e-10)
+
+
+def test_unwrap_phase_equals_reference_live():
+    """where the reference is mounted: utils.unwrap_phase on random series, both winding directions, in-place +pi shift"""
+    if not os.path.isdir('/root/reference/exptool'):
+        import pytest
+        pytest.skip('reference not mounted')
+    import importlib
+    from oracle import refshim
+    refshim.load()
+    rutils = importlib.import_module('exptool.utils.utils')
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(2, 120))
+        t = np.sort(rng.random(n))
+        if trial % 3 == 0:
+            ph = rng.uniform(-np.pi, np.pi, n)
+        elif trial % 3 == 1:
+            w = rng.uniform(1, 40) * (1 if trial % 2 else -1)
+            ph = np.arctan2(np.sin(7.3 * t * w), np.cos(7.3 * t * w))
+        else:
+            ph = rng.uniform(0, 2 * np.pi, n)
+        a, b = ph.copy(), ph.copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ra, rb = rutils.unwrap_phase(t, a), utils.unwrap_phase(t, b)
+        assert np.array_equal(a, b) and np.array_equal(ra, rb), trial
