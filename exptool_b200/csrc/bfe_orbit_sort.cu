@@ -142,7 +142,9 @@ orbit_unsort_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restric
 }
 
 int g_bfe_orbit_resort = 16;            // option "orbit_resort": steps between re-sorts (0: never use the sorted path)
-int g_bfe_orbit_sort_min = 65536;       // option "orbit_sort_min": smallest batch that takes the sorted path
+int g_bfe_orbit_sort_min = 400000;      // option "orbit_sort_min": smallest batch that takes the sorted path.  The gain needs >~ 32 orbits per
+                                        // occupied table cell: 10^6 orbits 3.41 -> 2.93 s (C4), 1.25e5 orbits neutral (0.467 -> 0.463 s on 8 GPUs),
+                                        // and below that the fixed cost of a re-sort (~50 us per 16 steps) would show
 
 static size_t os_align(size_t v) { return (v + 255) / 256 * 256; }
 

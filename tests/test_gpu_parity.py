@@ -621,4 +621,4 @@ def test_cell_sorted_field_and_leapfrog_paths(ops, name):
                 assert relerr(ss.cpu().numpy(), plain_s.cpu().numpy()) < 10 * FP32_TABLE_TOL
     finally:
         ops.set_option('field_sort_min', 0); ops.set_option('field_sort_chunk', 4 << 20)
-        ops.set_option('orbit_sort_min', 65536); ops.set_option('orbit_resort', 16); ops.set_option('table_fp32', 0)
+        ops.set_option('orbit_sort_min', 400000); ops.set_option('orbit_resort', 16); ops.set_option('table_fp32', 0)
