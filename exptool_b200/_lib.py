@@ -39,7 +39,10 @@ SIGNATURES = {
     'bfe_version': (_INT, []),
     'bfe_launch_count': (C.c_uint64, []),
     'bfe_set_option': (_INT, [C.c_char_p, _INT]),
+    'bfe_get_option': (_INT, [C.c_char_p]),
     'bfe_kernel_time_ms': (C.c_double, [C.c_char_p]),
+    'bfe_eof_set_table_fp32': (_INT, [_P, _INT]),
+    'bfe_sl_set_table_fp32': (_INT, [_P, _INT]),
     'bfe_eof_create': (_INT, [C.POINTER(EofParams)] + [_P] * 6 + [_P, C.POINTER(_P)]),
     'bfe_eof_destroy': (None, [_P]),
     'bfe_eof_clone': (_INT, [_P, _P, C.POINTER(_P)]),

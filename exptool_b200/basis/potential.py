@@ -134,6 +134,9 @@ class Fields():
                                 rforceC=self.rforceC, zforceC=self.zforceC, rforceS=self.rforceS, zforceS=self.zforceS)
         self._H = ops.SLTables(self.lmaxhalo, self.nmaxhalo, self.numrhalo, self.cmaphalo, self.scalehalo,
                                self.evtablehalo, self.eftablehalo, self.xihalo, self.p0halo, self.d0halo)
+        # table precision is a property of THIS instance's handles (no process-wide state involved)
+        self._E.set_table_fp32(bool(getattr(self, 'table_fp32', False)))
+        self._H.set_table_fp32(bool(getattr(self, 'table_fp32', False)))
         self._contract_key = None
 
     def set_field_parameters(self, no_odd=False, halo_l=-1, halo_n=-1, disk_m=-1, disk_n=-1):
@@ -177,7 +180,7 @@ class Fields():
         return self._E, self._H
 
     def precision(self):
-        """context manager for this instance's table precision around device calls (ops.table_precision)"""
+        """kept for callers of round 1: the table precision now lives in this instance's device handles (_build_device)"""
         return ops.table_precision(getattr(self, 'table_fp32', False))
 
     # -- forces ---------------------------------------------------------------

@@ -540,6 +540,20 @@ __device__ __forceinline__ SlField bfe_sl_eval(const SlGeom& g, const double2* _
     return f;
 }
 
+// factorial_return factors fac[l*(lmax+1)+m] (spheresl.py:26-35) either through a device pointer (__ldg) or BY VALUE in
+// the kernel parameter block (SlFacP): with the loops unrolled the indices are constants and the factor becomes a
+// constant-bank operand of the multiply -- 28 fewer load instructions per point at lmax = 6, each of which cost a full
+// 8-wavefront pass of the L1 data pipe (ncu l1tex__data_pipe_lsu_wavefronts is what bounds the coherent per-lane kernels).
+struct SlFacP { double v[49]; };               // (lmax+1)^2 <= 49: the block kernels cover lmax 4 and 6
+inline SlFacP bfe_sl_facp(const bfe_sl* h) {     // valid for lmax <= 6 (the block kernels)
+    SlFacP f;
+    const int nf = (h->g.lmax + 1) * (h->g.lmax + 1);
+    for (int k = 0; k < 49; ++k) f.v[k] = k < nf ? h->fac_host[k] : 0.0;
+    return f;
+}
+__device__ __forceinline__ double bfe_fac_at(const double* fac, int k) { return __ldg(fac + k); }
+__device__ __forceinline__ double bfe_fac_at(const SlFacP& fac, int k) { return fac.v[k]; }
+
 // interval blocks of A3 are padded to an even number of double2 (32-byte alignment for the 256-bit loads below)
 #define BFE_A3_STRIDE(npair) ((3 * (npair) + 1) & ~1)
 
@@ -699,9 +713,9 @@ __device__ __forceinline__ EofField bfe_eof_eval_blk(const EofGeom& g, const dou
 }
 
 // valid only when g.lmax == LCAP (LCAP = 6: 84 double2 = 1344 B per interval; LCAP = 4: 45 padded to 46)
-template <int LCAP>
+template <int LCAP, typename FacT>
 __device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double2* __restrict__ A3,
-                                                   const double* __restrict__ p0tab, const double* __restrict__ fac,
+                                                   const double* __restrict__ p0tab, const FacT& fac,
                                                    const SlBin& b, double costh, double c1, double s1,
                                                    bool trig_index_l) {
     constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
@@ -768,7 +782,7 @@ __device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double
                 cl = cn; sl = sn;
             }
             const double2 am = v[3 * (l - m)], a0 = v[3 * (l - m) + 1], ap = v[3 * (l - m) + 2];
-            const double fl = __ldg(fac + l * (LCAP + 1) + m);
+            const double fl = bfe_fac_at(fac, l * (LCAP + 1) + m);
             const double spc = wA * am.x + wB * a0.x + wC * ap.x;
             const double sdc = dA * am.x + dB * a0.x + dC * ap.x;
             if (m == 0) {
@@ -866,9 +880,9 @@ __device__ __forceinline__ EofField bfe_eof_eval_blk32(const EofGeom& g, const f
 // is formed from differences taken in FP64 BEFORE the rounding to float: storing the three node values as
 // floats and differencing afterwards amplifies their 6e-8 rounding by the ~1e3-1e4 cancellation of the stencil
 // (measured 3e-4 in the radial force; profiles/r01_blk_ab.json).
-template <int LCAP>
+template <int LCAP, typename FacT>
 __device__ __forceinline__ SlField bfe_sl_eval_blk32(const SlGeom& g, const float* __restrict__ A3f,
-                                                     const double* __restrict__ p0tab, const double* __restrict__ fac,
+                                                     const double* __restrict__ p0tab, const FacT& fac,
                                                      const SlBin& b, double costh, double c1, double s1,
                                                      bool trig_index_l) {
     constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
@@ -915,7 +929,7 @@ __device__ __forceinline__ SlField bfe_sl_eval_blk32(const SlGeom& g, const floa
             }
             float e[8];
             bfe_ldg256f(base + 8 * (offm + l - m), e);
-            const double fl = __ldg(fac + l * (LCAP + 1) + m);
+            const double fl = bfe_fac_at(fac, l * (LCAP + 1) + m);
             const double spc = wlo * (double)e[0] + whi * (double)e[2];
             const double sdc = fx2 * (double)e[6] + b.fac * (double)e[4];
             if (m == 0) {
@@ -1007,11 +1021,11 @@ __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const dou
 }
 
 // The same with the block evaluations above (G4 / A3, 256-bit loads); valid for g.lmax == LCAP.
-template <int MCAP, int LCAP, bool CYL = false, bool F32 = false>
+template <int MCAP, int LCAP, bool CYL = false, bool F32 = false, typename FacT = const double*>
 __device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const void* __restrict__ G4,
                                                         const SlGeom& gs, const void* __restrict__ A3,
                                                         const double* __restrict__ xi, const double* __restrict__ p0tab,
-                                                        const double* __restrict__ fac,
+                                                        const FacT& fac,
                                                         double x, double y, double z, double crot, double srot) {
     const double eps = CYL ? 1.e-10 : 1.e-15;
     double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + eps;

@@ -113,7 +113,7 @@ leapfrog_kernel(EofGeom ge, const double* __restrict__ G, int gstride,
 template <int MCAP, int LCAP, bool CYL, bool F32>
 __global__ void __launch_bounds__(128)
 field_cart_blk_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
-                      const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
+                      const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
                       int64_t n, const double* __restrict__ x, const double* __restrict__ y,
                       const double* __restrict__ z, double crot, double srot, double* __restrict__ out8) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -127,7 +127,7 @@ field_cart_blk_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const 
 template <int MCAP, int LCAP, bool F32>
 __global__ void __launch_bounds__(128)
 leapfrog_blk_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
-                    const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
+                    const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
                     int64_t norbit, int64_t nint, double dt, const double* __restrict__ dt_orbit, double rotfreq,
                     double* __restrict__ state6, double* __restrict__ traj, int64_t traj_stride,
                     int apse, int ap_max, int* __restrict__ nsteps_out) {
@@ -209,14 +209,15 @@ static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x,
         n >= g_bfe_field_sort_min && n < ((int64_t)1 << 31))
         return bfe_field_force_sorted(he, hs, n, x, y, z, crot, srot, out8, cyl, stream);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
-        const bool f32 = g_bfe_table_fp32 != 0;
+        const bool f32 = bfe_use_fp32(he);
         int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
         if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
         if (rc != BFE_OK) return rc;
         const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
         const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+        const SlFacP facp = bfe_sl_facp(hs);
 #define FIELD_BLK(L, C, F) field_cart_blk_kernel<6, L, C, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, \
-                                                                                    hs->fac, n, x, y, z, crot, srot, out8)
+                                                                                    facp, n, x, y, z, crot, srot, out8)
 #define FIELD_BLK2(L, C) do { if (f32) FIELD_BLK(L, C, true); else FIELD_BLK(L, C, false); } while (0)
         if (hs->g.lmax == 4) { if (cyl) FIELD_BLK2(4, true); else FIELD_BLK2(4, false); }
         else                 { if (cyl) FIELD_BLK2(6, true); else FIELD_BLK2(6, false); }
@@ -273,16 +274,17 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     // large batches without trajectory / apocentre bookkeeping: orbits kept cell-coherent by a re-sort every K steps
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6) && !traj && !apse &&
         g_bfe_orbit_resort > 0 && norbit >= g_bfe_orbit_sort_min && norbit < ((int64_t)1 << 31) &&
-        nint > 2 * (int64_t)g_bfe_orbit_resort && nint < ((int64_t)1 << 31))
+        nint > 2 * (int64_t)g_bfe_orbit_resort + 2 && nint < ((int64_t)1 << 31))
         return bfe_leapfrog_sorted(he, hs, norbit, nint, dt, dt_orbit, rotfreq, state6, nsteps_out, stream);
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
-        const bool f32 = g_bfe_table_fp32 != 0;
+        const bool f32 = bfe_use_fp32(he);
         int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
         if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
         if (rc != BFE_OK) return rc;
         const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
         const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
-#define LEAP_BLK(L, F) leapfrog_blk_kernel<6, L, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, \
+        const SlFacP facp = bfe_sl_facp(hs);
+#define LEAP_BLK(L, F) leapfrog_blk_kernel<6, L, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, facp, norbit, \
                                                                            nint, dt, dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out)
         if (hs->g.lmax == 4) { if (f32) LEAP_BLK(4, true); else LEAP_BLK(4, false); }
         else                 { if (f32) LEAP_BLK(6, true); else LEAP_BLK(6, false); }
@@ -377,6 +379,43 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "sl_deposit_mode")) { g_bfe_sl_deposit_mode = value; return BFE_OK; }
     if (!strcmp(name, "sort_min_particles")) { g_bfe_sort_min_particles = value; return BFE_OK; }
     return BFE_ERR_ARG;
+}
+
+// current value of a runtime option (so that tests and tools can restore what they change); INT_MIN for unknown names
+extern "C" int bfe_get_option(const char* name) {
+    if (!name) return -2147483647 - 1;
+    if (!strcmp(name, "eof_accumulate_mode")) return g_bfe_eof_accumulate_mode;
+    if (!strcmp(name, "eof_force_mode")) return g_bfe_eof_force_mode;
+    if (!strcmp(name, "time_kernels")) return g_bfe_time_kernels;
+    if (!strcmp(name, "staged_eval")) return g_bfe_staged_eval;
+    if (!strcmp(name, "blk_eval")) return g_bfe_blk_eval;
+    if (!strcmp(name, "table_fp32")) return g_bfe_table_fp32;
+    if (!strcmp(name, "force_mma")) return g_bfe_force_mma;
+    if (!strcmp(name, "pdl")) return g_bfe_pdl;
+    if (!strcmp(name, "field_sort_chunk")) return g_bfe_field_sort_chunk;
+    if (!strcmp(name, "field_sort_min")) return g_bfe_field_sort_min;
+    if (!strcmp(name, "orbit_resort")) return g_bfe_orbit_resort;
+    if (!strcmp(name, "orbit_sort_min")) return g_bfe_orbit_sort_min;
+    if (!strcmp(name, "grid_pct")) return g_bfe_grid_pct;
+    if (!strcmp(name, "contract_deep")) return g_bfe_contract_deep;
+    if (!strcmp(name, "host_chunk")) return g_bfe_host_chunk;
+    if (!strcmp(name, "l2_persist")) return g_bfe_l2_persist;
+    if (!strcmp(name, "sl_accumulate_mode")) return g_bfe_sl_accumulate_mode;
+    if (!strcmp(name, "sl_deposit_mode")) return g_bfe_sl_deposit_mode;
+    if (!strcmp(name, "sort_min_particles")) return g_bfe_sort_min_particles;
+    return -2147483647 - 1;
+}
+
+// per-handle table precision of the per-point field kernels (-1: follow the process option "table_fp32")
+extern "C" int bfe_eof_set_table_fp32(bfe_eof* h, int value) {
+    if (!h || value < -1 || value > 1) return BFE_ERR_ARG;
+    h->table_fp32 = value;
+    return BFE_OK;
+}
+extern "C" int bfe_sl_set_table_fp32(bfe_sl* h, int value) {
+    if (!h || value < -1 || value > 1) return BFE_ERR_ARG;
+    h->table_fp32 = value;
+    return BFE_OK;
 }
 
 // ---- optional per-kernel event timing

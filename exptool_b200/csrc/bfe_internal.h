@@ -55,8 +55,12 @@ struct bfe_eof {
     int prepared_has_mass;
     int owns_tables;         // 0 for a clone (bfe_eof_clone): t_acc / t_force belong to the parent handle
     void* host_pipe;         // staging buffers / streams of the host-array entry points (bfe_host.cu), lazily made
-    void* orbit_ws;          // workspace of the cell-sorted leapfrog path (bfe_orbit_sort.cu), grown on demand
+    void* orbit_ws;          // key-sort workspace of the table-coherent field / leapfrog paths (bfe_orbit_sort.cu), grown on demand
     int64_t orbit_cap;
+    void* orbit_rec;         // 96-byte orbit records of the key-ordered leapfrog path, grown on demand
+    int64_t orbit_rec_cap;
+    void* field_pipe;        // aux stream + events of the two-stream point pipeline (bfe_orbit_sort.cu), lazily made
+    int table_fp32;          // per-handle table precision of the per-point field kernels: -1 inherit option "table_fp32", 0 FP64, 1 FP32
 };
 
 struct bfe_sl {
@@ -88,9 +92,11 @@ struct bfe_sl {
     // radial-bin-sorted accumulate workspace (grown on demand)
     int64_t sort_cap;
     void* sort_ws;
+    int table_fp32;      // as bfe_eof::table_fp32 (SL-only evaluation calls)
 };
 
 extern "C" void bfe_count_launch(int n);
+struct SlFacP;                                              // bfe_device.cuh: the factorial factors by value (kernel parameter)
 
 // runtime options (bfe_set_option): 0 = auto, 1 = direct kernels, 2 = cell-sorted kernels
 extern int g_bfe_eof_accumulate_mode;
@@ -111,7 +117,9 @@ void bfe_set_cuda_error(cudaError_t e, const char* where);
 int bfe_eof_ensure_g4(bfe_eof* h, cudaStream_t stream);     // build G4 from g_con if stale
 int bfe_sl_ensure_a3(bfe_sl* h, cudaStream_t stream);       // build A3 from a_con if stale
 extern int g_bfe_force_mma;                                 // option "force_mma": sorted force eval on DMMA (1, default) / per lane (0)
-extern int g_bfe_table_fp32;                                // option "table_fp32": float contracted tables in the per-point field kernels
+extern int g_bfe_table_fp32;                                // option "table_fp32": process default for handles that do not set their own
+inline bool bfe_use_fp32(const bfe_eof* h) { return (h->table_fp32 >= 0 ? h->table_fp32 : g_bfe_table_fp32) != 0; }
+inline bool bfe_use_fp32(const bfe_sl* h) { return (h->table_fp32 >= 0 ? h->table_fp32 : g_bfe_table_fp32) != 0; }
 int bfe_eof_ensure_g4f(bfe_eof* h, cudaStream_t stream);
 int bfe_sl_ensure_a3f(bfe_sl* h, cudaStream_t stream);
 extern int g_bfe_blk_eval;                                  // option "blk_eval": per-lane block evaluation with 256-bit loads
@@ -130,6 +138,7 @@ void bfe_kt_end(int slot, cudaStream_t stream);
 //  * option "l2_persist" (default 0/1 see bfe_field.cu): an access-policy window marks a table (t_force, t_acc,
 //    g_con) persisting in the L2 set-aside so the 80 MB/step particle stream does not evict it.
 void bfe_host_pipe_destroy(void* pipe);
+void bfe_field_pipe_destroy(void* pipe);
 extern int g_bfe_host_chunk;                               // option "host_chunk"
 extern int g_bfe_contract_deep;                            // option "contract_deep": 9 (1) or 6 (0) table loads in flight
 extern int g_bfe_pdl;

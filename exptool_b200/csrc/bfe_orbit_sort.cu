@@ -1,299 +1,246 @@
-// bfe_orbit_sort.cu -- leapfrog integration of large orbit batches with the orbits kept CELL-COHERENT.
+// bfe_orbit_sort.cu -- per-point field evaluation and leapfrog integration with the warps kept TABLE-COHERENT.
 //
-// The per-point field evaluation is bound by the L1 tag stage: one cycle per distinct 128-byte line per load
-// instruction (ncu l1tex 92 %, profiles/r01_ncu_full_blk_kernels.csv).  When the 32 lanes of a warp sit in the same
-// (R, z) table cell they read the same per-cell block, and every load instruction touches ONE line instead of 32
-// (the SL interval blocks of such a warp span ~1/2 of the lines): measured 360 -> 156 us per 10^6 points with the
-// points merely re-ordered by cell, results bit-identical (profiles/sorted_points_probe.py).  Orbits drift out of
-// their cells within a few steps (the vertical cells are thin), so the batch is re-sorted every K steps (option
-// "orbit_resort", default 16; measured 0.343 -> 0.288 ns per orbit-step at 10^6 orbits, profiles/orbit_sort_probe.py):
+// The per-point field kernels (bfe_field.cu) are bound by the L1 tag stage: one cycle per distinct 128-byte line per load
+// instruction, 84 divergent 256-bit loads per point (ncu l1tex 92 %, FP64 pipe 20 %, profiles/r01_ncu_full_blk_kernels.csv).
+// When the 32 lanes of a warp sit in the same EOF (R, z) cell AND the same SL radial interval they read the same two blocks
+// (G4[cell], A3[j]): every load instruction touches ONE line, the evaluation becomes FP64-bound.  This file orders the
+// points / orbits by a composite key and evaluates in that order WITHOUT moving the data:
 //
-//   orbit_pack_kernel      : caller's SoA state (+ step size) -> 64-byte records {x,y,z,vx,vy,vz,dt,index}
-//   orbit_cell_hist_kernel : table cell of every orbit -> histogram, last CTA scans (same scheme as bfe_sort.cu)
-//   orbit_scatter_kernel   : records to their sorted slots (integer slot claims; two full-sector stores each)
-//   leapfrog_rec_kernel    : K velocity-Verlet steps on the sorted records, state in registers; the acceleration at
-//                            the chunk's first step is re-evaluated from the position (same inputs, same bits)
-//   orbit_unsort_kernel    : records -> caller's SoA order
+//   key  = (EOF cell << SUB) | (SL interval & (2^SUB - 1)),  SUB = 4           [FP32 arithmetic: an ordering key only]
+//          -- same cell => same G4 block; inside a cell the SL intervals a point can have span a range that depends on the
+//          cell (a few for disc-plane cells, ~100 for cells high above the plane): the low SUB bits group equal intervals
+//          exactly when the span is <= 16 and leave span/16 distinct intervals per bin otherwise.
+//   sort = ONE counting pass over nkeys = ncell * 16 bins (131072 for the 128 x 64 grid), permutation only:
+//            pt_key_kernel / orbit_pack_key_kernel : key, rank-in-bin by one integer atomicAdd WITH return  -> (key, rank)
+//            key_scan_kernel                       : exclusive scan of the histogram (1024-bin blocks + block prefixes by the
+//                                                    last CTA), histogram cleared for the next use
+//            perm_scatter_kernel                   : perm[bprefix[key>>10] + start[key] + rank] = i   (no atomics)
+//          The order inside a bin follows the atomic's arrival order; the VALUES do not depend on it (each point is evaluated
+//          on its own), so results are bit-identical to the caller-order kernels whatever the order.
+//   eval = field_rec_kernel / leapfrog_perm_kernel: 128-point tiles of the sorted order are handed out through an atomic
+//          ticket (tiles in sparse regions are latency-bound and take longer: with a static split the SMs idled 29 % of the
+//          kernel, ncu sm active vs elapsed cycles).  Points: 32-byte records {x,y,z,index} in sorted order in, 64-byte result
+//          slots in sorted order out (full sectors, coalesced), field_gather_kernel returns them to the caller's order.
+//          Orbits: the 96-byte record (three full sectors) stays in the caller's order and is gathered through the
+//          permutation; the key of the NEXT evaluation point (the following step's drift) is produced by the same kernel.
+//   What bounds the evaluation once the warps are coherent (ncu, profiles/r02_*): the L1 data pipe -- every 256-bit load
+//   is 8 wavefronts (1 KiB into the register file) whatever the coherence, 84 table loads per point -- and then FP64 issue
+//   (1700 instructions per point).  The factorial factors therefore travel in the kernel parameter block (SlFacP), not
+//   through 28 more loads.  Tried and dropped (profiles/r02_summary.md): two sorted points per lane sharing the loads (halves
+//   the L1 traffic, but 224 registers leave two warps per scheduler: 216 -> 278 us per 1e6 disc points) and an L1 prefetch
+//   (CCTL.E.PF1) of the next tile's blocks (no gain: the misses are already covered by the four-tile tickets).
 //
-// Used for batches without trajectory output and without apocentre counting (bfe_leapfrog / bfe_leapfrog_dt decide);
-// the arithmetic per step is bfe_field_cart_blk, so end states equal the unsorted kernel's bit for bit.
+// Points are processed in chunks (option "field_sort_chunk") so that the chunk's records, slots and keys (100 B per point, a
+// workspace that is re-used by every chunk) stay L2-resident: HBM sees the compulsory 24 B in + 64 B out per point.
+// Orbits are re-keyed every K steps (option "orbit_resort").  The per-point arithmetic is bfe_field_cart_blk, the same
+// function the caller-order kernels use, so results are bit-identical to theirs.
 #include "bfe_sortcore.cuh"
 
-struct __align__(32) OrbRec {
-    double x, y, z, vx, vy, vz, dt;
-    unsigned long long idx;
-};
+#define BFE_KEY_SUBBITS 4
+#define BFE_SCAN_BLOCK 1024
+#ifndef BFE_PERM_MINB
+#define BFE_PERM_MINB 3          // resident CTAs per SM the evaluation kernels are compiled for (4: 128 registers, 3: 168, no spills;
+                                 // a quarter of the register file stays free for the support kernels of the other stream)
+#endif
+
+__device__ __forceinline__ int bfe_sl_interval_fast(const SlGeom& g, float r) {
+    float x;
+    if (g.cmap == 1) { const float q = r * (float)g.inv_scale; x = (q - 1.0f) / (q + 1.0f); }
+    else if (g.cmap == 2) x = logf(r);
+    else x = r;
+    int i = (int)((x - (float)g.xi0) * (float)g.inv_dxi);      // NaN -> 0
+    if (i < 0) i = 0;
+    if (i > g.numr - 2) i = g.numr - 2;
+    return i;
+}
+
+__device__ __forceinline__ int bfe_point_key(const EofGeom& ge, const SlGeom& gs, int ncell, int subbits,
+                                             double px, double py, double pz) {
+    int cell;
+    bfe_eof_cell_fast(ge, px, py, pz, cell);
+    if ((unsigned)cell >= (unsigned)ncell) cell = 0;
+    const float xf = (float)px, yf = (float)py, zf = (float)pz;
+    const int j = bfe_sl_interval_fast(gs, sqrtf(fmaf(xf, xf, fmaf(yf, yf, zf * zf))));
+    return (cell << subbits) | (j & ((1 << subbits) - 1));
+}
+
+// Guided tickets over the 128-point tiles of the sorted order: the first 3/4 of the tiles are handed out four at a time
+// (a CTA that walks consecutive tiles finds the table lines of the previous tile in L1: with single-tile tickets every
+// tile started cold, L1 hit rate 39-55 %), the rest one at a time so that the finish line is one tile wide.
+struct TileTicket { unsigned int first, count; };
+__device__ __forceinline__ unsigned int bfe_ticket_count(unsigned int ntile) {
+    const unsigned int n4 = (ntile - ntile / 4) / 4;
+    return n4 + (ntile - 4 * n4);
+}
+__device__ __forceinline__ TileTicket bfe_ticket_tiles(unsigned int k, unsigned int ntile) {
+    const unsigned int n4 = (ntile - ntile / 4) / 4;
+    TileTicket t;
+    if (k < n4) { t.first = 4 * k; t.count = 4; }
+    else { t.first = 4 * n4 + (k - n4); t.count = 1; }
+    return t;
+}
+
+// rank of this lane's item inside its bin: lanes of the warp with the same key share ONE atomic
+__device__ __forceinline__ int bfe_claim_rank(int* __restrict__ hist, int key, bool on) {
+    const unsigned act = __ballot_sync(0xffffffffu, on);
+    int rank = 0;
+    if (on) {
+        const unsigned peers = __match_any_sync(act, key);
+        const int lane = threadIdx.x & 31;
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(hist + key, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        rank = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    return rank;
+}
 
 __global__ void __launch_bounds__(256)
-orbit_pack_kernel(int64_t n, const double* __restrict__ state6, double dt, const double* __restrict__ dt_orbit,
-                  OrbRec* __restrict__ rec) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        char* dst = reinterpret_cast<char*>(rec + i);
-        bfe_st256(dst, state6[i], state6[n + i], state6[2 * n + i], state6[3 * n + i]);
-        bfe_st256(dst + 32, state6[4 * n + i], state6[5 * n + i], dt_orbit ? dt_orbit[i] : dt,
-                  __longlong_as_double((long long)i));
+pt_key_kernel(EofGeom ge, SlGeom gs, int ncell, int subbits, int64_t n, const double* __restrict__ x,
+              const double* __restrict__ y, const double* __restrict__ z, int* __restrict__ hist, int2* __restrict__ keyrank) {
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const int64_t nround = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool on = i < n;
+        int key = 0;
+        // points arrive in the caller's order: the 32 keys of a warp differ, so one atomic per lane (no match / aggregation)
+        if (on) {
+            key = bfe_point_key(ge, gs, ncell, subbits, __ldg(x + i), __ldg(y + i), __ldg(z + i));
+            keyrank[i] = make_int2(key, atomicAdd(hist + key, 1));
+        }
     }
 }
 
-__global__ void __launch_bounds__(1024)
-orbit_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const OrbRec* __restrict__ rec, int* __restrict__ hist,
-                       int* __restrict__ cell_start, int* __restrict__ cursor, unsigned int* __restrict__ counter,
-                       int* __restrict__ cellid) {
-    extern __shared__ int s_hist[];
-    __shared__ int s_wsum[32];
+// start[k] = exclusive prefix of hist inside its 1024-bin block, hist cleared; the last CTA turns the block totals into
+// block prefixes.  Position of an item = bprefix[key >> 10] + start[key] + rank.
+__global__ void __launch_bounds__(BFE_SCAN_BLOCK)
+key_scan_kernel(int nkeys, int* __restrict__ hist, int* __restrict__ start, int* __restrict__ btot,
+                int* __restrict__ bprefix, unsigned int* __restrict__ counter, int ticket_slot) {
+    __shared__ int s_w[32];
     __shared__ bool s_last;
-    for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x)
-        cursor[(size_t)c * BFE_CURSOR_STRIDE] = 0;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) counter[1 + ticket_slot] = 0u;      // tile ticket of the evaluation kernel that follows
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = blockIdx.x * BFE_SCAN_BLOCK + tid;
+    int v = 0;
+    if (k < nkeys) { v = __ldcg(hist + k); hist[k] = 0; }
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double a, b, c, d;
-        bfe_ld256_nc(rec + i, a, b, c, d);                   // x, y, z, vx
-        int cell;
-        bfe_eof_cell_fast(g, a, b, c, cell);                  // an ordering key only: the clamped FP32 index will do
-        if (cell < 0 || cell >= ncell) cell = 0;
-        atomicAdd(&s_hist[cell], 1);
-        cellid[i] = cell;
+    if (warp == 0) {
+        int w = s_w[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += u; }
+        s_w[lane] = w;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
-        int v = s_hist[c];
-        if (v) atomicAdd(&hist[c], v);
-    }
+    const int excl = incl - v + (warp > 0 ? s_w[warp - 1] : 0);
+    if (k < nkeys) start[k] = excl;
+    if (tid == BFE_SCAN_BLOCK - 1) btot[blockIdx.x] = excl + v;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int done = atomicAdd(counter, 1u);
-        s_last = (done == gridDim.x - 1);
-    }
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (s_last) {
-        __threadfence();
-        bfe_block_scan_cells(ncell, hist, cell_start, s_hist, s_wsum);
-        if (threadIdx.x == 0) *counter = 0u;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-orbit_scatter_kernel(int64_t n, const OrbRec* __restrict__ src, const int* __restrict__ cellid,
-                     const int* __restrict__ cell_start, int* __restrict__ cursor, OrbRec* __restrict__ dst) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double a0, a1, a2, a3, b0, b1, b2, b3;
-        bfe_ld256_nc(src + i, a0, a1, a2, a3);
-        bfe_ld256_nc(reinterpret_cast<const char*>(src + i) + 32, b0, b1, b2, b3);
-        const int cell = __ldg(cellid + i);
-        const int pos = __ldg(cell_start + cell) + atomicAdd(&cursor[(size_t)cell * BFE_CURSOR_STRIDE], 1);   // integer slot claim
-        char* d = reinterpret_cast<char*>(dst + pos);
-        bfe_st256(d, a0, a1, a2, a3);
-        bfe_st256(d + 32, b0, b1, b2, b3);
-    }
-}
-
-template <int MCAP, int LCAP, bool F32>
-__global__ void __launch_bounds__(128)
-leapfrog_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
-                    const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
-                    int64_t norbit, int64_t step0, int nsteps, double rotfreq, OrbRec* __restrict__ rec) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= norbit) return;
-    double px, py, pz, vx, vy, vz, dt, idxbits;
-    // plain (coherent) loads: this kernel rewrites the record in place
-    {
-        const double4* r4 = reinterpret_cast<const double4*>(rec + i);
-        const double4 a = r4[0], b = r4[1];
-        px = a.x; py = a.y; pz = a.z; vx = a.w; vy = b.x; vz = b.y; dt = b.z; idxbits = b.w;
-    }
-    const double w = BFE_TWOPI * rotfreq;                    // barpos = 2 pi rotfreq (k dt), integrate.py:94-97
-    const double hdt2 = 0.5 * (dt * dt);
-    double srot, crot;
-    sincos(w * ((double)step0 * dt), &srot, &crot);
-    CartForce f = bfe_field_cart_blk<MCAP, LCAP, false, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
-    double ax = f.fxd + f.fxh, ay = f.fyd + f.fyh, az = f.fzd + f.fzh;
-    for (int k = 1; k <= nsteps; ++k) {
-        const int64_t step = step0 + k;
-        px = px + (vx * dt) + (ax * hdt2);                   // integrate.py:129-131
-        py = py + (vy * dt) + (ay * hdt2);
-        pz = pz + (vz * dt) + (az * hdt2);
-        sincos(w * ((double)step * dt), &srot, &crot);
-        f = bfe_field_cart_blk<MCAP, LCAP, false, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
-        const double bx = f.fxd + f.fxh, by = f.fyd + f.fyh, bz = f.fzd + f.fzh;             // 134-138
-        vx = vx + (0.5 * (ax + bx) * dt);                    // 141-143
-        vy = vy + (0.5 * (ay + by) * dt);
-        vz = vz + (0.5 * (az + bz) * dt);
-        ax = bx; ay = by; az = bz;
-    }
-    char* d = reinterpret_cast<char*>(rec + i);
-    bfe_st256(d, px, py, pz, vx);
-    bfe_st256(d + 32, vy, vz, dt, idxbits);
-}
-
-__global__ void __launch_bounds__(256)
-orbit_unsort_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restrict__ state6, int* __restrict__ nsteps_out,
-                    int nint) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double a0, a1, a2, a3, b0, b1, b2, b3;
-        bfe_ld256_nc(rec + i, a0, a1, a2, a3);
-        bfe_ld256_nc(reinterpret_cast<const char*>(rec + i) + 32, b0, b1, b2, b3);
-        const int64_t o = (int64_t)__double_as_longlong(b3);
-        state6[o] = a0; state6[n + o] = a1; state6[2 * n + o] = a2;
-        state6[3 * n + o] = a3; state6[4 * n + o] = b0; state6[5 * n + o] = b1;
-        if (nsteps_out) nsteps_out[o] = nint;
-    }
-}
-
-int g_bfe_orbit_resort = 16;            // option "orbit_resort": steps between re-sorts (0: never use the sorted path)
-int g_bfe_orbit_sort_min = 400000;      // option "orbit_sort_min": smallest batch that takes the sorted path.  The gain needs >~ 32 orbits per
-                                        // occupied table cell: 10^6 orbits 3.41 -> 2.93 s (C4), 1.25e5 orbits neutral (0.467 -> 0.463 s on 8 GPUs),
-                                        // and below that the fixed cost of a re-sort (~50 us per 16 steps) would show
-
-static size_t os_align(size_t v) { return (v + 255) / 256 * 256; }
-
-// sorted-path integration; the caller has checked eligibility (contracted handles, mmax <= 6, lmax 4 or 6)
-int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,
-                        double rotfreq, double* state6, int32_t* nsteps_out, cudaStream_t stream) {
-    const int ncell = he->g.numx * he->g.numy;
-    const size_t o_hist = 0;
-    const size_t o_start = os_align(o_hist + sizeof(int) * ncell);
-    const size_t o_cur = os_align(o_start + sizeof(int) * (ncell + 1));
-    const size_t o_cid = os_align(o_cur + sizeof(int) * (size_t)ncell * BFE_CURSOR_STRIDE);
-    if (norbit > he->orbit_cap || !he->orbit_ws) {
-        if (he->orbit_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_ws)); he->orbit_ws = nullptr; }
-        const int64_t cap = norbit + norbit / 8 + 1024;
-        const size_t o_a = os_align(o_cid + sizeof(int) * (size_t)cap);
-        BFE_CUDA(cudaMalloc(&he->orbit_ws, o_a + 2 * sizeof(OrbRec) * (size_t)cap));
-        BFE_CUDA(cudaMemset(he->orbit_ws, 0, o_cid));
-        BFE_CUDA(cudaDeviceSynchronize());
-        he->orbit_cap = cap;
-    }
-    char* b = (char*)he->orbit_ws;
-    int* hist = (int*)(b + o_hist); int* cell_start = (int*)(b + o_start); int* cursor = (int*)(b + o_cur);
-    int* cellid = (int*)(b + o_cid);
-    const size_t o_a = os_align(o_cid + sizeof(int) * (size_t)he->orbit_cap);
-    OrbRec* bufs[2] = {(OrbRec*)(b + o_a), (OrbRec*)(b + o_a) + he->orbit_cap};
-
-    const bool f32 = g_bfe_table_fp32 != 0;
-    int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
-    if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
-    if (rc != BFE_OK) return rc;
-    const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
-    const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
-
-    const int per = (ncell + 1023) / 1024;
-    const size_t ss = sizeof(int) * (size_t)per * 1024;
-    if (ss > 200 * 1024) return BFE_ERR_UNSUPPORTED;
-    if (ss > 48 * 1024)
-        BFE_CUDA(cudaFuncSetAttribute(orbit_cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
-    int ghist = (int)((norbit + 2047) / 2048);
-    if (ghist > he->num_sms) ghist = he->num_sms;
-    if (ghist < 1) ghist = 1;
-    int g256 = (int)((norbit + 255) / 256);
-    if (g256 > he->num_sms * 8) g256 = he->num_sms * 8;
-    const int glf = (int)((norbit + 127) / 128);
-
-    orbit_pack_kernel<<<g256, 256, 0, stream>>>(norbit, state6, dt, dt_orbit, bufs[0]);
-    BFE_LAUNCH_CHECK("orbit_pack_kernel");
-    int cur = 0;
-    const int K = g_bfe_orbit_resort > 0 ? g_bfe_orbit_resort : 32;
-    for (int64_t step0 = 0; step0 < nint - 1; step0 += K) {
-        const int k = (int)((nint - 1 - step0) < K ? (nint - 1 - step0) : K);
-        orbit_cell_hist_kernel<<<ghist, 1024, ss, stream>>>(he->g, ncell, norbit, bufs[cur], hist, cell_start, cursor,
-                                                           he->counter, cellid);
-        BFE_LAUNCH_CHECK("orbit_cell_hist_kernel");
-        orbit_scatter_kernel<<<g256, 256, 0, stream>>>(norbit, bufs[cur], cellid, cell_start, cursor, bufs[cur ^ 1]);
-        BFE_LAUNCH_CHECK("orbit_scatter_kernel");
-        cur ^= 1;
-#define LEAP_REC(L, F) leapfrog_rec_kernel<6, L, F><<<glf, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, norbit, \
-                                                                         step0, k, rotfreq, bufs[cur])
-        if (hs->g.lmax == 4) { if (f32) LEAP_REC(4, true); else LEAP_REC(4, false); }
-        else                 { if (f32) LEAP_REC(6, true); else LEAP_REC(6, false); }
-#undef LEAP_REC
-        BFE_LAUNCH_CHECK("leapfrog_rec_kernel");
-    }
-    orbit_unsort_kernel<<<g256, 256, 0, stream>>>(norbit, bufs[cur], state6, nsteps_out, (int)nint);
-    BFE_LAUNCH_CHECK("orbit_unsort_kernel");
-    return BFE_OK;
-}
-
-
-// ---------------------------------------------------------------------------
-// One-shot evaluation of many points (Fields.return_forces_cart / _cyl) in cell order:
-//   point_cell_hist_kernel  : cell of every point -> histogram (+ scan by the last CTA), cell id kept
-//   point_scatter_kernel    : 32-byte records {x, y, z, index} to their sorted slots, inverse permutation
-//   field_rec_kernel        : the field at the sorted records -> 64-byte result slots in sorted order (coalesced)
-//   field_gather_kernel     : caller's order: slot through the inverse permutation -> the eight SoA outputs (coalesced)
-// in chunks of g_bfe_field_sort_chunk points (bounded workspace).  Per 10^6 points: sort ~45 us + evaluation ~155 us + gather
-// ~30 us against 358 us for the evaluation in the caller's order -- for DISC-like point sets; see g_bfe_field_sort_min.
-// ---------------------------------------------------------------------------
-int g_bfe_field_sort_chunk = 4 << 20;   // option "field_sort_chunk": points per sort + evaluate + gather pass
-
-__global__ void __launch_bounds__(1024)
-point_cell_hist_kernel(EofGeom g, int ncell, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
-                       const double* __restrict__ z, int* __restrict__ hist, int* __restrict__ cell_start,
-                       int* __restrict__ cursor, unsigned int* __restrict__ counter, int* __restrict__ cellid) {
-    extern __shared__ int s_hist[];
-    __shared__ int s_wsum[32];
-    __shared__ bool s_last;
-    for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x)
-        cursor[(size_t)c * BFE_CURSOR_STRIDE] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int cell;
-        bfe_eof_cell_fast(g, __ldg(x + i), __ldg(y + i), __ldg(z + i), cell);     // ordering key only
-        if (cell < 0 || cell >= ncell) cell = 0;
-        atomicAdd(&s_hist[cell], 1);
-        cellid[i] = cell;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
-        int v = s_hist[c];
-        if (v) atomicAdd(&hist[c], v);
-    }
+    if (!s_last) return;
     __threadfence();
+    // up to 2048 blocks (nkeys <= 2^21): two totals per thread
+    const int nb = gridDim.x;
+    const int b0 = 2 * tid, b1 = 2 * tid + 1;
+    const int t0 = b0 < nb ? __ldcg(btot + b0) : 0, t1 = b1 < nb ? __ldcg(btot + b1) : 0;
+    int inc2 = t0 + t1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, off); if (lane >= off) inc2 += u; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int done = atomicAdd(counter, 1u);
-        s_last = (done == gridDim.x - 1);
+    if (lane == 31) s_w[warp] = inc2;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_w[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += u; }
+        s_w[lane] = w;
     }
     __syncthreads();
-    if (s_last) {
-        __threadfence();
-        bfe_block_scan_cells(ncell, hist, cell_start, s_hist, s_wsum);
-        if (threadIdx.x == 0) *counter = 0u;
-    }
+    const int ex2 = inc2 - (t0 + t1) + (warp > 0 ? s_w[warp - 1] : 0);
+    if (b0 < nb) bprefix[b0] = ex2;
+    if (b1 < nb) bprefix[b1] = ex2 + t0;
+    if (tid == 0) *counter = 0u;
 }
 
 __global__ void __launch_bounds__(256)
-point_scatter_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                     const int* __restrict__ cellid, const int* __restrict__ cell_start, int* __restrict__ cursor,
-                     double* __restrict__ rec4, int* __restrict__ inv) {
+perm_scatter_kernel(int64_t n, const int2* __restrict__ keyrank, const int* __restrict__ start,
+                    const int* __restrict__ bprefix, int* __restrict__ perm) {
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
-        const int cell = __ldg(cellid + i);
-        const int pos = __ldg(cell_start + cell) + atomicAdd(&cursor[(size_t)cell * BFE_CURSOR_STRIDE], 1);   // integer slot claim
-        bfe_st256(rec4 + 4 * (size_t)pos, px, py, pz, __longlong_as_double((long long)i));
+        const int2 kr = __ldcs(keyrank + i);
+        const int pos = __ldg(bprefix + (kr.x >> 10)) + __ldg(start + kr.x) + kr.y;
+        perm[pos] = (int)i;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fields.return_forces_cart / _cyl (potential.py:445-497 / 389-440) at the points of one chunk, in key order
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rec_scatter_kernel(int64_t n, const int2* __restrict__ keyrank, const int* __restrict__ start, const int* __restrict__ bprefix,
+                   const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                   double* __restrict__ rec4, int* __restrict__ inv) {
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 kr = __ldcs(keyrank + i);
+        const int pos = __ldg(bprefix + (kr.x >> 10)) + __ldg(start + kr.x) + kr.y;
+        bfe_st256(rec4 + 4 * (size_t)pos, __ldg(x + i), __ldg(y + i), __ldg(z + i), __longlong_as_double((long long)i));
         inv[i] = pos;
     }
 }
 
 template <int MCAP, int LCAP, bool CYL, bool F32>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, BFE_PERM_MINB)
 field_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
-                 const double* __restrict__ xi, const double* __restrict__ p0tab, const double* __restrict__ fac,
-                 int64_t n, const double* __restrict__ rec4, double crot, double srot, double* __restrict__ slot8) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double px, py, pz, id_;
-        bfe_ld256_nc(rec4 + 4 * (size_t)i, px, py, pz, id_);
-        const CartForce f = bfe_field_cart_blk<MCAP, LCAP, CYL, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
-        char* d = reinterpret_cast<char*>(slot8 + 8 * (size_t)i);
-        bfe_st256(d, f.fxd, f.fxh, f.fyd, f.fyh);
-        bfe_st256(d + 32, f.fzd, f.fzh, f.pd, f.ph);
+                 const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
+                 int64_t n, const double* __restrict__ rec4, double crot, double srot, double* __restrict__ slot8,
+                 unsigned int* __restrict__ ticket) {
+    __shared__ unsigned int s_tile;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const unsigned int ntile = (unsigned int)((n + 127) >> 7);
+    const unsigned int nticket = bfe_ticket_count(ntile);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        if (s_tile >= nticket) break;
+        const TileTicket tk = bfe_ticket_tiles(s_tile, ntile);
+        int64_t pos = (int64_t)tk.first * 128 + threadIdx.x;
+        double px = 0.0, py = 0.0, pz = 0.0, id_ = 0.0;
+        if (pos < n) bfe_ld256_nc(rec4 + 4 * (size_t)pos, px, py, pz, id_);
+        for (unsigned int u = 0; u < tk.count; ++u) {
+            const int64_t npos = pos + 128;
+            double nx = 0.0, ny = 0.0, nz = 0.0;
+            if (u + 1 < tk.count && npos < n) bfe_ld256_nc(rec4 + 4 * (size_t)npos, nx, ny, nz, id_);   // next tile's record in flight
+
+            if (pos < n) {
+                const CartForce f = bfe_field_cart_blk<MCAP, LCAP, CYL, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+                char* d = reinterpret_cast<char*>(slot8 + 8 * (size_t)pos);
+                bfe_st256(d, f.fxd, f.fxh, f.fyd, f.fyh);
+                bfe_st256(d + 32, f.fzd, f.fzh, f.pd, f.ph);
+            }
+            pos = npos; px = nx; py = ny; pz = nz;
+        }
     }
 }
 
 __global__ void __launch_bounds__(256)
 field_gather_kernel(int64_t n, int64_t ntot, const int* __restrict__ inv, const double* __restrict__ slot8,
                     double* __restrict__ out8) {
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const char* s = reinterpret_cast<const char*>(slot8 + 8 * (size_t)__ldg(inv + i));
         double a0, a1, a2, a3, b0, b1, b2, b3;
@@ -304,73 +251,345 @@ field_gather_kernel(int64_t n, int64_t ntot, const int* __restrict__ inv, const 
     }
 }
 
-int g_bfe_field_sort_min = 0;           // option "field_sort_min": smallest point set evaluated in cell order; 0 (default): never --
-                                        // measured per 10^6 points (profiles/field_sort_probe.py): disc points 358 -> 284 us, but halo points
-                                        // 349 -> 437 us (hot edge cells serialise the slot claims, no SL coherence inside a cell) and no gain
-                                        // with FP32 tables: the sort + gather (~90 us) only pays for disc-like sets
+// ---------------------------------------------------------------------------
+// integrate.leapfrog_integrate (integrate.py:53-190) on orbit records that stay in the caller's order
+// ---------------------------------------------------------------------------
+struct __align__(32) OrbRec {            // 96 bytes = three full sectors
+    double x, y, z, vx;
+    double vy, vz, dt, ax;
+    double ay, az, pad0, pad1;
+};
 
-int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
-                           double crot, double srot, double* out8, bool cyl, cudaStream_t stream) {
-    const int ncell = he->g.numx * he->g.numy;
-    const int64_t chunk_opt = g_bfe_field_sort_chunk > 0 ? g_bfe_field_sort_chunk : (4 << 20);
-    const int64_t chunk = n < chunk_opt ? n : chunk_opt;
+__global__ void __launch_bounds__(256)
+orbit_pack_key_kernel(EofGeom ge, SlGeom gs, int ncell, int subbits, int64_t n, const double* __restrict__ state6,
+                      double dt, const double* __restrict__ dt_orbit, OrbRec* __restrict__ rec, int* __restrict__ hist,
+                      int2* __restrict__ keyrank) {
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const int64_t nround = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool on = i < n;
+        int key = 0;
+        if (on) {
+            const double px = state6[i], py = state6[n + i], pz = state6[2 * n + i];
+            char* dst = reinterpret_cast<char*>(rec + i);
+            bfe_st256(dst, px, py, pz, state6[3 * n + i]);
+            bfe_st256(dst + 32, state6[4 * n + i], state6[5 * n + i], dt_orbit ? dt_orbit[i] : dt, 0.0);
+            bfe_st256(dst + 64, 0.0, 0.0, 0.0, 0.0);
+            key = bfe_point_key(ge, gs, ncell, subbits, px, py, pz);
+        }
+        const int rank = bfe_claim_rank(hist, key, on);
+        if (on) keyrank[i] = make_int2(key, rank);
+    }
+}
+
+// nsteps velocity-Verlet steps step0+1 .. step0+nsteps of every orbit, in key order.  first: the acceleration at step0 is
+// evaluated here (otherwise it is the one the previous launch left in the record: the same bits).  rekey: key and rank of
+// the end position for the next re-sort.
+template <int MCAP, int LCAP, bool F32>
+__global__ void __launch_bounds__(128, BFE_PERM_MINB)
+leapfrog_perm_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
+                     const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
+                     int64_t norbit, int64_t step0, int nsteps, double rotfreq, int first, int rekey, int ncell, int subbits,
+                     const int* __restrict__ perm, OrbRec* __restrict__ rec, int* __restrict__ hist,
+                     int2* __restrict__ keyrank, unsigned int* __restrict__ ticket) {
+    __shared__ unsigned int s_tile;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const unsigned int ntile = (unsigned int)((norbit + 127) >> 7);
+    const unsigned int nticket = bfe_ticket_count(ntile);
+    const double w = BFE_TWOPI * rotfreq;                    // barpos = 2 pi rotfreq (k dt), integrate.py:94-97
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        if (s_tile >= nticket) break;
+        const TileTicket tk = bfe_ticket_tiles(s_tile, ntile);
+        int64_t pos = (int64_t)tk.first * 128 + threadIdx.x;
+        int i = pos < norbit ? __ldg(perm + pos) : -1;
+        for (unsigned int u = 0; u < tk.count; ++u) {
+            const int64_t npos = pos + 128;
+            const int ni = (u + 1 < tk.count && npos < norbit) ? __ldg(perm + npos) : -1;
+            int key = 0;
+            if (i >= 0) {
+                double px, py, pz, vx, vy, vz, dt, ax, ay, az, u0, u1;
+                {
+                    // plain (coherent) loads: the record is rewritten in place by this kernel
+                    const double4* r4 = reinterpret_cast<const double4*>(rec + i);
+                    const double4 a = r4[0], b = r4[1], c = r4[2];
+                    px = a.x; py = a.y; pz = a.z; vx = a.w; vy = b.x; vz = b.y; dt = b.z; ax = b.w; ay = c.x; az = c.y;
+                    u0 = c.z; u1 = c.w;
+                }
+                const double hdt2 = 0.5 * (dt * dt);
+                double srot, crot;
+                if (first) {
+                    sincos(w * ((double)step0 * dt), &srot, &crot);
+                    const CartForce f = bfe_field_cart_blk<MCAP, LCAP, false, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+                    ax = f.fxd + f.fxh; ay = f.fyd + f.fyh; az = f.fzd + f.fzh;
+                }
+                for (int k = 1; k <= nsteps; ++k) {
+                    const int64_t step = step0 + k;
+                    px = px + (vx * dt) + (ax * hdt2);                   // integrate.py:129-131
+                    py = py + (vy * dt) + (ay * hdt2);
+                    pz = pz + (vz * dt) + (az * hdt2);
+                    sincos(w * ((double)step * dt), &srot, &crot);
+                    const CartForce f = bfe_field_cart_blk<MCAP, LCAP, false, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
+                    const double bx = f.fxd + f.fxh, by = f.fyd + f.fyh, bz = f.fzd + f.fzh;             // 134-138
+                    vx = vx + (0.5 * (ax + bx) * dt);                    // 141-143
+                    vy = vy + (0.5 * (ay + by) * dt);
+                    vz = vz + (0.5 * (az + bz) * dt);
+                    ax = bx; ay = by; az = bz;
+                }
+                char* d = reinterpret_cast<char*>(rec + i);
+                bfe_st256(d, px, py, pz, vx);
+                bfe_st256(d + 32, vy, vz, dt, ax);
+                bfe_st256(d + 64, ay, az, u0, u1);
+                // key of the NEXT evaluation point: the drift of the following step (the same expression, so the same bits)
+                // -- orbits cross an SL interval per step, so a key taken at the current position would be stale at once
+                if (rekey) key = bfe_point_key(ge, gs, ncell, subbits, px + (vx * dt) + (ax * hdt2), py + (vy * dt) + (ay * hdt2),
+                                               pz + (vz * dt) + (az * hdt2));
+            }
+            if (rekey) {
+                const int rank = bfe_claim_rank(hist, key, i >= 0);
+                if (i >= 0) keyrank[i] = make_int2(key, rank);
+            }
+            i = ni; pos = npos;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+orbit_unpack_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restrict__ state6, int* __restrict__ nsteps_out,
+                    int nint) {
+    bfe_pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a0, a1, a2, a3, b0, b1, b2, b3;
+        bfe_ld256_nc(rec + i, a0, a1, a2, a3);
+        bfe_ld256_nc(reinterpret_cast<const char*>(rec + i) + 32, b0, b1, b2, b3);
+        state6[i] = a0; state6[n + i] = a1; state6[2 * n + i] = a2;
+        state6[3 * n + i] = a3; state6[4 * n + i] = b0; state6[5 * n + i] = b1;
+        if (nsteps_out) nsteps_out[i] = nint;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between re-sorts of a large orbit batch (0: plain kernel)
+int g_bfe_orbit_sort_min = 65536;       // option "orbit_sort_min": smallest batch on the key-ordered path
+int g_bfe_field_sort_chunk = 1 << 20;   // option "field_sort_chunk": points per sort + evaluate pass (L2-resident working set)
+int g_bfe_field_sort_min = 65536;       // option "field_sort_min": smallest point set evaluated in key order (0: never)
+
+static size_t os_align(size_t v) { return (v + 255) / 256 * 256; }
+
+struct KeySortWs {
+    int ncell, subbits, nkeys, nblk;
+    int* hist; int* start; int* btot; int* bprefix; unsigned int* counter;     // counter[0]: scan's last-CTA count, [1], [2]: tile tickets
+    int2* keyrank[2]; int* perm[2];  // perm doubles as the inverse permutation of the point path
+    double* rec4[2]; double* slot8[2];   // point path only, two chunks in flight; slot8 aliases keyrank (dead after the scatter)
+};
+
+// workspace in he->orbit_ws, grown on demand: header + per item 12 bytes (orbits: keyrank, perm) or 2 x 100 bytes (points)
+static int keysort_ws(bfe_eof* he, int64_t cap_need, bool points, KeySortWs& w) {
+    w.ncell = he->g.numx * he->g.numy;
+    w.subbits = BFE_KEY_SUBBITS;
+    while (w.subbits > 0 && ((int64_t)w.ncell << w.subbits) > ((int64_t)1 << 21)) --w.subbits;
+    if (((int64_t)w.ncell << w.subbits) > ((int64_t)1 << 21)) return BFE_ERR_UNSUPPORTED;
+    w.nkeys = w.ncell << w.subbits;
+    w.nblk = (w.nkeys + BFE_SCAN_BLOCK - 1) / BFE_SCAN_BLOCK;
     const size_t o_hist = 0;
-    const size_t o_start = os_align(o_hist + sizeof(int) * ncell);
-    const size_t o_cur = os_align(o_start + sizeof(int) * (ncell + 1));
-    const size_t o_cid = os_align(o_cur + sizeof(int) * (size_t)ncell * BFE_CURSOR_STRIDE);
-    // the orbit workspace is shared: header + cell ids + 2 x 64 B per unit covers cell ids + inv + 32-B records + 64-B slots
-    if (chunk > he->orbit_cap || !he->orbit_ws) {
-        if (he->orbit_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_ws)); he->orbit_ws = nullptr; }
-        const int64_t cap = chunk + chunk / 8 + 1024;
-        const size_t o_a = os_align(o_cid + sizeof(int) * (size_t)cap);
-        BFE_CUDA(cudaMalloc(&he->orbit_ws, o_a + 2 * sizeof(OrbRec) * (size_t)cap));
-        BFE_CUDA(cudaMemset(he->orbit_ws, 0, o_cid));
+    const size_t o_start = os_align(o_hist + sizeof(int) * (size_t)w.nkeys);
+    const size_t o_btot = os_align(o_start + sizeof(int) * (size_t)w.nkeys);
+    const size_t o_bpre = os_align(o_btot + sizeof(int) * (size_t)w.nblk);
+    const size_t o_ctr = os_align(o_bpre + sizeof(int) * (size_t)(w.nblk + 1));
+    const size_t o_item = os_align(o_ctr + 64);
+    const size_t a64 = os_align(64 * (size_t)cap_need), a32 = os_align(32 * (size_t)cap_need), a8 = os_align(8 * (size_t)cap_need),
+                 a4 = os_align(4 * (size_t)cap_need);
+    const int64_t need = points ? (int64_t)(2 * (a64 + a32 + a4)) : (int64_t)(a8 + a4);
+    if (need > he->orbit_cap || !he->orbit_ws) {          // orbit_cap: BYTES available for items
+        if (he->orbit_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_ws)); he->orbit_ws = nullptr; he->orbit_cap = 0; }
+        const int64_t bytes = need + need / 8 + 4096;
+        BFE_CUDA(cudaMalloc(&he->orbit_ws, o_item + (size_t)bytes));
+        BFE_CUDA(cudaMemset(he->orbit_ws, 0, o_item));
         BFE_CUDA(cudaDeviceSynchronize());
-        he->orbit_cap = cap;
+        he->orbit_cap = bytes;
     }
     char* b = (char*)he->orbit_ws;
-    int* hist = (int*)(b + o_hist); int* cell_start = (int*)(b + o_start); int* cursor = (int*)(b + o_cur);
-    int* cellid = (int*)(b + o_cid);
-    const size_t o_a = os_align(o_cid + sizeof(int) * (size_t)he->orbit_cap);
-    double* slot8 = (double*)(b + o_a);                                          // 64 B per point
-    double* rec4 = (double*)(b + o_a + sizeof(OrbRec) * (size_t)he->orbit_cap);  // 32 B per point
-    int* inv = (int*)(b + o_a + sizeof(OrbRec) * (size_t)he->orbit_cap + 32 * (size_t)he->orbit_cap);   // 4 B per point
+    w.hist = (int*)(b + o_hist); w.start = (int*)(b + o_start); w.btot = (int*)(b + o_btot); w.bprefix = (int*)(b + o_bpre);
+    w.counter = (unsigned int*)(b + o_ctr);
+    char* it = b + o_item;
+    if (points) {
+        for (int k = 0; k < 2; ++k) {
+            char* q = it + (size_t)k * (a64 + a32 + a4);
+            w.slot8[k] = (double*)q;  w.keyrank[k] = (int2*)q;
+            w.rec4[k] = (double*)(q + a64);
+            w.perm[k] = (int*)(q + a64 + a32);
+        }
+    } else {
+        w.keyrank[0] = w.keyrank[1] = (int2*)it;
+        w.perm[0] = w.perm[1] = (int*)(it + a8);
+        w.rec4[0] = w.rec4[1] = nullptr; w.slot8[0] = w.slot8[1] = nullptr;
+    }
+    return BFE_OK;
+}
 
-    const bool f32 = g_bfe_table_fp32 != 0;
-    int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
+// aux stream + events of the two-stream point pipeline (lazily made, owned by the EOF handle)
+struct FieldPipe { cudaStream_t aux; cudaEvent_t ev_in, ev_k[2], ev_e[2], ev_out; };
+
+void bfe_field_pipe_destroy(void* p_) {
+    FieldPipe* p = (FieldPipe*)p_;
+    if (!p) return;
+    cudaEventDestroy(p->ev_in); cudaEventDestroy(p->ev_out);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(p->ev_k[k]); cudaEventDestroy(p->ev_e[k]); }
+    cudaStreamDestroy(p->aux);
+    delete p;
+}
+
+static int field_pipe(bfe_eof* he, FieldPipe*& out) {
+    if (!he->field_pipe) {
+        FieldPipe* p = new FieldPipe();
+        cudaError_t e = cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaEventCreateWithFlags(&p->ev_k[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_e[k], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) { bfe_set_cuda_error(e, "field_pipe"); delete p; return BFE_ERR_CUDA; }
+        he->field_pipe = p;
+    }
+    out = (FieldPipe*)he->field_pipe;
+    return BFE_OK;
+}
+
+static int grid_cap(int64_t n, int block, int cap) {
+    int64_t g = (n + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+#define KS_LAUNCH(name, kern, grid, block, ...) KS_LAUNCH_ON(stream, name, kern, grid, block, __VA_ARGS__)
+#define KS_LAUNCH_ON(strm, name, kern, grid, block, ...)                                                  \
+    do {                                                                                                  \
+        cudaError_t _e = bfe_launch(kern, dim3(grid), dim3(block), 0, strm, nullptr, 0, __VA_ARGS__);     \
+        if (_e != cudaSuccess) { bfe_set_cuda_error(_e, name); return BFE_ERR_CUDA; }                     \
+        bfe_count_launch(1);                                                                              \
+    } while (0)
+
+// Two chunks in flight: the caller's stream runs the FP64-bound evaluation kernels (three CTAs per SM, so a quarter of
+// the register file stays free), an internal stream runs the latency-bound support kernels of the neighbouring chunks
+// (key + scan + scatter of chunk c+1, gather of chunk c-1) underneath them; events order the two (serialised, the
+// support kernels were 30 % of the pass: ncu launch list profiles/r02_launches_points_*.csv).
+int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
+                           double crot, double srot, double* out8, bool cyl, cudaStream_t stream) {
+    const int64_t chunk_opt = g_bfe_field_sort_chunk > 0 ? g_bfe_field_sort_chunk : (1 << 19);
+    const int64_t chunk = n < chunk_opt ? n : chunk_opt;
+    KeySortWs w;
+    int rc = keysort_ws(he, chunk, true, w);
+    if (rc != BFE_OK) return rc;
+    FieldPipe* fp = nullptr;
+    rc = field_pipe(he, fp);
+    if (rc != BFE_OK) return rc;
+    const bool f32 = bfe_use_fp32(he);
+    rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
     if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
     if (rc != BFE_OK) return rc;
     const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
     const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
-    const int per = (ncell + 1023) / 1024;
-    const size_t ss = sizeof(int) * (size_t)per * 1024;
-    if (ss > 200 * 1024) return BFE_ERR_UNSUPPORTED;
-    if (ss > 48 * 1024)
-        BFE_CUDA(cudaFuncSetAttribute(point_cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
-    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
-        const int64_t m = (n - c0) < chunk ? (n - c0) : chunk;
-        int ghist = (int)((m + 2047) / 2048);
-        if (ghist > he->num_sms) ghist = he->num_sms;
-        if (ghist < 1) ghist = 1;
-        int g256 = (int)((m + 255) / 256);
-        if (g256 > he->num_sms * 8) g256 = he->num_sms * 8;
-        int64_t need = (m + 127) / 128, cap = (int64_t)he->num_sms * 16;
-        const int geval = (int)(need < cap ? need : cap);
-        point_cell_hist_kernel<<<ghist, 1024, ss, stream>>>(he->g, ncell, m, x + c0, y + c0, z + c0, hist, cell_start, cursor,
-                                                           he->counter, cellid);
-        BFE_LAUNCH_CHECK("point_cell_hist_kernel");
-        point_scatter_kernel<<<g256, 256, 0, stream>>>(m, x + c0, y + c0, z + c0, cellid, cell_start, cursor, rec4, inv);
-        BFE_LAUNCH_CHECK("point_scatter_kernel");
-#define FIELD_REC(L, C, F) field_rec_kernel<6, L, C, F><<<geval, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, hs->fac, m, \
-                                                                                rec4, crot, srot, slot8)
+    const SlFacP facp = bfe_sl_facp(hs);
+    const int kt = bfe_kt_begin("field_sorted_pass", stream);
+    cudaStream_t aux = fp->aux;
+    BFE_CUDA(cudaEventRecord(fp->ev_in, stream));
+    BFE_CUDA(cudaStreamWaitEvent(aux, fp->ev_in, 0));
+    const int64_t nchunk = (n + chunk - 1) / chunk;
+    auto sort_chunk = [&](int64_t c) -> int {
+        const int64_t c0 = c * chunk, m = (n - c0) < chunk ? (n - c0) : chunk;
+        const int b = (int)(c & 1);
+        const int g256 = grid_cap(m, 256, he->num_sms * 4);
+        KS_LAUNCH_ON(aux, "pt_key_kernel", pt_key_kernel, g256, 256, he->g, hs->g, w.ncell, w.subbits, m, x + c0, y + c0, z + c0,
+                     w.hist, w.keyrank[b]);
+        KS_LAUNCH_ON(aux, "key_scan_kernel", key_scan_kernel, w.nblk, BFE_SCAN_BLOCK, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
+                     w.counter, b);
+        KS_LAUNCH_ON(aux, "rec_scatter_kernel", rec_scatter_kernel, g256, 256, m, (const int2*)w.keyrank[b], (const int*)w.start,
+                     (const int*)w.bprefix, x + c0, y + c0, z + c0, w.rec4[b], w.perm[b]);
+        BFE_CUDA(cudaEventRecord(fp->ev_k[b], aux));
+        return BFE_OK;
+    };
+    rc = sort_chunk(0);
+    if (rc != BFE_OK) return rc;
+    for (int64_t c = 0; c < nchunk; ++c) {
+        const int64_t c0 = c * chunk, m = (n - c0) < chunk ? (n - c0) : chunk;
+        const int b = (int)(c & 1);
+        if (c + 1 < nchunk) { rc = sort_chunk(c + 1); if (rc != BFE_OK) return rc; }
+        BFE_CUDA(cudaStreamWaitEvent(stream, fp->ev_k[b], 0));
+        const int geval = grid_cap(m, 128, he->num_sms * BFE_PERM_MINB);
+#define FIELD_REC(L, C, F) KS_LAUNCH("field_rec_kernel", (field_rec_kernel<6, L, C, F>), geval, 128, he->g, G4, hs->g, A3,      \
+                                     (const double*)hs->xi, (const double*)hs->p0, facp, m, (const double*)w.rec4[b], crot, srot, \
+                                     w.slot8[b], w.counter + 1 + b)
 #define FIELD_REC2(L, C) do { if (f32) FIELD_REC(L, C, true); else FIELD_REC(L, C, false); } while (0)
         if (hs->g.lmax == 4) { if (cyl) FIELD_REC2(4, true); else FIELD_REC2(4, false); }
         else                 { if (cyl) FIELD_REC2(6, true); else FIELD_REC2(6, false); }
 #undef FIELD_REC2
 #undef FIELD_REC
-        BFE_LAUNCH_CHECK("field_rec_kernel");
-        field_gather_kernel<<<g256, 256, 0, stream>>>(m, n, inv, slot8, out8 + c0);
-        BFE_LAUNCH_CHECK("field_gather_kernel");
+        BFE_CUDA(cudaEventRecord(fp->ev_e[b], stream));
+        BFE_CUDA(cudaStreamWaitEvent(aux, fp->ev_e[b], 0));
+        const int g256 = grid_cap(m, 256, he->num_sms * 4);
+        KS_LAUNCH_ON(aux, "field_gather_kernel", field_gather_kernel, g256, 256, m, n, (const int*)w.perm[b],
+                     (const double*)w.slot8[b], out8 + c0);
     }
+    BFE_CUDA(cudaEventRecord(fp->ev_out, aux));
+    BFE_CUDA(cudaStreamWaitEvent(stream, fp->ev_out, 0));
+    bfe_kt_end(kt, stream);
+    return BFE_OK;
+}
+
+// key-ordered integration; the caller has checked eligibility (contracted handles, mmax <= 6, lmax 4 or 6, no trajectory
+// output, no apocentre counting)
+int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,
+                        double rotfreq, double* state6, int32_t* nsteps_out, cudaStream_t stream) {
+    KeySortWs w;
+    int rc = keysort_ws(he, norbit, false, w);
+    if (rc != BFE_OK) return rc;
+    if (norbit > he->orbit_rec_cap || !he->orbit_rec) {
+        if (he->orbit_rec) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_rec)); he->orbit_rec = nullptr; he->orbit_rec_cap = 0; }
+        const int64_t cap = norbit + norbit / 8 + 1024;
+        BFE_CUDA(cudaMalloc(&he->orbit_rec, sizeof(OrbRec) * (size_t)cap));
+        he->orbit_rec_cap = cap;
+    }
+    OrbRec* rec = (OrbRec*)he->orbit_rec;
+    const bool f32 = bfe_use_fp32(he);
+    rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
+    if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
+    if (rc != BFE_OK) return rc;
+    const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
+    const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+    const int g256 = grid_cap(norbit, 256, he->num_sms * 8);
+    const int glf = grid_cap(norbit, 128, he->num_sms * BFE_PERM_MINB);
+    const int K = g_bfe_orbit_resort > 0 ? g_bfe_orbit_resort : 4;
+    const SlFacP facp = bfe_sl_facp(hs);
+    const int kt = bfe_kt_begin("leapfrog_sorted_pass", stream);
+
+    KS_LAUNCH("orbit_pack_key_kernel", orbit_pack_key_kernel, g256, 256, he->g, hs->g, w.ncell, w.subbits, norbit,
+              (const double*)state6, dt, dt_orbit, rec, w.hist, w.keyrank[0]);
+    for (int64_t step0 = 0; step0 < nint - 1; step0 += K) {
+        const int64_t left = nint - 1 - step0;
+        const int k = (int)(left < K ? left : K);
+        const int last = (step0 + k >= nint - 1) ? 1 : 0;
+        KS_LAUNCH("key_scan_kernel", key_scan_kernel, w.nblk, BFE_SCAN_BLOCK, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
+                  w.counter, 0);
+        KS_LAUNCH("perm_scatter_kernel", perm_scatter_kernel, g256, 256, norbit, (const int2*)w.keyrank[0],
+                  (const int*)w.start, (const int*)w.bprefix, w.perm[0]);
+#define LEAP_PERM(L, F) KS_LAUNCH("leapfrog_perm_kernel", (leapfrog_perm_kernel<6, L, F>), glf, 128, he->g, G4, hs->g, A3,     \
+                                  (const double*)hs->xi, (const double*)hs->p0, facp, norbit, step0, k,                        \
+                                  rotfreq, (int)(step0 == 0), (int)!last, w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, \
+                                  w.keyrank[0], w.counter + 1)
+        if (hs->g.lmax == 4) { if (f32) LEAP_PERM(4, true); else LEAP_PERM(4, false); }
+        else                 { if (f32) LEAP_PERM(6, true); else LEAP_PERM(6, false); }
+#undef LEAP_PERM
+    }
+    KS_LAUNCH("orbit_unpack_kernel", orbit_unpack_kernel, g256, 256, norbit, (const OrbRec*)rec, state6, (int*)nsteps_out,
+              (int)nint);
+    bfe_kt_end(kt, stream);
     return BFE_OK;
 }

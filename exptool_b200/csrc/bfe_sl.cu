@@ -496,7 +496,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
-    h->sort_cap = 0; h->sort_ws = nullptr;
+    h->sort_cap = 0; h->sort_ws = nullptr; h->table_fp32 = -1;
     BFE_CUDA(cudaMemsetAsync(h->a_con, 0, nr * h->kpad * 2 * sizeof(double), stream));
     BFE_CUDA(cudaMemcpyAsync(h->xi, xi, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     BFE_CUDA(cudaMemcpyAsync(h->p0, p0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -596,7 +596,7 @@ extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, co
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
     if (g_bfe_blk_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
-        const bool f32 = g_bfe_table_fp32 != 0;
+        const bool f32 = bfe_use_fp32(h);
         int rc = f32 ? bfe_sl_ensure_a3f(h, stream) : bfe_sl_ensure_a3(h, stream);
         if (rc != BFE_OK) return rc;
         const void* A3 = f32 ? (const void*)h->a3f : (const void*)h->a3;

@@ -56,20 +56,26 @@ def set_option(name, value):
     _lib.check(_lib.load().bfe_set_option(name.encode(), int(value)))
 
 
-class table_precision(object):
-    """Context manager: option 'table_fp32' on for the enclosed per-point field calls, off again afterwards."""
+def get_option(name):
+    """bfe_get_option: current value of a runtime option (so that a caller can restore what it changes)."""
+    v = int(_lib.load().bfe_get_option(name.encode()))
+    if v == -2147483648:
+        raise KeyError(name)
+    return v
 
-    def __init__(self, fp32):
+
+class table_precision(object):
+    """Deprecated no-op context manager (round 1 toggled the process-wide option around each call, which raced between
+    threads and dropped a user's own setting).  Table precision is now a property of the HANDLE:
+    EOFTables.set_table_fp32 / SLTables.set_table_fp32 (bfe_eof_set_table_fp32)."""
+
+    def __init__(self, fp32=False):
         self.fp32 = bool(fp32)
 
     def __enter__(self):
-        if self.fp32:
-            set_option('table_fp32', 1)
         return self
 
     def __exit__(self, *exc):
-        if self.fp32:
-            set_option('table_fp32', 0)
         return False
 
 
@@ -125,6 +131,11 @@ class EOFTables(object):
         except Exception:
             pass
 
+    def set_table_fp32(self, value):
+        """Table precision of the per-point field kernels for THIS handle (bfe_eof_set_table_fp32): True / False, or None to
+        follow the process option 'table_fp32'.  The combined-field calls (field_force_*, leapfrog) read this handle."""
+        _lib.check(self.lib.bfe_eof_set_table_fp32(self.h, -1 if value is None else int(bool(value))))
+
     def get_pot(self, r, z, fac=1.0):
         """eof.get_pot (eof.py:430-457): Vc, Vs as (mmax+1, norder, n) device tensors."""
         r, z = dev(r), dev(z)
@@ -141,6 +152,7 @@ class EOFTables(object):
         """
         import copy
         other = copy.copy(self)
+        other.h = None                 # never let a half-built copy destroy the parent's handle
         h = C.c_void_p()
         _lib.check(self.lib.bfe_eof_clone(self.h, _stream(), C.byref(h)))
         other.h = h
@@ -304,6 +316,10 @@ class SLTables(object):
                 self.h = None
         except Exception:
             pass
+
+    def set_table_fp32(self, value):
+        """Table precision of the SL-only evaluation kernels for THIS handle (bfe_sl_set_table_fp32)."""
+        _lib.check(self.lib.bfe_sl_set_table_fp32(self.h, -1 if value is None else int(bool(value))))
 
     def accumulate(self, x, y, z, m, no_odd=False):
         """spheresl.compute_coefficients_solitary (spheresl.py:567-656) -> expcoef ((lmax+1)^2, nmax)."""

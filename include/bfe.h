@@ -61,6 +61,14 @@ uint64_t bfe_launch_count(void);
  * 0 = auto (bin-sorted kernels from "sort_min_particles" particles up, direct kernels below),
  * 1 = direct, 2 = sorted. */
 int bfe_set_option(const char* name, int value);
+/* current value of an option; INT_MIN if the name is unknown */
+int bfe_get_option(const char* name);
+
+/* Table precision of the per-point field kernels (bfe_field_force_*, bfe_leapfrog*, bfe_sl_force_*) PER HANDLE:
+ * 1 = the contracted tables are held as float (north_star: "<= 1e-5 where FP32 table interpolation is used"), 0 = FP64,
+ * -1 (initial) = follow the process option "table_fp32".  The combined-field calls read the EOF handle's setting. */
+int bfe_eof_set_table_fp32(bfe_eof* h, int value);
+int bfe_sl_set_table_fp32(bfe_sl* h, int value);
 
 /* With option "time_kernels" = 1 the EOF step kernels are bracketed by CUDA events on their stream;
  * bfe_kernel_time_ms(name) synchronises on and returns the duration (ms) of the latest launch of that kernel

@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r02_pytest3.log 2>&1; tail -5 gpurun_out/r02_pytest3.log
+python profiles/r02_field_probe.py --resorts 1,2,3,4 --steps 100 --chunks 131072,262144,524288,1048576 --out gpurun_out/r02_field_probe_c.json > gpurun_out/r02_probe_c.log 2>&1; tail -3 gpurun_out/r02_probe_c.log
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_orbit_c.csv python profiles/r02_field_probe.py --norb 1000000 --steps 12 --skip-points --resorts 1 > gpurun_out/ncu3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_points_c.csv python profiles/r02_field_probe.py --n 1000000 --skip-orbits --chunks 524288 > gpurun_out/ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:leapfrog_perm_kernel -s 6 -c 1 -o gpurun_out/r02_leapfrog_perm_c python profiles/r02_field_probe.py --norb 1000000 --steps 40 --skip-points --resorts 1 > gpurun_out/ncu5.log 2>&1; tail -2 gpurun_out/ncu5.log
+ncu --set full --clock-control none --import-source on -k regex:field_rec_kernel -s 2 -c 2 -o gpurun_out/r02_field_rec_c python profiles/r02_field_probe.py --n 1000000 --skip-orbits --chunks 524288 > gpurun_out/ncu6.log 2>&1; tail -2 gpurun_out/ncu6.log

@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r02_pytest4.log 2>&1; tail -5 gpurun_out/r02_pytest4.log
+python profiles/r02_field_probe.py --resorts 2,3,4,6 --steps 100 --chunks 262144,524288,1048576 --out gpurun_out/r02_field_probe_d.json > gpurun_out/r02_probe_d.log 2>&1; tail -3 gpurun_out/r02_probe_d.log
+BFE_LIB=$PWD/exptool_b200/libbfe_minb4.so python profiles/r02_field_probe.py --resorts 3,4 --steps 100 --chunks 524288,1048576 --out gpurun_out/r02_field_probe_d_minb4.json > gpurun_out/r02_probe_d4.log 2>&1; tail -3 gpurun_out/r02_probe_d4.log
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_orbit_d.csv python profiles/r02_field_probe.py --norb 1000000 --steps 14 --skip-points --resorts 4 > gpurun_out/ncu3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_launches_points_d.csv python profiles/r02_field_probe.py --n 1000000 --skip-orbits --chunks 524288 > gpurun_out/ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:leapfrog_perm_kernel -s 3 -c 1 -o gpurun_out/r02_leapfrog_perm_d python profiles/r02_field_probe.py --norb 1000000 --steps 40 --skip-points --resorts 4 > gpurun_out/ncu5.log 2>&1; tail -2 gpurun_out/ncu5.log
+ncu --set full --clock-control none --import-source on -k regex:field_rec_kernel -s 2 -c 2 -o gpurun_out/r02_field_rec_d python profiles/r02_field_probe.py --n 1000000 --skip-orbits --chunks 524288 > gpurun_out/ncu6.log 2>&1; tail -2 gpurun_out/ncu6.log

@@ -597,6 +597,7 @@ def test_cell_sorted_field_and_leapfrog_paths(ops, name):
     plain_s, _, plain_n = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, meta['dt'], rotfreq=meta['rotfreq'])
     dts = np.full(d['pos0'].shape[1], meta['dt']) * (1.0 + 0.1 * np.arange(d['pos0'].shape[1]))
     plain_d, _, _ = ops.leapfrog(E, H, d['pos0'], d['vel0'], nint, dts, rotfreq=meta['rotfreq'])
+    saved = {k: ops.get_option(k) for k in ('field_sort_min', 'field_sort_chunk', 'orbit_sort_min', 'orbit_resort', 'table_fp32')}
     try:
         ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 7)
         ops.set_option('orbit_sort_min', 1); ops.set_option('orbit_resort', 4)
@@ -620,5 +621,48 @@ def test_cell_sorted_field_and_leapfrog_paths(ops, name):
                 assert relerr(sc.cpu().numpy(), plain_c.cpu().numpy()) < FP32_TABLE_TOL
                 assert relerr(ss.cpu().numpy(), plain_s.cpu().numpy()) < 10 * FP32_TABLE_TOL
     finally:
-        ops.set_option('field_sort_min', 0); ops.set_option('field_sort_chunk', 4 << 20)
-        ops.set_option('orbit_sort_min', 400000); ops.set_option('orbit_resort', 16); ops.set_option('table_fp32', 0)
+        for k, v in saved.items():
+            ops.set_option(k, v)
+
+
+@pytest.mark.parametrize('lmax', [4, 6])
+def test_key_ordered_paths_at_size(ops, lmax):
+    """The key-ordered evaluation (composite (EOF cell, SL interval) key, two chunks in flight on two
+    streams; bfe_orbit_sort.cu) on 1.5e5 mixed disc + halo points in uneven chunks, and the re-sorted leapfrog on 3e4 orbits:
+    bit-identical to the caller-order kernels (same per-point arithmetic), for re-sort intervals 1, 3 and per-orbit steps."""
+    import torch
+    meta = dict(eof_params={}, sl_params=dict(lmax=lmax), kind='smooth', seed=0)
+    pe, T, g = eof_tables(meta)
+    ps, ev, ef, xi, p0, d0 = sl_tables(meta, seed_offset=1)
+    E, H = make_eof(ops, T, g), make_sl(ops, ps, ev, ef, xi, p0, d0)
+    xd, yd, zd, md = S.exponential_disc(90000, 11)
+    xh, yh, zh, mh = S.hernquist_halo(60001, 12)
+    c, s_ = E.accumulate(xd, yd, zd, md)
+    E.contract(c * 0.025, s_ * 0.025)
+    H.contract(H.accumulate(xh, yh, zh, mh))
+    x = np.concatenate([xd, xh]); y = np.concatenate([yd, yh]); z = np.concatenate([zd, zh])
+    keys = ('field_sort_min', 'field_sort_chunk', 'orbit_sort_min', 'orbit_resort')
+    saved = {k: ops.get_option(k) for k in keys}
+    try:
+        ops.set_option('field_sort_min', 0); ops.set_option('orbit_resort', 0)
+        ref_c = ops.field_force_cart(E, H, x, y, z, rotpos=0.3)
+        ref_y = ops.field_force_cyl(E, H, x, y, z, rotpos=-1.1)
+        norb, nint = 30001, 26
+        pos0 = np.stack([xd[:norb], yd[:norb], zd[:norb]])
+        R = np.sqrt(pos0[0] ** 2 + pos0[1] ** 2) + 1e-9
+        vel0 = np.stack([-pos0[1] / R, pos0[0] / R, 0.05 * np.cos(np.arange(norb))]) * 1.3
+        dts = 3e-4 * (1.0 + 0.5 * np.sin(np.arange(norb)))
+        ref_s, _, ref_n = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
+        ref_d, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
+        ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 40000); ops.set_option('orbit_sort_min', 1)
+        assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref_c)
+        assert torch.equal(ops.field_force_cyl(E, H, x, y, z, rotpos=-1.1), ref_y)
+        for K in (1, 3):
+            ops.set_option('orbit_resort', K)
+            st, _, ns = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
+            assert torch.equal(st, ref_s) and torch.equal(ns, ref_n), K
+            st, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
+            assert torch.equal(st, ref_d), K
+    finally:
+        for k, v in saved.items():
+            ops.set_option(k, v)
