@@ -41,6 +41,7 @@ SIGNATURES = {
     'bfe_set_option': (_INT, [C.c_char_p, _INT]),
     'bfe_get_option': (_INT, [C.c_char_p]),
     'bfe_kernel_time_ms': (C.c_double, [C.c_char_p]),
+    'bfe_fp64_peak': (_INT, [_INT, C.POINTER(C.c_double), _P]),
     'bfe_eof_set_table_fp32': (_INT, [_P, _INT]),
     'bfe_sl_set_table_fp32': (_INT, [_P, _INT]),
     'bfe_eof_create': (_INT, [C.POINTER(EofParams)] + [_P] * 6 + [_P, C.POINTER(_P)]),
@@ -70,6 +71,7 @@ SIGNATURES = {
     'bfe_peer_destroy': (None, [_P]),
     'bfe_peer_allreduce': (_INT, [_P, _P, _I64, _P]),
     'bfe_peer_error': (_INT, [_P, _P, C.POINTER(C.c_uint64)]),
+    'bfe_peer_poison': (_INT, [_P, C.c_uint64, _P]),
     'bfe_eof_return_bins': (_INT, [C.POINTER(EofParams), _I64] + [_P] * 6 + [_P]),
     'bfe_eof_get_pot': (_INT, [_P, _I64, _P, _P, C.c_double, _P, _P, _P]),
     'bfe_sl_radial_matrices': (_INT, [_P, _I64, _P, _P, _P, _P, _P]),

@@ -232,9 +232,10 @@ def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, 
     '''
     eof.make_coefficients_multi (eof.py:1415-1455).  The reference splits the particles over
     `nprocs` worker processes and sums the partial coefficients on the parent; here one GPU
-    takes the whole set, or -- when torch.distributed is initialised -- every rank takes its
-    block of the particles and the partial coefficients are summed with one NCCL allreduce
-    (exptool_b200.parallel).  `nprocs` is accepted for call compatibility.
+    takes the whole set (rank-local under torch.distributed, like eof.accumulate).  Inside
+    `with exptool_b200.parallel.sharded():` every rank takes its block of the SAME particle set
+    and the partial coefficients are summed with one allreduce over NVLink (exptool_b200.parallel).
+    `nprocs` is accepted for call compatibility.
     '''
     if VAR:
         # the reference sums per-worker tuples of unequal shapes here (np.array(a_coeffs), eof.py:1440), which NumPy
@@ -245,7 +246,11 @@ def make_coefficients_multi(ParticleInstance, nprocs, potC, potS, mmax, norder, 
     from .. import parallel
     x, y, z, m = particle.particle_arrays(ParticleInstance)
     E = device_tables(potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap)
-    c, s = parallel.eof_accumulate_host(E, x, y, z, m)
+    if parallel.sharded_api():
+        c, s = parallel.eof_accumulate_host(E, x, y, z, m)
+        parallel.raise_if_poisoned(c); parallel.raise_if_poisoned(s)
+    else:
+        c, s = E.accumulate_host(x, y, z, m)
     if verbose:
         dt = time.time() - t1
         print('eof.make_coefficients_multi: Accumulation took {0:3.2f} seconds, or {1:4.2f} microseconds per orbit.'

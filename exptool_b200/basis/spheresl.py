@@ -178,8 +178,8 @@ def compute_coefficients(PSPInput, sph_file, mod_file, verbose=1, no_odd=False):
     '''
     spheresl.compute_coefficients (spheresl.py:439-475) -> SL_Object.  The reference fans out
     over multiprocessing.Pool and sums on the parent (the sum has dtype=object there); here the
-    particles go to the GPU -- sharded over ranks with one NCCL allreduce when
-    torch.distributed is initialised -- and expcoef is a float64 array.
+    particles go to the GPU (rank-local under torch.distributed; sharded over the ranks with one
+    allreduce inside `with exptool_b200.parallel.sharded():`) and expcoef is a float64 array.
     '''
     from .. import parallel
     SL_Out = SL_Object()
@@ -194,7 +194,10 @@ def compute_coefficients(PSPInput, sph_file, mod_file, verbose=1, no_odd=False):
     SL_Out.lmax = T['lmax']
     SL_Out.nmax = T['nmax']
     t1 = time.time()
-    SL_Out.expcoef = parallel.sl_accumulate_sharded(H, x, y, z, m, no_odd=no_odd).cpu().numpy()
+    if parallel.sharded_api():          # opt-in: `with parallel.sharded():` -- every rank holds the same particle set
+        SL_Out.expcoef = parallel.raise_if_poisoned(parallel.sl_accumulate_sharded(H, x, y, z, m, no_odd=no_odd).cpu().numpy())
+    else:                               # rank-local, like compute_coefficients_solitary
+        SL_Out.expcoef = H.accumulate(x, y, z, m, no_odd=no_odd).cpu().numpy()
     if verbose > 0:
         dt = time.time() - t1
         print('spheresl.compute_coefficients: accumulation took {0:3.2f} seconds, or {1:4.2f} microseconds per orbit.'
@@ -316,16 +319,13 @@ def extract_sl_coefficients(f):
 
 
 def restore_sl_coefficients(infile):
-    '''spheresl.py:1442-1464: (last SL_Object, OrderedDict time -> SL_Object)'''
+    '''spheresl.py:1442-1464: (last SL_Object, dict np.round(time, 3) -> SL_Object)'''
     SL_Dict = OrderedDict()
     SL_Out = None
     with open(infile, 'rb') as f:
         [ndumps] = np.fromfile(f, dtype='i4', count=1)
         f.seek(4)
         for step in range(0, ndumps):
-            try:
-                SL_Out = extract_sl_coefficients(f)
-                SL_Dict[SL_Out.time] = SL_Out
-            except Exception:
-                pass
+            SL_Out = extract_sl_coefficients(f)            # a short / corrupt dump raises, as in the reference
+            SL_Dict[np.round(SL_Out.time, 3)] = SL_Out       # keyed by the ROUNDED time (spheresl.py:1461)
     return SL_Out, SL_Dict

@@ -11,7 +11,8 @@
 // One CTA, no host round trip, no separate communication stream.  Slots are double-buffered by the parity of the
 // sequence number: a rank can only push sequence s+2 after it has finished s+1, which needs every peer's push of
 // s+1, which the peer issues after it has consumed s (calls on one bfe_peer are stream-ordered on every rank).
-// A wait that sees no progress for 20 s raises the buffer's error word and gives up (no hung GPU).
+// A wait that sees no progress for 20 s raises the error word of EVERY rank's buffer (sticky), returns NaN instead of a
+// sum and gives up (no hung GPU, no silently wrong coefficients).
 #include "bfe_internal.h"
 #include "bfe_device.cuh"
 #include <new>
@@ -38,42 +39,64 @@ __device__ __forceinline__ double* peer_data(unsigned long long* base, long long
     return reinterpret_cast<double*>(base + BFE_PEER_HDR) + ((long long)slot * BFE_PEER_MAXW + r) * ncoef_max;
 }
 
+// The error word of a buffer is STICKY and shared: a rank whose wait times out (or that finds the word already set)
+// raises it in EVERY rank's buffer, so the peers stop waiting at once, and from then on every call on this bfe_peer
+// returns NaN in `data` -- a sum that could not be formed is never passed on as numbers (round 1 summed whatever the
+// slots held).  The host side sees it through bfe_peer_error() or simply through the NaNs.
 __global__ void __launch_bounds__(256)
 peer_allreduce_kernel(PeerParams pp, double* __restrict__ data, int n, unsigned long long seq) {
     __shared__ int s_fail;
     const int tid = threadIdx.x, slot = (int)(seq & 1ull);
+    unsigned long long* my_err = pp.buf[pp.rank] + 2 * BFE_PEER_MAXW;
     if (tid == 0) s_fail = 0;
     bfe_pdl_wait();                                   // the producer of `data` (previous kernel of the stream) is done
-    // 1. push this rank's block to every rank (own buffer included: step 4 then reads one layout)
-    for (int p = 0; p < pp.world; ++p) {
-        double* dst = peer_data(pp.buf[p], pp.ncoef_max, slot, pp.rank);
-        for (int j = tid; j < n; j += blockDim.x) dst[j] = data[j];
-    }
-    __threadfence_system();
     __syncthreads();
-    // 2. one thread per peer raises our flag there (release, system scope)
-    if (tid < pp.world) {
-        unsigned long long* f = peer_flag(pp.buf[tid], slot, pp.rank);
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(seq) : "memory");
+    if (tid == 0) {
+        unsigned long long e;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(e) : "l"(my_err) : "memory");
+        if (e != 0ull) s_fail = 1;                    // an earlier collective on this peer set failed
     }
-    // 3. one thread per peer waits for that peer's flag in OUR buffer
-    if (tid < pp.world) {
-        const unsigned long long* f = peer_flag(pp.buf[pp.rank], slot, tid);
-        unsigned long long v, t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= seq) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) { s_fail = 1; break; }             // 20 s without the peer: give up
-            __nanosleep(200);
+    __syncthreads();
+    if (!s_fail) {
+        // 1. push this rank's block to every rank (own buffer included: step 4 then reads one layout)
+        for (int p = 0; p < pp.world; ++p) {
+            double* dst = peer_data(pp.buf[p], pp.ncoef_max, slot, pp.rank);
+            for (int j = tid; j < n; j += blockDim.x) dst[j] = data[j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        // 2. one thread per peer raises our flag there (release, system scope)
+        if (tid < pp.world) {
+            unsigned long long* f = peer_flag(pp.buf[tid], slot, pp.rank);
+            asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(seq) : "memory");
+        }
+        // 3. one thread per peer waits for that peer's flag in OUR buffer (or for the error word)
+        if (tid < pp.world) {
+            const unsigned long long* f = peer_flag(pp.buf[pp.rank], slot, tid);
+            unsigned long long v, e, t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v >= seq) break;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(e) : "l"(my_err) : "memory");
+                if (e != 0ull) { s_fail = 1; break; }                            // a peer gave up: so do we
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) { s_fail = 1; break; }             // 20 s without the peer: give up
+                __nanosleep(200);
+            }
         }
     }
     __syncthreads();
     // Dependents are released only now: a pre-launched dependent grid parks its CTAs in griddepcontrol.wait, and
     // parked CTAs of one stream could keep the kernels of another stream -- which a PEER is waiting for -- off the SMs.
     bfe_pdl_trigger();
-    if (s_fail && tid == 0) pp.buf[pp.rank][2 * BFE_PEER_MAXW] = seq;         // error word: first sequence that timed out
+    if (s_fail) {
+        // error word (first sequence that failed) in every rank's buffer, never overwritten; NaN instead of a partial sum
+        if (tid < pp.world) atomicCAS_system(pp.buf[tid] + 2 * BFE_PEER_MAXW, 0ull, seq);
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        for (int j = tid; j < n; j += blockDim.x) data[j] = qnan;
+        return;
+    }
     // 4. fixed-order sum of the blocks in our own buffer (written by the peers: read around L1)
     for (int j = tid; j < n; j += blockDim.x) {
         double s = 0.0;
@@ -142,6 +165,15 @@ extern "C" int bfe_peer_allreduce(bfe_peer* p, double* data, int64_t n, void* st
     BFE_CUDA(bfe_launch(peer_allreduce_kernel, dim3(1), dim3(256), 0, stream, nullptr, 0, p->pp, data, (int)n, p->seq));
     bfe_kt_end(kt, stream);
     BFE_LAUNCH_CHECK("peer_allreduce_kernel");
+    return BFE_OK;
+}
+
+// fault injection (tests): raise this rank's error word as if collective `seq` had timed out
+extern "C" int bfe_peer_poison(bfe_peer* p, unsigned long long seq, void* stream_) {
+    if (!p || seq == 0) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BFE_CUDA(cudaMemcpyAsync(p->pp.buf[p->pp.rank] + 2 * BFE_PEER_MAXW, &seq, 8, cudaMemcpyHostToDevice, stream));
+    BFE_CUDA(cudaStreamSynchronize(stream));
     return BFE_OK;
 }
 

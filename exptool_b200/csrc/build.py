@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.environ.get('BFE_BUILD_OUT') or os.path.join(PKG, 'libbfe.so')     # BFE_BUILD_OUT + BFE_NVCC_FLAGS: variant builds
-SOURCES = ['bfe_eof.cu', 'bfe_sl.cu', 'bfe_field.cu', 'bfe_sort.cu', 'bfe_sl_sort.cu', 'bfe_host.cu', 'bfe_ingest.cu', 'bfe_blocks.cu', 'bfe_peer.cu', 'bfe_orbit_sort.cu']
+SOURCES = ['bfe_eof.cu', 'bfe_sl.cu', 'bfe_field.cu', 'bfe_sort.cu', 'bfe_sl_sort.cu', 'bfe_host.cu', 'bfe_ingest.cu', 'bfe_blocks.cu', 'bfe_peer.cu', 'bfe_orbit_sort.cu', 'bfe_peak.cu']
 HEADERS = ['bfe_device.cuh', 'bfe_sortcore.cuh', 'bfe_internal.h', os.path.join('..', '..', 'include', 'bfe.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 

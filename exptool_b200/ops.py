@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import torch_ops  # noqa: F401  (registers torch.ops.exptool_b200.*, which the methods below call)
 
 
 def _require_cuda():
@@ -79,6 +80,15 @@ class table_precision(object):
         return False
 
 
+def fp64_peak(kind='dfma'):
+    """Measured FP64 peak of the current device in TFLOP/s (bfe_fp64_peak): 'dfma' (vector pipe) or 'dmma' (FP64 tensor
+    cores).  ~10 ms of register-only arithmetic; synchronises the current stream."""
+    _require_cuda()
+    v = C.c_double(0.0)
+    _lib.check(_lib.load().bfe_fp64_peak(0 if kind == 'dfma' else 1, C.byref(v), _stream()))
+    return float(v.value)
+
+
 def kernel_time_ms(name):
     """Duration of the latest launch of kernel `name` recorded while option 'time_kernels' was on (ms; < 0: none)."""
     return float(_lib.load().bfe_kernel_time_ms(name.encode()))
@@ -131,6 +141,11 @@ class EOFTables(object):
         except Exception:
             pass
 
+    @property
+    def handle(self):
+        """address of the bfe_eof (the `handle` argument of the torch.ops.exptool_b200.* custom ops)"""
+        return int(self.h.value)
+
     def set_table_fp32(self, value):
         """Table precision of the per-point field kernels for THIS handle (bfe_eof_set_table_fp32): True / False, or None to
         follow the process option 'table_fp32'.  The combined-field calls (field_force_*, leapfrog) read this handle."""
@@ -166,9 +181,7 @@ class EOFTables(object):
         n = x.numel()
         if not (y.numel() == n and z.numel() == n and m.numel() == n):
             raise ValueError('particle arrays differ in length')
-        out = torch.empty((2, self.mmax + 1, self.norder), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.bfe_eof_accumulate(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(m),
-                                               _ptr(out[0]), _ptr(out[1]), _stream()))
+        out = torch.ops.exptool_b200.eof_accumulate(self.handle, x, y, z, m, self.mmax, self.norder)
         return out[0], out[1]
 
     # -- one cell sort shared by accumulate and force evaluation on the same particles
@@ -195,8 +208,7 @@ class EOFTables(object):
     def contract(self, cosc, sinc, m1=0, m2=1000, nuse=None, no_odd=False):
         cosc, sinc = self._coef(cosc), self._coef(sinc)
         nuse = self.norder if nuse is None else int(nuse)
-        _lib.check(self.lib.bfe_eof_contract(self.h, _ptr(cosc), _ptr(sinc), int(m1), int(min(m2, self.mmax)),
-                                             nuse, int(bool(no_odd)), _stream()))
+        torch.ops.exptool_b200.eof_contract(self.handle, cosc, sinc, int(m1), int(min(m2, self.mmax)), nuse, bool(no_odd))
 
     def _coef(self, c):
         c = dev(c)
@@ -210,11 +222,7 @@ class EOFTables(object):
     def force(self, x, y, z):
         """eof.accumulated_eval_particles outputs p0, p, fr, fp, fz, R (uses the held contraction)."""
         x, y, z = dev(x), dev(y), dev(z)
-        n = x.numel()
-        out = torch.empty((6, n), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.bfe_eof_force_contracted(self.h, n, _ptr(x), _ptr(y), _ptr(z),
-                                                     *[_ptr(out[i]) for i in range(6)], _stream()))
-        return out
+        return torch.ops.exptool_b200.eof_force(self.handle, x, y, z)
 
     # -- host-array entry points (chunked copy / compute pipeline inside libbfe, bfe_host.cu)
     def accumulate_host(self, x, y, z, m, reduce=None):
@@ -317,6 +325,11 @@ class SLTables(object):
         except Exception:
             pass
 
+    @property
+    def handle(self):
+        """address of the bfe_sl (the `handle` argument of the torch.ops.exptool_b200.* custom ops)"""
+        return int(self.h.value)
+
     def set_table_fp32(self, value):
         """Table precision of the SL-only evaluation kernels for THIS handle (bfe_sl_set_table_fp32)."""
         _lib.check(self.lib.bfe_sl_set_table_fp32(self.h, -1 if value is None else int(bool(value))))
@@ -327,10 +340,7 @@ class SLTables(object):
         n = x.numel()
         if not (y.numel() == n and z.numel() == n and m.numel() == n):
             raise ValueError('particle arrays differ in length')
-        out = torch.empty((self.nrow, self.nmax), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.bfe_sl_accumulate(self.h, n, _ptr(x), _ptr(y), _ptr(z), _ptr(m), int(bool(no_odd)),
-                                              _ptr(out), _stream()))
-        return out
+        return torch.ops.exptool_b200.sl_accumulate(self.handle, x, y, z, m, self.nrow, self.nmax, bool(no_odd))
 
     def _coef(self, c):
         c = dev(c)
@@ -345,16 +355,12 @@ class SLTables(object):
         nuse = self.nmax if nuse is None else int(nuse)
         l1 = max(int(l1), 0)
         l2 = min(int(l2), self.lmax)
-        _lib.check(self.lib.bfe_sl_contract(self.h, _ptr(c), l1, l2, nuse, int(bool(no_odd)), _stream()))
+        torch.ops.exptool_b200.sl_contract(self.handle, c, l1, l2, nuse, bool(no_odd))
 
     def force(self, x, y, z):
         """spheresl.all_eval_particles outputs pot0, pot1, potr, pott, potp, rr."""
         x, y, z = dev(x), dev(y), dev(z)
-        n = x.numel()
-        out = torch.empty((6, n), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.bfe_sl_force_contracted(self.h, n, _ptr(x), _ptr(y), _ptr(z),
-                                                    *[_ptr(out[i]) for i in range(6)], _stream()))
-        return out
+        return torch.ops.exptool_b200.sl_force(self.handle, x, y, z)
 
     def radial_matrices(self, r, dens=True, force=True, pot=True):
         """spheresl.get_halo_dens_pot_force (spheresl.py:106-160) at n radii: (dens, force, pot), each
@@ -405,21 +411,13 @@ class SLTables(object):
 def field_force_cart(eof_tables, sl_tables, x, y, z, rotpos=0.0):
     """Fields.return_forces_cart (potential.py:445-497) at n points -> (8, n) device tensor."""
     x, y, z = dev(x), dev(y), dev(z)
-    n = x.numel()
-    out = torch.empty((8, n), dtype=torch.float64, device=x.device)
-    _lib.check(eof_tables.lib.bfe_field_force_cart(eof_tables.h, sl_tables.h, n, _ptr(x), _ptr(y), _ptr(z),
-                                                   float(rotpos), _ptr(out), _stream()))
-    return out
+    return torch.ops.exptool_b200.field_force_cart(eof_tables.handle, sl_tables.handle, x, y, z, float(rotpos))
 
 
 def field_force_cyl(eof_tables, sl_tables, x, y, z, rotpos=0.0):
     """Fields.return_forces_cyl (potential.py:389-440) at n points -> (8, n) device tensor."""
     x, y, z = dev(x), dev(y), dev(z)
-    n = x.numel()
-    out = torch.empty((8, n), dtype=torch.float64, device=x.device)
-    _lib.check(eof_tables.lib.bfe_field_force_cyl(eof_tables.h, sl_tables.h, n, _ptr(x), _ptr(y), _ptr(z),
-                                                  float(rotpos), _ptr(out), _stream()))
-    return out
+    return torch.ops.exptool_b200.field_force_cyl(eof_tables.handle, sl_tables.handle, x, y, z, float(rotpos))
 
 
 def leapfrog(eof_tables, sl_tables, pos0, vel0, nint, dt, rotfreq=0.0, traj_stride=0, apse=False, ap_max=1000):

@@ -53,6 +53,11 @@ class PeerAllreduce(object):
     The coefficient sum as one kernel over NVLink peer memory (include/bfe.h: bfe_peer_*): every rank maps every
     other rank's exchange buffer through CUDA IPC; torch.distributed only carries the 64-byte handles once.
     One instance per stream of collectives (calls must come in the same order on every rank).
+
+    Construction is COLLECTIVE and its outcome is agreed: every rank runs every collective of the set-up whatever
+    happened locally, a success flag is reduced with MIN, and either all ranks get a working object or all ranks raise
+    (after freeing what they had built) -- a rank-local failure can no longer leave some ranks on the peer kernel and
+    the others on NCCL.
     """
 
     def __init__(self, ncoef_max=4096):
@@ -62,26 +67,41 @@ class PeerAllreduce(object):
         self.rank, self.world = world()
         self.ncoef_max = int(ncoef_max)
         self.h = None
-        local = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        _lib.check(self.lib.bfe_peer_buffer_create(self.ncoef_max, C.byref(local), handle))
-        self.local = local
-        handles = [None] * self.world
-        dist.all_gather_object(handles, handle.raw)
+        self.local = None
         self.opened = []
-        ptrs = (C.c_void_p * self.world)()
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs[r] = local.value
-            else:
-                p = C.c_void_p()
-                _lib.check(self.lib.bfe_peer_buffer_open(handles[r], C.byref(p)))
-                self.opened.append(p)
-                ptrs[r] = p.value
-        h = C.c_void_p()
-        _lib.check(self.lib.bfe_peer_create(self.rank, self.world, self.ncoef_max, ptrs, C.byref(h)))
-        self.h = h
-        dist.barrier()                      # every buffer is zeroed and mapped before the first push
+        err = None
+        handle = C.create_string_buffer(64)
+        try:
+            local = C.c_void_p()
+            _lib.check(self.lib.bfe_peer_buffer_create(self.ncoef_max, C.byref(local), handle))
+            self.local = local
+        except Exception as e:                                   # noqa: BLE001 -- reported after the agreement below
+            err = e
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw if err is None else None)
+        if err is None and all(hd is not None for hd in handles):
+            try:
+                ptrs = (C.c_void_p * self.world)()
+                for r in range(self.world):
+                    if r == self.rank:
+                        ptrs[r] = self.local.value
+                    else:
+                        p = C.c_void_p()
+                        _lib.check(self.lib.bfe_peer_buffer_open(handles[r], C.byref(p)))
+                        self.opened.append(p)
+                        ptrs[r] = p.value
+                h = C.c_void_p()
+                _lib.check(self.lib.bfe_peer_create(self.rank, self.world, self.ncoef_max, ptrs, C.byref(h)))
+                self.h = h
+            except Exception as e:                               # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError('a peer rank could not create its exchange buffer')
+        ok = torch.tensor([0.0 if err is not None else 1.0], device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                # all ranks or none; also orders "zeroed and mapped" before the first push
+        if float(ok.item()) == 0.0:
+            self.close()
+            raise RuntimeError('PeerAllreduce: set-up failed on at least one rank (%s)' % (err if err is not None else 'a peer failed'))
 
     def allreduce_(self, t, stream=None):
         """in-place sum over ranks of a contiguous FP64 device tensor with numel <= ncoef_max"""
@@ -101,20 +121,26 @@ class PeerAllreduce(object):
         return int(v.value)
 
     def close(self):
-        if self.h:
+        if torch.cuda.is_available():
             torch.cuda.synchronize()
+        if self.h:
             self.lib.bfe_peer_destroy(self.h)
             self.h = None
-            for p in self.opened:
-                self.lib.bfe_peer_buffer_close(p)
+        for p in self.opened:
+            self.lib.bfe_peer_buffer_close(p)
+        self.opened = []
+        if self.local is not None:
             self.lib.bfe_peer_buffer_destroy(self.local)
+            self.local = None
 
 
 _PEER = {'obj': None, 'failed': False}
 
 
 def _peer_allreduce_for(t):
-    """the process-wide PeerAllreduce for small coefficient blocks on the current stream, or None (-> NCCL)"""
+    """the process-wide PeerAllreduce for small coefficient blocks on the current stream, or None (-> NCCL).
+    Every rank takes the same branch: the eligibility tests depend only on the (rank-identical) call, and the
+    constructor agrees on its outcome collectively."""
     import os
     if _PEER['failed'] or os.environ.get('BFE_PEER_ALLREDUCE', '1') == '0':
         return None
@@ -125,12 +151,73 @@ def _peer_allreduce_for(t):
     if _PEER['obj'] is None:
         try:
             _PEER['obj'] = PeerAllreduce(4096)
-        except Exception as e:                         # no peer access / IPC on this box: NCCL does the sum
+        except Exception as e:                         # no peer access / IPC somewhere on this job: NCCL does the sum, on ALL ranks
             _PEER['failed'] = True
             import sys
             print('exptool_b200.parallel: peer-memory allreduce unavailable (%s); using NCCL' % (e,), file=sys.stderr)
             return None
     return _PEER['obj']
+
+
+def raise_if_poisoned(values, what='coefficients'):
+    """A coefficient sum that could not be formed (a rank missing for 20 s in the peer-memory kernel) comes back as NaN
+    on every rank: turn that into an exception at the point where the values reach the host."""
+    if is_distributed() and np.isnan(np.asarray(values)).any():
+        seq = 0
+        if _PEER['obj'] is not None:
+            try:
+                seq = _PEER['obj'].first_failed_sequence()
+            except Exception:                          # noqa: BLE001
+                pass
+        if seq:
+            raise RuntimeError('exptool_b200.parallel: the %s allreduce failed (peer-memory collective %d timed out: a rank '
+                               'did not arrive within 20 s); all ranks received NaN' % (what, seq))
+    return values
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference-named entry points (eof.make_coefficients_multi, eof.compute_coefficients, spheresl.compute_coefficients)
+# are RANK-LOCAL by default, like eof.accumulate and compute_coefficients_solitary: under torch.distributed every rank
+# computes the coefficients of exactly the arrays it was given (one rank per snapshot of a series just works).
+# Sharding the GIVEN arrays over the ranks with an allreduce of the partial sums is opt-in -- `with parallel.sharded():`
+# or parallel.set_sharded(True) -- and then every rank must pass the SAME full particle set and make the same calls in
+# the same order; the particle count is checked across ranks before slicing.  The explicit entry points below
+# (eof_accumulate_sharded, eof_accumulate_host, sl_accumulate_sharded) always take part in the collective.
+# ---------------------------------------------------------------------------------------------------------------------
+_SHARDED = {'on': False}
+
+
+def set_sharded(on=True):
+    _SHARDED['on'] = bool(on)
+
+
+def sharded_api():
+    return bool(_SHARDED['on']) and is_distributed()
+
+
+class sharded(object):
+    """context manager: the reference-named coefficient functions shard their particle arrays over the ranks"""
+
+    def __enter__(self):
+        self.prev = _SHARDED['on']
+        _SHARDED['on'] = True
+        return self
+
+    def __exit__(self, *exc):
+        _SHARDED['on'] = self.prev
+        return False
+
+
+def _check_same_count(n):
+    """all ranks must have been handed the same particle set before it is block-partitioned"""
+    t = torch.tensor([float(n), -float(n)], dtype=torch.float64)
+    if dist.get_backend() == 'nccl':
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if float(t[0].item()) != float(n) or -float(t[1].item()) != float(n):
+        raise ValueError('exptool_b200.parallel: sharded accumulation needs the SAME particle arrays on every rank '
+                         '(this rank has %d particles, the ranks hold between %d and %d); pass already_sharded=True for '
+                         'per-rank shards' % (n, int(-t[1].item()), int(t[0].item())))
 
 
 def allreduce_sum_(t):
@@ -174,6 +261,7 @@ def eof_accumulate_sharded(E, x, y, z, m, already_sharded=False):
     partials are summed with one allreduce.  Returns (cos, sin) device tensors.
     """
     if is_distributed() and not already_sharded:
+        _check_same_count(len(x))
         lo, hi = my_shard(len(x))
         x, y, z, m = _slice(x, lo, hi), _slice(y, lo, hi), _slice(z, lo, hi), _slice(m, lo, hi)
     c, s = E.accumulate(x, y, z, m)
@@ -191,6 +279,7 @@ def eof_accumulate_host(E, x, y, z, m, already_sharded=False):
     before the single small copy out.
     """
     if is_distributed() and not already_sharded:
+        _check_same_count(len(x))
         lo, hi = my_shard(len(x))
         x, y, z, m = _slice(x, lo, hi), _slice(y, lo, hi), _slice(z, lo, hi), _slice(m, lo, hi)
     return E.accumulate_host(x, y, z, m, reduce=allreduce_sum_ if is_distributed() else None)
@@ -199,6 +288,7 @@ def eof_accumulate_host(E, x, y, z, m, already_sharded=False):
 def sl_accumulate_sharded(H, x, y, z, m, no_odd=False, already_sharded=False):
     """SL coefficients of the global particle set (see eof_accumulate_sharded)."""
     if is_distributed() and not already_sharded:
+        _check_same_count(len(x))
         lo, hi = my_shard(len(x))
         x, y, z, m = _slice(x, lo, hi), _slice(y, lo, hi), _slice(z, lo, hi), _slice(m, lo, hi)
     c = H.accumulate(x, y, z, m, no_odd=no_odd)

@@ -70,6 +70,11 @@ int bfe_get_option(const char* name);
 int bfe_eof_set_table_fp32(bfe_eof* h, int value);
 int bfe_sl_set_table_fp32(bfe_sl* h, int value);
 
+/* Measured FP64 peak of the current device in TFLOP/s: kind 0 = vector DFMA (eight independent chains per thread),
+ * kind 1 = FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA).  Runs ~10 ms of register-only arithmetic on `stream` and
+ * synchronises it.  The FP64 side of bench.py's roofline uses these instead of a nominal figure. */
+int bfe_fp64_peak(int kind, double* tflops, void* stream);
+
 /* With option "time_kernels" = 1 the EOF step kernels are bracketed by CUDA events on their stream;
  * bfe_kernel_time_ms(name) synchronises on and returns the duration (ms) of the latest launch of that kernel
  * (e.g. "eof_segsum_kernel"), or a negative value if none was recorded. */
@@ -223,10 +228,13 @@ int bfe_peer_buffer_close(void* peer_ptr);
 int bfe_peer_buffer_destroy(void* local_ptr);
 int bfe_peer_create(int rank, int world, int64_t ncoef_max, void* const* bufs, bfe_peer** out);
 void bfe_peer_destroy(bfe_peer* p);
-/* data[0..n) (device, this rank's partial sums) := sum over ranks, in place, on `stream`. */
+/* data[0..n) (device, this rank's partial sums) := sum over ranks, in place, on `stream`.  If a rank does not arrive
+ * within 20 s the call fills data with NaN on every rank (never a partial sum) and the peer set stays failed. */
 int bfe_peer_allreduce(bfe_peer* p, double* data, int64_t n, void* stream);
-/* first sequence number whose wait gave up after 20 s (0: none). */
+/* first sequence number that failed on this peer set (0: none); synchronises `stream`. */
 int bfe_peer_error(bfe_peer* p, void* stream, unsigned long long* first_failed_seq);
+/* fault injection for tests: mark this rank's buffer as failed at collective `seq` (synchronises `stream`). */
+int bfe_peer_poison(bfe_peer* p, unsigned long long seq, void* stream);
 
 /* ---------------------------------------------------------------- building blocks ----------- */
 /* The per-point pieces the kernels above evaluate inline, callable with the meaning of the reference's own

@@ -403,3 +403,110 @@ def test_fields_table_fp32_option(api):
         o32 = integrate.leapfrog_integrate_batch(F32, 50, meta['dt'], d['pos0'], d['vel0'], rotfreq=meta['rotfreq'])
         o64 = integrate.leapfrog_integrate_batch(F64, 50, meta['dt'], d['pos0'], d['vel0'], rotfreq=meta['rotfreq'])
         assert 0 < relerr(o32['X'], o64['X']) < 1e-4
+
+
+def test_fanout_mirrors_and_eval_particles(api):
+    """The fan-out helpers the reference drives its Pool with -- eof.redistribute_particles / multi_accumulate /
+    find_forces_multi / mix_outputs (eof.py:1333-1590) -- and spheresl.eval_particles (spheresl.py:502-528), against the
+    goldens of the functions they wrap: block partials sum to the whole-set coefficients, per-block outputs concatenate to
+    the whole-set outputs, the m window passed to find_forces_multi is ignored (eof.py:1528)."""
+    eof, spheresl = api['eof'], api['spheresl']
+    d, meta = load_golden('eof_small_random_cmap1')
+    with tempfile.TemporaryDirectory() as tmp:
+        f = _eof_file(tmp, meta)
+        potC, rfC, zfC, dC, potS, rfS, zfS, dS = eof.parse_eof(f)
+        rmin, rmax, numx, numy, mmax, norder, ascale, hscale, cmap, dens = eof.eof_params(f)
+        XMIN, XMAX, dX, YMIN, YMAX, dY = eof.set_table_params(RMAX=rmax, RMIN=rmin, ASCALE=ascale, HSCALE=hscale,
+                                                              NUMX=numx, NUMY=numy, CMAP=cmap)
+        P = S.ParticleSet(d['x'], d['y'], d['z'], d['m'])
+        tabs = (potC, potS, mmax, norder, XMIN, dX, YMIN, dY, numx, numy, ascale, hscale, cmap)
+        holders = eof.redistribute_particles(P, 3)
+        sizes = [len(h.xpos) for h in holders]
+        assert sum(sizes) == d['x'].size and sizes[0] >= sizes[1] == sizes[2]          # block 0 takes the remainder
+        parts = eof.multi_accumulate(holders, 3, *tabs)
+        assert len(parts) == 3 and all(len(pc) == 2 for pc in parts)
+        csum = np.sum(np.array([pc[0] for pc in parts]), axis=0)                           # eof.py:1440
+        ssum = np.sum(np.array([pc[1] for pc in parts]), axis=0)
+        assert relerr(csum, d['cos_multi3']) < TOL and relerr(ssum, d['sin_multi3']) < TOL
+        nf = meta['nforce']
+        Pf = S.ParticleSet(d['x'][:nf], d['y'][:nf], d['z'][:nf], d['m'][:nf])
+        out = eof.find_forces_multi(Pf, 2, d['cos'], d['sin'], potC, rfC, zfC, potS, rfS, zfS, XMIN, dX, YMIN, dY, numx, numy,
+                                    mmax, norder, ascale, hscale, cmap, m1=1, m2=2)
+        for i in range(6):
+            assert relerr(out[i], d['full'][i]) < TOL, i                                   # window ignored: the full sum
+        kw = dict(potC=potC, rforceC=rfC, zforceC=zfC, potS=potS, rforceS=rfS, zforceS=zfS, rmin=XMIN, dR=dX, zmin=YMIN,
+                  dZ=dY, numx=numx, numy=numy, MMAX=mmax, NMAX=norder, ASCALE=ascale, HSCALE=hscale, CMAP=cmap, verbose=0)
+        blocks = [eof.accumulated_eval_particles(h, d['cos'], d['sin'], **kw) for h in eof.redistribute_particles(Pf, 3)]
+        mixed = eof.mix_outputs(blocks)
+        assert len(mixed) == 6
+        for i in range(6):
+            assert mixed[i].shape == (nf,) and relerr(mixed[i], d['full'][i]) < TOL, i
+    d, meta = load_golden('sl_std_l4')
+    with tempfile.TemporaryDirectory() as tmp:
+        sf, mf = _sl_files(tmp, meta)
+        nf = meta['nforce']
+        Pf = S.ParticleSet(d['x'][1:nf + 1], d['y'][1:nf + 1], d['z'][1:nf + 1], d['m'][1:nf + 1])
+        for key, kw in (('allp', {}), ('allp_win12', dict(l1=1, l2=2)), ('allp_noodd', dict(no_odd=True))):
+            out = spheresl.eval_particles(Pf, d['coef'], sf, mf, nprocs=4, verbose=0, **kw)
+            assert len(out) == 8
+            for j in range(8):
+                assert relerr(out[j], d[key][j]) < TOL, (key, j)
+
+
+def test_torch_library_custom_ops(api):
+    """The hot path as PyTorch custom ops (north_star; exptool_b200/torch_ops.py): torch.ops.exptool_b200.* called directly
+    with device tensors + table handles, against the same goldens as the reference-facing API."""
+    import torch
+    from exptool_b200 import ops, torch_ops
+    from helpers import eof_tables, sl_tables
+    T = torch.ops.exptool_b200
+    for name in torch_ops.OPS:
+        assert hasattr(T, name), name
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+    d, meta = load_golden('eof_std_smooth')
+    pe, Tt, g = eof_tables(meta)
+    E = ops.EOFTables(Tt['potC'], Tt['potS'], g['mmax'], g['norder'], g['XMIN'], g['dX'], g['YMIN'], g['dY'], g['numx'],
+                      g['numy'], g['ascale'], g['hscale'], g['cmap'], rforceC=Tt['rforceC'], zforceC=Tt['zforceC'],
+                      rforceS=Tt['rforceS'], zforceS=Tt['zforceS'])
+    x, y, z, m = [dev(d[k]) for k in 'xyzm']
+    cs = T.eof_accumulate(E.handle, x, y, z, m, g['mmax'], g['norder'])
+    assert cs.shape == (2, g['mmax'] + 1, g['norder']) and cs.is_cuda
+    assert relerr(cs[0].cpu().numpy(), d['cos']) < TOL and relerr(cs[1].cpu().numpy(), d['sin']) < TOL
+    T.eof_contract(E.handle, dev(d['cos']), dev(d['sin']), 0, g['mmax'], g['norder'], False)
+    nf = meta['nforce']
+    out = T.eof_force(E.handle, x[:nf].contiguous(), y[:nf].contiguous(), z[:nf].contiguous()).cpu().numpy()
+    for i in range(6):
+        assert relerr(out[i], d['full'][i]) < TOL, i
+    d, meta = load_golden('sl_std_l6')
+    ps, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = ops.SLTables(ps['lmax'], ps['nmax'], ps['numr'], ps['cmap'], ps['scale'], ev, ef, xi, p0, d0)
+    x, y, z, m = [dev(d[k]) for k in 'xyzm']
+    coef = T.sl_accumulate(H.handle, x, y, z, m, H.nrow, H.nmax, False)
+    assert relerr(coef.cpu().numpy(), d['coef']) < TOL
+    T.sl_contract(H.handle, dev(d['coef']), 0, ps['lmax'], ps['nmax'], False)
+    nf = meta['nforce']
+    out = T.sl_force(H.handle, x[1:nf + 1].contiguous(), y[1:nf + 1].contiguous(), z[1:nf + 1].contiguous()).cpu().numpy()
+    for j, k in enumerate((2, 3, 4, 5, 6, 7)):                # all_eval_particles: den0 den1 pot0 pot1 potr pott potp r
+        assert relerr(out[j], d['allp'][k]) < TOL, j
+    d, meta = load_golden('field_std')
+    pe, Tt, g = eof_tables(meta)
+    ps, ev, ef, xi, p0, d0 = sl_tables(meta, seed_offset=1)
+    E = ops.EOFTables(Tt['potC'], Tt['potS'], g['mmax'], g['norder'], g['XMIN'], g['dX'], g['YMIN'], g['dY'], g['numx'],
+                      g['numy'], g['ascale'], g['hscale'], g['cmap'], rforceC=Tt['rforceC'], zforceC=Tt['zforceC'],
+                      rforceS=Tt['rforceS'], zforceS=Tt['zforceS'])
+    H = ops.SLTables(ps['lmax'], ps['nmax'], ps['numr'], ps['cmap'], ps['scale'], ev, ef, xi, p0, d0)
+    T.eof_contract(E.handle, dev(d['cos']), dev(d['sin']), 0, g['mmax'], g['norder'], False)
+    T.sl_contract(H.handle, dev(meta['halofac'] * d['coef']), 0, ps['lmax'], ps['nmax'], False)
+    out = T.field_force_cart(E.handle, H.handle, dev(d['px']), dev(d['py']), dev(d['pz']), float(meta['rot_full'])).cpu().numpy()
+    for i in range(8):
+        assert relerr(out[i], d['cart_full'][:, i]) < TOL, i
+    outc = T.field_force_cyl(E.handle, H.handle, dev(d['px']), dev(d['py']), dev(d['pz']), float(meta['rot_full']))
+    assert outc.shape == out.shape
+    st = T.leapfrog(E.handle, H.handle, torch.cat([dev(d['pos0']), dev(d['vel0'])]).contiguous(), int(meta['nint']),
+                    float(meta['dt']), float(meta['rotfreq'])).cpu().numpy()
+    for k in range(d['orbits'].shape[0]):
+        for j in range(6):
+            assert abs(st[j, k] - d['orbits'][k, j, -1]) <= ORBIT_TOL * np.max(np.abs(d['orbits'][k, j])), (k, j)
+    with pytest.raises(Exception):                                # no CPU kernel behind the ops
+        T.eof_force(E.handle, torch.zeros(4, dtype=torch.float64), torch.zeros(4, dtype=torch.float64),
+                    torch.zeros(4, dtype=torch.float64))

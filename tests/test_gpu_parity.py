@@ -504,6 +504,21 @@ def test_peer_allreduce_protocol_single_gpu(ops):
         assert torch.equal(data[r], want), r
     # argument checks
     assert lib.bfe_peer_allreduce(peers[0], C.c_void_p(data[0, 0].data_ptr()), NMAX + 1, C.c_void_p(0)) != 0
+    # a failed collective never hands out numbers: rank 1's buffer is marked failed (fault injection) -> its next call
+    # returns NaN at once and raises the error word of every rank, so the ranks waiting for it give up with NaN too
+    # (round 1 summed whatever the slots held after a 20 s time-out)
+    _lib.check(lib.bfe_peer_poison(peers[1], 777, C.c_void_p(0)))
+    blocks = torch.ones(W, N, dtype=torch.float64, device='cuda')
+    t0 = __import__('time').time()
+    for r in (1, 0, 2):
+        _lib.check(lib.bfe_peer_allreduce(peers[r], C.c_void_p(blocks[r].data_ptr()), N, C.c_void_p(streams[r].cuda_stream)))
+    torch.cuda.synchronize()
+    assert __import__('time').time() - t0 < 10.0, 'the peers of a failed rank must not sit out the 20 s time-out'
+    assert bool(torch.isnan(blocks).all())
+    for r in range(W):
+        v = C.c_uint64(0)
+        _lib.check(lib.bfe_peer_error(peers[r], C.c_void_p(0), C.byref(v)))
+        assert v.value != 0, r
     for h in peers:
         lib.bfe_peer_destroy(h)
     for r in range(W):

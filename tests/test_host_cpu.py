@@ -171,6 +171,41 @@ def test_coefficient_dump_roundtrip_and_layout():
         assert os.path.getsize(f2) == 4 + 2 * (8 * 25 * 18 + 324)      # App. B.4
         last, D = spheresl.restore_sl_coefficients(f2)
         assert np.array_equal(last.expcoef, Sx.expcoef) and last.lmax == 4
+        # keyed by np.round(time, 3) like the reference (spheresl.py:1461): a caller can index with the plain number
+        assert list(D.keys()) == [np.round(np.float32(0.5), 3)] and D[0.5] is last
+        Sx.time = np.float32(0.2504)
+        spheresl.save_sl_coefficients(f2, Sx)
+        last, D = spheresl.restore_sl_coefficients(f2)
+        assert np.round(np.float32(0.2504), 3) in D and len(D) == 2
+        # a truncated dump raises (the reference does not swallow it, unlike eof.restore_eof_coefficients)
+        with open(f2, 'r+b') as fh:
+            fh.truncate(os.path.getsize(f2) - 100)
+        with pytest.raises(Exception):
+            spheresl.restore_sl_coefficients(f2)
+
+
+def test_factorial_return_matches_oracle():
+    """spheresl.factorial_return (spheresl.py:823-863) against the oracle's restatement (and, in test_oracle_vs_reference,
+    the oracle against the reference itself)"""
+    from exptool_b200.basis import spheresl
+    for lmax in (0, 1, 4, 6, 10):
+        a, b = spheresl.factorial_return(lmax), O.factorial_return(lmax)
+        assert a.shape == (lmax + 1, lmax + 1) and np.allclose(a, b, rtol=1e-15, atol=0)
+        assert np.all(np.triu(a, 1) == 0.0)
+
+
+def test_torch_library_ops_registered_and_cuda_only():
+    """torch.ops.exptool_b200.* exist with their schemas and have no CPU kernel (no fallback)."""
+    import torch
+    from exptool_b200 import torch_ops
+    for name in torch_ops.OPS:
+        op = getattr(torch.ops.exptool_b200, name)
+        assert 'exptool_b200::' + name in str(op.default._schema)
+    z = torch.zeros(4, dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        torch.ops.exptool_b200.eof_force(0, z, z, z)
+    with pytest.raises(NotImplementedError):
+        torch.ops.exptool_b200.field_force_cart(0, 0, z, z, z, 0.0)
 
 
 def test_shard_bounds_match_reference_partition():

@@ -67,3 +67,17 @@ def test_sl_accumulate_fresh_seed(ref):
     xi, r, p0, d0 = O.sl_init_table(R1, D1, P1, ps['numr'], ps['rmin'], ps['rmax'], ps['cmap'], ps['scale'])
     co = O.sl_accumulate(x, y, z, m, ps['lmax'], ps['nmax'], ev, ef, xi, p0, ps['cmap'], ps['scale'])
     assert relerr(co, c) < 1e-12
+
+
+def test_factorial_return_and_mirrors_vs_reference(ref):
+    """spheresl.factorial_return (spheresl.py:823-863), compatibility maps and eof.set_table_params of the product's
+    host-side mirrors against the reference's own functions (host code: no GPU needed)."""
+    from exptool_b200.basis import spheresl as mine, eof as myeof
+    for lmax in (0, 2, 6, 9):
+        r = ref['spheresl'].factorial_return(lmax)
+        assert np.array_equal(np.asarray(r), mine.factorial_return(lmax))
+        assert np.allclose(O.factorial_return(lmax), r, rtol=1e-15, atol=0)
+    for cmap in (0, 1):
+        a = ref['eof'].set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=cmap)
+        b = myeof.set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=cmap)
+        assert np.array_equal(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))
