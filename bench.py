@@ -20,6 +20,13 @@ roofline : dominant kernel, algorithmic HBM bytes / CUDA-event duration vs MEASU
 cpu_baseline : the oracle's C restatement of the reference's arithmetic (oracle/bfe_oracle.c, OpenMP,
            `kind: port`) on all host threads over a bounded sample of the same workload.
 
+configs  : the other four BASELINE.json configurations (C1 SL 10^5, C3 combined field 10^8 points, C4 10^6 orbits x 10^4
+           steps, C5 coefficient time series 200 x 10^7), each with its own `roofline` (HBM fraction of the measured copy
+           bandwidth AND FP64 fraction of the measured DFMA peak; `bound` = the larger), `cpu_baseline` (a port of the
+           reference formulation on a stated subsample) and `parity` (max relative error of the GPU result against that
+           CPU result on the same subsample).  Sizes are BASELINE.json's totals divided over the ranks (strong scaling).
+           --configs none skips them, --configs-scale S shrinks them (smoke runs).
+
 --impl reference times that CPU port as the reference arm (the reference itself is pure
 Python under /root/reference, which does not exist on the GPU box).
 """
@@ -48,14 +55,26 @@ PBE_PER_PARTICLE = 234
 # ----------------------------------------------------------------------------- helpers
 def eof_setup():
     from exptool_b200 import synthetic as S
-    from oracle import oracle_np as O
+    from exptool_b200.basis import eof as beof
     p, T = S.make_eof_tables({}, kind='smooth')
-    XMIN, XMAX, dX, YMIN, YMAX, dY = O.eof_set_table_params(RMAX=p['rmax'], RMIN=p['rmin'], ASCALE=p['ascale'],
-                                                            HSCALE=p['hscale'], NUMX=p['numx'], NUMY=p['numy'],
-                                                            CMAP=p['cmap'])
-    g = dict(XMIN=XMIN, dX=dX, YMIN=YMIN, dY=dY, numx=p['numx'], numy=p['numy'], mmax=p['mmax'], norder=p['norder'],
-             ascale=p['ascale'], hscale=p['hscale'], cmap=p['cmap'])
+    XMIN, XMAX, dX, YMIN, YMAX, dY = beof.set_table_params(RMAX=p['rmax'], RMIN=p['rmin'], ASCALE=p['ascale'],
+                                                           HSCALE=p['hscale'], NUMX=p['numx'], NUMY=p['numy'],
+                                                           CMAP=p['cmap'])
+    g = dict(XMIN=float(XMIN), dX=float(dX), YMIN=float(YMIN), dY=float(dY), numx=p['numx'], numy=p['numy'], mmax=p['mmax'],
+             norder=p['norder'], ascale=p['ascale'], hscale=p['hscale'], cmap=p['cmap'])
     return p, T, g
+
+
+def sl_setup(lmax):
+    """SL cache tables + model on the cache's xi grid, through the product's own host readers (halo_methods.init_table)"""
+    import tempfile
+    from exptool_b200 import synthetic as S
+    from exptool_b200.utils import halo_methods
+    ps, ev, ef = S.make_sl_tables(dict(lmax=lmax))
+    with tempfile.TemporaryDirectory() as tmp:
+        mf = S.write_hernquist_model(os.path.join(tmp, 'm'), a=ps['scale'])
+        xi, r, p0, d0 = halo_methods.init_table(mf, ps['numr'], ps['rmin'], ps['rmax'], cmap=ps['cmap'], scale=ps['scale'])
+    return ps, ev, ef, xi, p0, d0
 
 
 class ClockSampler(threading.Thread):
@@ -200,6 +219,314 @@ def run_reference(args):
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- the other BASELINE configurations
+FIELD_FLOP_PER_POINT = 2 * 835 + 577 + 142   # executed FP64 flop of one combined-field evaluation at mmax=6 / lmax=6: DFMA x2 + DMUL + DADD,
+                                             # static SASS count of field_rec_kernel<6,6> (fully unrolled; profiles/r02_sass_field_rec_kernel.txt)
+FIELD_BYTES_PER_POINT = 24 + 64              # x,y,z in + the 8-tuple out
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    den = float(np.max(np.abs(b))) if b.size else 0.0
+    return float(np.max(np.abs(a - b)) / den) if den > 0 else float(np.max(np.abs(a - b))) if b.size else 0.0
+
+
+def _roof(bytes_alg, flop_exec, ms, peaks, kernel, note=None):
+    """roofline object of one configuration: HBM side against the measured copy bandwidth, FP64 side against the measured
+    DFMA peak (bfe_fp64_peak); `bound` is whichever fraction is larger (SURVEY.md section 8d rule v)."""
+    sec = ms * 1e-3
+    hbm = bytes_alg / sec / 1e9 if bytes_alg else 0.0
+    hbm_frac = hbm / peaks['hbm_gbs']
+    out = {'kernel': kernel, 'hbm': {'achieved': hbm, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': hbm_frac,
+                                     'algorithmic_bytes': bytes_alg, 'peak_source': peaks['hbm_source']}, 'traffic': None}
+    if flop_exec:
+        tf = flop_exec / sec / 1e12
+        out['fp64'] = {'achieved': tf, 'peak': peaks['dfma_tflops'], 'unit': 'TFLOP/s', 'frac': tf / peaks['dfma_tflops'],
+                       'executed_flop': flop_exec, 'peak_source': 'measured in this run: bfe_fp64_peak(DFMA); DMMA %.1f'
+                       % peaks['dmma_tflops']}
+    else:
+        out['fp64'] = None
+    if out['fp64'] and out['fp64']['frac'] > hbm_frac:
+        out.update(bound='fp64', achieved=out['fp64']['achieved'], peak=peaks['dfma_tflops'], unit='TFLOP/s', frac=out['fp64']['frac'])
+    else:
+        out.update(bound='hbm', achieved=hbm, peak=peaks['hbm_gbs'], unit='GB/s', frac=hbm_frac)
+    if note:
+        out['note'] = note
+    return out
+
+
+def run_configs(args, E, T, g, world, rank, dev, peaks):
+    """C1, C3, C4, C5 of BASELINE.json:configs on this job's GPUs (C2 is the headline step above)."""
+    import torch
+    import torch.distributed as dist
+    from exptool_b200 import ops, parallel, synthetic as S
+    want = set(c.strip().upper() for c in args.configs.split(',')) if args.configs != 'all' else {'C1', 'C3', 'C4', 'C5'}
+    scale = args.configs_scale
+    cpu_ok = (rank == 0 and world == 1 and not args.no_cpu)
+    res = {}
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def dev_particles(kind, n, seed):
+        gen = S.hernquist_halo if kind == 'halo' else S.exponential_disc
+        parts = [[ops.dev(a) for a in gen(min(2000000, n - lo), seed + lo)] for lo in range(0, n, 2000000)]
+        return [torch.cat([q[k] for q in parts]) for k in range(4)]
+
+    def sl_handle(lmax):
+        ps, ev, ef, xi, p0, d0 = sl_setup(lmax)
+        return ops.SLTables(ps['lmax'], ps['nmax'], ps['numr'], ps['cmap'], ps['scale'], ev, ef, xi, p0, d0), (ps, ev, ef, xi, p0, d0)
+
+    def frozen(cosc, sinc, coef, sl):
+        from oracle import oracle_np as O
+        ps, ev, ef, xi, p0, d0 = sl
+        return O.FrozenField(cos=cosc, sin=sinc, potC=T['potC'], rforceC=T['rforceC'], zforceC=T['zforceC'], potS=T['potS'],
+                             rforceS=T['rforceS'], zforceS=T['zforceS'], XMIN=g['XMIN'], dX=g['dX'], YMIN=g['YMIN'], dY=g['dY'],
+                             numx=g['numx'], numy=g['numy'], mmax=g['mmax'], norder=g['norder'], ascale=g['ascale'],
+                             hscale=g['hscale'], cmapdisk=g['cmap'], halofac=1.0, expcoef=coef, xihalo=xi, p0halo=p0, d0halo=d0,
+                             cmaphalo=ps['cmap'], scalehalo=ps['scale'], lmaxhalo=ps['lmax'], nmaxhalo=ps['nmax'],
+                             evtablehalo=ev, eftablehalo=ef)
+
+    # ---------------- C1: SL lmax=4 nmax=18, accumulate + force eval, 10^5 Hernquist particles
+    if 'C1' in want:
+        n = max(int(1e5 * scale) // world, 1000)
+        H, sl = sl_handle(4)
+        h = dev_particles('halo', n, 1001 + rank)
+        box = {}
+
+        def c1():
+            box['coef'] = parallel.sl_accumulate_sharded(H, *h, already_sharded=True)
+            H.contract(box['coef'])
+            box['out'] = H.force(*h[:3])
+        ms = timed(c1, 20)
+        entry = {'config': 'C1 SL lmax=4 nmax=18: accumulate + force eval, 10^5-particle Hernquist halo', 'particles': n * world,
+                 'ms': ms, 'value': n * world / ms * 1e3, 'unit': 'particles/s', 'pbe_per_s': n * world / ms * 1e3 * 450,
+                 'scaling': 'strong',
+                 'roofline': _roof((32 + 72) * n, None, ms, peaks, 'sl_accumulate + sl_contract + sl_force',
+                                   note='10^5 particles are ~8 launches of 5-30 us: launch/latency-bound, not a bandwidth test')}
+        if cpu_ok:
+            from oracle import oracle_np as O
+            ps, ev, ef, xi, p0, d0 = sl
+            ns = min(n, 100000)
+            hx, hy, hz, hm = [a[:ns].cpu().numpy() for a in h]
+            t0 = time.perf_counter()
+            co = O.sl_accumulate(hx, hy, hz, hm, ps['lmax'], ps['nmax'], ev, ef, xi, p0, ps['cmap'], ps['scale'])
+            fo = O.sl_all_eval_particles(hx, hy, hz, co, ps['lmax'], ps['nmax'], ev, ef, xi, p0, d0, ps['cmap'], ps['scale'])
+            dt = time.perf_counter() - t0
+            cg = H.accumulate(*[a[:ns] for a in h])
+            H.contract(cg)
+            fg = H.force(*[a[:ns] for a in h[:3]]).cpu().numpy()
+            entry['cpu_baseline'] = {'value': ns / dt, 'unit': 'particles/s', 'cores': 1, 'kind': 'port',
+                                     'sample': '%d particles, NumPy port of the reference formulation (oracle_np), one core, %.1f s' % (ns, dt)}
+            entry['parity'] = {'coefficients_max_rel_err': _rel(cg.cpu().numpy(), co),
+                               'force_max_rel_err': max(_rel(fg[i], fo[i]) for i in range(6)), 'sample': ns, 'tolerance': 1e-10}
+        res['C1'] = entry
+        del H, h
+
+    # ---------------- C3 (+ C4): combined halo (SL lmax=6) + disc (EOF mmax=6) field
+    if 'C3' in want or 'C4' in want:
+        H6, sl6 = sl_handle(6)
+        nb = max(min(int(5e6 * scale), int(1e8 * scale) // (2 * world)), 500)
+        bd = dev_particles('disc', nb, 3003 + rank)
+        bh = dev_particles('halo', nb, 3503 + rank)
+        nc = min(nb, 1000000)
+        c, s_ = E.accumulate(*[q[:nc] for q in bd])
+        ch = H6.accumulate(*[q[:nc] for q in bh])
+        cosc, sinc = c * 0.025, s_ * 0.025
+        E.contract(cosc, sinc); H6.contract(ch)
+    if 'C3' in want:
+        n = max(int(1e8 * scale) // world, 1000)
+        nd = n // 2
+
+        def replicate(base, cnt):
+            # distinct points with the base set's (R, z) distribution: the base rotated about z by a different angle per copy
+            xs, ys, zs = [], [], []
+            k = 0
+            while sum(q.numel() for q in xs) < cnt:
+                ca, sa = float(np.cos(0.61803 * k)), float(np.sin(0.61803 * k))
+                xs.append(base[0] * ca - base[1] * sa); ys.append(base[0] * sa + base[1] * ca); zs.append(base[2]); k += 1
+            return [torch.cat(v)[:cnt] for v in (xs, ys, zs)]
+        pd_, ph_ = replicate(bd, nd), replicate(bh, n - nd)
+        x = torch.cat([pd_[0], ph_[0]]); y = torch.cat([pd_[1], ph_[1]]); z = torch.cat([pd_[2], ph_[2]])
+        del pd_, ph_
+        box = {}
+
+        def c3():
+            box['out'] = ops.field_force_cart(E, H6, x, y, z, rotpos=0.3)
+        ms = timed(c3, 3, warm=1)
+        kms = None
+        ops.set_option('time_kernels', 1)
+        c3()
+        kms = ops.kernel_time_ms('field_sorted_pass')
+        ops.set_option('time_kernels', 0)
+        entry = {'config': 'C3 combined halo (SL lmax=6) + disc (EOF mmax=6) Cartesian force eval, 10^8 points (half disc-like, half halo-like)',
+                 'particles': n * world, 'ms': ms, 'value': n * world / ms * 1e3, 'unit': 'particles/s',
+                 'pbe_per_s': n * world / ms * 1e3 * (234 + 882), 'scaling': 'strong',
+                 'tables': 'fp64', 'chunk': ops.get_option('field_sort_chunk'),
+                 'roofline': _roof(FIELD_BYTES_PER_POINT * n, FIELD_FLOP_PER_POINT * n, ms, peaks, 'field_rec_kernel<6,6> (key-ordered pass)',
+                                   note='pass = key + scan + scatter | evaluation | gather, two chunks in flight; evaluation kernel is bound by '
+                                        'the L1 data pipe and FP64 issue (ncu, profiles/r02_summary.md)'),
+                 'pass_ms_events_in_library': kms}
+        out = box['out']
+        idx = torch.cat([torch.arange(0, min(100000, nd), device=dev), torch.arange(nd, nd + min(100000, n - nd), device=dev)])
+        # the key-ordered path against the caller-order kernel on a prefix of each half: same arithmetic, so bit-identical
+        saved = ops.get_option('field_sort_min')
+        ops.set_option('field_sort_min', 0)
+        plain = ops.field_force_cart(E, H6, x[idx].contiguous(), y[idx].contiguous(), z[idx].contiguous(), rotpos=0.3)
+        ops.set_option('field_sort_min', saved)
+        entry['parity'] = {'key_ordered_equals_caller_order_bits': bool(torch.equal(out[:, idx], plain)), 'self_sample': int(idx.numel())}
+        if cpu_ok:
+            from oracle import oracle_np as O
+            F = frozen(cosc.cpu().numpy(), sinc.cpu().numpy(), ch.cpu().numpy(), sl6)
+            hx, hy, hz = x[idx].cpu().numpy(), y[idx].cpu().numpy(), z[idx].cpu().numpy()
+            t0 = time.perf_counter()
+            ref = O.fields_forces_cart(F, hx, hy, hz, rotpos=0.3)
+            dt = time.perf_counter() - t0
+            got = out[:, idx].cpu().numpy()
+            entry['cpu_baseline'] = {'value': idx.numel() / dt, 'unit': 'particles/s', 'cores': 1, 'kind': 'port',
+                                     'sample': '%d points (half disc, half halo), NumPy port of Fields.return_forces_cart '
+                                               '(oracle_np), one core, %.1f s' % (idx.numel(), dt)}
+            entry['parity'].update(vs_cpu_port_max_rel_err=max(_rel(got[i], ref[i]) for i in range(8)), sample=int(idx.numel()),
+                                   tolerance=1e-10)
+        res['C3'] = entry
+        del x, y, z, out, box
+
+    # ---------------- C4: 10^6 orbits x 10^4 leapfrog steps in the frozen field
+    if 'C4' in want:
+        norb = max(int(1e6 * scale) // world, 1000)
+        nint = 10000 if scale >= 1.0 else max(int(10000 * scale), 100)
+        dd = S.exponential_disc(norb, 4004 + rank)
+        pos0 = np.stack(dd[:3])
+        a = ops.field_force_cart(E, H6, pos0[0], pos0[1], pos0[2]).cpu().numpy()
+        R = np.sqrt(pos0[0] ** 2 + pos0[1] ** 2) + 1e-12
+        fr = ((a[0] + a[1]) * pos0[0] + (a[2] + a[3]) * pos0[1]) / R
+        vc = np.sqrt(np.maximum(-R * fr, 1e-12))
+        rng = np.random.default_rng(44 + rank)
+        f = rng.uniform(0.6, 1.1, norb)
+        vel0 = np.stack([-pos0[1] / R * vc * f, pos0[0] / R * vc * f, 0.1 * vc * rng.standard_normal(norb)])
+        P0, V0 = ops.dev(pos0), ops.dev(vel0)
+        box = {}
+        ops.leapfrog(E, H6, P0, V0, min(nint, 200), 3e-4, rotfreq=-5.0)          # warm-up (workspace, tables in L2)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        box['st'] = ops.leapfrog(E, H6, P0, V0, nint, 3e-4, rotfreq=-5.0)[0]
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        st = box['st']
+        steps_total = norb * world * (nint - 1)
+        entry = {'config': 'C4 leapfrog orbit integration, 10^6 orbits x 10^4 steps in the frozen halo (SL lmax=6) + disc (EOF mmax=6) field, '
+                           'dt=3e-4, rotfreq=-5', 'orbits': norb * world, 'steps': nint, 'ms': ms, 'value': steps_total / ms * 1e3,
+                 'unit': 'orbit-steps/s', 'scaling': 'strong', 'tables': 'fp64', 'resort_every': ops.get_option('orbit_resort'),
+                 'fraction_of_orbits_inside_R_lt_1': float((torch.sqrt(st[0] ** 2 + st[1] ** 2) < 1.0).double().mean().item()),
+                 'roofline': _roof(96 * norb, (FIELD_FLOP_PER_POINT + 60) * norb * (nint - 1), ms, peaks,
+                                   'leapfrog_perm_kernel<6,6> (key-ordered, re-sorted every %d steps)' % ops.get_option('orbit_resort'),
+                                   note='state lives in registers / a 96-byte record per orbit: HBM side is 96 B per orbit per RUN')}
+        # key-ordered path against the plain per-lane kernel: bit-identical end states
+        ns_ = min(norb, 100000)
+        k0 = ops.get_option('orbit_resort')
+        a1 = ops.leapfrog(E, H6, P0[:, :ns_].contiguous(), V0[:, :ns_].contiguous(), 41, 3e-4, rotfreq=-5.0)[0]
+        ops.set_option('orbit_resort', 0)
+        a0 = ops.leapfrog(E, H6, P0[:, :ns_].contiguous(), V0[:, :ns_].contiguous(), 41, 3e-4, rotfreq=-5.0)[0]
+        ops.set_option('orbit_resort', k0)
+        entry['parity'] = {'key_ordered_equals_caller_order_bits': bool(torch.equal(a0, a1)), 'self_sample': '%d orbits x 40 steps' % ns_}
+        if cpu_ok:
+            from oracle import oracle_np as O
+            F = frozen(cosc.cpu().numpy(), sinc.cpu().numpy(), ch.cpu().numpy(), sl6)
+            no_, nst = min(norb, 2000), 101
+            t0 = time.perf_counter()
+            pr, vr, potr, _ = O.leapfrog(F, nst, 3e-4, pos0[:, :no_], vel0[:, :no_], rotfreq=-5.0)
+            dt = time.perf_counter() - t0
+            sg = ops.leapfrog(E, H6, pos0[:, :no_], vel0[:, :no_], nst, 3e-4, rotfreq=-5.0)[0].cpu().numpy()
+            entry['cpu_baseline'] = {'value': no_ * (nst - 1) / dt, 'unit': 'orbit-steps/s', 'cores': 1, 'kind': 'port',
+                                     'sample': '%d orbits x %d steps, NumPy port of integrate.leapfrog_integrate (oracle_np, '
+                                               'vectorised over orbits), one core, %.1f s' % (no_, nst - 1, dt)}
+            entry['parity'].update(vs_cpu_port_max_rel_err=max(max(_rel(sg[i], pr[i]), _rel(sg[3 + i], vr[i])) for i in range(3)),
+                                   sample='%d orbits x %d steps' % (no_, nst - 1), tolerance=1e-8)
+        res['C4'] = entry
+        del P0, V0, box
+
+    # ---------------- C5: coefficient time series, 200 snapshots x 10^7 particles (10^6 disc + 9x10^6 halo), one allreduce
+    if 'C5' in want:
+        H, sl = sl_handle(4)
+        nsnap = 200 if scale >= 1.0 else max(int(200 * scale), 4)
+        ndisc = max(int(1e6 * scale) // world, 1000)
+        nhalo = max(int(9e6 * scale) // world, 1000)
+        base_d = dev_particles('disc', ndisc, 5005 + rank)
+        base_h = dev_particles('halo', nhalo, 5505 + rank)
+
+        def snaps():
+            for k in range(nsnap):      # distinct snapshots: the base set rotated by a different angle each time
+                ca, sa = float(np.cos(0.01 * k)), float(np.sin(0.01 * k))
+                yield ((base_d[0] * ca - base_d[1] * sa, base_d[0] * sa + base_d[1] * ca, base_d[2], base_d[3]),
+                       (base_h[0] * ca - base_h[1] * sa, base_h[0] * sa + base_h[1] * ca, base_h[2], base_h[3]))
+        box = {}
+
+        def c5():
+            box['out'] = parallel.accumulate_series(E, H, snaps())
+        ms = timed(c5, 1, warm=1)
+        npart = (ndisc + nhalo) * world * nsnap
+        entry = {'config': 'C5 coefficient time series: 200 snapshots x 10^7 particles (10^6 disc EOF + 9x10^6 halo SL lmax=4) accumulation, '
+                           'one allreduce of the [200, ncoef] block', 'snapshots': nsnap, 'particles_per_snapshot': (ndisc + nhalo) * world,
+                 'ms': ms, 'value': npart / ms * 1e3, 'unit': 'particles/s', 'scaling': 'strong',
+                 'roofline': _roof((32 + 24) * (ndisc + nhalo) * nsnap, None, ms, peaks, 'eof + sl sorted accumulate passes',
+                                   note='32 B/particle accumulate read + 24 B/particle for the on-device rotation that makes each snapshot distinct')}
+        cs, sn, ce = box['out']
+        par = {}
+        if world > 1:
+            # the allreduced block against the sum formed in rank order from the gathered partials (snapshot 0)
+            c0, s0 = E.accumulate(*next(snaps())[0])
+            part = torch.cat([c0.reshape(-1), s0.reshape(-1)])
+            gathered = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(gathered, part)
+            want_ = gathered[0].clone()
+            for r_ in range(1, world):
+                want_ += gathered[r_]
+            got_ = torch.cat([cs[0].reshape(-1), sn[0].reshape(-1)])
+            par['allreduce_vs_rank_order_sum_max_rel_err'] = float(((got_ - want_).abs().max() / want_.abs().max()).item())
+        if cpu_ok:
+            from oracle import oracle_c as OC
+            OC.use_all_cores()
+            ps, ev, ef, xi, p0, d0 = sl
+            nd_, nh_ = min(ndisc, 1000000), min(nhalo, 9000000)
+            dx = [q[:nd_].cpu().numpy() for q in base_d]; hx = [q[:nh_].cpu().numpy() for q in base_h]
+            t0 = time.perf_counter()
+            cc, sc = OC.eof_accumulate(dx[0], dx[1], dx[2], dx[3], T['potC'], T['potS'], g)
+            hc = OC.sl_accumulate(hx[0], hx[1], hx[2], hx[3], ps['lmax'], ps['nmax'], ev, ef, xi, p0, ps['cmap'], ps['scale'])
+            dt = time.perf_counter() - t0
+            cg, sg_ = E.accumulate(*[q[:nd_] for q in base_d])
+            hg = H.accumulate(*[q[:nh_] for q in base_h])
+            entry['cpu_baseline'] = {'value': (nd_ + nh_) / dt, 'unit': 'particles/s', 'cores': OC.threads(), 'kind': 'port',
+                                     'sample': 'one snapshot of %d disc + %d halo particles, C port (oracle/bfe_oracle.c, OpenMP), %.1f s'
+                                               % (nd_, nh_, dt)}
+            par.update(eof_coefficients_max_rel_err=max(_rel(cg.cpu().numpy(), cc), _rel(sg_.cpu().numpy(), sc)),
+                       sl_coefficients_max_rel_err=_rel(hg.cpu().numpy(), hc), sample=nd_ + nh_, tolerance=1e-10)
+        entry['parity'] = par
+        res['C5'] = entry
+    return res
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -431,14 +758,18 @@ def run_gpu(args):
     # 6 DMMA m8n8k4 per 8 records = 384 flop on the tensor pipe + ~57 flop per lane x 4 lanes = 228 flop of vector
     # FP64 (trig powers, harmonic sums, transposed reduce); nominal B200 FP64 peak 148 SMs x 64 lanes x 2 x 1.965 GHz.
     FP64_FLOP = {'eof_force_sorted_mma_kernel': 384 + 228}
+    dfma_peak, dmma_peak = ops.fp64_peak('dfma'), ops.fp64_peak('dmma')          # measured on this device, in this run
+    peaks = {'hbm_gbs': peak, 'hbm_source': peak_src, 'dfma_tflops': dfma_peak, 'dmma_tflops': dmma_peak}
     fp64 = None
     if dom in FP64_FLOP:
         tf = FP64_FLOP[dom] * N_PART / (kms[dom] * 1e-3) / 1e12
-        fp64 = {'flop_per_particle': FP64_FLOP[dom], 'achieved_tflops': tf, 'peak_tflops': 37.2,
-                'peak_source': 'nominal: 148 SMs x 64 FP64 lanes x 2 x 1.965 GHz', 'frac': tf / 37.2,
-                'ncu': 'FP64 pipe 23 % + DMMA pipe 28 % active, issue slots 52 % (profiles/r01_ncu_full_step_kernels_v2.csv)'}
-    roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'fp64': fp64,
+        fp64 = {'flop_per_particle': FP64_FLOP[dom], 'achieved_tflops': tf, 'peak_tflops': dfma_peak,
+                'peak_source': 'measured in this run: bfe_fp64_peak (DFMA %.1f, DMMA %.1f TFLOP/s; nominal 148 SMs x 64 lanes x 2 x '
+                               '1.965 GHz = 37.2)' % (dfma_peak, dmma_peak), 'frac': tf / dfma_peak}
+    bound = 'fp64' if (fp64 is not None and fp64['frac'] > achieved / peak) else 'hbm'
+    roofline = {'kernel': dom, 'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'fp64': fp64,
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'fp64_peaks_measured_tflops': {'dfma': dfma_peak, 'dmma': dmma_peak},
                 'algorithmic_bytes_per_launch': alg[dom],
                 'kernel_ms': kms,
                 'api_call_ms': {'bfe_eof_prepare': t_prep, 'bfe_eof_accumulate_prepared': t_acc,
@@ -495,6 +826,32 @@ def run_gpu(args):
                   ' + eof.accumulated_eval_particles, pinned host tensors in, NumPy arrays out; chunked '
                   'H2D | kernels | D2H pipeline on three streams inside each call'}
 
+    # ---- numerical evidence for the multi-GPU sum: the allreduced coefficients of one step against the sum formed in
+    #      rank order from the gathered partial blocks (bit-identical for the peer-memory kernel, which sums in rank order)
+    parity = None
+    if world > 1:
+        px, py, pz, pm = sets[0]
+        c0, s0 = E.accumulate(px, py, pz, pm)
+        part = torch.stack([c0, s0]).contiguous()
+        gathered = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(gathered, part)
+        want_ = gathered[0].clone()
+        for r_ in range(1, world):
+            want_ += gathered[r_]
+        got_ = part.clone()
+        pa = peers.get(torch.cuda.current_stream().cuda_stream)
+        if pa is not None:
+            pa.allreduce_(got_)
+        else:
+            dist.all_reduce(got_)
+        err = float(((got_ - want_).abs().max() / want_.abs().max()).item())
+        parity = {'allreduce_vs_rank_order_sum_max_rel_err': err, 'bit_identical': bool(torch.equal(got_, want_)),
+                  'allreduce': allreduce_kind, 'tolerance': 1e-14}
+
+    configs = None
+    if args.configs != 'none':
+        configs = run_configs(args, E, T, g, world, rank, dev, peaks)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline()
@@ -519,6 +876,10 @@ def run_gpu(args):
                 'roofline': roofline, 'clocks': clocks}
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if parity is not None:
+            line['parity'] = parity
+        if configs is not None:
+            line['configs'] = configs
         out = globals().get('_JSON_OUT') or sys.stdout
         out.write(json.dumps(line) + '\n')
         out.flush()
@@ -538,6 +899,9 @@ def main():
                     help='N>1: per-step coefficient sum by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--grid-pct', type=int, default=100, help='share of the SMs the persistent grids of the step are sized for')
     ap.add_argument('--pg-per-stream', type=int, default=0, help='N>1: one NCCL communicator per stream (1) or shared (0)')
+    ap.add_argument('--configs', default='all', help="the other BASELINE configurations to run after the headline step: 'all', 'none' "
+                                                      "or a comma list of C1,C3,C4,C5")
+    ap.add_argument('--configs-scale', type=float, default=1.0, help='multiplies the particle / orbit / step counts of --configs')
     args = ap.parse_args()
     if args.allreduce == 'nccl':
         os.environ['BFE_PEER_ALLREDUCE'] = '0'          # the API-level (e2e) coefficient sum follows the same choice
