@@ -819,12 +819,42 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N_PART * args.steps / float(te.item())
-    e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * 32 * N_PART - 8 * N_PART,
+    reused = ops.get_option('host_reused_last') == 1
+    e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': (32 if reused else 56) * N_PART,
            'd2h_bytes_per_step': 48 * N_PART + 2 * 8 * 126, 'ms_per_step': 1e3 * float(te.item()) / args.steps,
            'ms_per_step_median': 1e3 * float(np.median(per_call)),
+           'one_upload_per_snapshot': reused,
            'api': ('eof.make_coefficients_multi' if world == 1 else 'parallel.eof_accumulate_host') +
                   ' + eof.accumulated_eval_particles, pinned host tensors in, NumPy arrays out; chunked '
-                  'H2D | kernels | D2H pipeline on three streams inside each call'}
+                  'H2D | kernels | D2H pipeline on three streams inside each call; the accumulation uploads x,y,z,m every step '
+                  '(32 B/particle), the evaluation of the same arrays runs from that copy (option host_reuse)'}
+    # the same two calls with what a drop-in caller passes: plain (pageable) NumPy arrays
+    Pp = tuple(np.array(t.numpy(), copy=True) for t in P)
+
+    def e2e_step_pageable():
+        if world == 1:
+            c, s = beof.make_coefficients_multi(Pp, 1, *tabs_acc)
+        else:
+            Eh = beof.device_tables(*tabs_acc)
+            c, s = parallel.eof_accumulate_host(Eh, Pp[0], Pp[1], Pp[2], Pp[3], already_sharded=True)
+        return beof.accumulated_eval_particles(Pp, c, s, potC=T['potC'], rforceC=T['rforceC'], zforceC=T['zforceC'],
+                                               potS=T['potS'], rforceS=T['rforceS'], zforceS=T['zforceS'],
+                                               rmin=g['XMIN'], dR=g['dX'], zmin=g['YMIN'], dZ=g['dY'], numx=g['numx'],
+                                               numy=g['numy'], MMAX=g['mmax'], NMAX=g['norder'], ASCALE=g['ascale'],
+                                               HSCALE=g['hscale'], CMAP=g['cmap'], verbose=0)
+    for _ in range(3):
+        res = e2e_step_pageable()
+    barrier()
+    t0 = time.perf_counter()
+    npg = max(3, min(args.steps, 10))
+    for _ in range(npg):
+        res = e2e_step_pageable()
+    torch.cuda.synchronize()
+    tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    e2e['pageable'] = {'value': world * N_PART * npg / float(tp.item()), 'unit': UNIT, 'ms_per_step': 1e3 * float(tp.item()) / npg,
+                       'note': 'same calls with plain NumPy (pageable) inputs: what a drop-in caller passes'}
 
     # ---- numerical evidence for the multi-GPU sum: the allreduced coefficients of one step against the sum formed in
     #      rank order from the gathered partial blocks (bit-identical for the peer-memory kernel, which sums in rank order)

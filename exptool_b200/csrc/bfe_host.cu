@@ -11,8 +11,18 @@
 // from Python spent longer issuing its ~50 small copies than the copies took (profiles/r01_summary.md section 12).
 // Pinned host memory gives asynchronous DMA at 40-55 GB/s per direction (profiles/pcie_probe.py); pageable
 // memory is accepted and simply copies synchronously.
+//
+// One upload per snapshot (option "host_reuse", default 1): bfe_eof_accumulate_host lands its chunks in a device buffer
+// that is KEPT (process-wide, one per device); a following bfe_eof_force_host on the same host arrays -- same three
+// pointers, same length, same content tag -- evaluates from that copy and skips its own 24 B/particle upload, which also
+// lets its result copies run at the one-directional PCIe rate (55 instead of 40 GB/s when both directions are busy).
+// The tag is a hash of the first and last 64 values and of 1024 evenly spaced values of each array: an in-place change of
+// the whole set (a rotation, a drift step) is always seen, an edit of a few isolated particles between the two calls
+// may not be -- callers that do that set the option to 0.  bfe_eof_accumulate_host itself ALWAYS uploads.
 #include "bfe_internal.h"
 #include <algorithm>
+#include <mutex>
+#include <string.h>
 
 struct BfeHostPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -25,6 +35,47 @@ struct BfeHostPipe {
 };
 
 int g_bfe_host_chunk = 0;            // option "host_chunk": particles per pipeline chunk (0 = auto)
+int g_bfe_host_reused_last = 0;      // option (read-only) "host_reused_last": 1 if the latest bfe_eof_force_host evaluated from the kept copy
+int g_bfe_host_reuse = 1;            // option "host_reuse": force_host may evaluate from the copy accumulate_host uploaded
+
+// the particle set the last bfe_eof_accumulate_host call on this device uploaded: rows x, y, z, m of `cap` doubles
+struct BfeKeepSet {
+    int device = -1;
+    double* d = nullptr;
+    int64_t cap = 0, n = 0;
+    const double* hp[3] = {nullptr, nullptr, nullptr};
+    uint64_t tag[3] = {0, 0, 0};
+    bool valid = false;
+    cudaEvent_t ready = nullptr, released = nullptr;      // upload complete / last reader done
+    bool has_reader = false;
+};
+static BfeKeepSet g_keep[16];
+static std::mutex g_keep_mu;
+
+static uint64_t host_tag(const double* a, int64_t n) {
+    uint64_t h = 1469598103934665603ull ^ (uint64_t)n;
+    auto mix = [&](int64_t i) { uint64_t v; memcpy(&v, a + i, 8); h = (h ^ v) * 1099511628211ull; h ^= h >> 29; };
+    const int64_t edge = std::min<int64_t>(64, n);
+    for (int64_t i = 0; i < edge; ++i) mix(i);
+    for (int64_t i = std::max<int64_t>(edge, n - 64); i < n; ++i) mix(i);
+    if (n > 128) {
+        const int64_t step = std::max<int64_t>(1, (n - 128) / 1024);
+        for (int64_t i = 64; i < n - 64; i += step) mix(i);
+    }
+    return h;
+}
+
+static BfeKeepSet* keep_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    BfeKeepSet* k = &g_keep[dev];
+    if (k->device != dev) {
+        k->device = dev;
+        if (cudaEventCreateWithFlags(&k->ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&k->released, cudaEventDisableTiming) != cudaSuccess) { k->device = -1; return nullptr; }
+    }
+    return k;
+}
 
 __global__ void bfe_coef_add_kernel(double* __restrict__ a, const double* __restrict__ b, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,18 +186,40 @@ extern "C" int bfe_eof_accumulate_host(bfe_eof* h, int64_t n, const double* hx, 
     const double* rows[4] = {hx, hy, hz, hm};
     BFE_CUDA(cudaEventRecord(p->ev_start, stream));
     BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
+    // the upload lands in the kept buffer (full size: no double buffering needed) unless reuse is off or the set is huge
+    std::unique_lock<std::mutex> lock(g_keep_mu);
+    BfeKeepSet* ks = (g_bfe_host_reuse && n <= ((int64_t)1 << 27)) ? keep_slot() : nullptr;
+    if (ks) {
+        ks->valid = false;
+        if (ks->cap < n) {
+            if (ks->d) { BFE_CUDA(cudaDeviceSynchronize()); cudaFree(ks->d); ks->d = nullptr; ks->cap = 0; }
+            const int64_t cap = (n + n / 8 + 1023) / 16 * 16;
+            if (cudaMalloc(&ks->d, 4 * (size_t)cap * sizeof(double)) != cudaSuccess) { cudaGetLastError(); ks = nullptr; }
+            else ks->cap = cap;
+        }
+    }
+    if (ks) {
+        if (ks->has_reader) BFE_CUDA(cudaStreamWaitEvent(p->s_in, ks->released, 0));      // the last reader of the old set is done
+        for (int q = 0; q < 3; ++q) { ks->hp[q] = rows[q]; ks->tag[q] = host_tag(rows[q], n); }
+        ks->n = n;
+    }
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, ++k) {
         const int b = k & 1;
         const int64_t len = std::min(chunk, n - lo);
-        if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[b], 0));      // kernels of chunk k-2 have read din[b]
-        BFE_CUDA(copy_rows_h2d(p->din[b], p->cap, rows, 4, lo, len, p->s_in));
+        double* d;
+        int64_t pitch;
+        if (ks) { d = ks->d + lo; pitch = ks->cap; }
+        else {
+            if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[b], 0));  // kernels of chunk k-2 have read din[b]
+            d = p->din[b]; pitch = p->cap;
+        }
+        BFE_CUDA(copy_rows_h2d(d, pitch, rows, 4, lo, len, p->s_in));
         BFE_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
         BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_in[b], 0));
-        double* d = p->din[b];
         double* c = k == 0 ? cos_out : p->coef;
         double* s = k == 0 ? sin_out : p->coef + ncoef;
-        rc = bfe_eof_accumulate(h, len, d, d + p->cap, d + 2 * p->cap, d + 3 * p->cap, c, s, stream_);
+        rc = bfe_eof_accumulate(h, len, d, d + pitch, d + 2 * pitch, d + 3 * pitch, c, s, stream_);
         if (rc != BFE_OK) return rc;
         if (k > 0) {
             bfe_coef_add_kernel<<<(ncoef + 255) / 256, 256, 0, stream>>>(cos_out, p->coef, ncoef);
@@ -154,6 +227,11 @@ extern "C" int bfe_eof_accumulate_host(bfe_eof* h, int64_t n, const double* hx, 
             BFE_LAUNCH_CHECK("bfe_coef_add_kernel");
         }
         BFE_CUDA(cudaEventRecord(p->ev_cmp[b], stream));
+    }
+    if (ks) {
+        BFE_CUDA(cudaEventRecord(ks->ready, stream));      // after the last chunk's kernels (which waited for its upload)
+        ks->has_reader = false;
+        ks->valid = true;
     }
     return BFE_OK;
 }
@@ -176,18 +254,31 @@ extern "C" int bfe_eof_force_host(bfe_eof* h, int64_t n, const double* hx, const
     double* orow[6] = {hp0, hp, hfr, hfp, hfz, hR};
     BFE_CUDA(cudaEventRecord(p->ev_start, stream));
     BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
+    // the particles accumulate_host uploaded last, if these are the same host arrays with the same content tag
+    std::unique_lock<std::mutex> lock(g_keep_mu);
+    BfeKeepSet* ks = g_bfe_host_reuse ? keep_slot() : nullptr;
+    if (ks && !(ks->valid && ks->n == n && ks->hp[0] == hx && ks->hp[1] == hy && ks->hp[2] == hz &&
+                ks->tag[0] == host_tag(hx, n) && ks->tag[1] == host_tag(hy, n) && ks->tag[2] == host_tag(hz, n)))
+        ks = nullptr;
+    if (ks) BFE_CUDA(cudaStreamWaitEvent(stream, ks->ready, 0));
+    g_bfe_host_reused_last = ks ? 1 : 0;
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, ++k) {
         const int b = k & 1;
         const int64_t len = std::min(chunk, n - lo);
-        if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[b], 0));      // kernels of chunk k-2 have read din[b]
-        BFE_CUDA(copy_rows_h2d(p->din[b], p->cap, rows, 3, lo, len, p->s_in));
-        BFE_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
-        BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_in[b], 0));
+        double* d;
+        int64_t pitch;
+        if (ks) { d = ks->d + lo; pitch = ks->cap; }
+        else {
+            if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[b], 0));  // kernels of chunk k-2 have read din[b]
+            BFE_CUDA(copy_rows_h2d(p->din[b], p->cap, rows, 3, lo, len, p->s_in));
+            BFE_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
+            BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_in[b], 0));
+            d = p->din[b]; pitch = p->cap;
+        }
         if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_out[b], 0));       // chunk k-2 has left dout[b]
-        double* d = p->din[b];
         double* o = p->dout[b];
-        rc = bfe_eof_force_contracted(h, len, d, d + p->cap, d + 2 * p->cap, o, o + p->cap, o + 2 * p->cap,
+        rc = bfe_eof_force_contracted(h, len, d, d + pitch, d + 2 * pitch, o, o + p->cap, o + 2 * p->cap,
                                       o + 3 * p->cap, o + 4 * p->cap, o + 5 * p->cap, stream_);
         if (rc != BFE_OK) return rc;
         BFE_CUDA(cudaEventRecord(p->ev_cmp[b], stream));
@@ -195,6 +286,7 @@ extern "C" int bfe_eof_force_host(bfe_eof* h, int64_t n, const double* hx, const
         BFE_CUDA(copy_rows_d2h(orow, 6, lo, o, p->cap, len, p->s_out));
         BFE_CUDA(cudaEventRecord(p->ev_out[b], p->s_out));
     }
+    if (ks) { BFE_CUDA(cudaEventRecord(ks->released, stream)); ks->has_reader = true; }
     // the caller's stream completes only after the last copies out
     BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_out[(k - 1) & 1], 0));
     if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_out[k & 1], 0));

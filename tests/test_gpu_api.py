@@ -312,6 +312,36 @@ def test_eof_host_pipeline_matches_device(api):
         for k in range(6):
             assert isinstance(out[k], np.ndarray) and out[k].shape == (n,)
             assert relerr(out[k], ref[k]) < 1e-13
+    # one upload per snapshot (option host_reuse): the evaluation that follows an accumulation of the SAME host arrays
+    # runs from the copy that accumulation uploaded -- across table handles (accumulate-only vs with force tables) --
+    # and gives the bits of the path that uploads again; a changed set (in place, same pointers) is uploaded again.
+    saved = ops.get_option('host_reuse')
+    try:
+        ops.set_option('host_reuse', 0)
+        eof.make_coefficients_multi(pin, 1, *tabs)
+        base = eof.accumulated_eval_particles(pin, cd, sd, **kw)
+        assert ops.get_option('host_reused_last') == 0
+        ops.set_option('host_reuse', 1)
+        eof.make_coefficients_multi(pin, 1, *tabs)
+        again = eof.accumulated_eval_particles(pin, cd, sd, **kw)
+        assert ops.get_option('host_reused_last') == 1
+        for k in range(6):            # (the sorted evaluation is reproducible to ~1e-16, not bit for bit: slot claims by integer atomics)
+            assert relerr(again[k], base[k]) < 1e-13, k
+        other = eof.accumulated_eval_particles((x, y, z, m), cd, sd, **kw)      # other host arrays: not the kept set
+        assert ops.get_option('host_reused_last') == 0
+        pin[0].mul_(-1.0); pin[1].mul_(-1.0)                                      # in-place rotation by pi: same pointers, new content
+        moved = eof.accumulated_eval_particles(pin, cd, sd, **kw)
+        assert ops.get_option('host_reused_last') == 0
+        refm = E.force(-x, -y, z).cpu().numpy()
+        for k in range(6):
+            assert relerr(moved[k], refm[k]) < 1e-13, k
+        eof.make_coefficients_multi(pin, 1, *tabs)                                # a new accumulation uploads the moved set
+        moved2 = eof.accumulated_eval_particles(pin, cd, sd, **kw)
+        assert ops.get_option('host_reused_last') == 1
+        for k in range(6):
+            assert relerr(moved2[k], moved[k]) < 1e-13, k
+    finally:
+        ops.set_option('host_reuse', saved)
 
 
 @pytest.mark.parametrize('name', ['eof_dens_random', 'eof_dens_smooth'])
