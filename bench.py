@@ -323,6 +323,33 @@ def run_configs(args, E, T, g, world, rank, dev, peaks):
                  'scaling': 'strong',
                  'roofline': _roof((32 + 72) * n, None, ms, peaks, 'sl_accumulate + sl_contract + sl_force',
                                    note='10^5 particles are ~8 launches of 5-30 us: launch/latency-bound, not a bandwidth test')}
+        # e2e through the reference-facing API with host buffers: spheresl.compute_coefficients (chunked host pipeline,
+        # bfe_sl_accumulate_host) + spheresl.eval_particles (one upload, potential + density rows, one copy out)
+        import tempfile
+        from exptool_b200.basis import spheresl as bsl
+        with tempfile.TemporaryDirectory() as tmpd:
+            ps_, ev_, ef_ = sl[0], sl[1], sl[2]
+            sf = S.write_sl_cache(os.path.join(tmpd, 'sl.cache'), ps_, ev_, ef_)
+            mf = S.write_hernquist_model(os.path.join(tmpd, 'sl.model'), a=ps_['scale'])
+            Pp = tuple(a.cpu().pin_memory() for a in h)
+
+            def e2e1():
+                so = bsl.compute_coefficients(Pp, sf, mf, verbose=0)
+                return bsl.eval_particles(Pp, so.expcoef, sf, mf, verbose=0)
+            for _ in range(3):
+                e2e1()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                e2e1()
+            torch.cuda.synchronize()
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            entry['e2e'] = {'value': n * world * 10 / float(te.item()), 'unit': 'particles/s', 'ms_per_step': 1e2 * float(te.item()),
+                            'h2d_bytes_per_step': (32 + 24) * n, 'd2h_bytes_per_step': 64 * n + 8 * 450,
+                            'api': 'spheresl.compute_coefficients + spheresl.eval_particles, pinned host tensors in, NumPy arrays out '
+                                   '(rank-local at N > 1)'}
         if cpu_ok:
             from oracle import oracle_np as O
             ps, ev, ef, xi, p0, d0 = sl

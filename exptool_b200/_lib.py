@@ -61,6 +61,8 @@ SIGNATURES = {
     'bfe_sl_destroy': (None, [_P]),
     'bfe_sl_accumulate': (_INT, [_P, _I64] + [_P] * 4 + [_INT, _P, _P]),
     'bfe_sl_contract': (_INT, [_P, _P, _INT, _INT, _INT, _INT, _P]),
+    'bfe_sl_accumulate_host': (_INT, [_P, _I64] + [_P] * 4 + [_INT, _P, _P]),
+    'bfe_sl_force_host': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_sl_force_contracted': (_INT, [_P, _I64] + [_P] * 3 + [_P] * 6 + [_P]),
     'bfe_sl_force': (_INT, [_P, _I64] + [_P] * 3 + [_P, _INT, _INT, _INT] + [_P] * 6 + [_P]),
     'bfe_peer_buffer_create': (_INT, [_I64, C.POINTER(_P), C.c_char_p]),

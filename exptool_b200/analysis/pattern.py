@@ -3,10 +3,12 @@ pattern.py -- BarTransform (exptool/analysis/pattern.py:64-169): rotate a snapsh
 
 The m = 2 Fourier sums and the planar rotation run on the device (ops.bar_fourier_angle, ops.affine_xy ->
 bfe_bar_fourier, bfe_affine_xy); the class keeps the reference's interface (`.bar_angle`, `.data` dict with
-x, y, z, vx, vy, vz, m, potE, `.time`, `.filename`, `.comp`).  The other classes of the reference module
-(BarDetermine, pattern-speed fits) are post-processing and out of scope.
+x, y, z, vx, vy, vz, m, potE, `.time`, `.filename`, `.comp`).  Of BarDetermine only what the workflow driver
+potential.get_fields needs is mirrored (read_bar, frequency_and_derivative, find_barpattern: host-side post-processing
+of a printed bar file); bar tracking over file lists and the plotting helpers are out of scope.
 """
 import numpy as np
+from scipy.interpolate import UnivariateSpline
 
 from .. import ops
 
@@ -45,3 +47,54 @@ class BarTransform():
     def bar_fourier_compute(self, posx, posy, minr=0., maxr=1.):
         '''pattern.py:155-169: m = 2 phase angle of the particles with minr < R < maxr'''
         return ops.bar_fourier_angle(posx, posy, minr=minr, maxr=maxr)
+
+
+class BarDetermine():
+    '''BarDetermine (pattern.py:180-472), the parts potential.get_fields uses: a printed bar file (time, position
+    [, derivative] per line) -> pattern speed.'''
+
+    def __init__(self, **kwargs):
+        if 'file' in kwargs:
+            try:
+                self.read_bar(kwargs['file'])
+                print('pattern.BarDetermine: BarInstance sucessfully read.')
+            except Exception:
+                print('pattern.BarDetermine: no compatible bar file found.')
+
+    def frequency_and_derivative(self, smth_order=None, fft_order=None, spline_derivative=None, verbose=0):
+        '''pattern.py:362-401: backward differences, optionally replaced by a polynomial fit of the derivative or by the
+        derivative of a smoothing cubic spline of the position'''
+        if (smth_order or fft_order) and verbose:
+            print('Cannot assure proper functionality of both order smoothing and low pass filtering.')
+        self.deriv = np.zeros_like(self.pos)
+        for i in range(1, len(self.pos)):
+            self.deriv[i] = (self.pos[i] - self.pos[i - 1]) / (self.time[i] - self.time[i - 1])
+        if smth_order:
+            self.deriv = np.poly1d(np.polyfit(self.time, self.deriv, smth_order))(self.time)
+        if spline_derivative:
+            spl = UnivariateSpline(self.time, self.pos, k=3, s=spline_derivative)
+            self.deriv = (spl.derivative())(self.time)
+            self.dderiv = np.zeros_like(self.deriv)
+            for indx, timeval in enumerate(self.time):
+                self.dderiv[indx] = spl.derivatives(timeval)[2]
+
+    def read_bar(self, infile):
+        '''pattern.py:439-466'''
+        time, pos, deriv = [], [], []
+        with open(infile) as f:
+            for line in f:
+                q = [float(d) for d in line.split()]
+                time.append(q[0]); pos.append(q[1])
+                if len(q) > 2:
+                    deriv.append(q[2])
+        self.time = np.array(time); self.pos = np.array(pos); self.deriv = np.array(deriv)
+        if len(self.deriv) < 1:
+            BarDetermine.frequency_and_derivative(self)
+
+
+def find_barpattern(intime, BarInstance, smth_order=2):
+    '''pattern.py:549-578: the tabulated derivative nearest in time (scalar or array of times)'''
+    BarInstance.frequency_and_derivative(smth_order=smth_order)
+    if np.ndim(intime) > 0:
+        return np.array([BarInstance.deriv[abs(t - BarInstance.time).argmin()] for t in intime])
+    return BarInstance.deriv[abs(intime - BarInstance.time).argmin()]

@@ -8,6 +8,7 @@ are host-side NumPy, as in the reference.
 
 Not mirrored (outside the path): wake grids, plotting.
 """
+import os
 import time
 from collections import OrderedDict
 
@@ -119,13 +120,46 @@ _TABLE_CACHE = OrderedDict()
 _TABLE_CACHE_MAX = 4
 
 
+# How a host table is recognised on the next call (the reference API passes the NumPy tables on EVERY call):
+#   'sampled' (default): address, shape, dtype + the sum of 509 evenly spaced values and of the first / last 64 -- an
+#                        in-place edit that misses every sampled value goes unnoticed: call invalidate_tables() after
+#                        editing a table in place (or use 'full');
+#   'full'             : address, shape, dtype + a hash of ALL bytes (hashlib.blake2b; ~25 ms per 17 MB table per call);
+#   'off'              : no cache, tables are uploaded on every call.
+_CACHE_MODE = {'mode': os.environ.get('BFE_TABLE_CACHE', 'sampled')}
+
+
+def set_table_cache_mode(mode):
+    if mode not in ('sampled', 'full', 'off'):
+        raise ValueError("table cache mode must be 'sampled', 'full' or 'off'")
+    _CACHE_MODE['mode'] = mode
+    clear_table_cache()
+
+
+def invalidate_tables(*arrays):
+    """Forget the device copies made from these host arrays (all cached tables if none are given): call it after
+    editing a table in place.  Also drops the SL caches (spheresl.clear_table_cache)."""
+    if not arrays:
+        clear_table_cache()
+    else:
+        ptrs = set(np.asarray(a).__array_interface__['data'][0] for a in arrays if a is not None)
+        for key in [k for k in _TABLE_CACHE if any(fp is not None and fp[0] in ptrs for fp in k[0])]:
+            del _TABLE_CACHE[key]
+    from . import spheresl as _sl
+    _sl.clear_table_cache()
+
+
 def _fingerprint(a):
     if a is None:
         return None
     a = np.asarray(a)
     flat = a.reshape(-1)
+    head = (a.__array_interface__['data'][0], a.shape, a.dtype.str)
+    if _CACHE_MODE['mode'] == 'full':
+        import hashlib
+        return head + (hashlib.blake2b(np.ascontiguousarray(a).view(np.uint8).reshape(-1), digest_size=16).hexdigest(),)
     step = max(1, flat.size // 509)
-    return (a.__array_interface__['data'][0], a.shape, a.dtype.str, float(flat[::step].sum()))
+    return head + (float(flat[::step].sum()), float(flat[:64].sum()), float(flat[-64:].sum()))
 
 
 def device_tables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP,
@@ -134,7 +168,7 @@ def device_tables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE
     key = (tuple(_fingerprint(t) for t in (potC, potS, rforceC, zforceC, rforceS, zforceS)),
            int(MMAX), int(NMAX), float(XMIN), float(dX), float(YMIN), float(dY), int(NUMX), int(NUMY),
            float(ASCALE), float(HSCALE), int(CMAP), ops.torch.cuda.current_device() if ops.torch.cuda.is_available() else -1)
-    E = _TABLE_CACHE.get(key)
+    E = _TABLE_CACHE.get(key) if _CACHE_MODE['mode'] != 'off' else None
     if E is None:
         E = ops.EOFTables(potC, potS, MMAX, NMAX, XMIN, dX, YMIN, dY, NUMX, NUMY, ASCALE, HSCALE, CMAP,
                           rforceC=rforceC, zforceC=zforceC, rforceS=rforceS, zforceS=zforceS)

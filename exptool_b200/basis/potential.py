@@ -314,3 +314,27 @@ def make_fields(eof_file, sph_file, model_file, cos, sin, expcoef, halofac=1.0, 
     F.prep_tables()
     F.set_field_parameters()
     return F
+
+
+def get_fields(simulation_directory, simulation_name, intime, eof_file, sph_file, model_file, bar_file='', nhalo=1000000,
+               transform=True, fileprefix='OUT'):
+    '''potential.get_fields (potential.py:1243-1288): snapshot -> (Fields with coefficients and tables, pattern speed,
+    rotation frequency).  With transform the pattern speed comes from the printed bar file (pattern.BarDetermine).'''
+    from ..analysis import pattern
+    from ..io import particle
+    infile = simulation_directory + fileprefix + '.' + simulation_name + '.%05i' % intime
+    BarInstance = pattern.BarDetermine()
+    if transform:
+        BarInstance.read_bar(bar_file)
+        BarInstance.frequency_and_derivative(spline_derivative=2)
+        PSPDump = particle.Input(infile, comp='star')
+        patt = pattern.find_barpattern(PSPDump.time, BarInstance, smth_order=None)
+        rotfreq = patt / (2. * np.pi)
+    else:
+        patt = 0.
+        rotfreq = 0.
+    F = Fields(infile, eof_file, sph_file, model_file, nhalo=nhalo, transform=transform, no_odd=False, centering=True,
+               mutual_center=True)
+    F.total_coefficients()
+    F.prep_tables()
+    return F, patt, rotfreq

@@ -2,9 +2,9 @@
 spheresl.py -- drop-in for the hot-path entry points of exptool/basis/spheresl.py.
 
 Same names, argument order and return values as the reference; the arithmetic
-runs in libbfe.so (exptool_b200.ops -> include/bfe.h).  Density outputs
-(den0, den1) are outside the path and are returned as zeros
-where the reference's tuple layout requires a slot.
+runs in libbfe.so (exptool_b200.ops -> include/bfe.h), including the density
+outputs den0, den1 of all_eval / all_eval_particles with each function's own
+conventions.
 
 Not mirrored: wake grids, EXP-coefficient readers, rotation helpers
 (spheresl.py:1501-1764).
@@ -67,12 +67,9 @@ def device_tables_from_files(sph_file, model_file):
 
 
 def _fingerprint(a):
-    if a is None:
-        return None
-    a = np.asarray(a)
-    flat = a.reshape(-1)
-    step = max(1, flat.size // 509)
-    return (a.__array_interface__['data'][0], a.shape, a.dtype.str, float(flat[::step].sum()))
+    """as eof._fingerprint: one cache policy for both bases (eof.set_table_cache_mode / eof.invalidate_tables)"""
+    from . import eof as _eof
+    return _eof._fingerprint(a)
 
 
 def device_tables(xi, p0, d0, cmap, scale, evtable, eftable):
@@ -80,7 +77,8 @@ def device_tables(xi, p0, d0, cmap, scale, evtable, eftable):
     evtable = np.asarray(evtable); eftable = np.asarray(eftable)
     key = (_fingerprint(xi), _fingerprint(p0), _fingerprint(d0), _fingerprint(evtable), _fingerprint(eftable), int(cmap), float(scale),
            _dev_id())
-    H = _ARRAY_CACHE.get(key)
+    from . import eof as _eof
+    H = _ARRAY_CACHE.get(key) if _eof._CACHE_MODE['mode'] != 'off' else None
     if H is None:
         lmax = evtable.shape[0] - 1
         nmax = evtable.shape[1]
@@ -195,9 +193,9 @@ def compute_coefficients(PSPInput, sph_file, mod_file, verbose=1, no_odd=False):
     SL_Out.nmax = T['nmax']
     t1 = time.time()
     if parallel.sharded_api():          # opt-in: `with parallel.sharded():` -- every rank holds the same particle set
-        SL_Out.expcoef = parallel.raise_if_poisoned(parallel.sl_accumulate_sharded(H, x, y, z, m, no_odd=no_odd).cpu().numpy())
+        SL_Out.expcoef = parallel.raise_if_poisoned(parallel.sl_accumulate_host(H, x, y, z, m, no_odd=no_odd))
     else:                               # rank-local, like compute_coefficients_solitary
-        SL_Out.expcoef = H.accumulate(x, y, z, m, no_odd=no_odd).cpu().numpy()
+        SL_Out.expcoef = H.accumulate_host(x, y, z, m, no_odd=no_odd)
     if verbose > 0:
         dt = time.time() - t1
         print('spheresl.compute_coefficients: accumulation took {0:3.2f} seconds, or {1:4.2f} microseconds per orbit.'
@@ -257,9 +255,11 @@ def all_eval_particles(Particles, expcoef, sph_file, mod_file, verbose, L1=-1000
     H, _ = device_tables_from_files(sph_file, mod_file)
     x, y, z, _m = particle.particle_arrays(Particles)
     H.contract(expcoef, l1=L1, l2=L2, no_odd=NO_ODD)
-    pot0, pot1, potr, pott, potp, rr = ops.to_host(H.force(x, y, z))
     H.contract_density(expcoef, l1=L1, l2=L2, no_odd=NO_ODD)
-    den0, den1 = ops.to_host(H.density(x, y, z))
+    # ONE upload of x, y, z serves the potential and the density evaluation, ONE copy out of the eight rows
+    x, y, z = ops.dev(x), ops.dev(y), ops.dev(z)
+    out = ops.to_host(ops.torch.cat([H.density(x, y, z), H.force(x, y, z)]))
+    den0, den1, pot0, pot1, potr, pott, potp, rr = out
     return den0, den1, pot0, pot1, potr, pott, potp, rr
 
 

@@ -268,11 +268,11 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     if (norbit == 0) return BFE_OK;
     if (!state6) return BFE_ERR_ARG;
     if (traj && traj_stride < 1) return BFE_ERR_ARG;
-    if (ap_max < 1) ap_max = 1;
+    if (ap_max < 0) ap_max = 0;          // ap_max = 0: the reference's loop (integrate.py:126) takes no step at all
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = (int)((norbit + 127) / 128);
     // large batches without trajectory / apocentre bookkeeping: orbits kept cell-coherent by a re-sort every K steps
-    if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6) && !traj && !apse &&
+    if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6) && !traj && !apse && ap_max > 0 &&
         g_bfe_orbit_resort > 0 && norbit >= g_bfe_orbit_sort_min && norbit < ((int64_t)1 << 31) &&
         nint > 2 * (int64_t)g_bfe_orbit_resort + 2 && nint < ((int64_t)1 << 31))
         return bfe_leapfrog_sorted(he, hs, norbit, nint, dt, dt_orbit, rotfreq, state6, nsteps_out, stream);

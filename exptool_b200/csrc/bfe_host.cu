@@ -29,7 +29,8 @@ struct BfeHostPipe {
     int64_t cap = 0;                 // particles per staging buffer
     double* din[2] = {nullptr, nullptr};     // [4][cap]
     double* dout[2] = {nullptr, nullptr};    // [6][cap]
-    double* coef = nullptr;                  // per-chunk coefficient scratch, 2 * (mmax+1) * norder
+    double* coef = nullptr;                  // coefficient scratch (per-chunk block, running total)
+    size_t coef_cap = 0;
     cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2], ev_start;
     bool events = false;
 };
@@ -49,7 +50,7 @@ struct BfeKeepSet {
     cudaEvent_t ready = nullptr, released = nullptr;      // upload complete / last reader done
     bool has_reader = false;
 };
-static BfeKeepSet g_keep[16];
+static BfeKeepSet g_keep[16][2];            // [device][0 = EOF (disc) set, 1 = SL (halo) set]
 static std::mutex g_keep_mu;
 
 static uint64_t host_tag(const double* a, int64_t n) {
@@ -65,10 +66,10 @@ static uint64_t host_tag(const double* a, int64_t n) {
     return h;
 }
 
-static BfeKeepSet* keep_slot() {
+static BfeKeepSet* keep_slot(int kind) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    BfeKeepSet* k = &g_keep[dev];
+    BfeKeepSet* k = &g_keep[dev][kind];
     if (k->device != dev) {
         k->device = dev;
         if (cudaEventCreateWithFlags(&k->ready, cudaEventDisableTiming) != cudaSuccess ||
@@ -105,11 +106,11 @@ static int64_t pick_chunk(int64_t n) {
     return ((n + k - 1) / k + 15) / 16 * 16;
 }
 
-static int pipe_get(bfe_eof* h, int64_t chunk, bool need_out, BfeHostPipe** out) {
-    BfeHostPipe* p = (BfeHostPipe*)h->host_pipe;
+static int pipe_get(void** slot, size_t coef_doubles, int64_t chunk, bool need_out, BfeHostPipe** out) {
+    BfeHostPipe* p = (BfeHostPipe*)*slot;
     if (!p) {
         p = new BfeHostPipe();
-        h->host_pipe = p;
+        *slot = p;
         BFE_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
         BFE_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
@@ -119,7 +120,11 @@ static int pipe_get(bfe_eof* h, int64_t chunk, bool need_out, BfeHostPipe** out)
         }
         BFE_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
         p->events = true;
-        BFE_CUDA(cudaMalloc(&p->coef, 2 * (size_t)(h->g.mmax + 1) * h->g.norder * sizeof(double)));
+    }
+    if (coef_doubles > p->coef_cap) {
+        if (p->coef) { BFE_CUDA(cudaDeviceSynchronize()); cudaFree(p->coef); p->coef = nullptr; }
+        BFE_CUDA(cudaMalloc(&p->coef, coef_doubles * sizeof(double)));
+        p->coef_cap = coef_doubles;
     }
     if (chunk > p->cap) {
         BFE_CUDA(cudaDeviceSynchronize());
@@ -170,25 +175,21 @@ static cudaError_t copy_rows_d2h(double* const* rows, int nrows, int64_t lo, con
     return cudaSuccess;
 }
 
-// eof.accumulate on HOST particle arrays; the coefficients stay on the device (cos_out / sin_out are DEVICE
-// pointers) so that a multi-GPU caller can allreduce them before the one small copy out.
-extern "C" int bfe_eof_accumulate_host(bfe_eof* h, int64_t n, const double* hx, const double* hy, const double* hz,
-                                       const double* hm, double* cos_out, double* sin_out, void* stream_) {
-    if (!h || n < 0 || !cos_out || !sin_out) return BFE_ERR_ARG;
-    if (n > 0 && (!hx || !hy || !hz || !hm)) return BFE_ERR_ARG;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int ncoef = (h->g.mmax + 1) * h->g.norder;
-    if (n == 0) return bfe_eof_accumulate(h, 0, nullptr, nullptr, nullptr, nullptr, cos_out, sin_out, stream_);
+// Accumulation on HOST particle arrays (rows x, y, z, m); `run(len, d, pitch, dst)` enqueues the accumulation kernels of
+// one chunk whose rows start at d, d + pitch, ... and leaves its ncoef coefficients at dst.  The coefficients stay on the
+// device (out_dev) so that a multi-GPU caller can allreduce them before the one small copy out.
+template <class Run>
+static int accumulate_host_impl(void** pipe_slot, int kind, int64_t n, const double* const rows[4], int ncoef,
+                                double* out_dev, cudaStream_t stream, Run run) {
     const int64_t chunk = pick_chunk(n);
     BfeHostPipe* p = nullptr;
-    int rc = pipe_get(h, chunk, false, &p);
+    int rc = pipe_get(pipe_slot, (size_t)ncoef, chunk, false, &p);
     if (rc != BFE_OK) return rc;
-    const double* rows[4] = {hx, hy, hz, hm};
     BFE_CUDA(cudaEventRecord(p->ev_start, stream));
     BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
     // the upload lands in the kept buffer (full size: no double buffering needed) unless reuse is off or the set is huge
     std::unique_lock<std::mutex> lock(g_keep_mu);
-    BfeKeepSet* ks = (g_bfe_host_reuse && n <= ((int64_t)1 << 27)) ? keep_slot() : nullptr;
+    BfeKeepSet* ks = (g_bfe_host_reuse && n <= ((int64_t)1 << 27)) ? keep_slot(kind) : nullptr;
     if (ks) {
         ks->valid = false;
         if (ks->cap < n) {
@@ -217,13 +218,10 @@ extern "C" int bfe_eof_accumulate_host(bfe_eof* h, int64_t n, const double* hx, 
         BFE_CUDA(copy_rows_h2d(d, pitch, rows, 4, lo, len, p->s_in));
         BFE_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
         BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_in[b], 0));
-        double* c = k == 0 ? cos_out : p->coef;
-        double* s = k == 0 ? sin_out : p->coef + ncoef;
-        rc = bfe_eof_accumulate(h, len, d, d + pitch, d + 2 * pitch, d + 3 * pitch, c, s, stream_);
+        rc = run(len, d, pitch, k == 0 ? out_dev : p->coef);
         if (rc != BFE_OK) return rc;
         if (k > 0) {
-            bfe_coef_add_kernel<<<(ncoef + 255) / 256, 256, 0, stream>>>(cos_out, p->coef, ncoef);
-            bfe_coef_add_kernel<<<(ncoef + 255) / 256, 256, 0, stream>>>(sin_out, p->coef + ncoef, ncoef);
+            bfe_coef_add_kernel<<<(ncoef + 255) / 256, 256, 0, stream>>>(out_dev, p->coef, ncoef);
             BFE_LAUNCH_CHECK("bfe_coef_add_kernel");
         }
         BFE_CUDA(cudaEventRecord(p->ev_cmp[b], stream));
@@ -236,29 +234,61 @@ extern "C" int bfe_eof_accumulate_host(bfe_eof* h, int64_t n, const double* hx, 
     return BFE_OK;
 }
 
-// eof.accumulated_eval_particles on HOST arrays in and out (uses the held contraction).  On return all work is
-// enqueued; the six host arrays are complete once `stream` has been synchronised.
-extern "C" int bfe_eof_force_host(bfe_eof* h, int64_t n, const double* hx, const double* hy, const double* hz,
-                                  double* hp0, double* hp, double* hfr, double* hfp, double* hfz, double* hR,
-                                  void* stream_) {
-    if (!h || n < 0) return BFE_ERR_ARG;
-    if (!h->contracted) return BFE_ERR_STATE;
-    if (n == 0) return BFE_OK;
-    if (!hx || !hy || !hz || !hp0 || !hp || !hfr || !hfp || !hfz || !hR) return BFE_ERR_ARG;
+// eof.accumulate (eof.py:492) on host arrays: cos_out / sin_out are DEVICE pointers and need not be adjacent
+extern "C" int bfe_eof_accumulate_host(bfe_eof* h, int64_t n, const double* hx, const double* hy, const double* hz,
+                                       const double* hm, double* cos_out, double* sin_out, void* stream_) {
+    if (!h || n < 0 || !cos_out || !sin_out) return BFE_ERR_ARG;
+    if (n > 0 && (!hx || !hy || !hz || !hm)) return BFE_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
+    const int ncoef = (h->g.mmax + 1) * h->g.norder;
+    if (n == 0) return bfe_eof_accumulate(h, 0, nullptr, nullptr, nullptr, nullptr, cos_out, sin_out, stream_);
+    const double* rows[4] = {hx, hy, hz, hm};
+    // the pipeline sums chunk blocks of 2 * ncoef adjacent doubles: accumulate into a scratch pair, then copy out
+    BfeHostPipe* p = nullptr;
+    int rc = pipe_get(&h->host_pipe, 4 * (size_t)ncoef, pick_chunk(n), false, &p);
+    if (rc != BFE_OK) return rc;
+    double* total = p->coef + 2 * ncoef;
+    rc = accumulate_host_impl(&h->host_pipe, 0, n, rows, 2 * ncoef, total, stream,   // (its pipe_get asks for 2 * ncoef <= the 4 * ncoef held)
+                              [&](int64_t len, double* d, int64_t pitch, double* dst) {
+                                  return bfe_eof_accumulate(h, len, d, d + pitch, d + 2 * pitch, d + 3 * pitch, dst, dst + ncoef, stream_);
+                              });
+    if (rc != BFE_OK) return rc;
+    BFE_CUDA(cudaMemcpyAsync(cos_out, total, ncoef * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    BFE_CUDA(cudaMemcpyAsync(sin_out, total + ncoef, ncoef * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    return BFE_OK;
+}
+
+// spheresl.compute_coefficients_solitary (spheresl.py:567) on host arrays: expcoef is a DEVICE pointer
+extern "C" int bfe_sl_accumulate_host(bfe_sl* h, int64_t n, const double* hx, const double* hy, const double* hz,
+                                      const double* hm, int no_odd, double* expcoef, void* stream_) {
+    if (!h || n < 0 || !expcoef) return BFE_ERR_ARG;
+    if (n > 0 && (!hx || !hy || !hz || !hm)) return BFE_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return bfe_sl_accumulate(h, 0, nullptr, nullptr, nullptr, nullptr, no_odd, expcoef, stream_);
+    const int ncoef = h->g.nrow * h->g.nmax;
+    const double* rows[4] = {hx, hy, hz, hm};
+    return accumulate_host_impl(&h->host_pipe, 1, n, rows, ncoef, expcoef, stream,
+                                [&](int64_t len, double* d, int64_t pitch, double* dst) {
+                                    return bfe_sl_accumulate(h, len, d, d + pitch, d + 2 * pitch, d + 3 * pitch, no_odd, dst, stream_);
+                                });
+}
+
+// Evaluation on HOST arrays in (x, y, z) and out (six rows); `run(len, d, pitch, o, opitch)` enqueues the evaluation of one
+// chunk.  On return all work is enqueued; the six host arrays are complete once `stream` has been synchronised.
+template <class Run>
+static int force_host_impl(void** pipe_slot, int kind, int64_t n, const double* const rows[3], double* const orow[6],
+                           cudaStream_t stream, Run run) {
     const int64_t chunk = pick_chunk(n);
     BfeHostPipe* p = nullptr;
-    int rc = pipe_get(h, chunk, true, &p);
+    int rc = pipe_get(pipe_slot, 8, chunk, true, &p);
     if (rc != BFE_OK) return rc;
-    const double* rows[3] = {hx, hy, hz};
-    double* orow[6] = {hp0, hp, hfr, hfp, hfz, hR};
     BFE_CUDA(cudaEventRecord(p->ev_start, stream));
     BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_start, 0));
-    // the particles accumulate_host uploaded last, if these are the same host arrays with the same content tag
+    // the particles the accumulation uploaded last, if these are the same host arrays with the same content tag
     std::unique_lock<std::mutex> lock(g_keep_mu);
-    BfeKeepSet* ks = g_bfe_host_reuse ? keep_slot() : nullptr;
-    if (ks && !(ks->valid && ks->n == n && ks->hp[0] == hx && ks->hp[1] == hy && ks->hp[2] == hz &&
-                ks->tag[0] == host_tag(hx, n) && ks->tag[1] == host_tag(hy, n) && ks->tag[2] == host_tag(hz, n)))
+    BfeKeepSet* ks = g_bfe_host_reuse ? keep_slot(kind) : nullptr;
+    if (ks && !(ks->valid && ks->n == n && ks->hp[0] == rows[0] && ks->hp[1] == rows[1] && ks->hp[2] == rows[2] &&
+                ks->tag[0] == host_tag(rows[0], n) && ks->tag[1] == host_tag(rows[1], n) && ks->tag[2] == host_tag(rows[2], n)))
         ks = nullptr;
     if (ks) BFE_CUDA(cudaStreamWaitEvent(stream, ks->ready, 0));
     g_bfe_host_reused_last = ks ? 1 : 0;
@@ -278,8 +308,7 @@ extern "C" int bfe_eof_force_host(bfe_eof* h, int64_t n, const double* hx, const
         }
         if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_out[b], 0));       // chunk k-2 has left dout[b]
         double* o = p->dout[b];
-        rc = bfe_eof_force_contracted(h, len, d, d + pitch, d + 2 * pitch, o, o + p->cap, o + 2 * p->cap,
-                                      o + 3 * p->cap, o + 4 * p->cap, o + 5 * p->cap, stream_);
+        rc = run(len, d, pitch, o, p->cap);
         if (rc != BFE_OK) return rc;
         BFE_CUDA(cudaEventRecord(p->ev_cmp[b], stream));
         BFE_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_cmp[b], 0));
@@ -291,4 +320,38 @@ extern "C" int bfe_eof_force_host(bfe_eof* h, int64_t n, const double* hx, const
     BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_out[(k - 1) & 1], 0));
     if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_out[k & 1], 0));
     return BFE_OK;
+}
+
+// eof.accumulated_eval_particles (eof.py:989) on host arrays (uses the held contraction)
+extern "C" int bfe_eof_force_host(bfe_eof* h, int64_t n, const double* hx, const double* hy, const double* hz,
+                                  double* hp0, double* hp, double* hfr, double* hfp, double* hfz, double* hR,
+                                  void* stream_) {
+    if (!h || n < 0) return BFE_ERR_ARG;
+    if (!h->contracted) return BFE_ERR_STATE;
+    if (n == 0) return BFE_OK;
+    if (!hx || !hy || !hz || !hp0 || !hp || !hfr || !hfp || !hfz || !hR) return BFE_ERR_ARG;
+    const double* rows[3] = {hx, hy, hz};
+    double* orow[6] = {hp0, hp, hfr, hfp, hfz, hR};
+    return force_host_impl(&h->host_pipe, 0, n, rows, orow, (cudaStream_t)stream_,
+                           [&](int64_t len, double* d, int64_t pitch, double* o, int64_t op) {
+                               return bfe_eof_force_contracted(h, len, d, d + pitch, d + 2 * pitch, o, o + op, o + 2 * op,
+                                                               o + 3 * op, o + 4 * op, o + 5 * op, stream_);
+                           });
+}
+
+// spheresl.all_eval_particles (spheresl.py:1240) potential outputs on host arrays (uses the held contraction)
+extern "C" int bfe_sl_force_host(bfe_sl* h, int64_t n, const double* hx, const double* hy, const double* hz,
+                                 double* hpot0, double* hpot1, double* hpotr, double* hpott, double* hpotp, double* hrr,
+                                 void* stream_) {
+    if (!h || n < 0) return BFE_ERR_ARG;
+    if (!h->contracted) return BFE_ERR_STATE;
+    if (n == 0) return BFE_OK;
+    if (!hx || !hy || !hz || !hpot0 || !hpot1 || !hpotr || !hpott || !hpotp || !hrr) return BFE_ERR_ARG;
+    const double* rows[3] = {hx, hy, hz};
+    double* orow[6] = {hpot0, hpot1, hpotr, hpott, hpotp, hrr};
+    return force_host_impl(&h->host_pipe, 1, n, rows, orow, (cudaStream_t)stream_,
+                           [&](int64_t len, double* d, int64_t pitch, double* o, int64_t op) {
+                               return bfe_sl_force_contracted(h, len, d, d + pitch, d + 2 * pitch, o, o + op, o + 2 * op,
+                                                              o + 3 * op, o + 4 * op, o + 5 * op, stream_);
+                           });
 }

@@ -93,6 +93,7 @@ struct bfe_sl {
     int64_t sort_cap;
     void* sort_ws;
     int table_fp32;      // as bfe_eof::table_fp32 (SL-only evaluation calls)
+    void* host_pipe;     // staging buffers / streams of the host-array entry points (bfe_host.cu), lazily made
 };
 
 extern "C" void bfe_count_launch(int n);

@@ -496,7 +496,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
-    h->sort_cap = 0; h->sort_ws = nullptr; h->table_fp32 = -1;
+    h->sort_cap = 0; h->sort_ws = nullptr; h->table_fp32 = -1; h->host_pipe = nullptr;
     BFE_CUDA(cudaMemsetAsync(h->a_con, 0, nr * h->kpad * 2 * sizeof(double), stream));
     BFE_CUDA(cudaMemcpyAsync(h->xi, xi, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     BFE_CUDA(cudaMemcpyAsync(h->p0, p0, nr * sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -528,6 +528,7 @@ extern "C" void bfe_sl_destroy(bfe_sl* h) {
     cudaFree(h->ev); if (h->ad_con) cudaFree(h->ad_con); if (h->a3f) cudaFree(h->a3f);
     cudaFree(h->a_con); cudaFree(h->a3); cudaFree(h->partial); cudaFree(h->counter);
     if (h->sort_ws) cudaFree(h->sort_ws);
+    bfe_host_pipe_destroy(h->host_pipe);
     delete h;
 }
 

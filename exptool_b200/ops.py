@@ -342,6 +342,36 @@ class SLTables(object):
             raise ValueError('particle arrays differ in length')
         return torch.ops.exptool_b200.sl_accumulate(self.handle, x, y, z, m, self.nrow, self.nmax, bool(no_odd))
 
+    # -- host-array entry points (chunked copy / compute pipeline inside libbfe, bfe_host.cu)
+    def accumulate_host(self, x, y, z, m, no_odd=False, reduce=None):
+        """spheresl.compute_coefficients for HOST particle arrays -> expcoef NumPy ((lmax+1)^2, nmax).  `reduce`, if given,
+        is applied to the device tensor before it is copied out (multi-GPU allreduce).  Device tensors take the one-shot path."""
+        hx, hy, hz, hm = [_host_tensor(a) for a in (x, y, z, m)]
+        n = hx.numel()
+        if not (hy.numel() == n and hz.numel() == n and hm.numel() == n):
+            raise ValueError('particle arrays differ in length')
+        if hx.is_cuda:
+            buf = self.accumulate(hx, hy, hz, hm, no_odd=no_odd)
+        else:
+            buf = torch.empty((self.nrow, self.nmax), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.bfe_sl_accumulate_host(self.h, n, _ptr(hx), _ptr(hy), _ptr(hz), _ptr(hm), int(bool(no_odd)),
+                                                       _ptr(buf), _stream()))
+        if reduce is not None:
+            reduce(buf)
+        return to_host(buf)            # synchronises the stream: the host inputs may be released after this
+
+    def force_host(self, x, y, z):
+        """spheresl.all_eval_particles potential outputs for HOST arrays -> (6, n) NumPy pot0, pot1, potr, pott, potp, rr
+        (uses the held contraction; pinned result buffer from torch's caching host allocator)."""
+        hx, hy, hz = [_host_tensor(a) for a in (x, y, z)]
+        n = hx.numel()
+        if hx.is_cuda:
+            return to_host(self.force(hx, hy, hz))
+        h = pinned_empty((6, n))
+        _lib.check(self.lib.bfe_sl_force_host(self.h, n, _ptr(hx), _ptr(hy), _ptr(hz), *[_ptr(h[i]) for i in range(6)], _stream()))
+        torch.cuda.current_stream().synchronize()
+        return h.numpy()
+
     def _coef(self, c):
         c = dev(c)
         if tuple(c.shape) != (self.nrow, self.nmax):

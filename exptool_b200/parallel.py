@@ -296,6 +296,16 @@ def sl_accumulate_sharded(H, x, y, z, m, no_odd=False, already_sharded=False):
     return c
 
 
+def sl_accumulate_host(H, x, y, z, m, no_odd=False, already_sharded=False):
+    """sl_accumulate_sharded for HOST particle arrays, returning NumPy expcoef (chunked copy / compute pipeline,
+    ops.SLTables.accumulate_host; the allreduce runs on the device before the one small copy out)."""
+    if is_distributed() and not already_sharded:
+        _check_same_count(len(x))
+        lo, hi = my_shard(len(x))
+        x, y, z, m = _slice(x, lo, hi), _slice(y, lo, hi), _slice(z, lo, hi), _slice(m, lo, hi)
+    return H.accumulate_host(x, y, z, m, no_odd=no_odd, reduce=allreduce_sum_ if is_distributed() else None)
+
+
 def accumulate_series(E, H, snapshots, no_odd=False):
     """
     Coefficient time series (BASELINE.json configs[4]): `snapshots` yields, per

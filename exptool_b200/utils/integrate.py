@@ -9,8 +9,10 @@ field truncation, launches, and formats the Orbits dictionary.
 compute_timestep, the four integrate_grid* drivers and the orbit-map text format
  are mirrored too: a whole (radius, velocity[, z, vz]) grid is one
 batched time-step estimate plus one leapfrog launch with a step size per orbit.
-Not mirrored: the multiprocessing wrappers (do_integrate_multi, run_time*), which only fan
-the grid out over processes.
+do_integrate_multi and the re-forming helpers are mirrored (the Pool fan-out becomes ranks / one batched launch);
+run_time / run_time_mod (the notebook workflow drivers) are mirrored at the end of this file.  leapfrog_integrate accepts
+the reference's duck-typed FieldInstance: an exptool_b200 Fields runs on the GPU, any other object with
+set_field_parameters / return_forces_cart is integrated with its own force routine, as the reference would.
 """
 import time
 
@@ -42,14 +44,49 @@ def gen_init_step(xpos, vtan, z0=0.0, zvel0=0.):
 def _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n):
     FieldInstance.set_field_parameters(no_odd=no_odd, halo_l=halo_l, halo_n=halo_n, disk_m=disk_m, disk_n=disk_n)
     if not hasattr(FieldInstance, 'device_handles'):
-        raise TypeError('leapfrog_integrate: FieldInstance must be an exptool_b200.basis.potential.Fields '
-                        '(the time loop runs on the GPU; arbitrary Python force callbacks are not supported)')
+        raise TypeError('this entry point needs an exptool_b200.basis.potential.Fields (the time loop runs on the GPU); '
+                        'leapfrog_integrate itself also accepts any object with set_field_parameters / return_forces_cart')
     return FieldInstance.device_handles()
 
 
 def _precision(FieldInstance):
-    """the Fields instance's table precision (table_fp32) around a device call"""
+    """kept for callers of round 1: table precision lives in the Fields instance's device handles now"""
     return ops.table_precision(getattr(FieldInstance, 'table_fp32', False))
+
+
+def _leapfrog_generic(FieldInstance, nint, dt, initpos, initvel, rotfreq, force, ap_max, apse):
+    """integrate.leapfrog_integrate (integrate.py:94-190) for a FOREIGN field object -- anything with
+    set_field_parameters / return_forces_cart, the reference's duck-typed protocol (integrate.py:61-64).  The force
+    evaluation belongs to the caller's object, so there is nothing to put on the GPU: the reference's own scalar loop."""
+    times = np.arange(0, nint, 1) * dt
+    barpos = 2. * np.pi * rotfreq * times
+    X = np.zeros(nint); Y = np.zeros(nint); Z = np.zeros(nint)
+    VX = np.zeros(nint); VY = np.zeros(nint); VZ = np.zeros(nint)
+    FX = np.zeros(nint); FY = np.zeros(nint); FZ = np.zeros(nint); P = np.zeros(nint)
+    X[0], Y[0], Z[0] = initpos[0], initpos[1], initpos[2]
+    VX[0], VY[0], VZ[0] = initvel[0], initvel[1], initvel[2]
+    step = 1
+    dfx, hfx, dfy, hfy, dfz, hfz, dp, hp = FieldInstance.return_forces_cart(X[0], Y[0], Z[0], rotpos=barpos[0])
+    FX[0], FY[0], FZ[0], P[0] = dfx + hfx, dfy + hfy, dfz + hfz, dp + hp
+    n_aps = 0
+    while (n_aps < ap_max) & (step < nint):                                                   # 126
+        X[step] = X[step - 1] + (VX[step - 1] * dt) + (0.5 * FX[step - 1] * (dt ** 2.))       # 129-131
+        Y[step] = Y[step - 1] + (VY[step - 1] * dt) + (0.5 * FY[step - 1] * (dt ** 2.))
+        Z[step] = Z[step - 1] + (VZ[step - 1] * dt) + (0.5 * FZ[step - 1] * (dt ** 2.))
+        dfx, hfx, dfy, hfy, dfz, hfz, dp, hp = FieldInstance.return_forces_cart(X[step], Y[step], Z[step], rotpos=barpos[step])
+        FX[step], FY[step], FZ[step], P[step] = dfx + hfx, dfy + hfy, dfz + hfz, dp + hp
+        VX[step] = VX[step - 1] + (0.5 * (FX[step - 1] + FX[step]) * dt)                      # 141-143
+        VY[step] = VY[step - 1] + (0.5 * (FY[step - 1] + FY[step]) * dt)
+        VZ[step] = VZ[step - 1] + (0.5 * (FZ[step - 1] + FZ[step]) * dt)
+        if apse and step > 1:                                                                 # 146-153
+            r0 = X[step - 2] * X[step - 2] + Y[step - 2] * Y[step - 2]
+            r1 = X[step - 1] * X[step - 1] + Y[step - 1] * Y[step - 1]
+            r2 = X[step] * X[step] + Y[step] * Y[step]
+            if (r1 > r0) & (r1 > r2):
+                n_aps += 1
+        step += 1
+    traj = np.stack([X, Y, Z, VX, VY, VZ, P, FX, FY, FZ], axis=1)[:step]
+    return step, traj
 
 
 def leapfrog_integrate(FieldInstance, nint, dt, initpos, initvel, rotfreq=0., no_odd=False,
@@ -59,14 +96,19 @@ def leapfrog_integrate(FieldInstance, nint, dt, initpos, initvel, rotfreq=0., no
     T, X, Y, Z, VX, VY, VZ, P [, FX, FY, FZ], TX, TY, VTX, VTY, each of length `step`.
     '''
     t0 = time.time()
-    E, H = _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n)
-    pos0 = np.asarray(initpos, dtype=np.float64).reshape(3, 1)
-    vel0 = np.asarray(initvel, dtype=np.float64).reshape(3, 1)
-    with _precision(FieldInstance):
+    if not hasattr(FieldInstance, 'device_handles'):
+        # the reference's protocol is duck-typed (integrate.py:61-64, 89, 118): a foreign field object is integrated with
+        # its own return_forces_cart, exactly as the reference would
+        FieldInstance.set_field_parameters(no_odd=no_odd, halo_l=halo_l, halo_n=halo_n, disk_m=disk_m, disk_n=disk_n)
+        step, traj = _leapfrog_generic(FieldInstance, nint, dt, initpos, initvel, rotfreq, force, ap_max, apse)
+    else:
+        E, H = _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n)
+        pos0 = np.asarray(initpos, dtype=np.float64).reshape(3, 1)
+        vel0 = np.asarray(initvel, dtype=np.float64).reshape(3, 1)
         state, traj, nsteps = ops.leapfrog(E, H, pos0, vel0, nint, dt, rotfreq=rotfreq, traj_stride=1,
                                            apse=apse, ap_max=ap_max)
-    step = int(nsteps.cpu().numpy()[0])
-    traj = traj.cpu().numpy()[:step, :, 0]
+        step = int(nsteps.cpu().numpy()[0])
+        traj = traj.cpu().numpy()[:step, :, 0]
     times = np.arange(0, nint, 1) * dt
     barpos = (2. * np.pi * rotfreq * times)[0:step]
     if verbose:
@@ -99,9 +141,8 @@ def leapfrog_integrate_batch(FieldInstance, nint, dt, initpos, initvel, rotfreq=
     (no communication; outputs stay sharded).
     '''
     E, H = _handles(FieldInstance, no_odd, halo_l, halo_n, disk_m, disk_n)
-    with _precision(FieldInstance):
-        state, traj, nsteps = ops.leapfrog(E, H, initpos, initvel, nint, dt, rotfreq=rotfreq, traj_stride=traj_stride,
-                                           apse=apse, ap_max=ap_max)
+    state, traj, nsteps = ops.leapfrog(E, H, initpos, initvel, nint, dt, rotfreq=rotfreq, traj_stride=traj_stride,
+                                       apse=apse, ap_max=ap_max)
     if return_device:
         return dict(STATE=state, TRAJ=traj, NSTEPS=nsteps)
     s = state.cpu().numpy()
@@ -325,3 +366,88 @@ def read_integrations_3D(infile):
             for k, key in enumerate(('X', 'Y', 'Z', 'TX', 'TY', 'VX', 'VY', 'VZ')):
                 D[key][linenum] = d[(k * npoints) + 6:((k + 1) * npoints) + 6]
     return D
+
+
+# ---------------------------------------------------------------------------
+# workflow drivers -- integrate.py:571-755 (what the notebooks call)
+# ---------------------------------------------------------------------------
+def run_time(simulation_directory, simulation_name, eof_file, sph_file, model_file, intime, rads, vels, nint, dt, no_odd, halo_l,
+             max_m, dyn_res, ap_max, verbose, nprocs=-1, omegap=-1., orbitfile='', transform=True, fileprefix='OUT', launch='x'):
+    '''integrate.run_time (integrate.py:571-635): fields of one snapshot -> orbit grid -> omap text file.  As in the
+    reference, get_fields is called without a bar file here.'''
+    from ..basis import potential
+    if verbose:
+        print('exptool.integrate.run_time: in directory {}, run {} at output {}, with transform={}'.format(
+            simulation_directory, simulation_name, intime, transform))
+    F, patt, rotfreq = potential.get_fields(simulation_directory, simulation_name, intime, eof_file, sph_file, model_file,
+                                            transform=transform, fileprefix=fileprefix)
+    if omegap >= 0.:
+        patt = omegap
+    rotfreq = -1. * abs(patt / (2. * np.pi))
+    OrbitArray = do_integrate_multi(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, max_m, dyn_res, ap_max, verbose=verbose,
+                                    nprocs=nprocs, launch=launch)
+    fname = orbitfile if orbitfile != '' else simulation_directory + 'omap_' + str(intime) + '.txt'
+    with open(fname, 'w') as f:
+        print_orbit_array(f, OrbitArray)
+
+
+def run_time_mod(simulation_directory, simulation_name, eof_file, sph_file, model_file, intime, rads, vels, nint, dt, no_odd,
+                 halo_l, max_m, dyn_res, ap_max, verbose, nprocs=-1, omegap=-1., orbitfile='', transform=False, save_field=True,
+                 field_file_name='', field_file=None, bar_file='', fileprefix='OUT', threedee=False, zs=None, vzs=None,
+                 launch='x'):
+    '''integrate.run_time_mod (integrate.py:638-755): as run_time, with the frozen-field file (save / restore), an explicit
+    bar file for the transform, and the 3-D launch grid.'''
+    from ..basis import potential
+    from ..analysis import pattern
+    from ..io import particle
+    if verbose:
+        print('exptool.integrate.run_time: in directory {}, run {} at output {}, with transform={}'.format(
+            simulation_directory, simulation_name, intime, transform))
+    if transform is True and bar_file == '':
+        print('error - no bar file supplied for transform')
+        return
+    if field_file is None:
+        F, patt, rotfreq = potential.get_fields(simulation_directory, simulation_name, intime, eof_file, sph_file, model_file,
+                                                transform=transform, bar_file=bar_file, fileprefix=fileprefix)
+        if save_field is True:
+            if str(field_file_name) != '':
+                F.save_field(str(field_file_name))
+            else:
+                print('saving field file with default name (field_file) to local directory')
+                F.save_field('field_file')
+    else:
+        print('field file supplied! File name:')
+        print(field_file_name)
+        F = potential.restore_field(str(field_file_name))
+        if transform:
+            BarInstance = pattern.BarDetermine()
+            BarInstance.read_bar(bar_file)
+            BarInstance.frequency_and_derivative(spline_derivative=2)
+            infile = simulation_directory + fileprefix + '.' + simulation_name + '.{0:05d}'.format(intime)
+            PSPDump = particle.Input(infile, comp='star')
+            patt = pattern.find_barpattern(PSPDump.time, BarInstance, smth_order=None)
+        else:
+            patt = 0.
+    if omegap >= 0.:
+        patt = omegap
+    rotfreq = -1. * abs(patt / (2. * np.pi))
+    if threedee is False:
+        print('launching from ', launch, ' axis')
+        OrbitArray = do_integrate_multi(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, max_m, dyn_res, ap_max,
+                                        verbose=verbose, nprocs=nprocs, launch=launch)
+        if orbitfile == '':
+            print('Saving 2D orbit')
+        fname = orbitfile if orbitfile != '' else simulation_directory + 'omap_' + str(intime) + '.txt'
+        with open(fname, 'w') as f:
+            print_orbit_array(f, OrbitArray)
+    else:
+        if (zs is None) or (vzs is None):
+            print('ERROR: 3D orbit specified, but no z or vz values passed!')
+            return
+        OrbitArray = do_integrate_multi(rads, vels, F, nint, dt, rotfreq, no_odd, halo_l, max_m, dyn_res, ap_max,
+                                        verbose=verbose, nprocs=nprocs, threedee=threedee, zs=zs, vzs=vzs, launch=launch)
+        if orbitfile == '':
+            print('Saving 3D orbit')
+        fname = orbitfile if orbitfile != '' else simulation_directory + 'omap_3D_' + str(intime) + '.txt'
+        with open(fname, 'w') as f:
+            print_orbit_array_3D(f, OrbitArray)

@@ -116,7 +116,10 @@ int bfe_eof_force_prepared(bfe_eof* h, double* p0, double* p, double* fr, double
 /* Host-array entry points: the same two passes for particle arrays in HOST memory (what the reference's Python
  * functions receive and return: eof.accumulate eof.py:492, eof.accumulated_eval_particles eof.py:989).  The set is
  * cut into chunks and copy-in, kernels and copy-out run as a three-stage pipeline on internal streams (pinned
- * host memory gives asynchronous DMA; pageable memory is accepted and copies synchronously).
+ * host memory gives asynchronous DMA; pageable memory is accepted and copies synchronously).  One upload per snapshot
+ * (option "host_reuse", default 1): bfe_eof_accumulate_host ALWAYS uploads and keeps its device copy; a following
+ * bfe_eof_force_host on the same host arrays (same pointers, length and content tag: a hash of the first / last 64 and of
+ * 1024 evenly spaced values per array) evaluates from that copy instead of uploading x, y, z again.
  *   bfe_eof_accumulate_host: hx..hm host arrays of n doubles; cos_out / sin_out are DEVICE buffers (so a
  *       multi-GPU caller can allreduce before copying 2 kB out), complete in stream order.
  *   bfe_eof_force_host: hx, hy, hz host inputs; hp0..hR host outputs of n doubles each, complete once `stream`
@@ -181,6 +184,19 @@ int bfe_sl_force_contracted(bfe_sl* h, int64_t n,
                             const double* x, const double* y, const double* z,
                             double* pot0, double* pot1, double* potr, double* pott, double* potp,
                             double* rr, void* stream);
+
+/* Host-array entry points of the SL passes, as bfe_eof_*_host: chunked copy-in | kernels | copy-out pipeline, the
+ * evaluation of the arrays that were just accumulated runs from the accumulation's upload (option "host_reuse").
+ *   bfe_sl_accumulate_host: spheresl.compute_coefficients (spheresl.py:439-475); expcoef is a DEVICE buffer.
+ *   bfe_sl_force_host     : spheresl.all_eval_particles / eval_particles (spheresl.py:1240, 502): six HOST outputs
+ *                           pot0, pot1, potr, pott, potp, rr, complete once `stream` has been synchronised. */
+int bfe_sl_accumulate_host(bfe_sl* h, int64_t n,
+                           const double* hx, const double* hy, const double* hz, const double* hm,
+                           int no_odd, double* expcoef, void* stream);
+int bfe_sl_force_host(bfe_sl* h, int64_t n,
+                      const double* hx, const double* hy, const double* hz,
+                      double* hpot0, double* hpot1, double* hpotr, double* hpott, double* hpotp, double* hrr,
+                      void* stream);
 
 int bfe_sl_force(bfe_sl* h, int64_t n,
                  const double* x, const double* y, const double* z,

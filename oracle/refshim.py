@@ -49,6 +49,7 @@ def load():
                         ('halo_methods', 'exptool.utils.halo_methods'),
                         ('integrate', 'exptool.utils.integrate'),
                         ('particle', 'exptool.io.particle'),
-                        ('orbit', 'exptool.orbits.orbit')]:
+                        ('orbit', 'exptool.orbits.orbit'),
+                        ('pattern', 'exptool.analysis.pattern')]:
         mods[short] = importlib.import_module(full)
     return mods

@@ -276,6 +276,25 @@ def test_frozen_field_timestep_and_grids(api, name):
         parts = integrate.redistribute_arrays(np.arange(11), 3)
         assert [len(p_) for p_ in parts] == [5, 3, 3] and np.array_equal(np.concatenate(parts), np.arange(11))
         assert integrate.re_form_orbit_arrays([g[:1], g[1:]]).shape == g.shape
+        # run_time_mod (integrate.py:638-755), the workflow driver of the notebooks, on the frozen-field file: restore ->
+        # rotfreq = -|omegap / 2 pi| -> do_integrate_multi -> omap text file (2-D and 3-D launch grids)
+        omega = 2. * np.pi * abs(meta['rotfreq'])
+        of2, of3 = os.path.join(tmp, 'omap.txt'), os.path.join(tmp, 'omap3.txt')
+        with contextlib.redirect_stdout(io.StringIO()):
+            integrate.run_time_mod(tmp + '/', 'run', ef, sf, mf, 7, rads, vels, 40, 1.0e-5, False, -1, -1, 100., 1000, 0,
+                                   omegap=omega, orbitfile=of2, field_file=ff, field_file_name=ff)
+            integrate.run_time_mod(tmp + '/', 'run', ef, sf, mf, 7, rads[:2], vels, 24, 1.0e-5, False, -1, -1, 100., 1000, 0,
+                                   omegap=omega, orbitfile=of3, field_file=ff, field_file_name=ff, threedee=True,
+                                   zs=d['grid_zs'], vzs=d['grid_vzs'])
+            want2 = integrate.do_integrate_multi(rads, vels, R, 40, 1.0e-5, -abs(meta['rotfreq']), False, -1, -1, 100., 1000)
+        ref2 = os.path.join(tmp, 'ref2.txt')
+        with open(ref2, 'w') as fh:
+            integrate.print_orbit_array(fh, want2)
+        assert open(of2).read() == open(ref2).read() and os.path.getsize(of2) > 1000
+        assert os.path.getsize(of3) > 1000 and len(open(of3).readlines()) == 2 * len(vels) * len(d['grid_zs']) * len(d['grid_vzs'])
+        # ap_max = 0: the reference's loop takes no step (integrate.py:126)
+        O0 = integrate.leapfrog_integrate(F, 20, 1.0e-5, d['pos0'][:, 0], d['vel0'][:, 0], ap_max=0, apse=True)
+        assert len(O0['T']) == 1 and O0['X'][0] == d['pos0'][0, 0]
 
 
 def test_eof_host_pipeline_matches_device(api):
@@ -540,3 +559,37 @@ def test_torch_library_custom_ops(api):
     with pytest.raises(Exception):                                # no CPU kernel behind the ops
         T.eof_force(E.handle, torch.zeros(4, dtype=torch.float64), torch.zeros(4, dtype=torch.float64),
                     torch.zeros(4, dtype=torch.float64))
+
+
+def test_sl_host_pipeline_matches_device(api):
+    """spheresl.compute_coefficients through the chunked host pipeline (bfe_sl_accumulate_host) and all_eval_particles with
+    one upload / one copy out, on a set large enough for several chunks, against the one-shot device path."""
+    import torch
+    from exptool_b200 import ops
+    spheresl = api['spheresl']
+    d, meta = load_golden('sl_std_l4')
+    with tempfile.TemporaryDirectory() as tmp:
+        sf, mf = _sl_files(tmp, meta)
+        n = 2 * 131072 + 4321
+        x, y, z, m = S.hernquist_halo(n, 23)
+        H, T = spheresl.device_tables_from_files(sf, mf)
+        want = H.accumulate(x, y, z, m).cpu().numpy()
+        for P in (S.ParticleSet(x, y, z, m), tuple(torch.from_numpy(a).pin_memory() for a in (x, y, z, m))):
+            SO = spheresl.compute_coefficients(P, sf, mf, verbose=0)
+            assert SO.expcoef.shape == want.shape and relerr(SO.expcoef, want) < 1e-13
+        got = H.accumulate_host(x, y, z, m, no_odd=True)
+        assert relerr(got, H.accumulate(x, y, z, m, no_odd=True).cpu().numpy()) < 1e-13
+        H.contract(want)
+        ref = H.force(x, y, z).cpu().numpy()
+        pin = tuple(torch.from_numpy(a).pin_memory() for a in (x, y, z))
+        H.accumulate_host(pin[0], pin[1], pin[2], torch.from_numpy(m).pin_memory())
+        for args in ((x, y, z), pin):
+            out = H.force_host(*args)
+            assert out.shape == (6, n)
+            for k in range(6):
+                assert relerr(out[k], ref[k]) < 1e-13, k
+        assert ops.get_option('host_reused_last') == 1          # the pinned set is the one just accumulated
+        full = spheresl.all_eval_particles(S.ParticleSet(x[:5000], y[:5000], z[:5000], m[:5000]), want, sf, mf, 0)
+        assert len(full) == 8
+        for k in range(6):
+            assert relerr(full[2 + k], ref[k][:5000]) < 1e-13, k

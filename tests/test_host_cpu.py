@@ -374,3 +374,48 @@ def test_orbit_map_text_format_roundtrip():
         D3 = integrate.read_integrations_3D(fn3)
         g3 = d['grid3']
         assert np.allclose(D3['Z'][1], g3[0, 0, 1, 0, 2]) and np.allclose(D3['VZ'][1], g3[0, 0, 1, 0, 7])
+
+
+def test_table_cache_modes_and_invalidate():
+    """eof.set_table_cache_mode: 'sampled' (default) can miss an in-place edit between sampled values -- invalidate_tables()
+    is the explicit remedy -- 'full' hashes every byte."""
+    from exptool_b200.basis import eof
+    a = np.arange(200000.0).reshape(200, 1000)
+    try:
+        f1 = eof._fingerprint(a)
+        a[0, 0] += 1.0                       # the first / last 64 values are always part of the tag
+        assert eof._fingerprint(a) != f1
+        eof.set_table_cache_mode('full')
+        f1 = eof._fingerprint(a)
+        a[57, 311] += 1.0
+        assert eof._fingerprint(a) != f1
+        with pytest.raises(ValueError):
+            eof.set_table_cache_mode('sometimes')
+    finally:
+        eof.set_table_cache_mode('sampled')
+    eof.invalidate_tables(a)                 # no entry yet: a no-op that must not raise
+    eof.invalidate_tables()
+
+
+def test_leapfrog_integrate_accepts_foreign_field_objects():
+    """integrate.leapfrog_integrate with the reference's duck-typed FieldInstance protocol (integrate.py:61-64): an object
+    that is not an exptool_b200 Fields is integrated with its own return_forces_cart -- here a Kepler potential, whose
+    energy the velocity-Verlet scheme conserves to O(dt^2)."""
+    from exptool_b200.utils import integrate
+
+    class Kepler(object):
+        def set_field_parameters(self, **kw):
+            self.kw = kw
+
+        def return_forces_cart(self, x, y, z, rotpos=0.0):
+            r = np.sqrt(x * x + y * y + z * z)
+            return -x / r ** 3, 0.0, -y / r ** 3, 0.0, -z / r ** 3, 0.0, -1.0 / r, 0.0
+    K = Kepler()
+    O = integrate.leapfrog_integrate(K, 400, 0.01, [1.0, 0.0, 0.0], [0.0, 0.9, 0.1], rotfreq=0.2, force=True, no_odd=True)
+    assert K.kw['no_odd'] is True and len(O['T']) == 400 and 'FX' in O and 'TX' in O
+    e = 0.5 * (O['VX'] ** 2 + O['VY'] ** 2 + O['VZ'] ** 2) + O['P']
+    assert np.max(np.abs(e - e[0])) < 1e-4
+    Oa = integrate.leapfrog_integrate(K, 4000, 0.01, [1.0, 0.0, 0.0], [0.0, 0.9, 0.1], apse=True, ap_max=2)
+    assert 2 < len(Oa['T']) < 4000           # stopped after the second apocentre
+    with pytest.raises(TypeError):
+        integrate.leapfrog_integrate_batch(K, 10, 0.01, np.zeros((3, 2)), np.zeros((3, 2)))

@@ -81,3 +81,40 @@ def test_factorial_return_and_mirrors_vs_reference(ref):
         a = ref['eof'].set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=cmap)
         b = myeof.set_table_params(RMAX=20.0, RMIN=0.001, ASCALE=0.01, HSCALE=0.001, NUMX=128, NUMY=64, CMAP=cmap)
         assert np.array_equal(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))
+
+
+def test_leapfrog_foreign_field_and_bar_pattern_vs_reference(ref):
+    """The host-side pieces of the workflow drivers against the reference's own code: leapfrog_integrate on a foreign
+    (duck-typed) field object gives the reference's arrays bit for bit; BarDetermine.read_bar / frequency_and_derivative /
+    find_barpattern give the reference's pattern speed from the same printed bar file."""
+    from exptool_b200.utils import integrate as mine
+    from exptool_b200.analysis import pattern as mypattern
+
+    class Kepler(object):
+        def set_field_parameters(self, **kw):
+            pass
+
+        def return_forces_cart(self, x, y, z, rotpos=0.0):
+            r = np.sqrt(x * x + y * y + z * z)
+            return -x / r ** 3, 0.0, -y / r ** 3, 0.0, -z / r ** 3, 0.0, -1.0 / r, 0.0
+    a = (Kepler(), 300, 0.01, [1.0, 0.0, 0.02], [0.0, 0.8, 0.05])
+    for kw in (dict(rotfreq=0.3, force=True), dict(rotfreq=-0.3, apse=True, ap_max=1), dict(ap_max=0)):
+        Or = quiet(ref['integrate'].leapfrog_integrate, *a, **kw)
+        Om = mine.leapfrog_integrate(*a, **kw)
+        assert set(Or.keys()) == set(Om.keys())
+        for k in Or.keys():
+            assert np.array_equal(np.asarray(Or[k]), np.asarray(Om[k])), (kw, k)
+    with tempfile.TemporaryDirectory() as tmp:
+        bf = os.path.join(tmp, 'bar.dat')
+        t = np.linspace(0.0, 2.0, 101)
+        with open(bf, 'w') as f:
+            for ti in t:
+                f.write('%.6f %.8f\n' % (ti, 37.5 * ti - 3.0 * ti * ti))
+        Br, Bm = ref['pattern'].BarDetermine(), mypattern.BarDetermine()
+        Br.read_bar(bf); Bm.read_bar(bf)
+        assert np.array_equal(Br.time, Bm.time) and np.array_equal(Br.deriv, Bm.deriv)
+        Br.frequency_and_derivative(spline_derivative=2); Bm.frequency_and_derivative(spline_derivative=2)
+        assert np.array_equal(Br.deriv, Bm.deriv) and np.array_equal(Br.dderiv, Bm.dderiv)
+        for tt in (0.0, 0.777, np.array([0.1, 1.9])):
+            assert np.array_equal(np.asarray(ref['pattern'].find_barpattern(tt, Br, smth_order=None)),
+                                  np.asarray(mypattern.find_barpattern(tt, Bm, smth_order=None)))
