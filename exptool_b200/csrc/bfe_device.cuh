@@ -673,10 +673,29 @@ __device__ __forceinline__ void bfe_ldg256(const double2* p, double2& a, double2
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
 
+// How a block evaluator fetches 32 bytes: LdGlobal256 = one 256-bit read-only global load (the caller-order and
+// key-ordered per-lane kernels); LdGeneric = two 128-bit GENERIC loads, for a base pointer that is either a block staged
+// in shared memory by a TMA bulk copy or, for the points of a tile whose block was not staged, the block in global memory
+// (bfe_orbit_sort.cu).  A warp-uniform 16-byte shared-memory load costs ~1.5 cycles of the SM's data pipe against ~8.3
+// for a 32-byte global load that hits L1 (profiles/probes/lds_broadcast_probe.cu): 2.8x less per byte.
+struct LdGlobal256 {
+    static __device__ __forceinline__ void ld(const double2* p, double2& a, double2& b) { bfe_ldg256(p, a, b); }
+};
+struct LdGeneric {
+    static __device__ __forceinline__ void ld(const double2* p, double2& a, double2& b) { a = p[0]; b = p[1]; }
+};
+
+template <int MCAP, class LD = LdGlobal256>
+__device__ __forceinline__ EofField bfe_eof_eval_base(const EofGeom& g, const double2* base, const EofBin& b, double c1, double s1);
+
 template <int MCAP>
 __device__ __forceinline__ EofField bfe_eof_eval_blk(const EofGeom& g, const double2* __restrict__ G4,
                                                      const EofBin& b, double c1, double s1) {
-    const double2* base = G4 + (size_t)b.cell * (size_t)(12 * (g.mmax + 1));
+    return bfe_eof_eval_base<MCAP, LdGlobal256>(g, G4 + (size_t)b.cell * (size_t)(12 * (g.mmax + 1)), b, c1, s1);
+}
+
+template <int MCAP, class LD>
+__device__ __forceinline__ EofField bfe_eof_eval_base(const EofGeom& g, const double2* base, const EofBin& b, double c1, double s1) {
     EofField f;
     f.p0 = 0.0; f.p = 0.0; f.fr = 0.0; f.fp = 0.0; f.fz = 0.0;
     double cm = 1.0, sm = 0.0;
@@ -686,8 +705,8 @@ __device__ __forceinline__ EofField bfe_eof_eval_blk(const EofGeom& g, const dou
             // corners 00, 10, 01, 11; three double2 each: (pc,ps), (rc,rs), (zc,zs)
             const double2* q = base + 12 * m;
             double2 a0, a1, a2, b0, b1, b2, c0, c1v, c2, d0, d1, d2;
-            bfe_ldg256(q, a0, a1); bfe_ldg256(q + 2, a2, b0); bfe_ldg256(q + 4, b1, b2);
-            bfe_ldg256(q + 6, c0, c1v); bfe_ldg256(q + 8, c2, d0); bfe_ldg256(q + 10, d1, d2);
+            LD::ld(q, a0, a1); LD::ld(q + 2, a2, b0); LD::ld(q + 4, b1, b2);
+            LD::ld(q + 6, c0, c1v); LD::ld(q + 8, c2, d0); LD::ld(q + 10, d1, d2);
             double vpc = a0.x * b.c00 + b0.x * b.c10 + c0.x * b.c01 + d0.x * b.c11;
             double vps = a0.y * b.c00 + b0.y * b.c10 + c0.y * b.c01 + d0.y * b.c11;
             double vrc = a1.x * b.c00 + b1.x * b.c10 + c1v.x * b.c01 + d1.x * b.c11;
@@ -713,6 +732,11 @@ __device__ __forceinline__ EofField bfe_eof_eval_blk(const EofGeom& g, const dou
 }
 
 // valid only when g.lmax == LCAP (LCAP = 6: 84 double2 = 1344 B per interval; LCAP = 4: 45 padded to 46)
+template <int LCAP, typename FacT, class LD = LdGlobal256>
+__device__ __forceinline__ SlField bfe_sl_eval_base(const SlGeom& g, const double2* base,
+                                                    const double* __restrict__ p0tab, const FacT& fac,
+                                                    const SlBin& b, double costh, double c1, double s1, bool trig_index_l);
+
 template <int LCAP, typename FacT>
 __device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double2* __restrict__ A3,
                                                    const double* __restrict__ p0tab, const FacT& fac,
@@ -720,7 +744,16 @@ __device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double
                                                    bool trig_index_l) {
     constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
     const int j = (b.i == 0) ? 1 : b.i;
-    const double2* base = A3 + (size_t)j * BFE_A3_STRIDE(NPAIR);
+    return bfe_sl_eval_base<LCAP, FacT, LdGlobal256>(g, A3 + (size_t)j * BFE_A3_STRIDE(NPAIR), p0tab, fac, b, costh, c1, s1,
+                                                     trig_index_l);
+}
+
+// base = the block of radial index j = max(b.i, 1): A3 + j * BFE_A3_STRIDE(NPAIR), or its staged copy
+template <int LCAP, typename FacT, class LD>
+__device__ __forceinline__ SlField bfe_sl_eval_base(const SlGeom& g, const double2* base,
+                                                    const double* __restrict__ p0tab, const FacT& fac,
+                                                    const SlBin& b, double costh, double c1, double s1, bool trig_index_l) {
+    const int j = (b.i == 0) ? 1 : b.i;
     const double pm = __ldg(p0tab + j - 1), pc = __ldg(p0tab + j), pp = __ldg(p0tab + j + 1);
     double P0, wA, wB, wC;
     if (b.i == 0) { P0 = b.x1 * pm + b.x2 * pc; wA = b.x1; wB = b.x2; wC = 0.0; }
@@ -752,7 +785,7 @@ __device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double
                 const int pr = pa + pi;
                 if (pr <= pb) {
                     double2 lo, hi;
-                    bfe_ldg256(base + 2 * pr, lo, hi);
+                    LD::ld(base + 2 * pr, lo, hi);
                     if (2 * pr >= first) v[2 * pr - first] = lo;
                     if (2 * pr + 1 < first + count) v[2 * pr + 1 - first] = hi;
                 }
@@ -1021,32 +1054,60 @@ __device__ __forceinline__ CartForce bfe_field_cart(const EofGeom& ge, const dou
 }
 
 // The same with the block evaluations above (G4 / A3, 256-bit loads); valid for g.lmax == LCAP.
+// Split in two so that a kernel can stage the blocks a tile of points needs between the halves: the prologue finds
+// the bins, the epilogue evaluates from two block base pointers.
+struct FieldPt {
+    double x, y, z, r2, r3, costh, cr, sr;
+    EofBin eb;
+    SlBin sb;
+};
+
+template <bool CYL>
+__device__ __forceinline__ FieldPt bfe_field_prologue(const EofGeom& ge, const SlGeom& gs, const double* __restrict__ xi,
+                                                      double x, double y, double z, double crot, double srot) {
+    const double eps = CYL ? 1.e-10 : 1.e-15;
+    FieldPt p;
+    p.x = x; p.y = y; p.z = z;
+    p.r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + eps;
+    p.r3 = sqrt(BFE_ADD(BFE_MUL(p.r2, p.r2), BFE_MUL(z, z))) + eps;
+    p.costh = BFE_DIV(z, p.r3);
+    double c1, s1;
+    bfe_cossin_phi(x, y, c1, s1);
+    p.cr = c1 * crot - s1 * srot;
+    p.sr = s1 * crot + c1 * srot;
+    p.eb = bfe_eof_bin(ge, p.r2, z);
+    p.sb = bfe_sl_bin(gs, xi, p.r3);
+    return p;
+}
+
+// FP64 tables: baseE = block of cell p.eb.cell, baseS = block of radial index max(p.sb.i, 1)
+template <int MCAP, int LCAP, bool CYL, typename FacT, class LD>
+__device__ __forceinline__ CartForce bfe_field_epilogue(const EofGeom& ge, const SlGeom& gs, const double2* baseE,
+                                                        const double2* baseS, const double* __restrict__ p0tab,
+                                                        const FacT& fac, const FieldPt& p) {
+    const EofField d = bfe_eof_eval_base<MCAP, LD>(ge, baseE, p.eb, p.cr, p.sr);
+    const SlField h = bfe_sl_eval_base<LCAP, FacT, LD>(gs, baseS, p0tab, fac, p.sb, p.costh, p.cr, p.sr, true);
+    return bfe_cart_combine<CYL>(d, h, p.x, p.y, p.z, p.r2, p.r3, gs.xi0);
+}
+
 template <int MCAP, int LCAP, bool CYL = false, bool F32 = false, typename FacT = const double*>
 __device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const void* __restrict__ G4,
                                                         const SlGeom& gs, const void* __restrict__ A3,
                                                         const double* __restrict__ xi, const double* __restrict__ p0tab,
                                                         const FacT& fac,
                                                         double x, double y, double z, double crot, double srot) {
-    const double eps = CYL ? 1.e-10 : 1.e-15;
-    double r2 = sqrt(BFE_ADD(BFE_MUL(x, x), BFE_MUL(y, y))) + eps;
-    double r3 = sqrt(BFE_ADD(BFE_MUL(r2, r2), BFE_MUL(z, z))) + eps;
-    double costh = BFE_DIV(z, r3);
-    double c1, s1;
-    bfe_cossin_phi(x, y, c1, s1);
-    double cr = c1 * crot - s1 * srot;
-    double sr = s1 * crot + c1 * srot;
-    EofBin eb = bfe_eof_bin(ge, r2, z);
-    SlBin sb = bfe_sl_bin(gs, xi, r3);
-    EofField d;
-    SlField h;
+    const FieldPt p = bfe_field_prologue<CYL>(ge, gs, xi, x, y, z, crot, srot);
     if constexpr (F32) {
-        d = bfe_eof_eval_blk32<MCAP>(ge, static_cast<const float*>(G4), eb, cr, sr);
-        h = bfe_sl_eval_blk32<LCAP>(gs, static_cast<const float*>(A3), p0tab, fac, sb, costh, cr, sr, true);
+        const EofField d = bfe_eof_eval_blk32<MCAP>(ge, static_cast<const float*>(G4), p.eb, p.cr, p.sr);
+        const SlField h = bfe_sl_eval_blk32<LCAP>(gs, static_cast<const float*>(A3), p0tab, fac, p.sb, p.costh, p.cr, p.sr, true);
+        return bfe_cart_combine<CYL>(d, h, x, y, z, p.r2, p.r3, gs.xi0);
     } else {
-        d = bfe_eof_eval_blk<MCAP>(ge, static_cast<const double2*>(G4), eb, cr, sr);
-        h = bfe_sl_eval_blk<LCAP>(gs, static_cast<const double2*>(A3), p0tab, fac, sb, costh, cr, sr, true);
+        constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
+        const int j = (p.sb.i == 0) ? 1 : p.sb.i;
+        return bfe_field_epilogue<MCAP, LCAP, CYL, FacT, LdGlobal256>(
+            ge, gs, static_cast<const double2*>(G4) + (size_t)p.eb.cell * (size_t)(12 * (ge.mmax + 1)),
+            static_cast<const double2*>(A3) + (size_t)j * BFE_A3_STRIDE(NPAIR), p0tab, fac, p);
     }
-    return bfe_cart_combine<CYL>(d, h, x, y, z, r2, r3, gs.xi0);
 }
 
 template <int MCAP, int LCAP, bool CYL>

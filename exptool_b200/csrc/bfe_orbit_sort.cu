@@ -236,6 +236,129 @@ field_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void*
     }
 }
 
+// ---------------------------------------------------------------------------
+// Shared-memory staging of the table blocks of a tile (FP64 tables): BASELINE north_star (b), "tables staged in shared
+// memory (TMA bulk copies where the table fits)".  The tables do not fit, the blocks of a TILE do: the 128 points of a tile
+// of the key order sit in a few neighbouring cells and radial intervals, whose blocks are CONTIGUOUS in G4 / A3.  Per tile
+//   1. every thread finds its bins (bfe_field_prologue);
+//   2. block-wide min / max of the cell and interval indices (warp redux + 4 x 4 values through shared memory);
+//   3. one thread issues TWO TMA bulk copies (cp.async.bulk + mbarrier): blocks [cmin, cmin + NE) of G4 and
+//      [jmin, jmin + NS) of A3, clipped to the tile's range -- at most (8 + 16) x 1344 B;
+//   4. all threads wait on the mbarrier and evaluate (bfe_field_epilogue) from the staged copy -- warp-uniform 16-byte
+//      shared-memory loads cost ~1.5 data-pipe cycles against ~8.3 for the 32-byte global load that hits L1, 2.8x less per
+//      byte (profiles/probes/lds_broadcast_probe.cu), and the L1 data pipe is what bounds the per-lane kernels --
+//      while a thread whose cell or interval lies outside the staged range (sparse outskirts, halo points with ~100 intervals
+//      per cell) reads its block from global memory through the same generic loads.  Same arithmetic, same bits.
+// The other resident CTAs of the SM cover the ~1 us a tile waits for its copies.
+// ---------------------------------------------------------------------------
+#define BFE_STAGE_NE 8
+#define BFE_STAGE_NS 16
+#define BFE_STAGE_BLK 84                       // double2 per block, both tables at mmax = 6 / lmax = 6 (1344 B)
+#define BFE_STAGE_SMEM ((BFE_STAGE_NE + BFE_STAGE_NS) * BFE_STAGE_BLK * 16 + 256)
+
+struct StageCtx {
+    double2* sE; double2* sS;
+    int* red;                                  // [2 parities][4 warps][4]
+    unsigned int bar, parity, flip;            // mbarrier phase parity; flip: which half of `red` this tile uses
+};
+
+__device__ __forceinline__ StageCtx bfe_stage_init(unsigned char* smem) {
+    StageCtx c;
+    c.sE = reinterpret_cast<double2*>(smem);
+    c.sS = c.sE + BFE_STAGE_NE * BFE_STAGE_BLK;
+    unsigned char* tail = smem + (BFE_STAGE_NE + BFE_STAGE_NS) * BFE_STAGE_BLK * 16;
+    c.red = reinterpret_cast<int*>(tail + 16);
+    c.bar = bfe_smem_u32(tail);
+    c.parity = 0u; c.flip = 0u;
+    if (threadIdx.x == 0) {
+        bfe_mbar_init(c.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    return c;
+}
+
+// all 128 threads of the CTA call this together; `on` = this thread has a point
+template <int MCAP, int LCAP, bool CYL>
+__device__ __forceinline__ CartForce bfe_stage_eval(const EofGeom& ge, const double2* __restrict__ G4, const SlGeom& gs,
+                                                    const double2* __restrict__ A3, const double* __restrict__ p0tab,
+                                                    const SlFacP& fac, const FieldPt& p, bool on, StageCtx& c) {
+    constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
+    constexpr int SBLK = BFE_A3_STRIDE(NPAIR);
+    const int eblk = 12 * (ge.mmax + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cell = p.eb.cell, j = (p.sb.i == 0) ? 1 : p.sb.i;
+    const int c0 = __reduce_min_sync(0xffffffffu, on ? cell : 0x7fffffff), c1 = __reduce_max_sync(0xffffffffu, on ? cell : -1);
+    const int j0 = __reduce_min_sync(0xffffffffu, on ? j : 0x7fffffff), j1 = __reduce_max_sync(0xffffffffu, on ? j : -1);
+    int* red = c.red + 16 * (int)c.flip;       // double-buffered per tile: a fast warp never overwrites what a slow one still reads
+    c.flip ^= 1u;
+    if (lane == 0) { red[4 * warp] = c0; red[4 * warp + 1] = c1; red[4 * warp + 2] = j0; red[4 * warp + 3] = j1; }
+    __syncthreads();                           // also: every thread has finished with the previous tile's staged blocks
+    int cmin = red[0], cmax = red[1], jmin = red[2], jmax = red[3];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+        cmin = min(cmin, red[4 * w]); cmax = max(cmax, red[4 * w + 1]);
+        jmin = min(jmin, red[4 * w + 2]); jmax = max(jmax, red[4 * w + 3]);
+    }
+    const int ne = min(cmax - cmin + 1, BFE_STAGE_NE), ns = min(jmax - jmin + 1, BFE_STAGE_NS);
+    CartForce f = {};
+    if (cmax < cmin) return f;                 // no point in this tile (uniform across the CTA)
+    if (threadIdx.x == 0) {
+        const unsigned int be = (unsigned int)(ne * eblk * 16), bs = (unsigned int)(ns * SBLK * 16);
+        bfe_mbar_expect_tx(c.bar, be + bs);
+        bfe_bulk_g2s(bfe_smem_u32(c.sE), G4 + (size_t)cmin * eblk, be, c.bar);
+        bfe_bulk_g2s(bfe_smem_u32(c.sS), A3 + (size_t)jmin * SBLK, bs, c.bar);
+    }
+    bfe_mbar_wait(c.bar, c.parity);
+    c.parity ^= 1u;
+    if (on) {
+        const double2* baseE = (cell - cmin < ne) ? c.sE + (cell - cmin) * eblk : G4 + (size_t)cell * eblk;
+        const double2* baseS = (j - jmin < ns) ? c.sS + (j - jmin) * SBLK : A3 + (size_t)j * SBLK;
+        f = bfe_field_epilogue<MCAP, LCAP, CYL, SlFacP, LdGeneric>(ge, gs, baseE, baseS, p0tab, fac, p);
+    }
+    return f;
+}
+
+template <int MCAP, int LCAP, bool CYL>
+__global__ void __launch_bounds__(128, BFE_PERM_MINB)
+field_stage_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
+                   const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
+                   int64_t n, const double* __restrict__ rec4, double crot, double srot, double* __restrict__ slot8,
+                   unsigned int* __restrict__ ticket) {
+    extern __shared__ __align__(128) unsigned char s_stage[];
+    __shared__ unsigned int s_tile;
+    StageCtx ctx = bfe_stage_init(s_stage);
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const unsigned int ntile = (unsigned int)((n + 127) >> 7);
+    const unsigned int nticket = bfe_ticket_count(ntile);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        if (s_tile >= nticket) break;
+        const TileTicket tk = bfe_ticket_tiles(s_tile, ntile);
+        int64_t pos = (int64_t)tk.first * 128 + threadIdx.x;
+        double px = 0.0, py = 0.0, pz = 0.0, id_ = 0.0;
+        if (pos < n) bfe_ld256_nc(rec4 + 4 * (size_t)pos, px, py, pz, id_);
+        for (unsigned int u = 0; u < tk.count; ++u) {
+            const int64_t npos = pos + 128;
+            double nx = 0.0, ny = 0.0, nz = 0.0;
+            if (u + 1 < tk.count && npos < n) bfe_ld256_nc(rec4 + 4 * (size_t)npos, nx, ny, nz, id_);   // next tile's record in flight
+            const bool on = pos < n;
+            FieldPt p = {};
+            if (on) p = bfe_field_prologue<CYL>(ge, gs, xi, px, py, pz, crot, srot);
+            const CartForce f = bfe_stage_eval<MCAP, LCAP, CYL>(ge, G4, gs, A3, p0tab, fac, p, on, ctx);
+            if (on) {
+                char* d = reinterpret_cast<char*>(slot8 + 8 * (size_t)pos);
+                bfe_st256(d, f.fxd, f.fxh, f.fyd, f.fyh);
+                bfe_st256(d + 32, f.fzd, f.fzh, f.pd, f.ph);
+            }
+            pos = npos; px = nx; py = ny; pz = nz;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 field_gather_kernel(int64_t n, int64_t ntot, const int* __restrict__ inv, const double* __restrict__ slot8,
                     double* __restrict__ out8) {
@@ -358,6 +481,91 @@ leapfrog_perm_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const v
     }
 }
 
+// leapfrog_perm_kernel with the table blocks of every step's tile staged in shared memory (bfe_stage_eval), FP64 tables
+template <int MCAP, int LCAP>
+__global__ void __launch_bounds__(128, BFE_PERM_MINB)
+leapfrog_stage_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
+                      const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
+                      int64_t norbit, int64_t step0, int nsteps, double rotfreq, int first, int rekey, int ncell, int subbits,
+                      const int* __restrict__ perm, OrbRec* __restrict__ rec, int* __restrict__ hist,
+                      int2* __restrict__ keyrank, unsigned int* __restrict__ ticket) {
+    extern __shared__ __align__(128) unsigned char s_stage[];
+    __shared__ unsigned int s_tile;
+    StageCtx ctx = bfe_stage_init(s_stage);
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const unsigned int ntile = (unsigned int)((norbit + 127) >> 7);
+    const unsigned int nticket = bfe_ticket_count(ntile);
+    const double w = BFE_TWOPI * rotfreq;                    // barpos = 2 pi rotfreq (k dt), integrate.py:94-97
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        if (s_tile >= nticket) break;
+        const TileTicket tk = bfe_ticket_tiles(s_tile, ntile);
+        int64_t pos = (int64_t)tk.first * 128 + threadIdx.x;
+        int i = pos < norbit ? __ldg(perm + pos) : -1;
+        for (unsigned int u = 0; u < tk.count; ++u) {
+            const int64_t npos = pos + 128;
+            const int ni = (u + 1 < tk.count && npos < norbit) ? __ldg(perm + npos) : -1;
+            const bool on = i >= 0;
+            int key = 0;
+            double px = 0.0, py = 0.0, pz = 0.0, vx = 0.0, vy = 0.0, vz = 0.0, dt = 0.0, ax = 0.0, ay = 0.0, az = 0.0, u0 = 0.0, u1 = 0.0;
+            if (on) {
+                // plain (coherent) loads: the record is rewritten in place by this kernel
+                const double4* r4 = reinterpret_cast<const double4*>(rec + i);
+                const double4 a = r4[0], b = r4[1], c = r4[2];
+                px = a.x; py = a.y; pz = a.z; vx = a.w; vy = b.x; vz = b.y; dt = b.z; ax = b.w; ay = c.x; az = c.y;
+                u0 = c.z; u1 = c.w;
+            }
+            const double hdt2 = 0.5 * (dt * dt);
+            double srot, crot;
+            if (first) {                                             // CTA-uniform
+                FieldPt p = {};
+                if (on) {
+                    sincos(w * ((double)step0 * dt), &srot, &crot);
+                    p = bfe_field_prologue<false>(ge, gs, xi, px, py, pz, crot, srot);
+                }
+                const CartForce f = bfe_stage_eval<MCAP, LCAP, false>(ge, G4, gs, A3, p0tab, fac, p, on, ctx);
+                if (on) { ax = f.fxd + f.fxh; ay = f.fyd + f.fyh; az = f.fzd + f.fzh; }
+            }
+            for (int k = 1; k <= nsteps; ++k) {
+                const int64_t step = step0 + k;
+                FieldPt p = {};
+                if (on) {
+                    px = px + (vx * dt) + (ax * hdt2);                   // integrate.py:129-131
+                    py = py + (vy * dt) + (ay * hdt2);
+                    pz = pz + (vz * dt) + (az * hdt2);
+                    sincos(w * ((double)step * dt), &srot, &crot);
+                    p = bfe_field_prologue<false>(ge, gs, xi, px, py, pz, crot, srot);
+                }
+                const CartForce f = bfe_stage_eval<MCAP, LCAP, false>(ge, G4, gs, A3, p0tab, fac, p, on, ctx);
+                if (on) {
+                    const double bx = f.fxd + f.fxh, by = f.fyd + f.fyh, bz = f.fzd + f.fzh;         // 134-138
+                    vx = vx + (0.5 * (ax + bx) * dt);                    // 141-143
+                    vy = vy + (0.5 * (ay + by) * dt);
+                    vz = vz + (0.5 * (az + bz) * dt);
+                    ax = bx; ay = by; az = bz;
+                }
+            }
+            if (on) {
+                char* d = reinterpret_cast<char*>(rec + i);
+                bfe_st256(d, px, py, pz, vx);
+                bfe_st256(d + 32, vy, vz, dt, ax);
+                bfe_st256(d + 64, ay, az, u0, u1);
+                // key of the NEXT evaluation point: the drift of the following step (the same expression, so the same bits)
+                if (rekey) key = bfe_point_key(ge, gs, ncell, subbits, px + (vx * dt) + (ax * hdt2), py + (vy * dt) + (ay * hdt2),
+                                               pz + (vz * dt) + (az * hdt2));
+            }
+            if (rekey) {
+                const int rank = bfe_claim_rank(hist, key, on);
+                if (on) keyrank[i] = make_int2(key, rank);
+            }
+            i = ni; pos = npos;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 orbit_unpack_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restrict__ state6, int* __restrict__ nsteps_out,
                     int nint) {
@@ -378,6 +586,12 @@ orbit_unpack_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restric
 int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between re-sorts of a large orbit batch (0: plain kernel)
 int g_bfe_orbit_sort_min = 65536;       // option "orbit_sort_min": smallest batch on the key-ordered path
 int g_bfe_field_sort_chunk = 1 << 20;   // option "field_sort_chunk": points per sort + evaluate pass (L2-resident working set)
+int g_bfe_stage_eval = 0;               // option "stage_eval": FP64-table key-ordered kernels evaluate from TMA-staged shared-memory blocks (1) or
+                                        // with global loads (0, default).  Measured on B200 (profiles/r02_field_probe_stage*.json, r02_ncu_full_field_stage.csv):
+                                        // global-load requests per tile fall 3.7x and results stay bit-identical, but the warps of a 2^19..2^20-point
+                                        // chunk hold ~3 distinct (cell, interval) pairs, so a 16-byte shared load still takes 3.7 data-pipe wavefronts
+                                        // (1.5 when warp-uniform): 207 vs 210 us per 1e6 disc points, 387 vs 339 for halo points (their intervals
+                                        // overflow the 16 staged blocks and fall back to twice as many 128-bit loads), orbits 0.191 vs 0.187 ns
 int g_bfe_field_sort_min = 65536;       // option "field_sort_min": smallest point set evaluated in key order (0: never)
 
 static size_t os_align(size_t v) { return (v + 255) / 256 * 256; }
@@ -524,6 +738,20 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
         if (c + 1 < nchunk) { rc = sort_chunk(c + 1); if (rc != BFE_OK) return rc; }
         BFE_CUDA(cudaStreamWaitEvent(stream, fp->ev_k[b], 0));
         const int geval = grid_cap(m, 128, he->num_sms * BFE_PERM_MINB);
+        if (!f32 && g_bfe_stage_eval && he->g.mmax <= 6) {
+#define FIELD_STAGE(L, C)                                                                                                        \
+    do {                                                                                                                          \
+        cudaError_t _e = bfe_launch((field_stage_kernel<6, L, C>), dim3(geval), dim3(128), (size_t)BFE_STAGE_SMEM, stream, nullptr, 0, \
+                                    he->g, (const double2*)G4, hs->g, (const double2*)A3, (const double*)hs->xi,                 \
+                                    (const double*)hs->p0, facp, m, (const double*)w.rec4[b], crot, srot, w.slot8[b],            \
+                                    w.counter + 1 + b);                                                                           \
+        if (_e != cudaSuccess) { bfe_set_cuda_error(_e, "field_stage_kernel"); return BFE_ERR_CUDA; }                             \
+        bfe_count_launch(1);                                                                                                      \
+    } while (0)
+            if (hs->g.lmax == 4) { if (cyl) FIELD_STAGE(4, true); else FIELD_STAGE(4, false); }
+            else                 { if (cyl) FIELD_STAGE(6, true); else FIELD_STAGE(6, false); }
+#undef FIELD_STAGE
+        } else {
 #define FIELD_REC(L, C, F) KS_LAUNCH("field_rec_kernel", (field_rec_kernel<6, L, C, F>), geval, 128, he->g, G4, hs->g, A3,      \
                                      (const double*)hs->xi, (const double*)hs->p0, facp, m, (const double*)w.rec4[b], crot, srot, \
                                      w.slot8[b], w.counter + 1 + b)
@@ -532,6 +760,7 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
         else                 { if (cyl) FIELD_REC2(6, true); else FIELD_REC2(6, false); }
 #undef FIELD_REC2
 #undef FIELD_REC
+        }
         BFE_CUDA(cudaEventRecord(fp->ev_e[b], stream));
         BFE_CUDA(cudaStreamWaitEvent(aux, fp->ev_e[b], 0));
         const int g256 = grid_cap(m, 256, he->num_sms * 4);
@@ -584,8 +813,19 @@ int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, d
                                   (const double*)hs->xi, (const double*)hs->p0, facp, norbit, step0, k,                        \
                                   rotfreq, (int)(step0 == 0), (int)!last, w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, \
                                   w.keyrank[0], w.counter + 1)
-        if (hs->g.lmax == 4) { if (f32) LEAP_PERM(4, true); else LEAP_PERM(4, false); }
-        else                 { if (f32) LEAP_PERM(6, true); else LEAP_PERM(6, false); }
+#define LEAP_STAGE(L)                                                                                                            \
+    do {                                                                                                                          \
+        cudaError_t _e = bfe_launch((leapfrog_stage_kernel<6, L>), dim3(glf), dim3(128), (size_t)BFE_STAGE_SMEM, stream, nullptr, 0, \
+                                    he->g, (const double2*)G4, hs->g, (const double2*)A3, (const double*)hs->xi,                 \
+                                    (const double*)hs->p0, facp, norbit, step0, k, rotfreq, (int)(step0 == 0), (int)!last,       \
+                                    w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, w.keyrank[0], w.counter + 1);         \
+        if (_e != cudaSuccess) { bfe_set_cuda_error(_e, "leapfrog_stage_kernel"); return BFE_ERR_CUDA; }                          \
+        bfe_count_launch(1);                                                                                                      \
+    } while (0)
+        if (!f32 && g_bfe_stage_eval && he->g.mmax <= 6) { if (hs->g.lmax == 4) LEAP_STAGE(4); else LEAP_STAGE(6); }
+        else if (hs->g.lmax == 4) { if (f32) LEAP_PERM(4, true); else LEAP_PERM(4, false); }
+        else                      { if (f32) LEAP_PERM(6, true); else LEAP_PERM(6, false); }
+#undef LEAP_STAGE
 #undef LEAP_PERM
     }
     KS_LAUNCH("orbit_unpack_kernel", orbit_unpack_kernel, g256, 256, norbit, (const OrbRec*)rec, state6, (int*)nsteps_out,

@@ -656,7 +656,7 @@ def test_key_ordered_paths_at_size(ops, lmax):
     E.contract(c * 0.025, s_ * 0.025)
     H.contract(H.accumulate(xh, yh, zh, mh))
     x = np.concatenate([xd, xh]); y = np.concatenate([yd, yh]); z = np.concatenate([zd, zh])
-    keys = ('field_sort_min', 'field_sort_chunk', 'orbit_sort_min', 'orbit_resort')
+    keys = ('field_sort_min', 'field_sort_chunk', 'orbit_sort_min', 'orbit_resort', 'stage_eval')
     saved = {k: ops.get_option(k) for k in keys}
     try:
         ops.set_option('field_sort_min', 0); ops.set_option('orbit_resort', 0)
@@ -670,14 +670,16 @@ def test_key_ordered_paths_at_size(ops, lmax):
         ref_s, _, ref_n = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
         ref_d, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
         ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 40000); ops.set_option('orbit_sort_min', 1)
-        assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref_c)
-        assert torch.equal(ops.field_force_cyl(E, H, x, y, z, rotpos=-1.1), ref_y)
-        for K in (1, 3):
-            ops.set_option('orbit_resort', K)
-            st, _, ns = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
-            assert torch.equal(st, ref_s) and torch.equal(ns, ref_n), K
-            st, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
-            assert torch.equal(st, ref_d), K
+        for stage in (0, 1):          # 1: table blocks of every tile staged in shared memory by TMA bulk copies (option stage_eval)
+            ops.set_option('stage_eval', stage)
+            assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref_c), stage
+            assert torch.equal(ops.field_force_cyl(E, H, x, y, z, rotpos=-1.1), ref_y), stage
+            for K in (1, 3):
+                ops.set_option('orbit_resort', K)
+                st, _, ns = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
+                assert torch.equal(st, ref_s) and torch.equal(ns, ref_n), (stage, K)
+                st, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
+                assert torch.equal(st, ref_d), (stage, K)
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
