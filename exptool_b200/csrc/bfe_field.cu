@@ -372,6 +372,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }
     if (!strcmp(name, "host_chunk")) { g_bfe_host_chunk = value; return BFE_OK; }
     if (!strcmp(name, "host_reuse")) { g_bfe_host_reuse = value; return BFE_OK; }
+    if (!strcmp(name, "host_threads")) { if (value < 0 || value > 64) return BFE_ERR_ARG; g_bfe_host_threads = value; return BFE_OK; }
     if (!strcmp(name, "l2_persist")) {
         g_bfe_l2_persist = value;
         if (value > 0) return bfe_l2_persist_setup((size_t)96 << 20);
@@ -403,6 +404,7 @@ extern "C" int bfe_get_option(const char* name) {
     if (!strcmp(name, "contract_deep")) return g_bfe_contract_deep;
     if (!strcmp(name, "host_chunk")) return g_bfe_host_chunk;
     if (!strcmp(name, "host_reuse")) return g_bfe_host_reuse;
+    if (!strcmp(name, "host_threads")) return g_bfe_host_threads;
     if (!strcmp(name, "host_reused_last")) return g_bfe_host_reused_last;
     if (!strcmp(name, "l2_persist")) return g_bfe_l2_persist;
     if (!strcmp(name, "sl_accumulate_mode")) return g_bfe_sl_accumulate_mode;

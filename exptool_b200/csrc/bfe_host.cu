@@ -21,8 +21,11 @@
 // may not be -- callers that do that set the option to 0.  bfe_eof_accumulate_host itself ALWAYS uploads.
 #include "bfe_internal.h"
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <string.h>
+#include <thread>
+#include <vector>
 
 struct BfeHostPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -33,7 +36,86 @@ struct BfeHostPipe {
     size_t coef_cap = 0;
     cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2], ev_start;
     bool events = false;
+    // pinned bounce buffers for PAGEABLE host inputs ([4][cap] each), filled by the copy threads below
+    double* hstage[2] = {nullptr, nullptr};
+    int64_t hstage_cap = 0;
+    cudaEvent_t ev_stage[2];
+    bool stage_events = false;
 };
+
+// ---- pageable inputs.  A drop-in caller passes plain NumPy arrays; cudaMemcpyAsync from pageable memory is a synchronous,
+// single-threaded bounce through the driver's staging (~9 GB/s: 3.5 ms for the 32 MB of 10^6 particles against 0.6 ms from
+// pinned memory, profiles/r02_e2e_probe.py).  Here a small pool of copy threads fills a pinned bounce buffer of the NEXT chunk
+// (memcpy of the rows in slices, all threads in parallel) while the DMA of the previous chunk runs (option "host_threads").
+int g_bfe_host_threads = 4;          // option "host_threads": copy threads for pageable inputs (0: leave it to cudaMemcpyAsync)
+
+class BfeCopyPool {
+public:
+    struct Job { char* dst; const char* src; size_t bytes; };
+    explicit BfeCopyPool(int n) : stop_(false), pending_(0), epoch_(0) {
+        for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { run(i); });
+    }
+    ~BfeCopyPool() {
+        { std::lock_guard<std::mutex> l(mu_); stop_ = true; ++epoch_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return (int)threads_.size(); }
+    // copy all jobs; the calling thread takes its share and returns when every slice is done
+    void run_all(const std::vector<Job>& jobs) {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            jobs_ = &jobs; next_ = 0; pending_ = (int)jobs.size(); ++epoch_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> l(mu_);
+        done_.wait(l, [this] { return pending_ == 0; });
+        jobs_ = nullptr;
+    }
+private:
+    void work() {
+        for (;;) {
+            const Job* j = nullptr;
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                if (!jobs_ || next_ >= jobs_->size()) return;
+                j = &(*jobs_)[next_++];
+            }
+            memcpy(j->dst, j->src, j->bytes);
+            std::lock_guard<std::mutex> l(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void run(int) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::vector<Job>* jobs_ = nullptr;
+    size_t next_ = 0;
+    bool stop_;
+    int pending_;
+    unsigned long long epoch_;
+};
+static BfeCopyPool* g_copy_pool = nullptr;       // made on first use, lives for the process (threads sleep on a condition variable)
+static std::mutex g_copy_pool_mu;
+
+static bool host_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
 
 int g_bfe_host_chunk = 0;            // option "host_chunk": particles per pipeline chunk (0 = auto)
 int g_bfe_host_reused_last = 0;      // option (read-only) "host_reused_last": 1 if the latest bfe_eof_force_host evaluated from the kept copy
@@ -92,6 +174,8 @@ void bfe_host_pipe_destroy(void* p_) {
         for (int b = 0; b < 2; ++b) { cudaEventDestroy(p->ev_in[b]); cudaEventDestroy(p->ev_cmp[b]); cudaEventDestroy(p->ev_out[b]); }
         cudaEventDestroy(p->ev_start);
     }
+    for (int b = 0; b < 2; ++b) if (p->hstage[b]) cudaFreeHost(p->hstage[b]);
+    if (p->stage_events) for (int b = 0; b < 2; ++b) cudaEventDestroy(p->ev_stage[b]);
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_out) cudaStreamDestroy(p->s_out);
     delete p;
@@ -175,6 +259,48 @@ static cudaError_t copy_rows_d2h(double* const* rows, int nrows, int64_t lo, con
     return cudaSuccess;
 }
 
+// Upload `nrows` host rows [lo, lo + len) to dev + k * pitch on stream s.  Pinned rows go as one 2-D DMA (copy_rows_h2d);
+// pageable rows are first copied into the pipe's pinned bounce buffer `b` by the copy threads, then sent by DMA.
+static int upload_rows(BfeHostPipe* p, int b, bool pageable, double* dev, int64_t pitch, const double* const* rows, int nrows,
+                       int64_t lo, int64_t len, cudaStream_t s) {
+    if (!pageable || g_bfe_host_threads <= 0) {
+        BFE_CUDA(copy_rows_h2d(dev, pitch, rows, nrows, lo, len, s));
+        return BFE_OK;
+    }
+    if (p->hstage_cap < len) {
+        BFE_CUDA(cudaDeviceSynchronize());
+        for (int q = 0; q < 2; ++q) { if (p->hstage[q]) cudaFreeHost(p->hstage[q]); p->hstage[q] = nullptr; }
+        for (int q = 0; q < 2; ++q) BFE_CUDA(cudaHostAlloc((void**)&p->hstage[q], 4 * (size_t)len * sizeof(double), cudaHostAllocDefault));
+        p->hstage_cap = len;
+    }
+    if (!p->stage_events) {
+        for (int q = 0; q < 2; ++q) BFE_CUDA(cudaEventCreateWithFlags(&p->ev_stage[q], cudaEventDisableTiming));
+        p->stage_events = true;
+        for (int q = 0; q < 2; ++q) BFE_CUDA(cudaEventRecord(p->ev_stage[q], s));
+    }
+    BFE_CUDA(cudaEventSynchronize(p->ev_stage[b]));               // the DMA that last read this bounce buffer is done
+    {
+        std::lock_guard<std::mutex> l(g_copy_pool_mu);
+        if (!g_copy_pool || g_copy_pool->size() != g_bfe_host_threads - 1) {
+            delete g_copy_pool;
+            g_copy_pool = new BfeCopyPool(std::max(0, g_bfe_host_threads - 1));
+        }
+        std::vector<BfeCopyPool::Job> jobs;
+        const int64_t slice = 32768;                              // 256 kB per job
+        for (int k = 0; k < nrows; ++k)
+            for (int64_t o = 0; o < len; o += slice) {
+                const int64_t m = std::min(slice, len - o);
+                jobs.push_back({(char*)(p->hstage[b] + (size_t)k * p->hstage_cap + o), (const char*)(rows[k] + lo + o),
+                                (size_t)m * sizeof(double)});
+            }
+        g_copy_pool->run_all(jobs);
+    }
+    BFE_CUDA(cudaMemcpy2DAsync(dev, (size_t)pitch * sizeof(double), p->hstage[b], (size_t)p->hstage_cap * sizeof(double),
+                               (size_t)len * sizeof(double), nrows, cudaMemcpyHostToDevice, s));
+    BFE_CUDA(cudaEventRecord(p->ev_stage[b], s));
+    return BFE_OK;
+}
+
 // Accumulation on HOST particle arrays (rows x, y, z, m); `run(len, d, pitch, dst)` enqueues the accumulation kernels of
 // one chunk whose rows start at d, d + pitch, ... and leaves its ncoef coefficients at dst.  The coefficients stay on the
 // device (out_dev) so that a multi-GPU caller can allreduce them before the one small copy out.
@@ -204,6 +330,7 @@ static int accumulate_host_impl(void** pipe_slot, int kind, int64_t n, const dou
         for (int q = 0; q < 3; ++q) { ks->hp[q] = rows[q]; ks->tag[q] = host_tag(rows[q], n); }
         ks->n = n;
     }
+    const bool pageable = host_is_pageable(rows[0]);
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, ++k) {
         const int b = k & 1;
@@ -215,7 +342,8 @@ static int accumulate_host_impl(void** pipe_slot, int kind, int64_t n, const dou
             if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[b], 0));  // kernels of chunk k-2 have read din[b]
             d = p->din[b]; pitch = p->cap;
         }
-        BFE_CUDA(copy_rows_h2d(d, pitch, rows, 4, lo, len, p->s_in));
+        rc = upload_rows(p, b, pageable, d, pitch, rows, 4, lo, len, p->s_in);
+        if (rc != BFE_OK) return rc;
         BFE_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
         BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_in[b], 0));
         rc = run(len, d, pitch, k == 0 ? out_dev : p->coef);
@@ -292,6 +420,7 @@ static int force_host_impl(void** pipe_slot, int kind, int64_t n, const double* 
         ks = nullptr;
     if (ks) BFE_CUDA(cudaStreamWaitEvent(stream, ks->ready, 0));
     g_bfe_host_reused_last = ks ? 1 : 0;
+    const bool pageable = !ks && host_is_pageable(rows[0]);
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += chunk, ++k) {
         const int b = k & 1;
@@ -301,7 +430,8 @@ static int force_host_impl(void** pipe_slot, int kind, int64_t n, const double* 
         if (ks) { d = ks->d + lo; pitch = ks->cap; }
         else {
             if (k >= 2) BFE_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_cmp[b], 0));  // kernels of chunk k-2 have read din[b]
-            BFE_CUDA(copy_rows_h2d(p->din[b], p->cap, rows, 3, lo, len, p->s_in));
+            rc = upload_rows(p, b, pageable, p->din[b], p->cap, rows, 3, lo, len, p->s_in);
+            if (rc != BFE_OK) return rc;
             BFE_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
             BFE_CUDA(cudaStreamWaitEvent(stream, p->ev_in[b], 0));
             d = p->din[b]; pitch = p->cap;

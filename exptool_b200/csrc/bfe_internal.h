@@ -142,6 +142,7 @@ void bfe_host_pipe_destroy(void* pipe);
 void bfe_field_pipe_destroy(void* pipe);
 extern int g_bfe_host_chunk;                               // option "host_chunk"
 extern int g_bfe_host_reuse;                               // option "host_reuse"
+extern int g_bfe_host_threads;                             // option "host_threads"
 extern int g_bfe_host_reused_last;                         // read-only option "host_reused_last"
 extern int g_bfe_contract_deep;                            // option "contract_deep": 9 (1) or 6 (0) table loads in flight
 extern int g_bfe_pdl;
