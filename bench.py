@@ -212,7 +212,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'particles_per_step': n_step},
+            'config': {'workload': WORKLOAD, 'particles_per_gpu': N_PART, 'sample_particles_per_step': n_step},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': '%d particles per step (accumulate + force eval), C port of the reference '
                                        'formulation with OpenMP on %d threads' % (n_step, cores)},

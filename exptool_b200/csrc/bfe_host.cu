@@ -227,14 +227,24 @@ static int pipe_get(void** slot, size_t coef_doubles, int64_t chunk, bool need_o
 }
 
 // rows[k] + lo, len doubles each -> dev + k * pitch   (one 2-D DMA when the host rows are equally spaced)
+static const void* g_no2d_h2d = nullptr;     // rows[0] of the last host set whose 2-D DMA the driver refused
+static const void* g_no2d_d2h = nullptr;
+
 static cudaError_t copy_rows_h2d(double* dev, int64_t pitch, const double* const* rows, int nrows, int64_t lo,
                                  int64_t len, cudaStream_t s) {
-    bool even = nrows > 1;
+    bool even = nrows > 1 && g_no2d_h2d != (const void*)rows[0];
     const ptrdiff_t step = nrows > 1 ? (rows[1] - rows[0]) : 0;
     for (int k = 2; k < nrows && even; ++k) even = (rows[k] - rows[k - 1]) == step;
-    if (even && step >= len)
-        return cudaMemcpy2DAsync(dev, (size_t)pitch * sizeof(double), rows[0] + lo, (size_t)step * sizeof(double),
-                                 (size_t)len * sizeof(double), nrows, cudaMemcpyHostToDevice, s);
+    if (even && step >= len) {
+        // one 2-D DMA.  The driver rejects it (invalid argument) when the span between the rows crosses separately pinned
+        // allocations with unregistered gaps (small tensors of torch's pinned allocator; found by compute-sanitizer on a
+        // 5003-particle set): fall back to one copy per row then.
+        cudaError_t e = cudaMemcpy2DAsync(dev, (size_t)pitch * sizeof(double), rows[0] + lo, (size_t)step * sizeof(double),
+                                          (size_t)len * sizeof(double), nrows, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+        g_no2d_h2d = (const void*)rows[0];
+    }
     for (int k = 0; k < nrows; ++k) {
         cudaError_t e = cudaMemcpyAsync(dev + (size_t)k * pitch, rows[k] + lo, (size_t)len * sizeof(double),
                                         cudaMemcpyHostToDevice, s);
@@ -245,12 +255,16 @@ static cudaError_t copy_rows_h2d(double* dev, int64_t pitch, const double* const
 
 static cudaError_t copy_rows_d2h(double* const* rows, int nrows, int64_t lo, const double* dev, int64_t pitch,
                                  int64_t len, cudaStream_t s) {
-    bool even = nrows > 1;
+    bool even = nrows > 1 && g_no2d_d2h != (const void*)rows[0];
     const ptrdiff_t step = nrows > 1 ? (rows[1] - rows[0]) : 0;
     for (int k = 2; k < nrows && even; ++k) even = (rows[k] - rows[k - 1]) == step;
-    if (even && step >= len)
-        return cudaMemcpy2DAsync(rows[0] + lo, (size_t)step * sizeof(double), dev, (size_t)pitch * sizeof(double),
-                                 (size_t)len * sizeof(double), nrows, cudaMemcpyDeviceToHost, s);
+    if (even && step >= len) {
+        cudaError_t e = cudaMemcpy2DAsync(rows[0] + lo, (size_t)step * sizeof(double), dev, (size_t)pitch * sizeof(double),
+                                          (size_t)len * sizeof(double), nrows, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();                      // see copy_rows_h2d
+        g_no2d_d2h = (const void*)rows[0];
+    }
     for (int k = 0; k < nrows; ++k) {
         cudaError_t e = cudaMemcpyAsync(rows[k] + lo, dev + (size_t)k * pitch, (size_t)len * sizeof(double),
                                         cudaMemcpyDeviceToHost, s);

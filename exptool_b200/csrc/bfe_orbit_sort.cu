@@ -584,6 +584,7 @@ orbit_unpack_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restric
 // host side
 // ---------------------------------------------------------------------------
 int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between re-sorts of a large orbit batch (0: plain kernel)
+int g_bfe_key_subbits = BFE_KEY_SUBBITS; // option "key_subbits": low bits of the SL interval in the ordering key (bins = ncell << subbits)
 int g_bfe_orbit_sort_min = 65536;       // option "orbit_sort_min": smallest batch on the key-ordered path
 int g_bfe_field_sort_chunk = 1 << 20;   // option "field_sort_chunk": points per sort + evaluate pass (L2-resident working set)
 int g_bfe_stage_eval = 0;               // option "stage_eval": FP64-table key-ordered kernels evaluate from TMA-staged shared-memory blocks (1) or
@@ -606,7 +607,9 @@ struct KeySortWs {
 // workspace in he->orbit_ws, grown on demand: header + per item 12 bytes (orbits: keyrank, perm) or 2 x 100 bytes (points)
 static int keysort_ws(bfe_eof* he, int64_t cap_need, bool points, KeySortWs& w) {
     w.ncell = he->g.numx * he->g.numy;
-    w.subbits = BFE_KEY_SUBBITS;
+    w.subbits = g_bfe_key_subbits;
+    if (w.subbits < 0) w.subbits = 0;
+    if (w.subbits > 8) w.subbits = 8;
     while (w.subbits > 0 && ((int64_t)w.ncell << w.subbits) > ((int64_t)1 << 21)) --w.subbits;
     if (((int64_t)w.ncell << w.subbits) > ((int64_t)1 << 21)) return BFE_ERR_UNSUPPORTED;
     w.nkeys = w.ncell << w.subbits;

@@ -30,6 +30,25 @@ for lmax in (4, 6):
         ops.leapfrog(E, H, pos0, vel0, 12, 3e-4, rotfreq=-5.0, traj_stride=3, apse=True, ap_max=2)
         ops.leapfrog(E, H, pos0, vel0, 9, np.full(777, 2e-4), rotfreq=1.0, traj_stride=1)
     ops.set_option('staged_eval', 1); ops.set_option('blk_eval', 1); ops.set_option('table_fp32', 0); ops.set_option('eof_force_mode', 0)
+    # round 2: key-ordered field evaluation (two chunks in flight on two streams) and leapfrog, global loads / TMA-staged
+    # shared-memory blocks, FP64 / FP32 tables, uneven chunks, re-sort every 1 / 3 steps, per-orbit step sizes
+    saved = {k: ops.get_option(k) for k in ('field_sort_min', 'field_sort_chunk', 'orbit_sort_min', 'orbit_resort', 'stage_eval')}
+    xm = np.concatenate([d[0], h[0]]); ym = np.concatenate([d[1], h[1]]); zm = np.concatenate([d[2], h[2]])
+    ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 3001); ops.set_option('orbit_sort_min', 1)
+    for stage, f32 in ((0, 0), (1, 0), (0, 1)):
+        ops.set_option('stage_eval', stage); ops.set_option('table_fp32', f32)
+        ops.field_force_cart(E, H, xm, ym, zm, rotpos=0.2); ops.field_force_cyl(E, H, xm, ym, zm, rotpos=0.2)
+        for K in (1, 3):
+            ops.set_option('orbit_resort', K)
+            ops.leapfrog(E, H, pos0, vel0, 12, 3e-4, rotfreq=-5.0)
+            ops.leapfrog(E, H, pos0, vel0, 11, np.full(777, 2e-4), rotfreq=1.0)
+    ops.set_option('table_fp32', 0)
+    for k, v in saved.items():
+        ops.set_option(k, v)
+    # host-array pipelines: one upload per snapshot, pageable inputs through the copy threads, the SL pipeline
+    E.accumulate_host(*d); E.force_host(*d[:3]); H.accumulate_host(*h); H.force_host(*h[:3])
+    pin = [torch.from_numpy(a).pin_memory() for a in d]
+    E.accumulate_host(*pin); E.force_host(*pin[:3])
     E.prepare(*d); E.accumulate_prepared(); E.force_prepared()
     # density outputs, building blocks
     H.contract_density(ch); H.density(*h[:3]); H.density_eval_points(np.abs(h[0]) + 1e-3, np.clip(h[2], -1, 1), h[1])
@@ -56,4 +75,5 @@ for it in range(8):
 torch.cuda.synchronize()
 assert torch.equal(dat[0], dat[1])
 torch.cuda.synchronize()
+print('fp64 peaks', ops.fp64_peak('dfma'), ops.fp64_peak('dmma'))
 print('sanitize_run done')
