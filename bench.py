@@ -603,6 +603,8 @@ def run_gpu(args):
     # (profiles/dual_stream.py: 1 stream 174 us/step, 2 streams 138, 3 streams 133).
     NSTREAMS = max(1, args.streams)
     ops.set_option('grid_pct', args.grid_pct)
+    if args.sort_stable >= 0:
+        ops.set_option('sort_stable', args.sort_stable)
     Es = [E] + [E.clone() for _ in range(NSTREAMS - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
     coefbufs = [torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev) for _ in range(NSTREAMS)]
@@ -749,7 +751,7 @@ def run_gpu(args):
     t_con, t_force = time_kernel(k_con, reps), time_kernel(k_force, reps)
     # live duration of every kernel of the step: CUDA events recorded inside the library around each launch
     # (bfe_set_option "time_kernels"), averaged over whole steps on rotating particle sets
-    KNAMES = ['eof_cell_hist_kernel', 'eof_cell_scatter_kernel', 'eof_segsum_kernel', 'eof_node_contract_kernel',
+    KNAMES = ['eof_cell_hist_kernel', 'eof_tile_colscan_kernel', 'eof_cell_scatter_kernel', 'eof_segsum_kernel', 'eof_node_contract_kernel',
               'eof_contract_kernel',
               'eof_force_sorted_kernel', 'eof_force_sorted_mma_kernel', 'eof_force_gather_kernel']
     ops.set_option('time_kernels', 1)
@@ -765,7 +767,7 @@ def run_gpu(args):
     peak, peak_src = measured_peaks()
     # algorithmic HBM bytes per particle of the pass a kernel belongs to:
     # accumulate 32 B (x,y,z,m), force 72 B (x,y,z + six outputs); the contraction reads the six tables once.
-    alg = {'eof_cell_hist_kernel': BYTES_ACC * N_PART, 'eof_cell_scatter_kernel': BYTES_ACC * N_PART,
+    alg = {'eof_cell_hist_kernel': BYTES_ACC * N_PART, 'eof_tile_colscan_kernel': 2 * 148 * 128 * 64 * 4, 'eof_cell_scatter_kernel': BYTES_ACC * N_PART,
            'eof_segsum_kernel': BYTES_ACC * N_PART, 'eof_node_contract_kernel': 129 * 65 * 256 * 8,
            'eof_contract_kernel': 6 * 7 * 18 * 129 * 65 * 8,
            'eof_force_sorted_kernel': BYTES_FORCE * N_PART, 'eof_force_sorted_mma_kernel': BYTES_FORCE * N_PART,
@@ -778,8 +780,8 @@ def run_gpu(args):
         with open(tpath) as f:
             traffic = json.load(f).get(dom)
     step_alg = (BYTES_ACC + BYTES_FORCE) * N_PART            # 104 B / particle for the whole step
-    t_accpass = (kms['eof_cell_hist_kernel'] + kms['eof_cell_scatter_kernel'] + kms['eof_segsum_kernel'] +
-                 kms['eof_node_contract_kernel'])
+    t_accpass = (kms['eof_cell_hist_kernel'] + kms.get('eof_tile_colscan_kernel', 0.0) + kms['eof_cell_scatter_kernel'] +
+                 kms['eof_segsum_kernel'] + kms['eof_node_contract_kernel'])
     t_forcepass = sum(v for k, v in kms.items() if k.startswith('eof_force_'))
     # The executed FP64 work of the dominant kernel next to its HBM figure: per sorted record
     # 6 DMMA m8n8k4 per 8 records = 384 flop on the tensor pipe + ~57 flop per lane x 4 lanes = 228 flop of vector
@@ -961,6 +963,7 @@ def main():
                     help='N>1: per-step coefficient sum by the peer-memory kernel (default) or NCCL')
     ap.add_argument('--grid-pct', type=int, default=100, help='share of the SMs the persistent grids of the step are sized for')
     ap.add_argument('--pg-per-stream', type=int, default=0, help='N>1: one NCCL communicator per stream (1) or shared (0)')
+    ap.add_argument('--sort-stable', type=int, default=-1, help='option sort_stable of the cell sort (default: library default)')
     ap.add_argument('--configs', default='all', help="the other BASELINE configurations to run after the headline step: 'all', 'none' "
                                                       "or a comma list of C1,C3,C4,C5")
     ap.add_argument('--configs-scale', type=float, default=1.0, help='multiplies the particle / orbit / step counts of --configs')

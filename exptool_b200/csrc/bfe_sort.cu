@@ -185,6 +185,259 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
 }
 
 // ---------------------------------------------------------------------------
+// STABLE counting sort without global atomics (option "sort_stable", default 1; north_star (d): "no global atomics on
+// the hot loop").  The slot claims of eof_cell_scatter_kernel above are integer atomics on global counters: correct, but
+// the order of the records inside a cell -- and with it the FP64 summation order of the deposit -- follows the atomics'
+// arrival order, so the coefficients were reproducible to ~1e-16 only.  Here the position of every particle is a pure
+// function of the input:
+//   eof_tile_hist_kernel    : the set is cut into TILES of 1024 U consecutive particles (U <= 8, about one tile per SM);
+//                             one CTA per tile builds the tile's cell histogram in shared memory (shared-memory integer
+//                             counters: a count does not depend on the order of its increments) and writes it as row
+//                             H[tile][cell] (coalesced);
+//   eof_tile_colscan_kernel : thread per cell: exclusive prefix over the tiles in place, H[tile][cell] = number of
+//                             particles of that cell in EARLIER tiles; the last CTA scans the cell totals -> cell_start;
+//   eof_tile_scatter_kernel : one CTA per tile: shared-memory counting sort of the tile's particle ids by cell (the
+//                             provisional order inside a cell comes from shared-memory atomics), then every particle counts
+//                             the members of its own (tile, cell) group with a SMALLER id: its rank, independent of the
+//                             provisional order.  position = cell_start[cell] + H[tile][cell] + rank: the sort is stable
+//                             (ascending particle index inside every cell) and bit-reproducible, and so is everything
+//                             downstream of it.  Then the 64-byte record is built and stored as before.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+eof_tile_hist_kernel(EofGeom g, int ncell, int64_t n, int tile, const double* __restrict__ x, const double* __restrict__ y,
+                     const double* __restrict__ z, int* __restrict__ H, int* __restrict__ cellid) {
+    extern __shared__ int s_hist[];
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) s_hist[c] = 0;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * tile;
+    // two particles per pass: six independent loads in flight
+    for (int o = threadIdx.x; o < tile; o += 2048) {
+        const int64_t i = base + o, i2 = i + 1024;
+        const bool one = i < n, two = (o + 1024 < tile) && i2 < n;
+        const double px = one ? __ldg(x + i) : 1.0, py = one ? __ldg(y + i) : 0.0, pz = one ? __ldg(z + i) : 0.0;
+        const double qx = two ? __ldg(x + i2) : 1.0, qy = two ? __ldg(y + i2) : 0.0, qz = two ? __ldg(z + i2) : 0.0;
+        int cell, cell2;
+        if (one) {
+            if (!bfe_eof_cell_fast(g, px, py, pz, cell)) {        // near a cell edge / unusual input: exact FP64 index
+                const double r = sqrt(px * px + py * py + 1.e-10);
+                cell = bfe_eof_bin(g, r, pz).cell;
+            }
+            atomicAdd(&s_hist[cell], 1);                          // shared-memory integer count
+            cellid[i] = cell;
+        }
+        if (two) {
+            if (!bfe_eof_cell_fast(g, qx, qy, qz, cell2)) {
+                const double r = sqrt(qx * qx + qy * qy + 1.e-10);
+                cell2 = bfe_eof_bin(g, r, qz).cell;
+            }
+            atomicAdd(&s_hist[cell2], 1);
+            cellid[i2] = cell2;
+        }
+    }
+    __syncthreads();
+    int* row = H + (size_t)blockIdx.x * ncell;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) row[c] = s_hist[c];
+}
+
+// 256 cells x 4 tile groups per CTA: a thread sums its quarter of the tiles, the four partial sums of a cell are exchanged
+// through shared memory, then the thread rewrites its quarter as exclusive prefixes (a quarter of the serial load chain
+// of one thread per cell, and four times as many CTAs)
+__global__ void __launch_bounds__(1024)
+eof_tile_colscan_kernel(int ncell, int ntile, int* __restrict__ H, int* __restrict__ total, int* __restrict__ cell_start,
+                        unsigned int* __restrict__ counter) {
+    __shared__ int s_h[1024];
+    __shared__ int s_part[4][256];
+    __shared__ int s_wsum[32];
+    __shared__ bool s_last;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    const int cl = threadIdx.x & 255, q = threadIdx.x >> 8;
+    const int c = blockIdx.x * 256 + cl;
+    const int tq = (ntile + 3) / 4, t0 = q * tq, t1 = min(ntile, t0 + tq);
+    int sum = 0;
+    if (c < ncell) {
+        int t = t0;
+        for (; t + 7 < t1; t += 8) {                              // eight independent loads in flight
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(H + (size_t)(t + u) * ncell + c);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sum += v[u];
+        }
+        for (; t < t1; ++t) sum += __ldcg(H + (size_t)t * ncell + c);
+    }
+    s_part[q][cl] = sum;
+    __syncthreads();
+    if (c < ncell) {
+        int run = 0;
+        for (int k = 0; k < q; ++k) run += s_part[k][cl];
+        int t = t0;
+        for (; t + 7 < t1; t += 8) {
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(H + (size_t)(t + u) * ncell + c);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { H[(size_t)(t + u) * ncell + c] = run; run += v[u]; }
+        }
+        for (; t < t1; ++t) { const int v = __ldcg(H + (size_t)t * ncell + c); H[(size_t)t * ncell + c] = run; run += v; }
+    }
+    // exclusive prefix of this CTA's 256 cell totals (threads of tile group 3 hold them), block sum published
+    __syncthreads();
+    if (q == 3) s_part[0][cl] = (c < ncell) ? sum + s_part[0][cl] + s_part[1][cl] + s_part[2][cl] : 0;   // = total of cell c
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int v = s_part[0][threadIdx.x];
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int w = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += w; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncwarp();
+        s_part[1][threadIdx.x] = incl - v;                 // exclusive inside the warp
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const int warp = threadIdx.x >> 5;
+        int add = 0;
+        for (int k = 0; k < warp; ++k) add += s_wsum[k];
+        const int cc = blockIdx.x * 256 + threadIdx.x;
+        if (cc < ncell) cell_start[cc] = s_part[1][threadIdx.x] + add;      // local exclusive prefix; block prefix added below
+        if (threadIdx.x == 255) total[blockIdx.x] = s_part[1][255] + add + s_part[0][255];   // block sum (total[] re-used: nblk <= ncell)
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);       // one integer add per CTA: not on the particle loop
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        // block prefixes (<= 1024 blocks) by one warp-shuffle scan, then one coalesced pass that adds them
+        const int nb = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int v = (int)threadIdx.x < nb ? __ldcg(total + threadIdx.x) : 0;
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int w = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += w; }
+        __syncthreads();
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += u; }
+            s_wsum[lane] = w;
+        }
+        __syncthreads();
+        s_h[threadIdx.x] = incl - v + (warp > 0 ? s_wsum[warp - 1] : 0);       // exclusive prefix of block threadIdx.x
+        __syncthreads();
+        for (int cc = threadIdx.x; cc < ncell; cc += 1024) cell_start[cc] = __ldcg(cell_start + cc) + s_h[cc >> 8];
+        if ((int)threadIdx.x == nb - 1) cell_start[ncell] = s_h[nb - 1] + v;    // particle count
+        if (threadIdx.x == 0) *counter = 0u;
+        if ((int)threadIdx.x < nb) total[threadIdx.x] = 0;                       // hist / total array left clear, as the other paths expect
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+eof_tile_scatter_kernel(EofGeom g, int ncell, int64_t n, int tile, const double* __restrict__ x, const double* __restrict__ y,
+                        const double* __restrict__ z, const double* __restrict__ mass, const int* __restrict__ cell_start,
+                        const int* __restrict__ H, EofRec* __restrict__ rec, int* __restrict__ inv, double* __restrict__ r_orig) {
+    extern __shared__ int s_mem[];
+    __shared__ int s_wsum[32];
+    // ONE cell-sized array: counts -> exclusive starts (in place) -> group ENDS (the placement advances each start to the
+    // end of its group, which is the start of the next one), so group c is [c ? s_cnt[c-1] : 0, s_cnt[c])
+    int* s_cnt = s_mem;                                   // [per * 1024]
+    const int per = (ncell + 1023) / 1024;
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_mem + per * 1024);   // [tile] ids ordered by cell
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < per * 1024; c += 1024) s_cnt[c] = 0;
+    bfe_pdl_wait();
+    bfe_pdl_trigger();
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * tile;
+    const int nu = tile >> 10;                            // particles per thread (<= 8)
+    int cell[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        cell[u] = -1;
+        if (u < nu) {
+            const int64_t i = base + u * 1024 + tid;
+            if (i < n) { cell[u] = inv[i]; atomicAdd(&s_cnt[cell[u]], 1); }      // cell id left here by the histogram kernel
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the counts over the cells, in place (thread = `per` consecutive cells, two levels of warp shuffles)
+    {
+        const int lo = tid * per;
+        int sum = 0;
+        for (int k = 0; k < per; ++k) sum += s_cnt[lo + k];
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+            s_wsum[lane] = w;
+        }
+        __syncthreads();
+        int run = incl - sum + (warp > 0 ? s_wsum[warp - 1] : 0);
+        for (int k = 0; k < per; ++k) { const int h = s_cnt[lo + k]; s_cnt[lo + k] = run; run += h; }
+    }
+    __syncthreads();
+    // provisional placement of the ids (order inside a cell: arrival order of the shared-memory atomics)
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (cell[u] >= 0) s_list[atomicAdd(&s_cnt[cell[u]], 1)] = (unsigned short)(u * 1024 + tid);
+    __syncthreads();
+    // rank = members of the own (tile, cell) group with a smaller id; record; stores.  Two particles per pass: their loads
+    // (coordinates, cell_start, tile offset) are in flight together
+#pragma unroll 1
+    for (int u0 = 0; u0 < nu; u0 += 2) {
+        double px[2], py[2], pz[2], aux[2];
+        int gbase[2], cc[2];
+        int64_t idx[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int u = u0 + v;
+            cc[v] = (u < nu) ? cell[u] : -1;
+            idx[v] = base + u * 1024 + tid;
+            const bool on = cc[v] >= 0;
+            px[v] = on ? __ldg(x + idx[v]) : 1.0; py[v] = on ? __ldg(y + idx[v]) : 0.0; pz[v] = on ? __ldg(z + idx[v]) : 0.0;
+            aux[v] = (on && mass) ? __ldg(mass + idx[v]) : 0.0;
+            gbase[v] = on ? (__ldg(cell_start + cc[v]) + __ldg(H + (size_t)blockIdx.x * ncell + cc[v])) : 0;
+        }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            if (cc[v] < 0) continue;
+            const int c = cc[v];
+            const int lo = c ? s_cnt[c - 1] : 0, hi = s_cnt[c];
+            const int me = (u0 + v) * 1024 + tid;
+            // ids are 16-bit: compare two per 32-bit word (__vcmpltu2), unaligned ends one by one
+            int rank = 0;
+            int k = lo;
+            if ((k & 1) && k < hi) { rank += (s_list[k] < me) ? 1 : 0; ++k; }
+            const unsigned int me2 = (unsigned int)me * 0x00010001u;
+            const unsigned int* w32 = reinterpret_cast<const unsigned int*>(s_list);
+            for (; k + 1 < hi; k += 2) rank += __popc(__vcmpltu2(w32[k >> 1], me2)) >> 4;
+            if (k < hi) rank += (s_list[k] < me) ? 1 : 0;
+            const int pos = gbase[v] + rank;
+            const double r = sqrt(px[v] * px[v] + py[v] * py[v] + 1.e-10);   // eof.py:531 / 1070
+            const EofBin b = bfe_eof_bin(g, r, pz[v]);                       // b.cell == c
+            double c1, s1;
+            bfe_cossin_phi(px[v], py[v], c1, s1);
+            const unsigned long long cp = ((unsigned long long)(unsigned int)c << 32) | (unsigned long long)(unsigned int)idx[v];
+            char* dst = reinterpret_cast<char*>(rec + pos);                  // two full-sector stores per record
+            bfe_st256(dst, b.c00, b.c10, b.c01, b.c11);
+            bfe_st256(dst + 32, c1, s1, aux[v], __longlong_as_double((long long)cp));
+            inv[idx[v]] = pos;                                               // original index -> sorted slot (coalesced)
+            r_orig[idx[v]] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // deposit + contract over sorted records, in two kernels.
 //
 // eof_segsum_kernel -- a WARP owns a task of 128 consecutive sorted records (dynamic task queue) and walks it
@@ -766,7 +1019,14 @@ static inline int bfe_eff_sms(const bfe_eof* h) { int v = h->num_sms * g_bfe_gri
 
 struct SortWs {
     int* hist; int* cell_start; int* cursor; EofRec* rec; double* r_orig; double2* tmp; int* inv; double* seg;
+    int* H;                // [tiles][ncell] of the stable tile sort
 };
+int g_bfe_sort_stable = 1;     // option "sort_stable": stable, atomic-free tile counting sort (1) / slot claims by global integer atomics (0)
+
+static int64_t tile_rows_for(const bfe_eof* h, int64_t cap) {
+    const int64_t a = h->num_sms, b = cap / 8192 + 2;
+    return a > b ? a : b;
+}
 
 static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
     const int ncell = h->g.numx * h->g.numy;
@@ -780,7 +1040,8 @@ static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
         // per particle: 64-B record, R (8 B), 48-B force slot, inverse permutation (4 B); then the segment
         // tiles (512 B per cell and per 128-record task)
         BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)cap +
-                                             512 * ((size_t)ncell + (size_t)cap / SegSum::TASK + 2)));
+                                             512 * ((size_t)ncell + (size_t)cap / SegSum::TASK + 2) +
+                                             sizeof(int) * (size_t)ncell * (size_t)tile_rows_for(h, cap) + 256));
         BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
         BFE_CUDA(cudaDeviceSynchronize());
         h->sort_cap = cap;
@@ -792,6 +1053,8 @@ static int sort_workspace(bfe_eof* h, int64_t n, SortWs* ws) {
     ws->tmp = (double2*)(b + o_rec + (sizeof(EofRec) + sizeof(double)) * (size_t)h->sort_cap);
     ws->inv = (int*)(b + o_rec + (sizeof(EofRec) + sizeof(double) + 48) * (size_t)h->sort_cap);
     ws->seg = (double*)(b + o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)h->sort_cap);
+    ws->H = (int*)(b + align_up(o_rec + (sizeof(EofRec) + sizeof(double) + 48 + sizeof(int)) * (size_t)h->sort_cap +
+                                512 * ((size_t)ncell + (size_t)h->sort_cap / SegSum::TASK + 2), 256));
     return BFE_OK;
 }
 
@@ -807,6 +1070,41 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
     int rc = sort_workspace(h, n, &ws);
     if (rc != BFE_OK) return rc;
     const int ncell = h->g.numx * h->g.numy;
+    if (g_bfe_sort_stable && n > 0) {
+        // tiles of 1024 U consecutive particles, about one per SM, U <= 8 (ids fit 13 bits; rows fit the workspace)
+        int64_t U = (n + (int64_t)bfe_eff_sms(h) * 1024 - 1) / ((int64_t)bfe_eff_sms(h) * 1024);
+        U = U < 1 ? 1 : (U > 8 ? 8 : U);
+        const int tile = (int)(U * 1024);
+        const int ntile = (int)((n + tile - 1) / tile);
+        const int per = (ncell + 1023) / 1024;
+        const size_t ss_h = sizeof(int) * (size_t)per * 1024;
+        const size_t ss_s = sizeof(int) * (size_t)per * 1024 + sizeof(unsigned short) * (size_t)tile + 16;
+        if (ss_s <= 200 * 1024 && (int64_t)ntile <= tile_rows_for(h, h->sort_cap)) {
+            if (ss_h > 48 * 1024) {
+                BFE_CUDA(cudaFuncSetAttribute(eof_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_h));
+            }
+            if (ss_s > 48 * 1024)
+                BFE_CUDA(cudaFuncSetAttribute(eof_tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_s));
+            int kt = bfe_kt_begin("eof_cell_hist_kernel", stream);
+            BFE_CUDA(bfe_launch(eof_tile_hist_kernel, dim3(ntile), dim3(1024), ss_h, stream, nullptr, 0, h->g, ncell, n, tile, x, y,
+                                z, ws.H, ws.inv));
+            bfe_kt_end(kt, stream);
+            kt = bfe_kt_begin("eof_tile_colscan_kernel", stream);
+            BFE_CUDA(bfe_launch(eof_tile_colscan_kernel, dim3((ncell + 255) / 256), dim3(1024), 0, stream, nullptr, 0, ncell,
+                                ntile, ws.H, ws.hist, ws.cell_start, h->counter));
+            bfe_kt_end(kt, stream);
+            BFE_LAUNCH_CHECK("eof_tile_hist_kernel");
+            bfe_count_launch(1);
+            kt = bfe_kt_begin("eof_cell_scatter_kernel", stream);
+            BFE_CUDA(bfe_launch(eof_tile_scatter_kernel, dim3(ntile), dim3(1024), ss_s, stream, nullptr, 0, h->g, ncell, n, tile, x,
+                                y, z, mass, (const int*)ws.cell_start, (const int*)ws.H, ws.rec, ws.inv, ws.r_orig));
+            bfe_kt_end(kt, stream);
+            BFE_LAUNCH_CHECK("eof_tile_scatter_kernel");
+            h->prepared_n = n;
+            h->prepared_has_mass = mass ? 1 : 0;
+            return BFE_OK;
+        }
+    }
     int grid = (int)((n + 2047) / 2048);
     if (grid > bfe_eff_sms(h)) grid = bfe_eff_sms(h);        // one 1024-thread CTA per SM: the per-CTA merge is paid once per SM
     if (grid < 1) grid = 1;

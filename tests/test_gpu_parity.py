@@ -683,3 +683,43 @@ def test_key_ordered_paths_at_size(ops, lmax):
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
+
+
+def test_stable_cell_sort_is_bit_reproducible(ops):
+    """The stable, atomic-free tile counting sort behind bfe_eof_prepare (option sort_stable, default): the sorted accumulate
+    and the sorted force evaluation are bit-identical from run to run (round 1: slot claims by global integer atomics, order
+    inside a cell = arrival order, coefficients reproducible to ~1e-16 only), equal to the atomic-claim path and to the direct
+    kernel within rounding, for ragged sizes, a set concentrated in ONE cell, and a set with NaNs."""
+    import torch
+    meta = dict(eof_params={}, kind='smooth', seed=0)
+    pe, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    saved = {k: ops.get_option(k) for k in ('sort_stable', 'eof_accumulate_mode', 'eof_force_mode')}
+    try:
+        for n, seed in ((300001, 5), (40000, 6), (1025, 7)):
+            x, y, z, m = S.exponential_disc(n, seed)
+            if seed == 6:                                   # all particles in one table cell: the longest possible group
+                x = 0.01 + 1e-7 * x; y = 1e-7 * y; z = 1e-6 + 1e-9 * z
+            if seed == 7:
+                x = x.copy(); x[3] = np.nan
+            ops.set_option('eof_accumulate_mode', 2); ops.set_option('eof_force_mode', 2)
+            ops.set_option('sort_stable', 1)
+            runs = []
+            for rep in range(3):
+                c, s_ = E.accumulate(x, y, z, m)
+                E.contract(c, s_)
+                runs.append((c.clone(), s_.clone(), E.force(x, y, z).clone()))
+            for rep in (1, 2):
+                for a, b in zip(runs[0], runs[rep]):
+                    assert torch.equal(a, b) or (seed == 7 and torch.equal(torch.isnan(a), torch.isnan(b))), (n, rep)
+            if seed == 7:
+                continue
+            ops.set_option('sort_stable', 0)
+            c0, s0 = E.accumulate(x, y, z, m)
+            assert relerr(c0.cpu().numpy(), runs[0][0].cpu().numpy()) < 1e-12 and relerr(s0.cpu().numpy(), runs[0][1].cpu().numpy()) < 1e-12
+            ops.set_option('eof_accumulate_mode', 1)
+            c1, s1 = E.accumulate(x, y, z, m)
+            assert relerr(c1.cpu().numpy(), runs[0][0].cpu().numpy()) < 1e-12
+    finally:
+        for k, v in saved.items():
+            ops.set_option(k, v)
