@@ -62,13 +62,10 @@ def test_eof_accumulate_golden(ops, eof_mode, name):
     c, s = E.accumulate(d['x'], d['y'], d['z'], d['m'])
     assert relerr(c.cpu().numpy(), d['cos']) < TOL
     assert relerr(s.cpu().numpy(), d['sin']) < TOL
-    # repeat: the handle's workspace/counter must be reusable; the direct kernel is bit-deterministic,
-    # the sorted one sums each cell in cursor-claim order (differences at the 1e-16 level)
+    # repeat: the handle's workspace/counter must be reusable, and BOTH formulations are bit-deterministic (the sorted
+    # one since round 2: stable, atomic-free tile counting sort -- ascending particle index inside every cell)
     c2, s2 = E.accumulate(d['x'], d['y'], d['z'], d['m'])
-    if eof_mode == 'direct':
-        assert np.array_equal(c2.cpu().numpy(), c.cpu().numpy())
-    else:
-        assert relerr(c2.cpu().numpy(), c.cpu().numpy()) < 1e-13
+    assert np.array_equal(c2.cpu().numpy(), c.cpu().numpy()) and np.array_equal(s2.cpu().numpy(), s.cpu().numpy())
 
 
 @pytest.mark.parametrize('name', EOF_CASES)
