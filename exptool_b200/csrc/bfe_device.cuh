@@ -106,32 +106,42 @@ __device__ __forceinline__ EofBin bfe_eof_bin(const EofGeom& g, double r, double
 // Cell id only (no weights), for the histogram pass of the cell sort: the index arithmetic is done in FP32 and
 // accepted only when the result is provably the FP64 one -- X and Y further than a rigorous error bound from
 // every integer (cell edge) and finite.  Otherwise (about 1 particle in 10^3, plus NaN / overflow / denormal
-// inputs) the caller recomputes with bfe_eof_bin.  Error budget of the FP32 chain: inputs 6e-8 relative,
-// sqrt / divide / log <= 2 ulp each, so |xi_f - xi| <= 2e-7 max(1,|xi|) and likewise for y; the bound below
-// carries a factor 4 on top and the FP32 rounding of the final scale-and-shift.
+// inputs) the caller recomputes with bfe_eof_bin.  The FP32 chain uses the hardware approximations (sqrt.approx,
+// div.approx = __fdividef, lg2.approx = __logf: one MUFU each instead of ~10-20 instructions of IEEE fix-up; the
+// histogram kernel was issue-bound on them, ncu profiles/r02_ncu_full_step_kernels.csv).  Error budget: inputs 6e-8
+// relative; sqrt.approx 1 ulp, __fdividef 2 ulp (operands here are far inside 2^+-126), __logf 2^-21.4 = 3.6e-7 ABSOLUTE
+// for arguments in [0.5, 2] and 3 ulp outside -- its argument u + sqrt(u^2+1) is >= 1, and log r (cmap 2) of r in
+// [0.5, 2] has |xi| < 0.7.  Chains: xi (cmap 1) = (q-1)/(q+1): <= 6 ulp; y = sign * log(u + sqrt(u^2+1)): <= 3.6e-7
+// absolute + 8 ulp relative (with the z / (|z| + 1e-8) factor).  So |xi_f - xi| and |y_f - y| <= 8e-7 max(1, |.|); the bound below carries a factor 2
+// on top and the FP32 rounding of the final scale-and-shift.
+__device__ __forceinline__ float bfe_sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ bool bfe_eof_cell_fast(const EofGeom& g, double px, double py, double pz, int& cell) {
     const float xf = (float)px, yf = (float)py, zf = (float)pz;
-    const float r = sqrtf(fmaf(xf, xf, fmaf(yf, yf, 1.e-10f)));
+    const float r = bfe_sqrt_approx(fmaf(xf, xf, fmaf(yf, yf, 1.e-10f)));
     float xi;
     if (g.cmap == 1) {
-        const float q = r / (float)g.ascale;
-        xi = (q - 1.0f) / (q + 1.0f);
+        const float q = r * (float)g.inv_ascale;
+        xi = __fdividef(q - 1.0f, q + 1.0f);
     } else if (g.cmap == 2) {
-        xi = logf(r);
+        xi = __logf(r);
     } else {
         xi = r;
     }
     const float az = fabsf(zf);
-    const float u = az / fabsf((float)g.hscale);
-    const float ash = logf(u + sqrtf(fmaf(u, u, 1.0f)));
-    const float yy = (zf / (az + 1.0e-8f)) * ash;
+    const float u = az * fabsf((float)g.inv_hscale);
+    const float ash = __logf(u + bfe_sqrt_approx(fmaf(u, u, 1.0f)));
+    const float yy = __fdividef(zf, az + 1.0e-8f) * ash;
     const float idx = (float)g.inv_dx, idy = (float)g.inv_dy;
     const float X = (xi - (float)g.xmin) * idx;
     const float Y = (yy - (float)g.ymin) * idy;
-    const float tolx = 8.0e-7f * fabsf(idx) * fmaxf(1.0f, fmaxf(fabsf(xi), fabsf((float)g.xmin))) + 4.0e-7f * fabsf(X) + 1.0e-6f;
-    const float toly = 8.0e-7f * fabsf(idy) * fmaxf(1.0f, fmaxf(fabsf(yy), fabsf((float)g.ymin))) + 4.0e-7f * fabsf(Y) + 1.0e-6f;
+    const float tolx = 1.6e-6f * fabsf(idx) * fmaxf(1.0f, fmaxf(fabsf(xi), fabsf((float)g.xmin))) + 4.0e-7f * fabsf(X) + 1.0e-6f;
+    const float toly = 1.6e-6f * fabsf(idy) * fmaxf(1.0f, fmaxf(fabsf(yy), fabsf((float)g.ymin))) + 4.0e-7f * fabsf(Y) + 1.0e-6f;
     // finite, inside float's comfortable range, and away from every cell edge by more than the bound
-    bool ok = (fabsf(X) < 1.0e9f) && (fabsf(Y) < 1.0e9f) && (r > 1.0e-30f) && (r < 1.0e18f) && (az < 1.0e18f);
+    bool ok = (fabsf(X) < 1.0e9f) && (fabsf(Y) < 1.0e9f) && (r > 1.0e-18f) && (r < 1.0e18f) && (az < 1.0e18f);
     int ix, iy;
     if (X < -tolx) ix = 0;
     else if (X > (float)g.numx + tolx) ix = g.numx - 1;

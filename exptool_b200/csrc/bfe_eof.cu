@@ -154,49 +154,58 @@ eof_accumulate_kernel(EofGeom g, const double* __restrict__ t_acc, int nch, int 
 // grid: (ceil(nnode/128), (mmax+1)*6); thread per node, loops n (loads coalesced over nodes).
 // q = field*2 + trig : 0 pc, 1 ps, 2 rc, 3 rs, 4 zc, 5 zs.  t_force = [potC,rfC,zfC,potS,rfS,zfS].
 // ---------------------------------------------------------------------------
-__global__ void eof_contract_kernel(EofGeom g, const double* __restrict__ t_force, size_t tab_elems,
-                                    const double* __restrict__ cosc, const double* __restrict__ sinc,
-                                    int m1, int m2, int nuse, int no_odd,
-                                    double* __restrict__ G, int gstride, int deep) {
-    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+// Two nodes per thread, six terms each per pass: 12 independent table loads in flight per thread, and the grid
+// (33 x 42 CTAs for the 129 x 65 table) is resident in ONE wave -- with one node per thread it was 1.17 waves of
+// short-lived CTAs, i.e. the time of two (ncu: 36 % of DRAM peak, long-scoreboard 38 cycles per issue).
+__global__ void __launch_bounds__(128)
+eof_contract_kernel(EofGeom g, const double* __restrict__ t_force, size_t tab_elems,
+                    const double* __restrict__ cosc, const double* __restrict__ sinc,
+                    int m1, int m2, int nuse, int no_odd,
+                    double* __restrict__ G, int gstride, int deep) {
+    const int node = blockIdx.x * 256 + threadIdx.x, node2 = node + 128;
     const int m = blockIdx.y / 6, q = blockIdx.y % 6;
     bfe_pdl_wait();
     bfe_pdl_trigger();
     if (node >= g.nnode) return;
+    const bool two = node2 < g.nnode;
     const int field = q >> 1, trig = q & 1;
-    double s = 0.0;
+    double s = 0.0, r = 0.0;
     bool use = (m >= m1) && (m <= m2) && !(no_odd && (m & 1)) && !(trig == 1 && m == 0);
     if (use) {
         const double* T = t_force + (size_t)(trig * 3 + field) * tab_elems + (size_t)m * g.norder * g.nnode + node;
+        const double* T2 = two ? T + 128 : T;
         const double* c = (trig ? sinc : cosc) + m * g.norder;
         const int nn = nuse < g.norder ? nuse : g.norder;
-        // U independent table loads in flight per thread (the one-accumulator loop exposed one DRAM latency per
-        // term: long-scoreboard 40 cycles per issue, 34 % of DRAM peak in ncu)
-        double s1 = 0.0, s2 = 0.0;
+        double s1 = 0.0, s2 = 0.0, r1 = 0.0, r2 = 0.0;
         int k = 0;
         if (deep) {
             for (; k + 8 < nn; k += 9) {
-                double t[9];
+                double t[9], v[9];
 #pragma unroll
-                for (int u = 0; u < 9; ++u) t[u] = __ldg(T + (size_t)(k + u) * g.nnode);
+                for (int u = 0; u < 9; ++u) { t[u] = __ldg(T + (size_t)(k + u) * g.nnode); v[u] = __ldg(T2 + (size_t)(k + u) * g.nnode); }
 #pragma unroll
                 for (int u = 0; u < 9; u += 3) {
-                    s = fma(__ldg(c + k + u), t[u], s); s1 = fma(__ldg(c + k + u + 1), t[u + 1], s1);
-                    s2 = fma(__ldg(c + k + u + 2), t[u + 2], s2);
+                    const double c0 = __ldg(c + k + u), c1 = __ldg(c + k + u + 1), c2 = __ldg(c + k + u + 2);
+                    s = fma(c0, t[u], s); s1 = fma(c1, t[u + 1], s1); s2 = fma(c2, t[u + 2], s2);
+                    r = fma(c0, v[u], r); r1 = fma(c1, v[u + 1], r1); r2 = fma(c2, v[u + 2], r2);
                 }
             }
         }
         for (; k + 5 < nn; k += 6) {
-            double t[6];
+            double t[6], v[6], cc[6];
 #pragma unroll
-            for (int u = 0; u < 6; ++u) t[u] = __ldg(T + (size_t)(k + u) * g.nnode);
-            s = fma(__ldg(c + k), t[0], s);      s1 = fma(__ldg(c + k + 1), t[1], s1); s2 = fma(__ldg(c + k + 2), t[2], s2);
-            s = fma(__ldg(c + k + 3), t[3], s);  s1 = fma(__ldg(c + k + 4), t[4], s1); s2 = fma(__ldg(c + k + 5), t[5], s2);
+            for (int u = 0; u < 6; ++u) { t[u] = __ldg(T + (size_t)(k + u) * g.nnode); v[u] = __ldg(T2 + (size_t)(k + u) * g.nnode); cc[u] = __ldg(c + k + u); }
+            s = fma(cc[0], t[0], s); s1 = fma(cc[1], t[1], s1); s2 = fma(cc[2], t[2], s2);
+            s = fma(cc[3], t[3], s); s1 = fma(cc[4], t[4], s1); s2 = fma(cc[5], t[5], s2);
+            r = fma(cc[0], v[0], r); r1 = fma(cc[1], v[1], r1); r2 = fma(cc[2], v[2], r2);
+            r = fma(cc[3], v[3], r); r1 = fma(cc[4], v[4], r1); r2 = fma(cc[5], v[5], r2);
         }
-        for (; k < nn; ++k) s = fma(__ldg(c + k), __ldg(T + (size_t)k * g.nnode), s);
+        for (; k < nn; ++k) { const double ck = __ldg(c + k); s = fma(ck, __ldg(T + (size_t)k * g.nnode), s); r = fma(ck, __ldg(T2 + (size_t)k * g.nnode), r); }
         s += s1 + s2;
+        r += r1 + r2;
     }
     G[(size_t)node * gstride + m * 6 + q] = s;
+    if (two) G[(size_t)node2 * gstride + m * 6 + q] = r;
 }
 
 // ---------------------------------------------------------------------------
@@ -445,7 +454,7 @@ extern "C" int bfe_eof_contract(bfe_eof* h, const double* cosc, const double* si
     if (!h->t_force) return BFE_ERR_STATE;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nuse < 0) nuse = 0;
-    dim3 grd((h->g.nnode + 127) / 128, (h->g.mmax + 1) * 6);
+    dim3 grd((h->g.nnode + 255) / 256, (h->g.mmax + 1) * 6);
     const int kt = bfe_kt_begin("eof_contract_kernel", stream);
     BFE_CUDA(bfe_launch(eof_contract_kernel, grd, dim3(128), 0, stream, h->t_force, 6 * h->tab_elems * sizeof(double),
                         h->g, h->t_force, h->tab_elems, cosc, sinc, m1, m2, nuse, no_odd, h->g_con, h->gstride, g_bfe_contract_deep));

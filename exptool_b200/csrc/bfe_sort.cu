@@ -212,28 +212,28 @@ eof_tile_hist_kernel(EofGeom g, int ncell, int64_t n, int tile, const double* __
     bfe_pdl_trigger();
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * tile;
-    // two particles per pass: six independent loads in flight
-    for (int o = threadIdx.x; o < tile; o += 2048) {
-        const int64_t i = base + o, i2 = i + 1024;
-        const bool one = i < n, two = (o + 1024 < tile) && i2 < n;
-        const double px = one ? __ldg(x + i) : 1.0, py = one ? __ldg(y + i) : 0.0, pz = one ? __ldg(z + i) : 0.0;
-        const double qx = two ? __ldg(x + i2) : 1.0, qy = two ? __ldg(y + i2) : 0.0, qz = two ? __ldg(z + i2) : 0.0;
-        int cell, cell2;
-        if (one) {
-            if (!bfe_eof_cell_fast(g, px, py, pz, cell)) {        // near a cell edge / unusual input: exact FP64 index
-                const double r = sqrt(px * px + py * py + 1.e-10);
-                cell = bfe_eof_bin(g, r, pz).cell;
-            }
-            atomicAdd(&s_hist[cell], 1);                          // shared-memory integer count
-            cellid[i] = cell;
+    // two particles per pass: six independent loads in flight per thread (four per pass, fully unrolled, was slower)
+    constexpr int PB = 2;
+    for (int o0 = threadIdx.x; o0 < tile; o0 += PB * 1024) {
+        double px[PB], py[PB], pz[PB];
+        bool on[PB];
+#pragma unroll
+        for (int v = 0; v < PB; ++v) {
+            const int o = o0 + v * 1024;
+            const int64_t i = base + o;
+            on[v] = (o < tile) && (i < n);
+            px[v] = on[v] ? __ldg(x + i) : 1.0; py[v] = on[v] ? __ldg(y + i) : 0.0; pz[v] = on[v] ? __ldg(z + i) : 0.0;
         }
-        if (two) {
-            if (!bfe_eof_cell_fast(g, qx, qy, qz, cell2)) {
-                const double r = sqrt(qx * qx + qy * qy + 1.e-10);
-                cell2 = bfe_eof_bin(g, r, qz).cell;
+#pragma unroll
+        for (int v = 0; v < PB; ++v) {
+            if (!on[v]) continue;
+            int cell;
+            if (!bfe_eof_cell_fast(g, px[v], py[v], pz[v], cell)) {   // near a cell edge / unusual input: exact FP64 index
+                const double r = sqrt(px[v] * px[v] + py[v] * py[v] + 1.e-10);
+                cell = bfe_eof_bin(g, r, pz[v]).cell;
             }
-            atomicAdd(&s_hist[cell2], 1);
-            cellid[i2] = cell2;
+            atomicAdd(&s_hist[cell], 1);                              // shared-memory integer count
+            cellid[base + o0 + v * 1024] = cell;
         }
     }
     __syncthreads();
@@ -241,70 +241,88 @@ eof_tile_hist_kernel(EofGeom g, int ncell, int64_t n, int tile, const double* __
     for (int c = threadIdx.x; c < ncell; c += blockDim.x) row[c] = s_hist[c];
 }
 
-// 256 cells x 4 tile groups per CTA: a thread sums its quarter of the tiles, the four partial sums of a cell are exchanged
-// through shared memory, then the thread rewrites its quarter as exclusive prefixes (a quarter of the serial load chain
-// of one thread per cell, and four times as many CTAs)
+// 64 cells x 16 tile groups per CTA (128 CTAs for the 128 x 64 table): a thread loads its share of a cell's column -- up to
+// 16 rows, all in flight together, kept in registers -- the 16 partial sums of a cell are exchanged through shared memory,
+// and the thread writes its rows back as exclusive prefixes.  (First version: 256 cells x 4 groups = 32 CTAs, two passes
+// over the column with 35 dependent-latency loads each: 16 us against 2 us of L2 traffic.)
+#define BFE_COLSCAN_CW 64
+#define BFE_COLSCAN_TG 16
 __global__ void __launch_bounds__(1024)
 eof_tile_colscan_kernel(int ncell, int ntile, int* __restrict__ H, int* __restrict__ total, int* __restrict__ cell_start,
                         unsigned int* __restrict__ counter) {
+    constexpr int CW = BFE_COLSCAN_CW, TG = BFE_COLSCAN_TG, KEEP = 16;
     __shared__ int s_h[1024];
-    __shared__ int s_part[4][256];
+    __shared__ int s_part[TG][CW];
+    __shared__ int s_excl[CW];
     __shared__ int s_wsum[32];
     __shared__ bool s_last;
     bfe_pdl_wait();
     bfe_pdl_trigger();
-    const int cl = threadIdx.x & 255, q = threadIdx.x >> 8;
-    const int c = blockIdx.x * 256 + cl;
-    const int tq = (ntile + 3) / 4, t0 = q * tq, t1 = min(ntile, t0 + tq);
+    const int cl = threadIdx.x & (CW - 1), q = threadIdx.x / CW;
+    const int c = blockIdx.x * CW + cl;
+    const int tq = (ntile + TG - 1) / TG, t0 = q * tq, t1 = min(ntile, t0 + tq);
+    const bool inreg = tq <= KEEP;                              // warp-uniform
+    int v[KEEP];
     int sum = 0;
     if (c < ncell) {
-        int t = t0;
-        for (; t + 7 < t1; t += 8) {                              // eight independent loads in flight
-            int v[8];
+        if (inreg) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(H + (size_t)(t + u) * ncell + c);
+            for (int u = 0; u < KEEP; ++u) v[u] = (t0 + u < t1) ? __ldcg(H + (size_t)(t0 + u) * ncell + c) : 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) sum += v[u];
+            for (int u = 0; u < KEEP; ++u) sum += v[u];
+        } else {
+            int t = t0;
+            for (; t + 7 < t1; t += 8) {                          // eight independent loads in flight
+                int w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = __ldcg(H + (size_t)(t + u) * ncell + c);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum += w[u];
+            }
+            for (; t < t1; ++t) sum += __ldcg(H + (size_t)t * ncell + c);
         }
-        for (; t < t1; ++t) sum += __ldcg(H + (size_t)t * ncell + c);
     }
     s_part[q][cl] = sum;
     __syncthreads();
     if (c < ncell) {
         int run = 0;
         for (int k = 0; k < q; ++k) run += s_part[k][cl];
-        int t = t0;
-        for (; t + 7 < t1; t += 8) {
-            int v[8];
+        if (inreg) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(H + (size_t)(t + u) * ncell + c);
+            for (int u = 0; u < KEEP; ++u)
+                if (t0 + u < t1) { H[(size_t)(t0 + u) * ncell + c] = run; run += v[u]; }
+        } else {
+            int t = t0;
+            for (; t + 7 < t1; t += 8) {
+                int w[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { H[(size_t)(t + u) * ncell + c] = run; run += v[u]; }
+                for (int u = 0; u < 8; ++u) w[u] = __ldcg(H + (size_t)(t + u) * ncell + c);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { H[(size_t)(t + u) * ncell + c] = run; run += w[u]; }
+            }
+            for (; t < t1; ++t) { const int w = __ldcg(H + (size_t)t * ncell + c); H[(size_t)t * ncell + c] = run; run += w; }
         }
-        for (; t < t1; ++t) { const int v = __ldcg(H + (size_t)t * ncell + c); H[(size_t)t * ncell + c] = run; run += v; }
     }
-    // exclusive prefix of this CTA's 256 cell totals (threads of tile group 3 hold them), block sum published
-    __syncthreads();
-    if (q == 3) s_part[0][cl] = (c < ncell) ? sum + s_part[0][cl] + s_part[1][cl] + s_part[2][cl] : 0;   // = total of cell c
-    __syncthreads();
-    if (threadIdx.x < 256) {
+    // exclusive prefix of this CTA's CW cell totals (two warps), block sum published
+    if (threadIdx.x < CW) {
+        int tot = 0;
+        if (c < ncell)
+            for (int k = 0; k < TG; ++k) tot += s_part[k][threadIdx.x];
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int v = s_part[0][threadIdx.x];
-        int incl = v;
+        int incl = tot;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const int w = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += w; }
         if (lane == 31) s_wsum[warp] = incl;
-        __syncwarp();
-        s_part[1][threadIdx.x] = incl - v;                 // exclusive inside the warp
+        s_excl[threadIdx.x] = incl - tot;                   // exclusive inside the warp
+        s_h[threadIdx.x] = tot;
     }
     __syncthreads();
-    if (threadIdx.x < 256) {
+    if (threadIdx.x < CW) {
         const int warp = threadIdx.x >> 5;
         int add = 0;
         for (int k = 0; k < warp; ++k) add += s_wsum[k];
-        const int cc = blockIdx.x * 256 + threadIdx.x;
-        if (cc < ncell) cell_start[cc] = s_part[1][threadIdx.x] + add;      // local exclusive prefix; block prefix added below
-        if (threadIdx.x == 255) total[blockIdx.x] = s_part[1][255] + add + s_part[0][255];   // block sum (total[] re-used: nblk <= ncell)
+        if (c < ncell) cell_start[c] = s_excl[threadIdx.x] + add;          // local exclusive prefix; block prefix added below
+        if (threadIdx.x == CW - 1) total[blockIdx.x] = s_excl[CW - 1] + add + s_h[CW - 1];   // block sum (total[] re-used: nblk <= ncell)
     }
     __threadfence();
     __syncthreads();
@@ -314,8 +332,8 @@ eof_tile_colscan_kernel(int ncell, int ntile, int* __restrict__ H, int* __restri
         __threadfence();
         // block prefixes (<= 1024 blocks) by one warp-shuffle scan, then one coalesced pass that adds them
         const int nb = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int v = (int)threadIdx.x < nb ? __ldcg(total + threadIdx.x) : 0;
-        int incl = v;
+        const int bv = (int)threadIdx.x < nb ? __ldcg(total + threadIdx.x) : 0;
+        int incl = bv;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) { const int w = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += w; }
         __syncthreads();
@@ -328,10 +346,16 @@ eof_tile_colscan_kernel(int ncell, int ntile, int* __restrict__ H, int* __restri
             s_wsum[lane] = w;
         }
         __syncthreads();
-        s_h[threadIdx.x] = incl - v + (warp > 0 ? s_wsum[warp - 1] : 0);       // exclusive prefix of block threadIdx.x
+        s_h[threadIdx.x] = incl - bv + (warp > 0 ? s_wsum[warp - 1] : 0);      // exclusive prefix of block threadIdx.x
         __syncthreads();
-        for (int cc = threadIdx.x; cc < ncell; cc += 1024) cell_start[cc] = __ldcg(cell_start + cc) + s_h[cc >> 8];
-        if ((int)threadIdx.x == nb - 1) cell_start[ncell] = s_h[nb - 1] + v;    // particle count
+        for (int c0 = threadIdx.x; c0 < ncell; c0 += 8 * 1024) {       // eight loads in flight, then the stores (same array)
+            int w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int cc = c0 + u * 1024; w[u] = (cc < ncell) ? __ldcg(cell_start + cc) : 0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int cc = c0 + u * 1024; if (cc < ncell) cell_start[cc] = w[u] + s_h[cc / CW]; }
+        }
+        if ((int)threadIdx.x == nb - 1) cell_start[ncell] = s_h[nb - 1] + bv;   // particle count
         if (threadIdx.x == 0) *counter = 0u;
         if ((int)threadIdx.x < nb) total[threadIdx.x] = 0;                       // hist / total array left clear, as the other paths expect
     }
@@ -391,49 +415,62 @@ eof_tile_scatter_kernel(EofGeom g, int ncell, int64_t n, int tile, const double*
     for (int u = 0; u < 8; ++u)
         if (cell[u] >= 0) s_list[atomicAdd(&s_cnt[cell[u]], 1)] = (unsigned short)(u * 1024 + tid);
     __syncthreads();
-    // rank = members of the own (tile, cell) group with a smaller id; record; stores.  Two particles per pass: their loads
-    // (coordinates, cell_start, tile offset) are in flight together
+    // rank = members of the own (tile, cell) group with a smaller id; record; stores.  One particle per pass, the loads of
+    // the NEXT pass (coordinates, mass, cell_start, tile offset) issued before the arithmetic of this one: with two
+    // particles per pass and no look-ahead every pass exposed one DRAM latency (ncu: issue slots 46 % busy, 1 CTA of 32
+    // warps per SM).  The loop stays rolled: unrolled eight times it was 9800 instructions and slower (instruction cache).
+    struct Pre { double x, y, z, m; int g0, g1; };
+    auto cell_at = [&](int u) {                           // cell[] stays in registers: constant indices only
+        int c = cell[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) c = (u == k) ? cell[k] : c;
+        return c;
+    };
+    auto fetch = [&](int u, int c) {
+        Pre q;
+        const bool on = c >= 0;
+        const int64_t i = base + u * 1024 + tid;
+        q.x = on ? __ldg(x + i) : 1.0; q.y = on ? __ldg(y + i) : 0.0; q.z = on ? __ldg(z + i) : 0.0;
+        q.m = (on && mass) ? __ldg(mass + i) : 0.0;
+        q.g0 = on ? __ldg(cell_start + c) : 0;
+        q.g1 = on ? __ldg(H + (size_t)blockIdx.x * ncell + c) : 0;
+        return q;
+    };
+    Pre nxt = fetch(0, cell[0]);
 #pragma unroll 1
-    for (int u0 = 0; u0 < nu; u0 += 2) {
-        double px[2], py[2], pz[2], aux[2];
-        int gbase[2], cc[2];
-        int64_t idx[2];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int u = u0 + v;
-            cc[v] = (u < nu) ? cell[u] : -1;
-            idx[v] = base + u * 1024 + tid;
-            const bool on = cc[v] >= 0;
-            px[v] = on ? __ldg(x + idx[v]) : 1.0; py[v] = on ? __ldg(y + idx[v]) : 0.0; pz[v] = on ? __ldg(z + idx[v]) : 0.0;
-            aux[v] = (on && mass) ? __ldg(mass + idx[v]) : 0.0;
-            gbase[v] = on ? (__ldg(cell_start + cc[v]) + __ldg(H + (size_t)blockIdx.x * ncell + cc[v])) : 0;
+    for (int u = 0; u < nu; ++u) {
+        const Pre cur = nxt;
+        const int c = cell_at(u);
+        if (u + 1 < nu) nxt = fetch(u + 1, cell_at(u + 1));
+        if (c < 0) continue;
+        const int64_t idx = base + u * 1024 + tid;
+        const int lo = c ? s_cnt[c - 1] : 0, hi = s_cnt[c];
+        const int me = u * 1024 + tid;
+        // ids are < 2^13 in 16-bit slots: four per 64-bit shared-memory load, compared without a SIMD instruction (sm_100
+        // emulates __vcmpltu2 with ~6 logic ops): for x, me < 2^15 bit 15 of (me + 0x7fff - x) is set iff x < me, and
+        // neither half borrows from the other.
+        int rank = 0;
+        int k = lo;
+        for (; (k & 3) && k < hi; ++k) rank += (s_list[k] < me) ? 1 : 0;
+        const unsigned int K = (unsigned int)me * 0x00010001u + 0x7fff7fffu;
+        unsigned int acc = 0u;
+        for (; k + 3 < hi; k += 4) {
+            const uint2 w = *reinterpret_cast<const uint2*>(s_list + k);
+            acc += (((K - w.x) >> 15) & 0x00010001u) + (((K - w.y) >> 15) & 0x00010001u);
         }
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            if (cc[v] < 0) continue;
-            const int c = cc[v];
-            const int lo = c ? s_cnt[c - 1] : 0, hi = s_cnt[c];
-            const int me = (u0 + v) * 1024 + tid;
-            // ids are 16-bit: compare two per 32-bit word (__vcmpltu2), unaligned ends one by one
-            int rank = 0;
-            int k = lo;
-            if ((k & 1) && k < hi) { rank += (s_list[k] < me) ? 1 : 0; ++k; }
-            const unsigned int me2 = (unsigned int)me * 0x00010001u;
-            const unsigned int* w32 = reinterpret_cast<const unsigned int*>(s_list);
-            for (; k + 1 < hi; k += 2) rank += __popc(__vcmpltu2(w32[k >> 1], me2)) >> 4;
-            if (k < hi) rank += (s_list[k] < me) ? 1 : 0;
-            const int pos = gbase[v] + rank;
-            const double r = sqrt(px[v] * px[v] + py[v] * py[v] + 1.e-10);   // eof.py:531 / 1070
-            const EofBin b = bfe_eof_bin(g, r, pz[v]);                       // b.cell == c
-            double c1, s1;
-            bfe_cossin_phi(px[v], py[v], c1, s1);
-            const unsigned long long cp = ((unsigned long long)(unsigned int)c << 32) | (unsigned long long)(unsigned int)idx[v];
-            char* dst = reinterpret_cast<char*>(rec + pos);                  // two full-sector stores per record
-            bfe_st256(dst, b.c00, b.c10, b.c01, b.c11);
-            bfe_st256(dst + 32, c1, s1, aux[v], __longlong_as_double((long long)cp));
-            inv[idx[v]] = pos;                                               // original index -> sorted slot (coalesced)
-            r_orig[idx[v]] = r;
-        }
+        rank += (int)((acc & 0xffffu) + (acc >> 16));
+        for (; k < hi; ++k) rank += (s_list[k] < me) ? 1 : 0;
+        const int pos = cur.g0 + cur.g1 + rank;
+        const double r = sqrt(cur.x * cur.x + cur.y * cur.y + 1.e-10);   // eof.py:531 / 1070
+        const EofBin b = bfe_eof_bin(g, r, cur.z);                       // b.cell == c
+        double c1, s1;
+        bfe_cossin_phi(cur.x, cur.y, c1, s1);
+        const unsigned long long cp = ((unsigned long long)(unsigned int)c << 32) | (unsigned long long)(unsigned int)idx;
+        char* dst = reinterpret_cast<char*>(rec + pos);                  // two full-sector stores per record
+        bfe_st256(dst, b.c00, b.c10, b.c01, b.c11);
+        bfe_st256(dst + 32, c1, s1, cur.m, __longlong_as_double((long long)cp));
+        inv[idx] = pos;                                                  // original index -> sorted slot (coalesced)
+        r_orig[idx] = r;
     }
 }
 
@@ -993,6 +1030,8 @@ eof_force_sorted_mma_kernel(EofGeom g, const double* __restrict__ G, int gstride
     }
 }
 
+// (Two consecutive particles per thread with 16-byte vector loads / stores of inv, R and the outputs -- half the LSU
+// instructions -- measured SLOWER, 25.1 vs 23.4 us per 10^6: the random slot reads need the thread count, not fewer instructions.)
 __global__ void __launch_bounds__(256)
 eof_force_gather_kernel(int64_t n, const int* __restrict__ inv, const double* __restrict__ r_orig,
                         const double2* __restrict__ tmp, double* __restrict__ p0, double* __restrict__ p,
@@ -1090,7 +1129,7 @@ extern "C" int bfe_eof_prepare(bfe_eof* h, int64_t n, const double* x, const dou
                                 z, ws.H, ws.inv));
             bfe_kt_end(kt, stream);
             kt = bfe_kt_begin("eof_tile_colscan_kernel", stream);
-            BFE_CUDA(bfe_launch(eof_tile_colscan_kernel, dim3((ncell + 255) / 256), dim3(1024), 0, stream, nullptr, 0, ncell,
+            BFE_CUDA(bfe_launch(eof_tile_colscan_kernel, dim3((ncell + BFE_COLSCAN_CW - 1) / BFE_COLSCAN_CW), dim3(1024), 0, stream, nullptr, 0, ncell,
                                 ntile, ws.H, ws.hist, ws.cell_start, h->counter));
             bfe_kt_end(kt, stream);
             BFE_LAUNCH_CHECK("eof_tile_hist_kernel");
