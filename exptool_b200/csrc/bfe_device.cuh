@@ -741,6 +741,108 @@ __device__ __forceinline__ EofField bfe_eof_eval_base(const EofGeom& g, const do
     return f;
 }
 
+// ---------------------------------------------------------------------------
+// Per-INTERVAL polynomial blocks A4 (FP64; the default per-lane evaluation since round 2).
+// The per-lane field kernels are bound by the register-file WRITE port: every FP64 result takes two write cycles of its
+// scheduler and every 32 loaded bytes per lane one, and the two add up (profiles/probes/fp64_mix_probe.cu: 2 LDG.256 per
+// 32 FP64 instructions lower the FP64 rate from 1.76 to 1.39 per clk, the 64 / 80 the model gives; ncu: the fused kernel's
+// time is the sum of its load phase and its FP64 phase, whatever the occupancy).  So the lever is the instruction count.
+// On the interval i the radial interpolation of spheresl.py:153-155 is linear in x2:
+//     potential part   P0 (x1 a_i + x2 a_{i+1})                         = P0 (a_i + x2 S1),       S1 = a_{i+1} - a_i
+//     derivative part  fac ((x2 - 1/2) u_{j-1} - 2 x2 u_j + (x2 + 1/2) u_{j+1}) = fac (D1 + x2 D2),   u_k = p0[k] a_k, j = max(i, 1)
+//     D1 = (u_{j+1} - u_{j-1}) / 2,  D2 = u_{j-1} - 2 u_j + u_{j+1}
+// with P0 and fac common to all (l, m): they multiply the five sums once at the end.  The block of interval i holds, in the
+// evaluation order (m outer, l inner), {a_i, S1, D1, D2} for the cosine row of the m = 0 entries (32 B each) and for the
+// cosine and sine rows of the others (64 B each: {a.x, a.y, S1.x, S1.y}, {D1.x, D1.y, D2.x, D2.y}), every value already
+// multiplied by the factorial factor of (l, m).  Per (l, m > 0): 4 FMAs of interpolation instead of 12 and no factor
+// multiplies; the azimuthal factor m of potp is applied once per column.  1568 B per interval at lmax = 6 (A3: 1344 B).
+// ---------------------------------------------------------------------------
+#define BFE_A4_BYTES(lmax) (32 * ((lmax) + 1) + 64 * ((((lmax) + 1) * ((lmax) + 2)) / 2 - ((lmax) + 1)))
+
+template <int LCAP>
+__device__ __forceinline__ SlField bfe_sl_eval_poly(const SlGeom& g, const void* __restrict__ A4,
+                                                    const double* __restrict__ p0tab, const SlBin& b, double costh,
+                                                    double c1, double s1, bool trig_index_l) {
+    const double2* blk = reinterpret_cast<const double2*>(static_cast<const char*>(A4) + (size_t)b.i * BFE_A4_BYTES(LCAP));
+    const double P0 = b.x1 * __ldg(p0tab + b.i) + b.x2 * __ldg(p0tab + b.i + 1);
+    const double x2 = b.x2;
+
+    const double x = costh;
+    const double somx2 = sqrt(BFE_MUL(BFE_SUB(1.0, x), BFE_ADD(1.0, x)));
+    double xd = x;
+    if (1.0 - fabs(xd) < 1.0e-8) xd = (xd > 0.0) ? (1.0 - 1.0e-8) : -(1.0 - 1.0e-8);
+    const double dsom = BFE_DIV(1.0, BFE_SUB(BFE_MUL(xd, xd), 1.0));
+
+    double q0 = 0.0, q1 = 0.0, qr = 0.0, qt = 0.0, qp = 0.0;
+    double pmm = 1.0, fact = 1.0;
+    double cm = 1.0, sm = 0.0;
+    int off2 = 2 * (LCAP + 1);                     // double2 index of the first m > 0 entry
+#pragma unroll
+    for (int m = 0; m <= LCAP; ++m) {
+        if (m > 0) {
+            pmm = BFE_MUL(pmm, BFE_MUL(-fact, somx2));
+            fact += 2.0;
+            double cn = cm * c1 - sm * s1, sn = sm * c1 + cm * s1;
+            cm = cn; sm = sn;
+        }
+        double pl2 = 0.0, pl1 = pmm;
+        double cl = cm, sl = sm;
+        double colp = 0.0;
+#pragma unroll
+        for (int l = m; l <= LCAP; ++l) {
+            double P, dP;
+            if (l == m) {
+                P = pmm;
+                dP = (l == 0) ? 0.0 : BFE_MUL(BFE_MUL(BFE_MUL(dsom, xd), (double)l), P);
+            } else {
+                if (l == m + 1) P = BFE_MUL(BFE_MUL(x, 2.0 * m + 1.0), pl1);
+                else P = bfe_div_int(BFE_SUB(BFE_MUL(BFE_MUL(x, (double)(2 * l - 1)), pl1),
+                                             BFE_MUL((double)(l + m - 1), pl2)), l - m);
+                dP = BFE_MUL(dsom, BFE_SUB(BFE_MUL(BFE_MUL(xd, (double)l), P), BFE_MUL((double)(l + m), pl1)));
+                pl2 = pl1; pl1 = P;
+                double cn = cl * c1 - sl * s1, sn = sl * c1 + cl * s1;
+                cl = cn; sl = sn;
+            }
+            if (m == 0) {
+                double2 e0, e1;                                        // {a, S1}, {D1, D2}
+                bfe_ldg256(blk + 2 * l, e0, e1);
+                const double spc = e0.x + x2 * e0.y;
+                const double sdc = e1.x + x2 * e1.y;
+                if (l == 0) {
+                    q0 = spc;
+                    qr += sdc;
+                } else {
+                    q1 += P * spc;
+                    qr += P * sdc;
+                    qt += dP * spc;
+                }
+            } else {
+                double2 a, sd, d1, d2;                                 // {a.x, a.y}, {S1.x, S1.y}, {D1.x, D1.y}, {D2.x, D2.y}
+                bfe_ldg256(blk + off2 + 4 * (l - m), a, sd);
+                bfe_ldg256(blk + off2 + 4 * (l - m) + 2, d1, d2);
+                const double spc = a.x + x2 * sd.x, sps = a.y + x2 * sd.y;
+                const double sdc = d1.x + x2 * d2.x, sds = d1.y + x2 * d2.y;
+                const double ct = trig_index_l ? cl : cm;
+                const double stt = trig_index_l ? sl : sm;
+                const double Ap = spc * ct + sps * stt;
+                const double Ad = sdc * ct + sds * stt;
+                const double Bp = sps * ct - spc * stt;
+                q1 += P * Ap;
+                qr += P * Ad;
+                qt += dP * Ap;
+                colp += P * Bp;
+            }
+        }
+        if (m > 0) {
+            qp += (double)m * colp;
+            off2 += 4 * (LCAP - m + 1);
+        }
+    }
+    SlField f;
+    f.pot0 = P0 * q0; f.pot1 = P0 * q1; f.potr = b.fac * qr; f.pott = P0 * qt; f.potp = P0 * qp;
+    return f;
+}
+
 // valid only when g.lmax == LCAP (LCAP = 6: 84 double2 = 1344 B per interval; LCAP = 4: 45 padded to 46)
 template <int LCAP, typename FacT, class LD = LdGlobal256>
 __device__ __forceinline__ SlField bfe_sl_eval_base(const SlGeom& g, const double2* base,
@@ -748,14 +850,12 @@ __device__ __forceinline__ SlField bfe_sl_eval_base(const SlGeom& g, const doubl
                                                     const SlBin& b, double costh, double c1, double s1, bool trig_index_l);
 
 template <int LCAP, typename FacT>
-__device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const double2* __restrict__ A3,
+__device__ __forceinline__ SlField bfe_sl_eval_blk(const SlGeom& g, const void* __restrict__ A4,
                                                    const double* __restrict__ p0tab, const FacT& fac,
                                                    const SlBin& b, double costh, double c1, double s1,
                                                    bool trig_index_l) {
-    constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
-    const int j = (b.i == 0) ? 1 : b.i;
-    return bfe_sl_eval_base<LCAP, FacT, LdGlobal256>(g, A3 + (size_t)j * BFE_A3_STRIDE(NPAIR), p0tab, fac, b, costh, c1, s1,
-                                                     trig_index_l);
+    (void)fac;                                   // the factorial factors are folded into the A4 blocks
+    return bfe_sl_eval_poly<LCAP>(g, A4, p0tab, b, costh, c1, s1, trig_index_l);
 }
 
 // base = the block of radial index j = max(b.i, 1): A3 + j * BFE_A3_STRIDE(NPAIR), or its staged copy
@@ -1007,35 +1107,61 @@ __device__ __forceinline__ SlField bfe_sl_eval_blk32(const SlGeom& g, const floa
 // potential.py:475-497 (Cartesian) / 425-440 (cylindrical): disc + halo field components -> the 8 outputs.
 // The ten quotients by r2, r2^2, r3, r3^3 are formed from two reciprocals (a few ulp from the reference's
 // separate divisions: these are plain products, nothing downstream amplifies them).
+// The disc half and the halo half of the eight outputs depend on one expansion each, so the key-ordered point path can
+// evaluate them in two kernels (bfe_orbit_sort.cu); bfe_cart_combine is the two halves together -- same expressions.
+struct CartHalf { double fx, fy, fz, p; };
+
 template <bool CYL>
-__device__ __forceinline__ CartForce bfe_cart_combine(const EofField& d, const SlField& h, double x, double y, double z,
-                                                      double r2, double r3, double xi0) {
+__device__ __forceinline__ CartHalf bfe_cart_disc(const EofField& d, double x, double y, double r2, double r3, double xi0) {
     double diskfr = d.fr, diskfp = d.fp, diskfz = d.fz, diskp = d.p + d.p0;
+    if (r3 < xi0) diskfp = 0.0;                              // 483-485 (min(xi) = xi[0])
+    CartHalf o;
+    if (CYL) {
+        o.fx = diskfr;
+        o.fy = diskfp;
+        o.fz = diskfz;
+        o.p = -1.0 * diskp;                                  // 440
+        return o;
+    }
+    const double ir2 = 1.0 / r2;
+    const double ir2sq = ir2 * ir2;
+    o.fx = diskfr * (x * ir2) - diskfp * (y * ir2sq);
+    o.fy = diskfr * (y * ir2) + diskfp * (x * ir2sq);
+    o.fz = diskfz;
+    o.p = diskp;
+    return o;
+}
+
+template <bool CYL>
+__device__ __forceinline__ CartHalf bfe_cart_halo(const SlField& h, double x, double y, double z, double r2, double r3,
+                                                  double xi0) {
     double halofr = h.potr, haloft = h.pott, halofp = h.potp;
-    if (r3 < xi0) { halofp = 0.0; diskfp = 0.0; }            // 483-485 (min(xi) = xi[0])
-    CartForce o;
+    if (r3 < xi0) halofp = 0.0;                              // 483-485
+    CartHalf o;
     const double ir3 = 1.0 / r3;
     if (CYL) {
-        o.fxd = diskfr;
-        o.fxh = -1.0 * (r2 * halofr + z * haloft) * ir3;      // 433
-        o.fyd = diskfp;
-        o.fyh = -1.0 * halofp;
-        o.fzd = diskfz;
-        o.fzh = -1.0 * (z * halofr - r2 * haloft) * ir3;      // 435
-        o.pd = -1.0 * diskp;                                  // 440
-        o.ph = h.pot1 + h.pot0;
+        o.fx = -1.0 * (r2 * halofr + z * haloft) * ir3;      // 433
+        o.fy = -1.0 * halofp;
+        o.fz = -1.0 * (z * halofr - r2 * haloft) * ir3;      // 435
+        o.p = h.pot1 + h.pot0;
         return o;
     }
     const double ir2 = 1.0 / r2;
     const double ir2sq = ir2 * ir2, ir3cu = ir3 * ir3 * ir3;
-    o.fxd = diskfr * (x * ir2) - diskfp * (y * ir2sq);
-    o.fxh = -1.0 * (halofr * (x * ir3) - haloft * (x * z * ir3cu)) + halofp * (y * ir2sq);
-    o.fyd = diskfr * (y * ir2) + diskfp * (x * ir2sq);
-    o.fyh = -1.0 * (halofr * (y * ir3) - haloft * (y * z * ir3cu)) - halofp * (x * ir2sq);
-    o.fzd = diskfz;
-    o.fzh = -1.0 * (halofr * (z * ir3) + haloft * (r2 * r2 * ir3cu));
-    o.pd = diskp;
-    o.ph = h.pot1 + h.pot0;
+    o.fx = -1.0 * (halofr * (x * ir3) - haloft * (x * z * ir3cu)) + halofp * (y * ir2sq);
+    o.fy = -1.0 * (halofr * (y * ir3) - haloft * (y * z * ir3cu)) - halofp * (x * ir2sq);
+    o.fz = -1.0 * (halofr * (z * ir3) + haloft * (r2 * r2 * ir3cu));
+    o.p = h.pot1 + h.pot0;
+    return o;
+}
+
+template <bool CYL>
+__device__ __forceinline__ CartForce bfe_cart_combine(const EofField& d, const SlField& h, double x, double y, double z,
+                                                      double r2, double r3, double xi0) {
+    const CartHalf a = bfe_cart_disc<CYL>(d, x, y, r2, r3, xi0);
+    const CartHalf b = bfe_cart_halo<CYL>(h, x, y, z, r2, r3, xi0);
+    CartForce o;
+    o.fxd = a.fx; o.fxh = b.fx; o.fyd = a.fy; o.fyh = b.fy; o.fzd = a.fz; o.fzh = b.fz; o.pd = a.p; o.ph = b.p;
     return o;
 }
 
@@ -1112,11 +1238,11 @@ __device__ __forceinline__ CartForce bfe_field_cart_blk(const EofGeom& ge, const
         const SlField h = bfe_sl_eval_blk32<LCAP>(gs, static_cast<const float*>(A3), p0tab, fac, p.sb, p.costh, p.cr, p.sr, true);
         return bfe_cart_combine<CYL>(d, h, x, y, z, p.r2, p.r3, gs.xi0);
     } else {
-        constexpr int NPAIR = (LCAP + 1) * (LCAP + 2) / 2;
-        const int j = (p.sb.i == 0) ? 1 : p.sb.i;
-        return bfe_field_epilogue<MCAP, LCAP, CYL, FacT, LdGlobal256>(
-            ge, gs, static_cast<const double2*>(G4) + (size_t)p.eb.cell * (size_t)(12 * (ge.mmax + 1)),
-            static_cast<const double2*>(A3) + (size_t)j * BFE_A3_STRIDE(NPAIR), p0tab, fac, p);
+        // FP64: EOF block of the cell (G4), SL polynomial block of the interval (A4)
+        const EofField d = bfe_eof_eval_base<MCAP, LdGlobal256>(
+            ge, static_cast<const double2*>(G4) + (size_t)p.eb.cell * (size_t)(12 * (ge.mmax + 1)), p.eb, p.cr, p.sr);
+        const SlField h = bfe_sl_eval_poly<LCAP>(gs, A3, p0tab, p.sb, p.costh, p.cr, p.sr, true);
+        return bfe_cart_combine<CYL>(d, h, x, y, z, p.r2, p.r3, gs.xi0);
     }
 }
 

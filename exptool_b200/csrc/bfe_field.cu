@@ -211,10 +211,10 @@ static int field_force_impl(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x,
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
         const bool f32 = bfe_use_fp32(he);
         int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
-        if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
+        if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a4(hs, stream);
         if (rc != BFE_OK) return rc;
         const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
-        const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+        const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a4;      // FP64: the polynomial blocks
         const SlFacP facp = bfe_sl_facp(hs);
 #define FIELD_BLK(L, C, F) field_cart_blk_kernel<6, L, C, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, \
                                                                                     facp, n, x, y, z, crot, srot, out8)
@@ -279,10 +279,10 @@ static int leapfrog_impl(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, 
     if (g_bfe_blk_eval && he->g.mmax <= 6 && (hs->g.lmax == 4 || hs->g.lmax == 6)) {
         const bool f32 = bfe_use_fp32(he);
         int rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
-        if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
+        if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a4(hs, stream);
         if (rc != BFE_OK) return rc;
         const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
-        const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+        const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a4;      // FP64: the polynomial blocks
         const SlFacP facp = bfe_sl_facp(hs);
 #define LEAP_BLK(L, F) leapfrog_blk_kernel<6, L, F><<<grid, 128, 0, stream>>>(he->g, G4, hs->g, A3, hs->xi, hs->p0, facp, norbit, \
                                                                            nint, dt, dt_orbit, rotfreq, state6, traj, traj_stride, apse, ap_max, nsteps_out)

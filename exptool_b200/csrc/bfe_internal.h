@@ -86,6 +86,8 @@ struct bfe_sl {
     int a3_valid;
     float* a3f;          // FP32 copy of A3 for the table_fp32 mode (allocated on first use)
     int a3f_valid;
+    double* a4;          // FP64 per-interval polynomial blocks of the per-lane evaluation (bfe_sl_eval_poly; allocated on first use)
+    int a4_valid;
     double* partial;     // [max_ctas][nrow*nmax]
     unsigned int* counter;
     int max_ctas;
@@ -123,6 +125,7 @@ inline bool bfe_use_fp32(const bfe_eof* h) { return (h->table_fp32 >= 0 ? h->tab
 inline bool bfe_use_fp32(const bfe_sl* h) { return (h->table_fp32 >= 0 ? h->table_fp32 : g_bfe_table_fp32) != 0; }
 int bfe_eof_ensure_g4f(bfe_eof* h, cudaStream_t stream);
 int bfe_sl_ensure_a3f(bfe_sl* h, cudaStream_t stream);
+int bfe_sl_ensure_a4(bfe_sl* h, cudaStream_t stream);        // build A4 from a_con if stale
 extern int g_bfe_blk_eval;                                  // option "blk_eval": per-lane block evaluation with 256-bit loads
 extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0
 

@@ -228,14 +228,23 @@ field_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void*
             if (pos < n) {
                 const CartForce f = bfe_field_cart_blk<MCAP, LCAP, CYL, F32>(ge, G4, gs, A3, xi, p0tab, fac, px, py, pz, crot, srot);
                 char* d = reinterpret_cast<char*>(slot8 + 8 * (size_t)pos);
-                bfe_st256(d, f.fxd, f.fxh, f.fyd, f.fyh);
-                bfe_st256(d + 32, f.fzd, f.fzh, f.pd, f.ph);
+                bfe_st256(d, f.fxd, f.fyd, f.fzd, f.pd);           // slot = {disc: fx, fy, fz, p | halo: fx, fy, fz, p}
+                bfe_st256(d + 32, f.fxh, f.fyh, f.fzh, f.ph);
             }
             pos = npos; px = nx; py = ny; pz = nz;
         }
     }
 }
 
+// ---------------------------------------------------------------------------
+// Tried and removed (round 2): the same evaluation as TWO kernels, the disc half of a slot from the EOF blocks (80 registers,
+// 6 CTAs per SM) and the halo half from the SL blocks (128 registers, 4 CTAs per SM), to get more warps per scheduler than the
+// fused kernel's three.  No gain: 10^6 disc points 214 us against 212 fused; ncu (profiles/r02_ncu_full_field_half.csv,
+// _fused.csv; 2^20 points): EOF half 70 us (long-scoreboard 11.6 warps per issue, l1tex 62 %, FP64 pipe 37 %) + SL half
+// 97 us (FP64 pipe 64.5 %, math-pipe throttle 1.1) = 167 us against 161 us fused (FP64 pipe 50.5 %): the EOF phase is bound
+// by its 42 x 8 L1 data-pipe wavefronts per point and the SL phase by FP64 issue, the fused kernel's time is already the sum
+// of the two, and occupancy buys neither anything.  (Results were also not bit-identical to the caller-order kernel.)
+// ---------------------------------------------------------------------------
 // ---------------------------------------------------------------------------
 // Shared-memory staging of the table blocks of a tile (FP64 tables): BASELINE north_star (b), "tables staged in shared
 // memory (TMA bulk copies where the table fits)".  The tables do not fit, the blocks of a TILE do: the 128 points of a tile
@@ -351,8 +360,8 @@ field_stage_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const 
             const CartForce f = bfe_stage_eval<MCAP, LCAP, CYL>(ge, G4, gs, A3, p0tab, fac, p, on, ctx);
             if (on) {
                 char* d = reinterpret_cast<char*>(slot8 + 8 * (size_t)pos);
-                bfe_st256(d, f.fxd, f.fxh, f.fyd, f.fyh);
-                bfe_st256(d + 32, f.fzd, f.fzh, f.pd, f.ph);
+                bfe_st256(d, f.fxd, f.fyd, f.fzd, f.pd);           // slot = {disc: fx, fy, fz, p | halo: fx, fy, fz, p}
+                bfe_st256(d + 32, f.fxh, f.fyh, f.fzh, f.ph);
             }
             pos = npos; px = nx; py = ny; pz = nz;
         }
@@ -369,8 +378,9 @@ field_gather_kernel(int64_t n, int64_t ntot, const int* __restrict__ inv, const 
         double a0, a1, a2, a3, b0, b1, b2, b3;
         bfe_ld256_nc(s, a0, a1, a2, a3);
         bfe_ld256_nc(s + 32, b0, b1, b2, b3);
-        out8[i] = a0; out8[ntot + i] = a1; out8[2 * ntot + i] = a2; out8[3 * ntot + i] = a3;
-        out8[4 * ntot + i] = b0; out8[5 * ntot + i] = b1; out8[6 * ntot + i] = b2; out8[7 * ntot + i] = b3;
+        // slot = {disc: fx, fy, fz, p | halo: fx, fy, fz, p}; output rows fxd, fxh, fyd, fyh, fzd, fzh, pd, ph
+        out8[i] = a0; out8[2 * ntot + i] = a1; out8[4 * ntot + i] = a2; out8[6 * ntot + i] = a3;
+        out8[ntot + i] = b0; out8[3 * ntot + i] = b1; out8[5 * ntot + i] = b2; out8[7 * ntot + i] = b3;
     }
 }
 
@@ -710,10 +720,12 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
     if (rc != BFE_OK) return rc;
     const bool f32 = bfe_use_fp32(he);
     rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
-    if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
+    // FP64: the per-lane kernels read the per-interval polynomial blocks A4, the TMA-staged ones the three-node blocks A3
+    const bool staged = !f32 && g_bfe_stage_eval && he->g.mmax <= 6;
+    if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : (staged ? bfe_sl_ensure_a3(hs, stream) : bfe_sl_ensure_a4(hs, stream));
     if (rc != BFE_OK) return rc;
     const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
-    const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+    const void* A3 = f32 ? (const void*)hs->a3f : (staged ? (const void*)hs->a3 : (const void*)hs->a4);
     const SlFacP facp = bfe_sl_facp(hs);
     const int kt = bfe_kt_begin("field_sorted_pass", stream);
     cudaStream_t aux = fp->aux;
@@ -741,7 +753,7 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
         if (c + 1 < nchunk) { rc = sort_chunk(c + 1); if (rc != BFE_OK) return rc; }
         BFE_CUDA(cudaStreamWaitEvent(stream, fp->ev_k[b], 0));
         const int geval = grid_cap(m, 128, he->num_sms * BFE_PERM_MINB);
-        if (!f32 && g_bfe_stage_eval && he->g.mmax <= 6) {
+        if (staged) {
 #define FIELD_STAGE(L, C)                                                                                                        \
     do {                                                                                                                          \
         cudaError_t _e = bfe_launch((field_stage_kernel<6, L, C>), dim3(geval), dim3(128), (size_t)BFE_STAGE_SMEM, stream, nullptr, 0, \
@@ -792,10 +804,12 @@ int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, d
     OrbRec* rec = (OrbRec*)he->orbit_rec;
     const bool f32 = bfe_use_fp32(he);
     rc = f32 ? bfe_eof_ensure_g4f(he, stream) : bfe_eof_ensure_g4(he, stream);
-    if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : bfe_sl_ensure_a3(hs, stream);
+    // FP64: the per-lane kernels read the per-interval polynomial blocks A4, the TMA-staged ones the three-node blocks A3
+    const bool staged = !f32 && g_bfe_stage_eval && he->g.mmax <= 6;
+    if (rc == BFE_OK) rc = f32 ? bfe_sl_ensure_a3f(hs, stream) : (staged ? bfe_sl_ensure_a3(hs, stream) : bfe_sl_ensure_a4(hs, stream));
     if (rc != BFE_OK) return rc;
     const void* G4 = f32 ? (const void*)he->g4f : (const void*)he->g4;
-    const void* A3 = f32 ? (const void*)hs->a3f : (const void*)hs->a3;
+    const void* A3 = f32 ? (const void*)hs->a3f : (staged ? (const void*)hs->a3 : (const void*)hs->a4);
     const int g256 = grid_cap(norbit, 256, he->num_sms * 8);
     const int glf = grid_cap(norbit, 128, he->num_sms * BFE_PERM_MINB);
     const int K = g_bfe_orbit_resort > 0 ? g_bfe_orbit_resort : 4;
@@ -825,7 +839,7 @@ int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, d
         if (_e != cudaSuccess) { bfe_set_cuda_error(_e, "leapfrog_stage_kernel"); return BFE_ERR_CUDA; }                          \
         bfe_count_launch(1);                                                                                                      \
     } while (0)
-        if (!f32 && g_bfe_stage_eval && he->g.mmax <= 6) { if (hs->g.lmax == 4) LEAP_STAGE(4); else LEAP_STAGE(6); }
+        if (staged) { if (hs->g.lmax == 4) LEAP_STAGE(4); else LEAP_STAGE(6); }
         else if (hs->g.lmax == 4) { if (f32) LEAP_PERM(4, true); else LEAP_PERM(4, false); }
         else                      { if (f32) LEAP_PERM(6, true); else LEAP_PERM(6, false); }
 #undef LEAP_STAGE

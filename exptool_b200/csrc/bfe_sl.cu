@@ -226,6 +226,41 @@ __global__ void sl_expand_a3f_kernel(SlGeom g, const double2* __restrict__ A, in
     }
 }
 
+// FP64 polynomial blocks A4 of the per-lane evaluation (layout and rationale at bfe_sl_eval_poly): thread per
+// (interval i, entry (m, l) in evaluation order)
+__global__ void sl_expand_a4_kernel(SlGeom g, const double2* __restrict__ A, int qstride, const double* __restrict__ p0,
+                                    const double* __restrict__ fac, double* __restrict__ A4) {
+    const int npair = qstride;
+    const int np0 = g.lmax + 1;
+    const size_t blk_doubles = (size_t)(4 * np0 + 8 * (npair - np0));
+    const int64_t total = (int64_t)(g.numr - 1) * npair;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / npair), qm = (int)(t - (int64_t)i * npair);
+        int m = 0, off = 0;
+        while (qm >= off + (g.lmax - m + 1)) { off += g.lmax - m + 1; ++m; }
+        const int l = m + (qm - off);
+        const int q = (l * (l + 1)) / 2 + m;
+        const int j = (i == 0) ? 1 : i;
+        const double fl = fac[l * (g.lmax + 1) + m];
+        const double2 alo = A[(size_t)i * qstride + q], ahi = A[(size_t)(i + 1) * qstride + q];
+        const double2 am = A[(size_t)(j - 1) * qstride + q], a0 = A[(size_t)j * qstride + q], ap = A[(size_t)(j + 1) * qstride + q];
+        const double pm = p0[j - 1], pc = p0[j], pp = p0[j + 1];
+        const double umx = pm * am.x, u0x = pc * a0.x, upx = pp * ap.x;
+        const double umy = pm * am.y, u0y = pc * a0.y, upy = pp * ap.y;
+        double* o = A4 + (size_t)i * blk_doubles;
+        if (m == 0) {
+            o += 4 * l;
+            o[0] = fl * alo.x; o[1] = fl * (ahi.x - alo.x);
+            o[2] = fl * (0.5 * (upx - umx)); o[3] = fl * ((umx - u0x) + (upx - u0x));
+        } else {
+            o += 4 * np0 + 8 * (qm - np0);
+            o[0] = fl * alo.x; o[1] = fl * alo.y; o[2] = fl * (ahi.x - alo.x); o[3] = fl * (ahi.y - alo.y);
+            o[4] = fl * (0.5 * (upx - umx)); o[5] = fl * (0.5 * (upy - umy));
+            o[6] = fl * ((umx - u0x) + (upx - u0x)); o[7] = fl * ((umy - u0y) + (upy - u0y));
+        }
+    }
+}
+
 // per-lane block evaluation with 256-bit loads (bfe_sl_eval_blk); valid for g.lmax == LCAP
 template <int LCAP, bool F32>
 __global__ void __launch_bounds__(128)
@@ -245,14 +280,14 @@ sl_force_blk_kernel(SlGeom g, const void* __restrict__ A3, const double* __restr
         SlBin b = bfe_sl_bin(g, xi, r);
         SlField f;
         if constexpr (F32) f = bfe_sl_eval_blk32<LCAP>(g, static_cast<const float*>(A3), p0tab, fac, b, costh, c1, s1, false);
-        else               f = bfe_sl_eval_blk<LCAP>(g, static_cast<const double2*>(A3), p0tab, fac, b, costh, c1, s1, false);
+        else               f = bfe_sl_eval_blk<LCAP>(g, A3, p0tab, fac, b, costh, c1, s1, false);
         pot0[i] = f.pot0; pot1[i] = f.pot1; potr[i] = f.potr; pott[i] = f.pott; potp[i] = f.potp; rr[i] = rxy;
     }
 }
 
 template <int LCAP>
 __global__ void __launch_bounds__(128)
-sl_points_blk_kernel(SlGeom g, const double2* __restrict__ A3, const double* __restrict__ xi,
+sl_points_blk_kernel(SlGeom g, const void* __restrict__ A3, const double* __restrict__ xi,
                      const double* __restrict__ p0tab, const double* __restrict__ fac, int64_t n,
                      const double* __restrict__ r, const double* __restrict__ costh, const double* __restrict__ phi,
                      int trig_index_l,
@@ -493,6 +528,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
     BFE_CUDA(cudaMalloc(&h->a3, nr * (size_t)BFE_A3_STRIDE(h->kpad) * 2 * sizeof(double)));
     h->a3_valid = 0;
     h->a3f = nullptr; h->a3f_valid = 0;
+    h->a4 = nullptr; h->a4_valid = 0;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)h->max_ctas * g.nrow * g.nmax * sizeof(double)));
     BFE_CUDA(cudaMalloc(&h->counter, 4 * sizeof(unsigned int)));
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 4 * sizeof(unsigned int), stream));
@@ -525,7 +561,7 @@ extern "C" int bfe_sl_create(const bfe_sl_params* p, const double* evtable, cons
 extern "C" void bfe_sl_destroy(bfe_sl* h) {
     if (!h) return;
     cudaFree(h->e_node); cudaFree(h->xi); cudaFree(h->p0); cudaFree(h->d0); cudaFree(h->fac);
-    cudaFree(h->ev); if (h->ad_con) cudaFree(h->ad_con); if (h->a3f) cudaFree(h->a3f);
+    cudaFree(h->ev); if (h->ad_con) cudaFree(h->ad_con); if (h->a3f) cudaFree(h->a3f); if (h->a4) cudaFree(h->a4);
     cudaFree(h->a_con); cudaFree(h->a3); cudaFree(h->partial); cudaFree(h->counter);
     if (h->sort_ws) cudaFree(h->sort_ws);
     bfe_host_pipe_destroy(h->host_pipe);
@@ -559,6 +595,7 @@ extern "C" int bfe_sl_contract(bfe_sl* h, const double* expcoef, int l1, int l2,
     h->contracted = 1;
     h->a3_valid = 0;
     h->a3f_valid = 0;
+    h->a4_valid = 0;
     return BFE_OK;
 }
 
@@ -568,6 +605,16 @@ int bfe_sl_ensure_a3f(bfe_sl* h, cudaStream_t stream) {
     sl_expand_a3f_kernel<<<h->num_sms * 4, 256, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->p0, h->a3f);
     BFE_LAUNCH_CHECK("sl_expand_a3f_kernel");
     h->a3f_valid = 1;
+    return BFE_OK;
+}
+
+int bfe_sl_ensure_a4(bfe_sl* h, cudaStream_t stream) {
+    if (h->a4_valid) return BFE_OK;
+    if (!h->a4) BFE_CUDA(cudaMalloc(&h->a4, (size_t)h->g.numr * BFE_A4_BYTES(h->g.lmax)));
+    sl_expand_a4_kernel<<<h->num_sms * 4, 256, 0, stream>>>(h->g, reinterpret_cast<const double2*>(h->a_con), h->kpad, h->p0,
+                                                           h->fac, h->a4);
+    BFE_LAUNCH_CHECK("sl_expand_a4_kernel");
+    h->a4_valid = 1;
     return BFE_OK;
 }
 
@@ -598,9 +645,9 @@ extern "C" int bfe_sl_force_contracted(bfe_sl* h, int64_t n, const double* x, co
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
     if (g_bfe_blk_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
         const bool f32 = bfe_use_fp32(h);
-        int rc = f32 ? bfe_sl_ensure_a3f(h, stream) : bfe_sl_ensure_a3(h, stream);
+        int rc = f32 ? bfe_sl_ensure_a3f(h, stream) : bfe_sl_ensure_a4(h, stream);
         if (rc != BFE_OK) return rc;
-        const void* A3 = f32 ? (const void*)h->a3f : (const void*)h->a3;
+        const void* A3 = f32 ? (const void*)h->a3f : (const void*)h->a4;      // FP64: the polynomial blocks
 #define SL_BLK(L, F) sl_force_blk_kernel<L, F><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, x, y, z, pot0, pot1, potr, pott, potp, rr)
         if (h->g.lmax == 4) { if (f32) SL_BLK(4, true); else SL_BLK(4, false); }
         else                { if (f32) SL_BLK(6, true); else SL_BLK(6, false); }
@@ -648,9 +695,9 @@ extern "C" int bfe_sl_force_eval_points(bfe_sl* h, int64_t n, const double* r, c
     cudaStream_t stream = (cudaStream_t)stream_;
     int grid = sl_grid_for(n, 128, h->num_sms, 16);
     if (g_bfe_blk_eval && (h->g.lmax == 4 || h->g.lmax == 6)) {
-        int rc = bfe_sl_ensure_a3(h, stream);
+        int rc = bfe_sl_ensure_a4(h, stream);
         if (rc != BFE_OK) return rc;
-        const double2* A3 = reinterpret_cast<const double2*>(h->a3);
+        const void* A3 = (const void*)h->a4;
         if (h->g.lmax == 4) sl_points_blk_kernel<4><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l, potr, pott, potp, pot1, pot0);
         else                sl_points_blk_kernel<6><<<grid, 128, 0, stream>>>(h->g, A3, h->xi, h->p0, h->fac, n, r, costh, phi, trig_index_l, potr, pott, potp, pot1, pot0);
         BFE_LAUNCH_CHECK("sl_points_blk_kernel");

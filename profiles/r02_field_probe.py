@@ -21,12 +21,16 @@ ap.add_argument('--chunks', default='262144,524288,1048576,2097152')
 ap.add_argument('--resorts', default='2,3,4,6,8,16')
 ap.add_argument('--stage', type=int, default=-1, help='option stage_eval (default: library default)')
 ap.add_argument('--subbits', type=int, default=-1, help='option key_subbits')
+ap.add_argument('--opt', action='append', default=[], help='name=value library option, repeatable')
 args = ap.parse_args()
 
 if args.stage >= 0:
     ops.set_option('stage_eval', args.stage)
 if args.subbits >= 0:
     ops.set_option('key_subbits', args.subbits)
+for kv in args.opt:
+    k_, v_ = kv.split('=')
+    ops.set_option(k_, int(v_))
 E = BC.eof_handle(); H = BC.sl_handle(args.lmax)
 n = args.n; nd = n // 2
 pd = BC.dev_particles('disc', nd, 3003); ph = BC.dev_particles('halo', n - nd, 3503)

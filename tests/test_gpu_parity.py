@@ -667,16 +667,24 @@ def test_key_ordered_paths_at_size(ops, lmax):
         ref_s, _, ref_n = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
         ref_d, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
         ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 40000); ops.set_option('orbit_sort_min', 1)
-        for stage in (0, 1):          # 1: table blocks of every tile staged in shared memory by TMA bulk copies (option stage_eval)
+        def same(a, b, stage):
+            # stage 0 (per-lane loads, the default): the same arithmetic as the caller-order kernels -> the same bits.
+            # stage 1 (table blocks of every tile staged in shared memory by TMA bulk copies, option stage_eval) reads the
+            # three-node SL blocks A3, the per-lane kernels the per-interval polynomial blocks A4: equal to rounding.
+            if stage == 0:
+                return torch.equal(a, b)
+            a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)          # per output row, the parity tolerance
+            return bool(((a2 - b2).abs().amax(dim=1) <= TOL * b2.abs().amax(dim=1)).all())
+        for stage in (0, 1):
             ops.set_option('stage_eval', stage)
-            assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref_c), stage
-            assert torch.equal(ops.field_force_cyl(E, H, x, y, z, rotpos=-1.1), ref_y), stage
+            assert same(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref_c, stage), stage
+            assert same(ops.field_force_cyl(E, H, x, y, z, rotpos=-1.1), ref_y, stage), stage
             for K in (1, 3):
                 ops.set_option('orbit_resort', K)
                 st, _, ns = ops.leapfrog(E, H, pos0, vel0, nint, 3e-4, rotfreq=-5.0)
-                assert torch.equal(st, ref_s) and torch.equal(ns, ref_n), (stage, K)
+                assert same(st, ref_s, stage) and torch.equal(ns, ref_n), (stage, K)
                 st, _, _ = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=2.0)
-                assert torch.equal(st, ref_d), (stage, K)
+                assert same(st, ref_d, stage), (stage, K)
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
