@@ -608,6 +608,9 @@ def run_gpu(args):
     ops.set_option('grid_pct', args.grid_pct)
     if args.sort_stable >= 0:
         ops.set_option('sort_stable', args.sort_stable)
+    for kv in args.opt:
+        k_, v_ = kv.split('=')
+        ops.set_option(k_, int(v_))
     Es = [E] + [E.clone() for _ in range(NSTREAMS - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NSTREAMS)]
     coefbufs = [torch.empty((2, g['mmax'] + 1, g['norder']), dtype=torch.float64, device=dev) for _ in range(NSTREAMS)]
@@ -969,6 +972,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--opt', action='append', default=[], help='library option name=value (repeatable; profiling A/B runs)')
     ap.add_argument('--streams', type=int, default=3, help='independent particle sets in flight (CUDA streams)')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
                     help='N>1: per-step coefficient sum by the peer-memory kernel (default) or NCCL')

@@ -202,6 +202,8 @@ eof_cell_scatter_kernel(EofGeom g, int64_t n, const double* __restrict__ x, cons
 //                             provisional order.  position = cell_start[cell] + H[tile][cell] + rank: the sort is stable
 //                             (ascending particle index inside every cell) and bit-reproducible, and so is everything
 //                             downstream of it.  Then the 64-byte record is built and stored as before.
+// (512-thread tile CTAs, two per SM, so that tiles of two streams share an SM: measured slower -- scatter 45.7 vs 37.7 us
+// per 10^6, step 0.149 vs 0.144 ms -- the per-tile fixed work, clearing and scanning 8192 counters, doubles.)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 eof_tile_hist_kernel(EofGeom g, int ncell, int64_t n, int tile, const double* __restrict__ x, const double* __restrict__ y,
