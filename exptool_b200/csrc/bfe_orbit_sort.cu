@@ -67,13 +67,19 @@ __device__ __forceinline__ int bfe_point_key(const EofGeom& ge, const SlGeom& gs
 // Guided tickets over the 128-point tiles of the sorted order: the first 3/4 of the tiles are handed out four at a time
 // (a CTA that walks consecutive tiles finds the table lines of the previous tile in L1: with single-tile tickets every
 // tile started cold, L1 hit rate 39-55 %), the rest one at a time so that the finish line is one tile wide.
+// Small sets (fewer than 8 tiles per CTA of the grid: 1.25 x 10^5 orbits per GPU when 10^6 are spread over 8 GPUs) get single
+// tiles only -- with four-tile tickets most CTAs took exactly one ticket and the kernel lasted as long as four tiles x K steps
+// while the average CTA had work for 2.2 (C4 at N = 8: 56 us per step against 22 us at the single-GPU rate).
 struct TileTicket { unsigned int first, count; };
+__device__ __forceinline__ unsigned int bfe_ticket_n4(unsigned int ntile) {
+    return (ntile >= 8u * gridDim.x) ? (ntile - ntile / 4) / 4 : 0u;
+}
 __device__ __forceinline__ unsigned int bfe_ticket_count(unsigned int ntile) {
-    const unsigned int n4 = (ntile - ntile / 4) / 4;
+    const unsigned int n4 = bfe_ticket_n4(ntile);
     return n4 + (ntile - 4 * n4);
 }
 __device__ __forceinline__ TileTicket bfe_ticket_tiles(unsigned int k, unsigned int ntile) {
-    const unsigned int n4 = (ntile - ntile / 4) / 4;
+    const unsigned int n4 = bfe_ticket_n4(ntile);
     TileTicket t;
     if (k < n4) { t.first = 4 * k; t.count = 4; }
     else { t.first = 4 * n4 + (k - n4); t.count = 1; }
