@@ -725,6 +725,26 @@ def run_gpu(args):
     barrier()
     ms_single = l0.elapsed_time(l1) / args.steps
 
+    # the price of bit-reproducibility: the same timed region with the slot claims of the cell sort done by global integer
+    # atomics (option sort_stable = 0; results then agree to ~1e-16 from run to run instead of bit for bit)
+    atomic_sort = None
+    if ops.get_option('sort_stable') == 1:
+        ops.set_option('sort_stable', 0)
+        run_steps(0, max(args.warmup, 3))
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        run_steps(args.warmup, args.steps)
+        a1.record()
+        barrier()
+        ops.set_option('sort_stable', 1)
+        tat = torch.tensor([a0.elapsed_time(a1) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tat, op=dist.ReduceOp.MAX)
+        atomic_sort = {'ms_per_step': float(tat.item()), 'value': world * N_PART / (float(tat.item()) * 1e-3),
+                       'note': 'option sort_stable = 0: slot claims of the cell sort by global integer atomics, coefficients '
+                               'reproducible to ~1e-16 only; the headline runs the stable atomic-free sort (bit-reproducible)'}
+
     # ---- per-kernel durations (CUDA events on the launching stream) for the roofline object
     def time_kernel(fn, reps):
         for k in range(3):
@@ -950,6 +970,7 @@ def run_gpu(args):
                                           % world if world > 1 else 'single GPU'},
                 'host_issue_ms_per_step': host_issue_ms,
                 'single_stream': {'ms_per_step': ms_single, 'value': world * N_PART / (ms_single * 1e-3)},
+                'with_atomic_sort': atomic_sort,
                 'pbe_per_s': value * PBE_PER_PARTICLE, 'e2e': e2e, 'gpu_launches': int(launches),
                 'roofline': roofline, 'clocks': clocks}
         if cpu is not None:

@@ -125,6 +125,7 @@ inline bool bfe_use_fp32(const bfe_eof* h) { return (h->table_fp32 >= 0 ? h->tab
 inline bool bfe_use_fp32(const bfe_sl* h) { return (h->table_fp32 >= 0 ? h->table_fp32 : g_bfe_table_fp32) != 0; }
 int bfe_eof_ensure_g4f(bfe_eof* h, cudaStream_t stream);
 int bfe_sl_ensure_a3f(bfe_sl* h, cudaStream_t stream);
+int bfe_tile_colscan(int nbin, int ntile, int* H, int* total, int* bin_start, unsigned int* counter, cudaStream_t stream);   // bfe_sort.cu
 int bfe_sl_ensure_a4(bfe_sl* h, cudaStream_t stream);        // build A4 from a_con if stale
 extern int g_bfe_blk_eval;                                  // option "blk_eval": per-lane block evaluation with 256-bit loads
 extern int g_bfe_staged_eval;                               // option "staged_eval": 1 (default) / 0

@@ -118,6 +118,122 @@ sl_bin_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __r
 }
 
 // ---------------------------------------------------------------------------
+// STABLE radial-bin sort without global atomics (option "sort_stable", default 1): the tile counting sort of bfe_sort.cu
+// (eof_tile_hist_kernel / eof_tile_colscan_kernel / eof_tile_scatter_kernel) with the radial interval as the key.  Together
+// with the static task assignment of sl_deposit_kernel it makes the sorted SL accumulation bit-reproducible.
+//   sl_tile_hist_kernel    : one CTA per tile of 1024 U consecutive particles: interval per particle (FP64, as the record
+//                            needs it), shared-memory integer counters -> row H[tile][bin]; the interval is kept in binid[]
+//   (bfe_tile_colscan)     : H[tile][bin] -> members of the bin in earlier tiles; bin_start
+//   sl_tile_scatter_kernel : shared-memory counting sort of the tile's ids by bin, rank = members of the own (tile, bin)
+//                            group with a smaller id; position = bin_start[bin] + H[tile][bin] + rank; record stored
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+sl_tile_hist_kernel(SlGeom g, const double* __restrict__ xi, int nbin, int64_t n, int tile, const double* __restrict__ x,
+                    const double* __restrict__ y, const double* __restrict__ z, int* __restrict__ H, int* __restrict__ binid) {
+    extern __shared__ int s_hist[];
+    for (int c = threadIdx.x; c < nbin; c += blockDim.x) s_hist[c] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * tile;
+    for (int o = threadIdx.x; o < tile; o += 1024) {
+        const int64_t i = base + o;
+        if (i >= n) break;
+        const double px = __ldg(x + i), py = __ldg(y + i), pz = __ldg(z + i);
+        const double r2 = BFE_ADD(BFE_ADD(BFE_MUL(px, px), BFE_MUL(py, py)), BFE_MUL(pz, pz));
+        const double r = fmax(sqrt(r2), 1.0e-10);
+        const SlBin b = bfe_sl_bin(g, xi, r);
+        atomicAdd(&s_hist[b.i], 1);                       // shared-memory integer count
+        binid[i] = b.i;
+    }
+    __syncthreads();
+    int* row = H + (size_t)blockIdx.x * nbin;
+    for (int c = threadIdx.x; c < nbin; c += blockDim.x) row[c] = s_hist[c];
+}
+
+__global__ void __launch_bounds__(1024)
+sl_tile_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __restrict__ p0tab, int nbin, int64_t n, int tile,
+                       const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                       const double* __restrict__ mass, const int* __restrict__ bin_start, const int* __restrict__ H,
+                       SlRec* __restrict__ rec, const int* __restrict__ binid) {
+    extern __shared__ int s_mem[];
+    __shared__ int s_wsum[32];
+    int* s_cnt = s_mem;                                   // [per * 1024]: counts -> starts -> group ends (as in eof_tile_scatter_kernel)
+    const int per = (nbin + 1023) / 1024;
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_mem + per * 1024);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < per * 1024; c += 1024) s_cnt[c] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * tile;
+    const int nu = tile >> 10;                            // particles per thread (<= 8)
+    int bin[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        bin[u] = -1;
+        if (u < nu) {
+            const int64_t i = base + u * 1024 + tid;
+            if (i < n) { bin[u] = binid[i]; atomicAdd(&s_cnt[bin[u]], 1); }
+        }
+    }
+    __syncthreads();
+    {
+        const int lo = tid * per;
+        int sum = 0;
+        for (int k = 0; k < per; ++k) sum += s_cnt[lo + k];
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_wsum[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+            s_wsum[lane] = w;
+        }
+        __syncthreads();
+        int run = incl - sum + (warp > 0 ? s_wsum[warp - 1] : 0);
+        for (int k = 0; k < per; ++k) { const int hcnt = s_cnt[lo + k]; s_cnt[lo + k] = run; run += hcnt; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        if (bin[u] >= 0) s_list[atomicAdd(&s_cnt[bin[u]], 1)] = (unsigned short)(u * 1024 + tid);
+    __syncthreads();
+    auto bin_at = [&](int u) {
+        int c = bin[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) c = (u == k) ? bin[k] : c;
+        return c;
+    };
+#pragma unroll 1
+    for (int u = 0; u < nu; ++u) {
+        const int c = bin_at(u);
+        if (c < 0) continue;
+        const int64_t idx = base + u * 1024 + tid;
+        const double px = __ldg(x + idx), py = __ldg(y + idx), pz = __ldg(z + idx), pm = __ldg(mass + idx);
+        const int gbase = __ldg(bin_start + c) + __ldg(H + (size_t)blockIdx.x * nbin + c);
+        const int lo = c ? s_cnt[c - 1] : 0, hi = s_cnt[c];
+        const int me = u * 1024 + tid;
+        int rank = 0;
+        int k = lo;
+        for (; (k & 3) && k < hi; ++k) rank += (s_list[k] < me) ? 1 : 0;
+        const unsigned int K = (unsigned int)me * 0x00010001u + 0x7fff7fffu;      // see eof_tile_scatter_kernel
+        unsigned int acc = 0u;
+        for (; k + 3 < hi; k += 4) {
+            const uint2 w = *reinterpret_cast<const uint2*>(s_list + k);
+            acc += (((K - w.x) >> 15) & 0x00010001u) + (((K - w.y) >> 15) & 0x00010001u);
+        }
+        rank += (int)((acc & 0xffffu) + (acc >> 16));
+        for (; k < hi; ++k) rank += (s_list[k] < me) ? 1 : 0;
+        const int pos = gbase + rank;
+        const SlPrep pr = bfe_sl_prep(g, xi, p0tab, px, py, pz, pm);        // pr.i == c
+        const unsigned long long bp = ((unsigned long long)(unsigned int)c << 32) | (unsigned long long)(unsigned int)idx;
+        char* dst = reinterpret_cast<char*>(rec + pos);
+        bfe_st256(dst, pr.x1, pr.x2, pr.W, pr.costh);
+        bfe_st256(dst + 32, pr.c1, pr.s1, 0.0, __longlong_as_double((long long)bp));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // deposit: a warp owns TASK consecutive sorted records (dynamic task queue).
 //   expand (lanes = records): P_l^m recurrence (explicitly rounded, as bfe_legendre), cos/sin(m phi),
 //     w_k for all (lmax+1)^2 rows into the warp's shared-memory slab, plus x1, x2;
@@ -141,7 +257,7 @@ template <int LCAP, int KC>
 __global__ void __launch_bounds__(128, 3)
 sl_deposit_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ fac, int no_odd,
                   int64_t n, const SlRec* __restrict__ rec, double* __restrict__ partial,
-                  unsigned int* __restrict__ counter, int use_tma) {
+                  unsigned int* __restrict__ counter, int use_tma, int static_tasks) {
     constexpr int TASK = 128;
     constexpr int NW = 4;                          // warps per CTA
     constexpr int NROWCAP = (LCAP + 1) * (LCAP + 1);
@@ -189,10 +305,18 @@ sl_deposit_kernel(SlGeom g, const double* __restrict__ e_node, const double* __r
     unsigned int* task_counter = counter + 1;
     const int64_t ntasks = (n + TASK - 1) / TASK;
     SDBG_DECL;
+    // static_tasks (with the stable sort): warp w of the grid takes tasks w, w + W, w + 2W, ... -- which records a warp sums,
+    // and in which order, is then a function of the input alone (the dynamic queue made the per-CTA partials depend on the
+    // schedule: coefficients reproducible to ~1e-16 only); the stride spreads the slow short-run tasks of the outskirts
+    const int64_t gwarp = (int64_t)blockIdx.x * NW + warp, gstep = (int64_t)gridDim.x * NW;
+    int64_t snext = gwarp;
     for (;;) {
         int64_t task = 0;
-        if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
-        task = __shfl_sync(0xffffffffu, task, 0);
+        if (static_tasks) { task = snext; snext += gstep; }
+        else {
+            if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
+            task = __shfl_sync(0xffffffffu, task, 0);
+        }
         if (task >= ntasks) break;
 #ifdef BFE_PROFILE_DEPOSIT
         sd_ntask++;
@@ -617,7 +741,12 @@ static size_t sl_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlSortWs {
     int* hist; int* bin_start; int* cursor; SlRec* rec;
+    int* binid; int* H;          // stable tile sort: interval per particle, [tiles][nbin] counts
 };
+static int64_t sl_tile_rows_for(const bfe_sl* h, int64_t cap) {
+    const int64_t a = h->num_sms, b = cap / 8192 + 2;
+    return a > b ? a : b;
+}
 
 static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
     const int nbin = h->g.numr - 1;
@@ -628,7 +757,8 @@ static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
     if (n > h->sort_cap || !h->sort_ws) {
         if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
         int64_t cap = n + n / 8 + 1024;
-        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + sizeof(SlRec) * (size_t)cap));
+        BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(SlRec) + sizeof(int)) * (size_t)cap + 256 +
+                                             sizeof(int) * (size_t)nbin * (size_t)sl_tile_rows_for(h, cap) + 256));
         BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
         BFE_CUDA(cudaDeviceSynchronize());
         h->sort_cap = cap;
@@ -636,6 +766,8 @@ static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
     char* b = (char*)h->sort_ws;
     ws->hist = (int*)(b + o_hist); ws->bin_start = (int*)(b + o_start); ws->cursor = (int*)(b + o_cur);
     ws->rec = (SlRec*)(b + o_rec);
+    ws->binid = (int*)(b + sl_align_up(o_rec + sizeof(SlRec) * (size_t)h->sort_cap, 256));
+    ws->H = (int*)(b + sl_align_up(o_rec + (sizeof(SlRec) + sizeof(int)) * (size_t)h->sort_cap + 256, 256));
     return BFE_OK;
 }
 
@@ -656,7 +788,7 @@ static int sl_deposit_launch(bfe_sl* h, int64_t n, const SlRec* rec, int no_odd,
     if (grid < 1) grid = 1;
     if (grid > h->max_ctas) grid = h->max_ctas;
     const int use_tma = (h->g.ln % 2 == 0) ? 1 : 0;      // bulk copies need 16-byte aligned rows
-    kern<<<grid, 128, smem, stream>>>(h->g, h->e_node, h->fac, no_odd, n, rec, h->partial, h->counter, use_tma);
+    kern<<<grid, 128, smem, stream>>>(h->g, h->e_node, h->fac, no_odd, n, rec, h->partial, h->counter, use_tma, g_bfe_sort_stable ? 1 : 0);
     BFE_LAUNCH_CHECK("sl_deposit_kernel");
     sl_sorted_reduce_kernel<<<(ncoef + 7) / 8, 256, 0, stream>>>(h->partial, grid, ncoef, expcoef, h->counter);
     BFE_LAUNCH_CHECK("sl_sorted_reduce_kernel");
@@ -702,10 +834,32 @@ int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double
     int rc = sl_sort_workspace(h, n, &ws);
     if (rc != BFE_OK) return rc;
     const int nbin = h->g.numr - 1;
+    bool sorted_done = false;
+    if (g_bfe_sort_stable && n > 0 && g_bfe_sl_deposit_mode != 2) {
+        int64_t U = (n + (int64_t)h->num_sms * 1024 - 1) / ((int64_t)h->num_sms * 1024);
+        U = U < 1 ? 1 : (U > 8 ? 8 : U);
+        const int tile = (int)(U * 1024);
+        const int ntile = (int)((n + tile - 1) / tile);
+        const int per = (nbin + 1023) / 1024;
+        const size_t ss_h = sizeof(int) * (size_t)per * 1024;
+        const size_t ss_s = ss_h + sizeof(unsigned short) * (size_t)tile + 16;
+        if (ss_s <= 200 * 1024 && (int64_t)ntile <= sl_tile_rows_for(h, h->sort_cap) && (nbin + 63) / 64 <= 1024) {
+            if (ss_h > 48 * 1024) BFE_CUDA(cudaFuncSetAttribute(sl_tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_h));
+            if (ss_s > 48 * 1024) BFE_CUDA(cudaFuncSetAttribute(sl_tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_s));
+            sl_tile_hist_kernel<<<ntile, 1024, ss_h, stream>>>(h->g, h->xi, nbin, n, tile, x, y, z, ws.H, ws.binid);
+            BFE_LAUNCH_CHECK("sl_tile_hist_kernel");
+            rc = bfe_tile_colscan(nbin, ntile, ws.H, ws.hist, ws.bin_start, h->counter, stream);
+            if (rc != BFE_OK) return rc;
+            sl_tile_scatter_kernel<<<ntile, 1024, ss_s, stream>>>(h->g, h->xi, h->p0, nbin, n, tile, x, y, z, mass,
+                                                                 (const int*)ws.bin_start, (const int*)ws.H, ws.rec, (const int*)ws.binid);
+            BFE_LAUNCH_CHECK("sl_tile_scatter_kernel");
+            sorted_done = true;
+        }
+    }
     int grid = (int)((n + 1023) / 1024);
     if (grid > h->num_sms * 2) grid = h->num_sms * 2;
     if (grid < 1) grid = 1;
-    {
+    if (!sorted_done) {
         const int per = (nbin + 1023) / 1024;
         const size_t ss = sizeof(int) * (size_t)per * 1024;
         if (ss > 200 * 1024) return BFE_ERR_UNSUPPORTED;
@@ -718,8 +872,10 @@ int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double
     int g2 = (int)((n + 511) / 512);
     if (g2 > h->num_sms * 8) g2 = h->num_sms * 8;
     if (g2 < 1) g2 = 1;
-    sl_bin_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, h->xi, h->p0, n, x, y, z, mass, ws.bin_start, ws.cursor, ws.rec);
-    BFE_LAUNCH_CHECK("sl_bin_scatter_kernel");
+    if (!sorted_done) {
+        sl_bin_scatter_kernel<<<g2, 256, 0, stream>>>(h->g, h->xi, h->p0, n, x, y, z, mass, ws.bin_start, ws.cursor, ws.rec);
+        BFE_LAUNCH_CHECK("sl_bin_scatter_kernel");
+    }
     if (g_bfe_sl_deposit_mode == 2) {             // register formulation (option sl_deposit_mode = 2); default: slab kernel
         if (h->g.lmax <= 4) return sl_deposit_lane_launch<4, 1>(h, n, ws.rec, no_odd, expcoef, stream);
         return sl_deposit_lane_launch<6, 2>(h, n, ws.rec, no_odd, expcoef, stream);

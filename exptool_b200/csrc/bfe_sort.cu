@@ -363,6 +363,13 @@ eof_tile_colscan_kernel(int ncell, int ntile, int* __restrict__ H, int* __restri
     }
 }
 
+// the column scan for another table of bins (the SL radial-bin sort, bfe_sl_sort.cu); nbin / 64 <= 1024 blocks
+int bfe_tile_colscan(int nbin, int ntile, int* H, int* total, int* bin_start, unsigned int* counter, cudaStream_t stream) {
+    eof_tile_colscan_kernel<<<(nbin + BFE_COLSCAN_CW - 1) / BFE_COLSCAN_CW, 1024, 0, stream>>>(nbin, ntile, H, total, bin_start, counter);
+    BFE_LAUNCH_CHECK("eof_tile_colscan_kernel");
+    return BFE_OK;
+}
+
 __global__ void __launch_bounds__(1024)
 eof_tile_scatter_kernel(EofGeom g, int ncell, int64_t n, int tile, const double* __restrict__ x, const double* __restrict__ y,
                         const double* __restrict__ z, const double* __restrict__ mass, const int* __restrict__ cell_start,

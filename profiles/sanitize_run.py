@@ -50,6 +50,10 @@ for lmax in (4, 6):
     pin = [torch.from_numpy(a).pin_memory() for a in d]
     E.accumulate_host(*pin); E.force_host(*pin[:3])
     E.prepare(*d); E.accumulate_prepared(); E.force_prepared()
+    for st in (1, 0):                         # stable tile sorts (EOF cells, SL radial bins, static deposit tasks) / atomic slot claims
+        ops.set_option('sort_stable', st); ops.set_option('eof_accumulate_mode', 2); ops.set_option('sl_accumulate_mode', 2)
+        E.accumulate(*d); H.accumulate(*h)
+    ops.set_option('sort_stable', 1); ops.set_option('eof_accumulate_mode', 0); ops.set_option('sl_accumulate_mode', 0)
     # density outputs, building blocks
     H.contract_density(ch); H.density(*h[:3]); H.density_eval_points(np.abs(h[0]) + 1e-3, np.clip(h[2], -1, 1), h[1])
     H.radial_matrices(np.abs(h[0]) + 1e-6); ops.legendre_tables(lmax, np.clip(h[2], -1, 1))

@@ -728,3 +728,37 @@ def test_stable_cell_sort_is_bit_reproducible(ops):
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('lmax', [4, 6])
+def test_stable_sl_bin_sort_is_bit_reproducible(ops, lmax):
+    """The sorted SL accumulation with the stable tile sort of the radial bins and the static task assignment of the deposit
+    kernel (option sort_stable, default): the coefficients are bit-identical from run to run, for ragged sizes and a set
+    concentrated in one radial interval; equal within rounding to the path with slot claims by integer atomics + the dynamic
+    task queue, and to the direct kernel."""
+    import torch
+    meta = dict(sl_params=dict(lmax=lmax), kind='smooth', seed=0)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    saved = {k: ops.get_option(k) for k in ('sort_stable', 'sl_accumulate_mode')}
+    try:
+        for n, seed in ((300001, 11), (50000, 12), (1025, 13)):
+            x, y, z, m = S.hernquist_halo(n, seed)
+            if seed == 12:                                  # one radial interval: the longest possible group
+                rr = np.sqrt(x * x + y * y + z * z)
+                f = (0.02 * (1.0 + 1e-7 * np.arange(n) / n)) / rr
+                x, y, z = x * f, y * f, z * f
+            ops.set_option('sl_accumulate_mode', 2)
+            ops.set_option('sort_stable', 1)
+            runs = [H.accumulate(x, y, z, m).clone() for _ in range(3)]
+            assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2]), (n, lmax)
+            ops.set_option('sort_stable', 0)
+            c0 = H.accumulate(x, y, z, m)
+            assert relerr(c0.cpu().numpy(), runs[0].cpu().numpy()) < 1e-12, (n, lmax)
+            ops.set_option('sl_accumulate_mode', 1)
+            c1 = H.accumulate(x, y, z, m)
+            assert relerr(c1.cpu().numpy(), runs[0].cpu().numpy()) < 1e-12, (n, lmax)
+    finally:
+        for k, v in saved.items():
+            ops.set_option(k, v)
