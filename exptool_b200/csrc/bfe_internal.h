@@ -57,6 +57,7 @@ struct bfe_eof {
     void* host_pipe;         // staging buffers / streams of the host-array entry points (bfe_host.cu), lazily made
     void* orbit_ws;          // key-sort workspace of the table-coherent field / leapfrog paths (bfe_orbit_sort.cu), grown on demand
     int64_t orbit_cap;
+    int64_t orbit_hdr;       // bytes of the workspace header (histogram, starts, block prefixes: depends on option key_subbits)
     void* orbit_rec;         // 96-byte orbit records of the key-ordered leapfrog path, grown on demand
     int64_t orbit_rec_cap;
     void* field_pipe;        // aux stream + events of the two-stream point pipeline (bfe_orbit_sort.cu), lazily made
@@ -157,6 +158,7 @@ extern int g_bfe_field_sort_min;                           // option "field_sort
 extern int g_bfe_stage_eval;                               // option "stage_eval"
 extern int g_bfe_sort_stable;                              // option "sort_stable"
 extern int g_bfe_key_subbits;                              // option "key_subbits"
+extern int g_bfe_orbit_key_subbits;                        // option "orbit_key_subbits"
 int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
                            double crot, double srot, double* out8, bool cyl, cudaStream_t stream);
 int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,

@@ -600,9 +600,18 @@ orbit_unpack_kernel(int64_t n, const OrbRec* __restrict__ rec, double* __restric
 // host side
 // ---------------------------------------------------------------------------
 int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between re-sorts of a large orbit batch (0: plain kernel)
-int g_bfe_key_subbits = BFE_KEY_SUBBITS; // option "key_subbits": low bits of the SL interval in the ordering key (bins = ncell << subbits)
+// options "key_subbits" (points) / "orbit_key_subbits" (orbits): low bits of the SL interval in the ordering key (bins = ncell << bits).
+// Measured on 4e7-point sets (profiles/r02_chunk_probe2.json, us per 1e6 at 2^22-point chunks, bits 4 / 5 / 6 / 7 / 8): halo-like
+// 342 / 322 / 310 / 271 / 265 (a cell of the outer halo spans > 100 radial intervals: 16 slots alias them), disc-like 189 / 186 / 189 /
+// 198 / 207 (more bins = fewer points per bin and a longer scan).  Points: at most 7, fewer for small chunks (keysort_ws); orbits
+// (disc-like batches, one sort per K steps): 4.
+int g_bfe_key_subbits = 7;
+int g_bfe_orbit_key_subbits = BFE_KEY_SUBBITS;
 int g_bfe_orbit_sort_min = 65536;       // option "orbit_sort_min": smallest batch on the key-ordered path
-int g_bfe_field_sort_chunk = 1 << 20;   // option "field_sort_chunk": points per sort + evaluate pass (L2-resident working set)
+// option "field_sort_chunk": most points per sort + evaluate pass.  2^22 since the probe above (2^20 / 2^21 / 2^22 / 2^23 / 2^24: halo
+// 353 / 347 / 342 / 357 / 366, disc 205 / 196 / 189 / 206 / 212 at 4 bits): more points per bin beat L2 residency of the records;
+// sets smaller than four such chunks are cut in four (>= 2^20 points each) so that two chunks are still in flight
+int g_bfe_field_sort_chunk = 1 << 22;
 int g_bfe_stage_eval = 0;               // option "stage_eval": FP64-table key-ordered kernels evaluate from TMA-staged shared-memory blocks (1) or
                                         // with global loads (0, default).  Measured on B200 (profiles/r02_field_probe_stage*.json, r02_ncu_full_field_stage.csv):
                                         // global-load requests per tile fall 3.7x and results stay bit-identical, but the warps of a 2^19..2^20-point
@@ -623,29 +632,51 @@ struct KeySortWs {
 // workspace in he->orbit_ws, grown on demand: header + per item 12 bytes (orbits: keyrank, perm) or 2 x 100 bytes (points)
 static int keysort_ws(bfe_eof* he, int64_t cap_need, bool points, KeySortWs& w) {
     w.ncell = he->g.numx * he->g.numy;
-    w.subbits = g_bfe_key_subbits;
-    if (w.subbits < 0) w.subbits = 0;
-    if (w.subbits > 8) w.subbits = 8;
-    while (w.subbits > 0 && ((int64_t)w.ncell << w.subbits) > ((int64_t)1 << 21)) --w.subbits;
-    if (((int64_t)w.ncell << w.subbits) > ((int64_t)1 << 21)) return BFE_ERR_UNSUPPORTED;
+    auto clamp_bits = [&](int b) {
+        if (b < 0) b = 0;
+        if (b > 8) b = 8;
+        while (b > 0 && ((int64_t)w.ncell << b) > ((int64_t)1 << 21)) --b;
+        return b;
+    };
+    // points and orbits have their own key width (options key_subbits / orbit_key_subbits); the header is laid out for the
+    // wider of the two, so alternating between the two paths does not re-lay the workspace
+    const int sub_pts = clamp_bits(g_bfe_key_subbits), sub_orb = clamp_bits(g_bfe_orbit_key_subbits);
+    w.subbits = points ? sub_pts : sub_orb;
+    if (points) {
+        // the key width follows the chunk: ~4 points per (cell, slot) on average -- 2^22-point chunks on the 128 x 64 table take
+        // 7 bits, 2^19-point chunks 4 (with 7 bits a 2 x 10^6-point disc set lost its coherence: 303 us per 10^6 against 209)
+        int lg = 0;
+        while (((int64_t)w.ncell << (lg + 1)) <= cap_need) ++lg;             // floor(log2(chunk / ncell))
+        int want = lg - 2;
+        if (want < 4) want = 4;
+        if (w.subbits > want) w.subbits = want;
+    }
+    const int sub_cap = sub_pts > sub_orb ? sub_pts : sub_orb;
+    if (((int64_t)w.ncell << sub_cap) > ((int64_t)1 << 21)) return BFE_ERR_UNSUPPORTED;
     w.nkeys = w.ncell << w.subbits;
     w.nblk = (w.nkeys + BFE_SCAN_BLOCK - 1) / BFE_SCAN_BLOCK;
+    const int nkeys_cap = w.ncell << sub_cap, nblk_cap = (nkeys_cap + BFE_SCAN_BLOCK - 1) / BFE_SCAN_BLOCK;
     const size_t o_hist = 0;
-    const size_t o_start = os_align(o_hist + sizeof(int) * (size_t)w.nkeys);
-    const size_t o_btot = os_align(o_start + sizeof(int) * (size_t)w.nkeys);
-    const size_t o_bpre = os_align(o_btot + sizeof(int) * (size_t)w.nblk);
-    const size_t o_ctr = os_align(o_bpre + sizeof(int) * (size_t)(w.nblk + 1));
+    const size_t o_start = os_align(o_hist + sizeof(int) * (size_t)nkeys_cap);
+    const size_t o_btot = os_align(o_start + sizeof(int) * (size_t)nkeys_cap);
+    const size_t o_bpre = os_align(o_btot + sizeof(int) * (size_t)nblk_cap);
+    const size_t o_ctr = os_align(o_bpre + sizeof(int) * (size_t)(nblk_cap + 1));
     const size_t o_item = os_align(o_ctr + 64);
     const size_t a64 = os_align(64 * (size_t)cap_need), a32 = os_align(32 * (size_t)cap_need), a8 = os_align(8 * (size_t)cap_need),
                  a4 = os_align(4 * (size_t)cap_need);
     const int64_t need = points ? (int64_t)(2 * (a64 + a32 + a4)) : (int64_t)(a8 + a4);
-    if (need > he->orbit_cap || !he->orbit_ws) {          // orbit_cap: BYTES available for items
-        if (he->orbit_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_ws)); he->orbit_ws = nullptr; he->orbit_cap = 0; }
-        const int64_t bytes = need + need / 8 + 4096;
+    // orbit_cap: BYTES available for items; orbit_hdr: bytes of the header the workspace was laid out for.  The header depends
+    // on the option key_subbits (nkeys = ncell << subbits): a change of the option after the first call must re-lay the
+    // workspace (it used to keep the old allocation and the 16x larger histogram of subbits 8 ran into the item arrays)
+    if (need > he->orbit_cap || (int64_t)o_item != he->orbit_hdr || !he->orbit_ws) {
+        const int64_t keep = he->orbit_cap > need ? he->orbit_cap : need + need / 8 + 4096;
+        if (he->orbit_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_ws)); he->orbit_ws = nullptr; he->orbit_cap = 0; he->orbit_hdr = 0; }
+        const int64_t bytes = keep;
         BFE_CUDA(cudaMalloc(&he->orbit_ws, o_item + (size_t)bytes));
         BFE_CUDA(cudaMemset(he->orbit_ws, 0, o_item));
         BFE_CUDA(cudaDeviceSynchronize());
         he->orbit_cap = bytes;
+        he->orbit_hdr = (int64_t)o_item;
     }
     char* b = (char*)he->orbit_ws;
     w.hist = (int*)(b + o_hist); w.start = (int*)(b + o_start); w.btot = (int*)(b + o_btot); w.bprefix = (int*)(b + o_bpre);
@@ -717,7 +748,10 @@ static int grid_cap(int64_t n, int block, int cap) {
 int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
                            double crot, double srot, double* out8, bool cyl, cudaStream_t stream) {
     const int64_t chunk_opt = g_bfe_field_sort_chunk > 0 ? g_bfe_field_sort_chunk : (1 << 19);
-    const int64_t chunk = n < chunk_opt ? n : chunk_opt;
+    int64_t chunk = ((n + 3) / 4 + 127) / 128 * 128;
+    if (chunk < ((int64_t)1 << 20)) chunk = (int64_t)1 << 20;
+    if (chunk > chunk_opt) chunk = chunk_opt;
+    if (chunk > n) chunk = n;
     KeySortWs w;
     int rc = keysort_ws(he, chunk, true, w);
     if (rc != BFE_OK) return rc;

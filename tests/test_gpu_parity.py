@@ -762,3 +762,40 @@ def test_stable_sl_bin_sort_is_bit_reproducible(ops, lmax):
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
+
+
+@pytest.mark.gpu
+def test_key_subbits_change_relays_workspace(ops):
+    """Option key_subbits changes the size of the key-sort workspace's header (nkeys = ncell << subbits).  Changing it between
+    calls on the same handles must re-lay the workspace (round 2 bug: the old allocation was kept and the larger histogram
+    overran the item arrays -> CUDA error / silent corruption).  Results are the caller-order bits for every setting."""
+    import torch
+    meta = dict(eof_params={}, sl_params=dict(lmax=6), kind='smooth', seed=0)
+    pe, T, g = eof_tables(meta)
+    E = make_eof(ops, T, g)
+    p, ev, ef, xi, p0, d0 = sl_tables(meta)
+    H = make_sl(ops, p, ev, ef, xi, p0, d0)
+    xd, yd, zd, md = S.exponential_disc(120000, 21)
+    xh, yh, zh, mh = S.hernquist_halo(80000, 22)
+    c, s_ = E.accumulate(xd, yd, zd, md)
+    E.contract(c * 0.025, s_ * 0.025)
+    H.contract(H.accumulate(xh, yh, zh, mh))
+    x = np.concatenate([xd, xh]); y = np.concatenate([yd, yh]); z = np.concatenate([zd, zh])
+    keys = ('field_sort_min', 'field_sort_chunk', 'key_subbits', 'orbit_key_subbits', 'orbit_sort_min', 'orbit_resort')
+    saved = {k: ops.get_option(k) for k in keys}
+    try:
+        ops.set_option('field_sort_min', 0); ops.set_option('orbit_resort', 0)
+        ref = ops.field_force_cart(E, H, x, y, z, rotpos=0.3)
+        pos0 = np.stack([xd[:20000], yd[:20000], zd[:20000]])
+        vel0 = np.stack([-pos0[1], pos0[0], 0.0 * pos0[2]]) * 1.1
+        ref_s, _, _ = ops.leapfrog(E, H, pos0, vel0, 14, 3e-4, rotfreq=-5.0)
+        ops.set_option('field_sort_min', 1); ops.set_option('field_sort_chunk', 70000)
+        ops.set_option('orbit_sort_min', 1); ops.set_option('orbit_resort', 3)
+        for sub, osub in ((4, 4), (8, 4), (2, 8), (0, 0), (6, 7), (7, 4)):
+            ops.set_option('key_subbits', sub); ops.set_option('orbit_key_subbits', osub)
+            assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref), (sub, osub)
+            st, _, _ = ops.leapfrog(E, H, pos0, vel0, 14, 3e-4, rotfreq=-5.0)
+            assert torch.equal(st, ref_s), (sub, osub)
+    finally:
+        for k, v in saved.items():
+            ops.set_option(k, v)
