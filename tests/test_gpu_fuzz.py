@@ -145,3 +145,47 @@ def test_fuzz_sorted_accumulate_and_force(ops):
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
+
+
+def test_fuzz_host_pipelines(ops):
+    """The chunked host-array pipelines (EOF and SL, accumulate and evaluate) against the one-shot device path for random sizes,
+    pinned / pageable / mixed inputs, copy-thread counts and the one-upload-per-snapshot option."""
+    import torch
+    E, H = _handles(ops, 6)
+    rng = np.random.default_rng(777 + SEED)
+    keys = ('host_reuse', 'host_threads')
+    saved = {k: ops.get_option(k) for k in keys}
+
+    def rel(a, b):
+        a = np.asarray(a); b = np.asarray(b)
+        s = np.abs(b).max()
+        return np.abs(a - b).max() / s if s > 0 else np.abs(a - b).max()
+    try:
+        for it in range(ITERS or 8):
+            n = int(rng.choice([1, 5, 4099, 250001, int(rng.integers(2, 900000))]))
+            x, y, z, m = _points(rng, n)
+            ops.set_option('host_reuse', int(rng.integers(0, 2))); ops.set_option('host_threads', int(rng.integers(1, 6)))
+            mode = int(rng.integers(0, 3))                 # 0 pageable NumPy, 1 pinned tensors, 2 mixed
+            def host(a, k):
+                if mode == 1 or (mode == 2 and k % 2 == 0):
+                    return torch.from_numpy(a).pin_memory()
+                return a
+            P = [host(a, k) for k, a in enumerate((x, y, z, m))]
+            cd, sd = E.accumulate(x, y, z, m)
+            hd = H.accumulate(x, y, z, m)
+            ch, sh = E.accumulate_host(*P)
+            hh = H.accumulate_host(*P)
+            assert rel(ch, cd.cpu().numpy()) < 1e-11 and rel(sh, sd.cpu().numpy()) < 1e-11, (it, n, mode)
+            assert rel(hh, hd.cpu().numpy()) < 1e-11, (it, n, mode)
+            E.contract(cd, sd); H.contract(hd)
+            fe = E.force(x, y, z).cpu().numpy(); fs = H.force(x, y, z).cpu().numpy()
+            ge = E.force_host(*P[:3]); gs = H.force_host(*P[:3])
+            es = np.abs(fe[2:5]).max(); ss = np.abs(fs[2:5]).max()
+            for i in range(6):
+                if 2 <= i <= 4:
+                    assert np.abs(ge[i] - fe[i]).max() <= 1e-11 * es and np.abs(gs[i] - fs[i]).max() <= 1e-11 * ss, (it, n, mode, i)
+                else:
+                    assert rel(ge[i], fe[i]) < 1e-11 and rel(gs[i], fs[i]) < 1e-11, (it, n, mode, i)
+    finally:
+        for k, v in saved.items():
+            ops.set_option(k, v)
