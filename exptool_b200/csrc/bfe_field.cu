@@ -373,6 +373,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "orbit_sort_min")) { g_bfe_orbit_sort_min = value; return BFE_OK; }
     if (!strcmp(name, "grid_pct")) { if (value < 1 || value > 100) return BFE_ERR_ARG; g_bfe_grid_pct = value; return BFE_OK; }
     if (!strcmp(name, "contract_deep")) { g_bfe_contract_deep = value; return BFE_OK; }
+    if (!strcmp(name, "sl_flush_cost")) { g_bfe_sl_flush_cost = value < 0 ? 0 : value; return BFE_OK; }
     if (!strcmp(name, "host_chunk")) { g_bfe_host_chunk = value; return BFE_OK; }
     if (!strcmp(name, "host_reuse")) { g_bfe_host_reuse = value; return BFE_OK; }
     if (!strcmp(name, "host_threads")) { if (value < 0 || value > 64) return BFE_ERR_ARG; g_bfe_host_threads = value; return BFE_OK; }
@@ -408,6 +409,7 @@ extern "C" int bfe_get_option(const char* name) {
     if (!strcmp(name, "orbit_sort_min")) return g_bfe_orbit_sort_min;
     if (!strcmp(name, "grid_pct")) return g_bfe_grid_pct;
     if (!strcmp(name, "contract_deep")) return g_bfe_contract_deep;
+    if (!strcmp(name, "sl_flush_cost")) return g_bfe_sl_flush_cost;
     if (!strcmp(name, "host_chunk")) return g_bfe_host_chunk;
     if (!strcmp(name, "host_reuse")) return g_bfe_host_reuse;
     if (!strcmp(name, "host_threads")) return g_bfe_host_threads;

@@ -157,6 +157,7 @@ extern int g_bfe_field_sort_chunk;                         // option "field_sort
 extern int g_bfe_field_sort_min;                           // option "field_sort_min"
 extern int g_bfe_stage_eval;                               // option "stage_eval"
 extern int g_bfe_sort_stable;                              // option "sort_stable"
+extern int g_bfe_sl_flush_cost;                            // option "sl_flush_cost"
 extern int g_bfe_key_subbits;                              // option "key_subbits"
 extern int g_bfe_orbit_key_subbits;                        // option "orbit_key_subbits"
 int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,

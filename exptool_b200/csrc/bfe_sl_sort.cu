@@ -18,6 +18,8 @@
 #include "bfe_device.cuh"
 #include "bfe_sortcore.cuh"
 
+#define BFE_SL_MAX_GRANULES 131072      // granules of the static deposit split: <= 128 blocks of 1024
+
 struct __align__(16) SlRec {
     double x1, x2;               // linear weights of nodes i, i+1 (spheresl.py:327-328)
     double W;                    // -4 pi m (x1 p0[i] + x2 p0[i+1])
@@ -234,6 +236,49 @@ sl_tile_scatter_kernel(SlGeom g, const double* __restrict__ xi, const double* __
 }
 
 // ---------------------------------------------------------------------------
+// Static, balanced work split for the deposit kernel (with the stable sort; option sort_stable).  The sorted array is cut
+// into granules of G records; the cost of a granule is modelled as G + FC * (radial intervals it spans, <= G) -- every run of
+// equal intervals ends in a flush that costs about FC records' worth of time -- and warp w of the grid gets the contiguous
+// granules whose cumulative cost lies in [w, w + 1) * total / W.  The split is a function of the sorted data alone, so the
+// per-warp sums, the per-CTA partials and the coefficients are bit-reproducible, and a warp walks ONE contiguous range:
+// runs that continue across granules are not flushed in between (the dynamic queue flushed at the end of every
+// 128-record task).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+sl_granule_cost_kernel(int64_t n, int gran, int ngran, int flush_cost, const SlRec* __restrict__ rec,
+                       unsigned int* __restrict__ lprefix, unsigned int* __restrict__ btot) {
+    // thread per granule; exclusive prefix inside the block of 1024 granules -> lprefix, block total -> btot (the deposit
+    // kernel scans the <= 128 block totals itself)
+    __shared__ unsigned int s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x * 1024 + tid;
+    unsigned int cost = 0u;
+    if (g < ngran) {
+        const int64_t a = (int64_t)g * gran, b = min(n, a + gran) - 1;
+        const int ba = (int)((unsigned long long)__double_as_longlong(__ldg(reinterpret_cast<const double*>(rec + a) + 7)) >> 32);
+        const int bb = (int)((unsigned long long)__double_as_longlong(__ldg(reinterpret_cast<const double*>(rec + b) + 7)) >> 32);
+        int span = bb - ba + 1;
+        if (span < 1) span = 1;
+        if (span > gran) span = gran;
+        cost = (unsigned int)((int)(b - a + 1) + flush_cost * span);
+    }
+    unsigned int incl = cost;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = s_w[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+        s_w[lane] = w;
+    }
+    __syncthreads();
+    if (g < ngran) lprefix[g] = incl - cost + (warp > 0 ? s_w[warp - 1] : 0u);
+    if (tid == 1023) btot[blockIdx.x] = s_w[31];
+}
+
+// ---------------------------------------------------------------------------
 // deposit: a warp owns TASK consecutive sorted records (dynamic task queue).
 //   expand (lanes = records): P_l^m recurrence (explicitly rounded, as bfe_legendre), cos/sin(m phi),
 //     w_k for all (lmax+1)^2 rows into the warp's shared-memory slab, plus x1, x2;
@@ -257,7 +302,8 @@ template <int LCAP, int KC>
 __global__ void __launch_bounds__(128, 3)
 sl_deposit_kernel(SlGeom g, const double* __restrict__ e_node, const double* __restrict__ fac, int no_odd,
                   int64_t n, const SlRec* __restrict__ rec, double* __restrict__ partial,
-                  unsigned int* __restrict__ counter, int use_tma, int static_tasks) {
+                  unsigned int* __restrict__ counter, int use_tma, int static_tasks, int gran, int ngran,
+                  const unsigned int* __restrict__ gprefix) {
     constexpr int TASK = 128;
     constexpr int NW = 4;                          // warps per CTA
     constexpr int NROWCAP = (LCAP + 1) * (LCAP + 1);
@@ -305,24 +351,64 @@ sl_deposit_kernel(SlGeom g, const double* __restrict__ e_node, const double* __r
     unsigned int* task_counter = counter + 1;
     const int64_t ntasks = (n + TASK - 1) / TASK;
     SDBG_DECL;
-    // static_tasks (with the stable sort): warp w of the grid takes tasks w, w + W, w + 2W, ... -- which records a warp sums,
-    // and in which order, is then a function of the input alone (the dynamic queue made the per-CTA partials depend on the
-    // schedule: coefficients reproducible to ~1e-16 only); the stride spreads the slow short-run tasks of the outskirts
-    const int64_t gwarp = (int64_t)blockIdx.x * NW + warp, gstep = (int64_t)gridDim.x * NW;
-    int64_t snext = gwarp;
+    // static_tasks (with the stable sort): this warp's contiguous range of granules from the cost prefix (sl_granule_cost_kernel)
+    // -- a function of the sorted data alone, so the sums are bit-reproducible; the dynamic queue made the per-CTA partials depend
+    // on the schedule (coefficients reproducible to ~1e-16 only)
+    int64_t s_t0 = 0, s_cnt = 0;
+    if (static_tasks) {
+        // gprefix = [lprefix (ngran) | btot (<= 128 blocks of 1024 granules)]: block prefixes by one warp scan, four per lane
+        const unsigned int* btot = gprefix + BFE_SL_MAX_GRANULES;
+        const int nblkg = (ngran + 1023) >> 10;
+        unsigned int bt[4], bp[4];
+        unsigned int mine = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int bidx = lane * 4 + q; bt[q] = bidx < nblkg ? __ldg(btot + bidx) : 0u; mine += bt[q]; }
+        unsigned int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+        bp[0] = incl - mine; bp[1] = bp[0] + bt[0]; bp[2] = bp[1] + bt[1]; bp[3] = bp[2] + bt[2];     // exclusive block prefixes
+        const unsigned long long gw = (unsigned long long)blockIdx.x * NW + warp, W = (unsigned long long)gridDim.x * NW;
+        const unsigned int lo_c = (unsigned int)(total * gw / W), hi_c = (unsigned int)(total * (gw + 1) / W);
+        auto lower = [&](unsigned int c) {                 // first granule g with (global) prefix[g] >= c
+            // block: the last one whose prefix is <= c (blocks are non-empty, prefixes strictly increase)
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cnt += (lane * 4 + q < nblkg && bp[q] <= c) ? 1 : 0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+            const int blk = cnt > 0 ? cnt - 1 : 0;
+            unsigned int base = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const unsigned int v = __shfl_sync(0xffffffffu, bp[q], blk >> 2); if ((blk & 3) == q) base = v; }
+            const unsigned int cl = c - base;
+            int a = blk << 10, b = min(ngran, a + 1024);
+            while (a < b) { const int mid = (a + b) >> 1; if (__ldg(gprefix + mid) < cl) a = mid + 1; else b = mid; }
+            return a;
+        };
+        const int glo = lower(lo_c), ghi = (gw + 1 == W) ? ngran : lower(hi_c);
+        s_t0 = (int64_t)glo * gran;
+        const int64_t e = (int64_t)ghi * gran < n ? (int64_t)ghi * gran : n;
+        s_cnt = e > s_t0 ? e - s_t0 : 0;
+    }
     for (;;) {
-        int64_t task = 0;
-        if (static_tasks) { task = snext; snext += gstep; }
-        else {
+        int64_t t0;
+        int tcnt;
+        if (static_tasks) {
+            if (s_cnt <= 0) break;
+            t0 = s_t0; tcnt = (int)s_cnt;
+            s_cnt = 0;                                      // one pass over the whole range
+        } else {
+            int64_t task = 0;
             if (lane == 0) task = (int64_t)atomicAdd(task_counter, 1u);
             task = __shfl_sync(0xffffffffu, task, 0);
+            if (task >= ntasks) break;
+            t0 = task * TASK;
+            tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
         }
-        if (task >= ntasks) break;
 #ifdef BFE_PROFILE_DEPOSIT
         sd_ntask++;
 #endif
-        const int64_t t0 = task * TASK;
-        const int tcnt = (int)((n - t0) < TASK ? (n - t0) : TASK);
         double dA1 = 0.0, dA2 = 0.0, dB1 = 0.0, dB2 = 0.0;
         int cur = -1;
         double2 ra, rb, rc, rd;
@@ -737,12 +823,15 @@ sl_sorted_reduce_kernel(const double* __restrict__ partial, int nrows, int ncol,
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+int g_bfe_sl_flush_cost = 32;          // option "sl_flush_cost": cost of a run flush in records, for the static split of the deposit kernel
 static size_t sl_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlSortWs {
     int* hist; int* bin_start; int* cursor; SlRec* rec;
     int* binid; int* H;          // stable tile sort: interval per particle, [tiles][nbin] counts
+    unsigned int* gprefix;       // cost prefix over the granules of the sorted array (static deposit split)
 };
+
 static int64_t sl_tile_rows_for(const bfe_sl* h, int64_t cap) {
     const int64_t a = h->num_sms, b = cap / 8192 + 2;
     return a > b ? a : b;
@@ -758,7 +847,8 @@ static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
         if (h->sort_ws) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(h->sort_ws)); h->sort_ws = nullptr; }
         int64_t cap = n + n / 8 + 1024;
         BFE_CUDA(cudaMalloc(&h->sort_ws, o_rec + (sizeof(SlRec) + sizeof(int)) * (size_t)cap + 256 +
-                                             sizeof(int) * (size_t)nbin * (size_t)sl_tile_rows_for(h, cap) + 256));
+                                             sizeof(int) * (size_t)nbin * (size_t)sl_tile_rows_for(h, cap) + 512 +
+                                             sizeof(unsigned int) * (BFE_SL_MAX_GRANULES + 256)));
         BFE_CUDA(cudaMemset(h->sort_ws, 0, o_rec));
         BFE_CUDA(cudaDeviceSynchronize());
         h->sort_cap = cap;
@@ -768,11 +858,14 @@ static int sl_sort_workspace(bfe_sl* h, int64_t n, SlSortWs* ws) {
     ws->rec = (SlRec*)(b + o_rec);
     ws->binid = (int*)(b + sl_align_up(o_rec + sizeof(SlRec) * (size_t)h->sort_cap, 256));
     ws->H = (int*)(b + sl_align_up(o_rec + (sizeof(SlRec) + sizeof(int)) * (size_t)h->sort_cap + 256, 256));
+    ws->gprefix = (unsigned int*)(b + sl_align_up(o_rec + (sizeof(SlRec) + sizeof(int)) * (size_t)h->sort_cap + 256 +
+                                                  sizeof(int) * (size_t)nbin * (size_t)sl_tile_rows_for(h, h->sort_cap) + 256, 256));
     return BFE_OK;
 }
 
 template <int LCAP, int KC>
-static int sl_deposit_launch(bfe_sl* h, int64_t n, const SlRec* rec, int no_odd, double* expcoef, cudaStream_t stream) {
+static int sl_deposit_launch(bfe_sl* h, int64_t n, const SlRec* rec, unsigned int* gprefix, int no_odd, double* expcoef,
+                             cudaStream_t stream) {
     constexpr int NW = 4;
     const size_t smem = ((size_t)NW * (2 * (LCAP + 1) * 32) + (size_t)NW * ((LCAP + 1) * (LCAP + 1) + 2) * 33 +
                          (size_t)NW * 128) * sizeof(double) + NW * sizeof(unsigned long long) + 32 * KC * sizeof(int) + 128;
@@ -788,7 +881,18 @@ static int sl_deposit_launch(bfe_sl* h, int64_t n, const SlRec* rec, int no_odd,
     if (grid < 1) grid = 1;
     if (grid > h->max_ctas) grid = h->max_ctas;
     const int use_tma = (h->g.ln % 2 == 0) ? 1 : 0;      // bulk copies need 16-byte aligned rows
-    kern<<<grid, 128, smem, stream>>>(h->g, h->e_node, h->fac, no_odd, n, rec, h->partial, h->counter, use_tma, g_bfe_sort_stable ? 1 : 0);
+    const int static_tasks = (g_bfe_sort_stable && n > 0) ? 1 : 0;
+    int gran = 128, ngran = 0;
+    if (static_tasks) {
+        // granules of 128 records, coarser for very large sets (<= 128 blocks of 1024 granules)
+        while ((n + gran - 1) / gran > BFE_SL_MAX_GRANULES) gran *= 2;
+        ngran = (int)((n + gran - 1) / gran);
+        sl_granule_cost_kernel<<<(ngran + 1023) / 1024, 1024, 0, stream>>>(n, gran, ngran, g_bfe_sl_flush_cost, rec, gprefix,
+                                                                          gprefix + BFE_SL_MAX_GRANULES);
+        BFE_LAUNCH_CHECK("sl_granule_cost_kernel");
+    }
+    kern<<<grid, 128, smem, stream>>>(h->g, h->e_node, h->fac, no_odd, n, rec, h->partial, h->counter, use_tma, static_tasks,
+                                      gran, ngran, gprefix);
     BFE_LAUNCH_CHECK("sl_deposit_kernel");
     sl_sorted_reduce_kernel<<<(ncoef + 7) / 8, 256, 0, stream>>>(h->partial, grid, ncoef, expcoef, h->counter);
     BFE_LAUNCH_CHECK("sl_sorted_reduce_kernel");
@@ -881,6 +985,6 @@ int bfe_sl_accumulate_sorted(bfe_sl* h, int64_t n, const double* x, const double
         return sl_deposit_lane_launch<6, 2>(h, n, ws.rec, no_odd, expcoef, stream);
     }
     if (h->g.lmax <= 4 && h->g.nrow * h->g.nmax <= 32 * 15)
-        return sl_deposit_launch<4, 15>(h, n, ws.rec, no_odd, expcoef, stream);
-    return sl_deposit_launch<6, 28>(h, n, ws.rec, no_odd, expcoef, stream);
+        return sl_deposit_launch<4, 15>(h, n, ws.rec, ws.gprefix, no_odd, expcoef, stream);
+    return sl_deposit_launch<6, 28>(h, n, ws.rec, ws.gprefix, no_odd, expcoef, stream);
 }
