@@ -361,7 +361,7 @@ extern "C" int bfe_eof_create(const bfe_eof_params* p, const double* potC, const
     BFE_CUDA(cudaMalloc(&h->g4, (size_t)g.numx * g.numy * 12 * (p->mmax + 1) * 2 * sizeof(double)));
     h->g4_valid = 0;
     h->g4f = nullptr; h->g4f_valid = 0; h->table_fp32 = -1;
-    h->orbit_ws = nullptr; h->orbit_cap = 0; h->orbit_hdr = 0; h->orbit_rec = nullptr; h->orbit_rec_cap = 0; h->field_pipe = nullptr;
+    h->orbit_ws = nullptr; h->orbit_cap = 0; h->orbit_hdr = 0; h->keycell = nullptr; h->keycell_nkeys = 0; h->keycell_nkeys2 = 0; h->keycell_tag = 0; h->orbit_rec = nullptr; h->orbit_rec_cap = 0; h->field_pipe = nullptr;
     BFE_CUDA(cudaMalloc(&h->partial, (size_t)(h->max_ctas + 64) * h->nch_pad * sizeof(double)));   // + group rows of the two-level reduce
     BFE_CUDA(cudaMalloc(&h->counter, 128 * sizeof(unsigned int)));      // [0] last-CTA, [1] task queue, [64..] reduce groups
     BFE_CUDA(cudaMemsetAsync(h->counter, 0, 128 * sizeof(unsigned int), stream));
@@ -392,7 +392,7 @@ extern "C" int bfe_eof_clone(const bfe_eof* src, void* stream_, bfe_eof** out) {
     h->contracted = 0; h->g4_valid = 0; h->g4f = nullptr; h->g4f_valid = 0;
     h->sort_cap = 0; h->sort_ws = nullptr; h->prepared_n = -1; h->prepared_has_mass = 0;
     h->host_pipe = nullptr;
-    h->orbit_ws = nullptr; h->orbit_cap = 0; h->orbit_hdr = 0; h->orbit_rec = nullptr; h->orbit_rec_cap = 0; h->field_pipe = nullptr;
+    h->orbit_ws = nullptr; h->orbit_cap = 0; h->orbit_hdr = 0; h->keycell = nullptr; h->keycell_nkeys = 0; h->keycell_nkeys2 = 0; h->keycell_tag = 0; h->orbit_rec = nullptr; h->orbit_rec_cap = 0; h->field_pipe = nullptr;
     h->g_con = nullptr; h->g4 = nullptr; h->partial = nullptr; h->counter = nullptr;
     const EofGeom& g = h->g;
     cudaError_t e = cudaMalloc(&h->g_con, (size_t)g.nnode * h->gstride * sizeof(double));
@@ -415,6 +415,7 @@ extern "C" void bfe_eof_destroy(bfe_eof* h) {
     cudaFree(h->g_con); cudaFree(h->g4); cudaFree(h->partial); cudaFree(h->counter);
     if (h->g4f) cudaFree(h->g4f);
     if (h->orbit_ws) cudaFree(h->orbit_ws);
+    if (h->keycell) cudaFree(h->keycell);
     if (h->orbit_rec) cudaFree(h->orbit_rec);
     if (h->sort_ws) cudaFree(h->sort_ws);
     bfe_host_pipe_destroy(h->host_pipe);

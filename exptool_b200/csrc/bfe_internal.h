@@ -58,6 +58,9 @@ struct bfe_eof {
     void* orbit_ws;          // key-sort workspace of the table-coherent field / leapfrog paths (bfe_orbit_sort.cu), grown on demand
     int64_t orbit_cap;
     int64_t orbit_hdr;       // bytes of the workspace header (histogram, starts, block prefixes: depends on option key_subbits)
+    void* keycell;           // per-cell key spans {key offset, first interval, span, -} for the SL table of keycell_tag (bfe_orbit_sort.cu)
+    int keycell_nkeys, keycell_nkeys2;       // keys with one per interval / one per four intervals
+    unsigned long long keycell_tag;
     void* orbit_rec;         // 96-byte orbit records of the key-ordered leapfrog path, grown on demand
     int64_t orbit_rec_cap;
     void* field_pipe;        // aux stream + events of the two-stream point pipeline (bfe_orbit_sort.cu), lazily made
@@ -160,6 +163,8 @@ extern int g_bfe_sort_stable;                              // option "sort_stabl
 extern int g_bfe_sl_flush_cost;                            // option "sl_flush_cost"
 extern int g_bfe_key_subbits;                              // option "key_subbits"
 extern int g_bfe_orbit_key_subbits;                        // option "orbit_key_subbits"
+extern int g_bfe_key_mode;                                 // option "key_mode"
+extern int g_bfe_keycell_nkeys_last;
 int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
                            double crot, double srot, double* out8, bool cyl, cudaStream_t stream);
 int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,

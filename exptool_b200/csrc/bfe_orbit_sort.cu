@@ -54,14 +54,95 @@ __device__ __forceinline__ int bfe_sl_interval_fast(const SlGeom& g, float r) {
     return i;
 }
 
-__device__ __forceinline__ int bfe_point_key(const EofGeom& ge, const SlGeom& gs, int ncell, int subbits,
+// The ordering key.  Bit scheme (kc == nullptr): (cell << subbits) | (interval & mask).  Per-cell spans (kc != nullptr, the default):
+// kc[cell] = {first key of the cell, first radial interval the cell can reach, number of intervals it spans, -}, so a cell of the
+// disc plane (a few intervals) takes a few keys and a cell of the outer halo (hundreds) as many as it needs:
+// key = koff + (interval - jmin), clamped; spans above 256 (the open cells at the table's edges) alias modulo 256.  Built once per
+// (EOF table, SL table) pair by key_cell_span_kernel / key_cell_scan_kernel.  FP32 arithmetic, an ordering hint only.
+// With kc the argument `subbits` is the SHIFT of the slot index instead: 0 = one key per interval (.x offsets), 2 = one key per four
+// intervals (.w offsets), used for chunks too small to fill the fine keys.
+__device__ __forceinline__ int bfe_point_key(const EofGeom& ge, const SlGeom& gs, const int4* __restrict__ kc, int ncell, int subbits,
                                              double px, double py, double pz) {
     int cell;
     bfe_eof_cell_fast(ge, px, py, pz, cell);
     if ((unsigned)cell >= (unsigned)ncell) cell = 0;
     const float xf = (float)px, yf = (float)py, zf = (float)pz;
     const int j = bfe_sl_interval_fast(gs, sqrtf(fmaf(xf, xf, fmaf(yf, yf, zf * zf))));
+    if (kc) {
+        const int4 t = __ldg(kc + cell);
+        int d = j - t.y;
+        if (t.z <= 256) { d = d < 0 ? 0 : (d >= t.z ? t.z - 1 : d); }
+        else d &= 255;
+        return subbits ? (t.w + (d >> 2)) : (t.x + d);
+    }
     return (cell << subbits) | (j & ((1 << subbits) - 1));
+}
+
+// radial-interval range of every table cell: the cell covers X in [ix, ix+1], Y in [iy, iy+1] of the table's coordinates; the
+// radius over it runs from (R_lo, min |z|) to (R_hi, max |z|); cells on the table's rim are open (clamped bin indices)
+__global__ void key_cell_span_kernel(EofGeom ge, SlGeom gs, const double* __restrict__ xi, int4* __restrict__ kc) {
+    const int ncell = ge.numx * ge.numy;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    const int ix = cell / ge.numy, iy = cell - ix * ge.numy;
+    auto R_of = [&](double X) {                           // inverse of bfe_r_to_xi
+        const double v = ge.xmin + X * ge.dx;
+        if (ge.cmap == 1) return (v >= 1.0) ? 1.0e300 : ge.ascale * (1.0 + v) / (1.0 - v);
+        if (ge.cmap == 2) return exp(v);
+        return v;
+    };
+    auto z_of = [&](double Y) { return ge.hscale * sinh(ge.ymin + Y * ge.dy); };
+    double Rlo = (ix == 0) ? 0.0 : fmax(R_of((double)ix), 0.0);
+    double Rhi = fmax(R_of((double)ix + 1.0), 0.0);
+    const double za = z_of((double)iy), zb = z_of((double)iy + 1.0);
+    const double zmin = (za <= 0.0 && zb >= 0.0) ? 0.0 : fmin(fabs(za), fabs(zb));
+    const double zmax = fmax(fabs(za), fabs(zb));
+    const bool open = (ix == ge.numx - 1) || (iy == 0) || (iy == ge.numy - 1);
+    const double rmin = sqrt(Rlo * Rlo + zmin * zmin), rmax = sqrt(Rhi * Rhi + zmax * zmax);
+    int jmin = bfe_sl_bin(gs, xi, fmax(rmin, 1.0e-300)).i - 1;      // one interval of slack either side (FP32 keys)
+    int jmax = (open || !(rmax < 1.0e299)) ? gs.numr - 2 : bfe_sl_bin(gs, xi, rmax).i + 1;
+    if (jmin < 0) jmin = 0;
+    if (jmax > gs.numr - 2) jmax = gs.numr - 2;
+    if (jmax < jmin) jmax = jmin;
+    const int span = jmax - jmin + 1;
+    kc[cell] = make_int4(span <= 256 ? span : 256, jmin, span, 0);   // .x: keys of the cell, turned into the offset by the scan
+}
+
+// exclusive scans of the key counts over the cells (one CTA): fine keys (one per interval) -> .x, coarse keys (one per four
+// intervals) -> .w; totals -> nkeys_out[0], nkeys_out[1]
+__global__ void __launch_bounds__(1024) key_cell_scan_kernel(int ncell, int4* __restrict__ kc, int* __restrict__ nkeys_out) {
+    __shared__ int s_w[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (ncell + 1023) / 1024, c0 = tid * per, c1 = min(ncell, c0 + per);
+    int sum = 0, sum2 = 0;
+    for (int c = c0; c < c1; ++c) { const int k = kc[c].x; sum += k; sum2 += (k + 3) >> 2; }
+    int incl = sum, incl2 = sum2;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off), v2 = __shfl_up_sync(0xffffffffu, incl2, off);
+        if (lane >= off) { incl += v; incl2 += v2; }
+    }
+    if (lane == 31) { s_w[0][warp] = incl; s_w[1][warp] = incl2; }
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_w[0][lane], w2 = s_w[1][lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, off), v2 = __shfl_up_sync(0xffffffffu, w2, off);
+            if (lane >= off) { w += v; w2 += v2; }
+        }
+        s_w[0][lane] = w; s_w[1][lane] = w2;
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? s_w[0][warp - 1] : 0), run2 = incl2 - sum2 + (warp > 0 ? s_w[1][warp - 1] : 0);
+    for (int c = c0; c < c1; ++c) {
+        int4 t = kc[c];
+        const int k = t.x;
+        t.x = run; t.w = run2;
+        kc[c] = t;
+        run += k; run2 += (k + 3) >> 2;
+    }
+    if (tid == 1023) { nkeys_out[0] = s_w[0][31]; nkeys_out[1] = s_w[1][31]; }
 }
 
 // Guided tickets over the 128-point tiles of the sorted order: the first 3/4 of the tiles are handed out four at a time
@@ -103,7 +184,7 @@ __device__ __forceinline__ int bfe_claim_rank(int* __restrict__ hist, int key, b
 }
 
 __global__ void __launch_bounds__(256)
-pt_key_kernel(EofGeom ge, SlGeom gs, int ncell, int subbits, int64_t n, const double* __restrict__ x,
+pt_key_kernel(EofGeom ge, SlGeom gs, const int4* __restrict__ kc, int ncell, int subbits, int64_t n, const double* __restrict__ x,
               const double* __restrict__ y, const double* __restrict__ z, int* __restrict__ hist, int2* __restrict__ keyrank) {
     bfe_pdl_wait();
     bfe_pdl_trigger();
@@ -113,7 +194,7 @@ pt_key_kernel(EofGeom ge, SlGeom gs, int ncell, int subbits, int64_t n, const do
         int key = 0;
         // points arrive in the caller's order: the 32 keys of a warp differ, so one atomic per lane (no match / aggregation)
         if (on) {
-            key = bfe_point_key(ge, gs, ncell, subbits, __ldg(x + i), __ldg(y + i), __ldg(z + i));
+            key = bfe_point_key(ge, gs, kc, ncell, subbits, __ldg(x + i), __ldg(y + i), __ldg(z + i));
             keyrank[i] = make_int2(key, atomicAdd(hist + key, 1));
         }
     }
@@ -400,7 +481,7 @@ struct __align__(32) OrbRec {            // 96 bytes = three full sectors
 };
 
 __global__ void __launch_bounds__(256)
-orbit_pack_key_kernel(EofGeom ge, SlGeom gs, int ncell, int subbits, int64_t n, const double* __restrict__ state6,
+orbit_pack_key_kernel(EofGeom ge, SlGeom gs, const int4* __restrict__ kc, int ncell, int subbits, int64_t n, const double* __restrict__ state6,
                       double dt, const double* __restrict__ dt_orbit, OrbRec* __restrict__ rec, int* __restrict__ hist,
                       int2* __restrict__ keyrank) {
     bfe_pdl_wait();
@@ -415,7 +496,7 @@ orbit_pack_key_kernel(EofGeom ge, SlGeom gs, int ncell, int subbits, int64_t n, 
             bfe_st256(dst, px, py, pz, state6[3 * n + i]);
             bfe_st256(dst + 32, state6[4 * n + i], state6[5 * n + i], dt_orbit ? dt_orbit[i] : dt, 0.0);
             bfe_st256(dst + 64, 0.0, 0.0, 0.0, 0.0);
-            key = bfe_point_key(ge, gs, ncell, subbits, px, py, pz);
+            key = bfe_point_key(ge, gs, kc, ncell, subbits, px, py, pz);
         }
         const int rank = bfe_claim_rank(hist, key, on);
         if (on) keyrank[i] = make_int2(key, rank);
@@ -429,7 +510,7 @@ template <int MCAP, int LCAP, bool F32>
 __global__ void __launch_bounds__(128, BFE_PERM_MINB)
 leapfrog_perm_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
                      const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
-                     int64_t norbit, int64_t step0, int nsteps, double rotfreq, int first, int rekey, int ncell, int subbits,
+                     int64_t norbit, int64_t step0, int nsteps, double rotfreq, int first, int rekey, const int4* __restrict__ kc, int ncell, int subbits,
                      const int* __restrict__ perm, OrbRec* __restrict__ rec, int* __restrict__ hist,
                      int2* __restrict__ keyrank, unsigned int* __restrict__ ticket) {
     __shared__ unsigned int s_tile;
@@ -485,7 +566,7 @@ leapfrog_perm_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const v
                 bfe_st256(d + 64, ay, az, u0, u1);
                 // key of the NEXT evaluation point: the drift of the following step (the same expression, so the same bits)
                 // -- orbits cross an SL interval per step, so a key taken at the current position would be stale at once
-                if (rekey) key = bfe_point_key(ge, gs, ncell, subbits, px + (vx * dt) + (ax * hdt2), py + (vy * dt) + (ay * hdt2),
+                if (rekey) key = bfe_point_key(ge, gs, kc, ncell, subbits, px + (vx * dt) + (ax * hdt2), py + (vy * dt) + (ay * hdt2),
                                                pz + (vz * dt) + (az * hdt2));
             }
             if (rekey) {
@@ -502,7 +583,7 @@ template <int MCAP, int LCAP>
 __global__ void __launch_bounds__(128, BFE_PERM_MINB)
 leapfrog_stage_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, const double2* __restrict__ A3,
                       const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
-                      int64_t norbit, int64_t step0, int nsteps, double rotfreq, int first, int rekey, int ncell, int subbits,
+                      int64_t norbit, int64_t step0, int nsteps, double rotfreq, int first, int rekey, const int4* __restrict__ kc, int ncell, int subbits,
                       const int* __restrict__ perm, OrbRec* __restrict__ rec, int* __restrict__ hist,
                       int2* __restrict__ keyrank, unsigned int* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char s_stage[];
@@ -570,7 +651,7 @@ leapfrog_stage_kernel(EofGeom ge, const double2* __restrict__ G4, SlGeom gs, con
                 bfe_st256(d + 32, vy, vz, dt, ax);
                 bfe_st256(d + 64, ay, az, u0, u1);
                 // key of the NEXT evaluation point: the drift of the following step (the same expression, so the same bits)
-                if (rekey) key = bfe_point_key(ge, gs, ncell, subbits, px + (vx * dt) + (ax * hdt2), py + (vy * dt) + (ay * hdt2),
+                if (rekey) key = bfe_point_key(ge, gs, kc, ncell, subbits, px + (vx * dt) + (ax * hdt2), py + (vy * dt) + (ay * hdt2),
                                                pz + (vz * dt) + (az * hdt2));
             }
             if (rekey) {
@@ -605,6 +686,9 @@ int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between 
 // 342 / 322 / 310 / 271 / 265 (a cell of the outer halo spans > 100 radial intervals: 16 slots alias them), disc-like 189 / 186 / 189 /
 // 198 / 207 (more bins = fewer points per bin and a longer scan).  Points: at most 7, fewer for small chunks (keysort_ws); orbits
 // (disc-like batches, one sort per K steps): 4.
+int g_bfe_key_mode = 1;                 // option "key_mode": bit 0 = points, bit 1 = orbits ordered by per-cell interval spans (bfe_point_key);
+                                        // otherwise (cell << bits) | (interval & mask).  Orbits: measured 2.5 % slower with the spans (C4)
+int g_bfe_keycell_nkeys_last = 0;       // read-only option "keycell_nkeys": keys of the last per-cell span table built
 int g_bfe_key_subbits = 7;
 int g_bfe_orbit_key_subbits = BFE_KEY_SUBBITS;
 int g_bfe_orbit_sort_min = 65536;       // option "orbit_sort_min": smallest batch on the key-ordered path
@@ -624,14 +708,56 @@ static size_t os_align(size_t v) { return (v + 255) / 256 * 256; }
 
 struct KeySortWs {
     int ncell, subbits, nkeys, nblk;
+    const int4* kc;                  // per-cell key spans (option key_mode = 1) or nullptr (bit scheme)
     int* hist; int* start; int* btot; int* bprefix; unsigned int* counter;     // counter[0]: scan's last-CTA count, [1], [2]: tile tickets
     int2* keyrank[2]; int* perm[2];  // perm doubles as the inverse permutation of the point path
     double* rec4[2]; double* slot8[2];   // point path only, two chunks in flight; slot8 aliases keyrank (dead after the scatter)
 };
 
 // workspace in he->orbit_ws, grown on demand: header + per item 12 bytes (orbits: keyrank, perm) or 2 x 100 bytes (points)
-static int keysort_ws(bfe_eof* he, int64_t cap_need, bool points, KeySortWs& w) {
+// per-cell key spans for the (EOF table, SL table) pair: built on first use and whenever another SL table is paired
+static int key_cells(bfe_eof* he, bfe_sl* hs, cudaStream_t stream) {
+    const int ncell = he->g.numx * he->g.numy;
+    unsigned long long tag = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { tag = (tag ^ v) * 1099511628211ull; };
+    unsigned long long u;
+    mix((unsigned long long)hs->g.numr); mix((unsigned long long)hs->g.cmap);
+    memcpy(&u, &hs->g.xi0, 8); mix(u); memcpy(&u, &hs->g.dxi, 8); mix(u); memcpy(&u, &hs->g.scale, 8); mix(u);
+    mix((unsigned long long)(uintptr_t)hs->xi);
+    if (tag == 0) tag = 1;
+    if (he->keycell && he->keycell_tag == tag) return BFE_OK;
+    if (!he->keycell) BFE_CUDA(cudaMalloc(&he->keycell, sizeof(int4) * (size_t)ncell + 16));
+    int4* kc = (int4*)he->keycell;
+    int* d_n = (int*)(kc + ncell);
+    key_cell_span_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(he->g, hs->g, hs->xi, kc);
+    BFE_LAUNCH_CHECK("key_cell_span_kernel");
+    key_cell_scan_kernel<<<1, 1024, 0, stream>>>(ncell, kc, d_n);
+    BFE_LAUNCH_CHECK("key_cell_scan_kernel");
+    int nk[2] = {0, 0};
+    BFE_CUDA(cudaMemcpyAsync(nk, d_n, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BFE_CUDA(cudaStreamSynchronize(stream));
+    he->keycell_nkeys = nk[0];
+    he->keycell_nkeys2 = nk[1];
+    he->keycell_tag = tag;
+    g_bfe_keycell_nkeys_last = nk[0];
+    return BFE_OK;
+}
+
+static int keysort_ws(bfe_eof* he, bfe_sl* hs, cudaStream_t stream, int64_t cap_need, bool points, KeySortWs& w) {
     w.ncell = he->g.numx * he->g.numy;
+    w.kc = nullptr;
+    int nkeys_cells = 0, kc_shift = 0;
+    if (points ? (g_bfe_key_mode & 1) : (g_bfe_key_mode & 2)) {
+        int rc = key_cells(he, hs, stream);
+        if (rc != BFE_OK) return rc;
+        if (he->keycell_nkeys > 0 && he->keycell_nkeys <= (1 << 21)) {
+            w.kc = (const int4*)he->keycell;
+            // fine keys (one per interval) when the chunk brings >= ~5 points per key, else one key per four intervals
+            // (2 x 10^6 disc points in 10^6-point chunks: 228 us per 10^6 with the fine keys, 214 with 5 bits of the bit scheme)
+            kc_shift = (cap_need >= 5 * (int64_t)he->keycell_nkeys) ? 0 : 2;
+            nkeys_cells = kc_shift ? he->keycell_nkeys2 : he->keycell_nkeys;
+        }
+    }
     auto clamp_bits = [&](int b) {
         if (b < 0) b = 0;
         if (b > 8) b = 8;
@@ -653,9 +779,12 @@ static int keysort_ws(bfe_eof* he, int64_t cap_need, bool points, KeySortWs& w) 
     }
     const int sub_cap = sub_pts > sub_orb ? sub_pts : sub_orb;
     if (((int64_t)w.ncell << sub_cap) > ((int64_t)1 << 21)) return BFE_ERR_UNSUPPORTED;
-    w.nkeys = w.ncell << w.subbits;
+    w.nkeys = w.kc ? nkeys_cells : (w.ncell << w.subbits);
     w.nblk = (w.nkeys + BFE_SCAN_BLOCK - 1) / BFE_SCAN_BLOCK;
-    const int nkeys_cap = w.ncell << sub_cap, nblk_cap = (nkeys_cap + BFE_SCAN_BLOCK - 1) / BFE_SCAN_BLOCK;
+    int nkeys_cap = w.ncell << sub_cap;
+    if (w.kc && he->keycell_nkeys > nkeys_cap) nkeys_cap = he->keycell_nkeys;      // laid out for the fine keys: no re-lay when the shift changes
+    if (w.kc) w.subbits = kc_shift;                    // with the per-cell table the kernels' `subbits` argument is the slot shift
+    const int nblk_cap = (nkeys_cap + BFE_SCAN_BLOCK - 1) / BFE_SCAN_BLOCK;
     const size_t o_hist = 0;
     const size_t o_start = os_align(o_hist + sizeof(int) * (size_t)nkeys_cap);
     const size_t o_btot = os_align(o_start + sizeof(int) * (size_t)nkeys_cap);
@@ -753,7 +882,7 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
     if (chunk > chunk_opt) chunk = chunk_opt;
     if (chunk > n) chunk = n;
     KeySortWs w;
-    int rc = keysort_ws(he, chunk, true, w);
+    int rc = keysort_ws(he, hs, stream, chunk, true, w);
     if (rc != BFE_OK) return rc;
     FieldPipe* fp = nullptr;
     rc = field_pipe(he, fp);
@@ -776,7 +905,7 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
         const int64_t c0 = c * chunk, m = (n - c0) < chunk ? (n - c0) : chunk;
         const int b = (int)(c & 1);
         const int g256 = grid_cap(m, 256, he->num_sms * 4);
-        KS_LAUNCH_ON(aux, "pt_key_kernel", pt_key_kernel, g256, 256, he->g, hs->g, w.ncell, w.subbits, m, x + c0, y + c0, z + c0,
+        KS_LAUNCH_ON(aux, "pt_key_kernel", pt_key_kernel, g256, 256, he->g, hs->g, w.kc, w.ncell, w.subbits, m, x + c0, y + c0, z + c0,
                      w.hist, w.keyrank[b]);
         KS_LAUNCH_ON(aux, "key_scan_kernel", key_scan_kernel, w.nblk, BFE_SCAN_BLOCK, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
                      w.counter, b);
@@ -833,7 +962,7 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
 int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,
                         double rotfreq, double* state6, int32_t* nsteps_out, cudaStream_t stream) {
     KeySortWs w;
-    int rc = keysort_ws(he, norbit, false, w);
+    int rc = keysort_ws(he, hs, stream, norbit, false, w);
     if (rc != BFE_OK) return rc;
     if (norbit > he->orbit_rec_cap || !he->orbit_rec) {
         if (he->orbit_rec) { BFE_CUDA(cudaDeviceSynchronize()); BFE_CUDA(cudaFree(he->orbit_rec)); he->orbit_rec = nullptr; he->orbit_rec_cap = 0; }
@@ -856,7 +985,7 @@ int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, d
     const SlFacP facp = bfe_sl_facp(hs);
     const int kt = bfe_kt_begin("leapfrog_sorted_pass", stream);
 
-    KS_LAUNCH("orbit_pack_key_kernel", orbit_pack_key_kernel, g256, 256, he->g, hs->g, w.ncell, w.subbits, norbit,
+    KS_LAUNCH("orbit_pack_key_kernel", orbit_pack_key_kernel, g256, 256, he->g, hs->g, w.kc, w.ncell, w.subbits, norbit,
               (const double*)state6, dt, dt_orbit, rec, w.hist, w.keyrank[0]);
     for (int64_t step0 = 0; step0 < nint - 1; step0 += K) {
         const int64_t left = nint - 1 - step0;
@@ -868,14 +997,14 @@ int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, d
                   (const int*)w.start, (const int*)w.bprefix, w.perm[0]);
 #define LEAP_PERM(L, F) KS_LAUNCH("leapfrog_perm_kernel", (leapfrog_perm_kernel<6, L, F>), glf, 128, he->g, G4, hs->g, A3,     \
                                   (const double*)hs->xi, (const double*)hs->p0, facp, norbit, step0, k,                        \
-                                  rotfreq, (int)(step0 == 0), (int)!last, w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, \
+                                  rotfreq, (int)(step0 == 0), (int)!last, w.kc, w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, \
                                   w.keyrank[0], w.counter + 1)
 #define LEAP_STAGE(L)                                                                                                            \
     do {                                                                                                                          \
         cudaError_t _e = bfe_launch((leapfrog_stage_kernel<6, L>), dim3(glf), dim3(128), (size_t)BFE_STAGE_SMEM, stream, nullptr, 0, \
                                     he->g, (const double2*)G4, hs->g, (const double2*)A3, (const double*)hs->xi,                 \
                                     (const double*)hs->p0, facp, norbit, step0, k, rotfreq, (int)(step0 == 0), (int)!last,       \
-                                    w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, w.keyrank[0], w.counter + 1);         \
+                                    w.kc, w.ncell, w.subbits, (const int*)w.perm[0], rec, w.hist, w.keyrank[0], w.counter + 1);   \
         if (_e != cudaSuccess) { bfe_set_cuda_error(_e, "leapfrog_stage_kernel"); return BFE_ERR_CUDA; }                          \
         bfe_count_launch(1);                                                                                                      \
     } while (0)

@@ -781,9 +781,10 @@ def test_key_subbits_change_relays_workspace(ops):
     E.contract(c * 0.025, s_ * 0.025)
     H.contract(H.accumulate(xh, yh, zh, mh))
     x = np.concatenate([xd, xh]); y = np.concatenate([yd, yh]); z = np.concatenate([zd, zh])
-    keys = ('field_sort_min', 'field_sort_chunk', 'key_subbits', 'orbit_key_subbits', 'orbit_sort_min', 'orbit_resort')
+    keys = ('field_sort_min', 'field_sort_chunk', 'key_subbits', 'orbit_key_subbits', 'key_mode', 'orbit_sort_min', 'orbit_resort')
     saved = {k: ops.get_option(k) for k in keys}
     try:
+        ops.set_option('key_mode', 0)                 # the bit scheme: its key count follows the two options
         ops.set_option('field_sort_min', 0); ops.set_option('orbit_resort', 0)
         ref = ops.field_force_cart(E, H, x, y, z, rotpos=0.3)
         pos0 = np.stack([xd[:20000], yd[:20000], zd[:20000]])
@@ -796,6 +797,7 @@ def test_key_subbits_change_relays_workspace(ops):
             assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=0.3), ref), (sub, osub)
             st, _, _ = ops.leapfrog(E, H, pos0, vel0, 14, 3e-4, rotfreq=-5.0)
             assert torch.equal(st, ref_s), (sub, osub)
+            ops.set_option('key_mode', 3 - ops.get_option('key_mode'))          # alternate with the per-cell spans (points and orbits): another key count again
     finally:
         for k, v in saved.items():
             ops.set_option(k, v)
