@@ -222,8 +222,9 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- the other BASELINE configurations
-FIELD_FLOP_PER_POINT = 2 * 835 + 577 + 142   # executed FP64 flop of one combined-field evaluation at mmax=6 / lmax=6: DFMA x2 + DMUL + DADD,
-                                             # static SASS count of field_rec_kernel<6,6> (fully unrolled; profiles/r02_sass_field_rec_kernel.txt)
+FIELD_FLOP_PER_POINT = 2 * 741 + 409 + 136   # executed FP64 flop of one combined-field evaluation at mmax=6 / lmax=6: DFMA x2 + DMUL + DADD,
+                                             # static SASS count of field_rec_kernel<6,6> (fully unrolled; profiles/r02_sass_field_rec_kernel.txt;
+                                             # 2389 before the polynomial SL blocks: fewer flop for the same result lowers this fraction)
 FIELD_BYTES_PER_POINT = 24 + 64              # x,y,z in + the 8-tuple out
 
 
