@@ -369,6 +369,7 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "sort_stable")) { g_bfe_sort_stable = value; return BFE_OK; }
     if (!strcmp(name, "key_subbits")) { g_bfe_key_subbits = value; return BFE_OK; }
     if (!strcmp(name, "key_mode")) { g_bfe_key_mode = value & 3; return BFE_OK; }
+    if (!strcmp(name, "field_eval_static")) { g_bfe_field_eval_static = value ? 1 : 0; return BFE_OK; }
     if (!strcmp(name, "orbit_key_subbits")) { g_bfe_orbit_key_subbits = value; return BFE_OK; }
     if (!strcmp(name, "orbit_resort")) { g_bfe_orbit_resort = value; return BFE_OK; }
     if (!strcmp(name, "orbit_sort_min")) { g_bfe_orbit_sort_min = value; return BFE_OK; }
@@ -406,6 +407,7 @@ extern "C" int bfe_get_option(const char* name) {
     if (!strcmp(name, "sort_stable")) return g_bfe_sort_stable;
     if (!strcmp(name, "key_subbits")) return g_bfe_key_subbits;
     if (!strcmp(name, "key_mode")) return g_bfe_key_mode;
+    if (!strcmp(name, "field_eval_static")) return g_bfe_field_eval_static;
     if (!strcmp(name, "keycell_nkeys")) return g_bfe_keycell_nkeys_last;
     if (!strcmp(name, "orbit_key_subbits")) return g_bfe_orbit_key_subbits;
     if (!strcmp(name, "orbit_resort")) return g_bfe_orbit_resort;

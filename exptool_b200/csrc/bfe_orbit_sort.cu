@@ -188,18 +188,36 @@ pt_key_kernel(EofGeom ge, SlGeom gs, const int4* __restrict__ kc, int ncell, int
               const double* __restrict__ y, const double* __restrict__ z, int* __restrict__ hist, int2* __restrict__ keyrank) {
     bfe_pdl_wait();
     bfe_pdl_trigger();
-    const int64_t nround = (n + 31) & ~(int64_t)31;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
-        const bool on = i < n;
-        int key = 0;
-        // points arrive in the caller's order: the 32 keys of a warp differ, so one atomic per lane (no match / aggregation)
-        if (on) {
-            key = bfe_point_key(ge, gs, kc, ncell, subbits, __ldg(x + i), __ldg(y + i), __ldg(z + i));
-            keyrank[i] = make_int2(key, atomicAdd(hist + key, 1));
+    // points arrive in the caller's order: the 32 keys of a warp differ, so one atomic per lane (no match / aggregation).  Four
+    // points per thread per pass: the four rank claims (atomics WITH return, ~1 us each) are in flight together
+    constexpr int U = 4;
+    for (int64_t base = (int64_t)blockIdx.x * (blockDim.x * U) + threadIdx.x; base < n; base += (int64_t)gridDim.x * (blockDim.x * U)) {
+        double px[U], py[U], pz[U];
+        int key[U], rank[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            const bool on = i < n;
+            px[u] = on ? __ldg(x + i) : 1.0; py[u] = on ? __ldg(y + i) : 0.0; pz[u] = on ? __ldg(z + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) key[u] = bfe_point_key(ge, gs, kc, ncell, subbits, px[u], py[u], pz[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) rank[u] = (base + (int64_t)u * blockDim.x < n) ? atomicAdd(hist + key[u], 1) : 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            if (i < n) keyrank[i] = make_int2(key[u], rank[u]);
         }
     }
 }
 
+// (Tried and removed: the rank claims aggregated per CTA in a shared-memory hash table, one global atomic per distinct key of a
+// 2048-point pass, against the ~1 % of a chunk's points that share its hottest key.  pt_key 205 -> 176 us per 4 x 10^6 points
+// standalone, C3 20.8 -> 21.3 ms in the pipeline: the kernel is bound by the RATE of random L2 requests -- per point one table
+// look-up, one atomic -- not by same-address serialisation; ncu stall samples: 20 % on the coordinate loads, 34 % on the
+// per-cell table look-up, 31 % on the atomic's return.  Staging the per-cell table in shared memory, 128 kB, one 1024-thread CTA per SM,
+// did not change the kernel's time either, 207 vs 205 us: what is left is the rate of the atomics with return, ~21 G/s.)
 // start[k] = exclusive prefix of hist inside its 1024-bin block, hist cleared; the last CTA turns the block totals into
 // block prefixes.  Position of an item = bprefix[key >> 10] + start[key] + rank.
 __global__ void __launch_bounds__(BFE_SCAN_BLOCK)
@@ -279,11 +297,29 @@ rec_scatter_kernel(int64_t n, const int2* __restrict__ keyrank, const int* __res
                    double* __restrict__ rec4, int* __restrict__ inv) {
     bfe_pdl_wait();
     bfe_pdl_trigger();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int2 kr = __ldcs(keyrank + i);
-        const int pos = __ldg(bprefix + (kr.x >> 10)) + __ldg(start + kr.x) + kr.y;
-        bfe_st256(rec4 + 4 * (size_t)pos, __ldg(x + i), __ldg(y + i), __ldg(z + i), __longlong_as_double((long long)i));
-        inv[i] = pos;
+    // two points per thread per pass: their dependent position look-ups (bprefix, start) and coordinate loads overlap
+    constexpr int U = 2;
+    for (int64_t base = (int64_t)blockIdx.x * (blockDim.x * U) + threadIdx.x; base < n; base += (int64_t)gridDim.x * (blockDim.x * U)) {
+        int2 kr[U];
+        double px[U], py[U], pz[U];
+        int pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            const bool on = i < n;
+            kr[u] = on ? __ldcs(keyrank + i) : make_int2(0, 0);
+            px[u] = on ? __ldg(x + i) : 0.0; py[u] = on ? __ldg(y + i) : 0.0; pz[u] = on ? __ldg(z + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) pos[u] = __ldg(bprefix + (kr[u].x >> 10)) + __ldg(start + kr[u].x) + kr[u].y;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            if (i < n) {
+                bfe_st256(rec4 + 4 * (size_t)pos[u], px[u], py[u], pz[u], __longlong_as_double((long long)i));
+                inv[i] = pos[u];
+            }
+        }
     }
 }
 
@@ -292,18 +328,29 @@ __global__ void __launch_bounds__(128, BFE_PERM_MINB)
 field_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
                  const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
                  int64_t n, const double* __restrict__ rec4, double crot, double srot, double* __restrict__ slot8,
-                 unsigned int* __restrict__ ticket) {
+                 unsigned int* __restrict__ ticket, int static_grid) {
     __shared__ unsigned int s_tile;
     bfe_pdl_wait();
     bfe_pdl_trigger();
     const unsigned int ntile = (unsigned int)((n + 127) >> 7);
     const unsigned int nticket = bfe_ticket_count(ntile);
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();
-        if (s_tile >= nticket) break;
-        const TileTicket tk = bfe_ticket_tiles(s_tile, ntile);
+        TileTicket tk;
+        if (static_grid) {
+            // one CTA per four consecutive tiles, no persistent loop: SM slots come free every few tens of microseconds, so the
+            // (high-priority) support kernels of the other stream get onto the SMs WHILE this kernel runs -- a persistent grid
+            // at 3 x 128 x 168 registers fills the register file until the chunk is done and serialises the two streams
+            const unsigned int per = (unsigned int)static_grid;            // tiles per CTA: 4, or 1 for small sets
+            tk.first = per * blockIdx.x;
+            tk.count = (tk.first + per <= ntile) ? per : (ntile > tk.first ? ntile - tk.first : 0u);
+            if (tk.count == 0u) break;
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+            __syncthreads();
+            if (s_tile >= nticket) break;
+            tk = bfe_ticket_tiles(s_tile, ntile);
+        }
         int64_t pos = (int64_t)tk.first * 128 + threadIdx.x;
         double px = 0.0, py = 0.0, pz = 0.0, id_ = 0.0;
         if (pos < n) bfe_ld256_nc(rec4 + 4 * (size_t)pos, px, py, pz, id_);
@@ -320,6 +367,7 @@ field_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void*
             }
             pos = npos; px = nx; py = ny; pz = nz;
         }
+        if (static_grid) break;
     }
 }
 
@@ -460,14 +508,26 @@ field_gather_kernel(int64_t n, int64_t ntot, const int* __restrict__ inv, const 
                     double* __restrict__ out8) {
     bfe_pdl_wait();
     bfe_pdl_trigger();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const char* s = reinterpret_cast<const char*>(slot8 + 8 * (size_t)__ldg(inv + i));
-        double a0, a1, a2, a3, b0, b1, b2, b3;
-        bfe_ld256_nc(s, a0, a1, a2, a3);
-        bfe_ld256_nc(s + 32, b0, b1, b2, b3);
-        // slot = {disc: fx, fy, fz, p | halo: fx, fy, fz, p}; output rows fxd, fxh, fyd, fyh, fzd, fzh, pd, ph
-        out8[i] = a0; out8[2 * ntot + i] = a1; out8[4 * ntot + i] = a2; out8[6 * ntot + i] = a3;
-        out8[ntot + i] = b0; out8[3 * ntot + i] = b1; out8[5 * ntot + i] = b2; out8[7 * ntot + i] = b3;
+    // two points per thread per pass: four random 32-byte slot reads in flight
+    constexpr int U = 2;
+    for (int64_t base = (int64_t)blockIdx.x * (blockDim.x * U) + threadIdx.x; base < n; base += (int64_t)gridDim.x * (blockDim.x * U)) {
+        double a[U][4], b[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            const char* s = reinterpret_cast<const char*>(slot8 + 8 * (size_t)(i < n ? __ldg(inv + i) : 0));
+            bfe_ld256_nc(s, a[u][0], a[u][1], a[u][2], a[u][3]);
+            bfe_ld256_nc(s + 32, b[u][0], b[u][1], b[u][2], b[u][3]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x;
+            if (i < n) {
+                // slot = {disc: fx, fy, fz, p | halo: fx, fy, fz, p}; output rows fxd, fxh, fyd, fyh, fzd, fzh, pd, ph
+                out8[i] = a[u][0]; out8[2 * ntot + i] = a[u][1]; out8[4 * ntot + i] = a[u][2]; out8[6 * ntot + i] = a[u][3];
+                out8[ntot + i] = b[u][0]; out8[3 * ntot + i] = b[u][1]; out8[5 * ntot + i] = b[u][2]; out8[7 * ntot + i] = b[u][3];
+            }
+        }
     }
 }
 
@@ -688,6 +748,9 @@ int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between 
 // (disc-like batches, one sort per K steps): 4.
 int g_bfe_key_mode = 1;                 // option "key_mode": bit 0 = points, bit 1 = orbits ordered by per-cell interval spans (bfe_point_key);
                                         // otherwise (cell << bits) | (interval & mask).  Orbits: measured 2.5 % slower with the spans (C4)
+int g_bfe_field_eval_static = 1;        // option "field_eval_static": one evaluation CTA per four tiles (1) instead of a persistent grid with tickets (0).
+                                        // C3 21.75 -> 20.8 ms: the support stream's CTAs get SM slots while the evaluation runs.  (Evaluation limited
+                                        // to 2 persistent CTAs per SM so that a third of the register file stays free: 27.1 ms -- it needs its warps.)
 int g_bfe_keycell_nkeys_last = 0;       // read-only option "keycell_nkeys": keys of the last per-cell span table built
 int g_bfe_key_subbits = 7;
 int g_bfe_orbit_key_subbits = BFE_KEY_SUBBITS;
@@ -841,7 +904,10 @@ void bfe_field_pipe_destroy(void* p_) {
 static int field_pipe(bfe_eof* he, FieldPipe*& out) {
     if (!he->field_pipe) {
         FieldPipe* p = new FieldPipe();
-        cudaError_t e = cudaStreamCreateWithFlags(&p->aux, cudaStreamNonBlocking);
+        // the support stream has the highest priority: its short CTAs take the SM slots the evaluation kernel frees first
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        cudaError_t e = cudaStreamCreateWithPriority(&p->aux, cudaStreamNonBlocking, prio_hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming);
         for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
@@ -936,9 +1002,16 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
             else                 { if (cyl) FIELD_STAGE(6, true); else FIELD_STAGE(6, false); }
 #undef FIELD_STAGE
         } else {
-#define FIELD_REC(L, C, F) KS_LAUNCH("field_rec_kernel", (field_rec_kernel<6, L, C, F>), geval, 128, he->g, G4, hs->g, A3,      \
+        // static mode: four tiles per CTA when that still gives >= 8 CTAs per resident slot, else one
+        const int64_t ntile_h = (m + 127) / 128;
+        // only for the 2^22-point chunks of large sets: at 2^20-point (L2-resident) chunks the persistent grid with tickets is faster
+        // (n = 4 x 10^6: 243 vs 261 us per 10^6; n = 10^6: 0.281 vs 0.306 ms)
+        const bool st_on = g_bfe_field_eval_static && chunk >= ((int64_t)1 << 22);
+        const int st_per = st_on ? ((ntile_h >= 8 * 4 * (int64_t)he->num_sms * BFE_PERM_MINB) ? 4 : 1) : 0;
+        const int st_grid = st_per ? (int)((ntile_h + st_per - 1) / st_per) : 0;
+#define FIELD_REC(L, C, F) KS_LAUNCH("field_rec_kernel", (field_rec_kernel<6, L, C, F>), (st_grid ? st_grid : geval), 128, he->g, G4, hs->g, A3, \
                                      (const double*)hs->xi, (const double*)hs->p0, facp, m, (const double*)w.rec4[b], crot, srot, \
-                                     w.slot8[b], w.counter + 1 + b)
+                                     w.slot8[b], w.counter + 1 + b, st_per)
 #define FIELD_REC2(L, C) do { if (f32) FIELD_REC(L, C, true); else FIELD_REC(L, C, false); } while (0)
         if (hs->g.lmax == 4) { if (cyl) FIELD_REC2(4, true); else FIELD_REC2(4, false); }
         else                 { if (cyl) FIELD_REC2(6, true); else FIELD_REC2(6, false); }
