@@ -370,6 +370,8 @@ extern "C" int bfe_set_option(const char* name, int value) {
     if (!strcmp(name, "key_subbits")) { g_bfe_key_subbits = value; return BFE_OK; }
     if (!strcmp(name, "key_mode")) { g_bfe_key_mode = value & 3; return BFE_OK; }
     if (!strcmp(name, "field_eval_static")) { g_bfe_field_eval_static = value ? 1 : 0; return BFE_OK; }
+    if (!strcmp(name, "field_gather_stream")) { g_bfe_field_gather_stream = value ? 1 : 0; return BFE_OK; }
+    if (!strcmp(name, "field_support_slim")) { g_bfe_field_support_slim = value < 0 ? 0 : (value > 4 ? 4 : value); return BFE_OK; }
     if (!strcmp(name, "orbit_key_subbits")) { g_bfe_orbit_key_subbits = value; return BFE_OK; }
     if (!strcmp(name, "orbit_resort")) { g_bfe_orbit_resort = value; return BFE_OK; }
     if (!strcmp(name, "orbit_sort_min")) { g_bfe_orbit_sort_min = value; return BFE_OK; }
@@ -408,6 +410,8 @@ extern "C" int bfe_get_option(const char* name) {
     if (!strcmp(name, "key_subbits")) return g_bfe_key_subbits;
     if (!strcmp(name, "key_mode")) return g_bfe_key_mode;
     if (!strcmp(name, "field_eval_static")) return g_bfe_field_eval_static;
+    if (!strcmp(name, "field_gather_stream")) return g_bfe_field_gather_stream;
+    if (!strcmp(name, "field_support_slim")) return g_bfe_field_support_slim;
     if (!strcmp(name, "keycell_nkeys")) return g_bfe_keycell_nkeys_last;
     if (!strcmp(name, "orbit_key_subbits")) return g_bfe_orbit_key_subbits;
     if (!strcmp(name, "orbit_resort")) return g_bfe_orbit_resort;

@@ -166,6 +166,8 @@ extern int g_bfe_orbit_key_subbits;                        // option "orbit_key_
 extern int g_bfe_key_mode;                                 // option "key_mode"
 extern int g_bfe_keycell_nkeys_last;
 extern int g_bfe_field_eval_static;
+extern int g_bfe_field_support_slim;
+extern int g_bfe_field_gather_stream;
 int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, const double* y, const double* z,
                            double crot, double srot, double* out8, bool cyl, cudaStream_t stream);
 int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, double dt, const double* dt_orbit,

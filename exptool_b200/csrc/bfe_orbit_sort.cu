@@ -220,59 +220,68 @@ pt_key_kernel(EofGeom ge, SlGeom gs, const int4* __restrict__ kc, int ncell, int
 // did not change the kernel's time either, 207 vs 205 us: what is left is the rate of the atomics with return, ~21 G/s.)
 // start[k] = exclusive prefix of hist inside its 1024-bin block, hist cleared; the last CTA turns the block totals into
 // block prefixes.  Position of an item = bprefix[key >> 10] + start[key] + rank.
-__global__ void __launch_bounds__(BFE_SCAN_BLOCK)
+// 256 threads x 4 keys per block of 1024 keys: a block needs 256 x ~24 registers, so it fits on an SM beside the three resident
+// CTAs of the evaluation kernel (the point path runs the support kernels on a second stream WHILE the evaluation runs).
+__global__ void __launch_bounds__(256)
 key_scan_kernel(int nkeys, int* __restrict__ hist, int* __restrict__ start, int* __restrict__ btot,
                 int* __restrict__ bprefix, unsigned int* __restrict__ counter, int ticket_slot) {
-    __shared__ int s_w[32];
+    __shared__ int s_w[8];
     __shared__ bool s_last;
     bfe_pdl_wait();
     bfe_pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x == 0) counter[1 + ticket_slot] = 0u;      // tile ticket of the evaluation kernel that follows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = blockIdx.x * BFE_SCAN_BLOCK + tid;
-    int v = 0;
-    if (k < nkeys) { v = __ldcg(hist + k); hist[k] = 0; }
-    int incl = v;
+    const int k0 = blockIdx.x * BFE_SCAN_BLOCK + 4 * tid;                          // nkeys_cap is a multiple of 4: hist / start are 16-byte aligned
+    int4 v = make_int4(0, 0, 0, 0);
+    if (k0 + 3 < nkeys) {
+        v = __ldcg(reinterpret_cast<const int4*>(hist + k0));
+        *reinterpret_cast<int4*>(hist + k0) = make_int4(0, 0, 0, 0);
+    } else {
+        if (k0 < nkeys) { v.x = __ldcg(hist + k0); hist[k0] = 0; }
+        if (k0 + 1 < nkeys) { v.y = __ldcg(hist + k0 + 1); hist[k0 + 1] = 0; }
+        if (k0 + 2 < nkeys) { v.z = __ldcg(hist + k0 + 2); hist[k0 + 2] = 0; }
+    }
+    const int sum = v.x + v.y + v.z + v.w;
+    int incl = sum;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += u; }
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        int w = s_w[lane];
+    int wpre = 0, tot = 0;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += u; }
-        s_w[lane] = w;
+    for (int q = 0; q < 8; ++q) { const int t = s_w[q]; if (q < warp) wpre += t; tot += t; }
+    const int excl = incl - sum + wpre;
+    const int4 o = make_int4(excl, excl + v.x, excl + v.x + v.y, excl + v.x + v.y + v.z);
+    if (k0 + 3 < nkeys) *reinterpret_cast<int4*>(start + k0) = o;
+    else {
+        if (k0 < nkeys) start[k0] = o.x;
+        if (k0 + 1 < nkeys) start[k0 + 1] = o.y;
+        if (k0 + 2 < nkeys) start[k0 + 2] = o.z;
     }
-    __syncthreads();
-    const int excl = incl - v + (warp > 0 ? s_w[warp - 1] : 0);
-    if (k < nkeys) start[k] = excl;
-    if (tid == BFE_SCAN_BLOCK - 1) btot[blockIdx.x] = excl + v;
+    if (tid == 0) btot[blockIdx.x] = tot;
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // up to 2048 blocks (nkeys <= 2^21): two totals per thread
+    // up to 2048 blocks (nkeys <= 2^21): eight totals per thread
     const int nb = gridDim.x;
-    const int b0 = 2 * tid, b1 = 2 * tid + 1;
-    const int t0 = b0 < nb ? __ldcg(btot + b0) : 0, t1 = b1 < nb ? __ldcg(btot + b1) : 0;
-    int inc2 = t0 + t1;
+    int t[8], s8 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int bq = 8 * tid + q; t[q] = bq < nb ? __ldcg(btot + bq) : 0; s8 += t[q]; }
+    int inc2 = s8;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, off); if (lane >= off) inc2 += u; }
     __syncthreads();
     if (lane == 31) s_w[warp] = inc2;
     __syncthreads();
-    if (warp == 0) {
-        int w = s_w[lane];
+    int wp2 = 0;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += u; }
-        s_w[lane] = w;
-    }
-    __syncthreads();
-    const int ex2 = inc2 - (t0 + t1) + (warp > 0 ? s_w[warp - 1] : 0);
-    if (b0 < nb) bprefix[b0] = ex2;
-    if (b1 < nb) bprefix[b1] = ex2 + t0;
+    for (int q = 0; q < 8; ++q) if (q < warp) wp2 += s_w[q];
+    int run = inc2 - s8 + wp2;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int bq = 8 * tid + q; if (bq < nb) bprefix[bq] = run; run += t[q]; }
     if (tid == 0) *counter = 0u;
 }
 
@@ -323,8 +332,20 @@ rec_scatter_kernel(int64_t n, const int2* __restrict__ keyrank, const int* __res
     }
 }
 
+// The point-path evaluation kernel is capped at 144 registers (no spills; under __launch_bounds__(128, 3) ptxas took 168 of the 170 it
+// was allowed): 3 CTAs x 128 threads x 144 registers leave 10 240 registers of an SM free, which is one CTA of each support kernel
+// (key 128 x 48, scan 256 x 24, scatter 256 x 32, gather 128 x 60) -- so the support stream runs WHILE the evaluation runs instead of
+// between evaluation kernels.  BFE_EVAL_MAXNREG=0 restores the launch bounds.
+#ifndef BFE_EVAL_MAXNREG
+#define BFE_EVAL_MAXNREG 144
+#endif
+#if BFE_EVAL_MAXNREG > 0
+#define BFE_FIELD_REC_QUAL __maxnreg__(BFE_EVAL_MAXNREG)
+#else
+#define BFE_FIELD_REC_QUAL __launch_bounds__(128, BFE_PERM_MINB)
+#endif
 template <int MCAP, int LCAP, bool CYL, bool F32>
-__global__ void __launch_bounds__(128, BFE_PERM_MINB)
+__global__ void BFE_FIELD_REC_QUAL
 field_rec_kernel(EofGeom ge, const void* __restrict__ G4, SlGeom gs, const void* __restrict__ A3,
                  const double* __restrict__ xi, const double* __restrict__ p0tab, const SlFacP fac,
                  int64_t n, const double* __restrict__ rec4, double crot, double srot, double* __restrict__ slot8,
@@ -748,6 +769,8 @@ int g_bfe_orbit_resort = 3;             // option "orbit_resort": steps between 
 // (disc-like batches, one sort per K steps): 4.
 int g_bfe_key_mode = 1;                 // option "key_mode": bit 0 = points, bit 1 = orbits ordered by per-cell interval spans (bfe_point_key);
                                         // otherwise (cell << bits) | (interval & mask).  Orbits: measured 2.5 % slower with the spans (C4)
+int g_bfe_field_gather_stream = 0;      // option "field_gather_stream": gather kernel of the point path on its own support stream
+int g_bfe_field_support_slim = 1;       // option "field_support_slim": support kernels of the point path as one small CTA per SM beside the evaluation
 int g_bfe_field_eval_static = 1;        // option "field_eval_static": one evaluation CTA per four tiles (1) instead of a persistent grid with tickets (0).
                                         // C3 21.75 -> 20.8 ms: the support stream's CTAs get SM slots while the evaluation runs.  (Evaluation limited
                                         // to 2 persistent CTAs per SM so that a third of the register file stays free: 27.1 ms -- it needs its warps.)
@@ -890,14 +913,14 @@ static int keysort_ws(bfe_eof* he, bfe_sl* hs, cudaStream_t stream, int64_t cap_
 }
 
 // aux stream + events of the two-stream point pipeline (lazily made, owned by the EOF handle)
-struct FieldPipe { cudaStream_t aux; cudaEvent_t ev_in, ev_k[2], ev_e[2], ev_out; };
+struct FieldPipe { cudaStream_t aux, aux2; cudaEvent_t ev_in, ev_k[2], ev_e[2], ev_g[2], ev_out, ev_out2; };
 
 void bfe_field_pipe_destroy(void* p_) {
     FieldPipe* p = (FieldPipe*)p_;
     if (!p) return;
-    cudaEventDestroy(p->ev_in); cudaEventDestroy(p->ev_out);
-    for (int k = 0; k < 2; ++k) { cudaEventDestroy(p->ev_k[k]); cudaEventDestroy(p->ev_e[k]); }
-    cudaStreamDestroy(p->aux);
+    cudaEventDestroy(p->ev_in); cudaEventDestroy(p->ev_out); cudaEventDestroy(p->ev_out2);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(p->ev_k[k]); cudaEventDestroy(p->ev_e[k]); cudaEventDestroy(p->ev_g[k]); }
+    cudaStreamDestroy(p->aux); cudaStreamDestroy(p->aux2);
     delete p;
 }
 
@@ -908,11 +931,14 @@ static int field_pipe(bfe_eof* he, FieldPipe*& out) {
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         cudaError_t e = cudaStreamCreateWithPriority(&p->aux, cudaStreamNonBlocking, prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->aux2, cudaStreamNonBlocking, prio_hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out2, cudaEventDisableTiming);
         for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
             e = cudaEventCreateWithFlags(&p->ev_k[k], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_e[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_g[k], cudaEventDisableTiming);
         }
         if (e != cudaSuccess) { bfe_set_cuda_error(e, "field_pipe"); delete p; return BFE_ERR_CUDA; }
         he->field_pipe = p;
@@ -964,16 +990,27 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
     const SlFacP facp = bfe_sl_facp(hs);
     const int kt = bfe_kt_begin("field_sorted_pass", stream);
     cudaStream_t aux = fp->aux;
+    // option field_gather_stream: the gather of chunk c-1 on its own stream, beside key + scan + scatter of chunk c+1
+    const bool gsep = g_bfe_field_gather_stream != 0;
+    cudaStream_t gst = gsep ? fp->aux2 : fp->aux;
     BFE_CUDA(cudaEventRecord(fp->ev_in, stream));
     BFE_CUDA(cudaStreamWaitEvent(aux, fp->ev_in, 0));
     const int64_t nchunk = (n + chunk - 1) / chunk;
     auto sort_chunk = [&](int64_t c) -> int {
         const int64_t c0 = c * chunk, m = (n - c0) < chunk ? (n - c0) : chunk;
         const int b = (int)(c & 1);
-        const int g256 = grid_cap(m, 256, he->num_sms * 4);
-        KS_LAUNCH_ON(aux, "pt_key_kernel", pt_key_kernel, g256, 256, he->g, hs->g, w.kc, w.ncell, w.subbits, m, x + c0, y + c0, z + c0,
+        // the buffers of chunk c (keys = result slots, permutation) are those of chunk c-2: its gather (other support stream) must be done
+        if (gsep && c >= 2) BFE_CUDA(cudaStreamWaitEvent(aux, fp->ev_g[b], 0));
+        // slim support grids (option field_support_slim): one small CTA per SM, sized to fit beside the evaluation kernel's three
+        // slim only when the set has >= 3 chunks: with one or two there is nothing to hide the slim kernels behind
+        // (2 x 10^6 disc points: 246 us per 10^6 slim, 215 with full-size grids)
+        const bool slim = g_bfe_field_support_slim != 0 && nchunk >= 3;
+        const int sc = g_bfe_field_support_slim > 1 ? g_bfe_field_support_slim : 1;      // support CTAs per SM in slim mode
+        const int g256 = slim ? grid_cap(m, 256, he->num_sms * sc) : grid_cap(m, 256, he->num_sms * 4);
+        const int gkey = slim ? grid_cap(m, 128, he->num_sms * sc) : g256, bkey = slim ? 128 : 256;
+        KS_LAUNCH_ON(aux, "pt_key_kernel", pt_key_kernel, gkey, bkey, he->g, hs->g, w.kc, w.ncell, w.subbits, m, x + c0, y + c0, z + c0,
                      w.hist, w.keyrank[b]);
-        KS_LAUNCH_ON(aux, "key_scan_kernel", key_scan_kernel, w.nblk, BFE_SCAN_BLOCK, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
+        KS_LAUNCH_ON(aux, "key_scan_kernel", key_scan_kernel, w.nblk, 256, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
                      w.counter, b);
         KS_LAUNCH_ON(aux, "rec_scatter_kernel", rec_scatter_kernel, g256, 256, m, (const int2*)w.keyrank[b], (const int*)w.start,
                      (const int*)w.bprefix, x + c0, y + c0, z + c0, w.rec4[b], w.perm[b]);
@@ -1006,7 +1043,7 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
         const int64_t ntile_h = (m + 127) / 128;
         // only for the 2^22-point chunks of large sets: at 2^20-point (L2-resident) chunks the persistent grid with tickets is faster
         // (n = 4 x 10^6: 243 vs 261 us per 10^6; n = 10^6: 0.281 vs 0.306 ms)
-        const bool st_on = g_bfe_field_eval_static && chunk >= ((int64_t)1 << 22);
+        const bool st_on = g_bfe_field_eval_static && !(g_bfe_field_support_slim != 0 && nchunk >= 3) && chunk >= ((int64_t)1 << 22);
         const int st_per = st_on ? ((ntile_h >= 8 * 4 * (int64_t)he->num_sms * BFE_PERM_MINB) ? 4 : 1) : 0;
         const int st_grid = st_per ? (int)((ntile_h + st_per - 1) / st_per) : 0;
 #define FIELD_REC(L, C, F) KS_LAUNCH("field_rec_kernel", (field_rec_kernel<6, L, C, F>), (st_grid ? st_grid : geval), 128, he->g, G4, hs->g, A3, \
@@ -1019,13 +1056,20 @@ int bfe_field_force_sorted(bfe_eof* he, bfe_sl* hs, int64_t n, const double* x, 
 #undef FIELD_REC
         }
         BFE_CUDA(cudaEventRecord(fp->ev_e[b], stream));
-        BFE_CUDA(cudaStreamWaitEvent(aux, fp->ev_e[b], 0));
-        const int g256 = grid_cap(m, 256, he->num_sms * 4);
-        KS_LAUNCH_ON(aux, "field_gather_kernel", field_gather_kernel, g256, 256, m, n, (const int*)w.perm[b],
+        BFE_CUDA(cudaStreamWaitEvent(gst, fp->ev_e[b], 0));
+        const bool slim = g_bfe_field_support_slim != 0 && nchunk >= 3;
+        const int sc = g_bfe_field_support_slim > 1 ? g_bfe_field_support_slim : 1;
+        const int ggat = slim ? grid_cap(m, 128, he->num_sms * sc) : grid_cap(m, 256, he->num_sms * 4);
+        KS_LAUNCH_ON(gst, "field_gather_kernel", field_gather_kernel, ggat, (slim ? 128 : 256), m, n, (const int*)w.perm[b],
                      (const double*)w.slot8[b], out8 + c0);
+        if (gsep) BFE_CUDA(cudaEventRecord(fp->ev_g[b], gst));
     }
     BFE_CUDA(cudaEventRecord(fp->ev_out, aux));
     BFE_CUDA(cudaStreamWaitEvent(stream, fp->ev_out, 0));
+    if (gsep) {
+        BFE_CUDA(cudaEventRecord(fp->ev_out2, gst));
+        BFE_CUDA(cudaStreamWaitEvent(stream, fp->ev_out2, 0));
+    }
     bfe_kt_end(kt, stream);
     return BFE_OK;
 }
@@ -1064,7 +1108,7 @@ int bfe_leapfrog_sorted(bfe_eof* he, bfe_sl* hs, int64_t norbit, int64_t nint, d
         const int64_t left = nint - 1 - step0;
         const int k = (int)(left < K ? left : K);
         const int last = (step0 + k >= nint - 1) ? 1 : 0;
-        KS_LAUNCH("key_scan_kernel", key_scan_kernel, w.nblk, BFE_SCAN_BLOCK, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
+        KS_LAUNCH("key_scan_kernel", key_scan_kernel, w.nblk, 256, w.nkeys, w.hist, w.start, w.btot, w.bprefix,
                   w.counter, 0);
         KS_LAUNCH("perm_scatter_kernel", perm_scatter_kernel, g256, 256, norbit, (const int2*)w.keyrank[0],
                   (const int*)w.start, (const int*)w.bprefix, w.perm[0]);

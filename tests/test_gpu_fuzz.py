@@ -73,7 +73,7 @@ def test_fuzz_key_ordered_paths(ops, lmax):
     c, s_ = E.accumulate(xd, yd, zd, md)
     E.contract(c * 0.025, s_ * 0.025)
     H.contract(H.accumulate(xh, yh, zh, mh))
-    keys = ('field_sort_min', 'field_sort_chunk', 'key_subbits', 'orbit_key_subbits', 'key_mode', 'field_eval_static', 'orbit_sort_min', 'orbit_resort', 'pdl')
+    keys = ('field_sort_min', 'field_sort_chunk', 'key_subbits', 'orbit_key_subbits', 'key_mode', 'field_eval_static', 'field_support_slim', 'field_gather_stream', 'orbit_sort_min', 'orbit_resort', 'pdl')
     saved = {k: ops.get_option(k) for k in keys}
     try:
         for it in range(ITERS or 20):
@@ -94,7 +94,8 @@ def test_fuzz_key_ordered_paths(ops, lmax):
             ops.set_option('field_sort_chunk', int(rng.choice([1000, 65536, 1 << 20, 1 << 22])))
             ops.set_option('key_subbits', int(rng.integers(0, 9))); ops.set_option('orbit_key_subbits', int(rng.integers(0, 9)))
             ops.set_option('orbit_resort', int(rng.integers(1, 6))); ops.set_option('pdl', int(rng.integers(0, 2)))
-            ops.set_option('key_mode', int(rng.integers(0, 4))); ops.set_option('field_eval_static', int(rng.integers(0, 2)))
+            ops.set_option('key_mode', int(rng.integers(0, 4))); ops.set_option('field_eval_static', int(rng.integers(0, 2))); ops.set_option('field_support_slim', int(rng.integers(0, 3)))
+            ops.set_option('field_gather_stream', int(rng.integers(0, 2)))
             assert torch.equal(ops.field_force_cart(E, H, x, y, z, rotpos=rot), ref_c), (it, n)
             assert torch.equal(ops.field_force_cyl(E, H, x, y, z, rotpos=rot), ref_y), (it, n)
             st, _, ns = ops.leapfrog(E, H, pos0, vel0, nint, dts, rotfreq=rf)
